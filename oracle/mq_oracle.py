@@ -1,0 +1,472 @@
+"""CPU oracle for the mannequin2 training hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a fresh NumPy restatement of the algorithms on the hot path of
+squirrelinhell/mannequin2.  It is the *checker*: only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py`` may import it.  Nothing under
+``mannequin2_b200/`` imports it and the product path never falls back to it.
+
+Parity status (see DESIGN.md section "Oracle"):
+  * pinned against the reference's own goldens (tests/adam.out, basicnet.out,
+    graph.out, reshape.out, trajectory.out, running_mean.py, running_norm.py)
+    and against outputs of the *real* reference imported from /root/reference
+    in the build container (tests/golden/make_golden.py -> tests/golden/*.npz);
+  * ``gauss_logprob`` / ``dkl_uninormal`` gradients: the reference delegates
+    the derivative to the third-party ``autograd`` package (unpinned, absent).
+    The forward expressions are pinned by running the reference code with a
+    complex-step stand-in for ``autograd`` (make_golden.py); the closed-form
+    derivatives are additionally checked by finite differences;
+  * ``gauss_entropy`` has no reference code at all: "parity unpinned".
+
+All citations are relative to /root/reference.
+"""
+
+import numpy as np
+
+ACT_NONE, ACT_TANH, ACT_LRELU = 0, 1, 2
+
+
+# --------------------------------------------------------------------------
+# Flat parameter layout (mannequin/basicnet.py:13-23,35-51)
+# --------------------------------------------------------------------------
+
+def mlp_spec(n_in, widths, acts, leak=0.1):
+    """Describe a stack of Affine(+activation) layers.
+
+    Flat layout is DFS post-order of Params nodes: W1 (in x out, row-major),
+    b1, W2, b2, ...   (basicnet.py:303-311,319-320)
+    """
+    layers, pos, k = [], 0, int(n_in)
+    for n, a in zip(widths, acts):
+        n = int(n)
+        layers.append(dict(n_in=k, n_out=n, act=int(a), leak=float(leak),
+                           w_off=pos, b_off=pos + k * n))
+        pos += k * n + n
+        k = n
+    return dict(layers=layers, n_params=pos, n_in=int(n_in), n_out=k)
+
+
+def normed_columns(rs, n_in, n_out, scale=1.0):
+    """Column-normalised Gaussian init (basicnet.py:265-267,300-301)."""
+    m = rs.randn(n_in, n_out).astype(np.float32)
+    m = m / np.sqrt(np.sum(np.square(m), axis=0))
+    return (m * np.float32(scale)).astype(np.float32)
+
+
+def mlp_init(spec, rs, head_scale=1.0):
+    """theta in the reference's layout; biases zero (basicnet.py:310-311)."""
+    theta = np.zeros(spec["n_params"], dtype=np.float32)
+    last = len(spec["layers"]) - 1
+    for i, L in enumerate(spec["layers"]):
+        w = normed_columns(rs, L["n_in"], L["n_out"],
+                           head_scale if i == last else 1.0)
+        theta[L["w_off"]:L["b_off"]] = w.reshape(-1)
+    return theta
+
+
+def _wb(theta, L):
+    w = theta[L["w_off"]:L["b_off"]].reshape(L["n_in"], L["n_out"])
+    b = theta[L["b_off"]:L["b_off"] + L["n_out"]]
+    return w, b
+
+
+# --------------------------------------------------------------------------
+# MLP forward / backward (basicnet.py:192-259, backprop.py:11-60)
+# --------------------------------------------------------------------------
+
+def mlp_forward(theta, spec, x, dtype=np.float64):
+    """Returns the list of post-activation outputs, one per layer.
+
+    The reference keeps float32 until the first LReLU and float64 after it
+    (backprop.py:53-56); the oracle computes in ``dtype``
+    (float64 by default, which is at least as accurate as either).
+    """
+    theta = np.asarray(theta)
+    h = np.asarray(x, dtype=dtype).reshape(-1, spec["n_in"])
+    outs = []
+    for L in spec["layers"]:
+        w, b = _wb(theta, L)
+        z = h @ w.astype(dtype) + b.astype(dtype)
+        if L["act"] == ACT_TANH:
+            h = np.tanh(z)
+        elif L["act"] == ACT_LRELU:
+            h = np.where(z < 0.0, z * dtype(L["leak"]), z)
+        else:
+            h = z
+        outs.append(h)
+    return outs
+
+
+def mlp_backward(theta, spec, x, outs, dy, dtype=np.float64, want_dx=False):
+    """Flat parameter gradient, batch MEAN (basicnet.py:242-249)."""
+    theta = np.asarray(theta)
+    x = np.asarray(x, dtype=dtype).reshape(-1, spec["n_in"])
+    g = np.asarray(dy, dtype=dtype).reshape(x.shape[0], spec["n_out"])
+    batch = x.shape[0]
+    grad = np.zeros(spec["n_params"], dtype=dtype)
+    for i in range(len(spec["layers"]) - 1, -1, -1):
+        L = spec["layers"][i]
+        w, _ = _wb(theta, L)
+        y = outs[i]
+        if L["act"] == ACT_TANH:
+            g = g * (1.0 - np.square(y))                  # backprop.py:58-60
+        elif L["act"] == ACT_LRELU:
+            g = np.where(y < 0.0, g * dtype(L["leak"]), g)  # backprop.py:53-56
+        inp = outs[i - 1] if i > 0 else x
+        grad[L["w_off"]:L["b_off"]] = (inp.T @ g).reshape(-1) / batch
+        grad[L["b_off"]:L["b_off"] + L["n_out"]] = g.sum(axis=0) / batch
+        if i > 0 or want_dx:
+            g = g @ w.astype(dtype).T                     # backprop.py:48-51
+    if want_dx:
+        return grad.astype(np.float32), g
+    return grad.astype(np.float32)                        # basicnet.py:218
+
+
+# --------------------------------------------------------------------------
+# RunningMean / RunningNormalize (mannequin/_normalize.py:4-81)
+# --------------------------------------------------------------------------
+
+class RunningMeanO:
+    def __init__(self, shape=(), horizon=None):
+        self.shape = tuple(np.zeros(shape).shape)
+        self.mean = np.zeros(self.shape, dtype=np.float64)
+        self.tw = 0.0
+        self.decay = None if horizon is None else 1.0 - 1.0 / float(horizon)
+
+    def update(self, values, weight=1.0):
+        v = np.asarray(values, dtype=np.float64).reshape(self.shape)
+        weight = float(weight)
+        if self.decay is not None:
+            self.tw *= np.power(self.decay, weight)       # _normalize.py:18-22
+        self.tw += weight
+        self.mean = self.mean + (weight / self.tw) * (v - self.mean)
+
+    def get(self):
+        return np.array(self.mean)
+
+
+class RunningNormalizeO:
+    def __init__(self, shape=(), horizon=None):
+        self.shape = tuple(np.zeros(shape).shape)
+        self.m = RunningMeanO(self.shape, horizon)
+        self.v = RunningMeanO(self.shape, horizon)
+        self.n = 0
+
+    def update(self, value):
+        x = np.array(value, dtype=np.float64).reshape((-1,) + self.shape)
+        d_old = x - self.m.get()
+        self.m.update(x.mean(axis=0))                     # one weight-1 update per batch
+        d_new = x - self.m.get()
+        cov = (d_old * d_new).mean(axis=0)
+        if self.n >= 1:
+            self.v.update(cov)
+        elif len(x) >= 2:
+            w = (len(x) - 1.0) / len(x)                   # _normalize.py:50-55
+            self.v.update(cov / w, weight=w)
+        self.n += len(x)
+
+    def get_mean(self):
+        return self.m.get()
+
+    def get_var(self):
+        return np.ones(self.shape) if self.n < 2 else self.v.get()
+
+    def get_std(self):
+        return np.sqrt(self.get_var())
+
+    def apply(self, value):
+        if self.n < 2:
+            return np.zeros_like(value, dtype=np.float64)
+        return (value - self.m.get()) / np.maximum(1e-8, np.sqrt(self.v.get()))
+
+    def __call__(self, value):
+        self.update(value)
+        return self.apply(value)
+
+
+# --------------------------------------------------------------------------
+# Adam / Adams (mannequin/_adam.py:7-64): gradient ASCENT, fp64 state
+# --------------------------------------------------------------------------
+
+class AdamO:
+    def __init__(self, value, horizon, var_horizon=100, lr=None, epsilon=1e-8,
+                 adams=False):
+        self.value = np.array(value, dtype=np.float64)
+        self.b1 = 1.0 - 1.0 / float(horizon)
+        self.b2 = 1.0 - 1.0 / float(var_horizon)
+        self.tw1 = self.tw2 = 0.0
+        self.m = np.zeros_like(self.value)
+        self.v = np.zeros_like(self.value)
+        self.lr, self.eps, self.adams = lr, float(epsilon), bool(adams)
+
+    def apply_gradient(self, grad, lr=None, epsilon=None):
+        g = np.asarray(grad, dtype=np.float64)
+        assert g.shape == self.value.shape
+        lr = float(self.lr if lr is None else lr)
+        eps = self.eps if epsilon is None else float(epsilon)
+        self.tw1 = self.tw1 * self.b1 + 1.0
+        self.tw2 = self.tw2 * self.b2 + 1.0
+        self.m = self.m + (1.0 / self.tw1) * (g - self.m)
+        self.v = self.v + (1.0 / self.tw2) * (np.square(g) - self.v)
+        den = eps + (self.v if self.adams else np.sqrt(self.v))
+        self.value = self.value + lr * (self.m / den)     # _adam.py:42,50-53
+
+    def get_value(self):
+        return self.value
+
+
+# --------------------------------------------------------------------------
+# Diagonal Gaussian head (mannequin/distrib.py:41-76)
+# --------------------------------------------------------------------------
+
+def gauss_logprob(mu, logstd, sample):
+    """distrib.py:47,61-68: const - sum(logstd + 0.5*((s-mu)/exp(logstd))^2)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    ls = np.broadcast_to(np.asarray(logstd, dtype=np.float64), mu.shape)
+    s = np.asarray(sample, dtype=np.float64).reshape(mu.shape)
+    a = mu.shape[-1]
+    z = (s - mu) / np.exp(ls)
+    return -0.5 * a * np.log(2.0 * np.pi) - np.sum(ls + 0.5 * z * z, axis=-1)
+
+
+def gauss_logprob_grads(mu, logstd, sample, g):
+    """Closed-form derivative of gauss_logprob weighted by g[B].
+
+    Returns (d_mu[B,A], d_logstd[B,A]); when logstd is a Params(A) the caller
+    sums d_logstd over the batch (and basicnet.py:242-249 divides by B).
+    """
+    mu = np.asarray(mu, dtype=np.float64)
+    ls = np.broadcast_to(np.asarray(logstd, dtype=np.float64), mu.shape)
+    s = np.asarray(sample, dtype=np.float64).reshape(mu.shape)
+    g = np.asarray(g, dtype=np.float64).reshape(mu.shape[:-1] + (1,))
+    inv = np.exp(-ls)
+    z = (s - mu) * inv
+    return g * z * inv, g * (z * z - 1.0)
+
+
+def gauss_sample(mu, logstd, unit_noise):
+    """distrib.py:50-59 with the N(0,1) draw as an input."""
+    noise = np.asarray(unit_noise, dtype=np.float64) * np.exp(
+        np.asarray(logstd, dtype=np.float64))
+    return np.asarray(mu, dtype=np.float64) + noise, noise
+
+
+def gauss_entropy(logstd, n_act):
+    """Not in the reference: H = sum(logstd) + A/2 (1+ln 2pi)."""
+    ls = np.asarray(logstd, dtype=np.float64)
+    return np.sum(ls, axis=-1) + 0.5 * n_act * (1.0 + np.log(2.0 * np.pi))
+
+
+def policy_spec(n_obs, n_act, hid=64, n_hid=2):
+    """benchmarks/policy.py:7-27: Tanh MLP + Gauss; logstd = last A params."""
+    spec = mlp_spec(n_obs, [hid] * n_hid + [n_act],
+                    [ACT_TANH] * n_hid + [ACT_NONE])
+    spec = dict(spec)
+    spec["logstd_off"] = spec["n_params"]
+    spec["n_mlp_params"] = spec["n_params"]
+    spec["n_params"] = spec["n_params"] + n_act
+    return spec
+
+
+def policy_logprob(theta, spec, obs, act):
+    outs = mlp_forward(theta[:spec["n_mlp_params"]], _mlp_part(spec), obs)
+    ls = np.asarray(theta[spec["logstd_off"]:], dtype=np.float64)
+    return gauss_logprob(outs[-1], ls, act), outs
+
+
+def _mlp_part(spec):
+    s = dict(spec)
+    s["n_params"] = spec.get("n_mlp_params", spec["n_params"])
+    return s
+
+
+def policy_logprob_grad(theta, spec, obs, act, g, outs=None):
+    """Flat gradient [P] of sum_b g_b * logp_b, batch mean (F4)."""
+    if outs is None:
+        _, outs = policy_logprob(theta, spec, obs, act)
+    ls = np.asarray(theta[spec["logstd_off"]:], dtype=np.float64)
+    d_mu, d_ls = gauss_logprob_grads(outs[-1], ls, act, g)
+    grad = np.zeros(spec["n_params"], dtype=np.float32)
+    grad[:spec["n_mlp_params"]] = mlp_backward(
+        theta[:spec["n_mlp_params"]], _mlp_part(spec), obs, outs, d_mu)
+    grad[spec["logstd_off"]:] = (d_ls.sum(axis=0) / len(d_mu)).astype(np.float32)
+    return grad
+
+
+# --------------------------------------------------------------------------
+# PPO ratio/clip rule (benchmarks/ppo.py:27,29-40)
+# --------------------------------------------------------------------------
+
+def ppo_clip_weight(logp, logp_old, adv, lo=0.8, hi=1.2):
+    ratio = np.exp(np.asarray(logp, np.float64) - np.asarray(logp_old, np.float64))
+    adv = np.asarray(adv, dtype=np.float64)
+    w = ratio.copy()
+    w[np.logical_and(ratio > hi, adv > 0.0)] = 0.0
+    w[np.logical_and(ratio < lo, adv < 0.0)] = 0.0
+    return w * adv
+
+
+# --------------------------------------------------------------------------
+# GAE and discounted (benchmarks/gae.py:43-64, mannequin/_utils.py:9-20)
+# --------------------------------------------------------------------------
+
+def gae_advantages(rew, value, done, gam=0.99, lam=0.95, dtype=np.float64):
+    """rew[N], value[N+1], done[N] -> (adv[N] float32, ret[N] float32).
+
+    done[i] true means step i is the last of its episode (gae.py:50-52);
+    otherwise bootstrap from value[i+1] and chain gam*lam*adv[i+1]; adv[N]=0.
+    ``dtype=np.float32`` reproduces NumPy-2 (NEP 50) arithmetic of the
+    reference loop; float64 is the NumPy-1 behaviour.
+    """
+    n = len(rew)
+    r = np.asarray(rew, dtype=dtype)
+    v = np.asarray(value, dtype=dtype)
+    adv = np.zeros(n + 1, dtype=dtype)
+    g, gl = dtype(gam), dtype(float(gam) * float(lam))
+    for i in range(n - 1, -1, -1):
+        if done[i]:
+            adv[i] = r[i] - v[i]
+        else:
+            adv[i] = r[i] + g * v[i + 1] - v[i]
+            adv[i] += gl * adv[i + 1]
+    adv32 = adv[:n].astype(np.float32)
+    ret = (adv.astype(np.float32) + np.asarray(value, np.float32))[:n]  # gae.py:69
+    return adv32, ret
+
+
+def discounted(values, horizon):
+    step = 1.0 / float(horizon)
+    assert 1e-6 < step < 1.0
+    out = np.array(values, dtype=np.float64)
+    acc = 0.0
+    for i in range(len(out) - 1, -1, -1):
+        acc += step * (out[i] - acc)
+        out[i] = acc
+    return out
+
+
+# --------------------------------------------------------------------------
+# MNIST head (mnist/mlp.py:10-14,31-35) and VAE heads (mnist/vae.py:13-34)
+# --------------------------------------------------------------------------
+
+def softmax(v):
+    v = np.asarray(v, dtype=np.float64)
+    e = np.exp(v - v.max(axis=-1, keepdims=True))
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+def softmax_ce_grad(logits, onehot, l2=0.01):
+    logits = np.asarray(logits, dtype=np.float64)
+    return np.asarray(onehot, np.float64) - softmax(logits) - logits * l2
+
+
+def dkl_uninormal(mean, logstd):
+    """vae.py:13-22 (note exp(logstd), not exp(2 logstd))."""
+    mean = np.asarray(mean, np.float64)
+    logstd = np.asarray(logstd, np.float64)
+    return 0.5 * (np.sum(np.exp(logstd) - logstd + mean * mean, axis=-1)
+                  - mean.shape[-1])
+
+
+def dkl_uninormal_grads(mean, logstd, g):
+    g = np.asarray(g, np.float64).reshape(np.shape(mean)[:-1] + (1,))
+    return g * np.asarray(mean, np.float64), \
+        0.5 * g * (np.exp(np.asarray(logstd, np.float64)) - 1.0)
+
+
+def clip_forward(v, lo, hi):
+    return np.clip(v, lo, hi)
+
+
+def clip_backward(v, g, lo, hi):
+    g = np.array(g, dtype=np.float64)
+    g[np.logical_and(v < lo, g < 0.0)] = 0.0              # vae.py:26-33
+    g[np.logical_and(v > hi, g > 0.0)] = 0.0
+    return g
+
+
+# --------------------------------------------------------------------------
+# Trajectory dtype / indexing rules (mannequin/_trajectory.py:9-30,79-86)
+# --------------------------------------------------------------------------
+
+def standardize_field(values):
+    if isinstance(values[0], (int, np.integer)):
+        return np.asarray(values, dtype=np.int32)
+    return np.asarray(values, dtype=np.float32)
+
+
+def trajectory_take(obs, act, rew, idx):
+    o, a, r = obs[idx], act[idx], rew[idx]
+    if np.ndim(r) >= 1:
+        return o, a, r
+    return o[None], a[None], np.asarray([r], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------
+# Whole-step restatements used as parity targets and CPU baselines
+# --------------------------------------------------------------------------
+
+def mlp_sgd_step(theta, spec, opt, x, onehot, l2=0.01):
+    """One step of mnist/mlp.py:31-35.  Returns the new float32 theta."""
+    outs = mlp_forward(theta, spec, x)
+    dy = softmax_ce_grad(outs[-1], onehot, l2)
+    opt.apply_gradient(mlp_backward(theta, spec, x, outs, dy))
+    return opt.get_value().astype(np.float32)
+
+
+def value_sgd_step(theta, spec, opt, obs, target):
+    """benchmarks/gae.py:20-23: dy = labels - outputs."""
+    outs = mlp_forward(theta, spec, obs)
+    dy = np.asarray(target, np.float64).reshape(outs[-1].shape) - outs[-1]
+    opt.apply_gradient(mlp_backward(theta, spec, obs, outs, dy))
+    return opt.get_value().astype(np.float32)
+
+
+def ppo_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4,
+                    lo=0.8, hi=1.2):
+    """benchmarks/ppo.py:33-40 on an already gathered minibatch."""
+    logp, outs = policy_logprob(theta, spec, obs, act)
+    g = ppo_clip_weight(logp, logp_old, adv, lo, hi).astype(np.float32)
+    opt.apply_gradient(policy_logprob_grad(theta, spec, obs, act, g, outs), lr=lr)
+    return opt.get_value().astype(np.float32)
+
+
+def ppo_update(pol_theta, pol_spec, pol_opt, val_theta, val_spec, val_opt,
+               norm, obs, act, rew, done, val_idx, pol_idx,
+               gam=0.99, lam=0.95, pol_lr=3e-4):
+    """One chunk of benchmarks/ppo.py:22-40 + benchmarks/gae.py:34-75.
+
+    obs[N+1,D], act[N,A], rew[N], done[N]; val_idx/pol_idx are the
+    [steps, minibatch] int tables the reference draws with randint.
+    """
+    n = len(rew)
+    value = mlp_forward(val_theta, val_spec, obs)[-1].reshape(-1).astype(np.float32)
+    adv, ret = gae_advantages(rew, value, done, gam, lam)
+    for idx in val_idx:                                   # gae.py:71-73
+        val_theta = value_sgd_step(val_theta, val_spec, val_opt,
+                                   obs[:n][idx], ret[idx].reshape(-1, 1))
+    adv_n = np.tanh(norm(adv)).astype(np.float32)         # ppo.py:24-25
+    logp_old, _ = policy_logprob(pol_theta, pol_spec, obs[:n], act)
+    for idx in pol_idx:                                   # ppo.py:29-40
+        pol_theta = ppo_policy_step(pol_theta, pol_spec, pol_opt, obs[:n][idx],
+                                    act[idx], adv_n[idx], logp_old[idx], pol_lr)
+    return pol_theta, val_theta, dict(adv=adv, ret=ret, adv_n=adv_n,
+                                      logp_old=logp_old, value=value)
+
+
+def es_generation(theta, spec, opt, norm, noise, obs, ret_coef, lr=0.01):
+    """Population form of benchmarks/mutation.py:33-37.
+
+    noise[M,P] (already scaled by 0.1), shared obs[T,D]; synthetic return
+    R_p = sum_t sum_a act[p,t,a]*ret_coef[a]; all returns are fed to the
+    normaliser as ONE batch; grad = mean_p noise_p * r_p.
+    """
+    rets = np.zeros(len(noise), dtype=np.float64)
+    for p in range(len(noise)):
+        th = (np.asarray(theta, np.float64) + noise[p]).astype(np.float32)
+        a = mlp_forward(th, spec, obs, dtype=np.float32)[-1]
+        rets[p] = np.sum(a.astype(np.float64) @ np.asarray(ret_coef, np.float64))
+    r = norm(rets.astype(np.float32))
+    grad = (np.asarray(noise, np.float64) * r[:, None]).mean(axis=0)
+    opt.apply_gradient(grad, lr=lr)
+    return opt.get_value().astype(np.float32), rets, r

@@ -1,0 +1,451 @@
+#!/usr/bin/env python3
+"""Generate golden fixtures by running the REAL reference (build container only).
+
+    python tests/golden/make_golden.py         # needs /root/reference
+
+The reference (squirrelinhell/mannequin2) is pure Python, so it is imported
+unmodified from /root/reference.  Three third-party modules it needs are not
+installed here; they are replaced by minimal stand-ins that contain no
+hot-path arithmetic of their own:
+
+  * ``autograd``  -- ``autograd.grad`` is replaced by a complex-step derivative
+    (exact to fp64 rounding for the analytic expressions in
+    mannequin/distrib.py:61-68), ``autograd.numpy`` by numpy.  The forward
+    expression that runs is the reference's own code.
+  * ``gym``       -- only ``gym.Wrapper`` / ``gym.spaces.Box`` are needed by
+    mannequin/gym.py and benchmarks/policy.py; a synthetic environment drives
+    the rollout.
+  * ``_env``      -- benchmarks/_env.py (env factory + progress) is replaced
+    so that benchmarks/ppo.py:run() executes exactly two chunks.
+
+Unseeded ``np.random.RandomState()`` instances (distrib.py:13,46, gae.py:28)
+are made reproducible by patching the constructor; every random index table
+the reference draws is recorded so the oracle / CUDA path can replay it.
+
+Outputs: tests/golden/*.npz (committed).  Nothing here runs on the GPU box.
+"""
+
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("MQ_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ------------------------------------------------------------------ stand-ins
+def install_fake_autograd():
+    ag = types.ModuleType("autograd")
+
+    def grad(fun):
+        def dfun(a, ka, g):
+            res = []
+            for i in range(len(a)):
+                base = [np.asarray(v, dtype=np.complex128) for v in a]
+                d = np.zeros(base[i].shape, dtype=np.float64)
+                for idx in np.ndindex(*base[i].shape):
+                    pert = [v.copy() for v in base]
+                    pert[i][idx] += 1e-30j
+                    d[idx] = np.imag(fun(tuple(pert), ka, g)) / 1e-30
+                res.append(d)
+            return tuple(res)
+        return dfun
+
+    ag.grad = grad
+    ag.numpy = np
+    sys.modules["autograd"] = ag
+    sys.modules["autograd.numpy"] = np
+
+
+def install_fake_gym():
+    gym = types.ModuleType("gym")
+    spaces = types.ModuleType("gym.spaces")
+
+    class Box:
+        def __init__(self, low, high, shape=None):
+            shape = shape if shape is not None else np.shape(low)
+            self.low = np.full(shape, low, dtype=np.float32)
+            self.high = np.full(shape, high, dtype=np.float32)
+            self.shape = tuple(shape)
+
+    class Discrete:
+        def __init__(self, n):
+            self.n = n
+
+    class Wrapper:
+        def __init__(self, env):
+            self.env = env
+            self.observation_space = env.observation_space
+            self.action_space = env.action_space
+
+        def step(self, action):
+            return self._step(action)
+
+        def reset(self):
+            return self._reset()
+
+        def _step(self, action):
+            return self.env.step(action)
+
+        def _reset(self):
+            return self.env.reset()
+
+    spaces.Box, spaces.Discrete = Box, Discrete
+    gym.spaces, gym.Wrapper = spaces, Wrapper
+    sys.modules["gym"] = gym
+    sys.modules["gym.spaces"] = spaces
+    return gym
+
+
+class SyntheticEnv:
+    """Hopper-shaped (obs 11, act 3) random walk; episodes ~200 steps."""
+
+    def __init__(self, gym, seed):
+        self.rs = np.random.RandomState(seed)
+        self.observation_space = gym.spaces.Box(-np.inf, np.inf, (11,))
+        self.action_space = gym.spaces.Box(-1.0, 1.0, (3,))
+
+    def _step(self, action):
+        return self.step(action)
+
+    def _reset(self):
+        return self.reset()
+
+    def reset(self):
+        self.state = self.rs.randn(11)
+        return self.state.copy()
+
+    def step(self, action):
+        action = np.asarray(action, dtype=np.float64).reshape(-1)
+        self.state = 0.9 * self.state + 0.5 * self.rs.randn(11)
+        self.state[:3] += 0.1 * action
+        rew = float(self.rs.randn() + 0.3 * np.sum(action) - 0.05 * np.sum(action ** 2))
+        done = bool(self.rs.rand() < 1.0 / 200.0)
+        return self.state.copy(), rew, done, {}
+
+
+# ------------------------------------------------------------------- fixtures
+def gen_nets(out):
+    import mannequin.basicnet as bn
+    rs = np.random.RandomState(11)
+
+    # LReLU MLP (mnist/mlp.py structure at reduced size) with a (4,5) image input
+    np.random.seed(3)
+    m = bn.Input(4, 5)
+    for _ in range(2):
+        m = bn.LReLU(bn.Affine(m, 16))
+    m = bn.Affine(m, 5, init=0.1)
+    theta = m.get_params() + rs.randn(m.n_params).astype(np.float32) * 0.05
+    m.load_params(theta)
+    x = rs.rand(7, 4, 5).astype(np.float32)
+    dy = rs.randn(7, 5).astype(np.float32)
+    y, bpp = m.evaluate(x)
+    out["lrelu_theta"], out["lrelu_x"], out["lrelu_dy"] = m.get_params(), x, dy
+    out["lrelu_y"], out["lrelu_grad"] = np.asarray(y), bpp(dy)
+    out["lrelu_dx"] = np.asarray(m.prerequisites[0].last_gradient)
+
+    # Tanh policy trunk 11-64-64-3 (benchmarks/mutation.py:7-15), batch 64
+    np.random.seed(4)
+    p = bn.Input(11)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3)
+    theta = p.get_params()
+    theta[-3:] = rs.randn(3) * 0.1
+    p.load_params(theta)
+    x = np.clip(rs.randn(64, 11), -5, 5).astype(np.float32)
+    dy = rs.randn(64, 3).astype(np.float32)
+    y, bpp = p.evaluate(x)
+    out["tanh_theta"], out["tanh_x"], out["tanh_dy"] = p.get_params(), x, dy
+    out["tanh_y"], out["tanh_grad"] = np.asarray(y), bpp(dy)
+    # unbatched call (basicnet.py:242-249: no batch -> no division)
+    y1, bpp1 = p.evaluate(x[0])
+    out["tanh_y1"], out["tanh_grad1"] = np.asarray(y1), bpp1(dy[0])
+
+
+def gen_adam(out):
+    from mannequin import Adam, Adams
+    rs = np.random.RandomState(5)
+    for name, cls in (("adam", Adam), ("adams", Adams)):
+        opt = cls(rs.randn(37), horizon=10, lr=0.003)
+        grads = rs.randn(25, 37).astype(np.float32)
+        grads[3:6, 4] = 0.0
+        lrs = [None] * 20 + [0.01, 0.02, 0.001, 0.5, 0.003]
+        vals = [opt.get_value().copy()]
+        for g, lr in zip(grads, lrs):
+            if lr is None:
+                opt.apply_gradient(g)
+            else:
+                opt.apply_gradient(g, lr=lr, epsilon=1e-6)
+            vals.append(opt.get_value().copy())
+        out[name + "_grads"] = grads
+        out[name + "_lrs"] = np.array([np.nan if l is None else l for l in lrs])
+        out[name + "_values"] = np.array(vals)
+    # the two sequences of tests/adam.py at full precision
+    opt = Adam([10.0, -5.0], lr=2.0, horizon=3)
+    seq = []
+    for _ in range(10):
+        opt.apply_gradient(-opt.get_value())
+        seq.append(opt.get_value().copy())
+    out["adam_kat1"] = np.array(seq)
+    opt = Adam([0.0, 0.0, 0.0], horizon=1)
+    seq = []
+    for i in range(10):
+        opt.apply_gradient([0.1, 1.0, 10.0] - opt.get_value(), lr=7.0 / (i + 1))
+        seq.append(opt.get_value().copy())
+    out["adam_kat2"] = np.array(seq)
+
+
+def gen_norm(out):
+    from mannequin import RunningMean, RunningNormalize, discounted
+    rs = np.random.RandomState(6)
+    # scalar stream in batches of varying size, horizon 2 (benchmarks/ppo.py:19,24)
+    n = RunningNormalize(horizon=2)
+    sizes = [2048, 1, 5, 300]
+    data = [rs.randn(s) * 3.0 + 1.5 for s in sizes]
+    res = []
+    for d in data:
+        res.append(np.concatenate([n(d), [n.get_mean(), n.get_var()]]))
+    out["norm_scalar_in"] = np.concatenate(data)
+    out["norm_scalar_sizes"] = np.array(sizes)
+    out["norm_scalar_out"] = np.concatenate(res)
+    # first batch of a single sample, then more (zeros until 2 samples)
+    n = RunningNormalize(horizon=10)
+    seq = rs.randn(6) * 2.0
+    out["norm_single_in"] = seq
+    out["norm_single_out"] = np.array([n(v) for v in seq])
+    # vector stream [11], no horizon (mannequin/gym.py:66-78)
+    n = RunningNormalize((11,))
+    obs = rs.randn(9, 11) * np.arange(1, 12)
+    o = [n(v) for v in obs]
+    out["norm_vec_in"], out["norm_vec_out"] = obs, np.array(o)
+    out["norm_vec_batch_apply"] = n.apply(obs)
+    out["norm_vec_mean"], out["norm_vec_var"] = n.get_mean(), n.get_var()
+    # running mean with weights and horizon
+    m = RunningMean((7,), horizon=3)
+    xs, ws, ms = rs.randn(8, 7), rs.rand(8) * 2.0, []
+    for x, w in zip(xs, ws):
+        ms.append(m(x, weight=w))
+    out["rmean_x"], out["rmean_w"], out["rmean_out"] = xs, ws, np.array(ms)
+    r = rs.randn(700)
+    out["disc_in"] = r
+    out["disc_h500"] = discounted(r, horizon=500)
+    out["disc_h3"] = discounted(r, horizon=3)
+
+
+def gen_trajectory(out):
+    from mannequin import Trajectory
+    rs = np.random.RandomState(7)
+    o = rs.randn(40, 11)
+    a = rs.randn(40, 3)
+    r = rs.randn(40)
+    t = Trajectory(o, a, r)
+    idx = rs.randint(40, size=64)
+    b = t[idx]
+    out["traj_o"], out["traj_a"], out["traj_r"], out["traj_idx"] = o, a, r, idx
+    out["traj_take_o"], out["traj_take_a"], out["traj_take_r"] = b.o, b.a, b.r
+    s = t[5:33:3]
+    out["traj_slice_o"], out["traj_slice_r"] = s.o, s.r
+    d = t.discounted(horizon=20)
+    out["traj_disc_r"] = d.r
+    ti = Trajectory([3, 1, 2], [[1], [0], [1]])
+    out["traj_int_o"], out["traj_int_a"], out["traj_int_r"] = ti.o, ti.a, ti.r
+    j = Trajectory.joined(t[:3], t[10:12])
+    out["traj_join_r"] = j.r
+
+
+def gen_gauss(out):
+    import mannequin.basicnet as bn
+    from mannequin.distrib import Gauss
+    rs = np.random.RandomState(8)
+    np.random.seed(9)
+    p = bn.Input(11)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3, init=0.1)
+    pol = Gauss(mean=p)
+    theta = pol.get_params()
+    theta[-3:] = [-0.3, 0.1, 0.4]
+    pol.load_params(theta)
+    obs = np.clip(rs.randn(64, 11), -5, 5).astype(np.float32)
+    act = rs.randn(64, 3).astype(np.float32)
+    g = rs.randn(64).astype(np.float32)
+    logp, bpp = pol.logprob.evaluate(obs, sample=act)
+    out["gauss_theta"], out["gauss_obs"], out["gauss_act"], out["gauss_g"] = \
+        pol.get_params(), obs, act, g
+    out["gauss_logp"], out["gauss_grad"] = np.asarray(logp), bpp(g)
+    # sample path: mean + randn*exp(logstd) with backward (distrib.py:50-59)
+    smp, bpp = pol.sample.evaluate(obs[:5])
+    mu = pol.mean(obs[:5])
+    out["gauss_sample_unit"] = (np.asarray(smp) - mu) / np.exp(theta[-3:])
+    out["gauss_sample_out"] = np.asarray(smp)
+    gs = rs.randn(5, 3).astype(np.float32)
+    out["gauss_sample_g"], out["gauss_sample_grad"] = gs, bpp(gs)
+
+
+def gen_ppo(out, gym):
+    """Run benchmarks/ppo.py:run() itself for two chunks and record everything."""
+    import mannequin
+    import mannequin.gym as mgym
+
+    bench_dir = os.path.join(REF, "benchmarks")
+    sys.path.insert(0, bench_dir)
+
+    env_mod = types.ModuleType("_env")
+    calls = {"n": 0}
+
+    def get_progress():
+        calls["n"] += 1
+        return 0.0 if calls["n"] <= 2 else 1.0
+
+    env_mod.build_env = lambda: SyntheticEnv(gym, seed=21)
+    env_mod.get_progress = get_progress
+    sys.modules["_env"] = env_mod
+
+    # record every Adam the run constructs (policy first, value predictor second)
+    adams = []
+    RealAdam = mannequin.Adam
+
+    class RecordingAdam(RealAdam):
+        def __init__(self, value, **kw):
+            super().__init__(value, **kw)
+            self.init_value = np.array(value, dtype=np.float64)
+            self.trace = []
+            inner = self.apply_gradient
+
+            def apply(grad, **lk):
+                inner(grad, **lk)
+                self.trace.append(self.get_value().astype(np.float32))
+            self.apply_gradient = apply
+            adams.append(self)
+
+    mannequin.Adam = RecordingAdam
+
+    # seeded stand-ins for RandomState() and recording of index draws
+    RealRS = np.random.RandomState
+    rs_seed = {"n": 100}
+    idx_log = {"value": [], "policy": []}
+
+    class SeededRS(RealRS):
+        def __new__(cls, *a, **k):
+            return RealRS.__new__(cls)
+
+        def __init__(self, seed=None):
+            if seed is None:
+                rs_seed["n"] += 1
+                seed = rs_seed["n"]
+            super().__init__(seed)
+
+        def randint(self, *a, **k):
+            r = super().randint(*a, **k)
+            if k.get("size") == 64:
+                idx_log["value"].append(np.array(r))
+            return r
+
+    np.random.RandomState = SeededRS
+    real_randint = np.random.randint
+
+    def rec_randint(*a, **k):
+        r = real_randint(*a, **k)
+        if k.get("size") == 64:
+            idx_log["policy"].append(np.array(r))
+        return r
+
+    np.random.randint = rec_randint
+
+    hist = []
+    real_one_step = mgym.one_step
+
+    def rec_one_step(env, policy):
+        s = real_one_step(env, policy)
+        hist.append(s)
+        return s
+
+    mgym.one_step = rec_one_step
+
+    try:
+        np.random.seed(31)
+        import ppo
+        ppo.run()
+    finally:
+        np.random.RandomState = RealRS
+        np.random.randint = real_randint
+        mgym.one_step = real_one_step
+        mannequin.Adam = RealAdam
+        sys.path.remove(bench_dir)
+
+    pol, val = adams[0], adams[1]
+    assert len(pol.trace) == 600 and len(val.trace) == 600, (len(pol.trace), len(val.trace))
+    ck = [0, 1, 2, 4, 9, 19, 49, 99, 199, 299, 300, 301, 309, 399, 599]
+    out["ppo_obs"] = np.array([h[0] for h in hist], dtype=np.float32)
+    out["ppo_act"] = np.array([h[1] for h in hist], dtype=np.float32)
+    out["ppo_rew"] = np.array([h[2] for h in hist], dtype=np.float64)
+    out["ppo_done"] = np.array([h[3] for h in hist], dtype=np.bool_)
+    out["ppo_val_idx"] = np.array(idx_log["value"], dtype=np.int32)
+    out["ppo_pol_idx"] = np.array(idx_log["policy"], dtype=np.int32)
+    out["ppo_pol_init"] = pol.init_value.astype(np.float32)
+    out["ppo_val_init"] = val.init_value.astype(np.float32)
+    out["ppo_ck_steps"] = np.array(ck)
+    out["ppo_pol_ck"] = np.array([pol.trace[i] for i in ck])
+    out["ppo_val_ck"] = np.array([val.trace[i] for i in ck])
+
+
+def gen_gae(out, gym):
+    """benchmarks/gae.py:gae() driven directly: advantages of two chunks."""
+    import mannequin.gym as mgym
+    bench_dir = os.path.join(REF, "benchmarks")
+    sys.path.insert(0, bench_dir)
+    try:
+        import gae as gae_mod
+        env = mgym.NormalizedObservations(SyntheticEnv(gym, seed=77))
+        rs = np.random.RandomState(78)
+        hist = []
+        real_one_step = mgym.one_step
+
+        def rec_one_step(e, p):
+            s = real_one_step(e, p)
+            hist.append(s)
+            return s
+        mgym.one_step = rec_one_step
+        np.random.seed(79)
+        get_chunk = gae_mod.gae(env, lambda o: rs.randn(3) * 0.5, gam=0.97, lam=0.9)
+        t1 = get_chunk()
+        t2 = get_chunk()
+        mgym.one_step = real_one_step
+    finally:
+        sys.path.remove(bench_dir)
+    out["gae_obs"] = np.array([h[0] for h in hist], dtype=np.float32)
+    out["gae_rew"] = np.array([h[2] for h in hist], dtype=np.float64)
+    out["gae_done"] = np.array([h[3] for h in hist], dtype=np.bool_)
+    out["gae_adv1"], out["gae_adv2"] = t1.r, t2.r
+    out["gae_o2_first"] = t2.o[0]
+
+
+def main():
+    sys.path.insert(0, REF)
+    install_fake_autograd()
+    gym = install_fake_gym()
+    np.set_printoptions(precision=3, linewidth=100, suppress=True)
+
+    groups = {}
+    for name, fn in (("nets", gen_nets), ("adam", gen_adam), ("norm", gen_norm),
+                     ("trajectory", gen_trajectory), ("gauss", gen_gauss)):
+        d = {}
+        fn(d)
+        groups[name] = d
+    d = {}
+    gen_ppo(d, gym)
+    groups["ppo"] = d
+    d = {}
+    gen_gae(d, gym)
+    groups["gae"] = d
+    for name, d in groups.items():
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **d)
+        print("%-12s %3d arrays  %7.1f KB" % (name, len(d), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,279 @@
+"""Pin the CPU oracle (oracle/mq_oracle.py) to the reference.
+
+Two kinds of pins:
+  * literal known answers from the reference's own golden files
+    (/root/reference/tests/adam.out, basicnet.out -- values copied as data);
+  * tests/golden/*.npz, produced by running the real reference in the build
+    container (tests/golden/make_golden.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+from oracle import mq_oracle as O
+
+
+# ---- /root/reference/tests/adam.out:1-10 (Adam([10,-5], lr=2, horizon=3), grad=-value)
+ADAM_OUT_1 = [[8., -3.], [6.055, -1.155], [4.218, 0.335], [2.552, 1.247], [1.125, 1.509],
+              [-0.001, 1.25], [-0.789, 0.703], [-1.236, 0.105], [-1.376, -0.347], [-1.276, -0.545]]
+# ---- adam.out:12-21 (Adam(zeros(3), horizon=1), grad=[.1,1,10]-value, lr=7/(i+1))
+ADAM_OUT_2 = [[7., 7., 7.], [2.063, 2.129, 8.425], [0.958, 1.392, 9.031], [0.541, 1.17, 9.353],
+              [0.35, 1.084, 9.545], [0.25, 1.045, 9.669], [0.195, 1.026, 9.753],
+              [0.162, 1.015, 9.811], [0.142, 1.009, 9.853], [0.129, 1.006, 9.884]]
+
+
+def test_adam_reference_out_file():
+    opt = O.AdamO([10.0, -5.0], horizon=3, lr=2.0)
+    for want in ADAM_OUT_1:
+        opt.apply_gradient(-opt.get_value())
+        assert np.allclose(opt.get_value(), want, atol=6e-4)
+    opt = O.AdamO([0.0, 0.0, 0.0], horizon=1)
+    for i, want in enumerate(ADAM_OUT_2):
+        opt.apply_gradient([0.1, 1.0, 10.0] - opt.get_value(), lr=7.0 / (i + 1))
+        assert np.allclose(opt.get_value(), want, atol=6e-4)
+
+
+@pytest.mark.parametrize("name", ["adam", "adams"])
+def test_adam_bit_exact_vs_reference(name):
+    g = load_golden("adam")
+    opt = O.AdamO(g[name + "_values"][0], horizon=10, lr=0.003, adams=(name == "adams"))
+    for grad, lr, want in zip(g[name + "_grads"], g[name + "_lrs"], g[name + "_values"][1:]):
+        if np.isnan(lr):
+            opt.apply_gradient(grad)
+        else:
+            opt.apply_gradient(grad, lr=lr, epsilon=1e-6)
+        # same fp64 operation order as mannequin/_adam.py + _normalize.py -> identical bits
+        assert np.array_equal(opt.get_value(), want)
+    opt = O.AdamO([10.0, -5.0], horizon=3, lr=2.0)
+    for want in g["adam_kat1"]:
+        opt.apply_gradient(-opt.get_value())
+        assert np.array_equal(opt.get_value(), want)
+
+
+def test_basicnet_reference_out_file():
+    # /root/reference/tests/basicnet.py:6-22 + basicnet.out:1-7
+    spec = O.mlp_spec(2, [2, 2], [O.ACT_NONE, O.ACT_NONE])
+    theta = np.arange(12, dtype=np.float32)
+    outs = O.mlp_forward(theta, spec, [[1.0, 1.0]])
+    assert np.allclose(outs[-1], [[118., 134.]])
+    grad = O.mlp_backward(theta, spec, [[1.0, 1.0]], outs, [[1.0, -1.0]])
+    assert np.allclose(grad.reshape(-1, 6), [[-1, -1, -1, -1, -1, -1], [6, -6, 9, -9, 1, -1]])
+    outs = O.mlp_forward(theta, spec, np.eye(2))
+    assert np.allclose(outs[-1], [[82., 93.], [110., 125.]])
+    grad = O.mlp_backward(theta, spec, np.eye(2), outs, [[1.0, -1.0], [-2.0, 2.0]])
+    assert np.allclose(grad.reshape(-1, 6),
+                       [[-0.5, -0.5, 1, 1, 0.5, 0.5], [-4, 4, -5, 5, -0.5, 0.5]])
+    # basicnet.out:8-15: LReLU(0.1) / Tanh on top, input [-18.4, 2]
+    v = [[-18.4, 2.0]]
+    for act, y, g in (
+        (O.ACT_LRELU, [-0.12, 0.4], [[117.76, 150.88, -12.8, -16.4, -6.4, -8.2],
+                                     [0.8, -8.0, -0.74, 7.4, 0.1, -1.0]]),
+        (O.ACT_TANH, [-0.834, 0.38], [[76.532, 96.794, -8.319, -10.521, -4.159, -5.261],
+                                      [2.44, -6.845, -2.257, 6.332, 0.305, -0.856]])):
+        spec = O.mlp_spec(2, [2, 2], [O.ACT_NONE, act])
+        outs = O.mlp_forward(theta, spec, v)
+        assert np.allclose(outs[-1], [y], atol=6e-4)
+        grad = O.mlp_backward(theta, spec, v, outs, [[1.0, -1.0]])
+        assert np.allclose(grad.reshape(-1, 6), g, atol=6e-4)
+
+
+def test_nets_vs_reference():
+    g = load_golden("nets")
+    spec = O.mlp_spec(20, [16, 16, 5], [O.ACT_LRELU, O.ACT_LRELU, O.ACT_NONE])
+    outs = O.mlp_forward(g["lrelu_theta"], spec, g["lrelu_x"].reshape(7, 20))
+    assert_close(outs[-1], g["lrelu_y"])
+    grad, dx = O.mlp_backward(g["lrelu_theta"], spec, g["lrelu_x"].reshape(7, 20), outs,
+                              g["lrelu_dy"], want_dx=True)
+    assert_close(grad, g["lrelu_grad"])
+    assert_close(dx.reshape(7, 4, 5), g["lrelu_dx"])
+
+    spec = O.mlp_spec(11, [64, 64, 3], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    outs = O.mlp_forward(g["tanh_theta"], spec, g["tanh_x"])
+    assert_close(outs[-1], g["tanh_y"], rtol=2e-5, atol_scale=2e-6)   # reference is fp32 here
+    grad = O.mlp_backward(g["tanh_theta"], spec, g["tanh_x"], outs, g["tanh_dy"])
+    assert_close(grad, g["tanh_grad"], rtol=2e-5, atol_scale=2e-6)
+    # unbatched: batch of one, no division (basicnet.py:242-249)
+    outs = O.mlp_forward(g["tanh_theta"], spec, g["tanh_x"][:1])
+    assert_close(outs[-1][0], g["tanh_y1"], rtol=2e-5, atol_scale=2e-6)
+    grad = O.mlp_backward(g["tanh_theta"], spec, g["tanh_x"][:1], outs, g["tanh_dy"][:1])
+    assert_close(grad, g["tanh_grad1"], rtol=2e-5, atol_scale=2e-6)
+
+
+def test_running_stats_vs_reference():
+    g = load_golden("norm")
+    n = O.RunningNormalizeO(horizon=2)
+    pos, res = 0, []
+    for s in g["norm_scalar_sizes"]:
+        d = g["norm_scalar_in"][pos:pos + s]
+        pos += s
+        res.append(np.concatenate([n(d), [n.get_mean(), n.get_var()]]))
+    assert np.allclose(np.concatenate(res), g["norm_scalar_out"], rtol=1e-13, atol=1e-13)
+
+    n = O.RunningNormalizeO(horizon=10)
+    got = np.array([n(v) for v in g["norm_single_in"]])
+    assert np.allclose(got, g["norm_single_out"], rtol=1e-13, atol=1e-13)
+    assert got[0] == 0.0                                   # zeros until 2 samples
+
+    n = O.RunningNormalizeO((11,))
+    got = np.array([n(v).reshape(11) for v in g["norm_vec_in"]])
+    assert np.allclose(got, g["norm_vec_out"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(n.apply(g["norm_vec_in"]), g["norm_vec_batch_apply"], rtol=1e-12)
+    assert np.allclose(n.get_mean(), g["norm_vec_mean"], rtol=1e-13)
+    assert np.allclose(n.get_var(), g["norm_vec_var"], rtol=1e-13)
+
+    m = O.RunningMeanO((7,), horizon=3)
+    for x, w, want in zip(g["rmean_x"], g["rmean_w"], g["rmean_out"]):
+        m.update(x, weight=w)
+        assert np.array_equal(m.get(), want)
+
+    assert np.array_equal(O.discounted(g["disc_in"], 500), g["disc_h500"])
+    assert np.array_equal(O.discounted(g["disc_in"], 3), g["disc_h3"])
+
+
+def test_running_norm_reference_asserts():
+    # /root/reference/tests/running_norm.py:8-16,33-43: == np.mean / np.var(ddof=1)
+    n = O.RunningNormalizeO()
+    data = np.arange(10) + 10
+    n.update(data[0])
+    for i in range(2, len(data)):
+        n.update(data[i - 1])
+        assert abs(n.get_mean() - np.mean(data[:i])) < 1e-10
+        assert abs(n.get_var() - np.var(data[:i], ddof=1)) < 1e-10
+    rs = np.random.RandomState(0)
+    n = O.RunningNormalizeO((5,))
+    data = rs.rand(10, 5)
+    for d in data:
+        n.update(d)
+    want = (data - data.mean(axis=0)) / data.std(axis=0, ddof=1)
+    assert np.mean(np.abs(n.apply(data) - want)) < 1e-10
+
+
+def test_trajectory_rules_vs_reference():
+    g = load_golden("trajectory")
+    o, a, r = (O.standardize_field(g["traj_o"]), O.standardize_field(g["traj_a"]),
+               np.asarray(g["traj_r"], np.float32))
+    to, ta, tr = O.trajectory_take(o, a, r, g["traj_idx"])
+    assert np.array_equal(to, g["traj_take_o"]) and to.dtype == np.float32
+    assert np.array_equal(ta, g["traj_take_a"]) and np.array_equal(tr, g["traj_take_r"])
+    so, _, sr = O.trajectory_take(o, a, r, slice(5, 33, 3))
+    assert np.array_equal(so, g["traj_slice_o"]) and np.array_equal(sr, g["traj_slice_r"])
+    assert np.array_equal(O.discounted(r, 20).astype(np.float32), g["traj_disc_r"])
+    assert O.standardize_field([3, 1, 2]).dtype == np.int32 == g["traj_int_o"].dtype
+    assert np.array_equal(g["traj_int_r"], np.ones(3, np.float32))
+
+
+def test_gauss_vs_reference_and_fd():
+    g = load_golden("gauss")
+    spec = O.policy_spec(11, 3)
+    assert spec["n_params"] == 5126 == len(g["gauss_theta"])
+    logp, outs = O.policy_logprob(g["gauss_theta"], spec, g["gauss_obs"], g["gauss_act"])
+    assert_close(logp, g["gauss_logp"], rtol=2e-6, atol_scale=1e-6)
+    grad = O.policy_logprob_grad(g["gauss_theta"], spec, g["gauss_obs"], g["gauss_act"],
+                                 g["gauss_g"], outs)
+    assert_close(grad, g["gauss_grad"], rtol=3e-5, atol_scale=3e-6)
+    # closed form vs central finite differences (fp64)
+    rs = np.random.RandomState(1)
+    mu, ls, s, w = rs.randn(4, 3), rs.randn(3) * 0.3, rs.randn(4, 3), rs.randn(4)
+    d_mu, d_ls = O.gauss_logprob_grads(mu, ls, s, w)
+    f = lambda m, l: np.sum(O.gauss_logprob(m, l, s) * w)
+    for idx in np.ndindex(4, 3):
+        e = np.zeros((4, 3)); e[idx] = 1e-6
+        assert abs((f(mu + e, ls) - f(mu - e, ls)) / 2e-6 - d_mu[idx]) < 1e-6
+    for j in range(3):
+        e = np.zeros(3); e[j] = 1e-6
+        assert abs((f(mu, ls + e) - f(mu, ls - e)) / 2e-6 - d_ls.sum(axis=0)[j]) < 1e-6
+    # sample path: mean + unit*exp(logstd); backward (g, sum_b g*noise)
+    theta = g["gauss_theta"]
+    mu = O.mlp_forward(theta[:5123], O._mlp_part(spec), g["gauss_obs"][:5])[-1]
+    smp, noise = O.gauss_sample(mu, theta[-3:], g["gauss_sample_unit"])
+    assert_close(smp, g["gauss_sample_out"], rtol=1e-5)
+    gs = g["gauss_sample_g"].astype(np.float64)
+    grad = np.zeros(5126, np.float32)
+    outs = O.mlp_forward(theta[:5123], O._mlp_part(spec), g["gauss_obs"][:5])
+    grad[:5123] = O.mlp_backward(theta[:5123], O._mlp_part(spec), g["gauss_obs"][:5], outs, gs)
+    grad[5123:] = (gs * noise).sum(axis=0) / 5
+    assert_close(grad, g["gauss_sample_grad"], rtol=3e-5, atol_scale=3e-6)
+
+
+def test_vae_heads_fd():
+    rs = np.random.RandomState(2)
+    m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
+    dm, dl = O.dkl_uninormal_grads(m, l, w)
+    f = lambda a, b: np.sum(O.dkl_uninormal(a, b) * w)
+    for idx in np.ndindex(5, 3):
+        e = np.zeros((5, 3)); e[idx] = 1e-6
+        assert abs((f(m + e, l) - f(m - e, l)) / 2e-6 - dm[idx]) < 1e-6
+        assert abs((f(m, l + e) - f(m, l - e)) / 2e-6 - dl[idx]) < 1e-6
+    # Clip backward: /root/reference/tests/reshape.out "Gradient" blocks 2->3
+    v = np.array([[0., 0., -2.], [3., 0., -5.]])
+    assert np.array_equal(O.clip_forward(v, -2.5, 2.5), [[0, 0, -2], [2.5, 0, -2.5]])
+    assert np.array_equal(O.clip_backward(v, np.ones((2, 3)), -2.5, 2.5), [[1, 1, 1], [0, 1, 1]])
+
+
+def test_gae_vs_reference_chunks():
+    g = load_golden("gae")
+    # value predictions are internal to the reference closure; the advantages of the
+    # FIRST chunk use the freshly initialised predictor, which make_golden seeds
+    # with np.random.seed(79): rebuild it through the oracle's init.
+    np_state = np.random.RandomState(79)
+    spec = O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    theta = O.mlp_init(spec, np_state, head_scale=0.1)
+    n = 2048
+    obs, rew, done = g["gae_obs"], g["gae_rew"], g["gae_done"]
+    value = O.mlp_forward(theta, spec, obs[:n + 1], dtype=np.float32)[-1].reshape(-1)
+    adv, _ = O.gae_advantages(rew[:n], value, done[:n], 0.97, 0.9)
+    assert_close(adv, g["gae_adv1"], rtol=2e-5, atol_scale=2e-6)
+    adv32, _ = O.gae_advantages(rew[:n], value, done[:n], 0.97, 0.9, dtype=np.float32)
+    assert_close(adv32, g["gae_adv1"], rtol=2e-5, atol_scale=2e-6)
+    # chunk carry-over (gae.py:64): second chunk starts at step 2048
+    assert len(obs) == 2 * n + 1
+    assert np.array_equal(obs[n], g["gae_o2_first"])
+    # segmentation is integer-exact: with gam=lam=1 and integer data the scan is exact
+    rs = np.random.RandomState(5)
+    r = rs.randint(-3, 4, size=500).astype(np.float64)
+    v = rs.randint(-3, 4, size=501).astype(np.float64)
+    d = rs.rand(500) < 0.05
+    a, _ = O.gae_advantages(r, v, d, 1.0, 1.0)
+    want = np.zeros(501)
+    for i in range(499, -1, -1):
+        want[i] = r[i] - v[i] + (0 if d[i] else v[i + 1] + want[i + 1])
+    assert np.array_equal(a, want[:500].astype(np.float32))
+
+
+def test_ppo_run_vs_reference():
+    """Replays benchmarks/ppo.py:run() (two chunks) through the oracle."""
+    g = load_golden("ppo")
+    n = 2048
+    pol_spec = O.policy_spec(11, 3)
+    val_spec = O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    pol_theta, val_theta = g["ppo_pol_init"], g["ppo_val_init"]
+    pol_opt = O.AdamO(pol_theta, horizon=10)
+    val_opt = O.AdamO(val_theta, horizon=10, lr=0.003)
+    norm = O.RunningNormalizeO(horizon=2)
+    ck = {int(s): i for i, s in enumerate(g["ppo_ck_steps"])}
+    obs, act, rew, done = g["ppo_obs"], g["ppo_act"], g["ppo_rew"], g["ppo_done"]
+    assert len(obs) == 2 * n + 1
+    for c in range(2):
+        lo = c * n
+        # teacher-forced checkpoints: run each chunk with the oracle, compare the
+        # parameter trajectories at the recorded steps (tolerance grows with depth
+        # because fp32-vs-fp64 rounding feeds back through Adam).
+        value = O.mlp_forward(val_theta, val_spec, obs[lo:lo + n + 1])[-1].reshape(-1).astype(np.float32)
+        adv, ret = O.gae_advantages(rew[lo:lo + n], value, done[lo:lo + n])
+        o = obs[lo:lo + n]
+        for k, idx in enumerate(g["ppo_val_idx"][c * 300:(c + 1) * 300]):
+            val_theta = O.value_sgd_step(val_theta, val_spec, val_opt, o[idx], ret[idx].reshape(-1, 1))
+            s = c * 300 + k
+            if s in ck:
+                tol = 2e-6 * (1 + k)
+                assert np.max(np.abs(val_theta - g["ppo_val_ck"][ck[s]])) < tol + 1e-6, ("val", s)
+        adv_n = np.tanh(norm(adv)).astype(np.float32)
+        a = act[lo:lo + n]
+        logp_old, _ = O.policy_logprob(pol_theta, pol_spec, o, a)
+        for k, idx in enumerate(g["ppo_pol_idx"][c * 300:(c + 1) * 300]):
+            pol_theta = O.ppo_policy_step(pol_theta, pol_spec, pol_opt, o[idx], a[idx],
+                                          adv_n[idx], logp_old[idx])
+            s = c * 300 + k
+            if s in ck:
+                tol = 2e-6 * (1 + k)
+                assert np.max(np.abs(pol_theta - g["ppo_pol_ck"][ck[s]])) < tol + 1e-6, ("pol", s)
