@@ -1,0 +1,201 @@
+/* mq_b200.h -- C-ABI of the B200-native mannequin2 training hot path.
+ *
+ * The reference (squirrelinhell/mannequin2) is pure Python + NumPy and has no
+ * FFI of its own; its drop-in boundary is the Python API of package
+ * `mannequin`.  mannequin2_b200/ mirrors that API and binds the
+ * entry points below with ctypes (mannequin2_b200/_lib.py).  Each entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls only enqueue work, they never synchronise and never allocate;
+ *   - every function returns MQ_OK or a negative MQ_ERR_* code, never throws,
+ *     never exits; mq_last_error() gives the message for the calling thread;
+ *   - dtype selectors: MQ_F32 / MQ_F64.
+ */
+#ifndef MQ_B200_H
+#define MQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ_OK               0
+#define MQ_ERR_INVALID     (-1)  /* bad argument value            -> ValueError        */
+#define MQ_ERR_SHAPE       (-2)  /* shape / size contract broken  -> AssertionError    */
+#define MQ_ERR_UNSUPPORTED (-3)  /* net does not fit this kernel  -> NotImplementedError */
+#define MQ_ERR_CUDA        (-4)  /* CUDA runtime failure          -> RuntimeError      */
+
+#define MQ_F32 0
+#define MQ_F64 1
+
+#define MQ_ACT_NONE  0
+#define MQ_ACT_TANH  1   /* mannequin/backprop.py:58-60 */
+#define MQ_ACT_LRELU 2   /* mannequin/backprop.py:53-56, leak default 0.1 (basicnet.py:313) */
+
+#define MQ_MAX_LAYERS 8
+
+/* A stack of Affine(+activation) layers over ONE flat float32 parameter vector
+ * in the reference's order W1(in x out, row-major), b1, W2, b2, ...
+ * (mannequin/basicnet.py:13-23,35-51,303-311).  For Gauss(mean=net) the learnt
+ * state-independent logstd is the LAST n_out entries (mannequin/distrib.py:43). */
+typedef struct mq_net {
+    int32_t n_layers;
+    int32_t n_in;
+    int32_t n_out;
+    int32_t n_params;            /* including logstd when logstd_off >= 0 */
+    int32_t logstd_off;          /* -1: no Gaussian head parameters       */
+    int32_t in[MQ_MAX_LAYERS];
+    int32_t out[MQ_MAX_LAYERS];
+    int32_t act[MQ_MAX_LAYERS];
+    float   leak[MQ_MAX_LAYERS];
+    int32_t w_off[MQ_MAX_LAYERS];
+    int32_t b_off[MQ_MAX_LAYERS];
+} mq_net_t;
+
+/* Loss-gradient rules evaluated inside the fused kernels ("heads"). */
+#define MQ_HEAD_DY         0  /* dy[B,n_out] supplied: Function.evaluate()[1](dy), basicnet.py:209   */
+#define MQ_HEAD_DIFF       1  /* dy = target - out: benchmarks/gae.py:20-23                          */
+#define MQ_HEAD_SOFTMAX_CE 2  /* dy = onehot - softmax(out) - p0*out: mnist/mlp.py:10-14,31-35       */
+#define MQ_HEAD_GAUSS_LOGP 3  /* d/dtheta sum_b w_b logp_b, w supplied: distrib.py:61-68, gae.py:98-99 */
+#define MQ_HEAD_GAUSS_PPO  4  /* w_b = clip-rule(exp(logp-logp_old), adv)*adv: benchmarks/ppo.py:33-40 */
+
+typedef struct mq_head {
+    int32_t kind;
+    float   p0;                /* SOFTMAX_CE: logit L2 coefficient (0.01); GAUSS_PPO: clip low (0.8) */
+    float   p1;                /* GAUSS_PPO: clip high (1.2)                                         */
+    const float *dy;           /* DY: [rows,n_out]; GAUSS_LOGP: weights [rows]                        */
+    const float *target;       /* DIFF/SOFTMAX_CE: [rows,n_out]; GAUSS_*: sampled actions [rows,A]   */
+    const float *adv;          /* GAUSS_PPO: advantages [rows]                                       */
+    const float *logp_old;     /* GAUSS_PPO: log-probabilities under the pre-update policy [rows]    */
+} mq_head_t;
+/* When row_idx != NULL, x and every head array are indexed by row_idx[i] (they
+ * are whole-rollout arrays, mannequin/_trajectory.py:79-86 fused into the load);
+ * otherwise by the minibatch position i. */
+
+/* ---- library -------------------------------------------------------------- */
+const char *mq_last_error(void);
+int mq_version(void);
+int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
+
+/* ---- optimiser: mannequin/_adam.py:7-64 + mannequin/_normalize.py:9-25 ------
+ * value += lr * m / (eps + sqrt(v))     (gradient ASCENT; adams!=0: / (eps + v))
+ * m += c1*(g-m), v += c2*(g*g-v) with c = weight/total_weight kept by the host.
+ * state_dtype MQ_F64 follows the reference operation order bit for bit;
+ * theta_out (float32 model copy, basicnet.py:55-66,161-165) may be NULL. */
+int mq_adam_step(void *value, void *m, void *v, float *theta_out, const void *grad,
+                 int64_t n, int state_dtype, int grad_dtype, double c1, double c2,
+                 double lr, double eps, int adams, void *stream);
+/* mean += coef*(x-mean); old_out (nullable) receives the previous mean. */
+int mq_running_mean_update(double *mean, const void *x, int x_dtype, int64_t n,
+                           double coef, double *old_out, void *stream);
+
+/* ---- running normaliser: mannequin/_normalize.py:34-81 ---------------------- */
+int64_t mq_norm_ws_bytes(int64_t rows, int64_t cols);
+int mq_col_mean(const void *x, int x_dtype, int64_t rows, int64_t cols, double *out, void *ws,
+                int64_t ws_bytes, void *stream);
+/* out[c] = scale * mean_r (x[r,c]-mean_old[c])*(x[r,c]-mean_new[c]) */
+int mq_norm_cov(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *mean_old,
+                const double *mean_new, double scale, double *out, void *ws, int64_t ws_bytes,
+                void *stream);
+/* out = (x-mean)/max(1e-8,sqrt(var)); fuse_tanh applies benchmarks/ppo.py:25 */
+int mq_norm_apply(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *mean,
+                  const double *var, void *out, int out_dtype, int fuse_tanh, void *stream);
+
+/* ---- trajectories: mannequin/_trajectory.py:79-86, mannequin/_utils.py:9-20,
+ *      benchmarks/gae.py:43-64 ---------------------------------------------- */
+int mq_gather_rows(const void *src, const int32_t *idx, int64_t n_idx, int64_t row_bytes,
+                   int64_t n_src_rows, void *dst, void *stream);
+int64_t mq_scan_ws_bytes(int64_t n);
+/* adv[i] = r[i]-v[i] (+ gam*v[i+1] + gam*lam*adv[i+1] unless done[i]); ret = adv+v[:n] */
+int mq_gae(const float *rew, const float *value, const uint8_t *done, int64_t n, double gam,
+           double lam, float *adv, float *ret, void *ws, int64_t ws_bytes, void *stream);
+/* out[i] = out[i+1] + (in[i]-out[i+1])/horizon, fp64 like the reference */
+int mq_discounted(const double *in, int64_t n, double horizon, double *out, void *ws,
+                  int64_t ws_bytes, void *stream);
+
+/* ---- layered MLP path (any width; activations saved in HBM) ----------------
+ * mannequin/basicnet.py:192-259 + mannequin/backprop.py:11-60 for a chain of
+ * Affine / LReLU / Tanh.  acts holds every layer's output back to back, layer l
+ * as [batch,out[l]] row-major. */
+int64_t mq_mlp_acts_floats(const mq_net_t *net, int64_t batch);
+int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch);
+int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                   int64_t batch, float *acts, void *stream);
+/* grad[n_params] = scale * sum over batch (scale = 1/batch is the reference's
+ * batch MEAN, basicnet.py:242-249); dy is clobbered; dx (nullable) = grad wrt x. */
+int mq_mlp_backward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                    const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx,
+                    void *ws, int64_t ws_bytes, void *stream);
+
+/* ---- fused small-MLP path (weights resident in shared memory) -------------- */
+/* rows per tile the fused kernels would use for this net (0 = does not fit). */
+int mq_fused_tile_rows(const mq_net_t *net, int with_grad);
+int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch);
+/* out[batch,n_out] and/or logp[batch] (Gaussian nets; needs sample) may be NULL */
+int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                     int64_t batch, float *out, const float *sample, float *logp, void *stream);
+/* forward + head + backward in one launch; grad[n_params] = scale * sum_batch */
+int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                  int64_t batch, const mq_head_t *head, float scale, float *grad, float *out,
+                  float *logp, void *ws, int64_t ws_bytes, void *stream);
+/* n_steps dependent {gather, forward, head, backward, Adam} steps in ONE launch
+ * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73).  idx_table[n_steps,mb].
+ * Adam state (value,m,v: state_dtype) and theta are updated in place; tw[2]
+ * holds the two running total weights (host doubles, updated on return). */
+int mq_fused_train(const mq_net_t *net, float *theta, void *value, void *m, void *v, int state_dtype,
+                   const float *x, const mq_head_t *head, const int32_t *idx_table, int32_t n_steps,
+                   int32_t mb, double beta1, double beta2, double *tw_host, double lr, double eps,
+                   void *stream);
+
+/* ---- evolution strategies: benchmarks/mutation.py:33-37 -------------------- */
+/* returns[p] = sum_t sum_a policy(theta+noise[p])(obs[t])[a]*ret_coef[a] */
+int mq_es_eval(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members,
+               const float *obs, int64_t n_obs, const float *ret_coef, float *returns, void *stream);
+/* out[j] = scale * sum_p noise[p,j]*w[p]   (fixed summation order) */
+int mq_es_weighted_sum(const float *noise, const double *w, int64_t n_members, int64_t n_params,
+                       double scale, double *out, void *ws, int64_t ws_bytes, void *stream);
+int64_t mq_es_ws_bytes(int64_t n_members, int64_t n_params);
+
+/* ---- per-op kernels for the general graph (mannequin/backprop.py:11-60,
+ *      mannequin/distrib.py:50-68, mnist/vae.py:13-34) ----------------------- */
+/* C[M,N] = alpha * opA(A)[M,K] @ opB(B)[K,N]; element strides in floats */
+int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs,
+            float *c, int64_t m, int64_t n, int64_t k, float alpha, void *stream);
+int mq_add_bias(const float *x, const float *b, float *y, int64_t rows, int64_t cols, void *stream);
+int mq_binary(const float *a, const float *b, float *out, int64_t n, int64_t b_period, int op,
+              void *stream);                   /* op 0: a+b, 1: a*b; b is broadcast with period */
+/* out[c] = scale * sum_r g[r,c] * (a ? a[r,c] : 1) */
+int mq_col_sum(const float *g, const float *a, int64_t rows, int64_t cols, float scale, float *out,
+               void *stream);
+int mq_act_forward(const float *x, float *y, int64_t n, int act, float leak, void *stream);
+int mq_act_backward(const float *y, const float *g, float *out, int64_t n, int act, float leak,
+                    void *stream);
+int mq_clip_forward(const float *x, float *y, int64_t n, float lo, float hi, void *stream);
+int mq_clip_backward(const float *x, const float *g, float *out, int64_t n, float lo, float hi,
+                     void *stream);
+/* logstd_period = A (shared Params(A)) or rows*A (per-row sub-network) */
+int mq_gauss_logprob(const float *mu, const float *logstd, int64_t logstd_period, const float *sample,
+                     int64_t rows, int64_t a, float *logp, void *stream);
+int mq_gauss_logprob_bwd(const float *mu, const float *logstd, int64_t logstd_period,
+                         const float *sample, const float *g, int64_t rows, int64_t a, float *d_mu,
+                         float *d_logstd_rows, void *stream);
+int mq_gauss_sample(const float *mu, const float *logstd, int64_t logstd_period, const float *unit,
+                    int64_t rows, int64_t a, float *out, float *noise, void *stream);
+int mq_dkl_forward(const float *mean, const float *logstd, int64_t rows, int64_t d, float *out,
+                   void *stream);
+int mq_dkl_backward(const float *mean, const float *logstd, const float *g, int64_t rows, int64_t d,
+                    float *d_mean, float *d_logstd, void *stream);
+int mq_softmax_ce_grad(const float *logits, const float *onehot, const int32_t *row_idx,
+                       int64_t rows, int64_t cols, float l2, float *dy, void *stream);
+/* ppo.py:33-37: w = exp(logp-logp_old[idx]) with the clip rule, times adv[idx] */
+int mq_ppo_weight(const float *logp, const float *logp_old, const float *adv, const int32_t *row_idx,
+                  int64_t rows, float lo, float hi, float *w, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQ_B200_H */

@@ -1,0 +1,142 @@
+"""ctypes binding of libmq_b200.so (include/mq_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present,
+every numeric entry point of this package raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmq_b200.so")
+
+MQ_OK, MQ_ERR_INVALID, MQ_ERR_SHAPE, MQ_ERR_UNSUPPORTED, MQ_ERR_CUDA = 0, -1, -2, -3, -4
+MQ_F32, MQ_F64 = 0, 1
+ACT_NONE, ACT_TANH, ACT_LRELU = 0, 1, 2
+HEAD_DY, HEAD_DIFF, HEAD_SOFTMAX_CE, HEAD_GAUSS_LOGP, HEAD_GAUSS_PPO = 0, 1, 2, 3, 4
+MAX_LAYERS = 8
+
+
+class MqNet(ctypes.Structure):
+    _fields_ = [("n_layers", c_int32), ("n_in", c_int32), ("n_out", c_int32),
+                ("n_params", c_int32), ("logstd_off", c_int32),
+                ("in_", c_int32 * MAX_LAYERS), ("out", c_int32 * MAX_LAYERS),
+                ("act", c_int32 * MAX_LAYERS), ("leak", c_float * MAX_LAYERS),
+                ("w_off", c_int32 * MAX_LAYERS), ("b_off", c_int32 * MAX_LAYERS)]
+
+
+class MqHead(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("p0", c_float), ("p1", c_float), ("dy", c_void_p),
+                ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p)]
+
+
+P = c_void_p
+NETP = POINTER(MqNet)
+HEADP = POINTER(MqHead)
+
+SIGNATURES = {
+    "mq_last_error": (c_char_p, []),
+    "mq_version": (c_int, []),
+    "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
+    "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
+                             c_double, c_int, P]),
+    "mq_running_mean_update": (c_int, [P, P, c_int, c_int64, c_double, P, P]),
+    "mq_norm_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "mq_col_mean": (c_int, [P, c_int, c_int64, c_int64, P, P, c_int64, P]),
+    "mq_norm_cov": (c_int, [P, c_int, c_int64, c_int64, P, P, c_double, P, P, c_int64, P]),
+    "mq_norm_apply": (c_int, [P, c_int, c_int64, c_int64, P, P, P, c_int, c_int, P]),
+    "mq_gather_rows": (c_int, [P, P, c_int64, c_int64, c_int64, P, P]),
+    "mq_scan_ws_bytes": (c_int64, [c_int64]),
+    "mq_gae": (c_int, [P, P, P, c_int64, c_double, c_double, P, P, P, c_int64, P]),
+    "mq_discounted": (c_int, [P, c_int64, c_double, P, P, c_int64, P]),
+    "mq_mlp_acts_floats": (c_int64, [NETP, c_int64]),
+    "mq_mlp_ws_bytes": (c_int64, [NETP, c_int64]),
+    "mq_mlp_forward": (c_int, [NETP, P, P, P, c_int64, P, P]),
+    "mq_mlp_backward": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, P, c_int64, P]),
+    "mq_fused_tile_rows": (c_int, [NETP, c_int]),
+    "mq_fused_ws_bytes": (c_int64, [NETP, c_int64]),
+    "mq_fused_forward": (c_int, [NETP, P, P, P, c_int64, P, P, P, P]),
+    "mq_fused_grad": (c_int, [NETP, P, P, P, c_int64, HEADP, c_float, P, P, P, P, c_int64, P]),
+    "mq_fused_train": (c_int, [NETP, P, P, P, P, c_int, P, HEADP, P, c_int32, c_int32, c_double,
+                               c_double, POINTER(c_double), c_double, c_double, P]),
+    "mq_es_eval": (c_int, [NETP, P, P, c_int64, P, c_int64, P, P, P]),
+    "mq_es_weighted_sum": (c_int, [P, P, c_int64, c_int64, c_double, P, P, c_int64, P]),
+    "mq_es_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "mq_gemm": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64,
+                        c_float, P]),
+    "mq_add_bias": (c_int, [P, P, P, c_int64, c_int64, P]),
+    "mq_binary": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
+    "mq_col_sum": (c_int, [P, P, c_int64, c_int64, c_float, P, P]),
+    "mq_act_forward": (c_int, [P, P, c_int64, c_int, c_float, P]),
+    "mq_act_backward": (c_int, [P, P, P, c_int64, c_int, c_float, P]),
+    "mq_clip_forward": (c_int, [P, P, c_int64, c_float, c_float, P]),
+    "mq_clip_backward": (c_int, [P, P, P, c_int64, c_float, c_float, P]),
+    "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
+    "mq_gauss_logprob_bwd": (c_int, [P, P, c_int64, P, P, c_int64, c_int64, P, P, P]),
+    "mq_gauss_sample": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P, P]),
+    "mq_dkl_forward": (c_int, [P, P, c_int64, c_int64, P, P]),
+    "mq_dkl_backward": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
+    "mq_softmax_ce_grad": (c_int, [P, P, P, c_int64, c_int64, c_float, P, P]),
+    "mq_ppo_weight": (c_int, [P, P, P, P, c_int64, c_float, c_float, P, P]),
+}
+
+
+def bind(cdll):
+    """Attach argtypes/restype for every symbol include/mq_b200.h declares."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(cdll, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+_lib = None
+
+
+def lib():
+    """The loaded CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "mannequin2_b200: %s is missing -- build it with "
+                "`python -m mannequin2_b200.build` (there is no CPU fallback)" % LIB_PATH)
+        _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+class MqError(RuntimeError):
+    pass
+
+
+def check(rc, cdll=None):
+    """Map MQ_ERR_* to the exception types the reference raises."""
+    if rc == MQ_OK:
+        return
+    msg = (cdll or lib()).mq_last_error().decode("utf-8", "replace")
+    if rc == MQ_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == MQ_ERR_SHAPE:
+        raise AssertionError(msg)
+    if rc == MQ_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise MqError(msg)
+
+
+def make_net(n_in, widths, acts, leak=0.1, logstd=False):
+    """mq_net_t for Input(n_in) -> Affine(w)+act ... in the reference's flat layout."""
+    if len(widths) > MAX_LAYERS:
+        raise NotImplementedError("at most %d Affine layers" % MAX_LAYERS)
+    net = MqNet()
+    net.n_layers, net.n_in = len(widths), int(n_in)
+    pos, k = 0, int(n_in)
+    leaks = leak if isinstance(leak, (list, tuple)) else [leak] * len(widths)
+    for l, (n, a) in enumerate(zip(widths, acts)):
+        net.in_[l], net.out[l], net.act[l], net.leak[l] = k, int(n), int(a), float(leaks[l])
+        net.w_off[l], net.b_off[l] = pos, pos + k * int(n)
+        pos += k * int(n) + int(n)
+        k = int(n)
+    net.n_out = k
+    net.logstd_off = pos if logstd else -1
+    net.n_params = pos + (k if logstd else 0)
+    return net

@@ -1,0 +1,85 @@
+// Shared helpers for the mq_b200 kernels (sm_100a).
+#pragma once
+
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/mq_b200.h"
+
+#ifdef MQ_EMU
+// Developer-only host emulation (tools/emu): lets the kernel *logic* be checked
+// on a machine without a GPU.  Never built into the product library.
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define MQ_SHARED_BYTES(name) extern __shared__ __align__(16) unsigned char name[]
+#define MQ_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+#define MQ_NT 256  // threads per CTA used by every kernel in this library
+
+// ---- host-side error plumbing ------------------------------------------------
+void mq_set_error(const char *fmt, ...);
+
+#define MQ_REQUIRE(cond, code, ...)        \
+    do {                                   \
+        if (!(cond)) {                     \
+            mq_set_error(__VA_ARGS__);     \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+int mq_check_launch(const char *what);
+#define MQ_CHECK_LAUNCH(what)                  \
+    do {                                       \
+        int mq_rc_ = mq_check_launch(what);    \
+        if (mq_rc_ != MQ_OK) return mq_rc_;    \
+    } while (0)
+
+int mq_sm_count();
+int64_t mq_smem_optin();
+
+static inline int64_t mq_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t mq_round_up(int64_t a, int64_t b) { return mq_ceil_div(a, b) * b; }
+
+// ---- device helpers -----------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T mq_warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the CTA (MQ_NT threads); result valid in every thread.  `red` must
+// hold MQ_NT/32 elements of T in shared memory.  Fixed order => deterministic.
+template <typename T>
+__device__ __forceinline__ T mq_block_sum(T v, T *red) {
+    v = mq_warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    T s = red[0];
+#pragma unroll
+    for (int w = 1; w < MQ_NT / 32; ++w) s += red[w];
+    return s;
+}
+
+__device__ __forceinline__ float mq_act_apply(float z, int act, float leak) {
+    if (act == MQ_ACT_TANH) return tanhf(z);
+    if (act == MQ_ACT_LRELU) return z < 0.0f ? z * leak : z;
+    return z;
+}
+
+// derivative expressed through the saved OUTPUT y (backprop.py:53-60)
+__device__ __forceinline__ float mq_act_grad(float y, float g, int act, float leak) {
+    if (act == MQ_ACT_TANH) return g * (1.0f - y * y);
+    if (act == MQ_ACT_LRELU) {
+        const bool neg = (leak > 0.0f) ? (y < 0.0f) : (leak == 0.0f ? signbit(y) : (y > 0.0f));
+        return neg ? g * leak : g;
+    }
+    return g;
+}

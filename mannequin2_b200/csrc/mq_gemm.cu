@@ -1,0 +1,321 @@
+// Generic-stride FP32 GEMM with fused epilogues, and the layered MLP path on top.
+//
+// This is the path for Affine layers too large for the shared-memory-resident
+// fused kernels (mq_fused.cu), e.g. the 784x128 first layer of mnist/mlp.py,
+// and for `matmul` nodes of the general graph (mannequin/backprop.py:45-51).
+// FFMA register tiles (4x4 or 2x2 per thread), operand tiles staged in shared
+// memory, optional deterministic split-K, optional row gather on the batch axis
+// (mannequin/_trajectory.py:79-86 fused into the operand load).
+//
+// Epilogues (all mannequin/backprop.py):
+//   EPI_SCALE    C = alpha*acc                         (dW = x^T g / B, lines 48-51)
+//   EPI_BIAS_ACT C = act(acc + bias[n])                (add 11-19, relu 53-56, tanh 58-60)
+//   EPI_ACT_GRAD C = act'(Y[m,n]) * acc                (g W^T through the previous activation)
+#include "mq_common.cuh"
+
+#define GEMM_BK 16
+#define EPI_SCALE 0
+#define EPI_BIAS_ACT 1
+#define EPI_ACT_GRAD 2
+
+struct GemmArgs {
+    const float *a; int64_t a_rs, a_cs;
+    const float *b; int64_t b_rs, b_cs;
+    const int32_t *idx;      // gather on the batch axis of A (or NULL)
+    int idx_on_k;            // 0: index applies to A rows (m), 1: to A columns (k)
+    float *c;                // [M,N] row-major (or split-K partials [S,M,N])
+    int64_t m, n, k;
+    int64_t k_per_split;
+    float alpha;
+    int epi, act; float leak;
+    const float *bias;       // EPI_BIAS_ACT
+    const float *y;          // EPI_ACT_GRAD, [M,N] row-major
+};
+
+__device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int64_t m, int64_t n) {
+    if (g.epi == EPI_BIAS_ACT) return mq_act_apply(acc + g.bias[n], g.act, g.leak);
+    if (g.epi == EPI_ACT_GRAD) return mq_act_grad(g.y[m * g.n + n], acc, g.act, g.leak);
+    return g.alpha * acc;
+}
+
+template <int BM, int BN, bool SPLIT>
+__global__ void __launch_bounds__(MQ_NT)
+gemm_kernel(GemmArgs g) {
+    constexpr int TM = BM / 16, TN = BN / 16;
+    __shared__ __align__(16) float As[GEMM_BK][BM + 4];
+    __shared__ __align__(16) float Bs[GEMM_BK][BN + 4];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int64_t k_begin = (int64_t)blockIdx.z * g.k_per_split;
+    const int64_t k_end = (k_begin + g.k_per_split < g.k) ? k_begin + g.k_per_split : g.k;
+    constexpr int LA = BM * GEMM_BK / MQ_NT, LB = BN * GEMM_BK / MQ_NT;
+    float ra[LA], rb[LB];
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    const bool a_kfast = (g.a_cs == 1);
+    const bool b_nfast = (g.b_cs == 1);
+
+    auto load_tiles = [&](int64_t kt) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int e = t + i * MQ_NT;
+            const int mm = a_kfast ? e / GEMM_BK : e % BM;
+            const int kk = a_kfast ? e % GEMM_BK : e / BM;
+            int64_t gm = m0 + mm, gk = kt + kk;
+            float v = 0.0f;
+            if (gm < g.m && gk < k_end) {
+                if (g.idx) { if (g.idx_on_k) gk = g.idx[gk]; else gm = g.idx[gm]; }
+                v = g.a[gm * g.a_rs + gk * g.a_cs];
+            }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int e = t + i * MQ_NT;
+            const int kk = b_nfast ? e / BN : e % GEMM_BK;
+            const int nn = b_nfast ? e % BN : e / GEMM_BK;
+            const int64_t gk = kt + kk, gn = n0 + nn;
+            rb[i] = (gk < k_end && gn < g.n) ? g.b[gk * g.b_rs + gn * g.b_cs] : 0.0f;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int e = t + i * MQ_NT;
+            const int mm = a_kfast ? e / GEMM_BK : e % BM;
+            const int kk = a_kfast ? e % GEMM_BK : e / BM;
+            As[kk][mm] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int e = t + i * MQ_NT;
+            const int kk = b_nfast ? e / BN : e % GEMM_BK;
+            const int nn = b_nfast ? e % BN : e / GEMM_BK;
+            Bs[kk][nn] = rb[i];
+        }
+    };
+
+    if (k_begin < k_end) {
+        load_tiles(k_begin);
+        store_tiles();
+        __syncthreads();
+        for (int64_t kt = k_begin; kt < k_end; kt += GEMM_BK) {
+            const bool more = kt + GEMM_BK < k_end;
+            if (more) load_tiles(kt + GEMM_BK);
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK; ++kk) {
+                float av[TM], bv[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+            if (more) { store_tiles(); __syncthreads(); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t gm = m0 + ty * TM + i;
+        if (gm >= g.m) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int64_t gn = n0 + tx * TN + j;
+            if (gn >= g.n) continue;
+            if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = acc[i][j];
+            else g.c[gm * g.n + gn] = gemm_epilogue(g, acc[i][j], gm, gn);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MQ_NT)
+gemm_splitk_finish_kernel(GemmArgs g, const float *__restrict__ partial, int splits, float *__restrict__ c) {
+    const int64_t total = g.m * g.n;
+    for (int64_t e = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * MQ_NT) {
+        float s = 0.0f;
+        for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + e];
+        c[e] = gemm_epilogue(g, s, e / g.n, e % g.n);
+    }
+}
+
+// Decide tile size and split-K; `ws` may be NULL (then no split).
+static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, void *stream, const char *what) {
+    if (g.m <= 0 || g.n <= 0) return MQ_OK;
+    const int sms = mq_sm_count();
+    const bool big = mq_ceil_div(g.m, 64) * mq_ceil_div(g.n, 64) >= sms / 2;
+    const int bm = big ? 64 : 32;
+    const int64_t tiles = mq_ceil_div(g.m, bm) * mq_ceil_div(g.n, bm);
+    int64_t splits = 1;
+    if (ws && tiles < sms && g.k >= 512) {
+        splits = mq_ceil_div(2 * sms, tiles);
+        if (splits > g.k / 128) splits = g.k / 128;
+        if (splits > 64) splits = 64;
+        while (splits > 1 && splits * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) --splits;
+        if (splits < 1) splits = 1;
+    }
+    g.k_per_split = mq_round_up(mq_ceil_div(g.k > 0 ? g.k : 1, splits), GEMM_BK);
+    splits = mq_ceil_div(g.k > 0 ? g.k : 1, g.k_per_split);
+    dim3 grid((unsigned)mq_ceil_div(g.n, bm), (unsigned)mq_ceil_div(g.m, bm), (unsigned)splits);
+    float *c_final = g.c;
+    if (splits > 1) {
+        g.c = (float *)ws;
+        if (big) { auto kfn = gemm_kernel<64, 64, true>; MQ_LAUNCH(kfn, grid, MQ_NT, 0, stream, g); }
+        else { auto kfn = gemm_kernel<32, 32, true>; MQ_LAUNCH(kfn, grid, MQ_NT, 0, stream, g); }
+        int64_t nb = mq_ceil_div(g.m * g.n, MQ_NT);
+        if (nb > sms * 8) nb = sms * 8;
+        MQ_LAUNCH(gemm_splitk_finish_kernel, (unsigned)nb, MQ_NT, 0, stream, g, (const float *)ws,
+                  (int)splits, c_final);
+    } else {
+        if (big) { auto kfn = gemm_kernel<64, 64, false>; MQ_LAUNCH(kfn, grid, MQ_NT, 0, stream, g); }
+        else { auto kfn = gemm_kernel<32, 32, false>; MQ_LAUNCH(kfn, grid, MQ_NT, 0, stream, g); }
+    }
+    MQ_CHECK_LAUNCH(what);
+    return MQ_OK;
+}
+
+extern "C" int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs,
+                       int64_t b_cs, float *c, int64_t m, int64_t n, int64_t k, float alpha,
+                       void *stream) {
+    MQ_REQUIRE(m >= 0 && n >= 0 && k >= 0, MQ_ERR_SHAPE, "mq_gemm: negative size");
+    MQ_REQUIRE((m == 0 || n == 0) || (a && b && c), MQ_ERR_INVALID, "mq_gemm: null pointer");
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.a = a; g.a_rs = a_rs; g.a_cs = a_cs; g.b = b; g.b_rs = b_rs; g.b_cs = b_cs;
+    g.c = c; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.epi = EPI_SCALE;
+    return gemm_run(g, nullptr, 0, stream, "mq_gemm");
+}
+
+// ---- layered MLP path --------------------------------------------------------------
+static int net_check(const mq_net_t *net, const char *what) {
+    MQ_REQUIRE(net, MQ_ERR_INVALID, "%s: null net", what);
+    MQ_REQUIRE(net->n_layers >= 1 && net->n_layers <= MQ_MAX_LAYERS, MQ_ERR_SHAPE,
+               "%s: n_layers=%d out of range", what, net->n_layers);
+    int k = net->n_in;
+    for (int l = 0; l < net->n_layers; ++l) {
+        MQ_REQUIRE(net->in[l] == k && net->out[l] >= 1 && k >= 1, MQ_ERR_SHAPE,
+                   "%s: layer %d shape mismatch", what, l);
+        MQ_REQUIRE(net->act[l] >= 0 && net->act[l] <= 2, MQ_ERR_INVALID, "%s: layer %d activation", what, l);
+        k = net->out[l];
+    }
+    MQ_REQUIRE(k == net->n_out, MQ_ERR_SHAPE, "%s: n_out mismatch", what);
+    return MQ_OK;
+}
+
+static int64_t net_max_width(const mq_net_t *net) {
+    int64_t w = net->n_in;
+    for (int l = 0; l < net->n_layers; ++l) if (net->out[l] > w) w = net->out[l];
+    return w;
+}
+
+extern "C" int64_t mq_mlp_acts_floats(const mq_net_t *net, int64_t batch) {
+    int64_t s = 0;
+    for (int l = 0; l < net->n_layers; ++l) s += (int64_t)net->out[l] * batch;
+    return s;
+}
+
+extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
+    int64_t max_w = 0;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const int64_t w = (int64_t)net->in[l] * net->out[l];
+        if (w > max_w) max_w = w;
+    }
+    return (2 * batch * net_max_width(net) + 64 * max_w) * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x,
+                              const int32_t *row_idx, int64_t batch, float *acts, void *stream) {
+    int rc = net_check(net, "mq_mlp_forward");
+    if (rc != MQ_OK) return rc;
+    MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_mlp_forward: negative batch");
+    if (batch == 0) return MQ_OK;
+    MQ_REQUIRE(theta && x && acts, MQ_ERR_INVALID, "mq_mlp_forward: null pointer");
+    const float *inp = x;
+    float *out = acts;
+    for (int l = 0; l < net->n_layers; ++l) {
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.a = inp; g.a_rs = net->in[l]; g.a_cs = 1;
+        g.idx = (l == 0) ? row_idx : nullptr; g.idx_on_k = 0;
+        g.b = theta + net->w_off[l]; g.b_rs = net->out[l]; g.b_cs = 1;
+        g.c = out; g.m = batch; g.n = net->out[l]; g.k = net->in[l];
+        g.alpha = 1.0f; g.epi = EPI_BIAS_ACT; g.act = net->act[l]; g.leak = net->leak[l];
+        g.bias = theta + net->b_off[l];
+        rc = gemm_run(g, nullptr, 0, stream, "mq_mlp_forward");
+        if (rc != MQ_OK) return rc;
+        inp = out;
+        out += (int64_t)net->out[l] * batch;
+    }
+    return MQ_OK;
+}
+
+extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const float *x,
+                               const int32_t *row_idx, const float *acts, float *dy, int64_t batch,
+                               float scale, float *grad, float *dx, void *ws, int64_t ws_bytes,
+                               void *stream) {
+    int rc = net_check(net, "mq_mlp_backward");
+    if (rc != MQ_OK) return rc;
+    MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_mlp_backward: empty batch");
+    MQ_REQUIRE(theta && x && acts && dy && grad && ws, MQ_ERR_INVALID, "mq_mlp_backward: null pointer");
+    MQ_REQUIRE(ws_bytes >= mq_mlp_ws_bytes(net, batch), MQ_ERR_SHAPE, "mq_mlp_backward: workspace too small");
+    const int L = net->n_layers;
+    const int64_t maxw = net_max_width(net);
+    float *gbuf[2] = {(float *)ws, (float *)ws + batch * maxw};
+    float *split_ws = (float *)ws + 2 * batch * maxw;
+    const int64_t split_bytes = ws_bytes - 2 * batch * maxw * (int64_t)sizeof(float);
+
+    // offsets of each layer's saved output inside acts
+    int64_t off[MQ_MAX_LAYERS];
+    int64_t s = 0;
+    for (int l = 0; l < L; ++l) { off[l] = s; s += (int64_t)net->out[l] * batch; }
+
+    float *g_cur = dy;
+    if (net->act[L - 1] != MQ_ACT_NONE) {
+        rc = mq_act_backward(acts + off[L - 1], dy, dy, batch * net->out[L - 1], net->act[L - 1],
+                             net->leak[L - 1], stream);
+        if (rc != MQ_OK) return rc;
+    }
+    int flip = 0;
+    for (int l = L - 1; l >= 0; --l) {
+        const float *inp = (l == 0) ? x : acts + off[l - 1];
+        // dW = scale * inp^T g      A(m=in, k=batch) = inp[k*in + m]
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.a = inp; g.a_rs = 1; g.a_cs = net->in[l];
+        g.idx = (l == 0) ? row_idx : nullptr; g.idx_on_k = 1;
+        g.b = g_cur; g.b_rs = net->out[l]; g.b_cs = 1;
+        g.c = grad + net->w_off[l]; g.m = net->in[l]; g.n = net->out[l]; g.k = batch;
+        g.alpha = scale; g.epi = EPI_SCALE;
+        rc = gemm_run(g, split_ws, split_bytes, stream, "mq_mlp_backward(dW)");
+        if (rc != MQ_OK) return rc;
+        rc = mq_col_sum(g_cur, nullptr, batch, net->out[l], scale, grad + net->b_off[l], stream);
+        if (rc != MQ_OK) return rc;
+        if (l > 0 || dx) {
+            // g_prev = (g W^T) * act'(saved output of layer l-1)     B(k=out, n=in) = W[n*out + k]
+            float *dst = (l == 0) ? dx : gbuf[flip];
+            memset(&g, 0, sizeof(g));
+            g.a = g_cur; g.a_rs = net->out[l]; g.a_cs = 1;
+            g.b = theta + net->w_off[l]; g.b_rs = 1; g.b_cs = net->out[l];
+            g.c = dst; g.m = batch; g.n = net->in[l]; g.k = net->out[l];
+            g.alpha = 1.0f;
+            if (l > 0 && net->act[l - 1] != MQ_ACT_NONE) {
+                g.epi = EPI_ACT_GRAD; g.act = net->act[l - 1]; g.leak = net->leak[l - 1];
+                g.y = acts + off[l - 1];
+            } else {
+                g.epi = EPI_SCALE;
+            }
+            rc = gemm_run(g, nullptr, 0, stream, "mq_mlp_backward(dX)");
+            if (rc != MQ_OK) return rc;
+            g_cur = dst;
+            flip ^= 1;
+        }
+    }
+    return MQ_OK;
+}
