@@ -1,0 +1,134 @@
+"""RunningMean / RunningNormalize (mannequin/_normalize.py:4-81) on the device.
+
+The statistics (fp64 mean / variance vectors) live in device memory and every
+pass over the data is a kernel from csrc/mq_norm.cu / mq_adam.cu.  Only the
+data-independent scalars -- total weights, sample count, which branch of the
+update applies -- are tracked on the host, exactly as the reference computes
+them (they depend on batch sizes and weights alone).
+"""
+import numpy as np
+import torch
+
+from . import _device as D
+from ._lib import MQ_F32, MQ_F64
+
+
+def _code(t):
+    return MQ_F64 if t.dtype == torch.float64 else MQ_F32
+
+
+def _dev_in(values):
+    """float32 device data stays float32 (exactly representable in fp64)."""
+    if isinstance(values, D.DeviceVector):
+        values = values.dev()
+    if D.is_dev(values):
+        return values if values.dtype in (torch.float32, torch.float64) else values.to(torch.float64)
+    a = np.asarray(values)
+    return D.from_host(a.reshape(-1), np.float32 if a.dtype == np.float32 else np.float64)
+
+
+class RunningMean(object):
+    def __init__(self, shape=(), *, horizon=None):
+        self._shape = tuple(np.zeros(shape).shape)
+        self._n = int(np.prod(self._shape)) if self._shape else 1
+        self._mean = D.zeros(self._n, torch.float64)
+        self._tw = 0.0
+        self._horizon = horizon
+
+    def _coef(self, weight):
+        weight = float(weight)
+        assert weight >= 0.0
+        if self._horizon is not None:
+            self._tw *= np.power(1.0 - 1.0 / float(self._horizon), weight)
+        self._tw += weight
+        return weight / self._tw
+
+    def update(self, values, *, weight=1.0, _old_out=None):
+        x = _dev_in(values)
+        assert x.numel() == self._n
+        coef = self._coef(weight)
+        D.call("mq_running_mean_update", D.ptr(self._mean), D.ptr(x), _code(x), self._n, coef,
+               D.ptr(_old_out), D.stream())
+
+    def get_dev(self):
+        return self._mean
+
+    def get(self):
+        return D.to_host(self._mean).reshape(self._shape)
+
+    def __call__(self, values, **kwargs):
+        self.update(values, **kwargs)
+        return self.get()
+
+
+class RunningNormalize(object):
+    def __init__(self, shape=(), *, horizon=None):
+        self._shape = tuple(np.zeros(shape).shape)
+        self._d = int(np.prod(self._shape)) if self._shape else 1
+        self._mean = RunningMean(self._shape, horizon=horizon)
+        self._var = RunningMean(self._shape, horizon=horizon)
+        self._old = D.zeros(self._d, torch.float64)
+        self._tmp = D.zeros(self._d, torch.float64)
+        self._n_samples = 0
+
+    # -- device-level API (used by the fused PPO / ES drivers) -------------------
+    def update_dev(self, x, rows):
+        """x: device float32/float64 tensor holding rows*D values."""
+        lib = D._lib.lib()
+        d = self._d
+        wsb = lib.mq_norm_ws_bytes(rows, d)
+        ws = D.workspace("norm", wsb)
+        D.call("mq_col_mean", D.ptr(x), _code(x), rows, d, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
+        self._mean.update(self._tmp, _old_out=self._old)          # one weight-1 update per batch
+        weight, scale = None, 1.0
+        if self._n_samples >= 1:
+            weight = 1.0
+        elif rows >= 2:
+            weight = (rows - 1.0) / rows                          # _normalize.py:50-55
+            scale = 1.0 / weight
+        if weight is not None:
+            D.call("mq_norm_cov", D.ptr(x), _code(x), rows, d, D.ptr(self._old),
+                   D.ptr(self._mean.get_dev()), scale, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
+            self._var.update(self._tmp, weight=weight)
+        self._n_samples += rows
+
+    def apply_dev(self, x, rows, out=None, fuse_tanh=False, out_dtype=torch.float64):
+        if out is None:
+            out = torch.empty(rows * self._d, dtype=out_dtype, device=x.device)
+        if self._n_samples < 2:
+            out.zero_()
+            return out
+        D.call("mq_norm_apply", D.ptr(x), _code(x), rows, self._d, D.ptr(self._mean.get_dev()),
+               D.ptr(self._var.get_dev()), D.ptr(out), _code(out), 1 if fuse_tanh else 0, D.stream())
+        return out
+
+    # -- reference API -----------------------------------------------------------
+    def update(self, value):
+        a = np.asarray(value) if not D.is_dev(value) else None
+        x = _dev_in(value)
+        assert x.numel() % self._d == 0
+        self.update_dev(x, x.numel() // self._d)
+
+    def apply(self, value):
+        if self._n_samples < 2:
+            return np.zeros_like(value, dtype=np.float64)
+        shape = np.shape(value)
+        x = _dev_in(value)
+        assert x.numel() % self._d == 0
+        out = self.apply_dev(x, x.numel() // self._d)
+        return D.to_host(out).reshape(shape)
+
+    def get_mean(self):
+        return self._mean.get()
+
+    def get_var(self):
+        if self._n_samples < 2:
+            return np.ones(self._shape, dtype=np.float64)
+        return self._var.get()
+
+    def get_std(self):
+        return np.sqrt(self.get_var())
+
+    def __call__(self, value):
+        self.update(value)
+        return self.apply(value)

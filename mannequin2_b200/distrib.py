@@ -1,0 +1,94 @@
+"""Distributions with the API of mannequin/distrib.py.
+
+Gauss (distrib.py:41-76): diagonal Gaussian with a learnt state-independent
+logstd `Params(A)` (or a logstd sub-network).  `logprob` uses the closed-form
+derivative of distrib.py:61-68 in device kernels instead of the `autograd`
+package; `sample` is reparameterised with host-drawn N(0,1) noise (the reference
+draws from an OS-seeded RandomState, distrib.py:46, so the draw itself is an
+input of the kernel).
+"""
+import numpy as np
+import torch
+
+from . import _device as D
+from ._utils import endswith
+from .basicnet import Function, Params
+
+
+def _period(mean_v, logstd_v):
+    if tuple(mean_v.shape) == tuple(logstd_v.shape):
+        return mean_v.numel()
+    if endswith(tuple(mean_v.shape), tuple(logstd_v.shape)):
+        return logstd_v.numel()
+    raise ValueError("Invalid shapes: %s, %s" % (tuple(mean_v.shape), tuple(logstd_v.shape)))
+
+
+def _reduce_to(g, shape):
+    cols = int(np.prod(shape))
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=g.device)
+    D.call("mq_col_sum", D.ptr(g.contiguous()), None, g.numel() // cols, cols, 1.0, D.ptr(out), D.stream())
+    return out
+
+
+class Gauss(object):
+    def __init__(self, *, mean, logstd=None):
+        logstd = logstd or Params(*mean.shape)
+        assert logstd.shape == mean.shape
+        rng = np.random.RandomState()
+        n_act = int(np.prod(mean.shape))
+
+        def sample(mean_v, logstd_v):
+            mean_v, logstd_v = mean_v.contiguous(), logstd_v.contiguous()
+            period = _period(mean_v, logstd_v)
+            unit = D.from_host(rng.randn(*mean_v.shape), np.float32)
+            out, noise = torch.empty_like(mean_v), torch.empty_like(mean_v)
+            D.call("mq_gauss_sample", D.ptr(mean_v), D.ptr(logstd_v), period, D.ptr(unit),
+                   mean_v.numel() // n_act, n_act, D.ptr(out), D.ptr(noise), D.stream())
+            same = tuple(mean_v.shape) == tuple(logstd_v.shape)
+
+            def bpp(g):
+                gn = torch.empty_like(g)
+                D.call("mq_binary", D.ptr(g.contiguous()), D.ptr(noise), D.ptr(gn), g.numel(), g.numel(),
+                       1, D.stream())
+                return (g, gn if same else _reduce_to(gn, logstd_v.shape))
+            return out, bpp
+        sample._mq_dev = True
+        sample._mq_op = ("gauss_sample",)
+
+        def logprob(mean_v, logstd_v, *, sample):
+            mean_v, logstd_v = mean_v.contiguous(), logstd_v.contiguous()
+            period = _period(mean_v, logstd_v)
+            rows = mean_v.numel() // n_act
+            batch_shape = tuple(mean_v.shape)[:mean_v.dim() - len(mean.shape)]
+            s = D.from_host(np.asarray(sample, dtype=np.float32).reshape(-1))
+            assert s.numel() == mean_v.numel()
+            logp = torch.empty(batch_shape, dtype=torch.float32, device=mean_v.device)
+            D.call("mq_gauss_logprob", D.ptr(mean_v), D.ptr(logstd_v), period, D.ptr(s), rows, n_act,
+                   D.ptr(logp), D.stream())
+            same = tuple(mean_v.shape) == tuple(logstd_v.shape)
+
+            def bpp(g):
+                d_mu, d_ls = torch.empty_like(mean_v), torch.empty_like(mean_v)
+                D.call("mq_gauss_logprob_bwd", D.ptr(mean_v), D.ptr(logstd_v), period, D.ptr(s),
+                       D.ptr(g.contiguous()), rows, n_act, D.ptr(d_mu), D.ptr(d_ls), D.stream())
+                return (d_mu, d_ls if same else _reduce_to(d_ls, logstd_v.shape))
+            return logp, bpp
+        logprob._mq_dev = True
+        logprob._mq_op = ("gauss_logprob",)
+
+        self.mean = mean
+        self.logstd = logstd
+        self.sample = Function(mean, logstd, f=sample, shape=mean.shape)
+        self.logprob = Function(mean, logstd, f=logprob, shape=())
+        self.n_params = self.logprob.n_params
+        self.get_params = self.logprob.get_params
+        self.load_params = self.logprob.load_params
+
+
+class Discrete(object):
+    """Softmax categorical head (mannequin/distrib.py:8-39).
+
+    SURVEY.md 8f rank 1 ("next" row): not built in this round."""
+
+    def __init__(self, *, logits):
+        raise NotImplementedError("Discrete policy head is not implemented yet (SURVEY.md 8f rank 1)")

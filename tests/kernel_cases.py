@@ -1,0 +1,575 @@
+"""Kernel parity cases: the C-ABI (include/mq_b200.h) against the CPU oracle.
+
+Each case takes a backend `B` with
+    B.lib            bound library (mannequin2_b200._lib.bind)
+    B.up(a)          host ndarray -> buffer handle
+    B.zeros(shape,dtype) -> buffer handle
+    B.ptr(h)         address to pass through ctypes (None stays None)
+    B.down(h)        buffer handle -> host ndarray (synchronises)
+`tests/test_kernels_gpu.py` runs them on a B200 with device buffers (the parity
+tests proper); `tools/emu/check_kernels.py` runs the same cases on the
+developer-only host emulation.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from mannequin2_b200 import _lib as L
+from oracle import mq_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def ok(B, rc):
+    if rc != 0:
+        raise RuntimeError("rc=%d: %s" % (rc, B.lib.mq_last_error().decode()))
+
+
+def close(a, b, rtol=1e-5, atol_scale=2e-6, what=""):
+    """allclose(rtol, atol = atol_scale*max|ref|): the fp32 FFMA bar of BASELINE.md 3.6."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    atol = atol_scale * max(1e-30, np.max(np.abs(b)))
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    if not (err <= 0).all():
+        i = np.argmax(err)
+        raise AssertionError("%s: mismatch at %d: got %r want %r (max|ref|=%g)" % (
+            what, i, a.reshape(-1)[i], b.reshape(-1)[i], np.max(np.abs(b))))
+
+
+def net_of(spec, logstd=False):
+    Ls = spec["layers"]
+    return L.make_net(spec["n_in"], [l["n_out"] for l in Ls], [l["act"] for l in Ls],
+                      leak=[l["leak"] for l in Ls], logstd=logstd)
+
+
+def head(B, kind, p0=0.0, p1=0.0, dy=None, target=None, adv=None, logp_old=None):
+    h = L.MqHead()
+    h.kind, h.p0, h.p1 = kind, p0, p1
+    h.dy, h.target, h.adv, h.logp_old = B.ptr(dy), B.ptr(target), B.ptr(adv), B.ptr(logp_old)
+    h._keep = (dy, target, adv, logp_old)
+    return h
+
+
+def mlp_case(rs, n_in, widths, acts, batch):
+    spec = O.mlp_spec(n_in, widths, acts)
+    theta = O.mlp_init(spec, rs, head_scale=0.1) + rs.randn(spec["n_params"]).astype(np.float32) * 0.05
+    x = rs.randn(batch, n_in).astype(np.float32)
+    return spec, theta, x
+
+
+# ------------------------------------------------------------------------- cases
+def case_adam(B):
+    """mannequin/_adam.py: fp64 state is bit-exact with the reference's op order."""
+    lib = B.lib
+    g = golden("adam")
+    for name, adams in (("adam", 0), ("adams", 1)):
+        vals = g[name + "_values"]
+        n = vals.shape[1]
+        val, m, v = B.up(vals[0].copy()), B.zeros(n, np.float64), B.zeros(n, np.float64)
+        th = B.zeros(n, np.float32)
+        tw1 = tw2 = 0.0
+        for grad, lr, want in zip(g[name + "_grads"], g[name + "_lrs"], vals[1:]):
+            tw1, tw2 = tw1 * 0.9 + 1.0, tw2 * 0.99 + 1.0
+            lr, eps = (0.003, 1e-8) if np.isnan(lr) else (float(lr), 1e-6)
+            hg = B.up(grad)
+            ok(B, lib.mq_adam_step(B.ptr(val), B.ptr(m), B.ptr(v), B.ptr(th), B.ptr(hg), n, L.MQ_F64,
+                                   L.MQ_F32, 1.0 / tw1, 1.0 / tw2, lr, eps, adams, B.stream))
+            assert np.array_equal(B.down(val), want), "fp64 %s must match the reference bit for bit" % name
+            assert np.array_equal(B.down(th), want.astype(np.float32))
+    rs = np.random.RandomState(0)
+    for n in (5, 37, 1024 + 3, 100003):
+        val0 = rs.randn(n)
+        grads = rs.randn(4, n).astype(np.float32)
+        ref = O.AdamO(val0, horizon=10, lr=0.003)
+        val, m, v = B.up(val0.copy()), B.zeros(n, np.float64), B.zeros(n, np.float64)
+        f32 = [B.up(val0.astype(np.float32)), B.zeros(n, np.float32), B.zeros(n, np.float32)]
+        tw1 = tw2 = 0.0
+        for grad in grads:
+            ref.apply_gradient(grad)
+            tw1, tw2 = tw1 * 0.9 + 1.0, tw2 * 0.99 + 1.0
+            hg = B.up(grad)
+            ok(B, lib.mq_adam_step(B.ptr(val), B.ptr(m), B.ptr(v), None, B.ptr(hg), n, L.MQ_F64, L.MQ_F32,
+                                   1.0 / tw1, 1.0 / tw2, 0.003, 1e-8, 0, B.stream))
+            ok(B, lib.mq_adam_step(B.ptr(f32[0]), B.ptr(f32[1]), B.ptr(f32[2]), None, B.ptr(hg), n,
+                                   L.MQ_F32, L.MQ_F32, 1.0 / tw1, 1.0 / tw2, 0.003, 1e-8, 0, B.stream))
+        assert np.array_equal(B.down(val), ref.get_value())
+        close(B.down(f32[0]), ref.get_value(), what="adam fp32 state n=%d" % n)
+    # fp64 gradient input (host scripts pass python lists, tests/adam.py)
+    val, m, v = B.up(np.array([10.0, -5.0])), B.zeros(2, np.float64), B.zeros(2, np.float64)
+    tw1 = tw2 = 0.0
+    for want in g["adam_kat1"]:
+        tw1, tw2 = tw1 * (1 - 1 / 3.0) + 1.0, tw2 * 0.99 + 1.0
+        hg = B.up(-B.down(val))
+        ok(B, lib.mq_adam_step(B.ptr(val), B.ptr(m), B.ptr(v), None, B.ptr(hg), 2, L.MQ_F64, L.MQ_F64,
+                               1.0 / tw1, 1.0 / tw2, 2.0, 1e-8, 0, B.stream))
+        assert np.array_equal(B.down(val), want)
+
+
+def case_norm(B):
+    lib = B.lib
+    rs = np.random.RandomState(1)
+    for rows, cols, dt in ((2048, 1, np.float32), (5000, 1, np.float64), (9, 11, np.float64),
+                           (300, 5, np.float32), (1, 1, np.float32), (70000, 1, np.float32)):
+        x = (rs.randn(rows, cols) * 3 + 1).astype(dt)
+        code = L.MQ_F64 if dt == np.float64 else L.MQ_F32
+        wsb = lib.mq_norm_ws_bytes(rows, cols)
+        hx, ws = B.up(x), B.zeros(wsb, np.uint8)
+        mean = B.zeros(cols, np.float64)
+        ok(B, lib.mq_col_mean(B.ptr(hx), code, rows, cols, B.ptr(mean), B.ptr(ws), wsb, B.stream))
+        hmean = B.down(mean)
+        assert np.allclose(hmean, x.astype(np.float64).mean(axis=0), rtol=1e-13, atol=1e-13)
+        mo = rs.randn(cols)
+        hmo, cov = B.up(mo), B.zeros(cols, np.float64)
+        ok(B, lib.mq_norm_cov(B.ptr(hx), code, rows, cols, B.ptr(hmo), B.ptr(mean), 2.0, B.ptr(cov),
+                              B.ptr(ws), wsb, B.stream))
+        want = 2.0 * ((x.astype(np.float64) - mo) * (x.astype(np.float64) - hmean)).mean(axis=0)
+        assert np.allclose(B.down(cov), want, rtol=1e-12, atol=1e-12)
+        var = np.abs(want) + 0.1
+        hvar = B.up(var)
+        out = B.zeros((rows, cols), np.float32)
+        ok(B, lib.mq_norm_apply(B.ptr(hx), code, rows, cols, B.ptr(mean), B.ptr(hvar), B.ptr(out), L.MQ_F32,
+                                1, B.stream))
+        close(B.down(out), np.tanh(((x - hmean) / np.maximum(1e-8, np.sqrt(var))).astype(np.float32)),
+              what="norm apply+tanh")
+        out64 = B.zeros((rows, cols), np.float64)
+        ok(B, lib.mq_norm_apply(B.ptr(hx), code, rows, cols, B.ptr(mean), B.ptr(hvar), B.ptr(out64),
+                                L.MQ_F64, 0, B.stream))
+        assert np.allclose(B.down(out64), (x.astype(np.float64) - hmean) / np.sqrt(var), rtol=1e-13, atol=1e-13)
+    mean0, x = rs.randn(7), rs.randn(7)
+    mean, hx, old = B.up(mean0.copy()), B.up(x), B.zeros(7, np.float64)
+    ok(B, lib.mq_running_mean_update(B.ptr(mean), B.ptr(hx), L.MQ_F64, 7, 0.3, B.ptr(old), B.stream))
+    assert np.array_equal(B.down(mean), mean0 + 0.3 * (x - mean0)) and np.array_equal(B.down(old), mean0)
+
+
+def case_gather(B):
+    """mannequin/_trajectory.py:79-86 t[idx]: bit-exact, NumPy negative-index rule."""
+    lib = B.lib
+    rs = np.random.RandomState(2)
+    for cols, dt in ((11, np.float32), (12, np.float32), (3, np.float32), (1, np.float32), (5, np.uint8),
+                     (4, np.int32)):
+        src = (rs.randn(40, cols) * 100).astype(dt)
+        idx = rs.randint(-40, 40, size=64).astype(np.int32)
+        hs, hi, dst = B.up(src), B.up(idx), B.zeros((64, cols), dt)
+        ok(B, lib.mq_gather_rows(B.ptr(hs), B.ptr(hi), 64, cols * src.itemsize, 40, B.ptr(dst), B.stream))
+        assert np.array_equal(B.down(dst), src[idx])
+    g = golden("trajectory")
+    o = g["traj_o"].astype(np.float32)
+    hs, hi, dst = B.up(o), B.up(g["traj_idx"].astype(np.int32)), B.zeros((64, 11), np.float32)
+    ok(B, lib.mq_gather_rows(B.ptr(hs), B.ptr(hi), 64, 44, 40, B.ptr(dst), B.stream))
+    assert np.array_equal(B.down(dst), g["traj_take_o"])
+    assert lib.mq_gather_rows(B.ptr(hs), B.ptr(hi), 0, 44, 40, B.ptr(dst), B.stream) == 0     # empty index
+
+
+def case_scan(B, sizes=(1, 2, 700, 2048, 2049, 5000, 70001)):
+    """benchmarks/gae.py:43-64,69 and mannequin/_utils.py:9-20."""
+    lib = B.lib
+    rs = np.random.RandomState(3)
+    for n in sizes:
+        r = rs.randn(n).astype(np.float32)
+        v = rs.randn(n + 1).astype(np.float32)
+        d = (rs.rand(n) < 0.02).astype(np.uint8)
+        wsb = lib.mq_scan_ws_bytes(n)
+        hr, hv, hd, ws = B.up(r), B.up(v), B.up(d), B.zeros(wsb, np.uint8)
+        adv, ret = B.zeros(n, np.float32), B.zeros(n, np.float32)
+        ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 0.99, 0.95, B.ptr(adv), B.ptr(ret), B.ptr(ws),
+                         wsb, B.stream))
+        wa, wr = O.gae_advantages(r, v, d)
+        close(B.down(adv), wa, what="gae adv n=%d" % n)
+        close(B.down(ret), wr, what="gae ret n=%d" % n)
+        # episode segmentation is integer-exact: integer data with gam=lam=1 has no rounding
+        ri = rs.randint(-3, 4, size=n).astype(np.float32)
+        vi = rs.randint(-3, 4, size=n + 1).astype(np.float32)
+        d2 = (rs.rand(n) < 0.05).astype(np.uint8)
+        hr, hv, hd = B.up(ri), B.up(vi), B.up(d2)
+        ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 1.0, 1.0, B.ptr(adv), B.ptr(ret), B.ptr(ws),
+                         wsb, B.stream))
+        wa, wr = O.gae_advantages(ri, vi, d2, 1.0, 1.0)
+        assert np.array_equal(B.down(adv), wa) and np.array_equal(B.down(ret), wr), "segmentation n=%d" % n
+        x = rs.randn(n)
+        hx, out = B.up(x), B.zeros(n, np.float64)
+        ok(B, lib.mq_discounted(B.ptr(hx), n, 500.0, B.ptr(out), B.ptr(ws), wsb, B.stream))
+        assert np.allclose(B.down(out), O.discounted(x, 500), rtol=1e-11, atol=1e-13)
+    # all-terminal and no-terminal rollouts
+    n = 300
+    r, v = rs.randn(n).astype(np.float32), rs.randn(n + 1).astype(np.float32)
+    for d in (np.ones(n, np.uint8), np.zeros(n, np.uint8)):
+        wsb = lib.mq_scan_ws_bytes(n)
+        hr, hv, hd, ws = B.up(r), B.up(v), B.up(d), B.zeros(wsb, np.uint8)
+        adv, ret = B.zeros(n, np.float32), B.zeros(n, np.float32)
+        ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 0.99, 0.95, B.ptr(adv), B.ptr(ret), B.ptr(ws),
+                         wsb, B.stream))
+        close(B.down(adv), O.gae_advantages(r, v, d)[0], what="gae edge")
+    # reference output of benchmarks/gae.py:gae() (tests/golden/gae.npz), first chunk
+    g = golden("gae")
+    spec = O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    theta = O.mlp_init(spec, np.random.RandomState(79), head_scale=0.1)
+    n = 2048
+    value = O.mlp_forward(theta, spec, g["gae_obs"][:n + 1], dtype=np.float32)[-1].reshape(-1)
+    hr, hv, hd = B.up(g["gae_rew"][:n].astype(np.float32)), B.up(value), B.up(g["gae_done"][:n].astype(np.uint8))
+    adv, ret = B.zeros(n, np.float32), B.zeros(n, np.float32)
+    ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 0.97, 0.9, B.ptr(adv), B.ptr(ret), None, 0, B.stream))
+    close(B.down(adv), g["gae_adv1"], rtol=2e-5, atol_scale=2e-6, what="gae vs reference chunk")
+    assert lib.mq_discounted(B.ptr(hx), 5, 0.5, B.ptr(out), None, 0, B.stream) == L.MQ_ERR_SHAPE
+
+
+def case_layered_mlp(B):
+    lib = B.lib
+    rs = np.random.RandomState(4)
+    g = golden("nets")
+    # reference outputs (tests/golden/nets.npz): LReLU net with image input, Tanh policy trunk
+    for name, n_in, widths, acts in (("lrelu", 20, [16, 16, 5], [2, 2, 0]), ("tanh", 11, [64, 64, 3], [1, 1, 0])):
+        spec = O.mlp_spec(n_in, widths, acts)
+        net = net_of(spec)
+        theta, x, dy = g[name + "_theta"], g[name + "_x"].reshape(-1, n_in), g[name + "_dy"]
+        batch = len(x)
+        ht, hx, hdy = B.up(theta), B.up(x), B.up(dy.copy())
+        acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
+        ok(B, lib.mq_mlp_forward(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(acts_buf), B.stream))
+        close(B.down(acts_buf)[-batch * widths[-1]:].reshape(batch, -1), g[name + "_y"].reshape(batch, -1),
+              rtol=2e-5, what="layered fwd vs reference " + name)
+        wsb = lib.mq_mlp_ws_bytes(net, batch)
+        ws, grad, dx = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32), B.zeros((batch, n_in), np.float32)
+        ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), None, B.ptr(acts_buf), B.ptr(hdy), batch,
+                                  1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), g[name + "_grad"], rtol=2e-5, atol_scale=2e-6, what="layered grad vs reference " + name)
+        if name == "lrelu":
+            close(B.down(dx), g["lrelu_dx"].reshape(batch, n_in), rtol=2e-5, what="layered dx vs reference")
+    for n_in, widths, acts, batch in ((70, [33, 10], [2, 1], 65), (784, [128, 128, 10], [2, 2, 0], 128),
+                                      (5, [7], [0], 1)):
+        spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
+        net = net_of(spec)
+        ht, hx = B.up(theta), B.up(x)
+        acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
+        ok(B, lib.mq_mlp_forward(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(acts_buf), B.stream))
+        outs = O.mlp_forward(theta, spec, x)
+        got, pos = B.down(acts_buf), 0
+        for o in outs:
+            close(got[pos:pos + o.size].reshape(o.shape), o, what="layered fwd %s" % (widths,))
+            pos += o.size
+        dy = rs.randn(batch, widths[-1]).astype(np.float32)
+        want, wdx = O.mlp_backward(theta, spec, x, outs, dy, want_dx=True)
+        wsb = lib.mq_mlp_ws_bytes(net, batch)
+        ws, grad, dx, hdy = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32), \
+            B.zeros((batch, n_in), np.float32), B.up(dy.copy())
+        ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), None, B.ptr(acts_buf), B.ptr(hdy), batch,
+                                  1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), want, what="layered grad %s" % (widths,))
+        close(B.down(dx), wdx, what="layered dx %s" % (widths,))
+    # gathered rows (Trajectory indexing fused into the load) + split-K over a long batch
+    spec, theta, x = mlp_case(rs, 11, [64, 64, 1], [1, 1, 0], 300)
+    idx = rs.randint(300, size=1024).astype(np.int32)
+    net = net_of(spec)
+    ht, hx, hi = B.up(theta), B.up(x), B.up(idx)
+    acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, 1024), np.float32)
+    ok(B, lib.mq_mlp_forward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), 1024, B.ptr(acts_buf), B.stream))
+    outs = O.mlp_forward(theta, spec, x[idx])
+    dy = rs.randn(1024, 1).astype(np.float32)
+    wsb = lib.mq_mlp_ws_bytes(net, 1024)
+    ws, grad, hdy = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32), B.up(dy.copy())
+    ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), 1024,
+                              1.0 / 1024, B.ptr(grad), None, B.ptr(ws), wsb, B.stream))
+    close(B.down(grad), O.mlp_backward(theta, spec, x[idx], outs, dy), what="layered grad gathered/split-K")
+
+
+def case_fused_heads(B, batches=(64, 200)):
+    lib = B.lib
+    rs = np.random.RandomState(5)
+    cases = [(11, [64, 64, 3], [1, 1, 0], b) for b in batches] + [
+        (20, [16, 16, 5], [2, 2, 0], 7), (1, [64, 64, 1], [1, 1, 0], 128), (2, [2, 2], [0, 1], 3),
+        (11, [64, 64, 1], [1, 1, 0], 300), (3, [5], [0], 1), (6, [128, 10], [2, 0], 33)]
+    for n_in, widths, acts, batch in cases:
+        spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
+        net = net_of(spec)
+        assert lib.mq_fused_tile_rows(net, 1) > 0
+        n_out = widths[-1]
+        ht, hx = B.up(theta), B.up(x)
+        out = B.zeros((batch, n_out), np.float32)
+        ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(out), None, None, B.stream))
+        outs = O.mlp_forward(theta, spec, x)
+        close(B.down(out), outs[-1], what="fused fwd %s" % (widths,))
+        wsb = lib.mq_fused_ws_bytes(net, batch)
+        ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
+        dy = rs.randn(batch, n_out).astype(np.float32)
+        hdy = B.up(dy)
+        h = head(B, L.HEAD_DY, dy=hdy)
+        out2 = B.zeros((batch, n_out), np.float32)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                B.ptr(grad), B.ptr(out2), None, B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), O.mlp_backward(theta, spec, x, outs, dy), what="fused grad DY %s b=%d" % (widths, batch))
+        close(B.down(out2), outs[-1], what="fused grad out")
+        tgt = rs.randn(batch, n_out).astype(np.float32)
+        h = head(B, L.HEAD_DIFF, target=B.up(tgt))
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), O.mlp_backward(theta, spec, x, outs, tgt - outs[-1]), what="fused grad DIFF")
+        if n_out >= 2 and acts[-1] == 0:
+            onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
+            h = head(B, L.HEAD_SOFTMAX_CE, p0=0.01, target=B.up(onehot))
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                    B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, O.softmax_ce_grad(outs[-1], onehot)),
+                  what="fused grad CE")
+    # reference fixtures through the fused path
+    g = golden("nets")
+    spec = O.mlp_spec(11, [64, 64, 3], [1, 1, 0])
+    net = net_of(spec)
+    ht, hx, hdy = B.up(g["tanh_theta"]), B.up(g["tanh_x"]), B.up(g["tanh_dy"])
+    grad, out = B.zeros(spec["n_params"], np.float32), B.zeros((64, 3), np.float32)
+    h = head(B, L.HEAD_DY, dy=hdy)
+    ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad),
+                            B.ptr(out), None, None, 0, B.stream))
+    close(B.down(out), g["tanh_y"], rtol=2e-5, what="fused fwd vs reference")
+    close(B.down(grad), g["tanh_grad"], rtol=2e-5, atol_scale=2e-6, what="fused grad vs reference")
+    # a net too wide for shared memory is refused, not silently mis-handled
+    big = L.make_net(784, [128, 128, 10], [2, 2, 0])
+    assert lib.mq_fused_tile_rows(big, 1) == 0
+    assert lib.mq_fused_grad(big, B.ptr(ht), B.ptr(hx), None, 64, ctypes.byref(h), 1.0, B.ptr(grad), None,
+                             None, None, 0, B.stream) == L.MQ_ERR_UNSUPPORTED
+
+
+def case_fused_gauss_ppo(B, minibatches=(64, 200)):
+    lib = B.lib
+    rs = np.random.RandomState(6)
+    g = golden("gauss")
+    spec = O.policy_spec(11, 3)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    theta, obs, act, w = g["gauss_theta"], g["gauss_obs"], g["gauss_act"], g["gauss_g"]
+    ht, ho, ha, hw = B.up(theta), B.up(obs), B.up(act), B.up(w)
+    logp = B.zeros(64, np.float32)
+    ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(ho), None, 64, None, B.ptr(ha), B.ptr(logp), B.stream))
+    close(B.down(logp), g["gauss_logp"], what="fused logp vs reference")
+    wsb = lib.mq_fused_ws_bytes(net, 4096)
+    ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
+    h = head(B, L.HEAD_GAUSS_LOGP, dy=hw, target=ha)
+    ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad), None,
+                            B.ptr(logp), B.ptr(ws), wsb, B.stream))
+    close(B.down(grad), g["gauss_grad"], rtol=3e-5, atol_scale=3e-6, what="fused gauss grad vs reference")
+    n = 300
+    o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+    a = rs.randn(n, 3).astype(np.float32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
+    ho, ha, hadv, hlp = B.up(o), B.up(a), B.up(adv), B.up(lp_old)
+    for mb in minibatches:
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+        lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
+        wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
+        assert (wgt == 0).any() and (wgt != 0).any()          # both branches of the clip rule
+        close(B.down(grad), O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs), rtol=3e-5,
+              atol_scale=3e-6, what="fused ppo grad mb=%d" % mb)
+
+
+def case_fused_train(B, steps=5):
+    lib = B.lib
+    rs = np.random.RandomState(7)
+    spec = O.policy_spec(11, 3)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    theta0 = np.concatenate([O.mlp_init(O._mlp_part(spec), rs, 0.1), np.zeros(3, np.float32)])
+    n, mb = 256, 64
+    o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+    a = rs.randn(n, 3).astype(np.float32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_old = O.policy_logprob(theta0, spec, o, a)[0].astype(np.float32)
+    idx = rs.randint(n, size=(steps, mb)).astype(np.int32)
+    ho, ha, hadv, hlp, hi = B.up(o), B.up(a), B.up(adv), B.up(lp_old), B.up(idx)
+    for dtype, code in ((np.float64, L.MQ_F64), (np.float32, L.MQ_F32)):
+        opt = O.AdamO(theta0, horizon=10)
+        th_ref = theta0.copy()
+        for s in range(steps):
+            th_ref = O.ppo_policy_step(th_ref, spec, opt, o[idx[s]], a[idx[s]], adv[idx[s]], lp_old[idx[s]])
+        ht = B.up(theta0.copy())
+        val, m, v = B.up(theta0.astype(dtype)), B.zeros(5126, dtype), B.zeros(5126, dtype)
+        tw = (ctypes.c_double * 2)(0.0, 0.0)
+        h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+        ok(B, lib.mq_fused_train(net, B.ptr(ht), B.ptr(val), B.ptr(m), B.ptr(v), code, B.ptr(ho),
+                                 ctypes.byref(h), B.ptr(hi), steps, mb, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
+        theta = B.down(ht)
+        assert abs(tw[0] - opt.tw1) < 1e-12 and abs(tw[1] - opt.tw2) < 1e-12
+        # per-step error bar 2e-6 (fp32 gradient rounding feeding Adam), cf. test_oracle_golden
+        assert np.max(np.abs(theta - th_ref)) < 2e-6 * (1 + steps) + 1e-6, np.max(np.abs(theta - th_ref))
+        assert np.max(np.abs(theta - theta0)) > 1e-4
+        assert np.array_equal(theta, B.down(val).astype(np.float32))
+    vspec = O.mlp_spec(11, [64, 64, 1], [1, 1, 0])
+    vnet = net_of(vspec)
+    vt0 = O.mlp_init(vspec, rs, 0.1)
+    ret = rs.randn(n, 1).astype(np.float32)
+    opt = O.AdamO(vt0, horizon=10, lr=0.003)
+    th_ref = vt0.copy()
+    for s in range(steps):
+        th_ref = O.value_sgd_step(th_ref, vspec, opt, o[idx[s]], ret[idx[s]])
+    ht, hret = B.up(vt0.copy()), B.up(ret)
+    val, m, v = B.up(vt0.astype(np.float64)), B.zeros(len(vt0), np.float64), B.zeros(len(vt0), np.float64)
+    tw = (ctypes.c_double * 2)(0.0, 0.0)
+    h = head(B, L.HEAD_DIFF, target=hret)
+    ok(B, lib.mq_fused_train(vnet, B.ptr(ht), B.ptr(val), B.ptr(m), B.ptr(v), L.MQ_F64, B.ptr(ho),
+                             ctypes.byref(h), B.ptr(hi), steps, mb, 0.9, 0.99, tw, 0.003, 1e-8, B.stream))
+    err = np.max(np.abs(B.down(ht) - th_ref))
+    assert err < 2e-5 * (1 + steps), err
+
+
+def case_ppo_reference_replay(B, n_steps=300):
+    """Replays the policy half of benchmarks/ppo.py:run() recorded from the REAL
+    reference (tests/golden/ppo.npz, first chunk) through mq_fused_train."""
+    lib = B.lib
+    g = golden("ppo")
+    n = 2048
+    pol_spec = O.policy_spec(11, 3)
+    val_spec = O.mlp_spec(11, [64, 64, 1], [1, 1, 0])
+    obs, act, rew, done = g["ppo_obs"], g["ppo_act"], g["ppo_rew"], g["ppo_done"]
+    # value half on the device: forward, GAE, 300 value steps
+    vnet, pnet = net_of(val_spec), L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    hvt = B.up(g["ppo_val_init"].copy())
+    ho = B.up(obs[:n + 1].copy())
+    value = B.zeros(n + 1, np.float32)
+    ok(B, lib.mq_fused_forward(vnet, B.ptr(hvt), B.ptr(ho), None, n + 1, B.ptr(value), None, None, B.stream))
+    hr, hd = B.up(rew[:n].astype(np.float32)), B.up(done[:n].astype(np.uint8))
+    adv, ret = B.zeros(n, np.float32), B.zeros(n, np.float32)
+    ok(B, lib.mq_gae(B.ptr(hr), B.ptr(value), B.ptr(hd), n, 0.99, 0.95, B.ptr(adv), B.ptr(ret), None, 0, B.stream))
+    vval, vm, vv = B.up(g["ppo_val_init"].astype(np.float64)), B.zeros(4993, np.float64), B.zeros(4993, np.float64)
+    tw = (ctypes.c_double * 2)(0.0, 0.0)
+    hvi = B.up(g["ppo_val_idx"][:n_steps].copy())
+    h = head(B, L.HEAD_DIFF, target=ret)
+    ok(B, lib.mq_fused_train(vnet, B.ptr(hvt), B.ptr(vval), B.ptr(vm), B.ptr(vv), L.MQ_F64, B.ptr(ho),
+                             ctypes.byref(h), B.ptr(hvi), n_steps, 64, 0.9, 0.99, tw, 0.003, 1e-8, B.stream))
+    ck = {int(s): i for i, s in enumerate(g["ppo_ck_steps"])}
+    tol = 2e-6 * (1 + n_steps) + 1e-6
+    if n_steps - 1 in ck:
+        err = np.max(np.abs(B.down(hvt) - g["ppo_val_ck"][ck[n_steps - 1]]))
+        assert err < tol, ("value net vs reference", err)
+    # policy half: normalise (host-known stats -> device apply), old log-probs, 300 PPO steps
+    adv_h = B.down(adv)
+    norm = O.RunningNormalizeO(horizon=2)
+    norm.update(adv_h)
+    mean, var = B.up(np.array([norm.get_mean()]).reshape(1)), B.up(np.array([norm.get_var()]).reshape(1))
+    adv_n = B.zeros(n, np.float32)
+    ok(B, lib.mq_norm_apply(B.ptr(adv), L.MQ_F32, n, 1, B.ptr(mean), B.ptr(var), B.ptr(adv_n), L.MQ_F32, 1, B.stream))
+    hpt, ha = B.up(g["ppo_pol_init"].copy()), B.up(act[:n].copy())
+    lp_old = B.zeros(n, np.float32)
+    ok(B, lib.mq_fused_forward(pnet, B.ptr(hpt), B.ptr(ho), None, n, None, B.ptr(ha), B.ptr(lp_old), B.stream))
+    pval, pm, pv = B.up(g["ppo_pol_init"].astype(np.float64)), B.zeros(5126, np.float64), B.zeros(5126, np.float64)
+    tw = (ctypes.c_double * 2)(0.0, 0.0)
+    hpi = B.up(g["ppo_pol_idx"][:n_steps].copy())
+    h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=adv_n, logp_old=lp_old)
+    ok(B, lib.mq_fused_train(pnet, B.ptr(hpt), B.ptr(pval), B.ptr(pm), B.ptr(pv), L.MQ_F64, B.ptr(ho),
+                             ctypes.byref(h), B.ptr(hpi), n_steps, 64, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
+    if n_steps - 1 in ck:
+        err = np.max(np.abs(B.down(hpt) - g["ppo_pol_ck"][ck[n_steps - 1]]))
+        assert err < tol, ("policy vs reference", err)
+    return B.down(hpt), B.down(hvt)
+
+
+def case_es(B, members=6, n_obs=150):
+    lib = B.lib
+    rs = np.random.RandomState(8)
+    spec = O.mlp_spec(11, [64, 64, 3], [1, 1, 0])
+    net = net_of(spec)
+    theta = O.mlp_init(spec, rs)
+    noise = (rs.randn(members, spec["n_params"]) * 0.1).astype(np.float32)
+    obs = np.clip(rs.randn(n_obs, 11), -5, 5).astype(np.float32)
+    coef = np.array([1.0, -0.5, 0.25], np.float32)
+    ht, hn, ho, hc = B.up(theta), B.up(noise), B.up(obs), B.up(coef)
+    rets = B.zeros(members, np.float32)
+    ok(B, lib.mq_es_eval(net, B.ptr(ht), B.ptr(hn), members, B.ptr(ho), n_obs, B.ptr(hc), B.ptr(rets), B.stream))
+    want = np.zeros(members)
+    for p in range(members):
+        th = (theta.astype(np.float64) + noise[p]).astype(np.float32)
+        want[p] = np.sum(O.mlp_forward(th, spec, obs)[-1] @ coef.astype(np.float64))
+    close(B.down(rets), want, rtol=2e-5, atol_scale=1e-5, what="es returns")
+    w = rs.randn(members)
+    wsb = lib.mq_es_ws_bytes(members, spec["n_params"])
+    hw, ws, out = B.up(w), B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float64)
+    ok(B, lib.mq_es_weighted_sum(B.ptr(hn), B.ptr(hw), members, spec["n_params"], 1.0 / members, B.ptr(out),
+                                 B.ptr(ws), wsb, B.stream))
+    assert np.allclose(B.down(out), (noise.astype(np.float64) * w[:, None]).mean(axis=0), rtol=1e-12, atol=1e-15)
+
+
+def case_ops(B):
+    lib = B.lib
+    rs = np.random.RandomState(9)
+    a = rs.randn(33, 70).astype(np.float32)
+    b = rs.randn(70, 21).astype(np.float32)
+    ha, hb, c = B.up(a), B.up(b), B.zeros((33, 21), np.float32)
+    ok(B, lib.mq_gemm(B.ptr(ha), 70, 1, B.ptr(hb), 21, 1, B.ptr(c), 33, 21, 70, 1.0, B.stream))
+    close(B.down(c), a.astype(np.float64) @ b, what="gemm NN")
+    ct = B.zeros((70, 70), np.float32)
+    ok(B, lib.mq_gemm(B.ptr(ha), 1, 70, B.ptr(ha), 70, 1, B.ptr(ct), 70, 70, 33, 0.5, B.stream))
+    close(B.down(ct), 0.5 * a.T.astype(np.float64) @ a, what="gemm TN")
+    cn = B.zeros((33, 33), np.float32)
+    ok(B, lib.mq_gemm(B.ptr(ha), 70, 1, B.ptr(ha), 1, 70, B.ptr(cn), 33, 33, 70, 1.0, B.stream))
+    close(B.down(cn), a.astype(np.float64) @ a.T, what="gemm NT")
+    g = rs.randn(50, 7).astype(np.float32)
+    x = rs.randn(50, 7).astype(np.float32)
+    hg, hx, out = B.up(g), B.up(x), B.zeros(7, np.float32)
+    ok(B, lib.mq_col_sum(B.ptr(hg), B.ptr(hx), 50, 7, 0.5, B.ptr(out), B.stream))
+    close(B.down(out), 0.5 * (g * x).sum(axis=0), what="col_sum")
+    y = B.zeros((50, 7), np.float32)
+    ok(B, lib.mq_binary(B.ptr(hx), B.ptr(out), B.ptr(y), 350, 7, 1, B.stream))
+    assert np.array_equal(B.down(y), x * B.down(out))
+    ok(B, lib.mq_add_bias(B.ptr(hx), B.ptr(out), B.ptr(y), 50, 7, B.stream))
+    assert np.array_equal(B.down(y), x + B.down(out))
+    for act, leak in ((L.ACT_TANH, 0.0), (L.ACT_LRELU, 0.1), (L.ACT_LRELU, 0.0)):
+        ok(B, lib.mq_act_forward(B.ptr(hx), B.ptr(y), 350, act, leak, B.stream))
+        want = np.tanh(x) if act == L.ACT_TANH else np.where(x < 0, x * np.float32(leak), x)
+        close(B.down(y), want, what="act fwd")
+        gy = B.zeros((50, 7), np.float32)
+        ok(B, lib.mq_act_backward(B.ptr(y), B.ptr(hg), B.ptr(gy), 350, act, leak, B.stream))
+        wantg = g * (1 - np.tanh(x) ** 2) if act == L.ACT_TANH else np.where(x < 0, g * np.float32(leak), g)
+        close(B.down(gy), wantg, what="act bwd")
+    ok(B, lib.mq_clip_forward(B.ptr(hx), B.ptr(y), 350, -0.5, 0.5, B.stream))
+    assert np.array_equal(B.down(y), np.clip(x, -0.5, 0.5))
+    ok(B, lib.mq_clip_backward(B.ptr(hx), B.ptr(hg), B.ptr(y), 350, -0.5, 0.5, B.stream))
+    assert np.array_equal(B.down(y), O.clip_backward(x, g, -0.5, 0.5).astype(np.float32))
+    mu, ls, s = rs.randn(9, 3).astype(np.float32), (rs.randn(3) * 0.3).astype(np.float32), rs.randn(9, 3).astype(np.float32)
+    hmu, hls, hs, lp = B.up(mu), B.up(ls), B.up(s), B.zeros(9, np.float32)
+    ok(B, lib.mq_gauss_logprob(B.ptr(hmu), B.ptr(hls), 3, B.ptr(hs), 9, 3, B.ptr(lp), B.stream))
+    close(B.down(lp), O.gauss_logprob(mu, ls, s), what="gauss logp")
+    w = rs.randn(9).astype(np.float32)
+    hw, dmu, dls = B.up(w), B.zeros((9, 3), np.float32), B.zeros((9, 3), np.float32)
+    ok(B, lib.mq_gauss_logprob_bwd(B.ptr(hmu), B.ptr(hls), 3, B.ptr(hs), B.ptr(hw), 9, 3, B.ptr(dmu), B.ptr(dls), B.stream))
+    wm, wl = O.gauss_logprob_grads(mu, ls, s, w)
+    close(B.down(dmu), wm, what="gauss dmu")
+    close(B.down(dls), wl, what="gauss dls")
+    unit = rs.randn(9, 3).astype(np.float32)
+    hu, so, nz = B.up(unit), B.zeros((9, 3), np.float32), B.zeros((9, 3), np.float32)
+    ok(B, lib.mq_gauss_sample(B.ptr(hmu), B.ptr(hls), 3, B.ptr(hu), 9, 3, B.ptr(so), B.ptr(nz), B.stream))
+    ws_, wn_ = O.gauss_sample(mu, ls, unit)
+    close(B.down(so), ws_, what="gauss sample")
+    close(B.down(nz), wn_, what="gauss noise")
+    m, l = rs.randn(5, 3).astype(np.float32), (rs.randn(5, 3) * 0.5).astype(np.float32)
+    hm, hl, o5 = B.up(m), B.up(l), B.zeros(5, np.float32)
+    ok(B, lib.mq_dkl_forward(B.ptr(hm), B.ptr(hl), 5, 3, B.ptr(o5), B.stream))
+    close(B.down(o5), O.dkl_uninormal(m, l), what="dkl")
+    w5 = rs.randn(5).astype(np.float32)
+    hw5, dm, dl = B.up(w5), B.zeros((5, 3), np.float32), B.zeros((5, 3), np.float32)
+    ok(B, lib.mq_dkl_backward(B.ptr(hm), B.ptr(hl), B.ptr(hw5), 5, 3, B.ptr(dm), B.ptr(dl), B.stream))
+    wdm, wdl = O.dkl_uninormal_grads(m, l, w5)
+    close(B.down(dm), wdm, what="dkl dmean")
+    close(B.down(dl), wdl, what="dkl dlogstd")
+    lg = rs.randn(6, 10).astype(np.float32)
+    oh = np.eye(10, dtype=np.float32)[rs.randint(10, size=6)]
+    hlg, hoh, dy = B.up(lg), B.up(oh), B.zeros((6, 10), np.float32)
+    ok(B, lib.mq_softmax_ce_grad(B.ptr(hlg), B.ptr(hoh), None, 6, 10, 0.01, B.ptr(dy), B.stream))
+    close(B.down(dy), O.softmax_ce_grad(lg, oh), what="softmax ce")
+    lpn, lpo, adv = rs.randn(40).astype(np.float32) * 0.3, rs.randn(50).astype(np.float32) * 0.3, rs.randn(50).astype(np.float32)
+    idx = rs.randint(50, size=40).astype(np.int32)
+    h1, h2, h3, h4, wo = B.up(lpn), B.up(lpo), B.up(adv), B.up(idx), B.zeros(40, np.float32)
+    ok(B, lib.mq_ppo_weight(B.ptr(h1), B.ptr(h2), B.ptr(h3), B.ptr(h4), 40, 0.8, 1.2, B.ptr(wo), B.stream))
+    close(B.down(wo), O.ppo_clip_weight(lpn, lpo[idx], adv[idx]), what="ppo weight")
+    # error contract: bad arguments return codes, never crash
+    assert lib.mq_act_forward(B.ptr(hx), B.ptr(y), 350, 7, 0.0, B.stream) == L.MQ_ERR_INVALID
+    assert lib.mq_binary(B.ptr(hx), B.ptr(out), B.ptr(y), 350, 8, 0, B.stream) == L.MQ_ERR_SHAPE
+    assert b"broadcast" in lib.mq_last_error()
+
+
+ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_fused_heads,
+             case_fused_gauss_ppo, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
