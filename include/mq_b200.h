@@ -78,6 +78,8 @@ typedef struct mq_head {
 
 /* ---- library -------------------------------------------------------------- */
 const char *mq_last_error(void);
+/* developer aid: device buffer of 8 int64 that mq_fused_train fills with per-phase cycles */
+int mq_debug_set_phase_buffer(void *dev_buf);
 int mq_version(void);
 int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
 

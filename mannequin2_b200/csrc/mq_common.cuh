@@ -68,8 +68,23 @@ __device__ __forceinline__ T mq_block_sum(T v, T *red) {
     return s;
 }
 
+// Branch-free tanh (so that independent evaluations interleave): odd polynomial for |x| < 0.1
+// (truncation < 3e-11), 1 - 2/(exp(2|x|)+1) otherwise (absolute error ~2e-7).
+__device__ __forceinline__ float mq_tanh(float x) {
+#ifdef MQ_EMU
+    return tanhf(x);
+#else
+    const float ax = fabsf(x);
+    const float x2 = x * x;
+    const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
+    const float t = __expf(2.0f * ax);
+    const float big = copysignf(1.0f - __fdividef(2.0f, t + 1.0f), x);
+    return ax < 0.1f ? poly : big;
+#endif
+}
+
 __device__ __forceinline__ float mq_act_apply(float z, int act, float leak) {
-    if (act == MQ_ACT_TANH) return tanhf(z);
+    if (act == MQ_ACT_TANH) return mq_tanh(z);
     if (act == MQ_ACT_LRELU) return z < 0.0f ? z * leak : z;
     return z;
 }

@@ -10,48 +10,66 @@
 //   backprop              mannequin/basicnet.py:209-257 + mannequin/backprop.py:11-60
 //   (mq_fused_train also) mannequin/_adam.py:23-53 and Trajectory.__getitem__ gathers
 //
-// Layout in shared memory (floats):
-//   sW   weights, layer l as [in][out padded to 4] + bias + logstd     (natural order)
-//   sWt  transposed copy of layers >= 1, [out][in padded to 4]         (for g W^T)
-//   sG   gradient accumulators, same layout as sW
-//   sA_l activations, TRANSPOSED: [width_l][tile_rows + 4]; rows contiguous so a thread
-//        reads its 8 rows of one feature with two 128-bit loads, and dW (a contraction
-//        over rows) reads both operands with unit stride.
-// FFMA register tiles: forward / g W^T use (RM rows x 4 cols) per thread, dW uses 4x4
-// over (in,out) with the row range split across thread groups when the layer is small;
-// bias and logstd gradients are warp-shuffle row sums.  All reductions have a fixed
-// order, so results are bit-reproducible run to run.
+// Shared-memory layout (floats), tbp = tile_rows + 4 (so that tbp = 4 mod 32):
+//   sW   layer l as [in][npad] + bias[npad] (+ logstd); weight COLUMNS ARE PERMUTED,
+//        pos(n) = (n % CG)*4 + n / CG with CG = npad/4, so that the four columns a thread
+//        owns (cg, cg+CG, cg+2CG, cg+3CG) are one 128-bit word AND neighbouring threads write
+//        neighbouring activation rows (conflict-free epilogue stores)
+//   sWt  transposed copy of layers >= 1, [out][kpad+4], columns permuted the same way
+//   sG   gradient accumulators, same layout as sW (so Adam is a straight loop over sW/sG)
+//   sA_l activations, TRANSPOSED [width_l][tbp]: a thread reads its RM rows of one feature
+//        with one vector load; dW (a contraction over rows) reads both operands unit-stride
+//   DZ   two ping-pong buffers for the back-propagated signal, so dW_l and dX_l need no
+//        barrier between them
+// FFMA register tiles: forward / g W^T use (RM rows x 4 cols) per thread, dW a 4x4 tile over
+// (in,out) with the row range split across thread groups when the layer is small; the bias
+// gradient rides along in the dW tiles that own input row 0; the logstd gradient is a
+// warp-shuffle row sum.  Every reduction has a fixed order: bit-reproducible run to run.
 #include "mq_common.cuh"
 
+// Developer aid: per-phase cycle counters (buffer is NULL in normal use).
+struct PhaseProf { long long *buf; long long last; };
+#ifndef MQ_EMU
+#define PHASE_MARK(pp, i) do { if ((pp).buf && threadIdx.x == 0) { long long now_ = clock64(); (pp).buf[i] += now_ - (pp).last; (pp).last = now_; } } while (0)
+#else
+#define PHASE_MARK(pp, i) do { } while (0)
+#endif
+
 #define HALF_LOG_2PI 0.91893853320467274178f
-#define DW_SCRATCH_FLOATS (MQ_NT * 16)
+#define DW_SLOTS 20                  // scratch floats per thread: 16 dW partials + 4 bias partials
+#define TRAIN_NT 256                 // threads of the persistent training CTA
 
 struct FusedPlan {
     mq_net_t net;
     int tb, tbp;
-    int npad[MQ_MAX_LAYERS], kpad[MQ_MAX_LAYERS];
+    int npad[MQ_MAX_LAYERS], kpad[MQ_MAX_LAYERS], ldwt[MQ_MAX_LAYERS];
     int sw_off[MQ_MAX_LAYERS], sb_off[MQ_MAX_LAYERS], swt_off[MQ_MAX_LAYERS];
     int sls_off;
     int p_pad, wt_total;
     int act_off[MQ_MAX_LAYERS + 1];
-    int head_off, act_total;
+    int aux_off;                     // head inputs: target[n_out][tbp], hterm[n_out][tbp], misc[2][tbp]
+    int act_total;
+    int dz_floats;                   // one ping-pong buffer
+    int scratch_floats;
     int with_grad;
     int64_t smem_bytes;
 };
 
-static int64_t plan_build(const mq_net_t *net, int tb, int with_grad, FusedPlan *p) {
+static int64_t plan_build(const mq_net_t *net, int tb, int with_grad, FusedPlan *p, int smem_state, int nt) {
     memset(p, 0, sizeof(*p));
     p->net = *net;
     p->tb = tb;
     p->tbp = tb + 4;
     p->with_grad = with_grad;
-    int pos = 0, wt = 0;
+    int pos = 0, wt = 0, maxw = 4;
     for (int l = 0; l < net->n_layers; ++l) {
         p->npad[l] = (int)mq_round_up(net->out[l], 4);
         p->kpad[l] = (int)mq_round_up(net->in[l], 4);
+        p->ldwt[l] = p->kpad[l] + 4;
         p->sw_off[l] = pos; pos += net->in[l] * p->npad[l];
         p->sb_off[l] = pos; pos += p->npad[l];
-        if (with_grad && l >= 1) { p->swt_off[l] = wt; wt += net->out[l] * p->kpad[l]; }
+        if (with_grad && l >= 1) { p->swt_off[l] = wt; wt += net->out[l] * p->ldwt[l]; }
+        if (net->out[l] > maxw) maxw = net->out[l];
     }
     p->sls_off = pos;
     if (net->logstd_off >= 0) pos += (int)mq_round_up(net->n_out, 4);
@@ -60,73 +78,120 @@ static int64_t plan_build(const mq_net_t *net, int tb, int with_grad, FusedPlan 
     int a = 0;
     p->act_off[0] = a; a += net->n_in * p->tbp;
     for (int l = 0; l < net->n_layers; ++l) { p->act_off[l + 1] = a; a += net->out[l] * p->tbp; }
-    p->head_off = a; a += net->n_out * p->tbp;
+    p->aux_off = a; a += (2 * net->n_out + 2) * p->tbp;
     p->act_total = a;
+    p->dz_floats = maxw * p->tbp;
+    p->scratch_floats = nt * DW_SLOTS;
     int64_t floats = (int64_t)p->p_pad + p->act_total;
-    if (with_grad) floats += (int64_t)p->wt_total + p->p_pad + DW_SCRATCH_FLOATS;
+    if (with_grad) floats += (int64_t)p->wt_total + p->p_pad + 2 * p->dz_floats + p->scratch_floats;
+    if (smem_state) floats += 2 * p->p_pad;
     p->smem_bytes = floats * (int64_t)sizeof(float);
     return p->smem_bytes;
 }
 
-static int plan_choose(const mq_net_t *net, int64_t batch, int with_grad, FusedPlan *p) {
+static int plan_choose(const mq_net_t *net, int64_t batch, int with_grad, FusedPlan *p, int smem_state = 0,
+                       int nt = MQ_NT) {
     const int64_t lim = mq_smem_optin();
     int tb = 128;
     if (batch <= 32) tb = 32; else if (batch <= 64) tb = 64;
     for (; tb >= 32; tb >>= 1)
-        if (plan_build(net, tb, with_grad, p) <= lim) return tb;
+        if (plan_build(net, tb, with_grad, p, smem_state, nt) <= lim) return tb;
     return 0;
 }
 
-__device__ __forceinline__ float *smem_W(const FusedPlan &p, unsigned char *base) { return (float *)base; }
-__device__ __forceinline__ float *smem_A(const FusedPlan &p, unsigned char *base) {
-    return (float *)base + p.p_pad;
+struct Smem {
+    float *W, *A, *Wt, *G, *DZ, *S, *M, *V;
+    __device__ __forceinline__ Smem(const FusedPlan &p, unsigned char *base) {
+        W = (float *)base;
+        A = W + p.p_pad;
+        Wt = A + p.act_total;
+        G = Wt + p.wt_total;
+        DZ = G + p.p_pad;
+        S = DZ + 2 * p.dz_floats;
+        M = S + p.scratch_floats;
+        V = M + p.p_pad;
+    }
+};
+
+__device__ __forceinline__ int perm_pos(int n, int cg_count) { return (n % cg_count) * 4 + n / cg_count; }
+
+// flat parameter j -> padded shared index (runs once per launch: divisions are fine here)
+template <int NT, typename F>
+__device__ __forceinline__ void for_each_param(const FusedPlan &p, F f) {
+    for (int l = 0; l < p.net.n_layers; ++l) {
+        const int K = p.net.in[l], N = p.net.out[l], CG = p.npad[l] >> 2;
+        for (int e = threadIdx.x; e < K * N; e += NT) {
+            const int k = e / N, n = e - k * N;
+            f(p.net.w_off[l] + e, p.sw_off[l] + k * p.npad[l] + perm_pos(n, CG));
+        }
+        for (int n = threadIdx.x; n < N; n += NT) f(p.net.b_off[l] + n, p.sb_off[l] + n);
+    }
+    if (p.net.logstd_off >= 0)
+        for (int a = threadIdx.x; a < p.net.n_out; a += NT) f(p.net.logstd_off + a, p.sls_off + a);
 }
-__device__ __forceinline__ float *smem_Wt(const FusedPlan &p, unsigned char *base) {
-    return (float *)base + p.p_pad + p.act_total;
+
+__device__ __forceinline__ int flat_to_pad(const FusedPlan &p, int j) {
+    for (int l = 0; l < p.net.n_layers; ++l) {
+        const int N = p.net.out[l];
+        if (j < p.net.b_off[l]) {
+            const int e = j - p.net.w_off[l];
+            const int k = e / N, n = e - k * N;
+            return p.sw_off[l] + k * p.npad[l] + perm_pos(n, p.npad[l] >> 2);
+        }
+        if (j < p.net.b_off[l] + N) return p.sb_off[l] + (j - p.net.b_off[l]);
+    }
+    return p.sls_off + (j - p.net.logstd_off);
 }
-__device__ __forceinline__ float *smem_G(const FusedPlan &p, unsigned char *base) {
-    return (float *)base + p.p_pad + p.act_total + p.wt_total;
-}
-__device__ __forceinline__ float *smem_S(const FusedPlan &p, unsigned char *base) {
-    return (float *)base + p.p_pad + p.act_total + p.wt_total + p.p_pad;
+
+// sWt[n][pos(k)] = sW[k][pos(n)] for layers >= 1.  n is the fast index (<= 4-way conflicts on
+// both sides); when N divides NT every thread keeps its n and walks k without any division.
+template <int NT>
+__device__ void refresh_transposes(const FusedPlan &p, const float *sW, float *sWt) {
+    for (int l = 1; l < p.net.n_layers; ++l) {
+        const int K = p.net.in[l], N = p.net.out[l], CG = p.npad[l] >> 2, CGK = p.kpad[l] >> 2;
+        const float *src = sW + p.sw_off[l];
+        float *dst = sWt + p.swt_off[l];
+        if (NT % N == 0) {
+            const int n = threadIdx.x % N, kstep = NT / N;
+            const int srcn = perm_pos(n, CG), dstn = n * p.ldwt[l];
+            int k = threadIdx.x / N;
+            int kq = k / CGK, kr = k - kq * CGK;
+            for (; k < K; k += kstep) {
+                dst[dstn + kr * 4 + kq] = src[k * p.npad[l] + srcn];
+                kr += kstep;
+                while (kr >= CGK) { kr -= CGK; ++kq; }
+            }
+        } else {
+            for (int e = threadIdx.x; e < K * N; e += NT) {
+                const int k = e / N, n = e - k * N;
+                dst[n * p.ldwt[l] + perm_pos(k, CGK)] = src[k * p.npad[l] + perm_pos(n, CG)];
+            }
+        }
+    }
 }
 
 // ---- weights: flat theta (+ optional per-member noise) -> padded shared layout --------
+template <int NT>
 __device__ void load_weights(const FusedPlan &p, const float *__restrict__ theta,
                              const float *__restrict__ noise, float *sW, float *sWt) {
-    const int t = threadIdx.x;
-    for (int e = t; e < p.p_pad; e += MQ_NT) sW[e] = 0.0f;
-    if (sWt) for (int e = t; e < p.wt_total; e += MQ_NT) sWt[e] = 0.0f;
+    for (int e = threadIdx.x; e < p.p_pad; e += NT) sW[e] = 0.0f;
+    if (sWt) for (int e = threadIdx.x; e < p.wt_total; e += NT) sWt[e] = 0.0f;
     __syncthreads();
-    for (int l = 0; l < p.net.n_layers; ++l) {
-        const int K = p.net.in[l], N = p.net.out[l];
-        for (int e = t; e < K * N; e += MQ_NT) {
-            const int k = e / N, n = e - k * N;
-            float w = theta[p.net.w_off[l] + e];
-            if (noise) w += noise[p.net.w_off[l] + e];
-            sW[p.sw_off[l] + k * p.npad[l] + n] = w;
-            if (sWt && l >= 1) sWt[p.swt_off[l] + n * p.kpad[l] + k] = w;
-        }
-        for (int n = t; n < N; n += MQ_NT) {
-            float b = theta[p.net.b_off[l] + n];
-            if (noise) b += noise[p.net.b_off[l] + n];
-            sW[p.sb_off[l] + n] = b;
-        }
-    }
-    if (p.net.logstd_off >= 0)
-        for (int a = t; a < p.net.n_out; a += MQ_NT) {
-            float v = theta[p.net.logstd_off + a];
-            if (noise) v += noise[p.net.logstd_off + a];
-            sW[p.sls_off + a] = v;
-        }
+    for_each_param<NT>(p, [&](int flat, int pad) {
+        float w = theta[flat];
+        if (noise) w += noise[flat];
+        sW[pad] = w;
+    });
     __syncthreads();
+    if (sWt) { refresh_transposes<NT>(p, sW, sWt); __syncthreads(); }
 }
 
-// ---- input tile: x[row, :] (optionally gathered) -> sA0[k][r] -------------------------
+// ---- input tile (optionally gathered) -> sA0[k][r]; head inputs -> aux ------------------
+template <int NT>
 __device__ void load_rows(const FusedPlan &p, const float *__restrict__ x,
                           const int32_t *__restrict__ idx, int64_t row0, int64_t n_rows, float *sA0) {
     const int K = p.net.n_in;
-    for (int e = threadIdx.x; e < p.tb * K; e += MQ_NT) {
+    for (int e = threadIdx.x; e < p.tb * K; e += NT) {
         const int r = e / K, k = e - r * K;
         const int64_t gr = row0 + r;
         float v = 0.0f;
@@ -138,30 +203,74 @@ __device__ void load_rows(const FusedPlan &p, const float *__restrict__ x,
     }
 }
 
-template <int RM> struct RowVec;
-template <> struct RowVec<1> { static __device__ __forceinline__ void ld(const float *p, float *a) { a[0] = p[0]; } };
-template <> struct RowVec<2> { static __device__ __forceinline__ void ld(const float *p, float *a) {
-    float2 v = *reinterpret_cast<const float2 *>(p); a[0] = v.x; a[1] = v.y; } };
-template <> struct RowVec<4> { static __device__ __forceinline__ void ld(const float *p, float *a) {
-    float4 v = *reinterpret_cast<const float4 *>(p); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; } };
-template <> struct RowVec<8> { static __device__ __forceinline__ void ld(const float *p, float *a) {
-    RowVec<4>::ld(p, a); RowVec<4>::ld(p + 4, a + 4); } };
+template <int NT>
+__device__ void load_head_inputs(const FusedPlan &p, const mq_head_t &h, const int32_t *__restrict__ idx,
+                                 int64_t row0, int64_t n_rows, float *aux) {
+    const int N = p.net.n_out, tbp = p.tbp;
+    const float *mat = (h.kind == MQ_HEAD_DY) ? h.dy : h.target;
+    for (int e = threadIdx.x; e < p.tb * N; e += NT) {
+        const int r = e / N, n = e - r * N;
+        const int64_t gr = row0 + r;
+        float v = 0.0f;
+        if (gr < n_rows) v = mat[(idx ? (int64_t)idx[gr] : gr) * N + n];
+        aux[n * tbp + r] = v;
+    }
+    if (h.kind == MQ_HEAD_GAUSS_LOGP || h.kind == MQ_HEAD_GAUSS_PPO) {
+        float *misc = aux + 2 * N * tbp;
+        const float *v0 = (h.kind == MQ_HEAD_GAUSS_PPO) ? h.adv : h.dy;
+        for (int e = threadIdx.x; e < 2 * p.tb; e += NT) {
+            const int which = e / p.tb, r = e - which * p.tb;
+            const int64_t gr = row0 + r;
+            float v = 0.0f;
+            if (gr < n_rows) {
+                const int64_t src = idx ? (int64_t)idx[gr] : gr;
+                if (which == 0) v = v0[src];
+                else if (h.kind == MQ_HEAD_GAUSS_PPO) v = h.logp_old[src];
+            }
+            misc[which * tbp + r] = v;
+        }
+    }
+}
 
-// out[n][r] = epi( sum_k in[k][r] * w[k*ldw + n] ),  in: [K][tbp], out: [N][tbp]
+template <int RM> struct RowVec;
+template <> struct RowVec<1> {
+    static __device__ __forceinline__ void ld(const float *p, float *a) { a[0] = p[0]; }
+    static __device__ __forceinline__ void st(float *p, const float *a) { p[0] = a[0]; }
+};
+template <> struct RowVec<2> {
+    static __device__ __forceinline__ void ld(const float *p, float *a) {
+        float2 v = *reinterpret_cast<const float2 *>(p); a[0] = v.x; a[1] = v.y; }
+    static __device__ __forceinline__ void st(float *p, const float *a) {
+        *reinterpret_cast<float2 *>(p) = make_float2(a[0], a[1]); }
+};
+template <> struct RowVec<4> {
+    static __device__ __forceinline__ void ld(const float *p, float *a) {
+        float4 v = *reinterpret_cast<const float4 *>(p); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+    static __device__ __forceinline__ void st(float *p, const float *a) {
+        *reinterpret_cast<float4 *>(p) = make_float4(a[0], a[1], a[2], a[3]); }
+};
+template <> struct RowVec<8> {
+    static __device__ __forceinline__ void ld(const float *p, float *a) { RowVec<4>::ld(p, a); RowVec<4>::ld(p + 4, a + 4); }
+    static __device__ __forceinline__ void st(float *p, const float *a) { RowVec<4>::st(p, a); RowVec<4>::st(p + 4, a + 4); }
+};
+
+// out[n][r] = epi( sum_k in[k][r] * w[k*ldw + pos(n)] ),  in: [K][tbp], out: [N][tbp]
 //   BWD == false: out = act(acc + bias[n])
-//   BWD == true : out = act'(out) * acc        (in place on the saved activation)
-template <int RM, bool BWD>
+//   BWD == true : out = act'(saved[n][r]) * acc
+template <int NT, int RM, bool BWD>
 __device__ void tile_gemm(const float *__restrict__ in, int K, const float *__restrict__ w, int ldw,
-                          int N, float *out, int tb, int tbp, const float *bias, int act, float leak) {
-    const int CG = (N + 3) >> 2;
+                          int N, int CG, float *__restrict__ out, const float *__restrict__ saved, int tb,
+                          int tbp, const float *__restrict__ bias, int act, float leak) {
     const int items = CG * (tb / RM);
-    for (int item = threadIdx.x; item < items; item += MQ_NT) {
+    for (int item = threadIdx.x; item < items; item += NT) {
         const int cg = item % CG, rg = item / CG;
         const float *ip = in + rg * RM;
         const float *wp = w + cg * 4;
-        float acc[RM][4];
+        float acc[4][RM];
 #pragma unroll
-        for (int i = 0; i < RM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < RM; ++i) acc[j][i] = 0.0f;
 #pragma unroll 4
         for (int k = 0; k < K; ++k) {
             float a[RM];
@@ -169,74 +278,86 @@ __device__ void tile_gemm(const float *__restrict__ in, int K, const float *__re
             const float4 wv = *reinterpret_cast<const float4 *>(wp + k * ldw);
 #pragma unroll
             for (int i = 0; i < RM; ++i) {
-                acc[i][0] = fmaf(a[i], wv.x, acc[i][0]);
-                acc[i][1] = fmaf(a[i], wv.y, acc[i][1]);
-                acc[i][2] = fmaf(a[i], wv.z, acc[i][2]);
-                acc[i][3] = fmaf(a[i], wv.w, acc[i][3]);
+                acc[0][i] = fmaf(a[i], wv.x, acc[0][i]);
+                acc[1][i] = fmaf(a[i], wv.y, acc[1][i]);
+                acc[2][i] = fmaf(a[i], wv.z, acc[2][i]);
+                acc[3][i] = fmaf(a[i], wv.w, acc[3][i]);
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = cg * 4 + j;
+            const int n = cg + j * CG;
             if (n >= N) continue;
             float *op = out + n * tbp + rg * RM;
-            const float bn = BWD ? 0.0f : bias[n];
+            float res[RM];
+            if (BWD) {
+                float y[RM];
+                RowVec<RM>::ld(saved + n * tbp + rg * RM, y);
 #pragma unroll
-            for (int i = 0; i < RM; ++i) {
-                if (BWD) op[i] = mq_act_grad(op[i], acc[i][j], act, leak);
-                else op[i] = mq_act_apply(acc[i][j] + bn, act, leak);
+                for (int i = 0; i < RM; ++i) res[i] = mq_act_grad(y[i], acc[j][i], act, leak);
+            } else {
+                const float bn = bias[n];
+#pragma unroll
+                for (int i = 0; i < RM; ++i) res[i] = mq_act_apply(acc[j][i] + bn, act, leak);
             }
+            RowVec<RM>::st(op, res);
         }
     }
 }
 
-template <bool BWD>
+template <int NT, bool BWD>
 __device__ __forceinline__ void tile_gemm_any(const float *in, int K, const float *w, int ldw, int N,
-                                              float *out, int tb, int tbp, const float *bias, int act,
-                                              float leak) {
-    const int CG = (N + 3) >> 2;
+                                              int CG, float *out, const float *saved, int tb, int tbp,
+                                              const float *bias, int act, float leak) {
     int rm = 8;
-    while (rm > 1 && (tb / rm) * CG < MQ_NT) rm >>= 1;
-    if (rm == 8) tile_gemm<8, BWD>(in, K, w, ldw, N, out, tb, tbp, bias, act, leak);
-    else if (rm == 4) tile_gemm<4, BWD>(in, K, w, ldw, N, out, tb, tbp, bias, act, leak);
-    else if (rm == 2) tile_gemm<2, BWD>(in, K, w, ldw, N, out, tb, tbp, bias, act, leak);
-    else tile_gemm<1, BWD>(in, K, w, ldw, N, out, tb, tbp, bias, act, leak);
+    while (rm > 1 && (tb / rm) * CG < NT) rm >>= 1;
+    if (rm == 8) tile_gemm<NT, 8, BWD>(in, K, w, ldw, N, CG, out, saved, tb, tbp, bias, act, leak);
+    else if (rm == 4) tile_gemm<NT, 4, BWD>(in, K, w, ldw, N, CG, out, saved, tb, tbp, bias, act, leak);
+    else if (rm == 2) tile_gemm<NT, 2, BWD>(in, K, w, ldw, N, CG, out, saved, tb, tbp, bias, act, leak);
+    else tile_gemm<NT, 1, BWD>(in, K, w, ldw, N, CG, out, saved, tb, tbp, bias, act, leak);
 }
 
-__device__ void forward_tile(const FusedPlan &p, const float *sW, float *sA) {
+template <int NT>
+__device__ void forward_tile(const FusedPlan &p, const float *sW, float *sA, PhaseProf &pp) {
     for (int l = 0; l < p.net.n_layers; ++l) {
-        tile_gemm_any<false>(sA + p.act_off[l], p.net.in[l], sW + p.sw_off[l], p.npad[l], p.net.out[l],
-                             sA + p.act_off[l + 1], p.tb, p.tbp, sW + p.sb_off[l], p.net.act[l],
-                             p.net.leak[l]);
+        tile_gemm_any<NT, false>(sA + p.act_off[l], p.net.in[l], sW + p.sw_off[l], p.npad[l], p.net.out[l],
+                                 p.npad[l] >> 2, sA + p.act_off[l + 1], nullptr, p.tb, p.tbp,
+                                 sW + p.sb_off[l], p.net.act[l], p.net.leak[l]);
         __syncthreads();
+        PHASE_MARK(pp, 20 + l);
     }
 }
 
-// G[k*ldw + n] += sum_r X[k][r] * dZ[n][r]     (4x4 register tile over (k,n))
+// G[k*ldw + pos(n)] += sum_r X[k][r] * dZ[n][r]  and  Gb[n] += sum_r dZ[n][r].
+// Thread tile: k = kg + i*KG, n = ng + j*NG (interleaved, so neighbouring threads read
+// neighbouring rows 4 banks apart: conflict free).  The tiles with kg == 0 also carry the
+// bias sums.  Small layers split the row range over S thread groups; partials go through
+// `scratch` laid out [group][slot][item] and are summed in a fixed order by ALL threads.
+template <int NT>
 __device__ void tile_dw(const float *__restrict__ X, int K, const float *__restrict__ dZ, int N,
-                        float *G, int ldw, int tb, int tbp, float *scratch) {
-    const int KG = (K + 3) >> 2, NG = (N + 3) >> 2;
+                        float *G, float *Gb, int ldw, int tb, int tbp, float *scratch) {
+    const int KG = (K + 3) >> 2, NG = ldw >> 2;
     const int items = KG * NG;
     int S = 1;
-    if (items < MQ_NT) {
-        while (S * 2 * items <= MQ_NT && S * 2 <= tb / 4) S <<= 1;
+    if (items < NT) {
+        while (S * 2 * items <= NT && S * 2 <= tb / 4) S <<= 1;
     }
     const int span = tb / S;
-    const int nloop = (S > 1) ? 1 : (items + MQ_NT - 1) / MQ_NT;
+    const int nloop = (S > 1) ? 1 : (items + NT - 1) / NT;
     for (int it = 0; it < nloop; ++it) {
-        const int lin = threadIdx.x + it * MQ_NT;
+        const int lin = threadIdx.x + it * NT;
         const int s = (S > 1) ? lin / items : 0;
-        const int item = (S > 1) ? lin % items : lin;
+        const int item = (S > 1) ? lin - s * items : lin;
         const bool active = (S > 1) ? (s < S) : (item < items);
-        float acc[4][4];
+        float acc[4][4], bsum[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; bsum[i] = 0.0f; }
         const int kg = item / NG, ng = item - kg * NG;
         if (active) {
             const float *xp[4], *zp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int k = min(kg * 4 + i, K - 1), n = min(ng * 4 + i, N - 1);
+                const int k = min(kg + i * KG, K - 1), n = min(ng + i * NG, N - 1);
                 xp[i] = X + k * tbp;
                 zp[i] = dZ + n * tbp;
             }
@@ -246,6 +367,10 @@ __device__ void tile_dw(const float *__restrict__ X, int K, const float *__restr
                 for (int i = 0; i < 4; ++i) {
                     xv[i] = *reinterpret_cast<const float4 *>(xp[i] + r);
                     zv[i] = *reinterpret_cast<const float4 *>(zp[i] + r);
+                }
+                if (kg == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bsum[j] += (zv[j].x + zv[j].y) + (zv[j].z + zv[j].w);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -262,13 +387,20 @@ __device__ void tile_dw(const float *__restrict__ X, int K, const float *__restr
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int k = kg * 4 + i;
+                    const int k = kg + i * KG;
                     if (k >= K) continue;
+                    float4 *gp = reinterpret_cast<float4 *>(G + k * ldw + ng * 4);
+                    float4 g = *gp;
+                    if (ng < N) g.x += acc[i][0];
+                    if (ng + NG < N) g.y += acc[i][1];
+                    if (ng + 2 * NG < N) g.z += acc[i][2];
+                    if (ng + 3 * NG < N) g.w += acc[i][3];
+                    *gp = g;
+                }
+                if (kg == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int n = ng * 4 + j;
-                        if (n < N) G[k * ldw + n] += acc[i][j];
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (ng + j * NG < N) Gb[ng + j * NG] += bsum[j];
                 }
             }
         } else {
@@ -276,22 +408,29 @@ __device__ void tile_dw(const float *__restrict__ X, int K, const float *__restr
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) scratch[(s * items + item) * 16 + i * 4 + j] = acc[i][j];
+                    for (int j = 0; j < 4; ++j) scratch[(s * DW_SLOTS + i * 4 + j) * items + item] = acc[i][j];
+                if (kg == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) scratch[(s * DW_SLOTS + 16 + j) * items + item] = bsum[j];
+                }
             }
             __syncthreads();
-            if (active && s == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = kg * 4 + i;
-                    if (k >= K) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int n = ng * 4 + j;
-                        if (n >= N) continue;
-                        float sum = 0.0f;
-                        for (int q = 0; q < S; ++q) sum += scratch[(q * items + item) * 16 + i * 4 + j];
-                        G[k * ldw + n] += sum;
-                    }
+            for (int o = threadIdx.x; o < DW_SLOTS * items; o += NT) {
+                const int slot = o / items, im = o - slot * items;
+                const int kg2 = im / NG, ng2 = im - kg2 * NG;
+                if (slot < 16) {
+                    const int i = slot >> 2, j = slot & 3;
+                    const int k = kg2 + i * KG, n = ng2 + j * NG;
+                    if (k >= K || n >= N) continue;
+                    float sum = 0.0f;
+                    for (int q = 0; q < S; ++q) sum += scratch[(q * DW_SLOTS + slot) * items + im];
+                    G[k * ldw + ng2 * 4 + j] += sum;
+                } else {
+                    const int n = ng2 + (slot - 16) * NG;
+                    if (kg2 != 0 || n >= N) continue;
+                    float sum = 0.0f;
+                    for (int q = 0; q < S; ++q) sum += scratch[(q * DW_SLOTS + slot) * items + im];
+                    Gb[n] += sum;
                 }
             }
             __syncthreads();
@@ -299,10 +438,11 @@ __device__ void tile_dw(const float *__restrict__ X, int K, const float *__restr
     }
 }
 
-// G[n] += sum_r Z[n][r]   one warp per row of Z, warp-shuffle reduction
+// G[n] += sum_r Z[n][r]   one warp per row of Z, warp-shuffle reduction (logstd gradient)
+template <int NT>
 __device__ void tile_rowsum(const float *__restrict__ Z, int N, float *G, int tb, int tbp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int n = warp; n < N; n += MQ_NT / 32) {
+    for (int n = warp; n < N; n += NT / 32) {
         float s = 0.0f;
         for (int r = lane * 4; r < tb; r += 128) {
             const float4 v = *reinterpret_cast<const float4 *>(Z + n * tbp + r);
@@ -313,33 +453,35 @@ __device__ void tile_rowsum(const float *__restrict__ Z, int N, float *G, int tb
     }
 }
 
-// Loss-gradient rule on the output tile (one thread per row).  On return sA_out holds
-// d(loss)/d(pre-activation of the last layer); sH holds per-row logstd terms.
-__device__ void head_tile(const FusedPlan &p, const mq_head_t &h, const float *sW, float *sAout,
-                          float *sH, const int32_t *__restrict__ idx, int64_t row0, int64_t n_rows,
+// Loss-gradient rule on the output tile (one thread per row); all inputs are already in
+// shared memory (aux).  Writes d(loss)/d(pre-activation of the last layer) to dzout and the
+// per-row logstd terms to aux.hterm.
+template <int NT>
+__device__ void head_tile(const FusedPlan &p, const mq_head_t &h, const float *sW, const float *sAout,
+                          float *aux, float *dzout, int64_t row0, int64_t n_rows,
                           float *__restrict__ out, float *__restrict__ logp_out) {
     const int N = p.net.n_out, tbp = p.tbp;
     const int lastact = p.net.act[p.net.n_layers - 1];
     const float lastleak = p.net.leak[p.net.n_layers - 1];
-    for (int r = threadIdx.x; r < p.tb; r += MQ_NT) {
+    const float *tgt = aux;
+    float *hterm = aux + N * tbp;
+    const float *misc = aux + 2 * N * tbp;
+    for (int r = threadIdx.x; r < p.tb; r += NT) {
         const int64_t gr = row0 + r;
         const bool valid = gr < n_rows;
-        const int64_t src = (valid && idx) ? (int64_t)idx[gr] : gr;
         if (valid && out)
             for (int n = 0; n < N; ++n) out[gr * N + n] = sAout[n * tbp + r];
         if (!valid) {
-            for (int n = 0; n < N; ++n) { sAout[n * tbp + r] = 0.0f; sH[n * tbp + r] = 0.0f; }
+            for (int n = 0; n < N; ++n) { dzout[n * tbp + r] = 0.0f; hterm[n * tbp + r] = 0.0f; }
             continue;
         }
         if (h.kind == MQ_HEAD_DY) {
-            for (int n = 0; n < N; ++n) {
-                const float y = sAout[n * tbp + r];
-                sAout[n * tbp + r] = mq_act_grad(y, h.dy[src * N + n], lastact, lastleak);
-            }
+            for (int n = 0; n < N; ++n)
+                dzout[n * tbp + r] = mq_act_grad(sAout[n * tbp + r], tgt[n * tbp + r], lastact, lastleak);
         } else if (h.kind == MQ_HEAD_DIFF) {
             for (int n = 0; n < N; ++n) {
                 const float y = sAout[n * tbp + r];
-                sAout[n * tbp + r] = mq_act_grad(y, h.target[src * N + n] - y, lastact, lastleak);
+                dzout[n * tbp + r] = mq_act_grad(y, tgt[n * tbp + r] - y, lastact, lastleak);
             }
         } else if (h.kind == MQ_HEAD_SOFTMAX_CE) {
             float mx = sAout[r];
@@ -349,88 +491,84 @@ __device__ void head_tile(const FusedPlan &p, const mq_head_t &h, const float *s
             const float inv = 1.0f / sum;
             for (int n = 0; n < N; ++n) {
                 const float y = sAout[n * tbp + r];
-                const float dy = h.target[src * N + n] - expf(y - mx) * inv - h.p0 * y;
-                sAout[n * tbp + r] = mq_act_grad(y, dy, lastact, lastleak);
+                const float dy = tgt[n * tbp + r] - expf(y - mx) * inv - h.p0 * y;
+                dzout[n * tbp + r] = mq_act_grad(y, dy, lastact, lastleak);
             }
         } else {
             // diagonal Gaussian: distrib.py:61-68 and its closed-form derivative
             float acc = 0.0f;
             for (int a = 0; a < N; ++a) {
                 const float ls = sW[p.sls_off + a];
-                const float z = (h.target[src * N + a] - sAout[a * tbp + r]) * expf(-ls);
+                const float z = (tgt[a * tbp + r] - sAout[a * tbp + r]) * expf(-ls);
                 acc += ls + 0.5f * z * z;
             }
             const float lp = -(float)N * HALF_LOG_2PI - acc;
             if (logp_out) logp_out[gr] = lp;
             float w;
             if (h.kind == MQ_HEAD_GAUSS_PPO) {
-                const float adv = h.adv[src];
-                const float ratio = expf(lp - h.logp_old[src]);
+                const float adv = misc[r];
+                const float ratio = expf(lp - misc[tbp + r]);
                 const bool kill = (ratio > h.p1 && adv > 0.0f) || (ratio < h.p0 && adv < 0.0f);
                 w = kill ? 0.0f : ratio * adv;
             } else {
-                w = h.dy[src];
+                w = misc[r];
             }
             for (int a = 0; a < N; ++a) {
                 const float inv = expf(-sW[p.sls_off + a]);
                 const float y = sAout[a * tbp + r];
-                const float z = (h.target[src * N + a] - y) * inv;
-                sH[a * tbp + r] = w * (z * z - 1.0f);
-                sAout[a * tbp + r] = mq_act_grad(y, w * z * inv, lastact, lastleak);
+                const float z = (tgt[a * tbp + r] - y) * inv;
+                hterm[a * tbp + r] = w * (z * z - 1.0f);
+                dzout[a * tbp + r] = mq_act_grad(y, w * z * inv, lastact, lastleak);
             }
         }
     }
 }
 
-__device__ void backward_tile(const FusedPlan &p, const float *sWt, float *sA, float *sG,
-                              float *scratch, bool gauss) {
+// Backward over one tile.  On entry dZ of the last layer is in DZ buffer 0.
+template <int NT>
+__device__ void backward_tile(const FusedPlan &p, const Smem &sm, bool gauss, PhaseProf &pp) {
     const int L = p.net.n_layers;
-    if (gauss) tile_rowsum(sA + p.head_off, p.net.n_out, sG + p.sls_off, p.tb, p.tbp);
+    float *sA = sm.A, *sG = sm.G;
+    if (gauss) tile_rowsum<NT>(sA + p.aux_off + p.net.n_out * p.tbp, p.net.n_out, sG + p.sls_off, p.tb, p.tbp);
+    int cur = 0;
     for (int l = L - 1; l >= 0; --l) {
-        const float *dZ = sA + p.act_off[l + 1];
-        tile_rowsum(dZ, p.net.out[l], sG + p.sb_off[l], p.tb, p.tbp);
-        tile_dw(sA + p.act_off[l], p.net.in[l], dZ, p.net.out[l], sG + p.sw_off[l], p.npad[l], p.tb,
-                p.tbp, scratch);
-        __syncthreads();
+        const float *dZ = sm.DZ + cur * p.dz_floats;
         if (l > 0) {
-            tile_gemm_any<true>(dZ, p.net.out[l], sWt + p.swt_off[l], p.kpad[l], p.net.in[l],
-                                sA + p.act_off[l], p.tb, p.tbp, nullptr, p.net.act[l - 1],
-                                p.net.leak[l - 1]);
-            __syncthreads();
+            // dZ_{l-1} = (dZ_l W_l^T) * act'(A_l)  -> other ping-pong buffer (no barrier vs dW_l)
+            tile_gemm_any<NT, true>(dZ, p.net.out[l], sm.Wt + p.swt_off[l], p.ldwt[l], p.net.in[l],
+                                    p.kpad[l] >> 2, sm.DZ + (cur ^ 1) * p.dz_floats, sA + p.act_off[l],
+                                    p.tb, p.tbp, nullptr, p.net.act[l - 1], p.net.leak[l - 1]);
+            PHASE_MARK(pp, 10 + 3 * l);
         }
+        tile_dw<NT>(sA + p.act_off[l], p.net.in[l], dZ, p.net.out[l], sG + p.sw_off[l], sG + p.sb_off[l],
+                    p.npad[l], p.tb, p.tbp, sm.S);
+        __syncthreads();
+        PHASE_MARK(pp, 9 + 3 * l);
+        cur ^= 1;
     }
-}
-
-// flat[j] = f(padded accumulator) for every parameter j
-template <typename F>
-__device__ __forceinline__ void for_each_param(const FusedPlan &p, F f) {
-    for (int l = 0; l < p.net.n_layers; ++l) {
-        const int K = p.net.in[l], N = p.net.out[l];
-        for (int e = threadIdx.x; e < K * N; e += MQ_NT) {
-            const int k = e / N, n = e - k * N;
-            f(p.net.w_off[l] + e, p.sw_off[l] + k * p.npad[l] + n, l, k, n);
-        }
-        for (int n = threadIdx.x; n < N; n += MQ_NT) f(p.net.b_off[l] + n, p.sb_off[l] + n, -1, 0, n);
-    }
-    if (p.net.logstd_off >= 0)
-        for (int a = threadIdx.x; a < p.net.n_out; a += MQ_NT) f(p.net.logstd_off + a, p.sls_off + a, -1, 0, a);
 }
 
 // ---- kernels ---------------------------------------------------------------------------
+static long long *g_phase_prof = nullptr;
+extern "C" int mq_debug_set_phase_buffer(void *dev_buf) { g_phase_prof = (long long *)dev_buf; return MQ_OK; }
+long long *mq_phase_prof_ptr() { return g_phase_prof; }
+
 __global__ void __launch_bounds__(MQ_NT)
 fused_forward_kernel(FusedPlan p, const float *__restrict__ theta, const float *__restrict__ x,
                      const int32_t *__restrict__ idx, int64_t n_rows, float *__restrict__ out,
                      const float *__restrict__ sample, float *__restrict__ logp) {
     MQ_SHARED_BYTES(smem);
-    float *sW = smem_W(p, smem), *sA = smem_A(p, smem);
-    load_weights(p, theta, nullptr, sW, nullptr);
+    Smem sm(p, smem);
+    float *sW = sm.W, *sA = sm.A;
+    load_weights<MQ_NT>(p, theta, nullptr, sW, nullptr);
     const int64_t ntiles = (n_rows + p.tb - 1) / p.tb;
     const int N = p.net.n_out, tbp = p.tbp;
+    PhaseProf pp = {nullptr, 0};
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * p.tb;
-        load_rows(p, x, idx, row0, n_rows, sA + p.act_off[0]);
+        load_rows<MQ_NT>(p, x, idx, row0, n_rows, sA + p.act_off[0]);
         __syncthreads();
-        forward_tile(p, sW, sA);
+        forward_tile<MQ_NT>(p, sW, sA, pp);
         const float *sO = sA + p.act_off[p.net.n_layers];
         for (int r = threadIdx.x; r < p.tb; r += MQ_NT) {
             const int64_t gr = row0 + r;
@@ -457,26 +595,28 @@ fused_grad_kernel(FusedPlan p, const float *__restrict__ theta, const float *__r
                   float *__restrict__ grad_or_partial, int direct, float *__restrict__ out,
                   float *__restrict__ logp) {
     MQ_SHARED_BYTES(smem);
-    float *sW = smem_W(p, smem), *sA = smem_A(p, smem), *sWt = smem_Wt(p, smem);
-    float *sG = smem_G(p, smem), *sS = smem_S(p, smem);
-    load_weights(p, theta, nullptr, sW, sWt);
-    for (int e = threadIdx.x; e < p.p_pad; e += MQ_NT) sG[e] = 0.0f;
+    Smem sm(p, smem);
+    load_weights<MQ_NT>(p, theta, nullptr, sm.W, sm.Wt);
+    for (int e = threadIdx.x; e < p.p_pad; e += MQ_NT) sm.G[e] = 0.0f;
     const bool gauss = head.kind == MQ_HEAD_GAUSS_LOGP || head.kind == MQ_HEAD_GAUSS_PPO;
     const int64_t ntiles = (n_rows + p.tb - 1) / p.tb;
+    PhaseProf pp = {nullptr, 0};
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * p.tb;
-        load_rows(p, x, idx, row0, n_rows, sA + p.act_off[0]);
+        load_rows<MQ_NT>(p, x, idx, row0, n_rows, sm.A + p.act_off[0]);
+        load_head_inputs<MQ_NT>(p, head, idx, row0, n_rows, sm.A + p.aux_off);
         __syncthreads();
-        forward_tile(p, sW, sA);
-        head_tile(p, head, sW, sA + p.act_off[p.net.n_layers], sA + p.head_off, idx, row0, n_rows, out, logp);
+        forward_tile<MQ_NT>(p, sm.W, sm.A, pp);
+        head_tile<MQ_NT>(p, head, sm.W, sm.A + p.act_off[p.net.n_layers], sm.A + p.aux_off, sm.DZ, row0,
+                         n_rows, out, logp);
         __syncthreads();
-        backward_tile(p, sWt, sA, sG, sS, gauss);
-        __syncthreads();
+        backward_tile<MQ_NT>(p, sm, gauss, pp);
     }
     float *dst = direct ? grad_or_partial : grad_or_partial + (int64_t)blockIdx.x * p.net.n_params;
     const float sc = direct ? scale : 1.0f;
-    for_each_param(p, [&](int flat, int pad, int, int, int) { dst[flat] = sG[pad] * sc; });
+    const float *sG = sm.G;
+    for_each_param<MQ_NT>(p, [&](int flat, int pad) { dst[flat] = sG[pad] * sc; });
 }
 
 __global__ void __launch_bounds__(MQ_NT)
@@ -507,20 +647,32 @@ template <> struct AdamMath<float> {
     }
 };
 
-// One CTA runs n_steps dependent optimiser steps: weights, their transposes and the
-// gradient accumulators stay in shared memory for the whole launch.
-template <typename ST>
-__global__ void __launch_bounds__(MQ_NT)
+// One CTA runs n_steps dependent optimiser steps: weights, their transposes, the gradient
+// accumulators and (fp32 state) the Adam moments stay in shared memory for the whole launch.
+template <typename ST, bool ONCHIP, int NT>
+__global__ void __launch_bounds__(NT)
 fused_train_kernel(FusedPlan p, float *__restrict__ theta, ST *__restrict__ value, ST *__restrict__ am,
                    ST *__restrict__ av, const float *__restrict__ x, mq_head_t head,
                    const int32_t *__restrict__ idx_table, int n_steps, int mb, double beta1,
-                   double beta2, double tw1, double tw2, double lr, double eps,
-                   double *__restrict__ tw_out) {
+                   double beta2, double tw1, double tw2, double lr, double eps, long long *prof) {
     MQ_SHARED_BYTES(smem);
-    float *sW = smem_W(p, smem), *sA = smem_A(p, smem), *sWt = smem_Wt(p, smem);
-    float *sG = smem_G(p, smem), *sS = smem_S(p, smem);
-    load_weights(p, theta, nullptr, sW, sWt);
-    for (int e = threadIdx.x; e < p.p_pad; e += MQ_NT) sG[e] = 0.0f;
+    Smem sm(p, smem);
+    float *sW = sm.W, *sG = sm.G, *sM = sm.M, *sV = sm.V;
+    PhaseProf pp = {prof, 0};
+#ifndef MQ_EMU
+    if (prof && threadIdx.x == 0) pp.last = clock64();
+#endif
+    load_weights<NT>(p, theta, nullptr, sW, sm.Wt);
+    for (int e = threadIdx.x; e < p.p_pad; e += NT) sG[e] = 0.0f;
+    if (ONCHIP) {
+        for (int e = threadIdx.x; e < 2 * p.p_pad; e += NT) sM[e] = 0.0f;
+        __syncthreads();
+        for_each_param<NT>(p, [&](int flat, int pad) {
+            sW[pad] = (float)value[flat]; sM[pad] = (float)am[flat]; sV[pad] = (float)av[flat];
+        });
+        __syncthreads();
+        refresh_transposes<NT>(p, sW, sm.Wt);
+    }
     const bool gauss = head.kind == MQ_HEAD_GAUSS_LOGP || head.kind == MQ_HEAD_GAUSS_PPO;
     const int ntiles = (mb + p.tb - 1) / p.tb;
     const float inv_mb = 1.0f / (float)mb;
@@ -529,32 +681,67 @@ fused_train_kernel(FusedPlan p, float *__restrict__ theta, ST *__restrict__ valu
         const int32_t *idx = idx_table + (int64_t)step * mb;
         for (int tile = 0; tile < ntiles; ++tile) {
             const int64_t row0 = (int64_t)tile * p.tb;
-            load_rows(p, x, idx, row0, mb, sA + p.act_off[0]);
+            load_rows<NT>(p, x, idx, row0, mb, sm.A + p.act_off[0]);
+            load_head_inputs<NT>(p, head, idx, row0, mb, sm.A + p.aux_off);
             __syncthreads();
-            forward_tile(p, sW, sA);
-            head_tile(p, head, sW, sA + p.act_off[p.net.n_layers], sA + p.head_off, idx, row0, mb,
-                      nullptr, nullptr);
+            PHASE_MARK(pp, 0);
+            forward_tile<NT>(p, sW, sm.A, pp);
+            head_tile<NT>(p, head, sW, sm.A + p.act_off[p.net.n_layers], sm.A + p.aux_off, sm.DZ, row0, mb,
+                          nullptr, nullptr);
             __syncthreads();
-            backward_tile(p, sWt, sA, sG, sS, gauss);
-            __syncthreads();
+            PHASE_MARK(pp, 2);
+            backward_tile<NT>(p, sm, gauss, pp);
         }
         tw1 = tw1 * beta1 + 1.0;                       // _normalize.py:18-23 with weight 1
         tw2 = tw2 * beta2 + 1.0;
         const ST c1 = (ST)(1.0 / tw1), c2 = (ST)(1.0 / tw2);
-        for_each_param(p, [&](int flat, int pad, int l, int k, int n) {
-            const float g = sG[pad] * inv_mb;          // batch mean (basicnet.py:242-249)
-            sG[pad] = 0.0f;
-            ST val = value[flat], m = am[flat], v = av[flat];
-            AdamMath<ST>::step(val, m, v, (ST)g, c1, c2, (ST)lr, (ST)eps);
-            value[flat] = val; am[flat] = m; av[flat] = v;
-            const float w = (float)val;                // load_params: fp64 -> fp32 (basicnet.py:56)
-            theta[flat] = w;
-            sW[pad] = w;
-            if (l >= 1) sWt[p.swt_off[l] + n * p.kpad[l] + k] = w;
-        });
+        if (ONCHIP) {
+            // fp32 state: moments in shared memory, the value IS the weight copy sW.  Straight
+            // loop over the padded layout (padding stays 0: g = m = v = 0).
+            for (int e = threadIdx.x; e < p.p_pad; e += NT) {
+                const float g = sG[e] * inv_mb;        // batch mean (basicnet.py:242-249)
+                sG[e] = 0.0f;
+                float val = sW[e], m = sM[e], v = sV[e];
+                AdamMath<float>::step(val, m, v, g, (float)c1, (float)c2, (float)lr, (float)eps);
+                sW[e] = val; sM[e] = m; sV[e] = v;
+            }
+        } else {
+            // state in global memory (L2 resident): issue the loads of 4 elements together
+            const int P = p.net.n_params;
+            for (int j0 = threadIdx.x; j0 < P; j0 += 4 * NT) {
+                ST val[4], m[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j < P) { val[u] = value[j]; m[u] = am[j]; v[u] = av[j]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j >= P) continue;
+                    const int pad = flat_to_pad(p, j);
+                    const float g = sG[pad] * inv_mb;
+                    sG[pad] = 0.0f;
+                    AdamMath<ST>::step(val[u], m[u], v[u], (ST)g, c1, c2, (ST)lr, (ST)eps);
+                    value[j] = val[u]; am[j] = m[u]; av[j] = v[u];
+                    const float w = (float)val[u];     // load_params: fp64 -> fp32 (basicnet.py:56)
+                    theta[j] = w;
+                    sW[pad] = w;
+                }
+            }
+        }
         __syncthreads();
+        PHASE_MARK(pp, 4);
+        refresh_transposes<NT>(p, sW, sm.Wt);
+        __syncthreads();
+        PHASE_MARK(pp, 5);
     }
-    if (threadIdx.x == 0 && tw_out) { tw_out[0] = tw1; tw_out[1] = tw2; }
+    if (ONCHIP) {
+        for_each_param<NT>(p, [&](int flat, int pad) {
+            value[flat] = (ST)sW[pad]; am[flat] = (ST)sM[pad]; av[flat] = (ST)sV[pad];
+            theta[flat] = sW[pad];
+        });
+    }
 }
 
 // One CTA per population member: theta + noise[p] is built in shared memory, the shared
@@ -565,17 +752,19 @@ es_eval_kernel(FusedPlan p, const float *__restrict__ theta, const float *__rest
                const float *__restrict__ ret_coef, float *__restrict__ returns) {
     MQ_SHARED_BYTES(smem);
     __shared__ float red[MQ_NT / 32];
-    float *sW = smem_W(p, smem), *sA = smem_A(p, smem);
+    Smem sm(p, smem);
+    float *sW = sm.W, *sA = sm.A;
     const int N = p.net.n_out, tbp = p.tbp;
     const int64_t ntiles = (n_obs + p.tb - 1) / p.tb;
+    PhaseProf pp = {nullptr, 0};
     for (int64_t member = blockIdx.x; member < n_members; member += gridDim.x) {
-        load_weights(p, theta, noise + member * p.net.n_params, sW, nullptr);
+        load_weights<MQ_NT>(p, theta, noise + member * p.net.n_params, sW, nullptr);
         float acc = 0.0f;
         for (int64_t tile = 0; tile < ntiles; ++tile) {
             const int64_t row0 = tile * p.tb;
-            load_rows(p, obs, nullptr, row0, n_obs, sA + p.act_off[0]);
+            load_rows<MQ_NT>(p, obs, nullptr, row0, n_obs, sA + p.act_off[0]);
             __syncthreads();
-            forward_tile(p, sW, sA);
+            forward_tile<MQ_NT>(p, sW, sA, pp);
             const float *sO = sA + p.act_off[p.net.n_layers];
             for (int r = threadIdx.x; r < p.tb; r += MQ_NT)
                 if (row0 + r < n_obs)
@@ -610,6 +799,11 @@ es_wsum_finish_kernel(const double *__restrict__ partial, int nsplit, int64_t n_
         out[j] = s * scale;
     }
 }
+
+// row-owner-warp persistent chain (mq_chain.cu); MQ_ERR_UNSUPPORTED if the net does not fit it
+int mq_chain_train_f32(const mq_net_t *net, float *theta, float *value, float *m, float *v, const float *x,
+                       const mq_head_t *head, const int32_t *idx_table, int32_t n_steps, int32_t mb,
+                       double beta1, double beta2, const double *tw, double lr, double eps, void *stream);
 
 // ---- host entry points -----------------------------------------------------------------
 static int fused_net_check(const mq_net_t *net, const char *what) {
@@ -742,26 +936,37 @@ extern "C" int mq_fused_train(const mq_net_t *net, float *theta, void *value, vo
     MQ_REQUIRE(theta && value && m && v && x && idx_table && tw_host, MQ_ERR_INVALID,
                "mq_fused_train: null pointer");
     FusedPlan p;
-    MQ_REQUIRE(plan_choose(net, mb, 1, &p) > 0, MQ_ERR_UNSUPPORTED,
-               "mq_fused_train: net does not fit in shared memory");
+#define MQ_TRAIN_GO(ST, ONCHIP)                                                                      \
+    do {                                                                                             \
+        auto kfn = fused_train_kernel<ST, ONCHIP, TRAIN_NT>;                                         \
+        rc = set_smem(kfn, p.smem_bytes, "mq_fused_train");                                          \
+        if (rc != MQ_OK) return rc;                                                                  \
+        MQ_LAUNCH(kfn, 1, TRAIN_NT, p.smem_bytes, stream, p, theta, (ST *)value, (ST *)m, (ST *)v,   \
+                  x, *head, idx_table, (int)n_steps, (int)mb, beta1, beta2, tw_host[0], tw_host[1],  \
+                  lr, eps, g_phase_prof);                                                            \
+    } while (0)
     if (state_dtype == MQ_F64) {
-        auto kfn = fused_train_kernel<double>;
-        rc = set_smem(kfn, p.smem_bytes, "mq_fused_train");
-        if (rc != MQ_OK) return rc;
-        MQ_LAUNCH(kfn, 1, MQ_NT, p.smem_bytes, stream, p, theta, (double *)value, (double *)m,
-                  (double *)v, x, *head, idx_table, (int)n_steps, (int)mb, beta1, beta2, tw_host[0],
-                  tw_host[1], lr, eps, (double *)nullptr);
+        MQ_REQUIRE(plan_choose(net, mb, 1, &p, 0, TRAIN_NT) > 0, MQ_ERR_UNSUPPORTED,
+                   "mq_fused_train: net does not fit in shared memory");
+        MQ_TRAIN_GO(double, false);
     } else if (state_dtype == MQ_F32) {
-        auto kfn = fused_train_kernel<float>;
-        rc = set_smem(kfn, p.smem_bytes, "mq_fused_train");
-        if (rc != MQ_OK) return rc;
-        MQ_LAUNCH(kfn, 1, MQ_NT, p.smem_bytes, stream, p, theta, (float *)value, (float *)m, (float *)v,
-                  x, *head, idx_table, (int)n_steps, (int)mb, beta1, beta2, tw_host[0], tw_host[1], lr,
-                  eps, (double *)nullptr);
+        rc = mq_chain_train_f32(net, theta, (float *)value, (float *)m, (float *)v, x, head, idx_table,
+                                n_steps, mb, beta1, beta2, tw_host, lr, eps, stream);
+        if (rc != MQ_OK && rc != MQ_ERR_UNSUPPORTED) return rc;
+        if (rc == MQ_OK) {
+            // launched by the row-owner-warp kernel
+        } else if (plan_choose(net, mb, 1, &p, 1, TRAIN_NT) > 0) {
+            MQ_TRAIN_GO(float, true);
+        } else {
+            MQ_REQUIRE(plan_choose(net, mb, 1, &p, 0, TRAIN_NT) > 0, MQ_ERR_UNSUPPORTED,
+                       "mq_fused_train: net does not fit in shared memory");
+            MQ_TRAIN_GO(float, false);
+        }
     } else {
         mq_set_error("mq_fused_train: unknown state dtype %d", state_dtype);
         return MQ_ERR_INVALID;
     }
+#undef MQ_TRAIN_GO
     MQ_CHECK_LAUNCH("mq_fused_train");
     // the total-weight recurrence is data independent: mirror it on the host
     for (int s = 0; s < n_steps; ++s) {

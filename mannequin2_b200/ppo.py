@@ -1,0 +1,136 @@
+"""Fused PPO update: one chunk of benchmarks/ppo.py:22-40 + benchmarks/gae.py:34-75.
+
+Everything the reference does per 2048-step chunk in ~1,300 NumPy calls runs as a
+handful of launches, with the two 300-step optimiser chains (value predictor,
+policy) each inside ONE persistent kernel (csrc/mq_fused.cu: mq_fused_train) and
+running concurrently on two CUDA streams:
+
+    value  = V(obs[0..N])                       mq_fused_forward        gae.py:43-45
+    adv,ret= GAE(rew, value, done)              mq_gae                  gae.py:48-56,69
+    300 x value step on (obs[idx], ret[idx])    mq_fused_train (DIFF)   gae.py:71-73,20-23
+    adv_n  = tanh(RunningNormalize_h2(adv))     mq_col_mean/cov/apply   ppo.py:24-25
+    logp0  = logprob(obs, act)                  mq_fused_forward        ppo.py:27
+    300 x PPO step on minibatch idx             mq_fused_train (PPO)    ppo.py:29-40
+
+Random draws (minibatch index tables) are inputs.  With a process
+group (mannequin2_b200.dist) large minibatches are sharded by rows and the flat
+gradient is all-reduced once per optimiser step.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib
+from ._adam import Adam
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_GAUSS_PPO, MQ_F32, MQ_F64, MqHead
+from ._normalize import RunningNormalize
+from .basicnet import normed_columns
+
+
+def init_mlp(n_in, widths, head_scale):
+    """Flat float32 parameters, same draws as Affine() stacks (basicnet.py:265-267,300-311)."""
+    parts, k = [], n_in
+    for i, n in enumerate(widths):
+        w = normed_columns(k, n)
+        if i == len(widths) - 1:
+            w = w * np.float32(head_scale)
+        parts += [w.reshape(-1).astype(np.float32), np.zeros(n, np.float32)]
+        k = n
+    return np.concatenate(parts)
+
+
+class _Net(object):
+    """Parameters + Adam state of one net, all device resident."""
+
+    def __init__(self, net, theta_host, horizon, state_dtype):
+        self.net = net
+        self.theta = D.from_host(theta_host, np.float32)
+        self.opt = Adam(theta_host, horizon=horizon, state_dtype=state_dtype)
+        self.code = self.opt._code
+
+    def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8):
+        value, m, v, _ = self.opt.state()
+        tw = (ctypes.c_double * 2)(*self.opt._tw)
+        D.call("mq_fused_train", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(value), D.ptr(m), D.ptr(v),
+               self.code, D.ptr(x), ctypes.byref(head), D.ptr(idx_table), n_steps, mb, self.opt._b1,
+               self.opt._b2, tw, lr, eps, D.stream())
+        self.opt._tw = [tw[0], tw[1]]
+        self.opt._out = None
+
+
+class PPOUpdater(object):
+    def __init__(self, n_obs, n_act, *, hid=64, n_hid=2, gam=0.99, lam=0.95, pol_lr=3e-4, val_lr=3e-3,
+                 horizon=10, clip=(0.8, 1.2), norm_horizon=2, state_dtype="float32",
+                 policy_params=None, value_params=None):
+        widths = [hid] * n_hid
+        acts = [ACT_TANH] * n_hid + [ACT_NONE]
+        pnet = _lib.make_net(n_obs, widths + [n_act], acts, logstd=True)
+        vnet = _lib.make_net(n_obs, widths + [1], acts)
+        if policy_params is None:                                   # policy.py:7-27, Gauss logstd zeros
+            policy_params = np.concatenate([init_mlp(n_obs, widths + [n_act], 0.1), np.zeros(n_act, np.float32)])
+        if value_params is None:                                    # gae.py:12-18
+            value_params = init_mlp(n_obs, widths + [1], 0.1)
+        assert len(policy_params) == pnet.n_params and len(value_params) == vnet.n_params
+        self.n_obs, self.n_act = n_obs, n_act
+        self.gam, self.lam, self.pol_lr, self.val_lr, self.clip = gam, lam, pol_lr, val_lr, clip
+        self.policy = _Net(pnet, np.asarray(policy_params, np.float32), horizon, state_dtype)
+        self.value = _Net(vnet, np.asarray(value_params, np.float32), horizon, state_dtype)
+        self.normalize = RunningNormalize(horizon=norm_horizon)
+        self._side = torch.cuda.Stream()
+        self._ev_gae, self._ev_val = torch.cuda.Event(), torch.cuda.Event()
+        self._bufs = {}
+
+    def _buf(self, name, n, dtype=torch.float32):
+        t = self._bufs.get(name)
+        if t is None or t.numel() != n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype, device=D.device())
+            self._bufs[name] = t
+        return t
+
+    def update_dev(self, obs, act, rew, done, val_idx, pol_idx):
+        """All arguments are device tensors: obs f32[N+1,D], act f32[N,A], rew f32[N],
+        done u8[N], val_idx / pol_idx i32[steps, mb].  Returns device (adv, ret)."""
+        lib = _lib.lib()
+        n = rew.numel()
+        assert obs.numel() == (n + 1) * self.n_obs and act.numel() == n * self.n_act
+        pol, val = self.policy, self.value
+        value = self._buf("value", n + 1)
+        adv, ret = self._buf("adv", n), self._buf("ret", n)
+        adv_n, logp0 = self._buf("adv_n", n), self._buf("logp0", n)
+        main = torch.cuda.current_stream()
+        # value predictions for every state incl. the bootstrap state (gae.py:43-45)
+        D.call("mq_fused_forward", ctypes.byref(val.net), D.ptr(val.theta), D.ptr(obs), None, n + 1,
+               D.ptr(value), None, None, D.stream())
+        wsb = lib.mq_scan_ws_bytes(n)
+        ws = D.workspace("scan", wsb)
+        D.call("mq_gae", D.ptr(rew), D.ptr(value), D.ptr(done), n, self.gam, self.lam, D.ptr(adv), D.ptr(ret),
+               D.ptr(ws), wsb, D.stream())
+        self._ev_gae.record(main)
+        # value predictor chain on the side stream (gae.py:66-73)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_gae)
+            head = MqHead()
+            head.kind, head.target = HEAD_DIFF, D.ptr(ret)
+            val.train(obs, head, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
+            self._ev_val.record(self._side)
+        # policy chain on the main stream (ppo.py:24-40)
+        self.normalize.update_dev(adv, n)
+        self.normalize.apply_dev(adv, n, out=adv_n, fuse_tanh=True)
+        D.call("mq_fused_forward", ctypes.byref(pol.net), D.ptr(pol.theta), D.ptr(obs), None, n, None,
+               D.ptr(act), D.ptr(logp0), D.stream())
+        head = MqHead()
+        head.kind, head.p0, head.p1 = HEAD_GAUSS_PPO, self.clip[0], self.clip[1]
+        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
+        pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
+        main.wait_event(self._ev_val)
+        return adv, ret
+
+    def update(self, obs, act, rew, done, val_idx, pol_idx):
+        """Host arrays in, new (policy_params, value_params) host arrays out (end-to-end call)."""
+        up = lambda a, dt: D.from_host(np.ascontiguousarray(a, dtype=dt))
+        self.update_dev(up(obs, np.float32), up(act, np.float32), up(rew, np.float32),
+                        up(np.asarray(done, dtype=np.uint8), np.uint8), up(val_idx, np.int32),
+                        up(pol_idx, np.int32))
+        return D.to_host(self.policy.theta), D.to_host(self.value.theta)

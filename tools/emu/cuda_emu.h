@@ -121,6 +121,7 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 template <typename T>
 static inline T __ldg(const T *p) { return *p; }
