@@ -193,7 +193,332 @@ class PPOWorkload(object):
             self.norm, o, a, r, d.astype(bool), vi, pi)
 
 
-WORKLOADS = {"ppo": PPOWorkload}
+class PPOLargeWorkload(object):
+    """BASELINE.json configs[2]: large-batch PPO.  Per GPU: 2^20 synthetic transitions in
+    variable-length episodes (done p=1/500, forced cut every 1000 steps), one update =
+    value forward (N+1), GAE, advantage normalise+tanh, old log-probs (N), then 10 epochs x 16
+    permutation minibatches of 65,536 rows for the value net AND for the policy (160 + 160
+    Adam steps).  With G GPUs every rank holds its own 2^20-transition shard and the global
+    minibatch is G x 65,536 rows: one NCCL all-reduce of the flat gradient per optimiser step
+    (weak scaling)."""
+    name = "ppo_large_1Mx10epochsx65536 (configs[2])"
+    metric = "ppo_update_transitions_per_s"
+    unit = "transitions/s"
+    N, EPOCHS, MB = 1 << 20, 10, 65536
+
+    def __init__(self, n_rollouts=2, seed=1, n=None, epochs=None):
+        self.N = n or self.N
+        self.EPOCHS = epochs or self.EPOCHS
+        self.MB = min(self.MB, self.N)
+        rs = np.random.RandomState(seed)
+        self.rollouts = []
+        per = self.N // self.MB
+        for _ in range(n_rollouts):
+            o, a, r, d = ppo_rollout(rs, self.N, p_done=1.0 / 500, cut=1000)
+            tabs = []
+            for _t in range(2):
+                t = np.concatenate([rs.permutation(self.N).astype(np.int32).reshape(per, self.MB)
+                                    for _e in range(self.EPOCHS)])
+                tabs.append(t)
+            self.rollouts.append((o, a, r, d, tabs[0], tabs[1]))
+        self.units_per_step = self.N
+        self.steps_per_net = self.EPOCHS * per
+
+    def setup_gpu(self):
+        import torch
+        from mannequin2_b200 import _device as D
+        from mannequin2_b200.ppo import PPOUpdater
+        np.random.seed(0)
+        self.torch, self.D = torch, D
+        self.upd = PPOUpdater(11, 3)
+        self.dev = [tuple(D.from_host(x) for x in r) for r in self.rollouts]
+        self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r) for r in self.rollouts[:1]]
+        self.out_pinned = (torch.empty(5126, dtype=torch.float32).pin_memory(),
+                           torch.empty(4993, dtype=torch.float32).pin_memory())
+        self.h2d = sum(x.nbytes for x in self.rollouts[0])
+        self.d2h = (5126 + 4993) * 4
+
+    def step_gpu(self, i):
+        self.upd.update_dev(*self.dev[i % len(self.dev)])
+
+    def step_e2e(self, i):
+        dev = self.D.device()
+        args = [x.to(dev, non_blocking=True) for x in self.pinned[0]]
+        self.upd.update_dev(*args)
+        self.out_pinned[0].copy_(self.upd.policy.theta, non_blocking=True)
+        self.out_pinned[1].copy_(self.upd.value.theta, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    def launches_per_step(self):
+        return 11 + 2 * self.steps_per_net * 3      # (+ NCCL all-reduces, not ours, when sharded)
+
+    def dominant_kernel(self, peaks):
+        """fused_grad_kernel on one 65,536-row policy minibatch, timed alone on its stream."""
+        import ctypes as C
+        t, D, upd = self.torch, self.D, self.upd
+        from mannequin2_b200 import _lib as L
+        obs, act, rew, done, vi, pi = self.dev[0]
+        head = L.MqHead()
+        head.kind, head.p0, head.p1 = L.HEAD_GAUSS_PPO, 0.8, 1.2
+        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(upd._bufs["adv_n"]), D.ptr(upd._bufs["logp0"])
+        net = upd.policy.net
+        wsb = L.lib().mq_fused_ws_bytes(C.byref(net), self.MB)
+        ws = D.workspace("bench", wsb)
+        times = []
+        for k in range(8):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            D.call("mq_fused_grad", C.byref(net), D.ptr(upd.policy.theta), D.ptr(obs), D.ptr(pi) + k * self.MB * 4,
+                   self.MB, C.byref(head), 1.0 / self.MB, D.ptr(upd.policy.grad), None, None, D.ptr(ws), wsb,
+                   D.stream())
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[2:]))
+        bytes_per_launch = self.MB * 64                    # SURVEY 8d: 64 B gathered per minibatch row
+        flops = self.MB * 28544.0                          # SURVEY 8d: 28,544 FLOP per row (fwd+dW+dX)
+        ach = bytes_per_launch / (ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        return dict(bound="hbm", kernel="fused_grad_kernel (policy, 65536 rows; launch includes fused_reduce_kernel)",
+                    achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
+                    peak_source=peaks["source"], ms_per_launch=ms,
+                    limiter="fp32 FFMA pipe: 446 FLOP per algorithmic byte, far above the fp32 ridge (~11)",
+                    fp32_tflops=flops / (ms * 1e-3) / 1e12, fp32_peak_tflops_nominal=fp32_peak,
+                    fp32_frac=flops / (ms * 1e-3) / 1e12 / fp32_peak)
+
+    # CPU arm: the same per-transition work on a bounded sample
+    SAMPLE_N = 65536
+
+    def setup_cpu(self):
+        PPOWorkload.setup_cpu(self)
+        rs = np.random.RandomState(5)
+        n = self.SAMPLE_N
+        o, a, r, d = ppo_rollout(rs, n, p_done=1.0 / 500, cut=1000)
+        tabs = [np.stack([rs.permutation(n).astype(np.int32) for _e in range(self.EPOCHS)]) for _t in range(2)]
+        self.cpu_sample = (o, a, r, d, tabs[0], tabs[1])
+
+    def step_cpu(self, i):
+        o, a, r, d, vi, pi = self.cpu_sample
+        self.pol_theta, self.val_theta, _ = self.O.ppo_update(
+            self.pol_theta, self.pol_spec, self.pol_opt, self.val_theta, self.val_spec, self.val_opt,
+            self.norm, o, a, r, d.astype(bool), vi, pi)
+
+    cpu_units_per_step = SAMPLE_N
+    cpu_sample_desc = ("65,536 transitions, 10 epochs x 1 minibatch of 65,536 rows per net "
+                       "(same 10 passes per transition as the full workload)")
+
+
+class MLPWorkload(object):
+    """BASELINE.json configs[0]: mnist/mlp.py step -- 784-128-128-10 LReLU(0.1) MLP (script shape,
+    SURVEY F9), softmax-CE(+0.01 logit L2) gradient, Adam(h=10, lr 1e-3), batch 128 drawn by index
+    from 60,000 synthetic MNIST-shaped images.  One bench step = one block of 32 optimiser steps
+    (one CUDA-graph replay)."""
+    name = "mlp_784-128-128-10_batch128 (configs[0])"
+    metric = "mlp_fwd_bwd_adam_samples_per_s"
+    unit = "samples/s"
+    B, BLOCK = 128, 32
+
+    def __init__(self, seed=1, n_data=60000):
+        rs = np.random.RandomState(seed)
+        self.x = rs.rand(n_data, 784).astype(np.float32)
+        self.y = np.eye(10, dtype=np.float32)[rs.randint(10, size=n_data)]
+        self.tables = [rs.randint(n_data, size=(self.BLOCK, self.B)).astype(np.int32) for _ in range(16)]
+        self.units_per_step = self.BLOCK * self.B
+
+    def setup_gpu(self):
+        import torch
+        from mannequin2_b200 import _device as D
+        from mannequin2_b200.mlp import MLPTrainer
+        np.random.seed(0)
+        self.torch, self.D = torch, D
+        self.tr = MLPTrainer(batch=self.B, graph_steps=self.BLOCK)
+        self.xd, self.yd = D.from_host(self.x), D.from_host(self.y)
+        self.tabs_d = [D.from_host(t) for t in self.tables]
+        self.h2d = self.BLOCK * self.B * (784 + 10) * 4
+        self.d2h = 118282 * 4
+        self.pin_x = torch.empty(self.B, 784).pin_memory()
+        self.pin_y = torch.empty(self.B, 10).pin_memory()
+        self.out_pinned = torch.empty(118282).pin_memory()
+
+    def step_gpu(self, i):
+        self.tr.train_block(self.xd, self.yd, self.tabs_d[i % len(self.tabs_d)])
+
+    def step_e2e(self, i):
+        # the reference's own call: sgd_step(host batch, host labels), 32 times, then read the params
+        tab = self.tables[i % len(self.tables)]
+        for s in range(self.BLOCK):
+            self.tr.sgd_step(self.x[tab[s]], self.y[tab[s]])
+        self.out_pinned.copy_(self.tr.theta, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    def launches_per_step(self):
+        return self.BLOCK * 14
+
+    def dominant_kernel(self, peaks):
+        t = self.torch
+        times = []
+        for k in range(6):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            self.tr.train_block(self.xd, self.yd, self.tabs_d[k])
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[2:])) / self.BLOCK
+        bytes_per_step = self.B * 3216 + 24 * 118282        # SURVEY 8d: 3.25 MB per step
+        ach = bytes_per_step / (ms * 1e-3) / 1e9
+        return dict(bound="hbm", kernel="one optimiser step (14 launches: 3 fwd GEMM, head, 8 bwd, Adam)",
+                    achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
+                    peak_source=peaks["source"], ms_per_launch=ms,
+                    note="latency-bound at batch 128: 3.25 MB / 65 MFLOP per step is 0.5 us at roofline")
+
+    def setup_cpu(self):
+        from oracle import mq_oracle as O
+        self.O = O
+        self.spec = O.mlp_spec(784, [128, 128, 10], [O.ACT_LRELU, O.ACT_LRELU, O.ACT_NONE])
+        self.theta = O.mlp_init(self.spec, np.random.RandomState(0), 0.1)
+        self.opt = O.AdamO(self.theta, horizon=10, lr=1e-3)
+
+    def step_cpu(self, i):
+        tab = self.tables[i % len(self.tables)]
+        for s in range(self.BLOCK):
+            self.theta = self.O.mlp_sgd_step(self.theta, self.spec, self.opt, self.x[tab[s]], self.y[tab[s]])
+
+
+class ESWorkload(object):
+    """BASELINE.json configs[3]: evolution strategies, population 4096 x 64-64 policy (P=5,123),
+    shared batch of 1000 observations, synthetic linear return, RunningNormalize(h=10), Adam(lr .01).
+    The population is sharded across GPUs (4096 members per GPU: weak scaling)."""
+    name = "es_population4096_T1000 (configs[3])"
+    metric = "es_members_per_s"
+    unit = "members/s"
+    M, T = 4096, 1000
+
+    def __init__(self, seed=1, m=None):
+        self.M = m or self.M
+        rs = np.random.RandomState(seed)
+        self.noise = (rs.randn(self.M, 5123) * 0.1).astype(np.float32)
+        self.obs = np.clip(rs.randn(self.T, 11), -5, 5).astype(np.float32)
+        self.coef = np.array([1.0, -0.5, 0.25], np.float32)
+        self.units_per_step = self.M
+
+    def setup_gpu(self):
+        import torch
+        from mannequin2_b200 import _device as D
+        from mannequin2_b200.es import ESPopulation
+        np.random.seed(0)
+        self.torch, self.D = torch, D
+        self.es = ESPopulation(11, 3)
+        self.nd, self.od, self.cd = D.from_host(self.noise), D.from_host(self.obs), D.from_host(self.coef)
+        self.pin = torch.from_numpy(self.noise).pin_memory()
+        self.out_pinned = torch.empty(self.M).pin_memory()
+        self.h2d, self.d2h = self.noise.nbytes, self.M * 4
+
+    def step_gpu(self, i):
+        self.es.generation(self.nd, self.od, self.cd)
+
+    def step_e2e(self, i):
+        nd = self.pin.to(self.D.device(), non_blocking=True)
+        rets = self.es.generation(nd, self.od, self.cd)
+        self.out_pinned.copy_(rets, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    def launches_per_step(self):
+        return 12
+
+    def dominant_kernel(self, peaks):
+        import ctypes as C
+        t, D = self.torch, self.D
+        value, _, _, theta = self.es.opt.state()
+        rets = t.empty(self.M, dtype=t.float32, device=D.device())
+        times = []
+        for k in range(6):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            D.call("mq_es_eval", C.byref(self.es.net), D.ptr(theta), D.ptr(self.nd), self.M, D.ptr(self.od),
+                   self.T, D.ptr(self.cd), D.ptr(rets), D.stream())
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[2:]))
+        bytes_per_launch = self.M * 5123 * 4               # SURVEY 8d: noise read once, 20.5 KB / member
+        flops = self.M * 2.0 * 4992 * self.T
+        ach = bytes_per_launch / (ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        return dict(bound="hbm", kernel="es_eval_kernel", achieved=ach, peak=peaks["hbm"], unit="GB/s",
+                    frac=ach / peaks["hbm"], traffic=None, peak_source=peaks["source"], ms_per_launch=ms,
+                    limiter="fp32 FFMA pipe (9.98 MFLOP per member vs 20.5 KB)",
+                    fp32_tflops=flops / (ms * 1e-3) / 1e12, fp32_frac=flops / (ms * 1e-3) / 1e12 / fp32_peak)
+
+    def setup_cpu(self):
+        from oracle import mq_oracle as O
+        self.O = O
+        self.spec = O.mlp_spec(11, [64, 64, 3], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+        self.theta = O.mlp_init(self.spec, np.random.RandomState(0))
+        self.opt = O.AdamO(self.theta, horizon=10, lr=0.01)
+        self.norm = O.RunningNormalizeO(horizon=10)
+
+    cpu_units_per_step = 256
+    cpu_sample_desc = "256 of the 4096 members (same observations)"
+
+    def step_cpu(self, i):
+        self.theta, _, _ = self.O.es_generation(self.theta, self.spec, self.opt, self.norm,
+                                                self.noise[:256], self.obs, self.coef)
+
+
+WORKLOADS = {"ppo": PPOWorkload, "ppo_large": PPOLargeWorkload, "mlp": MLPWorkload, "es": ESWorkload}
+
+
+def kernel_sweep(peaks):
+    """HBM-bound kernels at sizes far beyond L2 (126 MB): achieved algorithmic GB/s vs measured peak."""
+    import ctypes as C
+    import torch
+    from mannequin2_b200 import _device as D, _lib as L
+    lib, dev, out = L.lib(), D.device(), {}
+
+    def timeit(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts[1:]))
+
+    n = 64 << 20                                            # 64 Mi params
+    val, m, v, g = (torch.zeros(n, device=dev) for _ in range(4))
+    g.normal_()
+    th = torch.empty(n, device=dev)
+    ms = timeit(lambda: D.call("mq_adam_step", D.ptr(val), D.ptr(m), D.ptr(v), D.ptr(th), D.ptr(g), n, L.MQ_F32,
+                               L.MQ_F32, 0.1, 0.01, 1e-3, 1e-8, 0, D.stream()))
+    out["adam_f32_64Mi"] = dict(bytes_per_elem=32, ms=ms, gbs=32.0 * n / ms / 1e6, frac=32.0 * n / ms / 1e6 / peaks["hbm"])
+    del val, m, v, g, th
+    n = 32 << 20
+    val, m, v = (torch.zeros(n, device=dev, dtype=torch.float64) for _ in range(3))
+    g = torch.randn(n, device=dev)
+    th = torch.empty(n, device=dev)
+    ms = timeit(lambda: D.call("mq_adam_step", D.ptr(val), D.ptr(m), D.ptr(v), D.ptr(th), D.ptr(g), n, L.MQ_F64,
+                               L.MQ_F32, 0.1, 0.01, 1e-3, 1e-8, 0, D.stream()))
+    out["adam_f64_32Mi"] = dict(bytes_per_elem=56, ms=ms, gbs=56.0 * n / ms / 1e6, frac=56.0 * n / ms / 1e6 / peaks["hbm"])
+    del val, m, v, g, th
+    n = 64 << 20                                            # 64 Mi transitions
+    r, vv = torch.randn(n, device=dev), torch.randn(n + 1, device=dev)
+    d = (torch.rand(n, device=dev) < 0.002).to(torch.uint8)
+    adv, ret = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    wsb = lib.mq_scan_ws_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: D.call("mq_gae", D.ptr(r), D.ptr(vv), D.ptr(d), n, 0.99, 0.95, D.ptr(adv), D.ptr(ret),
+                               D.ptr(ws), wsb, D.stream()))
+    out["gae_64Mi"] = dict(bytes_per_elem=17, ms=ms, gbs=17.0 * n / ms / 1e6, frac=17.0 * n / ms / 1e6 / peaks["hbm"])
+    from mannequin2_b200 import RunningNormalize
+    norm = RunningNormalize(horizon=2)
+    o = torch.empty(n, device=dev)
+    def nrm():
+        norm.update_dev(r, n)
+        norm.apply_dev(r, n, out=o, fuse_tanh=True)
+    ms = timeit(nrm)
+    out["normalize_update_apply_64Mi"] = dict(bytes_per_elem=16, ms=ms, gbs=16.0 * n / ms / 1e6,
+                                              frac=16.0 * n / ms / 1e6 / peaks["hbm"])
+    return out
 
 
 # ------------------------------------------------------------------ CPU timing helpers
@@ -204,7 +529,7 @@ def _cpu_worker(args):
         limiter = threadpool_limits(limits=1)
     except Exception:
         limiter = None
-    wl = WORKLOADS[name](seed=seed + 1)
+    wl = WORKLOADS[name](seed=seed + 1, **CPU_KW.get(name, {}))
     wl.setup_cpu()
     for i in range(warmup):
         wl.step_cpu(i)
@@ -214,31 +539,80 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+CPU_KW = {"ppo_large": dict(n=65536, n_rollouts=1), "es": dict(m=256), "mlp": dict(n_data=8192)}
+
+
 def time_cpu(name, steps, warmup, procs):
     """`procs` independent single-thread replicas in parallel (how the reference uses a multi-core
     box: run_benchmarks.sh:98-102, one process per seed); aggregate units/s."""
     import multiprocessing as mp
-    wl = WORKLOADS[name]()
+    wl = WORKLOADS[name](**CPU_KW.get(name, {}))
+    units = getattr(wl, "cpu_units_per_step", wl.units_per_step)
     if procs <= 1:
         dt = _cpu_worker((name, steps, warmup, 0))
-        return steps * wl.units_per_step / dt, dt
+        return steps * units / dt, dt
     with mp.get_context("fork").Pool(procs) as pool:
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(name, steps, warmup, s) for s in range(procs)])
-        wall = time.perf_counter() - t0
-    # wall includes per-process set-up and warm-up: conservative for the CPU (lower bound on its speed)
-    dts = None
-    return procs * steps * wl.units_per_step / wall, wall
+        dts = pool.map(_cpu_worker, [(name, steps, warmup, s) for s in range(procs)])
+    slowest = max(dts)                       # timed region of the slowest replica (set-up/warm-up excluded)
+    return procs * steps * units / slowest, slowest
 
 
 # ------------------------------------------------------------------ main
+def measure(wl, steps, warmup, world, rank, flush):
+    """W untimed steps, then K steps each timed on the device with its own CUDA-event pair on the
+    launching stream; L2 is flushed (256 MB write) between steps, outside the timed intervals.
+    Device-resident inputs first (`value`), then the same steps through host buffers (`e2e`).
+    Returns (ms_total, ms_e2e_total) as the MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, n):
+        total = 0.0
+        for i in range(n):
+            flush.fill_(float(i))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn(i)
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    for i in range(warmup):
+        wl.step_gpu(i)
+    barrier()
+    ms = timed(lambda i: wl.step_gpu(warmup + i), steps)
+    barrier()
+    wl.step_e2e(0)
+    barrier()
+    ms_e2e = timed(lambda i: wl.step_e2e(warmup + i), steps)
+    barrier()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), float(t[1])
+
+
+PARALLELISM = {"ppo_large": "dp%d: every rank trains on its own 2^20-transition shard, global minibatch = %d x 65,536 "
+                            "rows, one NCCL all-reduce of the flat gradient per optimiser step",
+               "ppo": "%d independent replicas (a 64-row minibatch does not shard)",
+               "mlp": "%d independent replicas (batch 128 does not shard)",
+               "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ppo", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ppo_large", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / kernel sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -249,17 +623,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        wl = WORKLOADS[args.workload]()
+        wl = WORKLOADS[args.workload](**CPU_KW.get(args.workload, {}))
         procs = max(1, min(cores, 32))
-        steps = max(1, min(args.steps, 4))
+        steps = max(1, min(args.steps, 3))
         val, wall = time_cpu(args.workload, steps, 1, procs)
+        sample = getattr(wl, "cpu_sample_desc", "the full workload step")
         line = dict(metric=wl.metric, value=val, unit=wl.unit, n_gpus=args.gpus, steps=steps, warmup=1,
                     ms_per_step=1e3 * wall / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic", impl="reference",
-                    config=dict(workload=wl.name, note="oracle port of the NumPy reference; %d independent "
-                                "single-thread replicas, aggregate" % procs),
+                    config=dict(workload=wl.name, sample=sample,
+                                note="CPU restatement (oracle port) of the NumPy reference path; %d independent "
+                                     "single-thread replicas run in parallel, aggregate throughput (how the "
+                                     "reference uses a multi-core box: run_benchmarks.sh:98-102)" % procs),
                     cpu_baseline=dict(value=val, unit=wl.unit, cores=procs, kind="port",
-                                      sample="%d steps x %d replicas" % (steps, procs)),
+                                      sample="%d steps x %d replicas; each step: %s" % (steps, procs, sample)),
                     e2e=dict(value=val, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
@@ -276,65 +653,58 @@ def main():
     wl = WORKLOADS[args.workload](seed=1 + rank)
     wl.setup_gpu()
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, n, use_events=True):
-        """Each step is timed on the device with its own event pair; L2 is flushed
-        (256 MB write) between steps, outside the timed intervals."""
-        total = 0.0
-        for i in range(n):
-            flush.fill_(float(i))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_fn(i)
-            e1.record()
-            e1.synchronize()
-            total += e0.elapsed_time(e1)
-        return total
-
-    for i in range(warmup):
-        wl.step_gpu(i)
-    barrier()
+    wl.step_gpu(0)
+    torch.cuda.synchronize()
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    barrier()
-    ms = timed(lambda i: wl.step_gpu(warmup + i), args.steps)
-    barrier()
-    for i in range(2):
-        wl.step_e2e(i)
-    barrier()
-    ms_e2e = timed(lambda i: wl.step_e2e(warmup + i), args.steps)
-    barrier()
+    ms, ms_e2e = measure(wl, args.steps, warmup, world, rank, flush)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
     units = wl.units_per_step * args.steps * world
     if rank == 0:
         roof = wl.dominant_kernel(peaks)
-        cpu = None
-        if not args.no_cpu_baseline:
-            v1, w1 = time_cpu(args.workload, 2, 1, 1)
-            cpu = dict(value=v1, unit=wl.unit, cores=1, kind="port",
-                       sample="2 steps of the same workload after 1 warm-up, one process (OpenBLAS default threads)",
-                       host_cores=cores)
         line = dict(metric=wl.metric, value=units / (ms * 1e-3), unit=wl.unit, n_gpus=world, steps=args.steps,
                     warmup=warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=wl.name, l2="flushed between steps (256 MB write)",
-                                adam_state="f32 (moments on chip)", parallelism="replicas" if world > 1 else "single"),
+                    config=dict(workload=wl.name,
+                                l2="flushed (256 MB write) between timed steps; per-step inputs exceed L2",
+                                adam_state="f32", parallelism=PARALLELISM[args.workload] % ((world, world) if
+                                args.workload == "ppo_large" else (world,)) if world > 1 else "single GPU"),
                     e2e=dict(value=units / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=wl.h2d,
                              d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=wl.launches_per_step() * args.steps, roofline=roof, cpu_baseline=cpu,
-                    clocks=clocks)
+                    gpu_launches=wl.launches_per_step() * args.steps, roofline=roof, clocks=clocks)
+        if not args.no_cpu_baseline and world == 1:
+            v1, w1 = time_cpu(args.workload, 1, 1, 1)
+            line["cpu_baseline"] = dict(
+                value=v1, unit=wl.unit, cores=1, kind="port", host_cores=cores,
+                sample="1 step after 1 warm-up in one process (NumPy/OpenBLAS default threads); each step: "
+                       + getattr(wl, "cpu_sample_desc", "the full workload step"))
+        else:
+            line["cpu_baseline"] = None
+        if not args.no_extras and world == 1:
+            del wl
+            torch.cuda.empty_cache()
+            others = {}
+            for name in ("ppo", "mlp", "es"):
+                if name == args.workload:
+                    continue
+                w2 = WORKLOADS[name](seed=7)
+                w2.setup_gpu()
+                m1, m2 = measure(w2, 5, 3, 1, 0, flush)
+                u = w2.units_per_step * 5
+                r2 = w2.dominant_kernel(peaks)
+                c1, _ = time_cpu(name, 1, 1, 1)
+                others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
+                                    e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,
+                                    roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",
+                                                                             "fp32_tflops", "fp32_frac", "note")})
+                del w2
+                torch.cuda.empty_cache()
+            line["other_workloads"] = others
+            line["kernels"] = kernel_sweep(peaks)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -91,14 +91,19 @@ int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int
 int mq_adam_step(void *value, void *m, void *v, float *theta_out, const void *grad,
                  int64_t n, int state_dtype, int grad_dtype, double c1, double c2,
                  double lr, double eps, int adams, void *stream);
+/* Same step with {c1, c2, lr, eps} read from 4 doubles in DEVICE memory, so that a sequence of
+ * steps can be captured once in a CUDA graph and replayed with fresh coefficients. */
+int mq_adam_step_dev(void *value, void *m, void *v, float *theta_out, const void *grad, int64_t n,
+                     int state_dtype, int grad_dtype, const double *coefs_dev, int adams, void *stream);
 /* mean += coef*(x-mean); old_out (nullable) receives the previous mean. */
 int mq_running_mean_update(double *mean, const void *x, int x_dtype, int64_t n,
                            double coef, double *old_out, void *stream);
 
 /* ---- running normaliser: mannequin/_normalize.py:34-81 ---------------------- */
 int64_t mq_norm_ws_bytes(int64_t rows, int64_t cols);
-int mq_col_mean(const void *x, int x_dtype, int64_t rows, int64_t cols, double *out, void *ws,
-                int64_t ws_bytes, void *stream);
+/* out[c] = scale * mean_r x[r,c]   (scale = 1/world turns a later sum over ranks into the global mean) */
+int mq_col_mean(const void *x, int x_dtype, int64_t rows, int64_t cols, double scale, double *out,
+                void *ws, int64_t ws_bytes, void *stream);
 /* out[c] = scale * mean_r (x[r,c]-mean_old[c])*(x[r,c]-mean_new[c]) */
 int mq_norm_cov(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *mean_old,
                 const double *mean_new, double scale, double *out, void *ws, int64_t ws_bytes,

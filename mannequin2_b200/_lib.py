@@ -41,9 +41,10 @@ SIGNATURES = {
     "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
                              c_double, c_int, P]),
+    "mq_adam_step_dev": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P, c_int, P]),
     "mq_running_mean_update": (c_int, [P, P, c_int, c_int64, c_double, P, P]),
     "mq_norm_ws_bytes": (c_int64, [c_int64, c_int64]),
-    "mq_col_mean": (c_int, [P, c_int, c_int64, c_int64, P, P, c_int64, P]),
+    "mq_col_mean": (c_int, [P, c_int, c_int64, c_int64, c_double, P, P, c_int64, P]),
     "mq_norm_cov": (c_int, [P, c_int, c_int64, c_int64, P, P, c_double, P, P, c_int64, P]),
     "mq_norm_apply": (c_int, [P, c_int, c_int64, c_int64, P, P, P, c_int, c_int, P]),
     "mq_gather_rows": (c_int, [P, P, c_int64, c_int64, c_int64, P, P]),

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _device as D
+from . import dist as mqdist
 from ._lib import MQ_F32, MQ_F64
 
 
@@ -72,14 +73,21 @@ class RunningNormalize(object):
         self._n_samples = 0
 
     # -- device-level API (used by the fused PPO / ES drivers) -------------------
-    def update_dev(self, x, rows):
-        """x: device float32/float64 tensor holding rows*D values."""
+    def update_dev(self, x, rows, sharded=False):
+        """x: device float32/float64 tensor holding rows*D values.  With sharded=True every rank
+        passes its equally sized shard of one global batch: the two batch statistics are
+        all-reduced (2 x D doubles), everything else is replicated."""
         lib = D._lib.lib()
         d = self._d
+        w = mqdist.world() if sharded else 1
         wsb = lib.mq_norm_ws_bytes(rows, d)
         ws = D.workspace("norm", wsb)
-        D.call("mq_col_mean", D.ptr(x), _code(x), rows, d, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
+        D.call("mq_col_mean", D.ptr(x), _code(x), rows, d, 1.0 / w, D.ptr(self._tmp), D.ptr(ws), wsb,
+               D.stream())
+        if w > 1:
+            mqdist.allreduce_sum_(self._tmp)
         self._mean.update(self._tmp, _old_out=self._old)          # one weight-1 update per batch
+        local_rows, rows = rows, rows * w
         weight, scale = None, 1.0
         if self._n_samples >= 1:
             weight = 1.0
@@ -87,8 +95,10 @@ class RunningNormalize(object):
             weight = (rows - 1.0) / rows                          # _normalize.py:50-55
             scale = 1.0 / weight
         if weight is not None:
-            D.call("mq_norm_cov", D.ptr(x), _code(x), rows, d, D.ptr(self._old),
-                   D.ptr(self._mean.get_dev()), scale, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
+            D.call("mq_norm_cov", D.ptr(x), _code(x), local_rows, d, D.ptr(self._old),
+                   D.ptr(self._mean.get_dev()), scale / w, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
+            if w > 1:
+                mqdist.allreduce_sum_(self._tmp)
             self._var.update(self._tmp, weight=weight)
         self._n_samples += rows
 

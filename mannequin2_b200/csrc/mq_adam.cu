@@ -58,7 +58,10 @@ template <typename ST, typename GT, bool ADAMS, bool VEC>
 __global__ void __launch_bounds__(MQ_NT)
 adam_kernel(ST *__restrict__ value, ST *__restrict__ m, ST *__restrict__ v,
             float *__restrict__ theta_out, const GT *__restrict__ grad, int64_t n, ST c1, ST c2,
-            ST lr, ST eps) {
+            ST lr, ST eps, const double *__restrict__ coefs_dev) {
+    if (coefs_dev) {                 // {c1, c2, lr, eps} from device memory (CUDA-graph replay)
+        c1 = (ST)coefs_dev[0]; c2 = (ST)coefs_dev[1]; lr = (ST)coefs_dev[2]; eps = (ST)coefs_dev[3];
+    }
     const int64_t tid = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * MQ_NT;
     if (VEC) {
@@ -99,7 +102,8 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 template <typename ST, typename GT>
 static int adam_launch(void *value, void *m, void *v, float *theta_out, const void *grad, int64_t n,
-                       double c1, double c2, double lr, double eps, int adams, void *stream) {
+                       double c1, double c2, double lr, double eps, int adams, void *stream,
+                       const double *coefs_dev = nullptr) {
     const bool vec = aligned16(value) && aligned16(m) && aligned16(v) && aligned16(grad) &&
                      (theta_out == nullptr || aligned16(theta_out)) && n >= 4;
     const int64_t work = vec ? (n >> 2) : n;
@@ -111,7 +115,7 @@ static int adam_launch(void *value, void *m, void *v, float *theta_out, const vo
     do {                                                                                       \
         auto kfn = adam_kernel<ST, GT, A, V>;                                                  \
         MQ_LAUNCH(kfn, (unsigned)blocks, MQ_NT, 0, stream, (ST *)value, (ST *)m, (ST *)v,      \
-                  theta_out, (const GT *)grad, n, (ST)c1, (ST)c2, (ST)lr, (ST)eps);            \
+                  theta_out, (const GT *)grad, n, (ST)c1, (ST)c2, (ST)lr, (ST)eps, coefs_dev); \
     } while (0)
     if (adams) { if (vec) MQ_ADAM_GO(true, true); else MQ_ADAM_GO(true, false); }
     else       { if (vec) MQ_ADAM_GO(false, true); else MQ_ADAM_GO(false, false); }
@@ -133,6 +137,20 @@ extern "C" int mq_adam_step(void *value, void *m, void *v, float *theta_out, con
     if (state_dtype == MQ_F32 && grad_dtype == MQ_F32)
         return adam_launch<float, float>(value, m, v, theta_out, grad, n, c1, c2, lr, eps, adams, stream);
     mq_set_error("mq_adam_step: unsupported dtype pair (%d,%d)", state_dtype, grad_dtype);
+    return MQ_ERR_INVALID;
+}
+
+extern "C" int mq_adam_step_dev(void *value, void *m, void *v, float *theta_out, const void *grad,
+                                int64_t n, int state_dtype, int grad_dtype, const double *coefs_dev,
+                                int adams, void *stream) {
+    MQ_REQUIRE(value && m && v && grad && coefs_dev, MQ_ERR_INVALID, "mq_adam_step_dev: null pointer");
+    MQ_REQUIRE(n >= 0, MQ_ERR_SHAPE, "mq_adam_step_dev: negative size");
+    if (n == 0) return MQ_OK;
+    if (state_dtype == MQ_F64 && grad_dtype == MQ_F32)
+        return adam_launch<double, float>(value, m, v, theta_out, grad, n, 0, 0, 0, 0, adams, stream, coefs_dev);
+    if (state_dtype == MQ_F32 && grad_dtype == MQ_F32)
+        return adam_launch<float, float>(value, m, v, theta_out, grad, n, 0, 0, 0, 0, adams, stream, coefs_dev);
+    mq_set_error("mq_adam_step_dev: unsupported dtype pair (%d,%d)", state_dtype, grad_dtype);
     return MQ_ERR_INVALID;
 }
 

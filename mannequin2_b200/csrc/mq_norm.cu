@@ -96,11 +96,11 @@ static int norm_reduce(const void *x, int64_t rows, int64_t cols, const double *
     return MQ_OK;
 }
 
-extern "C" int mq_col_mean(const void *x, int x_dtype, int64_t rows, int64_t cols, double *out,
-                           void *ws, int64_t ws_bytes, void *stream) {
+extern "C" int mq_col_mean(const void *x, int x_dtype, int64_t rows, int64_t cols, double scale,
+                           double *out, void *ws, int64_t ws_bytes, void *stream) {
     if (x_dtype == MQ_F64)
-        return norm_reduce<double, false>(x, rows, cols, nullptr, nullptr, 1.0, out, ws, ws_bytes, stream, "mq_col_mean");
-    return norm_reduce<float, false>(x, rows, cols, nullptr, nullptr, 1.0, out, ws, ws_bytes, stream, "mq_col_mean");
+        return norm_reduce<double, false>(x, rows, cols, nullptr, nullptr, scale, out, ws, ws_bytes, stream, "mq_col_mean");
+    return norm_reduce<float, false>(x, rows, cols, nullptr, nullptr, scale, out, ws, ws_bytes, stream, "mq_col_mean");
 }
 
 extern "C" int mq_norm_cov(const void *x, int x_dtype, int64_t rows, int64_t cols,

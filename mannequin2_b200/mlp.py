@@ -1,0 +1,107 @@
+"""Fused training loop of mnist/mlp.py:24-43: Input(28,28) -> 2 x LReLU(Affine 128) -> Affine(10),
+dy = onehot - softmax(out) - 0.01*out, Adam(horizon 10, lr 1e-3), batch 128 drawn by index.
+
+The 784x128 first layer (401 KB) does not fit in one SM's shared memory, so this net runs on
+the layered path: one GEMM launch per layer with fused bias/activation epilogues
+(csrc/mq_gemm.cu), the softmax head, the backward GEMMs and the fused Adam step.  A whole block
+of steps is captured ONCE in a CUDA graph (Adam coefficients and minibatch indices are read
+from device tables), so a training block is a single graph launch.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib
+from ._adam import Adam
+from ._lib import ACT_LRELU, ACT_NONE, MQ_F32
+from .ppo import init_mlp
+
+
+class MLPTrainer(object):
+    def __init__(self, n_in=784, widths=(128, 128, 10), acts=(ACT_LRELU, ACT_LRELU, ACT_NONE), *,
+                 leak=0.1, batch=128, horizon=10, lr=1e-3, l2=0.01, params=None, state_dtype="float32",
+                 graph_steps=32):
+        self.net = _lib.make_net(n_in, list(widths), list(acts), leak=leak)
+        if params is None:
+            params = init_mlp(n_in, list(widths), 0.1)                # mlp.py:24-27 (init=0.1 head)
+        assert len(params) == self.net.n_params
+        self.batch, self.lr, self.l2, self.n_in, self.n_out = batch, lr, l2, n_in, widths[-1]
+        self.theta = D.from_host(np.asarray(params, np.float32))
+        self.opt = Adam(params, horizon=horizon, state_dtype=state_dtype)
+        lib = _lib.lib()
+        nb = ctypes.byref(self.net)
+        self.acts = D.empty(lib.mq_mlp_acts_floats(nb, batch))
+        self.dy = D.empty(batch * self.n_out)
+        self.grad = D.zeros(self.net.n_params)
+        self.wsb = lib.mq_mlp_ws_bytes(nb, batch)
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=D.device())
+        self.graph_steps = graph_steps
+        self.idx = torch.zeros(graph_steps * batch, dtype=torch.int32, device=D.device())
+        self.coefs = torch.zeros(graph_steps * 4, dtype=torch.float64, device=D.device())
+        self._graph, self._graph_data = None, None
+
+    # one step, all pointers fixed except through the idx / coef tables ---------------------
+    def _enqueue_step(self, x, y, s):
+        nb, B = ctypes.byref(self.net), self.batch
+        idx_ptr = D.ptr(self.idx) + s * B * 4
+        value, m, v, _ = self.opt.state()
+        D.call("mq_mlp_forward", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, B, D.ptr(self.acts), D.stream())
+        logits = self.acts[self.acts.numel() - B * self.n_out:]
+        D.call("mq_softmax_ce_grad", D.ptr(logits), D.ptr(y), idx_ptr, B, self.n_out, self.l2,
+               D.ptr(self.dy), D.stream())
+        D.call("mq_mlp_backward", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
+               D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, D.ptr(self.ws), self.wsb, D.stream())
+        D.call("mq_adam_step_dev", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
+               self.net.n_params, self.opt._code, MQ_F32, D.ptr(self.coefs) + s * 32, 0, D.stream())
+
+    def train_block(self, x, y, idx_table):
+        """x f32[n,784] and y f32[n,10] device tensors (whole data set), idx_table host or device
+        int32 [steps, batch] with steps <= graph_steps.  Runs the steps as one graph replay."""
+        steps = idx_table.shape[0]
+        assert steps <= self.graph_steps and idx_table.shape[1] == self.batch
+        idx_d = idx_table if D.is_dev(idx_table) else D.from_host(np.ascontiguousarray(idx_table, np.int32))
+        self.idx[:steps * self.batch].copy_(idx_d.reshape(-1), non_blocking=True)
+        co = np.zeros((self.graph_steps, 4))
+        for s in range(steps):
+            c1, c2 = self.opt.next_coefs()
+            co[s] = (c1, c2, self.lr, 1e-8)
+        self.coefs.copy_(D.from_host(co.reshape(-1), np.float64), non_blocking=True)
+        self.opt._out = None
+        key = (D.ptr(x), D.ptr(y), steps)
+        if self._graph is None or self._graph_data != key:
+            self._enqueue_step(x, y, 0)                    # warm-up outside capture (sets kernel attributes)
+            torch.cuda.current_stream().synchronize()
+            value, m, v, _ = self.opt.state()
+            snap = [t.clone() for t in (self.theta, value, m, v)]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for s in range(steps):
+                    self._enqueue_step(x, y, s)
+            for t, c in zip((self.theta, value, m, v), snap):   # undo the warm-up step
+                t.copy_(c)
+            self._graph, self._graph_data = g, key
+        self._graph.replay()
+
+    def sgd_step(self, inps, lbls):
+        """mlp.py:31-35 with host arrays: one H2D copy of the batch, one step, no D2H."""
+        B = self.batch
+        x = D.from_host(np.asarray(inps, np.float32).reshape(B, self.n_in))
+        y = D.from_host(np.asarray(lbls, np.float32).reshape(B, self.n_out))
+        self.idx[:B].copy_(torch.arange(B, dtype=torch.int32, device=self.idx.device))
+        c1, c2 = self.opt.next_coefs()
+        self.coefs[:4].copy_(D.from_host(np.array([c1, c2, self.lr, 1e-8]), np.float64))
+        self.opt._out = None
+        self._enqueue_step(x, y, 0)
+
+    def forward(self, inps):
+        x = np.asarray(inps, np.float32).reshape(-1, self.n_in)
+        xd = D.from_host(x)
+        acts = D.empty(_lib.lib().mq_mlp_acts_floats(ctypes.byref(self.net), len(x)))
+        D.call("mq_mlp_forward", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(xd), None, len(x),
+               D.ptr(acts), D.stream())
+        return D.to_host(acts[acts.numel() - len(x) * self.n_out:]).reshape(len(x), self.n_out)
+
+    def get_params(self):
+        return D.to_host(self.theta)

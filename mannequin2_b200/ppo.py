@@ -23,6 +23,7 @@ import torch
 
 from . import _device as D
 from . import _lib
+from . import dist as mqdist
 from ._adam import Adam
 from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_GAUSS_PPO, MQ_F32, MQ_F64, MqHead
 from ._normalize import RunningNormalize
@@ -41,6 +42,9 @@ def init_mlp(n_in, widths, head_scale):
     return np.concatenate(parts)
 
 
+CHAIN_MAX_MB = 256        # minibatches up to this size run inside the persistent single-CTA chain
+
+
 class _Net(object):
     """Parameters + Adam state of one net, all device resident."""
 
@@ -49,8 +53,16 @@ class _Net(object):
         self.theta = D.from_host(theta_host, np.float32)
         self.opt = Adam(theta_host, horizon=horizon, state_dtype=state_dtype)
         self.code = self.opt._code
+        self.grad = D.zeros(net.n_params)
 
     def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8):
+        """n_steps optimiser steps; idx_table is i32[n_steps, mb] (rows of THIS rank)."""
+        if mb <= CHAIN_MAX_MB and mqdist.world() == 1:
+            return self._train_chain(x, head, idx_table, n_steps, mb, lr, eps)
+        return self._train_loop(x, head, idx_table, n_steps, mb, lr, eps)
+
+    # -- small minibatches: one persistent CTA runs the whole dependent chain ------------
+    def _train_chain(self, x, head, idx_table, n_steps, mb, lr, eps):
         value, m, v, _ = self.opt.state()
         tw = (ctypes.c_double * 2)(*self.opt._tw)
         D.call("mq_fused_train", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(value), D.ptr(m), D.ptr(v),
@@ -58,6 +70,29 @@ class _Net(object):
                self.opt._b2, tw, lr, eps, D.stream())
         self.opt._tw = [tw[0], tw[1]]
         self.opt._out = None
+
+    # -- large minibatches: all SMs per step, one gradient all-reduce across GPUs ---------
+    def _one_step(self, x, head, idx_ptr, mb, scale, ws, wsb, c1, c2, lr, eps):
+        value, m, v, _ = self.opt.state()
+        D.call("mq_fused_grad", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), idx_ptr, mb,
+               ctypes.byref(head), scale, D.ptr(self.grad), None, None, D.ptr(ws), wsb, D.stream())
+        mqdist.allreduce_sum_(self.grad)
+        D.call("mq_adam_step", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
+               self.net.n_params, self.code, MQ_F32, c1, c2, lr, eps, 0, D.stream())
+
+    def _train_loop(self, x, head, idx_table, n_steps, mb, lr, eps):
+        lib = _lib.lib()
+        wsb = lib.mq_fused_ws_bytes(ctypes.byref(self.net), mb)
+        ws = D.workspace(("fused", id(self)), wsb)
+        scale = 1.0 / float(mb * mqdist.world())            # batch MEAN over the GLOBAL minibatch
+        coefs = [self.opt.next_coefs() for _ in range(n_steps)]
+        self.opt._out = None
+        base, stride = D.ptr(idx_table), mb * 4
+
+        # 3 launches per step (grad over all SMs, fixed-order reduce, Adam); at >= 8k rows the
+        # kernels outlast the launch cost, so no CUDA graph is needed.
+        for s in range(n_steps):
+            self._one_step(x, head, base + s * stride, mb, scale, ws, wsb, coefs[s][0], coefs[s][1], lr, eps)
 
 
 class PPOUpdater(object):
@@ -107,16 +142,21 @@ class PPOUpdater(object):
         ws = D.workspace("scan", wsb)
         D.call("mq_gae", D.ptr(rew), D.ptr(value), D.ptr(done), n, self.gam, self.lam, D.ptr(adv), D.ptr(ret),
                D.ptr(ws), wsb, D.stream())
-        self._ev_gae.record(main)
-        # value predictor chain on the side stream (gae.py:66-73)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_gae)
-            head = MqHead()
-            head.kind, head.target = HEAD_DIFF, D.ptr(ret)
-            val.train(obs, head, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
-            self._ev_val.record(self._side)
+        # Small minibatches: the two 300-step chains are single-CTA kernels -> run them side by
+        # side on two streams.  Large / sharded minibatches fill the GPU: run them in sequence.
+        concurrent = val_idx.shape[1] <= CHAIN_MAX_MB and mqdist.world() == 1
+        vhead = MqHead()
+        vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
+        if concurrent:
+            self._ev_gae.record(main)
+            with torch.cuda.stream(self._side):              # value predictor chain (gae.py:66-73)
+                self._side.wait_event(self._ev_gae)
+                val.train(obs, vhead, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
+                self._ev_val.record(self._side)
+        else:
+            val.train(obs, vhead, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
         # policy chain on the main stream (ppo.py:24-40)
-        self.normalize.update_dev(adv, n)
+        self.normalize.update_dev(adv, n, sharded=True)
         self.normalize.apply_dev(adv, n, out=adv_n, fuse_tanh=True)
         D.call("mq_fused_forward", ctypes.byref(pol.net), D.ptr(pol.theta), D.ptr(obs), None, n, None,
                D.ptr(act), D.ptr(logp0), D.stream())
@@ -124,7 +164,8 @@ class PPOUpdater(object):
         head.kind, head.p0, head.p1 = HEAD_GAUSS_PPO, self.clip[0], self.clip[1]
         head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
         pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
-        main.wait_event(self._ev_val)
+        if concurrent:
+            main.wait_event(self._ev_val)
         return adv, ret
 
     def update(self, obs, act, rew, done, val_idx, pol_idx):

@@ -121,7 +121,7 @@ def case_norm(B):
         wsb = lib.mq_norm_ws_bytes(rows, cols)
         hx, ws = B.up(x), B.zeros(wsb, np.uint8)
         mean = B.zeros(cols, np.float64)
-        ok(B, lib.mq_col_mean(B.ptr(hx), code, rows, cols, B.ptr(mean), B.ptr(ws), wsb, B.stream))
+        ok(B, lib.mq_col_mean(B.ptr(hx), code, rows, cols, 1.0, B.ptr(mean), B.ptr(ws), wsb, B.stream))
         hmean = B.down(mean)
         assert np.allclose(hmean, x.astype(np.float64).mean(axis=0), rtol=1e-13, atol=1e-13)
         mo = rs.randn(cols)
