@@ -1,0 +1,443 @@
+"""The reference's own test-suite (tests/*.py + *.out goldens), run against the drop-in API
+of mannequin2_b200 on a B200.  Golden outputs are copied from /root/reference/tests/*.out as
+data; printing uses NumPy's legacy 1.13 format, which is what the goldens were written in."""
+import io
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _printopts():
+    old = np.get_printoptions()
+    np.set_printoptions(precision=3, linewidth=100, suppress=True, legacy="1.13")
+    yield
+    np.set_printoptions(**old)
+
+
+def _lines(text):
+    return [" ".join(l.split()) for l in text.strip().splitlines()]
+
+
+def test_adam_py():
+    """tests/adam.py vs tests/adam.out (20 vectors; ascent sign, bias correction, per-call lr)."""
+    from mannequin2_b200 import Adam
+    out = io.StringIO()
+    with redirect_stdout(out):
+        opt = Adam([10.0, -5.0], lr=2.0, horizon=3)
+        for i in range(10):
+            opt.apply_gradient(-opt.get_value())
+            print(opt.get_value())
+        print()
+        opt = Adam([0.0, 0.0, 0.0], horizon=1)
+        for i in range(10):
+            opt.apply_gradient([0.1, 1.0, 10.0] - opt.get_value(), lr=7.0 / (i + 1))
+            print(opt.get_value())
+    want = """[ 8. -3.]
+[ 6.055 -1.155]
+[ 4.218  0.335]
+[ 2.552  1.247]
+[ 1.125  1.509]
+[-0.001  1.25 ]
+[-0.789  0.703]
+[-1.236  0.105]
+[-1.376 -0.347]
+[-1.276 -0.545]
+
+[ 7.  7.  7.]
+[ 2.063  2.129  8.425]
+[ 0.958  1.392  9.031]
+[ 0.541  1.17   9.353]
+[ 0.35   1.084  9.545]
+[ 0.25   1.045  9.669]
+[ 0.195  1.026  9.753]
+[ 0.162  1.015  9.811]
+[ 0.142  1.009  9.853]
+[ 0.129  1.006  9.884]"""
+    assert _lines(out.getvalue()) == _lines(want)
+    # and bit-exact fp64 against the real reference's trace (tests/golden/adam.npz)
+    g = load_golden("adam")
+    opt = Adam(g["adam_values"][0], horizon=10, lr=0.003)
+    for grad, lr, want_v in zip(g["adam_grads"], g["adam_lrs"], g["adam_values"][1:]):
+        if np.isnan(lr):
+            opt.apply_gradient(grad)
+        else:
+            opt.apply_gradient(grad, lr=lr, epsilon=1e-6)
+        assert np.array_equal(np.asarray(opt.get_value()), want_v)
+    with pytest.raises(TypeError):
+        Adam([1.0], horizon=3).apply_gradient([1.0])          # lr is required, like the reference
+
+
+def test_basicnet_py():
+    """tests/basicnet.py vs tests/basicnet.out: flat layout, batch-MEAN gradient, LReLU / Tanh."""
+    import mannequin2_b200.basicnet as net
+    m = net.Affine(net.Affine(net.Input(2), 2), 2)
+    m.load_params(np.arange(12))
+
+    def check(m, x, g):
+        v, backprop = m.evaluate(x)
+        return [v, backprop(g).reshape(-1, 6)]
+
+    values = []
+    values += check(m, [1.0, 1.0], [1.0, -1.0])
+    values += check(m, np.eye(2), [[1.0, -1.0], [-2.0, 2.0]])
+    alt = np.mean([m.evaluate([1.0, 0.0])[1]([1.0, -1.0]).reshape(-1, 6),
+                   m.evaluate([0.0, 1.0])[1]([-2.0, 2.0]).reshape(-1, 6)], axis=0)
+    assert np.allclose(alt, values[-1])
+    v = [-18.4, 2.0]
+    values += [m(v)]
+    values += check(net.LReLU(m), v, [1.0, -1.0])
+    values += [m(v)]
+    values += check(net.Tanh(m), v, [1.0, -1.0])
+    out = io.StringIO()
+    with redirect_stdout(out):
+        for x in values:
+            print(x)
+    want = """[ 118.  134.]
+[[-1. -1. -1. -1. -1. -1.]
+ [ 6. -6.  9. -9.  1. -1.]]
+[[  82.   93.]
+ [ 110.  125.]]
+[[-0.5 -0.5  1.   1.   0.5  0.5]
+ [-4.   4.  -5.   5.  -0.5  0.5]]
+[-1.2  0.4]
+[-0.12  0.4 ]
+[[ 117.76  150.88  -12.8   -16.4    -6.4    -8.2 ]
+ [   0.8    -8.     -0.74    7.4     0.1    -1.  ]]
+[-1.2  0.4]
+[-0.834  0.38 ]
+[[ 76.532  96.794  -8.319 -10.521  -4.159  -5.261]
+ [  2.44   -6.845  -2.257   6.332   0.305  -0.856]]"""
+    assert _lines(out.getvalue()) == _lines(want)
+    assert m.n_params == 12 and np.array_equal(m.get_params(), np.arange(12, dtype=np.float32))
+    with pytest.raises(ValueError):
+        m.evaluate([1.0, 2.0, 3.0])
+
+
+def test_graph_py():
+    """tests/graph.py vs graph.out: fan-out DAG, each node evaluated once, user Python layers."""
+    from mannequin2_b200.basicnet import Bias, Function, Input, Tanh
+
+    def PrintLayer(inner):
+        return Function(inner, f=lambda a: ((print("Forward pass:", a), a)[1], lambda g: (g,)))
+
+    def test(m, inps=[2., 3.]):
+        inps = np.array(inps)
+        val, bpp = m.evaluate(inps)
+        print(val, np.asarray(bpp(np.ones(inps.shape))))
+
+    out = io.StringIO()
+    with redirect_stdout(out):
+        a = Bias(PrintLayer(Input(2)))
+        b = Tanh(a)
+        test(a)
+        test(b)
+        test(a + b)
+        test(a * a)
+    want = """Forward pass: [ 2.  3.]
+[ 2.  3.] [ 1.  1.]
+Forward pass: [ 2.  3.]
+[ 0.964  0.995] [ 0.071  0.01 ]
+Forward pass: [ 2.  3.]
+[ 2.964  3.995] [ 1.071  1.01 ]
+Forward pass: [ 2.  3.]
+[ 4.  9.] [ 4.  6.]"""
+    assert _lines(out.getvalue()) == _lines(want)
+
+
+def test_reshape_py():
+    """tests/reshape.py vs reshape.out: Reshape, Multiply with broadcast Params, Clip, batch (1,1)."""
+    from mannequin2_b200.basicnet import Function, Input, Params, Reshape
+
+    def PrintLayer(inner):
+        return Function(inner, f=lambda a: ((print("Layer output:\n%s\n" % a), a)[1],
+                                            lambda g: (print("Gradient:\n%s\n" % g), g)[1:]))
+
+    def Clip(inner, a, b):
+        def clip(v):
+            def bpp(g):
+                g = np.array(g)
+                g[np.logical_and(v < a, g < 0.0)] = 0.0
+                g[np.logical_and(v > b, g > 0.0)] = 0.0
+                return (g,)
+            return np.clip(v, a, b), bpp
+        return Function(inner, f=clip)
+
+    out = io.StringIO()
+    with redirect_stdout(out):
+        a = PrintLayer(Input(3, 2))
+        a = PrintLayer(Reshape(a, (2, 3)))
+        a = PrintLayer(a * Params(3))
+        a = PrintLayer(Clip(a, -2.5, 2.5))
+        a = PrintLayer(Reshape(a, -1))
+        a.load_params([1, 0, -1])
+        val, bpp = a.evaluate(np.arange(6).reshape((1, 1, 3, 2)))
+        print(np.asarray(bpp(np.ones(val.shape))))
+    text = out.getvalue()
+    assert "[[[ 0.   0.  -2.   2.5  0.  -2.5]]]" in text          # last Layer output block
+    assert _lines(text)[-1] == "[ 0. 5. 7.]"
+    grads = text.split("Gradient:")
+    assert len(grads) == 6
+    assert _lines(grads[3])[:2] == ["[[[[ 1. 1. 1.]", "[ 0. 1. 1.]]]]"]      # after Clip backward
+    assert _lines(grads[4])[:2] == ["[[[[ 1. 0. -1.]", "[ 0. 0. -1.]]]]"]    # after Multiply backward
+
+
+def test_running_mean_and_norm_py():
+    """tests/running_mean.py and tests/running_norm.py (1e-10 against np.mean / np.var(ddof=1))."""
+    from mannequin2_b200 import RunningMean, RunningNormalize
+    m = RunningMean()
+    data = np.arange(10) + 10
+    for d in [data[:i] for i in range(1, len(data))]:
+        assert np.abs(m(d[-1]) - np.mean(d)) < 1e-10
+    rs = np.random.RandomState(0)
+    m = RunningMean((7,), horizon=2)
+    data = rs.rand(4, 7)
+    np_data = []
+    for i, d in enumerate(data):
+        for _ in range(2 ** i):
+            np_data.append(d)
+        assert np.mean(np.abs(m(d) - np.mean(np_data, axis=0))) < 1e-10
+    m = RunningMean((5,))
+    data = rs.rand(4, 5)
+    m.update(data[0], weight=0.2); m.update(data[0], weight=0.8); m.update(data[1])
+    m.update(data[2], weight=1.9); m.update(data[2], weight=0.1); m.update(data[3])
+    assert np.mean(np.abs(m.get() - np.mean(data[[0, 1, 2, 2, 3]], axis=0))) < 1e-10
+
+    n = RunningNormalize()
+    data = np.arange(10) + 10
+    n.update(data[0])
+    for d in [data[:i] for i in range(2, len(data))]:
+        n.update(d[-1])
+        assert np.abs(n.get_mean() - np.mean(d)) < 1e-10
+        assert np.abs(n.get_var() - np.var(d, ddof=1)) < 1e-10
+    n = RunningNormalize()
+    data = np.random.RandomState(123).rand(10, 5)
+    for d in [data[:i] for i in range(1, len(data))]:
+        n.update(d[-1])
+        want = (np.array([4.0, 5.0]) - np.mean(d)) / np.std(d, ddof=1)
+        assert np.mean(np.abs(n.apply([4.0, 5.0]) - want)) < 1e-10
+    n = RunningNormalize((5,))
+    data = rs.rand(10, 5)
+    for d in data:
+        n.update(d)
+    want = (data - np.mean(data, axis=0)) / np.std(data, axis=0, ddof=1)
+    assert np.mean(np.abs(n.apply(data) - want)) < 1e-10
+    n = RunningNormalize((5,), horizon=2)
+    data = rs.rand(4, 5)
+    np_data = []
+    for i, d in enumerate(data):
+        n.update(d)
+        for _ in range(2 ** i):
+            np_data.append(d)
+    np_data = np.array(np_data)
+    want = (data - np.mean(np_data, axis=0)) / np.std(np_data, axis=0, ddof=1)
+    assert np.mean(np.abs(n.apply(data) - want)) < 1e-10
+    # against the real reference's trace (tests/golden/norm.npz), incl. zeros until 2 samples
+    g = load_golden("norm")
+    n = RunningNormalize(horizon=2)
+    pos, res = 0, []
+    for s in g["norm_scalar_sizes"]:
+        d = g["norm_scalar_in"][pos:pos + s]
+        pos += s
+        res.append(np.concatenate([n(d), [n.get_mean(), n.get_var()]]))
+    assert np.allclose(np.concatenate(res), g["norm_scalar_out"], rtol=1e-12, atol=1e-12)
+    n = RunningNormalize(horizon=10)
+    got = np.array([n(v) for v in g["norm_single_in"]])
+    assert got[0] == 0.0 and np.allclose(got, g["norm_single_out"], rtol=1e-12, atol=1e-12)
+
+
+def test_initializer_py():
+    """tests/initializer.py: normed_columns init gives unit output std; init=10 scales it."""
+    from mannequin2_b200.basicnet import Affine, Input, Linear
+    rs = np.random.RandomState(1)
+    np.random.seed(2)
+
+    def std_of(Model, dims, n=150):
+        vals = []
+        for _ in range(n):
+            a, b = dims()
+            v2, _ = Model(Input(a), b).evaluate(rs.randn(a))
+            vals.append(np.asarray(v2).reshape(-1))
+        return np.std(np.concatenate(vals))
+
+    rand_dims = lambda: rs.randint(16, size=2) + 5
+    assert 0.9 < std_of(Linear, lambda: (5, 20)) < 1.1
+    assert 0.9 < std_of(Affine, rand_dims) < 1.1
+    assert 9.0 < std_of(lambda *p: Linear(*p, init=10.0), rand_dims) < 11.0
+
+
+def test_predictor_py():
+    """tests/predictor1.py + predictor2.py: 64-64 Tanh MLP + Adam(h=10) regression end to end."""
+    from mannequin2_b200 import Adam
+    from mannequin2_b200.basicnet import Affine, Input, Tanh
+    np.random.seed(5)
+
+    def SimplePredictor(in_size, out_size, lr):
+        model = Input(in_size)
+        for _ in range(2):
+            model = Tanh(Affine(model, 64))
+        model = Affine(model, out_size, init=0.1)
+        opt = Adam(model.get_params(), horizon=10, lr=lr)
+
+        def sgd_step(inps, lbls):
+            outs, backprop = model.evaluate(inps)
+            opt.apply_gradient(backprop(lbls - outs))
+            model.load_params(opt.get_value())
+        model.sgd_step = sgd_step
+        return model
+
+    pred = SimplePredictor(1, 1, 0.01)
+    for _ in range(100):
+        x = np.random.randn(128, 1) * 2.0
+        pred.sgd_step(x, np.sin(x))
+    assert pred([1.0]).shape == (1,)
+    x = np.linspace(-5.0, 5.0, 101).reshape(-1, 1)
+    y = pred(x)
+    assert y.shape == x.shape
+    assert np.mean(np.abs(y - np.sin(x))) < 0.2
+
+    func = lambda x, y: [np.exp(x), x * y]
+    np.random.seed(5)
+    pred = SimplePredictor(2, 2, 0.015)
+    for _ in range(500):
+        xy = np.random.randn(256).reshape(-1, 2)
+        pred.sgd_step(xy, np.array([func(a, b) for a, b in xy]))
+    assert pred(np.eye(2)).shape == (2, 2)
+    errors = []
+    for a in np.linspace(-2.0, 2.0, 21):
+        for b in np.linspace(-2.0, 2.0, 21):
+            p = pred([a, b])
+            assert p.shape == (2,)
+            errors.append(np.abs(p - func(a, b)))
+    # The reference's "< 0.2" bound is seed dependent (it fails for the reference itself with
+    # this seed).  Stronger: the REAL reference, run in the build container with
+    # np.random.seed(5) and this exact loop, ends at mean errors [0.21544665, 0.10674201];
+    # 500 optimiser steps on the GPU must land on the same numbers.
+    assert np.allclose(np.mean(errors, axis=0), [0.21544665, 0.10674201], atol=2e-4)
+
+
+def test_nets_against_reference_fixtures():
+    """evaluate/backprop of the layer API against outputs of the REAL reference (golden/nets.npz)."""
+    import mannequin2_b200.basicnet as bn
+    g = load_golden("nets")
+    m = bn.Input(4, 5)
+    for _ in range(2):
+        m = bn.LReLU(bn.Affine(m, 16))
+    m = bn.Affine(m, 5, init=0.1)
+    m.load_params(g["lrelu_theta"])
+    y, bpp = m.evaluate(g["lrelu_x"])
+    assert_close(y, g["lrelu_y"], rtol=2e-5)
+    assert_close(np.asarray(bpp(g["lrelu_dy"])), g["lrelu_grad"], rtol=2e-5, atol_scale=2e-6)
+    assert_close(m.prerequisites[0].last_gradient, g["lrelu_dx"], rtol=2e-5, atol_scale=2e-6)
+    p = bn.Input(11)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3)
+    p.load_params(g["tanh_theta"])
+    y, bpp = p.evaluate(g["tanh_x"])
+    assert_close(y, g["tanh_y"], rtol=2e-5, atol_scale=2e-6)
+    assert_close(np.asarray(bpp(g["tanh_dy"])), g["tanh_grad"], rtol=2e-5, atol_scale=2e-6)
+    y1, bpp1 = p.evaluate(g["tanh_x"][0])                       # unbatched: no division
+    assert_close(y1, g["tanh_y1"], rtol=2e-5, atol_scale=2e-6)
+    assert_close(np.asarray(bpp1(g["tanh_dy"][0])), g["tanh_grad1"], rtol=2e-5, atol_scale=2e-6)
+    # a net too wide for the fused kernels takes the layered path: same answers as the oracle
+    from oracle import mq_oracle as O
+    np.random.seed(3)
+    w = bn.Input(28, 28)
+    for _ in range(2):
+        w = bn.LReLU(bn.Affine(w, 128))
+    w = bn.Affine(w, 10, init=0.1)
+    assert w.n_params == 118282
+    rs = np.random.RandomState(4)
+    x, dy = rs.rand(128, 28, 28).astype(np.float32), rs.randn(128, 10).astype(np.float32)
+    y, bpp = w.evaluate(x)
+    spec = O.mlp_spec(784, [128, 128, 10], [O.ACT_LRELU, O.ACT_LRELU, O.ACT_NONE])
+    theta = w.get_params()
+    outs = O.mlp_forward(theta, spec, x.reshape(128, 784))
+    assert_close(y, outs[-1], rtol=2e-5, atol_scale=2e-6)
+    assert_close(np.asarray(bpp(dy)), O.mlp_backward(theta, spec, x.reshape(128, 784), outs, dy), rtol=2e-5,
+                 atol_scale=2e-6)
+
+
+def test_gauss_policy_against_reference_fixture():
+    """Gauss(mean=net).logprob / .sample against the real reference (golden/gauss.npz)."""
+    import mannequin2_b200.basicnet as bn
+    from mannequin2_b200.distrib import Gauss
+    g = load_golden("gauss")
+    p = bn.Input(11)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3, init=0.1)
+    pol = Gauss(mean=p)
+    assert pol.n_params == 5126
+    pol.load_params(g["gauss_theta"])
+    assert np.array_equal(pol.get_params(), g["gauss_theta"])
+    logp, bpp = pol.logprob.evaluate(g["gauss_obs"], sample=g["gauss_act"])
+    assert_close(logp, g["gauss_logp"], rtol=1e-5, atol_scale=1e-6)
+    assert_close(np.asarray(bpp(g["gauss_g"])), g["gauss_grad"], rtol=3e-5, atol_scale=3e-6)
+    # general graph path (no plan) gives the same numbers: evaluate logprob of a single sample
+    l1, b1 = pol.logprob.evaluate(g["gauss_obs"][0], sample=g["gauss_act"][0])
+    assert abs(float(l1) - g["gauss_logp"][0]) < 1e-4
+    smp, bpp = pol.sample.evaluate(g["gauss_obs"][:5])
+    mu = pol.mean(g["gauss_obs"][:5])
+    noise = np.asarray(smp) - mu
+    assert noise.shape == (5, 3) and np.abs(noise).max() > 0
+    gs = g["gauss_sample_g"]
+    grad = np.asarray(bpp(gs))
+    assert_close(grad[-3:], (gs * noise).sum(axis=0) / 5, rtol=1e-4, atol_scale=1e-5)
+
+
+def test_trajectory_device_gather_and_discounted():
+    from mannequin2_b200 import Trajectory, discounted
+    g = load_golden("trajectory")
+    t = Trajectory(g["traj_o"], g["traj_a"], g["traj_r"])
+    o, a, r = t.take_dev(g["traj_idx"])
+    assert np.array_equal(o.cpu().numpy().reshape(64, 11), g["traj_take_o"])
+    assert np.array_equal(a.cpu().numpy().reshape(64, 3), g["traj_take_a"])
+    assert np.array_equal(r.cpu().numpy(), g["traj_take_r"])
+    assert np.allclose(t.discounted(horizon=20).r, g["traj_disc_r"], rtol=1e-6)
+    n = load_golden("norm")
+    assert np.allclose(discounted(n["disc_in"], horizon=500), n["disc_h500"], rtol=1e-11, atol=1e-13)
+    with pytest.raises(AssertionError):
+        discounted([1.0, 2.0], horizon=0.5)
+
+
+def test_unmodified_script_loop_via_compat_alias():
+    """`import mannequin2_b200.compat` lets reference scripts run unchanged: the inner loop of
+    mnist/mlp.py:24-35 written against `mannequin`, on synthetic MNIST-shaped data."""
+    import mannequin2_b200.compat  # noqa: F401
+    from mannequin import Adam, bar
+    from mannequin.basicnet import Input, Affine, LReLU
+    np.random.seed(0)
+    rs = np.random.RandomState(1)
+    proto = rs.rand(10, 28, 28).astype(np.float32)
+    labels = rs.randint(10, size=2048)
+    x = np.clip(proto[labels] + 0.3 * rs.randn(2048, 28, 28), 0, 1).astype(np.float32)
+    y = np.eye(10)[labels]
+
+    def softmax(v):
+        v = v.T
+        v = np.exp(v - np.amax(v, axis=0))
+        v /= np.sum(v, axis=0)
+        return v.T
+
+    model = Input(28, 28)
+    for _ in range(2):
+        model = LReLU(Affine(model, 128))
+    model = Affine(model, 10, init=0.1)
+    opt = Adam(model.get_params(), horizon=10, lr=0.001)
+    for _ in range(60):
+        idx = np.random.randint(len(x), size=128)
+        outs, backprop = model.evaluate(x[idx])
+        grad = y[idx] - softmax(outs) - outs * 0.01
+        opt.apply_gradient(backprop(grad))
+        model.load_params(opt.get_value())
+    acc = np.mean(np.argmax(model(x[:512]), axis=-1) == labels[:512])
+    assert acc > 0.9, acc
+    assert bar(100.0 * acc).startswith(" ")
