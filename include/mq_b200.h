@@ -80,6 +80,12 @@ typedef struct mq_head {
 const char *mq_last_error(void);
 /* developer aid: device buffer of 8 int64 that mq_fused_train fills with per-phase cycles */
 int mq_debug_set_phase_buffer(void *dev_buf);
+/* developer aid: force the row-tile size of the fused kernels (0 = automatic) */
+int mq_debug_set_tile_rows(int tb);
+/* developer aid: 0 makes mq_fused_grad use the tile kernel instead of the row-owner-warp kernel */
+int mq_debug_use_chain_grad(int on);
+/* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */
+int mq_debug_set_chain_warps(int nw);
 int mq_version(void);
 int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
 

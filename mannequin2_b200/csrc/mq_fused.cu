@@ -89,11 +89,15 @@ static int64_t plan_build(const mq_net_t *net, int tb, int with_grad, FusedPlan 
     return p->smem_bytes;
 }
 
+static int g_force_tb = 0;            // developer knob (mq_debug_set_tile_rows), 0 = automatic
+extern "C" int mq_debug_set_tile_rows(int tb) { g_force_tb = tb; return MQ_OK; }
+
 static int plan_choose(const mq_net_t *net, int64_t batch, int with_grad, FusedPlan *p, int smem_state = 0,
                        int nt = MQ_NT) {
     const int64_t lim = mq_smem_optin();
     int tb = 128;
     if (batch <= 32) tb = 32; else if (batch <= 64) tb = 64;
+    if (g_force_tb && batch > g_force_tb) tb = g_force_tb;
     for (; tb >= 32; tb >>= 1)
         if (plan_build(net, tb, with_grad, p, smem_state, nt) <= lim) return tb;
     return 0;
@@ -619,12 +623,31 @@ fused_grad_kernel(FusedPlan p, const float *__restrict__ theta, const float *__r
     for_each_param<MQ_NT>(p, [&](int flat, int pad) { dst[flat] = sG[pad] * sc; });
 }
 
+// grad[j] = scale * sum_b partial[b][j]: 32 parameters x 8 groups of CTAs per block, group sums
+// combined in fixed order (deterministic), 4 loads in flight per thread.
 __global__ void __launch_bounds__(MQ_NT)
 fused_reduce_kernel(const float *__restrict__ partial, int nblocks, int n_params, float scale,
                     float *__restrict__ grad) {
-    for (int j = blockIdx.x * MQ_NT + threadIdx.x; j < n_params; j += gridDim.x * MQ_NT) {
-        float s = 0.0f;
-        for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * n_params + j];
+    __shared__ float part[8][33];
+    const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + jx;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (j < n_params) {
+        int b = gy;
+        for (; b + 24 < nblocks; b += 32) {
+            s0 += partial[(int64_t)b * n_params + j];
+            s1 += partial[(int64_t)(b + 8) * n_params + j];
+            s2 += partial[(int64_t)(b + 16) * n_params + j];
+            s3 += partial[(int64_t)(b + 24) * n_params + j];
+        }
+        for (; b < nblocks; b += 8) s0 += partial[(int64_t)b * n_params + j];
+    }
+    part[gy][jx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (gy == 0 && j < n_params) {
+        float s = part[0][jx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += part[k][jx];
         grad[j] = s * scale;
     }
 }
@@ -805,6 +828,12 @@ int mq_chain_train_f32(const mq_net_t *net, float *theta, float *value, float *m
                        const mq_head_t *head, const int32_t *idx_table, int32_t n_steps, int32_t mb,
                        double beta1, double beta2, const double *tw, double lr, double eps, void *stream);
 
+int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                  int64_t batch, const mq_head_t *head, float scale, float *grad, float *out, float *logp,
+                  void *ws, int64_t ws_bytes, int *grid_out, void *stream);
+static int g_use_chain_grad = 1;     // developer knob: 0 forces the tile kernel
+extern "C" int mq_debug_use_chain_grad(int on) { g_use_chain_grad = on; return MQ_OK; }
+
 // ---- host entry points -----------------------------------------------------------------
 static int fused_net_check(const mq_net_t *net, const char *what) {
     MQ_REQUIRE(net, MQ_ERR_INVALID, "%s: null net", what);
@@ -860,14 +889,21 @@ extern "C" int mq_fused_tile_rows(const mq_net_t *net, int with_grad) {
     return plan_choose(net, 1 << 20, with_grad, &p);
 }
 
-static int64_t fused_grid(int64_t ntiles) {
+// CTAs per launch: as many as can be co-resident (shared memory bound), never more than tiles.
+// Tiles are strided by the grid size; bid and bid+148 land on the same SM, so the per-SM load
+// stays balanced (ceil vs floor of tiles/148) and the summation order stays fixed.
+static int64_t fused_grid(int64_t ntiles, int64_t smem_bytes) {
     const int64_t sms = mq_sm_count();
-    return ntiles < sms ? (ntiles < 1 ? 1 : ntiles) : sms;
+    int64_t per_sm = (228 * 1024) / (smem_bytes + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    const int64_t cap = sms * per_sm;
+    return ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap;
 }
 
 extern "C" int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch) {
     (void)batch;
-    return (int64_t)mq_sm_count() * net->n_params * (int64_t)sizeof(float) + 256;
+    return 2 * (int64_t)mq_sm_count() * net->n_params * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x,
@@ -885,7 +921,7 @@ extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const f
                "mq_fused_forward: net does not fit in shared memory");
     rc = set_smem(fused_forward_kernel, p.smem_bytes, "mq_fused_forward");
     if (rc != MQ_OK) return rc;
-    const int64_t grid = fused_grid(mq_ceil_div(batch, p.tb));
+    const int64_t grid = fused_grid(mq_ceil_div(batch, p.tb), p.smem_bytes);
     MQ_LAUNCH(fused_forward_kernel, (unsigned)grid, MQ_NT, p.smem_bytes, stream, p, theta, x, row_idx,
               batch, out, sample, logp);
     MQ_CHECK_LAUNCH("mq_fused_forward");
@@ -902,12 +938,26 @@ extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const floa
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_fused_grad: empty batch");
     MQ_REQUIRE(theta && x && grad, MQ_ERR_INVALID, "mq_fused_grad: null pointer");
+    if (g_use_chain_grad) {
+        int cgrid = 0;
+        rc = mq_chain_grad(net, theta, x, row_idx, batch, head, scale, grad, out, logp, ws, ws_bytes, &cgrid,
+                           stream);
+        if (rc == MQ_OK) {
+            if (cgrid > 1) {
+                MQ_LAUNCH(fused_reduce_kernel, (unsigned)mq_ceil_div(net->n_params, 32), MQ_NT, 0, stream,
+                          (const float *)ws, cgrid, net->n_params, scale, grad);
+                MQ_CHECK_LAUNCH("mq_fused_grad");
+            }
+            return MQ_OK;
+        }
+        if (rc != MQ_ERR_UNSUPPORTED) return rc;
+    }
     FusedPlan p;
     MQ_REQUIRE(plan_choose(net, batch, 1, &p) > 0, MQ_ERR_UNSUPPORTED,
                "mq_fused_grad: net does not fit in shared memory");
     rc = set_smem(fused_grad_kernel, p.smem_bytes, "mq_fused_grad");
     if (rc != MQ_OK) return rc;
-    const int64_t grid = fused_grid(mq_ceil_div(batch, p.tb));
+    const int64_t grid = fused_grid(mq_ceil_div(batch, p.tb), p.smem_bytes);
     if (grid == 1) {
         MQ_LAUNCH(fused_grad_kernel, 1, MQ_NT, p.smem_bytes, stream, p, theta, x, row_idx, batch, *head,
                   scale, grad, 1, out, logp);
@@ -916,7 +966,7 @@ extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const floa
                    "mq_fused_grad: workspace too small");
         MQ_LAUNCH(fused_grad_kernel, (unsigned)grid, MQ_NT, p.smem_bytes, stream, p, theta, x, row_idx,
                   batch, *head, scale, (float *)ws, 0, out, logp);
-        MQ_LAUNCH(fused_reduce_kernel, (unsigned)mq_ceil_div(net->n_params, MQ_NT), MQ_NT, 0, stream,
+        MQ_LAUNCH(fused_reduce_kernel, (unsigned)mq_ceil_div(net->n_params, 32), MQ_NT, 0, stream,
                   (const float *)ws, (int)grid, net->n_params, scale, grad);
     }
     MQ_CHECK_LAUNCH("mq_fused_grad");
