@@ -86,6 +86,8 @@ int mq_debug_set_tile_rows(int tb);
 int mq_debug_use_chain_grad(int on);
 /* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */
 int mq_debug_set_chain_warps(int nw);
+/* developer aid: tcgen05 path of mq_fused_grad / mq_fused_forward: 0 never, 1 automatic (batch >= 8192), 2 whenever the net fits */
+int mq_debug_set_tc_mode(int mode);
 int mq_version(void);
 int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
 

@@ -831,6 +831,9 @@ int mq_chain_train_f32(const mq_net_t *net, float *theta, float *value, float *m
 int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                   int64_t batch, const mq_head_t *head, float scale, float *grad, float *out, float *logp,
                   void *ws, int64_t ws_bytes, int *grid_out, void *stream);
+int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                 int64_t batch, const mq_head_t *head, int with_grad, float *out, float *logp,
+                 void *ws, int64_t ws_bytes, int *grid_out, void *stream);
 static int g_use_chain_grad = 1;     // developer knob: 0 forces the tile kernel
 extern "C" int mq_debug_use_chain_grad(int on) { g_use_chain_grad = on; return MQ_OK; }
 
@@ -916,6 +919,14 @@ extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const f
     MQ_REQUIRE(theta && x, MQ_ERR_INVALID, "mq_fused_forward: null pointer");
     MQ_REQUIRE(!logp || (sample && net->logstd_off >= 0), MQ_ERR_INVALID,
                "mq_fused_forward: logp needs sample and logstd parameters");
+    {   // large batches: tcgen05 / TMEM kernel (mq_tc.cu), forward + outputs only
+        mq_head_t fh;
+        memset(&fh, 0, sizeof(fh));
+        fh.kind = logp ? MQ_HEAD_GAUSS_LOGP : MQ_HEAD_DY;
+        fh.target = sample;
+        rc = mq_tc_launch(net, theta, x, row_idx, batch, &fh, 0, out, logp, nullptr, 0, nullptr, stream);
+        if (rc != MQ_ERR_UNSUPPORTED) return rc;
+    }
     FusedPlan p;
     MQ_REQUIRE(plan_choose(net, batch, 0, &p) > 0, MQ_ERR_UNSUPPORTED,
                "mq_fused_forward: net does not fit in shared memory");
@@ -938,6 +949,17 @@ extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const floa
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_fused_grad: empty batch");
     MQ_REQUIRE(theta && x && grad, MQ_ERR_INVALID, "mq_fused_grad: null pointer");
+    {   // large batches: tcgen05 / TMEM kernel (mq_tc.cu)
+        int tgrid = 0;
+        rc = mq_tc_launch(net, theta, x, row_idx, batch, head, 1, out, logp, ws, ws_bytes, &tgrid, stream);
+        if (rc == MQ_OK) {
+            MQ_LAUNCH(fused_reduce_kernel, (unsigned)mq_ceil_div(net->n_params, 32), MQ_NT, 0, stream,
+                      (const float *)ws, tgrid, net->n_params, scale, grad);
+            MQ_CHECK_LAUNCH("mq_fused_grad");
+            return MQ_OK;
+        }
+        if (rc != MQ_ERR_UNSUPPORTED) return rc;
+    }
     if (g_use_chain_grad) {
         int cgrid = 0;
         rc = mq_chain_grad(net, theta, x, row_idx, batch, head, scale, grad, out, logp, ws, ws_bytes, &cgrid,

@@ -571,5 +571,89 @@ def case_ops(B):
     assert b"broadcast" in lib.mq_last_error()
 
 
+def case_tc_paths(B):
+    """tcgen05 / TMEM kernel (mq_tc.cu) forced on (mode 2) for every net it accepts: the same fp32
+    bars as the FFMA kernels (three-plane bf16 operands keep 24 mantissa bits)."""
+    lib = B.lib
+    rs = np.random.RandomState(15)
+    ok(B, lib.mq_debug_set_tc_mode(2))
+    try:
+        cases = [(11, [64, 64, 3], [1, 1, 0], 64), (11, [64, 64, 3], [1, 1, 0], 1000),
+                 (11, [64, 64, 1], [1, 1, 0], 40000), (20, [16, 16, 5], [2, 2, 0], 777),
+                 (6, [32, 10], [2, 0], 333), (17, [64, 48, 6], [1, 2, 1], 2500)]
+        for n_in, widths, acts, batch in cases:
+            spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
+            net = net_of(spec)
+            n_out = widths[-1]
+            ht, hx = B.up(theta), B.up(x)
+            out = B.zeros((batch, n_out), np.float32)
+            ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(out), None, None, B.stream))
+            outs = O.mlp_forward(theta, spec, x)
+            close(B.down(out), outs[-1], what="tc fwd %s b=%d" % (widths, batch))
+            wsb = lib.mq_fused_ws_bytes(net, batch)
+            ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
+            dy = rs.randn(batch, n_out).astype(np.float32)
+            h = head(B, L.HEAD_DY, dy=B.up(dy))
+            out2 = B.zeros((batch, n_out), np.float32)
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                    B.ptr(grad), B.ptr(out2), None, B.ptr(ws), wsb, B.stream))
+            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, dy), what="tc grad DY %s b=%d" % (widths, batch))
+            close(B.down(out2), outs[-1], what="tc grad out")
+            tgt = rs.randn(batch, n_out).astype(np.float32)
+            h = head(B, L.HEAD_DIFF, target=B.up(tgt))
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                    B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, tgt - outs[-1]), what="tc grad DIFF %s" % (widths,))
+            if n_out >= 2 and acts[-1] == 0:
+                onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
+                h = head(B, L.HEAD_SOFTMAX_CE, p0=0.01, target=B.up(onehot))
+                ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                        B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+                close(B.down(grad), O.mlp_backward(theta, spec, x, outs, O.softmax_ce_grad(outs[-1], onehot)),
+                      what="tc grad CE %s" % (widths,))
+        # Gaussian policy: reference fixtures, then the PPO head with gathered rows
+        g = golden("gauss")
+        spec = O.policy_spec(11, 3)
+        net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+        theta, obs, act, w = g["gauss_theta"], g["gauss_obs"], g["gauss_act"], g["gauss_g"]
+        ht, ho, ha, hw = B.up(theta), B.up(obs), B.up(act), B.up(w)
+        logp = B.zeros(64, np.float32)
+        ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(ho), None, 64, None, B.ptr(ha), B.ptr(logp), B.stream))
+        close(B.down(logp), g["gauss_logp"], what="tc logp vs reference")
+        wsb = lib.mq_fused_ws_bytes(net, 1 << 16)
+        ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
+        h = head(B, L.HEAD_GAUSS_LOGP, dy=hw, target=ha)
+        logp2 = B.zeros(64, np.float32)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad), None,
+                                B.ptr(logp2), B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), g["gauss_grad"], rtol=3e-5, atol_scale=3e-6, what="tc gauss grad vs reference")
+        close(B.down(logp2), g["gauss_logp"], what="tc grad logp vs reference")
+        n = 30000
+        o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+        a = rs.randn(n, 3).astype(np.float32)
+        adv = np.tanh(rs.randn(n)).astype(np.float32)
+        lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
+        ho, ha, hadv, hlp = B.up(o), B.up(a), B.up(adv), B.up(lp_old)
+        for mb in (64, 200, 20000):
+            idx = rs.randint(n, size=mb).astype(np.int32)
+            hi = B.up(idx)
+            h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                    B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+            lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
+            wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
+            close(B.down(grad), O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs), rtol=3e-5,
+                  atol_scale=3e-6, what="tc ppo grad mb=%d" % mb)
+            # the tensor-core and the FFMA kernel agree with each other at the same bar
+            ok(B, lib.mq_debug_set_tc_mode(0))
+            g2 = B.zeros(5126, np.float32)
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                    B.ptr(g2), None, None, B.ptr(ws), wsb, B.stream))
+            ok(B, lib.mq_debug_set_tc_mode(2))
+            close(B.down(grad), B.down(g2), rtol=3e-5, atol_scale=3e-6, what="tc vs ffma mb=%d" % mb)
+    finally:
+        lib.mq_debug_set_tc_mode(1)
+
+
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_fused_heads,
-             case_fused_gauss_ppo, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_tc_paths, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
