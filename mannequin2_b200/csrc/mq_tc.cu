@@ -12,18 +12,27 @@
 // (x = x0 + x1 + x2, 24 mantissa bits) and a product is the six plane pairs with i + j <= 2,
 // accumulated in fp32 in TMEM; the dropped terms are below 2^-24 |a||b|.
 //
-// One CTA (256 threads) per SM walks tiles of <= 128 batch rows:
+// An MMA of this size costs max(~32 cycles, operand bytes / 128 B per cycle, M*N/256) (measured,
+// tools/tc_mma_bench.cu), so the plane pairs are NOT issued one by one: planes are laid out next to
+// each other and one instruction covers several pairs through a wide N
+//   forward / dA   A_0 x [W_0|W_1], A_1 x [W_0|W_1], A_0 x W_2, A_2 x W_0   (two 64-column blocks that
+//                  the epilogue adds)
+//   dW^T, db       dZ_0 x [A_2|A_1|A_0|1], dZ_1 x [A_1|A_0|1], dZ_2 x [A_0|1] into one accumulator
+//                  whose three column blocks (+ the ones column = bias gradient) are added at the end.
+//
+// One CTA (512 threads) per SM walks tiles of <= 128 batch rows:
 //   smem  operands as 8 x 16 B core matrices (SWIZZLE_NONE).  An activation buffer is
-//         [plane][feature chunk of 8][row] so that the SAME bytes serve as the K-major A operand
-//         of the next layer / of dA (rows = M) and as the MN-major operand of dW (rows = K);
-//         weights are staged once per launch as [plane][k chunk][n], K-major for the forward
-//         product and MN-major (same bytes) for dA = dZ W^T.
-//   TMEM  lane = batch row.  Z_l is overwritten in place by the fp32 activation (kept for the
-//         backward pass), dA_l has its own columns, the dW / db accumulators (M = 64: row i in
-//         lane i%16 + 32*(i/16)) persist across all tiles of the CTA and are read once.
+//         [plane 2,1,0][feature chunk of 8][row] + one chunk of ones, so that the SAME bytes serve as
+//         the K-major A operand of the next layer / of dA (rows = M) and, planes side by side, as the
+//         MN-major operand of dW (rows = K).  Weights are staged once per launch in two images:
+//         [k chunk][plane][n] (K-major B of the forward product, planes side by side along N) and
+//         [plane][k chunk][n] (MN-major B of dA = dZ W^T, planes side by side along N').
+//   TMEM  lane = batch row for Z / dA (128 columns, reused by every layer); the dW / db accumulators
+//         (M = 64: row i in lane i%16 + 32*(i/16)) persist across all tiles of the CTA.
 //   dZ_l overwrites A_{l+1} in shared memory in place (same thread, same element), after the
 //   commit that covers the last MMA reading A_{l+1}.
-// MMAs are issued by one thread; completion is a tcgen05.commit on one mbarrier per phase.
+// MMAs are issued by one elected lane inside warp-uniform control flow (descriptors stay in uniform
+// registers); completion is a tcgen05.commit on one mbarrier per phase.
 // Per-CTA partial gradients go to the workspace and are summed in fixed order by
 // fused_reduce_kernel (mq_fused.cu): bit-reproducible run to run.
 #include "mq_common.cuh"
@@ -32,11 +41,10 @@
 #include <cuda_bf16.h>
 
 #define HALF_LOG_2PI 0.91893853320467274178f
-#define TC_NT 256
-#define TC_ROWS 128              // MMA M
+#define TC_NT 512
+#define TC_ROWS 128              // MMA M of the row-major products
 #define TC_HID 64                // padded hidden width
 #define TC_NO 16                 // padded output width
-#define TC_PLANES 3
 #define TC_CHUNK_BYTES 2048      // one 8-feature chunk of all 128 rows (128 rows x 16 B)
 #define TC_MAXL 3
 
@@ -47,12 +55,12 @@ struct TcPlan {
     int kp[TC_MAXL], np[TC_MAXL];
     int tile_rows;               // rows per tile, multiple of 16, <= 128
     int with_grad;
-    // shared-memory byte offsets
-    int off_dzl, off_act[TC_MAXL], act_plane[TC_MAXL], off_ones, off_w[TC_MAXL], w_plane[TC_MAXL];
+    // shared-memory byte offsets.  act[l]: planes 2,1,0 then the ones chunk; dzl: planes 2,1,0
+    int off_dzl, off_act[TC_MAXL], act_plane[TC_MAXL], off_wf[TC_MAXL], off_wb[TC_MAXL], wb_plane[TC_MAXL];
     int off_bias, off_misc;
     int smem_bytes;
     // TMEM columns
-    int col_z[TC_MAXL], col_da[TC_MAXL], col_dw[TC_MAXL], col_db[TC_MAXL];
+    int col_za, col_save, col_acc[TC_MAXL], col_rb;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -107,22 +115,6 @@ __device__ __forceinline__ void tc_publish() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
     asm volatile(
@@ -136,20 +128,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const float *v) {
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float *v) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
         ::"r"(taddr),
           "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
           "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
           "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -168,68 +154,121 @@ __device__ __forceinline__ void tc_split_pair(float a, float b, uint32_t &w0, ui
     w2 = *reinterpret_cast<uint32_t *>(&h2);
 }
 
+// address of (chunk, row) in plane 0 of an activation buffer (planes are stored 2,1,0)
+__device__ __forceinline__ unsigned char *tc_chunk_ptr(unsigned char *buf, int plane_bytes, int chunk, int row) {
+    return buf + 2 * plane_bytes + chunk * TC_CHUNK_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+}
+
 // store 8 consecutive features of one row as one 16-byte chunk in each of the three planes
-__device__ __forceinline__ void tc_store_chunk(unsigned char *buf, int plane_bytes, int chunk, int row,
-                                               const float *v) {
+__device__ __forceinline__ void tc_store_chunk(unsigned char *buf, int plane_bytes, int chunk, int row, const float *v) {
     uint32_t w[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) tc_split_pair(v[2 * j], v[2 * j + 1], w[0][j], w[1][j], w[2][j]);
-    unsigned char *p = buf + chunk * TC_CHUNK_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+    unsigned char *p = tc_chunk_ptr(buf, plane_bytes, chunk, row);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl)
-        *reinterpret_cast<uint4 *>(p + pl * plane_bytes) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+        *reinterpret_cast<uint4 *>(p - pl * plane_bytes) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
 }
 
-// ---- MMA issue helpers (one thread) -----------------------------------------------------------
-// (called by the elected lane of a warp inside warp-uniform control flow, so that descriptors live in uniform registers)
-struct TcOperand {
-    uint32_t lo, hi;      // descriptor words of plane 0, K step 0
-    uint32_t plane16;     // (bytes between planes) >> 4
-    uint32_t k16;         // (bytes per K step of 16 elements) >> 4
-    int planes;           // 3, or 1 for the ones matrix
-};
-
-// D (+)= A * B over the plane pairs with i + j <= 2 (largest terms first)
-__device__ __forceinline__ void tc_product(uint32_t d_tmem, const TcOperand &a, const TcOperand &b,
-                                           uint32_t idesc, int ksteps, bool accumulate) {
-    uint32_t acc = accumulate ? 1u : 0u;
+// the exact fp32 values back from the three planes
+__device__ __forceinline__ void tc_load_chunk(const unsigned char *buf, int plane_bytes, int chunk, int row, float *v) {
+    const unsigned char *p = tc_chunk_ptr(const_cast<unsigned char *>(buf), plane_bytes, chunk, row);
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    const uint4 b = *reinterpret_cast<const uint4 *>(p - plane_bytes);
+    const uint4 c = *reinterpret_cast<const uint4 *>(p - 2 * plane_bytes);
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w}, wc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-#pragma unroll
-        for (int i = 0; i <= s; ++i) {
-            const int j = s - i;
-            if (i >= a.planes || j >= b.planes) continue;
-            uint32_t alo = a.lo + i * a.plane16, blo = b.lo + j * b.plane16;
-#pragma unroll 1
-            for (int k = 0; k < ksteps; ++k) {
-                tc_mma(d_tmem, alo, a.hi, blo, b.hi, idesc, acc);
-                alo += a.k16;
-                blo += b.k16;
-                acc = 1u;
-            }
-        }
+    for (int j = 0; j < 4; ++j) {
+        v[2 * j] = (__uint_as_float(wa[j] << 16) + __uint_as_float(wb[j] << 16)) + __uint_as_float(wc[j] << 16);
+        v[2 * j + 1] = (__uint_as_float(wa[j] & 0xFFFF0000u) + __uint_as_float(wb[j] & 0xFFFF0000u)) +
+                       __uint_as_float(wc[j] & 0xFFFF0000u);
     }
 }
 
-// activation buffer viewed K-major (M = rows, K = features): LBO = chunk stride, SBO = row-group stride
-__device__ __forceinline__ TcOperand tc_act_k(uint32_t base, int plane) {
-    return TcOperand{tc_desc_lo(base, TC_CHUNK_BYTES), tc_desc_hi(128u), (uint32_t)plane >> 4, (2u * TC_CHUNK_BYTES) >> 4, 3};
+// ---- MMA issue helpers ----------------------------------------------------------------------------
+// (called by the elected lane of a warp inside warp-uniform control flow, so that descriptors live in
+// uniform registers).  A view is the two descriptor words of its first K step plus the K-step advance.
+struct TcView { uint32_t lo, hi, k16; };
+
+// activation buffer plane at `addr` viewed K-major (M = rows, K = features): LBO = chunk stride, SBO = row-group stride
+__device__ __forceinline__ TcView tc_rows_k(uint32_t addr) {
+    return TcView{tc_desc_lo(addr, TC_CHUNK_BYTES), tc_desc_hi(128u), (2u * TC_CHUNK_BYTES) >> 4};
 }
-// activation buffer viewed MN-major (M or N = features, K = rows): LBO = row-group stride, SBO = chunk stride
-__device__ __forceinline__ TcOperand tc_act_mn(uint32_t base, int plane) {
-    return TcOperand{tc_desc_lo(base, 128u), tc_desc_hi(TC_CHUNK_BYTES), (uint32_t)plane >> 4, 256u >> 4, 3};
+// activation buffer from `addr` on viewed MN-major (M or N = features, planes side by side; K = rows)
+__device__ __forceinline__ TcView tc_feat_mn(uint32_t addr) {
+    return TcView{tc_desc_lo(addr, 128u), tc_desc_hi(TC_CHUNK_BYTES), 256u >> 4};
 }
-// weight image [k chunk][n][8 k] viewed K-major (N = out, K = in): forward
-__device__ __forceinline__ TcOperand tc_w_k(uint32_t base, int plane, int np) {
-    return TcOperand{tc_desc_lo(base, (uint32_t)np * 16u), tc_desc_hi(128u), (uint32_t)plane >> 4, ((uint32_t)np * 32u) >> 4, 3};
+// forward weight image [k chunk][plane][n][8 k] from row `addr` on, K-major (N = plane*np + n, K = in)
+__device__ __forceinline__ TcView tc_wf_k(uint32_t addr, int np) {
+    return TcView{tc_desc_lo(addr, 3u * (uint32_t)np * 16u), tc_desc_hi(128u), (6u * (uint32_t)np * 16u) >> 4};
 }
-// same bytes viewed MN-major (N' = in, K' = out): dA = dZ W^T
-__device__ __forceinline__ TcOperand tc_w_mn(uint32_t base, int plane, int np) {
-    return TcOperand{tc_desc_lo(base, 128u), tc_desc_hi((uint32_t)np * 16u), (uint32_t)plane >> 4, 256u >> 4, 3};
+// backward weight image [plane][k chunk][n][8 k] from `addr` on, MN-major (N' = plane*kp + k, K' = n)
+__device__ __forceinline__ TcView tc_wb_mn(uint32_t addr, int np) {
+    return TcView{tc_desc_lo(addr, 128u), tc_desc_hi((uint32_t)np * 16u), 256u >> 4};
+}
+
+// D[128 x (two blocks of nb)] = sum over plane pairs of A_i B_j, A row-major planes (2,1,0 in memory, `a_plane`
+// bytes apart, a0 = plane 0), B a weight image whose planes sit side by side along N (b_plane16 = plane stride >> 4
+// in descriptor units).  Four instructions per K step.
+__device__ __forceinline__ void tc_rows_product(uint32_t d_tmem, uint32_t a0_addr, uint32_t a_plane, const TcView &b,
+                                                int b_mn, uint32_t b_plane16, int nb, int ksteps) {
+    const TcView a0 = tc_rows_k(a0_addr);
+    const uint32_t ap16 = a_plane >> 4;
+    const uint32_t id2 = tc_idesc(TC_ROWS, 2 * nb, 0, b_mn);
+    const uint32_t id1 = tc_idesc(TC_ROWS, nb, 0, b_mn);
+    uint32_t alo = a0.lo, blo = b.lo;
+#pragma unroll 1
+    for (int k = 0; k < ksteps; ++k) {
+        tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id2, k > 0 ? 1u : 0u);             // A_0 x [B_0|B_1]
+        tc_mma(d_tmem, alo - ap16, a0.hi, blo, b.hi, id2, 1u);                    // A_1 x [B_0|B_1]
+        tc_mma(d_tmem, alo, a0.hi, blo + 2 * b_plane16, b.hi, id1, 1u);           // A_0 x B_2
+        tc_mma(d_tmem, alo - 2 * ap16, a0.hi, blo, b.hi, id1, 1u);                // A_2 x B_0
+        alo += a0.k16;
+        blo += b.k16;
+    }
+}
+
+// acc[64 x (2 nb + extra)] (+)= sum over plane pairs of Da_i^T Db_j over the rows of the tile: Da, Db activation
+// buffers (planes 2,1,0 in memory), Da's features are M, Db's planes 1,0 side by side (+ `extra` columns behind
+// plane 0) are N.  Column blocks: [Db_1 | Db_0 | extra]; Da_0 x Db_2 is added into the first block (the final
+// epilogue adds the blocks anyway).  Four instructions per K step of 16 rows.
+__device__ __forceinline__ void tc_feat_product(uint32_t acc_tmem, uint32_t da_base, uint32_t da_plane, uint32_t db_base,
+                                                uint32_t db_plane, int nb, int extra, int ksteps, bool accumulate) {
+    const TcView a = tc_feat_mn(da_base), b = tc_feat_mn(db_base);
+    const uint32_t ap16 = da_plane >> 4, bp16 = db_plane >> 4;
+    const uint32_t id_all = tc_idesc(64, 2 * nb + extra, 1, 1), id_one = tc_idesc(64, nb + extra, 1, 1), id_blk = tc_idesc(64, nb, 1, 1);
+    uint32_t alo = a.lo, blo = b.lo;
+#pragma unroll 1
+    for (int k = 0; k < ksteps; ++k) {
+        tc_mma(acc_tmem, alo + 2 * ap16, a.hi, blo + bp16, b.hi, id_all, (accumulate || k > 0) ? 1u : 0u);   // Da_0 x [Db_1|Db_0|e]
+        tc_mma(acc_tmem, alo + ap16, a.hi, blo + bp16, b.hi, id_all, 1u);                                    // Da_1 x [Db_1|Db_0|e]
+        tc_mma(acc_tmem + nb, alo, a.hi, blo + 2 * bp16, b.hi, id_one, 1u);                                  // Da_2 x [Db_0|e]
+        tc_mma(acc_tmem, alo + 2 * ap16, a.hi, blo, b.hi, id_blk, 1u);                                       // Da_0 x Db_2
+        alo += a.k16;
+        blo += b.k16;
+    }
+}
+
+// branch-free tanh on raw MUFU ops: 1 - 2/(2^(2 log2(e) |x|) + 1) with the sign of x, odd polynomial below 0.1
+// (same formulation and error, ~2e-7 absolute, as mq_tanh)
+__device__ __forceinline__ float tc_tanh(float x) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    const float big = copysignf(fmaf(r, -2.0f, 1.0f), x);
+    const float x2 = x * x;
+    const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
+    return fabsf(x) < 0.1f ? poly : big;
+}
+
+template <int ACT>
+__device__ __forceinline__ float tc_act(float z, float leak) {
+    if (ACT == MQ_ACT_TANH) return tc_tanh(z);
+    return z < 0.0f ? z * leak : z;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------
-template <int K0>
+template <int K0, int HACT>
 __global__ void __launch_bounds__(TC_NT, 1)
 tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restrict__ x,
                const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
@@ -243,10 +282,11 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     long long t_last = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
     if (profiling) t_last = clock64();
+    if (prof != nullptr && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); prof[64 + 2 * blockIdx.x] = (long long)gt; }
 #define TC_MARK(i) do { if (profiling) { long long now_ = clock64(); prof[i] += now_ - t_last; t_last = now_; } } while (0)
     const int L = p.L;
     const int n_in = p.net.n_in, n_out = p.net.n_out;
-    constexpr int XCH = K0 / 16;                       // 8-feature chunks per thread of the input tile
+    constexpr int XCHUNKS = K0 / 8;
 
     // ---- one-time setup: TMEM, barrier, operand images of the weights --------------------------
     if (warp == 0) {
@@ -261,22 +301,34 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     __syncthreads();
     {
         __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
-        uint16_t ob = *reinterpret_cast<uint16_t *>(&one);
-        for (int i = tid; i < TC_CHUNK_BYTES / 2; i += TC_NT) reinterpret_cast<uint16_t *>(smem + p.off_ones)[i] = ob;
+        const uint32_t ob = *reinterpret_cast<uint16_t *>(&one);
+        for (int l = 0; l < L; ++l) {
+            uint32_t *ones = reinterpret_cast<uint32_t *>(smem + p.off_act[l] + 3 * p.act_plane[l]);
+            for (int i = tid; i < TC_CHUNK_BYTES / 4; i += TC_NT) ones[i] = ob | (ob << 16);
+        }
     }
     float *sBias = reinterpret_cast<float *>(smem + p.off_bias);      // [L][64]
     float *sMisc = reinterpret_cast<float *>(smem + p.off_misc);      // logstd[16], exp(-logstd)[16]
     for (int l = 0; l < L; ++l) {
         const int in = p.net.in[l], on = p.net.out[l], np = p.np[l];
         const float *w = theta + p.net.w_off[l];
-        for (int e = tid; e < in * on; e += TC_NT) {
+        const int total = in * on;
+#pragma unroll 4
+        for (int e = tid; e < total; e += TC_NT) {
             const int k = e / on, n = e - k * on;
             uint32_t w0, w1, w2;
-            tc_split_pair(w[e], 0.0f, w0, w1, w2);
-            unsigned char *dst = smem + p.off_w[l] + (k >> 3) * (np * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
-            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(w0 & 0xFFFFu);
-            *reinterpret_cast<uint16_t *>(dst + p.w_plane[l]) = (uint16_t)(w1 & 0xFFFFu);
-            *reinterpret_cast<uint16_t *>(dst + 2 * p.w_plane[l]) = (uint16_t)(w2 & 0xFFFFu);
+            tc_split_pair(__ldg(w + e), 0.0f, w0, w1, w2);
+            // forward image [k chunk][plane][n][8 k]
+            unsigned char *df = smem + p.off_wf[l] + (k >> 3) * (3 * np * 16) + n * 16 + (k & 7) * 2;
+            *reinterpret_cast<uint16_t *>(df) = (uint16_t)(w0 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(df + np * 16) = (uint16_t)(w1 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(df + 2 * np * 16) = (uint16_t)(w2 & 0xFFFFu);
+            if (l > 0 && p.with_grad) {      // backward image [plane][k chunk][n][8 k]
+                unsigned char *db = smem + p.off_wb[l] + (k >> 3) * (np * 16) + n * 16 + (k & 7) * 2;
+                *reinterpret_cast<uint16_t *>(db) = (uint16_t)(w0 & 0xFFFFu);
+                *reinterpret_cast<uint16_t *>(db + p.wb_plane[l]) = (uint16_t)(w1 & 0xFFFFu);
+                *reinterpret_cast<uint16_t *>(db + 2 * p.wb_plane[l]) = (uint16_t)(w2 & 0xFFFFu);
+            }
         }
         for (int n = tid; n < on; n += TC_NT) sBias[l * 64 + n] = theta[p.net.b_off[l] + n];
     }
@@ -294,9 +346,10 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     bool pending = false;                               // a committed MMA batch nobody waited for yet
     bool dw_started = false;                            // dW / db accumulators hold data
 
-    const int row = (warp & 3) * 32 + lane;             // TMEM lane == batch row of the tile
-    const int half = warp >> 2;                         // which 32 of the 64 columns this thread owns
-    const uint32_t tlane = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int cg = warp >> 2;                           // which 16 of the 64 columns this thread owns
+    const int row = quarter * 32 + lane;                // TMEM lane == batch row of the tile
+    const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
     const int tr = p.tile_rows;
     const int64_t ntiles = (n_rows + tr - 1) / tr;
     const int dw_ksteps = tr / 16;
@@ -304,37 +357,39 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     const int lastact = p.net.act[L - 1];
     const float lastleak = p.net.leak[L - 1];
 
-    // input-tile staging: thread (row = tid & 127) owns chunks (tid >> 7) + 2 j
-    const int xrow = tid & 127;
-    float xr[XCH][8];
-    auto load_x = [&](int64_t tile) {
+    // input-tile staging: thread t < 128 * XCHUNKS owns (row = t & 127, chunk = t >> 7); the row index of the NEXT
+    // tile is fetched one tile ahead of its features so that the gather never waits on the index
+    const int xrow = tid & 127, xchunk = tid >> 7;
+    const bool xthread = xchunk < XCHUNKS;
+    float xr[8];
+    int64_t xsrc_next = -1;
+    auto load_src = [&](int64_t tile) -> int64_t {
         const int64_t gr = tile * tr + xrow;
-        const bool valid = xrow < tr && gr < n_rows;
-        const int64_t src = valid ? (idx ? (int64_t)idx[gr] : gr) : 0;
-        const float *xp = x + src * n_in;
+        if (!(xrow < tr && gr < n_rows && tile < ntiles)) return -1;
+        return idx ? (int64_t)__ldg(idx + gr) : gr;
+    };
+    auto load_x = [&](int64_t src) {
 #pragma unroll
-        for (int j = 0; j < XCH; ++j) {
-            const int c = (tid >> 7) + 2 * j;
-#pragma unroll
-            for (int f = 0; f < 8; ++f) {
-                const int col = c * 8 + f;
-                xr[j][f] = (valid && col < n_in) ? __ldg(xp + col) : 0.0f;
-            }
+        for (int f = 0; f < 8; ++f) {
+            const int col = xchunk * 8 + f;
+            xr[f] = (src >= 0 && col < n_in) ? __ldg(x + src * n_in + col) : 0.0f;
         }
     };
-    if ((int64_t)blockIdx.x < ntiles) load_x(blockIdx.x);
+    if (xthread) {
+        load_x(load_src(blockIdx.x));
+        xsrc_next = load_src((int64_t)blockIdx.x + gridDim.x);
+    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * tr;
         const int64_t gr = row0 + row;
         const bool rvalid = row < tr && gr < n_rows;
-        const int64_t hsrc = rvalid ? (idx ? (int64_t)idx[gr] : gr) : 0;
+        int64_t hsrc = 0;
+        if (cg == 0 && rvalid) hsrc = idx ? (int64_t)__ldg(idx + gr) : gr;
         if (pending) { tc_wait(mbar, parity); parity ^= 1; pending = false; }
         TC_MARK(1);
         // ---- stage the input tile ---------------------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < XCH; ++j)
-            tc_store_chunk(smem + p.off_act[0], p.act_plane[0], (tid >> 7) + 2 * j, xrow, xr[j]);
+        if (xthread) tc_store_chunk(smem + p.off_act[0], p.act_plane[0], xchunk, xrow, xr);
         tc_publish();
         TC_MARK(2);
         // ---- forward ------------------------------------------------------------------------------
@@ -342,19 +397,21 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         float h_adv = 0.0f, h_lpold = 0.0f;
         for (int l = 0; l < L; ++l) {
             if (warp == 0) {
-              if (tc_elect_one()) {
-                tc_product(tm + p.col_z[l], tc_act_k(sbase + p.off_act[l], p.act_plane[l]),
-                           tc_w_k(sbase + p.off_w[l], p.w_plane[l], p.np[l]),
-                           tc_idesc(TC_ROWS, p.np[l], 0, 0), p.kp[l] / 16, false);
-                tc_commit(mbar);
-              }
-              __syncwarp();
+                if (tc_elect_one()) {
+                    tc_rows_product(tm + p.col_za, sbase + p.off_act[l] + 2 * p.act_plane[l], p.act_plane[l],
+                                    tc_wf_k(sbase + p.off_wf[l], p.np[l]), 0, (uint32_t)p.np[l], p.np[l], p.kp[l] / 16);
+                    tc_commit(mbar);
+                }
+                __syncwarp();
             }
             TC_MARK(3);
             if (l == 0) {
                 // overlap global loads with the first products: next tile's rows, this tile's head inputs
-                if (tile + gridDim.x < ntiles) load_x(tile + gridDim.x);
-                if (half == 0) {
+                if (xthread) {
+                    load_x(xsrc_next);
+                    xsrc_next = load_src(tile + 2 * (int64_t)gridDim.x);
+                }
+                if (cg == 0) {
                     const float *mat = (head.kind == MQ_HEAD_DY) ? head.dy : head.target;
 #pragma unroll
                     for (int n = 0; n < TC_NO; ++n) tgt[n] = (rvalid && n < n_out && mat) ? __ldg(mat + hsrc * n_out + n) : 0.0f;
@@ -370,30 +427,37 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
             tc_wait(mbar, parity); parity ^= 1;
             TC_MARK(5 + l);
             if (l < L - 1) {
-                // A_{l+1} = act(Z_l + b_l): fp32 copy back to TMEM, three bf16 planes to shared memory
-                float v[32];
-                tc_ld32(tlane + p.col_z[l] + half * 32, v);
-                const float *b = sBias + l * 64 + half * 32;
-                const int act = p.net.act[l];
+                // A_{l+1} = act(Z_l + b_l), Z_l = the two column blocks: fp32 copy to TMEM for the backward pass,
+                // three bf16 planes to shared memory
+                float v[16], v2[16];
+                tc_ld16(tlane + p.col_za + cg * 16, v);
+                tc_ld16(tlane + p.col_za + TC_HID + cg * 16, v2);
+                const float4 *b4 = reinterpret_cast<const float4 *>(sBias + l * 64 + cg * 16);
                 const float leak = p.net.leak[l];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = mq_act_apply(v[j] + b[j], act, leak);
-                if (p.with_grad) tc_st32(tlane + p.col_z[l] + half * 32, v);
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], half * 4 + c, row, v + 8 * c);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = b4[j];
+                    v[4 * j + 0] = tc_act<HACT>((v[4 * j + 0] + v2[4 * j + 0]) + bb.x, leak);
+                    v[4 * j + 1] = tc_act<HACT>((v[4 * j + 1] + v2[4 * j + 1]) + bb.y, leak);
+                    v[4 * j + 2] = tc_act<HACT>((v[4 * j + 2] + v2[4 * j + 2]) + bb.z, leak);
+                    v[4 * j + 3] = tc_act<HACT>((v[4 * j + 3] + v2[4 * j + 3]) + bb.w, leak);
+                }
+                if (p.with_grad) tc_st16(tlane + p.col_save + l * TC_HID + cg * 16, v);
+                tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2, row, v);
+                tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2 + 1, row, v + 8);
                 tc_publish();
                 TC_MARK(8 + l);
             }
         }
         // ---- head: loss-gradient rule on the output row (one thread per row, warps 0-3) ------------
-        if (half == 0) {
-            float y[TC_NO], dz[TC_NO];
-            tc_ld16(tlane + p.col_z[L - 1], y);
+        if (cg == 0) {
+            float y[TC_NO], y2[TC_NO], dz[TC_NO];
+            tc_ld16(tlane + p.col_za, y);
+            tc_ld16(tlane + p.col_za + TC_NO, y2);
             const float *b = sBias + (L - 1) * 64;
 #pragma unroll
             for (int n = 0; n < TC_NO; ++n) {
-                y[n] = (n < n_out) ? mq_act_apply(y[n] + b[n], lastact, lastleak) : 0.0f;
+                y[n] = (n < n_out) ? mq_act_apply((y[n] + y2[n]) + b[n], lastact, lastleak) : 0.0f;
                 dz[n] = 0.0f;
             }
             if (rvalid && out) {
@@ -448,52 +512,61 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 }
             }
             if (p.with_grad) {
-                tc_store_chunk(smem + p.off_dzl, TC_NO / 8 * TC_CHUNK_BYTES, 0, row, dz);
-                tc_store_chunk(smem + p.off_dzl, TC_NO / 8 * TC_CHUNK_BYTES, 1, row, dz + 8);
+                tc_store_chunk(smem + p.off_dzl, 2 * TC_CHUNK_BYTES, 0, row, dz);
+                tc_store_chunk(smem + p.off_dzl, 2 * TC_CHUNK_BYTES, 1, row, dz + 8);
             }
         }
-        if (!p.with_grad) { tc_publish(); continue; }
         tc_publish();
         TC_MARK(11);
+        if (!p.with_grad) continue;
         // ---- backward -----------------------------------------------------------------------------
         for (int l = L - 1; l >= 0; --l) {
-            // dZ_l lives in dzl (l == L-1) or in act[l+1] (in place of A_{l+1})
-            const uint32_t dz_base = sbase + (l == L - 1 ? p.off_dzl : p.off_act[l + 1]);
-            const int dz_plane = (l == L - 1) ? TC_NO / 8 * TC_CHUNK_BYTES : p.act_plane[l + 1];
             if (warp == 0) {
-              if (tc_elect_one()) {
-                if (l > 0)      // dA_l = dZ_l W_l^T  (M = rows, N = in_l = 64, K = out_l)
-                    tc_product(tm + p.col_da[l], tc_act_k(dz_base, dz_plane), tc_w_mn(sbase + p.off_w[l], p.w_plane[l], p.np[l]),
-                               tc_idesc(TC_ROWS, p.kp[l], 0, 1), p.np[l] / 16, false);
-                if (l > 0)      // dW_l += A_l^T dZ_l   (M = in_l = 64, N = out_l, K = rows)
-                    tc_product(tm + p.col_dw[l], tc_act_mn(sbase + p.off_act[l], p.act_plane[l]), tc_act_mn(dz_base, dz_plane),
-                               tc_idesc(64, p.np[l], 1, 1), dw_ksteps, dw_started);
-                else            // dW_0^T += dZ_0^T A_0 (M = out_0 = 64, N = k0, K = rows)
-                    tc_product(tm + p.col_dw[0], tc_act_mn(dz_base, dz_plane), tc_act_mn(sbase + p.off_act[0], p.act_plane[0]),
-                               tc_idesc(64, K0, 1, 1), dw_ksteps, dw_started);
-                // db_l += dZ_l^T 1        (M = 64 feature rows of dZ_l, N = 8 identical columns)
-                tc_product(tm + p.col_db[l], tc_act_mn(dz_base, dz_plane),
-                           TcOperand{tc_desc_lo(sbase + (uint32_t)p.off_ones, 128u), tc_desc_hi(TC_CHUNK_BYTES), 0u, 256u >> 4, 1},
-                           tc_idesc(64, 8, 1, 1), dw_ksteps, dw_started);
-                tc_commit(mbar);
-              }
-              __syncwarp();
+                if (tc_elect_one()) {
+                    if (l == L - 1) {
+                        // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
+                        tc_rows_product(tm + p.col_za, sbase + p.off_dzl + 2 * (2 * TC_CHUNK_BYTES), 2 * TC_CHUNK_BYTES,
+                                        tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l], 1);
+                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l], p.act_plane[l], sbase + p.off_dzl,
+                                        2 * TC_CHUNK_BYTES, TC_NO, 0, dw_ksteps, dw_started);
+                        const TcView ones = tc_feat_mn(sbase + p.off_act[l] + 3 * p.act_plane[l]);
+                        const TcView dzl = tc_feat_mn(sbase + p.off_dzl);
+                        const uint32_t dzp16 = (2u * TC_CHUNK_BYTES) >> 4;
+                        uint32_t alo = ones.lo, blo = dzl.lo;
+#pragma unroll 1
+                        for (int k = 0; k < dw_ksteps; ++k) {    // rows 0-7 of the result: column sums of [dZ_1|dZ_0] (+ dZ_2)
+                            tc_mma(tm + p.col_rb, alo, ones.hi, blo + dzp16, dzl.hi, tc_idesc(64, 2 * TC_NO, 1, 1), (dw_started || k > 0) ? 1u : 0u);
+                            tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, TC_NO, 1, 1), 1u);
+                            alo += ones.k16;
+                            blo += dzl.k16;
+                        }
+                    } else {
+                        // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
+                        if (l > 0)
+                            tc_rows_product(tm + p.col_za, sbase + p.off_act[l + 1] + 2 * p.act_plane[l + 1], p.act_plane[l + 1],
+                                            tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l],
+                                            p.np[l] / 16);
+                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l + 1], p.act_plane[l + 1], sbase + p.off_act[l],
+                                        p.act_plane[l], p.kp[l], 8, dw_ksteps, dw_started);
+                    }
+                    tc_commit(mbar);
+                }
+                __syncwarp();
             }
             TC_MARK(12);
             if (l == 0) { pending = true; break; }
             tc_wait(mbar, parity); parity ^= 1;
             TC_MARK(13 + l);
-            // dZ_{l-1} = dA_l * act'(A_l), written over A_l
-            float a[32], g[32];
-            tc_ld32(tlane + p.col_z[l - 1] + half * 32, a);
-            tc_ld32(tlane + p.col_da[l] + half * 32, g);
-            const int act = p.net.act[l - 1];
+            // dZ_{l-1} = dA_l * act'(A_l), written over A_l (the fp32 A_l was saved in TMEM by the forward epilogue)
+            float a[16], g[16], g2[16];
+            tc_ld16(tlane + p.col_za + cg * 16, g);
+            tc_ld16(tlane + p.col_za + TC_HID + cg * 16, g2);
+            tc_ld16(tlane + p.col_save + (l - 1) * TC_HID + cg * 16, a);
             const float leak = p.net.leak[l - 1];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = mq_act_grad(a[j], g[j], act, leak);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                tc_store_chunk(smem + p.off_act[l], p.act_plane[l], half * 4 + c, row, g + 8 * c);
+            for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], g[j] + g2[j], HACT, leak);
+            tc_store_chunk(smem + p.off_act[l], p.act_plane[l], cg * 2, row, g);
+            tc_store_chunk(smem + p.off_act[l], p.act_plane[l], cg * 2 + 1, row, g + 8);
             tc_publish();
             TC_MARK(16 + l);
         }
@@ -507,37 +580,54 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
         if (!dw_started) {
             for (int j = tid; j < p.net.n_params; j += TC_NT) dst[j] = 0.0f;
-        } else if (warp < 4) {
-            // M = 64 accumulators: row i is lane i%16 of warp i/16
-            const int i = warp * 16 + lane;
+        } else {
+            // M = 64 accumulators: row i is lane i%16 of the warps of quarter i/16; the four warps of a quarter
+            // split the columns of a block
+            const int i = quarter * 16 + lane;
             const bool lv = lane < 16;
             for (int l = 0; l < L; ++l) {
                 const int in = p.net.in[l], on = p.net.out[l];
-                for (int c0 = 0; c0 < (l == 0 ? K0 : p.np[l]); c0 += 16) {
-                    float v[16];
-                    tc_ld16(tlane + p.col_dw[l] + c0, v);
+                const int nb = (l == L - 1) ? TC_NO : p.kp[l];          // columns per block
+                for (int c0 = cg * 16; c0 < nb; c0 += 64) {
+                    float v0[16], v1[16];
+                    tc_ld16(tlane + p.col_acc[l] + c0, v0);
+                    tc_ld16(tlane + p.col_acc[l] + nb + c0, v1);
                     if (!lv) continue;
-                    if (l == 0) {           // D[o][k] = dW_0[k][o]
+                    if (l < L - 1) {        // acc[o][k] = dW_l[k][o]
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (i < on && c0 + j < in) dst[p.net.w_off[0] + (c0 + j) * on + i] = v[j];
-                    } else {                // D[k][o]
+                            if (i < on && c0 + j < in) dst[p.net.w_off[l] + (c0 + j) * on + i] = v0[j] + v1[j];
+                    } else {                // acc[k][o]
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (i < in && c0 + j < on) dst[p.net.w_off[l] + i * on + c0 + j] = v[j];
+                            if (i < in && c0 + j < on) dst[p.net.w_off[l] + i * on + c0 + j] = v0[j] + v1[j];
                     }
                 }
-                float v[16];
-                tc_ld16(tlane + p.col_db[l], v);     // 8 identical columns (+ 8 unrelated ones)
-                if (lv && i < on) dst[p.net.b_off[l] + i] = v[0];
-                if (l == L - 1 && p.net.logstd_off >= 0 && lv && i >= 8 && i < 8 + n_out)
-                    dst[p.net.logstd_off + i - 8] = gauss ? v[0] : 0.0f;
+                if (l < L - 1 && cg == 1) {     // the ones column behind the two blocks
+                    float v[16];
+                    tc_ld16(tlane + p.col_acc[l] + 2 * nb - 8, v);
+                    if (lv && i < on) dst[p.net.b_off[l] + i] = v[8];
+                }
+            }
+            if (cg == 2 && quarter == 0) {      // last layer: row 0 of the ones product = column sums of dZ (two blocks)
+                float v0[16], v1[16];
+                tc_ld16(tlane + p.col_rb, v0);
+                tc_ld16(tlane + p.col_rb + TC_NO, v1);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float s = v0[j] + v1[j];
+                        if (j < n_out) dst[p.net.b_off[L - 1] + j] = s;
+                        if (p.net.logstd_off >= 0 && j >= 8 && j < 8 + n_out) dst[p.net.logstd_off + j - 8] = gauss ? s : 0.0f;
+                    }
+                }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     TC_MARK(20);
+    if (prof != nullptr && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); prof[65 + 2 * blockIdx.x] = (long long)gt; }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
 }
 
@@ -548,7 +638,10 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
     const int L = net->n_layers;
     if (L < 2 || L > TC_MAXL) return 0;
     if (net->n_in > 32 || net->n_out > TC_NO) return 0;
-    for (int l = 0; l + 1 < L; ++l) if (net->out[l] > TC_HID) return 0;
+    for (int l = 0; l + 1 < L; ++l) {
+        if (net->out[l] > TC_HID) return 0;
+        if (net->act[l] != net->act[0] || (net->act[l] != MQ_ACT_TANH && net->act[l] != MQ_ACT_LRELU)) return 0;
+    }
     const bool gauss = head && (head->kind == MQ_HEAD_GAUSS_LOGP || head->kind == MQ_HEAD_GAUSS_PPO);
     if ((gauss || net->logstd_off >= 0) && net->n_out > 8) return 0;
     p->L = L;
@@ -566,24 +659,27 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
     if (tr < 16) tr = 16;
     p->tile_rows = (int)tr;
     int off = 0;
-    p->off_dzl = off; off += TC_PLANES * (TC_NO / 8) * TC_CHUNK_BYTES;
+    p->off_dzl = off; off += 3 * 2 * TC_CHUNK_BYTES;
     for (int l = 0; l < L; ++l) {
         p->act_plane[l] = (p->kp[l] / 8) * TC_CHUNK_BYTES;
-        p->off_act[l] = off; off += TC_PLANES * p->act_plane[l];
+        p->off_act[l] = off; off += 3 * p->act_plane[l] + TC_CHUNK_BYTES;
     }
-    p->off_ones = off; off += TC_CHUNK_BYTES;
-    for (int l = 0; l < L; ++l) {
-        p->w_plane[l] = p->np[l] * p->kp[l] * 2;
-        p->off_w[l] = off; off += TC_PLANES * p->w_plane[l];
+    for (int l = 0; l < L; ++l) { p->off_wf[l] = off; off += 3 * p->np[l] * p->kp[l] * 2; }
+    for (int l = 1; l < L; ++l) {
+        p->wb_plane[l] = p->np[l] * p->kp[l] * 2;
+        p->off_wb[l] = off; off += 3 * p->wb_plane[l];
     }
     p->off_bias = off; off += TC_MAXL * 64 * 4;
     p->off_misc = off; off += 32 * 4;
+    // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] on: keep that in bounds
+    if (off < p->off_act[L - 1] + 3 * p->act_plane[L - 1] + 8 * TC_CHUNK_BYTES)
+        off = p->off_act[L - 1] + 3 * p->act_plane[L - 1] + 8 * TC_CHUNK_BYTES;
     p->smem_bytes = (int)mq_round_up(off, 16);
     int col = 0;
-    for (int l = 0; l < L; ++l) { p->col_z[l] = col; col += p->np[l]; }
-    for (int l = 1; l < L; ++l) { p->col_da[l] = col; col += TC_HID; }
-    for (int l = 0; l < L; ++l) { p->col_dw[l] = col; col += (l == 0 ? p->k0 : p->np[l]); }
-    for (int l = 0; l < L; ++l) { p->col_db[l] = col; col += 16; }
+    p->col_za = col; col += 2 * TC_HID;
+    p->col_save = col; col += (L - 1) * TC_HID;            // fp32 activations of the hidden layers
+    for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? 2 * TC_NO : 2 * p->kp[l] + 8; }
+    p->col_rb = col; col += 2 * TC_NO;
     if (col > 512) return 0;
     if (p->smem_bytes + 1024 > mq_smem_optin()) return 0;
     return 1;
@@ -609,18 +705,20 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
     if (with_grad)
         MQ_REQUIRE(ws && ws_bytes >= (int64_t)grid * net->n_params * (int64_t)sizeof(float), MQ_ERR_INVALID,
                    "mq_tc_launch: workspace too small");
-    cudaError_t e;
-    if (p.k0 == 16) {
-        e = cudaFuncSetAttribute(tc_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
-        if (e == cudaSuccess)
-            tc_grad_kernel<16><<<grid, TC_NT, p.smem_bytes, (cudaStream_t)stream>>>(p, theta, x, row_idx, batch, *head,
-                                                                                   (float *)ws, out, logp, mq_phase_prof_ptr());
-    } else {
-        e = cudaFuncSetAttribute(tc_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
-        if (e == cudaSuccess)
-            tc_grad_kernel<32><<<grid, TC_NT, p.smem_bytes, (cudaStream_t)stream>>>(p, theta, x, row_idx, batch, *head,
-                                                                                   (float *)ws, out, logp, mq_phase_prof_ptr());
-    }
+    cudaError_t e = cudaSuccess;
+#define TC_LAUNCH(K0_, ACT_)                                                                                             \
+    do {                                                                                                                 \
+        e = cudaFuncSetAttribute(tc_grad_kernel<K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
+        if (e == cudaSuccess)                                                                                            \
+            tc_grad_kernel<K0_, ACT_><<<grid, TC_NT, p.smem_bytes, (cudaStream_t)stream>>>(                             \
+                p, theta, x, row_idx, batch, *head, (float *)ws, out, logp, mq_phase_prof_ptr());                       \
+    } while (0)
+    const int hact = net->act[0];
+    if (p.k0 == 16 && hact == MQ_ACT_TANH) TC_LAUNCH(16, MQ_ACT_TANH);
+    else if (p.k0 == 16) TC_LAUNCH(16, MQ_ACT_LRELU);
+    else if (hact == MQ_ACT_TANH) TC_LAUNCH(32, MQ_ACT_TANH);
+    else TC_LAUNCH(32, MQ_ACT_LRELU);
+#undef TC_LAUNCH
     if (e != cudaSuccess) {
         mq_set_error("mq_tc_launch: %s", cudaGetErrorString(e));
         return MQ_ERR_CUDA;

@@ -580,7 +580,7 @@ def case_tc_paths(B):
     try:
         cases = [(11, [64, 64, 3], [1, 1, 0], 64), (11, [64, 64, 3], [1, 1, 0], 1000),
                  (11, [64, 64, 1], [1, 1, 0], 40000), (20, [16, 16, 5], [2, 2, 0], 777),
-                 (6, [32, 10], [2, 0], 333), (17, [64, 48, 6], [1, 2, 1], 2500)]
+                 (6, [32, 10], [2, 0], 333), (17, [64, 48, 6], [1, 2, 1], 2500), (20, [48, 7], [1, 0], 1500)]
         for n_in, widths, acts, batch in cases:
             spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
             net = net_of(spec)

@@ -62,17 +62,21 @@ int main() {
     const uint32_t CH = 2048, RG = 128;
     Case cs[] = {
         // name, a_lbo, a_sbo, a_k16, b_lbo, b_sbo, b_k16, a_mn, b_mn, m, n, ksteps, reps
-        {"fwd  K/K   M128 N64 (A 4K + B 2K)", CH, RG, 2 * CH / 16, 64 * 16, RG, 64 * 32 / 16, 0, 0, 128, 64, 4, 64},
-        {"fwd  K/K   M128 N16", CH, RG, 2 * CH / 16, 16 * 16, RG, 16 * 32 / 16, 0, 0, 128, 16, 4, 64},
-        {"fwd  K/K   M128 N128", CH, RG, 2 * CH / 16, 128 * 16, RG, 128 * 32 / 16, 0, 0, 128, 128, 4, 64},
-        {"fwd  K/K   M128 N256", CH, RG, 2 * CH / 16, 256 * 16, RG, 256 * 32 / 16, 0, 0, 128, 256, 4, 64},
+        {"fwd  K/K   M128 N128 (wf image)", CH, RG, 2 * CH / 16, 3 * 64 * 16, RG, 6 * 64 * 16 / 16, 0, 0, 128, 128, 4, 64},
+        {"fwd  K/K   M128 N64", CH, RG, 2 * CH / 16, 3 * 64 * 16, RG, 6 * 64 * 16 / 16, 0, 0, 128, 64, 4, 64},
+        {"fwd  K/K   M128 N32 (last)", CH, RG, 2 * CH / 16, 3 * 16 * 16, RG, 6 * 16 * 16 / 16, 0, 0, 128, 32, 4, 64},
+        {"fwd  K/K   M128 N16 (last)", CH, RG, 2 * CH / 16, 3 * 16 * 16, RG, 6 * 16 * 16 / 16, 0, 0, 128, 16, 4, 64},
+        {"dA   K/MN  M128 N128", CH, RG, 2 * CH / 16, RG, 64 * 16, 256 / 16, 0, 1, 128, 128, 4, 64},
         {"dA   K/MN  M128 N64", CH, RG, 2 * CH / 16, RG, 64 * 16, 256 / 16, 0, 1, 128, 64, 4, 64},
+        {"dW   MN/MN M64  N136", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 136, 8, 32},
+        {"dW   MN/MN M64  N72", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 72, 8, 32},
         {"dW   MN/MN M64  N64", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 64, 8, 32},
-        {"dW   MN/MN M128 N64", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 128, 64, 8, 32},
+        {"dW   MN/MN M64  N40", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 40, 8, 32},
+        {"dW   MN/MN M64  N32", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 32, 8, 32},
+        {"dW   MN/MN M64  N24", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 24, 8, 32},
         {"dW   MN/MN M64  N16", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 16, 8, 32},
-        {"db   MN/MN M64  N8", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 8, 8, 32},
-        {"dW   MN/MN M128 N128", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 128, 128, 8, 32},
-        {"dW   MN/MN M128 N256", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 128, 256, 8, 32},
+        {"dW   MN/MN M128 N136", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 128, 144, 8, 32},
+        {"dW   MN/MN M64  N200", RG, CH, 256 / 16, RG, CH, 256 / 16, 1, 1, 64, 200, 8, 32},
     };
     long long *d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -24,16 +24,21 @@ def run():
            C.byref(head), 1.0 / MB, D.ptr(upd.policy.grad), None, None, D.ptr(ws), wsb, D.stream())
 for _ in range(3): run()
 torch.cuda.synchronize()
-prof = torch.zeros(32, dtype=torch.int64, device="cuda")
+prof = torch.zeros(512, dtype=torch.int64, device="cuda")
 lib.mq_debug_set_phase_buffer(prof.data_ptr())
 run(); torch.cuda.synchronize()
 lib.mq_debug_set_phase_buffer(None)
 names = {0: "setup", 1: "wait_prev_tile", 2: "stage_x", 3: "issue_fwd", 4: "prefetch", 5: "wait_fwd0", 6: "wait_fwd1", 7: "wait_fwd2",
          8: "epi0", 9: "epi1", 11: "head", 12: "issue_bwd", 15: "wait_bwd2", 14: "wait_bwd1", 18: "epi_b2", 17: "epi_b1", 19: "wait_last", 20: "final"}
 p = prof.cpu().numpy()
-print("total cycles CTA0: %d (%.1f us at 1.965 GHz)" % (p.sum(), p.sum() / 1965.0))
+print("total cycles CTA0: %d (%.1f us at 1.965 GHz)" % (p[:32].sum(), p[:32].sum() / 1965.0))
 for i in range(32):
     if p[i]: print("  %-16s %8d" % (names.get(i, i), p[i]))
+g = p[64:64 + 2 * 148].reshape(148, 2)
+t0 = g[:, 0].min()
+print("CTA start offsets (us): min %.1f median %.1f max %.1f;  CTA end offsets: min %.1f median %.1f max %.1f;  durations: min %.1f median %.1f max %.1f" % (
+    0, np.median(g[:, 0] - t0) / 1e3, (g[:, 0] - t0).max() / 1e3, (g[:, 1] - t0).min() / 1e3, np.median(g[:, 1] - t0) / 1e3, (g[:, 1] - t0).max() / 1e3,
+    (g[:, 1] - g[:, 0]).min() / 1e3, np.median(g[:, 1] - g[:, 0]) / 1e3, (g[:, 1] - g[:, 0]).max() / 1e3))
 ts = []
 for k in range(10):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
