@@ -277,14 +277,30 @@ class PPOLargeWorkload(object):
         ms = float(np.median(times[2:]))
         bytes_per_launch = self.MB * 64                    # 64 B gathered per minibatch row
         flops = self.MB * 28544.0                          # 28,544 FLOP per row (fwd+dW+dX)
-        ach = bytes_per_launch / (ms * 1e-3) / 1e9
+        # tensor-core work actually issued: six bf16 plane pairs per fp32 product, operands padded
+        # to 16/64 columns, M = 128 rows per tile of `tile_rows` valid rows
+        sms = 148
+        waves = -(-self.MB // (sms * 128))
+        tile_rows = min(128, -(-(-(-self.MB // (sms * waves))) // 16) * 16)
+        tiles = -(-self.MB // tile_rows)
+        ks = tile_rows // 16
+        rows_pair = 2 * 16 * 128 * (128 + 128 + 64 + 64)          # one K step of a row-major product (hidden width 64)
+        per_tile = rows_pair * (1 + 4 + 1 + 4) + 2 * 16 * 128 * 96 * 4 \
+            + ks * 2 * 16 * 64 * ((32 + 32 + 16 + 16) + (32 + 16) + (136 + 136 + 72 + 64) + (40 + 40 + 24 + 16))
+        executed = tiles * float(per_tile)
+        tf = flops / (ms * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        return dict(bound="hbm", kernel="fused_grad_kernel (policy, 65536 rows; launch includes fused_reduce_kernel)",
-                    achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
+        return dict(bound="tensor", kernel="tc_grad_kernel<16,tanh> (policy, 65536 rows, tcgen05 bf16x3 planes; "
+                                           "launch includes fused_reduce_kernel)",
+                    achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None,
                     peak_source=peaks["source"], ms_per_launch=ms,
-                    limiter="fp32 FFMA pipe: 446 FLOP per algorithmic byte, far above the fp32 ridge (~11)",
-                    fp32_tflops=flops / (ms * 1e-3) / 1e12, fp32_peak_tflops_nominal=fp32_peak,
-                    fp32_frac=flops / (ms * 1e-3) / 1e12 / fp32_peak)
+                    limiter="fp32-exact products = 6 bf16 plane pairs with K = 16..64: the tensor pipe is fed at the "
+                            "shared-memory operand rate (measured 128 B/cycle/SM) and waits on the per-layer epilogues; "
+                            "neither HBM (64 B/row) nor the dense bf16 peak is the bound",
+                    executed_tensor_tflops=executed / (ms * 1e-3) / 1e12,
+                    executed_tensor_frac=executed / (ms * 1e-3) / 1e12 / peaks["bf16"],
+                    hbm_gbs=bytes_per_launch / (ms * 1e-3) / 1e9,
+                    fp32_frac_of_ffma_peak=tf / fp32_peak, fp32_peak_tflops_nominal=fp32_peak)
 
     # CPU arm: the same per-transition work on a bounded sample
     SAMPLE_N = 65536
@@ -668,7 +684,10 @@ def main():
                     vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=wl.name,
                                 l2="flushed (256 MB write) between timed steps; per-step inputs exceed L2",
-                                adam_state="f32", parallelism=PARALLELISM[args.workload] % ((world, world) if
+                                adam_state="f32",
+                                arithmetic="fp32 results (parity rtol 1e-5): large-batch Affine products run on tcgen05 as "
+                                           "3 exact bf16 planes per operand, fp32 accumulation in TMEM; the rest is fp32 FFMA",
+                                parallelism=PARALLELISM[args.workload] % ((world, world) if
                                 args.workload == "ppo_large" else (world,)) if world > 1 else "single GPU"),
                     e2e=dict(value=units / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=wl.h2d,
                              d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps),
