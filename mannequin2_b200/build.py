@@ -18,6 +18,8 @@ BUILD = os.path.join(CSRC, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+if os.environ.get("MQ_TC_PROFILE"):          # developer aid: per-phase cycle counters in the tcgen05 kernel (tools/tc_phases.py)
+    FLAGS.append("-DMQ_TC_PROFILE")
 
 
 def sources():

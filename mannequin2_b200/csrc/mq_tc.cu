@@ -47,6 +47,7 @@
 #define TC_NO 16                 // padded output width
 #define TC_CHUNK_BYTES 2048      // one 8-feature chunk of all 128 rows (128 rows x 16 B)
 #define TC_MAXL 3
+#define TC_HIN 20                // floats of head input per tile row: 16 targets, weight / advantage, old log-prob
 
 struct TcPlan {
     mq_net_t net;
@@ -54,10 +55,11 @@ struct TcPlan {
     int k0;                      // padded input width (16 or 32)
     int kp[TC_MAXL], np[TC_MAXL];
     int tile_rows;               // rows per tile, multiple of 16, <= 128
+    int x_step_q, x_step_r, h_step_q, h_step_r;   // TC_NT / n_in, TC_NT % n_in, TC_NT / n_out, TC_NT % n_out
     int with_grad;
     // shared-memory byte offsets.  act[l]: planes 2,1,0 then the ones chunk; dzl: planes 2,1,0
     int off_dzl, off_act[TC_MAXL], act_plane[TC_MAXL], off_wf[TC_MAXL], off_wb[TC_MAXL], wb_plane[TC_MAXL];
-    int off_bias, off_misc;
+    int off_bias, off_misc, off_hin, off_idx;
     int smem_bytes;
     // TMEM columns
     int col_za, col_save, col_acc[TC_MAXL], col_rb;
@@ -138,6 +140,19 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const float *v) {
           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Gather loads that must be ISSUED where they are written (volatile: ptxas would otherwise sink them next to their
+// first use, one epilogue later, and expose the full HBM latency there).
+__device__ __forceinline__ float tc_ldg_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int tc_ldg_s32(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 // ---- exact three-way bf16 split -------------------------------------------------------------
@@ -278,12 +293,17 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     __shared__ __align__(8) uint64_t s_mbar;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler too
-    // developer aid: per-phase cycles of CTA 0 (prof is NULL in normal use)
+    // developer aid (compile with -DMQ_TC_PROFILE): per-phase cycles of CTA 0 and every CTA's start / end time
+#ifdef MQ_TC_PROFILE
     long long t_last = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
     if (profiling) t_last = clock64();
     if (prof != nullptr && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); prof[64 + 2 * blockIdx.x] = (long long)gt; }
 #define TC_MARK(i) do { if (profiling) { long long now_ = clock64(); prof[i] += now_ - t_last; t_last = now_; } } while (0)
+#else
+    (void)prof;
+#define TC_MARK(i) do { } while (0)
+#endif
     const int L = p.L;
     const int n_in = p.net.n_in, n_out = p.net.n_out;
     constexpr int XCHUNKS = K0 / 8;
@@ -297,8 +317,12 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_mbar)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    for (int i = tid; i < p.smem_bytes / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    TC_MARK(21);
+    // clear shared memory except the hidden activation buffers (every tile rewrites all of their rows)
+    for (int i = tid; i < p.off_act[1] / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = p.off_wf[0] / 16 + tid; i < p.smem_bytes / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    TC_MARK(22);
     {
         __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
         const uint32_t ob = *reinterpret_cast<uint16_t *>(&one);
@@ -309,47 +333,52 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     }
     float *sBias = reinterpret_cast<float *>(smem + p.off_bias);      // [L][64]
     float *sMisc = reinterpret_cast<float *>(smem + p.off_misc);      // logstd[16], exp(-logstd)[16]
-    for (int l = 0; l < L; ++l) {
-        const int in = p.net.in[l], on = p.net.out[l], np = p.np[l];
-        const float *w = theta + p.net.w_off[l];
-        const int total = in * on;
-#pragma unroll 4
-        for (int e = tid; e < total; e += TC_NT) {
-            const int k = e / on, n = e - k * on;
-            uint32_t w0, w1, w2;
-            tc_split_pair(__ldg(w + e), 0.0f, w0, w1, w2);
-            // forward image [k chunk][plane][n][8 k]
-            unsigned char *df = smem + p.off_wf[l] + (k >> 3) * (3 * np * 16) + n * 16 + (k & 7) * 2;
-            *reinterpret_cast<uint16_t *>(df) = (uint16_t)(w0 & 0xFFFFu);
-            *reinterpret_cast<uint16_t *>(df + np * 16) = (uint16_t)(w1 & 0xFFFFu);
-            *reinterpret_cast<uint16_t *>(df + 2 * np * 16) = (uint16_t)(w2 & 0xFFFFu);
-            if (l > 0 && p.with_grad) {      // backward image [plane][k chunk][n][8 k]
-                unsigned char *db = smem + p.off_wb[l] + (k >> 3) * (np * 16) + n * 16 + (k & 7) * 2;
-                *reinterpret_cast<uint16_t *>(db) = (uint16_t)(w0 & 0xFFFFu);
-                *reinterpret_cast<uint16_t *>(db + p.wb_plane[l]) = (uint16_t)(w1 & 0xFFFFu);
-                *reinterpret_cast<uint16_t *>(db + 2 * p.wb_plane[l]) = (uint16_t)(w2 & 0xFFFFu);
+    float *sHin = reinterpret_cast<float *>(smem + p.off_hin);        // head inputs of the tile: [128][TC_HIN]
+    int *sIdx = reinterpret_cast<int *>(smem + p.off_idx);            // source rows of three consecutive tiles: [3][128]
+    TC_MARK(23);
+    // weight images: one work item = 8 consecutive inputs (one 16-byte chunk) of one output column
+    {
+        int items[TC_MAXL + 1];
+        items[0] = 0;
+        for (int l = 0; l < L; ++l) items[l + 1] = items[l] + (p.kp[l] / 8) * p.net.out[l];
+#pragma unroll 2
+        for (int it = tid; it < items[L]; it += TC_NT) {
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < TC_MAXL; ++q) if (q < L && it >= items[q]) l = q;
+            const int on = p.net.out[l], np = p.np[l], in = p.net.in[l];
+            const int local = it - items[l];
+            const int kc = local / on, n = local - kc * on;
+            const float *w = theta + p.net.w_off[l] + (kc * 8) * on + n;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (kc * 8 + j < in) ? __ldg(w + j * on) : 0.0f;
+            uint32_t q[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tc_split_pair(v[2 * j], v[2 * j + 1], q[0][j], q[1][j], q[2][j]);
+            unsigned char *df = smem + p.off_wf[l] + kc * (3 * np * 16) + n * 16;          // [k chunk][plane][n][8 k]
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+                *reinterpret_cast<uint4 *>(df + pl * np * 16) = make_uint4(q[pl][0], q[pl][1], q[pl][2], q[pl][3]);
+            if (l > 0 && p.with_grad) {
+                unsigned char *db = smem + p.off_wb[l] + kc * (np * 16) + n * 16;           // [plane][k chunk][n][8 k]
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+                    *reinterpret_cast<uint4 *>(db + pl * p.wb_plane[l]) = make_uint4(q[pl][0], q[pl][1], q[pl][2], q[pl][3]);
             }
         }
-        for (int n = tid; n < on; n += TC_NT) sBias[l * 64 + n] = theta[p.net.b_off[l] + n];
+        for (int l = 0; l < L; ++l)
+            for (int n = tid; n < p.net.out[l]; n += TC_NT) sBias[l * 64 + n] = __ldg(theta + p.net.b_off[l] + n);
+        if (p.net.logstd_off >= 0 && tid < n_out) {
+            const float ls = __ldg(theta + p.net.logstd_off + tid);
+            sMisc[tid] = ls;
+            sMisc[16 + tid] = expf(-ls);
+        }
     }
-    if (p.net.logstd_off >= 0 && tid < n_out) {
-        const float ls = theta[p.net.logstd_off + tid];
-        sMisc[tid] = ls;
-        sMisc[16 + tid] = expf(-ls);
-    }
-    tc_publish();
-    TC_MARK(0);
-    const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
-    const uint32_t mbar = tc_smem_u32(&s_mbar);
-    const uint32_t sbase = tc_smem_u32(smem);
-    uint32_t parity = 0;
-    bool pending = false;                               // a committed MMA batch nobody waited for yet
-    bool dw_started = false;                            // dW / db accumulators hold data
-
+    TC_MARK(24);
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
     const int cg = warp >> 2;                           // which 16 of the 64 columns this thread owns
     const int row = quarter * 32 + lane;                // TMEM lane == batch row of the tile
-    const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
     const int tr = p.tile_rows;
     const int64_t ntiles = (n_rows + tr - 1) / tr;
     const int dw_ksteps = tr / 16;
@@ -357,44 +386,118 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     const int lastact = p.net.act[L - 1];
     const float lastleak = p.net.leak[L - 1];
 
-    // input-tile staging: thread t < 128 * XCHUNKS owns (row = t & 127, chunk = t >> 7); the row index of the NEXT
-    // tile is fetched one tile ahead of its features so that the gather never waits on the index
-    const int xrow = tid & 127, xchunk = tid >> 7;
-    const bool xthread = xchunk < XCHUNKS;
-    float xr[8];
-    int64_t xsrc_next = -1;
-    auto load_src = [&](int64_t tile) -> int64_t {
-        const int64_t gr = tile * tr + xrow;
-        if (!(xrow < tr && gr < n_rows && tile < ntiles)) return -1;
-        return idx ? (int64_t)__ldg(idx + gr) : gr;
-    };
-    auto load_x = [&](int64_t src) {
+    // ---- gathers.  Lanes run along the FEATURES of a row (a warp-wide load touches ~3 rows, not 32), the source
+    // row of every tile row is staged in shared memory two tiles ahead, the features of the next tile wait in
+    // registers until the MMAs reading the current input tile are done.
+    constexpr int XE = K0 / 4;                          // elements of the 128 x n_in input tile per thread
+    constexpr int HE = TC_NO * TC_ROWS / TC_NT;         // elements of the 128 x n_out target tile per thread
+    float xr[XE];
+    int xrf[XE], hrf[HE];                               // (row << 8 | feature) of this thread's elements, -1: none
+    {
+        int r = tid / n_in, f = tid - r * n_in;
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            const int col = xchunk * 8 + f;
-            xr[f] = (src >= 0 && col < n_in) ? __ldg(x + src * n_in + col) : 0.0f;
+        for (int j = 0; j < XE; ++j) {                  // e = tid + j * TC_NT, stepped without divisions
+            xrf[j] = r < TC_ROWS ? ((r << 8) | f) : -1;
+            r += p.x_step_q; f += p.x_step_r;
+            if (f >= n_in) { f -= n_in; ++r; }
+        }
+        r = tid / n_out; f = tid - r * n_out;
+#pragma unroll
+        for (int j = 0; j < HE; ++j) {
+            hrf[j] = r < TC_ROWS ? ((r << 8) | f) : -1;
+            r += p.h_step_q; f += p.h_step_r;
+            if (f >= n_out) { f -= n_out; ++r; }
+        }
+    }
+    // gathered values are only LOADED while the first products run and are written to shared memory one epilogue later,
+    // so that nobody waits for HBM
+    int pend_idx = -1;
+    float pend_t[TC_NO * TC_ROWS / TC_NT], pend_a = 0.0f, pend_l = 0.0f;
+    (void)0;
+    auto fetch_idx = [&](int64_t tile) {                // threads 0..127: source row (or -1) of every row of `tile`
+        pend_idx = -1;
+        if (tid < TC_ROWS) {
+            const int64_t gr = tile * tr + tid;
+            if (tile < ntiles && tid < tr && gr < n_rows) pend_idx = idx ? tc_ldg_s32(idx + gr) : (int)gr;
         }
     };
-    if (xthread) {
-        load_x(load_src(blockIdx.x));
-        xsrc_next = load_src((int64_t)blockIdx.x + gridDim.x);
-    }
+    auto commit_idx = [&](int slot) { if (tid < TC_ROWS) sIdx[slot * TC_ROWS + tid] = pend_idx; };
+    auto load_x = [&](int slot) {
+#pragma unroll
+        for (int j = 0; j < XE; ++j) {
+            float v = 0.0f;
+            if (xrf[j] >= 0) {
+                const int src = sIdx[slot * TC_ROWS + (xrf[j] >> 8)];
+                if (src >= 0) v = tc_ldg_f32(x + (int64_t)src * n_in + (xrf[j] & 255));
+            }
+            xr[j] = v;
+        }
+    };
+    auto store_x = [&]() {
+#pragma unroll
+        for (int j = 0; j < XE; ++j) {
+            if (xrf[j] < 0) continue;
+            const int r = xrf[j] >> 8, f = xrf[j] & 255;
+            uint32_t w0, w1, w2;
+            tc_split_pair(xr[j], 0.0f, w0, w1, w2);
+            unsigned char *d = tc_chunk_ptr(smem + p.off_act[0], p.act_plane[0], f >> 3, r) + (f & 7) * 2;
+            *reinterpret_cast<uint16_t *>(d) = (uint16_t)(w0 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(d - p.act_plane[0]) = (uint16_t)(w1 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(d - 2 * p.act_plane[0]) = (uint16_t)(w2 & 0xFFFFu);
+        }
+    };
+    auto fetch_head_inputs = [&](int slot) {            // this tile's targets / weights
+        const float *mat = (head.kind == MQ_HEAD_DY) ? head.dy : head.target;
+#pragma unroll
+        for (int j = 0; j < HE; ++j) {
+            float v = 0.0f;
+            if (mat && hrf[j] >= 0) {
+                const int src = sIdx[slot * TC_ROWS + (hrf[j] >> 8)];
+                if (src >= 0) v = tc_ldg_f32(mat + (int64_t)src * n_out + (hrf[j] & 255));
+            }
+            pend_t[j] = v;
+        }
+        pend_a = 0.0f; pend_l = 0.0f;
+        if (gauss && tid < TC_ROWS) {
+            const int src = sIdx[slot * TC_ROWS + tid];
+            if (src >= 0) {
+                if (head.kind == MQ_HEAD_GAUSS_PPO) { pend_a = tc_ldg_f32(head.adv + src); pend_l = tc_ldg_f32(head.logp_old + src); }
+                else if (head.dy) pend_a = tc_ldg_f32(head.dy + src);
+            }
+        }
+    };
+    auto commit_head_inputs = [&]() {
+#pragma unroll
+        for (int j = 0; j < HE; ++j)
+            if (hrf[j] >= 0) sHin[(hrf[j] >> 8) * TC_HIN + (hrf[j] & 255)] = pend_t[j];
+        if (gauss && tid < TC_ROWS) { sHin[tid * TC_HIN + 16] = pend_a; sHin[tid * TC_HIN + 17] = pend_l; }
+    };
+    TC_MARK(25);
+    fetch_idx(blockIdx.x); commit_idx(0);
+    fetch_idx((int64_t)blockIdx.x + gridDim.x); commit_idx(1);
+    tc_publish();
+    TC_MARK(0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
+    const uint32_t mbar = tc_smem_u32(&s_mbar);
+    const uint32_t sbase = tc_smem_u32(smem);
+    const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
+    uint32_t parity = 0;
+    bool pending = false;                               // a committed MMA batch nobody waited for yet
+    bool dw_started = false;                            // dW / db accumulators hold data
+    load_x(0);
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int ord = 0;                                        // ordinal of the tile within this CTA
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ord) {
         const int64_t row0 = tile * tr;
         const int64_t gr = row0 + row;
         const bool rvalid = row < tr && gr < n_rows;
-        int64_t hsrc = 0;
-        if (cg == 0 && rvalid) hsrc = idx ? (int64_t)__ldg(idx + gr) : gr;
         if (pending) { tc_wait(mbar, parity); parity ^= 1; pending = false; }
         TC_MARK(1);
         // ---- stage the input tile ---------------------------------------------------------------
-        if (xthread) tc_store_chunk(smem + p.off_act[0], p.act_plane[0], xchunk, xrow, xr);
+        store_x();
         tc_publish();
         TC_MARK(2);
         // ---- forward ------------------------------------------------------------------------------
-        float tgt[TC_NO];                               // head inputs, fetched while the MMAs run
-        float h_adv = 0.0f, h_lpold = 0.0f;
         for (int l = 0; l < L; ++l) {
             if (warp == 0) {
                 if (tc_elect_one()) {
@@ -406,22 +509,11 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
             }
             TC_MARK(3);
             if (l == 0) {
-                // overlap global loads with the first products: next tile's rows, this tile's head inputs
-                if (xthread) {
-                    load_x(xsrc_next);
-                    xsrc_next = load_src(tile + 2 * (int64_t)gridDim.x);
-                }
-                if (cg == 0) {
-                    const float *mat = (head.kind == MQ_HEAD_DY) ? head.dy : head.target;
-#pragma unroll
-                    for (int n = 0; n < TC_NO; ++n) tgt[n] = (rvalid && n < n_out && mat) ? __ldg(mat + hsrc * n_out + n) : 0.0f;
-                    if (head.kind == MQ_HEAD_GAUSS_PPO) {
-                        h_adv = rvalid ? __ldg(head.adv + hsrc) : 0.0f;
-                        h_lpold = rvalid ? __ldg(head.logp_old + hsrc) : 0.0f;
-                    } else if (head.kind == MQ_HEAD_GAUSS_LOGP) {
-                        h_adv = (rvalid && head.dy) ? __ldg(head.dy + hsrc) : 0.0f;
-                    }
-                }
+                // overlap the gathers with the first products: this tile's head inputs, the next tile's rows, and the
+                // source rows of the tile after that
+                fetch_head_inputs(ord % 3);
+                load_x((ord + 1) % 3);
+                fetch_idx(tile + 2 * (int64_t)gridDim.x);
             }
             TC_MARK(4);
             tc_wait(mbar, parity); parity ^= 1;
@@ -445,22 +537,37 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 if (p.with_grad) tc_st16(tlane + p.col_save + l * TC_HID + cg * 16, v);
                 tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2, row, v);
                 tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2 + 1, row, v + 8);
+                if (l == 0) { commit_head_inputs(); commit_idx((ord + 2) % 3); }
                 tc_publish();
                 TC_MARK(8 + l);
             }
         }
-        // ---- head: loss-gradient rule on the output row (one thread per row, warps 0-3) ------------
-        if (cg == 0) {
-            float y[TC_NO], y2[TC_NO], dz[TC_NO];
-            tc_ld16(tlane + p.col_za, y);
-            tc_ld16(tlane + p.col_za + TC_NO, y2);
-            const float *b = sBias + (L - 1) * 64;
+        // ---- head: loss-gradient rule on the output row.  All four threads of a row evaluate it (inputs come from
+        // shared memory) and each splits / stores its own 4 of the 16 dZ columns.
+        {
+            float y[TC_NO], dz[TC_NO];
+            {
+                float y2[TC_NO];
+                tc_ld16(tlane + p.col_za, y);
+                tc_ld16(tlane + p.col_za + TC_NO, y2);
+                const float *b = sBias + (L - 1) * 64;
 #pragma unroll
-            for (int n = 0; n < TC_NO; ++n) {
-                y[n] = (n < n_out) ? mq_act_apply((y[n] + y2[n]) + b[n], lastact, lastleak) : 0.0f;
-                dz[n] = 0.0f;
+                for (int n = 0; n < TC_NO; ++n) {
+                    y[n] = (n < n_out) ? mq_act_apply((y[n] + y2[n]) + b[n], lastact, lastleak) : 0.0f;
+                    dz[n] = 0.0f;
+                }
             }
-            if (rvalid && out) {
+            float tgt[TC_NO];
+            {
+                const float4 *h4 = reinterpret_cast<const float4 *>(sHin + row * TC_HIN);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = h4[q];
+                    tgt[4 * q] = t.x; tgt[4 * q + 1] = t.y; tgt[4 * q + 2] = t.z; tgt[4 * q + 3] = t.w;
+                }
+            }
+            const float h_adv = sHin[row * TC_HIN + 16], h_lpold = sHin[row * TC_HIN + 17];
+            if (rvalid && out && cg == 1) {
 #pragma unroll
                 for (int n = 0; n < TC_NO; ++n) if (n < n_out) out[gr * n_out + n] = y[n];
             }
@@ -492,7 +599,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                             acc += sMisc[a] + 0.5f * z * z;
                         }
                     const float lp = -(float)n_out * HALF_LOG_2PI - acc;
-                    if (logp_out) logp_out[gr] = lp;
+                    if (logp_out && cg == 2) logp_out[gr] = lp;
                     float w;
                     if (head.kind == MQ_HEAD_GAUSS_PPO) {
                         const float ratio = expf(lp - h_lpold);
@@ -512,8 +619,17 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 }
             }
             if (p.with_grad) {
-                tc_store_chunk(smem + p.off_dzl, 2 * TC_CHUNK_BYTES, 0, row, dz);
-                tc_store_chunk(smem + p.off_dzl, 2 * TC_CHUNK_BYTES, 1, row, dz + 8);
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (cg == q) { s0 = dz[4 * q]; s1 = dz[4 * q + 1]; s2 = dz[4 * q + 2]; s3 = dz[4 * q + 3]; }
+                uint32_t a0, a1, a2, b0, b1, b2;
+                tc_split_pair(s0, s1, a0, a1, a2);
+                tc_split_pair(s2, s3, b0, b1, b2);
+                unsigned char *d = tc_chunk_ptr(smem + p.off_dzl, 2 * TC_CHUNK_BYTES, cg >> 1, row) + (cg & 1) * 8;
+                *reinterpret_cast<uint2 *>(d) = make_uint2(a0, b0);
+                *reinterpret_cast<uint2 *>(d - 2 * TC_CHUNK_BYTES) = make_uint2(a1, b1);
+                *reinterpret_cast<uint2 *>(d - 4 * TC_CHUNK_BYTES) = make_uint2(a2, b2);
             }
         }
         tc_publish();
@@ -627,7 +743,9 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     TC_MARK(20);
+#ifdef MQ_TC_PROFILE
     if (prof != nullptr && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); prof[65 + 2 * blockIdx.x] = (long long)gt; }
+#endif
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
 }
 
@@ -658,6 +776,8 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
     if (tr > TC_ROWS) tr = TC_ROWS;
     if (tr < 16) tr = 16;
     p->tile_rows = (int)tr;
+    p->x_step_q = TC_NT / net->n_in; p->x_step_r = TC_NT % net->n_in;
+    p->h_step_q = TC_NT / net->n_out; p->h_step_r = TC_NT % net->n_out;
     int off = 0;
     p->off_dzl = off; off += 3 * 2 * TC_CHUNK_BYTES;
     for (int l = 0; l < L; ++l) {
@@ -671,6 +791,8 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
     }
     p->off_bias = off; off += TC_MAXL * 64 * 4;
     p->off_misc = off; off += 32 * 4;
+    p->off_hin = off; off += TC_ROWS * TC_HIN * 4;
+    p->off_idx = off; off += 3 * TC_ROWS * 4;
     // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] on: keep that in bounds
     if (off < p->off_act[L - 1] + 3 * p->act_plane[L - 1] + 8 * TC_CHUNK_BYTES)
         off = p->off_act[L - 1] + 3 * p->act_plane[L - 1] + 8 * TC_CHUNK_BYTES;

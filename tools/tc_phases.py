@@ -29,7 +29,7 @@ lib.mq_debug_set_phase_buffer(prof.data_ptr())
 run(); torch.cuda.synchronize()
 lib.mq_debug_set_phase_buffer(None)
 names = {0: "setup", 1: "wait_prev_tile", 2: "stage_x", 3: "issue_fwd", 4: "prefetch", 5: "wait_fwd0", 6: "wait_fwd1", 7: "wait_fwd2",
-         8: "epi0", 9: "epi1", 11: "head", 12: "issue_bwd", 15: "wait_bwd2", 14: "wait_bwd1", 18: "epi_b2", 17: "epi_b1", 19: "wait_last", 20: "final"}
+         8: "epi0", 9: "epi1", 11: "head", 12: "issue_bwd", 15: "wait_bwd2", 14: "wait_bwd1", 18: "epi_b2", 17: "epi_b1", 19: "wait_last", 20: "final", 21: "setup:alloc", 22: "setup:zero", 23: "setup:ones", 24: "setup:images", 25: "setup:coords"}
 p = prof.cpu().numpy()
 print("total cycles CTA0: %d (%.1f us at 1.965 GHz)" % (p[:32].sum(), p[:32].sum() / 1965.0))
 for i in range(32):
