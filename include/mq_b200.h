@@ -157,6 +157,30 @@ int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x, co
 int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                   int64_t batch, const mq_head_t *head, float scale, float *grad, float *out,
                   float *logp, void *ws, int64_t ws_bytes, void *stream);
+/* Same, but stops before the cross-CTA sum: ws receives n_parts UNSCALED partial gradients, [n_parts][n_params]
+ * (n_parts = CTAs of the gradient kernel), to be consumed by mq_reduce_step. */
+int mq_fused_grad_partials(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                           int64_t batch, const mq_head_t *head, float *out, float *logp, void *ws,
+                           int64_t ws_bytes, int32_t *n_parts_out, void *stream);
+
+/* Peer-memory descriptor of the in-kernel all-reduce (one exchange of the flat gradient per
+ * optimiser step).  grad_bufs / flag_bufs are DEVICE arrays of `world` pointers: rank r's exchange buffer
+ * (float[2][buf_stride]) and flag pad (uint32[2][world][mq_step_blocks(n)], zero-initialised), each mapped into
+ * this process (symmetric memory).  step must be non-zero and increase by one per call on every rank. */
+typedef struct mq_peer {
+    int32_t rank, world;
+    float *const *grad_bufs;
+    uint32_t *const *flag_bufs;
+    int64_t buf_stride;
+    uint32_t step;
+} mq_peer_t;
+int64_t mq_step_blocks(int64_t n);
+/* One launch: g = scale * sum_k partials[k] (fixed order) [-> sum over ranks through peer memory, rank order]
+ * -> Adam / Adams step (mannequin/_adam.py:23-53) -> theta_out (float32 model copy, nullable), grad_out (nullable).
+ * peer == NULL or world 1: single GPU. */
+int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m, void *v,
+                   float *theta_out, float *grad_out, int state_dtype, double c1, double c2, double lr,
+                   double eps, int adams, const mq_peer_t *peer, void *stream);
 /* n_steps dependent {gather, forward, head, backward, Adam} steps in ONE launch
  * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73).  idx_table[n_steps,mb].
  * Adam state (value,m,v: state_dtype) and theta are updated in place; tw[2]

@@ -30,9 +30,16 @@ class MqHead(ctypes.Structure):
                 ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p)]
 
 
+class MqPeer(ctypes.Structure):
+    """mq_peer_t: peer-memory descriptor of the in-kernel gradient all-reduce."""
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("grad_bufs", c_void_p), ("flag_bufs", c_void_p),
+                ("buf_stride", c_int64), ("step", ctypes.c_uint32)]
+
+
 P = c_void_p
 NETP = POINTER(MqNet)
 HEADP = POINTER(MqHead)
+PEERP = POINTER(MqPeer)
 
 SIGNATURES = {
     "mq_last_error": (c_char_p, []),
@@ -63,6 +70,10 @@ SIGNATURES = {
     "mq_fused_ws_bytes": (c_int64, [NETP, c_int64]),
     "mq_fused_forward": (c_int, [NETP, P, P, P, c_int64, P, P, P, P]),
     "mq_fused_grad": (c_int, [NETP, P, P, P, c_int64, HEADP, c_float, P, P, P, P, c_int64, P]),
+    "mq_fused_grad_partials": (c_int, [NETP, P, P, P, c_int64, HEADP, P, P, P, c_int64, POINTER(c_int32), P]),
+    "mq_step_blocks": (c_int64, [c_int64]),
+    "mq_reduce_step": (c_int, [P, c_int32, c_int64, c_float, P, P, P, P, P, c_int, c_double, c_double, c_double,
+                               c_double, c_int, PEERP, P]),
     "mq_fused_train": (c_int, [NETP, P, P, P, P, c_int, P, HEADP, P, c_int32, c_int32, c_double,
                                c_double, POINTER(c_double), c_double, c_double, P]),
     "mq_es_eval": (c_int, [NETP, P, P, c_int64, P, c_int64, P, P, P]),

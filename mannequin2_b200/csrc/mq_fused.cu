@@ -906,7 +906,7 @@ static int64_t fused_grid(int64_t ntiles, int64_t smem_bytes) {
 
 extern "C" int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch) {
     (void)batch;
-    return 2 * (int64_t)mq_sm_count() * net->n_params * (int64_t)sizeof(float) + 256;
+    return (2 * (int64_t)mq_sm_count() + 1) * (net->n_params + 64) * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x,
@@ -993,6 +993,28 @@ extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const floa
     }
     MQ_CHECK_LAUNCH("mq_fused_grad");
     return MQ_OK;
+}
+
+extern "C" int mq_fused_grad_partials(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                                      int64_t batch, const mq_head_t *head, float *out, float *logp, void *ws,
+                                      int64_t ws_bytes, int32_t *n_parts_out, void *stream) {
+    int rc = fused_net_check(net, "mq_fused_grad_partials");
+    if (rc != MQ_OK) return rc;
+    rc = head_check(net, head, "mq_fused_grad_partials");
+    if (rc != MQ_OK) return rc;
+    MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_fused_grad_partials: empty batch");
+    MQ_REQUIRE(theta && x && ws && n_parts_out, MQ_ERR_INVALID, "mq_fused_grad_partials: null pointer");
+    int tgrid = 0;
+    rc = mq_tc_launch(net, theta, x, row_idx, batch, head, 1, out, logp, ws, ws_bytes, &tgrid, stream);
+    if (rc == MQ_OK) { *n_parts_out = tgrid; return MQ_OK; }
+    if (rc != MQ_ERR_UNSUPPORTED) return rc;
+    // other kernels: one already summed, unscaled vector at the head of the workspace
+    const int64_t head_bytes = mq_round_up((int64_t)net->n_params * (int64_t)sizeof(float), 256);
+    MQ_REQUIRE(ws_bytes > head_bytes, MQ_ERR_INVALID, "mq_fused_grad_partials: workspace too small");
+    rc = mq_fused_grad(net, theta, x, row_idx, batch, head, 1.0f, (float *)ws, out, logp, (char *)ws + head_bytes,
+                       ws_bytes - head_bytes, stream);
+    if (rc == MQ_OK) *n_parts_out = 1;
+    return rc;
 }
 
 extern "C" int mq_fused_train(const mq_net_t *net, float *theta, void *value, void *m, void *v,

@@ -1,0 +1,141 @@
+// One optimiser step after the gradient kernel, in ONE launch:
+//   fixed-order sum of the per-CTA partial gradients  ->  (multi-GPU) all-reduce over NVLink peer memory
+//   ->  two-moment (Adam) update  ->  float32 model copy.
+//
+// Replaces mannequin/_adam.py:23-53 + mannequin/_normalize.py:9-25 (one apply_gradient call) and, for
+// sharded minibatches, the gradient exchange of SURVEY.md 8e, which the reference does not have: every
+// rank holds the same parameters and Adam state and applies the identical update to the identical
+// summed gradient.
+//
+// The exchange is a one-shot all-reduce written into the kernel (no NCCL call on this path): a block
+// owns 32 parameters; it writes its 32 local sums into this rank's exchange buffer (symmetric memory,
+// mapped into every peer), releases a flag in every peer's flag pad, waits until every peer's flag for
+// the same block has arrived, then reads the 32 values of every rank through the peer mappings and adds
+// them in RANK ORDER (so all ranks compute bit-identical sums) before the Adam update.  Blocks only wait
+// for the same block index on the other GPUs, never for another block of their own GPU.  Exchange
+// buffers and flags are double-buffered by step parity: a rank can only be one step ahead of the slowest.
+#include "mq_common.cuh"
+
+#ifndef MQ_EMU
+
+template <bool ADAMS>
+__device__ __forceinline__ void step_elem(double &val, double &m, double &v, double g, double c1, double c2, double lr,
+                                          double eps) {
+    m = __dadd_rn(m, __dmul_rn(c1, __dsub_rn(g, m)));
+    v = __dadd_rn(v, __dmul_rn(c2, __dsub_rn(__dmul_rn(g, g), v)));
+    const double den = __dadd_rn(eps, ADAMS ? v : __dsqrt_rn(v));
+    val = __dadd_rn(val, __dmul_rn(lr, __ddiv_rn(m, den)));
+}
+template <bool ADAMS>
+__device__ __forceinline__ void step_elem(float &val, float &m, float &v, float g, float c1, float c2, float lr, float eps) {
+    m += c1 * (g - m);
+    v += c2 * (g * g - v);
+    const float den = eps + (ADAMS ? v : sqrtf(v));
+    val += lr * (m / den);
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// 32 parameters x 8 groups of partial vectors per block; group sums combined in fixed order.
+template <typename ST, bool ADAMS>
+__global__ void __launch_bounds__(MQ_NT)
+reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float scale, ST *__restrict__ value,
+                   ST *__restrict__ m, ST *__restrict__ v, float *__restrict__ theta_out, float *__restrict__ grad_out,
+                   ST c1, ST c2, ST lr, ST eps, mq_peer_t peer) {
+    __shared__ float part[8][33];
+    const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + jx;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (j < n) {
+        int b = gy;
+        for (; b + 24 < n_parts; b += 32) {
+            s0 += partial[(int64_t)b * n + j];
+            s1 += partial[(int64_t)(b + 8) * n + j];
+            s2 += partial[(int64_t)(b + 16) * n + j];
+            s3 += partial[(int64_t)(b + 24) * n + j];
+        }
+        for (; b < n_parts; b += 8) s0 += partial[(int64_t)b * n + j];
+    }
+    part[gy][jx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (gy != 0) return;
+    float g = part[0][jx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) g += part[k][jx];
+    if (peer.world > 1) {
+        // ---- one-shot all-reduce over peer memory ------------------------------------------------
+        const int par = (int)(peer.step & 1u);
+        float *mine = peer.grad_bufs[peer.rank] + (int64_t)par * peer.buf_stride;
+        if (j < n) mine[j] = g;
+        __threadfence_system();
+        __syncwarp();
+        const int nblk = gridDim.x;
+        if (jx < peer.world)            // lane r tells rank r that this rank's block is ready
+            st_release_sys(peer.flag_bufs[jx] + ((int64_t)par * peer.world + peer.rank) * nblk + blockIdx.x, peer.step);
+        if (jx < peer.world) {          // lane r waits for rank r's block
+            const uint32_t *f = peer.flag_bufs[peer.rank] + ((int64_t)par * peer.world + jx) * nblk + blockIdx.x;
+            while (ld_acquire_sys(f) != peer.step) { }
+        }
+        __syncwarp();
+        g = 0.0f;
+        if (j < n)
+            for (int r = 0; r < peer.world; ++r)
+                g += ld_relaxed_sys(peer.grad_bufs[r] + (int64_t)par * peer.buf_stride + j);
+    }
+    if (j >= n) return;
+    g *= scale;
+    if (grad_out) grad_out[j] = g;
+    ST a = value[j], b = m[j], c = v[j];
+    step_elem<ADAMS>(a, b, c, (ST)g, c1, c2, lr, eps);
+    value[j] = a; m[j] = b; v[j] = c;
+    if (theta_out) theta_out[j] = (float)a;
+}
+
+extern "C" int64_t mq_step_blocks(int64_t n) { return mq_ceil_div(n, 32); }
+
+extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
+                              void *v, float *theta_out, float *grad_out, int state_dtype, double c1, double c2,
+                              double lr, double eps, int adams, const mq_peer_t *peer, void *stream) {
+    MQ_REQUIRE(partials && value && m && v, MQ_ERR_INVALID, "mq_reduce_step: null pointer");
+    MQ_REQUIRE(n_parts >= 1 && n >= 1 && n < (1LL << 31), MQ_ERR_SHAPE, "mq_reduce_step: sizes");
+    mq_peer_t pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.world = 1;
+    if (peer && peer->world > 1) {
+        pr = *peer;
+        MQ_REQUIRE(pr.world <= 32 && pr.rank >= 0 && pr.rank < pr.world && pr.grad_bufs && pr.flag_bufs &&
+                       pr.buf_stride >= n && pr.step != 0,
+                   MQ_ERR_INVALID, "mq_reduce_step: bad peer descriptor");
+    }
+    const unsigned blocks = (unsigned)mq_ceil_div(n, 32);
+#define MQ_STEP_GO(ST, A)                                                                                      \
+    do {                                                                                                       \
+        auto kfn = reduce_step_kernel<ST, A>;                                                                  \
+        MQ_LAUNCH(kfn, blocks, MQ_NT, 0, stream, partials, (int)n_parts, (int)n, scale, (ST *)value, (ST *)m, \
+                  (ST *)v, theta_out, grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr);                          \
+    } while (0)
+    if (state_dtype == MQ_F32) { if (adams) MQ_STEP_GO(float, true); else MQ_STEP_GO(float, false); }
+    else if (state_dtype == MQ_F64) { if (adams) MQ_STEP_GO(double, true); else MQ_STEP_GO(double, false); }
+    else { mq_set_error("mq_reduce_step: state dtype %d", state_dtype); return MQ_ERR_INVALID; }
+#undef MQ_STEP_GO
+    MQ_CHECK_LAUNCH("mq_reduce_step");
+    return MQ_OK;
+}
+
+#else   // MQ_EMU
+extern "C" int64_t mq_step_blocks(int64_t n) { return mq_ceil_div(n, 32); }
+extern "C" int mq_reduce_step(const float *, int32_t, int64_t, float, void *, void *, void *, float *, float *, int, double,
+                              double, double, double, int, const mq_peer_t *, void *) { return MQ_ERR_UNSUPPORTED; }
+#endif

@@ -54,6 +54,7 @@ class _Net(object):
         self.opt = Adam(theta_host, horizon=horizon, state_dtype=state_dtype)
         self.code = self.opt._code
         self.grad = D.zeros(net.n_params)
+        self._peer = None
 
     def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8):
         """n_steps optimiser steps; idx_table is i32[n_steps, mb] (rows of THIS rank)."""
@@ -71,9 +72,22 @@ class _Net(object):
         self.opt._tw = [tw[0], tw[1]]
         self.opt._out = None
 
-    # -- large minibatches: all SMs per step, one gradient all-reduce across GPUs ---------
+    # -- large minibatches: all SMs per step, one gradient exchange across GPUs ----------------
     def _one_step(self, x, head, idx_ptr, mb, scale, ws, wsb, c1, c2, lr, eps):
         value, m, v, _ = self.opt.state()
+        if self._peer is None:
+            self._peer = mqdist.PeerExchange(self.net.n_params)
+        if mqdist.world() == 1 or self._peer.available():
+            # 2 launches: gradient kernel (per-CTA partials), then ONE kernel that sums them in fixed order,
+            # all-reduces over NVLink peer memory when sharded, and applies Adam (csrc/mq_step.cu)
+            n_parts = ctypes.c_int32(0)
+            D.call("mq_fused_grad_partials", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), idx_ptr, mb,
+                   ctypes.byref(head), None, None, D.ptr(ws), wsb, ctypes.byref(n_parts), D.stream())
+            peer = ctypes.byref(self._peer.descriptor()) if mqdist.world() > 1 else None
+            D.call("mq_reduce_step", D.ptr(ws), n_parts.value, self.net.n_params, scale, D.ptr(value), D.ptr(m),
+                   D.ptr(v), D.ptr(self.theta), None, self.code, c1, c2, lr, eps, 0, peer, D.stream())
+            return
+        # fallback (no peer mapping): gradient, NCCL / gloo all-reduce, Adam
         D.call("mq_fused_grad", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), idx_ptr, mb,
                ctypes.byref(head), scale, D.ptr(self.grad), None, None, D.ptr(ws), wsb, D.stream())
         mqdist.allreduce_sum_(self.grad)
@@ -88,9 +102,6 @@ class _Net(object):
         coefs = [self.opt.next_coefs() for _ in range(n_steps)]
         self.opt._out = None
         base, stride = D.ptr(idx_table), mb * 4
-
-        # 3 launches per step (grad over all SMs, fixed-order reduce, Adam); at >= 8k rows the
-        # kernels outlast the launch cost, so no CUDA graph is needed.
         for s in range(n_steps):
             self._one_step(x, head, base + s * stride, mb, scale, ws, wsb, coefs[s][0], coefs[s][1], lr, eps)
 

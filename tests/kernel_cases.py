@@ -655,5 +655,38 @@ def case_tc_paths(B):
         lib.mq_debug_set_tc_mode(1)
 
 
+def case_reduce_step(B):
+    """mq_reduce_step (single GPU): fixed-order sum of partial gradients + Adam in one launch equals
+    mq_adam_step on the summed gradient (fp32 state) and the oracle's Adam (fp64 state, bit exact)."""
+    lib = B.lib
+    rs = np.random.RandomState(21)
+    for n, parts in ((5126, 148), (4993, 1), (33, 7), (118282, 40)):
+        partial = (rs.randn(parts, n) * 0.1).astype(np.float32)
+        scale = 1.0 / 4096
+        g64 = partial.astype(np.float64).sum(0) * scale
+        val0 = rs.randn(n)
+        hp = B.up(partial)
+        # fp64 state against the oracle, teacher-forced with the kernel's own fp32 gradient
+        val, m, v = B.up(val0.copy()), B.zeros(n, np.float64), B.zeros(n, np.float64)
+        th, gout = B.zeros(n, np.float32), B.zeros(n, np.float32)
+        ok(B, lib.mq_reduce_step(B.ptr(hp), parts, n, scale, B.ptr(val), B.ptr(m), B.ptr(v), B.ptr(th), B.ptr(gout),
+                                 L.MQ_F64, 1.0, 1.0, 1e-3, 1e-8, 0, None, B.stream))
+        g = B.down(gout)
+        close(g, g64, rtol=1e-5, atol_scale=1e-6, what="reduce_step grad n=%d" % n)
+        ref = O.AdamO(val0, horizon=10, lr=1e-3)
+        ref.apply_gradient(g)
+        assert np.array_equal(B.down(val), ref.get_value()), "reduce_step fp64 Adam n=%d" % n
+        assert np.array_equal(B.down(th), ref.get_value().astype(np.float32))
+        # fp32 state against mq_adam_step on the same gradient
+        v32 = [B.up(val0.astype(np.float32)), B.zeros(n, np.float32), B.zeros(n, np.float32)]
+        w32 = [B.up(val0.astype(np.float32)), B.zeros(n, np.float32), B.zeros(n, np.float32)]
+        ok(B, lib.mq_reduce_step(B.ptr(hp), parts, n, scale, B.ptr(v32[0]), B.ptr(v32[1]), B.ptr(v32[2]), None, None,
+                                 L.MQ_F32, 0.5, 0.25, 3e-4, 1e-8, 0, None, B.stream))
+        ok(B, lib.mq_adam_step(B.ptr(w32[0]), B.ptr(w32[1]), B.ptr(w32[2]), None, B.ptr(gout), n, L.MQ_F32, L.MQ_F32,
+                               0.5, 0.25, 3e-4, 1e-8, 0, B.stream))
+        for a, b in zip(v32, w32):
+            assert np.array_equal(B.down(a), B.down(b)), "reduce_step fp32 state n=%d" % n
+
+
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_fused_heads,
-             case_fused_gauss_ppo, case_tc_paths, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]

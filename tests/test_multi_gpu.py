@@ -20,8 +20,10 @@ def _data(seed, n):
     return o, a, r, d, vi, pi
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, peer):
     sys.path.insert(0, ROOT)
+    if not peer:
+        os.environ["MQ_NO_PEER_EXCHANGE"] = "1"           # NCCL all-reduce + separate Adam launch
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -34,18 +36,20 @@ def _worker(rank, world, port, out_dir):
     shard = _data(10 + rank, 4096)
     upd.update_dev(*[D.from_host(x) for x in shard])
     torch.cuda.synchronize()
+    assert (upd.policy._peer is not None and upd.policy._peer.available()) == bool(peer), "exchange path"
     np.save(os.path.join(out_dir, "pol%d.npy" % rank), D.to_host(upd.policy.theta))
     np.save(os.path.join(out_dir, "val%d.npy" % rank), D.to_host(upd.value.theta))
     dist.destroy_process_group()
 
 
-def test_sharded_update_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("peer", [True, False], ids=["peer_memory_exchange", "nccl_allreduce"])
+def test_sharded_update_matches_single_gpu(tmp_path, peer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + os.getpid() % 2000 + (7 if peer else 0)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), peer), nprocs=2, join=True)
     pol = [np.load(os.path.join(tmp_path, "pol%d.npy" % r)) for r in range(2)]
     val = [np.load(os.path.join(tmp_path, "val%d.npy" % r)) for r in range(2)]
     assert np.array_equal(pol[0], pol[1]) and np.array_equal(val[0], val[1])     # replicas stay identical
