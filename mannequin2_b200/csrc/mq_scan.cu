@@ -10,10 +10,13 @@
 // Episode boundaries are carried by a[i] = 0, so segmentation is exact by
 // construction.  Affine maps compose associatively:
 //     (a1,b1) then (a2,b2)  =  (a1*a2, b2 + a2*b1)
-// Each CTA scans a chunk of 2048 elements (8 per thread, warp-shuffle scan);
-// chunk aggregates are scanned by one CTA; a third pass applies the carries.
-// Rollouts of <= 2048 steps need a single launch.  HBM-bound: 17 B / transition
-// algorithmic; the second read of the inputs is served by the 126 MB L2.
+// ONE pass over HBM (17 B / transition: the algorithmic minimum): a CTA takes the chunk of 2048
+// elements of its block index, stages it in shared memory with coalesced loads,
+// scans it (8 elements per thread, warp-shuffle scan), publishes the chunk's map, obtains the value
+// entering the chunk by looking back over the preceding chunks (decoupled look-back; a chunk that
+// contains an episode end has a = 0 and ends the walk at once), publishes the value leaving it and
+// writes its outputs with coalesced stores.  Rollouts of <= 2048 steps are a single CTA.
+// (The three-launch chunk / carry / apply kernels below remain for that case and for tools/emu.)
 #include "mq_common.cuh"
 
 #define SCAN_ITEMS 8
@@ -144,13 +147,198 @@ scan_carry_kernel(const Lin<T> *__restrict__ agg, int64_t nb, T *__restrict__ ca
     }
 }
 
-extern "C" int64_t mq_scan_ws_bytes(int64_t n) {
-    const int64_t nb = mq_ceil_div(n < 1 ? 1 : n, SCAN_CHUNK);
-    return nb * 3 * (int64_t)sizeof(double) + 64;
+// ---- single-pass variant -----------------------------------------------------------------------------
+#define SCAN_PAD(i) ((i) + ((i) >> 5))             // conflict-free 8-consecutive-per-thread access
+
+struct GaeStage {
+    const float *rew, *val;
+    const uint8_t *done;
+    float *adv, *ret;
+    float g, gl;
+    static constexpr int kSmemBytes = (SCAN_PAD(SCAN_CHUNK) + 1) * 4 * 2 + SCAN_CHUNK + 64;
+    // memory rows [lo, lo+cnt) -> shared memory; val also at lo+cnt (bootstrap / next state)
+    __device__ __forceinline__ void stage(unsigned char *sm, int64_t lo, int cnt) const {
+        float *sr = reinterpret_cast<float *>(sm), *sv = sr + SCAN_PAD(SCAN_CHUNK) + 1;
+        uint8_t *sd = reinterpret_cast<uint8_t *>(sv + SCAN_PAD(SCAN_CHUNK) + 1 + 8);
+        for (int i = threadIdx.x; i < cnt; i += MQ_NT) { sr[SCAN_PAD(i)] = rew[lo + i]; sd[i] = done[lo + i]; }
+        for (int i = threadIdx.x; i <= cnt; i += MQ_NT) sv[SCAN_PAD(i)] = val[lo + i];
+    }
+    __device__ __forceinline__ Lin<float> get(const unsigned char *sm, int li) const {
+        const float *sr = reinterpret_cast<const float *>(sm), *sv = sr + SCAN_PAD(SCAN_CHUNK) + 1;
+        const uint8_t *sd = reinterpret_cast<const uint8_t *>(sv + SCAN_PAD(SCAN_CHUNK) + 1 + 8);
+        Lin<float> e;
+        const float v0 = sv[SCAN_PAD(li)];
+        if (sd[li]) { e.a = 0.0f; e.b = sr[SCAN_PAD(li)] - v0; }
+        else { e.a = gl; e.b = sr[SCAN_PAD(li)] + g * sv[SCAN_PAD(li + 1)] - v0; }
+        return e;
+    }
+    __device__ __forceinline__ void put(unsigned char *sm, int li, float y) const {
+        reinterpret_cast<float *>(sm)[SCAN_PAD(li)] = y;          // over the reward: already consumed
+    }
+    __device__ __forceinline__ void flush(const unsigned char *sm, int64_t lo, int cnt) const {
+        const float *sr = reinterpret_cast<const float *>(sm), *sv = sr + SCAN_PAD(SCAN_CHUNK) + 1;
+        for (int i = threadIdx.x; i < cnt; i += MQ_NT) {
+            const float y = sr[SCAN_PAD(i)];
+            adv[lo + i] = y;
+            ret[lo + i] = y + sv[SCAN_PAD(i)];
+        }
+    }
+};
+
+struct DiscStage {
+    const double *in;
+    double *out;
+    double keep, step;
+    static constexpr int kSmemBytes = (SCAN_PAD(SCAN_CHUNK) + 1) * 8;
+    __device__ __forceinline__ void stage(unsigned char *sm, int64_t lo, int cnt) const {
+        double *sx = reinterpret_cast<double *>(sm);
+        for (int i = threadIdx.x; i < cnt; i += MQ_NT) sx[SCAN_PAD(i)] = in[lo + i];
+    }
+    __device__ __forceinline__ Lin<double> get(const unsigned char *sm, int li) const {
+        Lin<double> e;
+        e.a = keep;
+        e.b = step * reinterpret_cast<const double *>(sm)[SCAN_PAD(li)];
+        return e;
+    }
+    __device__ __forceinline__ void put(unsigned char *sm, int li, double y) const {
+        reinterpret_cast<double *>(sm)[SCAN_PAD(li)] = y;
+    }
+    __device__ __forceinline__ void flush(const unsigned char *sm, int64_t lo, int cnt) const {
+        const double *sx = reinterpret_cast<const double *>(sm);
+        for (int i = threadIdx.x; i < cnt; i += MQ_NT) out[lo + i] = sx[SCAN_PAD(i)];
+    }
+};
+
+// per-chunk descriptor: status 0 = empty, 1 = map of the chunk alone, 2 = value leaving the chunk
+template <typename T> struct ScanTile { T a, b, y; int status; int pad; };
+
+__device__ __forceinline__ int scan_ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void scan_st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <typename T, typename E>
-static int scan_run(E el, int64_t n, void *ws, int64_t ws_bytes, void *stream, const char *what) {
+__global__ void __launch_bounds__(MQ_NT, 8)
+scan_lookback_kernel(E el, int64_t n, ScanTile<T> *__restrict__ tiles, unsigned int *__restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    __shared__ Lin<T> warp_tot[MQ_NT / 32];
+    __shared__ T s_yin;
+    // chunk = block index: like cub::DeviceScan this relies on the hardware dispatching blocks in index order, so
+    // that every chunk a block waits for belongs to a block that is already resident (a ticket counter costs one
+    // same-address atomic per chunk, which at 32,768 chunks was 12 % of the kernel)
+    (void)ticket;
+    const int64_t c = blockIdx.x;
+    // reversed positions [c*CH, (c+1)*CH) = memory rows [lo, hi]
+    const int64_t hi = n - 1 - c * SCAN_CHUNK;
+    const int64_t lo = hi - (SCAN_CHUNK - 1) > 0 ? hi - (SCAN_CHUNK - 1) : 0;
+    const int cnt = (int)(hi - lo + 1);
+    el.stage(sm, lo, cnt);
+    __syncthreads();
+    // (the elements are re-read from shared memory in the output pass instead of being kept in registers:
+    //  8 CTAs per SM keep enough bytes in flight to cover the look-back and the phase changes)
+    Lin<T> local; local.a = (T)1; local.b = (T)0;
+    const int jl0 = threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int li = cnt - 1 - (jl0 + k);          // memory-local index of reversed position jl0 + k
+        if (li >= 0) local = lin_then(local, el.get(sm, li));
+    }
+    Lin<T> excl, total;
+    lin_block_scan(local, excl, total, warp_tot);
+    // ---- publish this chunk's map, look back for the value entering it (warp 0) --------------------
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        // a chunk that contains an episode end (a = 0) leaves the same value whatever enters it: publish that value
+        // at once so that later chunks never wait for this chunk's own look-back
+        const bool closed = total.a == (T)0;
+        if (lane == 0) {
+            tiles[c].a = total.a; tiles[c].b = total.b; tiles[c].y = total.b;
+            __threadfence();
+            scan_st_release(&tiles[c].status, closed ? 2 : 1);
+        }
+        // acc = composition of the chunks already folded in (those nearest to c); identity at first
+        Lin<T> acc; acc.a = (T)1; acc.b = (T)0;
+        bool done = false;
+        int64_t base = c - 1;                          // nearest predecessor not yet folded in
+        while (!done) {
+            const int64_t q = base - lane;             // lane 0 = nearest
+            T qa = (T)0, qb = (T)0;                    // before chunk 0 the recurrence is 0: a terminator
+            if (q >= 0) {
+                int st;
+                do { st = scan_ld_acquire(&tiles[q].status); } while (st == 0);
+                if (st == 2) qb = tiles[q].y;          // value LEAVING chunk q: ignores what entered it
+                else { qa = tiles[q].a; qb = tiles[q].b; }
+            }
+            const unsigned term = __ballot_sync(0xffffffffu, qa == (T)0);
+            const int stop = term ? __ffs(term) - 1 : 31;
+            Lin<T> win; win.a = (T)1; win.b = (T)0;    // chunks base-stop .. base, oldest applied first
+            for (int l = stop; l >= 0; --l) {
+                Lin<T> e;
+                e.a = __shfl_sync(0xffffffffu, qa, l);
+                e.b = __shfl_sync(0xffffffffu, qb, l);
+                win = lin_then(win, e);
+            }
+            acc = lin_then(win, acc);
+            done = term != 0u;
+            base -= 32;
+        }
+        if (lane == 0) {
+            s_yin = acc.b;
+            if (!closed) {
+                tiles[c].y = total.b + total.a * acc.b;
+                __threadfence();
+                scan_st_release(&tiles[c].status, 2);
+            }
+        }
+    }
+    __syncthreads();
+    T y = excl.b + excl.a * s_yin;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int li = cnt - 1 - (jl0 + k);
+        if (li >= 0) {
+            const Lin<T> e = el.get(sm, li);
+            y = e.b + e.a * y;
+            el.put(sm, li, y);
+        }
+    }
+    __syncthreads();
+    el.flush(sm, lo, cnt);
+}
+
+extern "C" int64_t mq_scan_ws_bytes(int64_t n) {
+    const int64_t nb = mq_ceil_div(n < 1 ? 1 : n, SCAN_CHUNK);
+    return nb * (int64_t)sizeof(ScanTile<double>) + 64;
+}
+
+#ifndef MQ_EMU
+template <typename T, typename E, typename S>
+static int scan_run(E el, S st, int64_t n, void *ws, int64_t ws_bytes, void *stream, const char *what) {
+    if (n == 0) return MQ_OK;
+    const int64_t nb = mq_ceil_div(n, SCAN_CHUNK);
+    if (nb == 1) {
+        auto k1 = scan_chunk_kernel<T, E, 1>;
+        MQ_LAUNCH(k1, 1, MQ_NT, 0, stream, el, n, (Lin<T> *)nullptr, (const T *)nullptr);
+    } else {
+        MQ_REQUIRE(ws && ws_bytes >= mq_scan_ws_bytes(n), MQ_ERR_SHAPE, "%s: workspace too small", what);
+        const int64_t used = nb * (int64_t)sizeof(ScanTile<T>) + 64;
+        cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)used, (cudaStream_t)stream);
+        if (e != cudaSuccess) { mq_set_error("%s: %s", what, cudaGetErrorString(e)); return MQ_ERR_CUDA; }
+        unsigned int *ticket = (unsigned int *)ws;
+        ScanTile<T> *tiles = (ScanTile<T> *)((char *)ws + 64);
+        auto k = scan_lookback_kernel<T, S>;
+        MQ_LAUNCH(k, (unsigned)nb, MQ_NT, S::kSmemBytes, stream, st, n, tiles, ticket);
+    }
+    MQ_CHECK_LAUNCH(what);
+    return MQ_OK;
+}
+#else
+template <typename T, typename E, typename S>
+static int scan_run(E el, S, int64_t n, void *ws, int64_t ws_bytes, void *stream, const char *what) {
     if (n == 0) return MQ_OK;
     const int64_t nb = mq_ceil_div(n, SCAN_CHUNK);
     if (nb == 1) {
@@ -170,6 +358,7 @@ static int scan_run(E el, int64_t n, void *ws, int64_t ws_bytes, void *stream, c
     MQ_CHECK_LAUNCH(what);
     return MQ_OK;
 }
+#endif
 
 extern "C" int mq_gae(const float *rew, const float *value, const uint8_t *done, int64_t n,
                       double gam, double lam, float *adv, float *ret, void *ws, int64_t ws_bytes,
@@ -180,7 +369,9 @@ extern "C" int mq_gae(const float *rew, const float *value, const uint8_t *done,
     el.rew = rew; el.val = value; el.done = done; el.adv = adv; el.ret = ret;
     el.g = (float)gam;
     el.gl = (float)(gam * lam);           // gae.py:56: python-float product, then fp32
-    return scan_run<float, GaeElems>(el, n, ws, ws_bytes, stream, "mq_gae");
+    GaeStage st;
+    st.rew = rew; st.val = value; st.done = done; st.adv = adv; st.ret = ret; st.g = el.g; st.gl = el.gl;
+    return scan_run<float, GaeElems, GaeStage>(el, st, n, ws, ws_bytes, stream, "mq_gae");
 }
 
 extern "C" int mq_discounted(const double *in, int64_t n, double horizon, double *out, void *ws,
@@ -192,5 +383,7 @@ extern "C" int mq_discounted(const double *in, int64_t n, double horizon, double
     MQ_REQUIRE(n == 0 || (in && out), MQ_ERR_INVALID, "mq_discounted: null pointer");
     DiscElems el;
     el.in = in; el.out = out; el.keep = 1.0 - step; el.step = step;
-    return scan_run<double, DiscElems>(el, n, ws, ws_bytes, stream, "mq_discounted");
+    DiscStage st;
+    st.in = in; st.out = out; st.keep = el.keep; st.step = step;
+    return scan_run<double, DiscElems, DiscStage>(el, st, n, ws, ws_bytes, stream, "mq_discounted");
 }
