@@ -62,15 +62,19 @@ typedef struct mq_net {
 #define MQ_HEAD_SOFTMAX_CE 2  /* dy = onehot - softmax(out) - p0*out: mnist/mlp.py:10-14,31-35       */
 #define MQ_HEAD_GAUSS_LOGP 3  /* d/dtheta sum_b w_b logp_b, w supplied: distrib.py:61-68, gae.py:98-99 */
 #define MQ_HEAD_GAUSS_PPO  4  /* w_b = clip-rule(exp(logp-logp_old), adv)*adv: benchmarks/ppo.py:33-40 */
+#define MQ_HEAD_DISCRETE_LOGP 5 /* categorical: d/dtheta sum_b w_b log softmax(out_b)[a_b], distrib.py:24-32;
+                                  the action is a ONE-HOT row of `target`, w = dy                       */
+#define MQ_HEAD_DISCRETE_PPO  6 /* the same with the PPO clip weights (benchmarks/ppo.py:33-40)        */
 
 typedef struct mq_head {
     int32_t kind;
     float   p0;                /* SOFTMAX_CE: logit L2 coefficient (0.01); GAUSS_PPO: clip low (0.8) */
     float   p1;                /* GAUSS_PPO: clip high (1.2)                                         */
-    const float *dy;           /* DY: [rows,n_out]; GAUSS_LOGP: weights [rows]                        */
-    const float *target;       /* DIFF/SOFTMAX_CE: [rows,n_out]; GAUSS_*: sampled actions [rows,A]   */
-    const float *adv;          /* GAUSS_PPO: advantages [rows]                                       */
-    const float *logp_old;     /* GAUSS_PPO: log-probabilities under the pre-update policy [rows]    */
+    const float *dy;           /* DY: [rows,n_out]; GAUSS_LOGP / DISCRETE_LOGP: weights [rows]        */
+    const float *target;       /* DIFF/SOFTMAX_CE: [rows,n_out]; GAUSS_*: sampled actions [rows,A];
+                                  DISCRETE_*: one-hot actions [rows,n_out]                            */
+    const float *adv;          /* *_PPO: advantages [rows]                                           */
+    const float *logp_old;     /* *_PPO: log-probabilities under the pre-update policy [rows]        */
 } mq_head_t;
 /* When row_idx != NULL, x and every head array are indexed by row_idx[i] (they
  * are whole-rollout arrays, mannequin/_trajectory.py:79-86 fused into the load);
@@ -150,7 +154,8 @@ int mq_mlp_backward(const mq_net_t *net, const float *theta, const float *x, con
 /* rows per tile the fused kernels would use for this net (0 = does not fit). */
 int mq_fused_tile_rows(const mq_net_t *net, int with_grad);
 int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch);
-/* out[batch,n_out] and/or logp[batch] (Gaussian nets; needs sample) may be NULL */
+/* out[batch,n_out] and/or logp[batch] may be NULL.  logp needs `sample`: sampled actions [batch,A] when the net
+ * has logstd parameters (Gaussian), one-hot actions [batch,n_out] otherwise (categorical, distrib.py:24-30). */
 int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                      int64_t batch, float *out, const float *sample, float *logp, void *stream);
 /* forward + head + backward in one launch; grad[n_params] = scale * sum_batch */
@@ -222,6 +227,12 @@ int mq_gauss_logprob(const float *mu, const float *logstd, int64_t logstd_period
 int mq_gauss_logprob_bwd(const float *mu, const float *logstd, int64_t logstd_period,
                          const float *sample, const float *g, int64_t rows, int64_t a, float *d_mu,
                          float *d_logstd_rows, void *stream);
+/* categorical log-prob (mannequin/distrib.py:24-32): logp[r] = log softmax(logits[r])[sample[r]] and / or
+ * d_logits[r] = g[r] * (onehot(sample[r]) - softmax(logits[r])); g is only read when d_logits != NULL */
+int mq_discrete_logprob(const float *logits, const int32_t *sample, const float *g, int64_t rows, int64_t n,
+                        float *logp, float *d_logits, void *stream);
+/* out[rows,n] = one-hot rows of idx: the `target` of the categorical heads */
+int mq_onehot(const int32_t *idx, int64_t rows, int64_t n, float *out, void *stream);
 int mq_gauss_sample(const float *mu, const float *logstd, int64_t logstd_period, const float *unit,
                     int64_t rows, int64_t a, float *out, float *noise, void *stream);
 int mq_dkl_forward(const float *mean, const float *logstd, int64_t rows, int64_t d, float *out,

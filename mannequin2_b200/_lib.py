@@ -14,6 +14,7 @@ MQ_OK, MQ_ERR_INVALID, MQ_ERR_SHAPE, MQ_ERR_UNSUPPORTED, MQ_ERR_CUDA = 0, -1, -2
 MQ_F32, MQ_F64 = 0, 1
 ACT_NONE, ACT_TANH, ACT_LRELU = 0, 1, 2
 HEAD_DY, HEAD_DIFF, HEAD_SOFTMAX_CE, HEAD_GAUSS_LOGP, HEAD_GAUSS_PPO = 0, 1, 2, 3, 4
+HEAD_DISCRETE_LOGP, HEAD_DISCRETE_PPO = 5, 6
 MAX_LAYERS = 8
 
 
@@ -90,6 +91,8 @@ SIGNATURES = {
     "mq_clip_backward": (c_int, [P, P, P, c_int64, c_float, c_float, P]),
     "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
     "mq_gauss_logprob_bwd": (c_int, [P, P, c_int64, P, P, c_int64, c_int64, P, P, P]),
+    "mq_discrete_logprob": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
+    "mq_onehot": (c_int, [P, c_int64, c_int64, P, P]),
     "mq_gauss_sample": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P, P]),
     "mq_dkl_forward": (c_int, [P, P, c_int64, c_int64, P, P]),
     "mq_dkl_backward": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),

@@ -5,6 +5,7 @@ Recognised roots (everything else runs node by node, basicnet.Function):
   chain  = Input -> [Reshape(-1)] -> (Linear -> Bias -> [LReLU|Tanh])+
   logp   = Gauss.logprob over `chain` with a learnt Params(A) logstd
            (mannequin/distrib.py:61-68,73)
+  logp   = Discrete.logprob over `chain` (mannequin/distrib.py:24-32,35)
 
 A root is only compiled when its Params are one contiguous arena slice in the
 reference's flat order (W1, b1, W2, b2, ..., logstd), so the kernels can address
@@ -17,7 +18,7 @@ import torch
 
 from . import _device as D
 from . import _lib
-from ._lib import ACT_NONE, HEAD_DY, HEAD_GAUSS_LOGP, MqHead
+from ._lib import ACT_NONE, HEAD_DISCRETE_LOGP, HEAD_DY, HEAD_GAUSS_LOGP, MqHead
 from ._utils import endswith
 
 
@@ -80,6 +81,15 @@ def compile_root(root):
         if list(root._params) != order or root._flat is None:
             return None
         return MLPPlan(root, inp, layers, gauss=True)
+    if op and op[0] == "discrete_logprob":
+        m = _match_chain(root.inputs[0])
+        if m is None or len(m[1]) > _lib.MAX_LAYERS:
+            return None
+        inp, layers = m
+        order = [p for l in layers for p in (l[0], l[1])]
+        if list(root._params) != order or root._flat is None:
+            return None
+        return MLPPlan(root, inp, layers, gauss=False, discrete=True)
     m = _match_chain(root)
     if m is None or len(m[1]) > _lib.MAX_LAYERS:
         return None
@@ -91,8 +101,8 @@ def compile_root(root):
 
 
 class MLPPlan(object):
-    def __init__(self, root, inp, layers, gauss):
-        self.root, self.inp, self.gauss = root, inp, gauss
+    def __init__(self, root, inp, layers, gauss, discrete=False):
+        self.root, self.inp, self.gauss, self.discrete = root, inp, gauss, discrete
         self.n_in = int(np.prod(inp.shape))
         self.net = _lib.make_net(self.n_in, [l[0].shape[1] for l in layers], [l[2] for l in layers],
                                  leak=[l[3] for l in layers], logstd=gauss)
@@ -129,7 +139,7 @@ class MLPPlan(object):
 
     # ------------------------------------------------------------------ evaluate
     def evaluate(self, array, **kwargs):
-        if self.gauss:
+        if self.gauss or self.discrete:
             return self._evaluate_logprob(array, **kwargs)
         if kwargs:
             raise TypeError("unexpected keyword arguments %s" % sorted(kwargs))
@@ -189,7 +199,12 @@ class MLPPlan(object):
         if not self.fused_bwd:
             return self.root._evaluate_graph(array, sample=sample)
         x = D.from_host(array.reshape(batch, self.n_in))
-        s = D.from_host(np.asarray(sample, dtype=np.float32).reshape(batch, net.n_out))
+        if self.discrete:                    # the categorical heads take the action as a one-hot target row
+            a = D.from_host(np.asarray(sample, dtype=np.int32).reshape(batch), np.int32)
+            s = D.empty(batch * net.n_out)
+            D.call("mq_onehot", D.ptr(a), batch, net.n_out, D.ptr(s), D.stream())
+        else:
+            s = D.from_host(np.asarray(sample, dtype=np.float32).reshape(batch, net.n_out))
         logp = D.empty(batch)
         D.call("mq_fused_forward", ctypes.byref(net), D.ptr(self.theta), D.ptr(x), None, batch, None,
                D.ptr(s), D.ptr(logp), D.stream())
@@ -201,7 +216,7 @@ class MLPPlan(object):
                 grad = np.asarray(grad, dtype=np.float32)
             assert tuple(grad.shape) == batch_shape
             w = D.as_dev_f32(grad).reshape(-1)
-            g = self._fused_grad(x, batch, HEAD_GAUSS_LOGP, dy=w, target=s)
+            g = self._fused_grad(x, batch, HEAD_DISCRETE_LOGP if self.discrete else HEAD_GAUSS_LOGP, dy=w, target=s)
             return _finish(g, self.root.n_params, output)
 
         return host, backprop

@@ -298,6 +298,30 @@ __device__ __forceinline__ void warp_head(const ChainPlan &p, const mq_head_t &h
             const float dy = tgt[n * CH_TBP + r] - expf(y - mx) * inv - h.p0 * y;
             dzout[n * CH_TBP + r] = mq_act_grad(y, dy, lastact, lastleak);
         }
+    } else if (mq_head_discrete(h.kind)) {
+        // categorical log-prob (distrib.py:24-32): target row is the one-hot action
+        float mx = sAout[r];
+        for (int n = 1; n < N; ++n) mx = fmaxf(mx, sAout[n * CH_TBP + r]);
+        float sum = 0.0f;
+        for (int n = 0; n < N; ++n) sum += expf(sAout[n * CH_TBP + r] - mx);
+        const float lse = mx + logf(sum);
+        float lp = 0.0f;
+        for (int n = 0; n < N; ++n) lp += tgt[n * CH_TBP + r] * (sAout[n * CH_TBP + r] - lse);
+        if (logp_out) logp_out[grow0 + r] = lp;
+        float w;
+        if (h.kind == MQ_HEAD_DISCRETE_PPO) {
+            const float adv = misc[r];
+            const float ratio = expf(lp - misc[CH_TBP + r]);
+            const bool kill = (ratio > h.p1 && adv > 0.0f) || (ratio < h.p0 && adv < 0.0f);
+            w = kill ? 0.0f : ratio * adv;
+        } else {
+            w = misc[r];
+        }
+        for (int n = 0; n < N; ++n) {
+            const float y = sAout[n * CH_TBP + r];
+            dzout[n * CH_TBP + r] = mq_act_grad(y, w * (tgt[n * CH_TBP + r] - expf(y - lse)), lastact, lastleak);
+            hterm[n * CH_TBP + r] = 0.0f;
+        }
     } else {
         float acc = 0.0f;
         for (int a = 0; a < N; ++a) {
@@ -525,7 +549,8 @@ chain_train_kernel(ChainPlan p, float *__restrict__ theta, float *__restrict__ v
     const int ntiles = (mb + CH_TB - 1) / CH_TB;
     const float inv_mb = 1.0f / (float)mb;
     const float *hmat = (head.kind == MQ_HEAD_DY) ? head.dy : head.target;
-    const float *hv0 = (head.kind == MQ_HEAD_GAUSS_PPO) ? head.adv : head.dy;
+    const float *hv0 = mq_head_ppo(head.kind) ? head.adv : head.dy;
+    const bool prob = mq_head_prob(head.kind);
     float *aux = sm.A + p.aux_off;
 
     // ---- load state: value/m/v (fp32) -> shared, padded entries zero
@@ -582,12 +607,12 @@ chain_train_kernel(ChainPlan p, float *__restrict__ theta, float *__restrict__ v
             }
         }
         pm = 0.0f;
-        if (gauss && tid < 2 * CH_TB) {
+        if (prob && tid < 2 * CH_TB) {
             const int which = tid / CH_TB, r = tid - which * CH_TB;
             const int src = I[r];
             if (src >= 0) {
                 if (which == 0) pm = hv0[src];
-                else if (head.kind == MQ_HEAD_GAUSS_PPO) pm = head.logp_old[src];
+                else if (mq_head_ppo(head.kind)) pm = head.logp_old[src];
             }
         }
     };
@@ -608,7 +633,7 @@ chain_train_kernel(ChainPlan p, float *__restrict__ theta, float *__restrict__ v
                 const int e = tid + q * CH_NT;
                 if (e < CH_TB * NO) { const int r = e / NO, n = e - r * NO; aux[n * CH_TBP + r] = ph[q]; }
             }
-            if (gauss && tid < 2 * CH_TB) {
+            if (prob && tid < 2 * CH_TB) {
                 const int which = tid / CH_TB, r = tid - which * CH_TB;
                 aux[2 * NO * CH_TBP + which * CH_TBP + r] = pm;
             }
@@ -687,7 +712,8 @@ chain_grad_kernel(ChainPlan p, const float *__restrict__ theta, const float *__r
     const int L = p.net.n_layers, K0 = p.net.n_in, NO = p.net.n_out;
     const bool gauss = head.kind == MQ_HEAD_GAUSS_LOGP || head.kind == MQ_HEAD_GAUSS_PPO;
     const float *hmat = (head.kind == MQ_HEAD_DY) ? head.dy : head.target;
-    const float *hv0 = (head.kind == MQ_HEAD_GAUSS_PPO) ? head.adv : head.dy;
+    const float *hv0 = mq_head_ppo(head.kind) ? head.adv : head.dy;
+    const bool prob = mq_head_prob(head.kind);
     float *aux = sm.A + p.aux_off;
 
     for (int e = tid; e < 2 * p.p_pad + p.wt_total; e += CH_NT) sm.W[e] = 0.0f;
@@ -733,12 +759,12 @@ chain_grad_kernel(ChainPlan p, const float *__restrict__ theta, const float *__r
             }
         }
         pm = 0.0f;
-        if (gauss && tid < 2 * CH_TB) {
+        if (prob && tid < 2 * CH_TB) {
             const int which = tid / CH_TB, r = tid - which * CH_TB;
             const int src = I[r];
             if (src >= 0) {
                 if (which == 0) pm = hv0[src];
-                else if (head.kind == MQ_HEAD_GAUSS_PPO) pm = head.logp_old[src];
+                else if (mq_head_ppo(head.kind)) pm = head.logp_old[src];
             }
         }
     };
@@ -757,7 +783,7 @@ chain_grad_kernel(ChainPlan p, const float *__restrict__ theta, const float *__r
             const int e = tid + q * CH_NT;
             if (e < CH_TB * NO) { const int r = e / NO, n = e - r * NO; aux[n * CH_TBP + r] = ph[q]; }
         }
-        if (gauss && tid < 2 * CH_TB) {
+        if (prob && tid < 2 * CH_TB) {
             const int which = tid / CH_TB, r = tid - which * CH_TB;
             aux[2 * NO * CH_TBP + which * CH_TBP + r] = pm;
         }

@@ -21,6 +21,15 @@
 
 #define MQ_NT 256  // threads per CTA used by every kernel in this library
 
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+static __host__ __device__ inline bool mq_head_gauss(int k) { return k == MQ_HEAD_GAUSS_LOGP || k == MQ_HEAD_GAUSS_PPO; }
+static __host__ __device__ inline bool mq_head_discrete(int k) { return k == MQ_HEAD_DISCRETE_LOGP || k == MQ_HEAD_DISCRETE_PPO; }
+static __host__ __device__ inline bool mq_head_ppo(int k) { return k == MQ_HEAD_GAUSS_PPO || k == MQ_HEAD_DISCRETE_PPO; }
+static __host__ __device__ inline bool mq_head_prob(int k) { return mq_head_gauss(k) || mq_head_discrete(k); }
+
 // ---- host-side error plumbing ------------------------------------------------
 void mq_set_error(const char *fmt, ...);
 

@@ -219,9 +219,9 @@ __device__ void load_head_inputs(const FusedPlan &p, const mq_head_t &h, const i
         if (gr < n_rows) v = mat[(idx ? (int64_t)idx[gr] : gr) * N + n];
         aux[n * tbp + r] = v;
     }
-    if (h.kind == MQ_HEAD_GAUSS_LOGP || h.kind == MQ_HEAD_GAUSS_PPO) {
+    if (mq_head_prob(h.kind)) {
         float *misc = aux + 2 * N * tbp;
-        const float *v0 = (h.kind == MQ_HEAD_GAUSS_PPO) ? h.adv : h.dy;
+        const float *v0 = mq_head_ppo(h.kind) ? h.adv : h.dy;
         for (int e = threadIdx.x; e < 2 * p.tb; e += NT) {
             const int which = e / p.tb, r = e - which * p.tb;
             const int64_t gr = row0 + r;
@@ -229,7 +229,7 @@ __device__ void load_head_inputs(const FusedPlan &p, const mq_head_t &h, const i
             if (gr < n_rows) {
                 const int64_t src = idx ? (int64_t)idx[gr] : gr;
                 if (which == 0) v = v0[src];
-                else if (h.kind == MQ_HEAD_GAUSS_PPO) v = h.logp_old[src];
+                else if (mq_head_ppo(h.kind)) v = h.logp_old[src];
             }
             misc[which * tbp + r] = v;
         }
@@ -498,6 +498,30 @@ __device__ void head_tile(const FusedPlan &p, const mq_head_t &h, const float *s
                 const float dy = tgt[n * tbp + r] - expf(y - mx) * inv - h.p0 * y;
                 dzout[n * tbp + r] = mq_act_grad(y, dy, lastact, lastleak);
             }
+        } else if (mq_head_discrete(h.kind)) {
+            // categorical log-prob (distrib.py:24-32): target row is the one-hot action
+            float mx = sAout[r];
+            for (int n = 1; n < N; ++n) mx = fmaxf(mx, sAout[n * tbp + r]);
+            float sum = 0.0f;
+            for (int n = 0; n < N; ++n) sum += expf(sAout[n * tbp + r] - mx);
+            const float lse = mx + logf(sum);
+            float lp = 0.0f;
+            for (int n = 0; n < N; ++n) lp += tgt[n * tbp + r] * (sAout[n * tbp + r] - lse);
+            if (logp_out) logp_out[gr] = lp;
+            float w;
+            if (h.kind == MQ_HEAD_DISCRETE_PPO) {
+                const float adv = misc[r];
+                const float ratio = expf(lp - misc[tbp + r]);
+                const bool kill = (ratio > h.p1 && adv > 0.0f) || (ratio < h.p0 && adv < 0.0f);
+                w = kill ? 0.0f : ratio * adv;
+            } else {
+                w = misc[r];
+            }
+            for (int n = 0; n < N; ++n) {
+                const float y = sAout[n * tbp + r];
+                dzout[n * tbp + r] = mq_act_grad(y, w * (tgt[n * tbp + r] - expf(y - lse)), lastact, lastleak);
+                hterm[n * tbp + r] = 0.0f;
+            }
         } else {
             // diagonal Gaussian: distrib.py:61-68 and its closed-form derivative
             float acc = 0.0f;
@@ -578,7 +602,17 @@ fused_forward_kernel(FusedPlan p, const float *__restrict__ theta, const float *
             const int64_t gr = row0 + r;
             if (gr >= n_rows) continue;
             if (out) for (int n = 0; n < N; ++n) out[gr * N + n] = sO[n * tbp + r];
-            if (logp) {
+            if (logp && p.net.logstd_off < 0) {          // categorical: sample row is the one-hot action
+                const int64_t src = idx ? (int64_t)idx[gr] : gr;
+                float mx = sO[r];
+                for (int n = 1; n < N; ++n) mx = fmaxf(mx, sO[n * tbp + r]);
+                float sum = 0.0f;
+                for (int n = 0; n < N; ++n) sum += expf(sO[n * tbp + r] - mx);
+                const float lse = mx + logf(sum);
+                float lp = 0.0f;
+                for (int n = 0; n < N; ++n) lp += sample[src * N + n] * (sO[n * tbp + r] - lse);
+                logp[gr] = lp;
+            } else if (logp) {
                 const int64_t src = idx ? (int64_t)idx[gr] : gr;
                 float acc = 0.0f;
                 for (int a = 0; a < N; ++a) {
@@ -865,6 +899,14 @@ static int head_check(const mq_net_t *net, const mq_head_t *h, const char *what)
             MQ_REQUIRE(h->target && h->adv && h->logp_old && net->logstd_off >= 0, MQ_ERR_INVALID,
                        "%s: PPO head needs sample, adv, logp_old and logstd parameters", what);
             break;
+        case MQ_HEAD_DISCRETE_LOGP:
+            MQ_REQUIRE(h->target && h->dy && net->logstd_off < 0, MQ_ERR_INVALID,
+                       "%s: categorical head needs one-hot actions and weights (and a net without logstd)", what);
+            break;
+        case MQ_HEAD_DISCRETE_PPO:
+            MQ_REQUIRE(h->target && h->adv && h->logp_old && net->logstd_off < 0, MQ_ERR_INVALID,
+                       "%s: categorical PPO head needs one-hot actions, adv and logp_old", what);
+            break;
         default: mq_set_error("%s: unknown head kind %d", what, h->kind); return MQ_ERR_INVALID;
     }
     return MQ_OK;
@@ -917,12 +959,11 @@ extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const f
     MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_fused_forward: negative batch");
     if (batch == 0) return MQ_OK;
     MQ_REQUIRE(theta && x, MQ_ERR_INVALID, "mq_fused_forward: null pointer");
-    MQ_REQUIRE(!logp || (sample && net->logstd_off >= 0), MQ_ERR_INVALID,
-               "mq_fused_forward: logp needs sample and logstd parameters");
+    MQ_REQUIRE(!logp || sample, MQ_ERR_INVALID, "mq_fused_forward: logp needs sample");
     {   // large batches: tcgen05 / TMEM kernel (mq_tc.cu), forward + outputs only
         mq_head_t fh;
         memset(&fh, 0, sizeof(fh));
-        fh.kind = logp ? MQ_HEAD_GAUSS_LOGP : MQ_HEAD_DY;
+        fh.kind = !logp ? MQ_HEAD_DY : (net->logstd_off >= 0 ? MQ_HEAD_GAUSS_LOGP : MQ_HEAD_DISCRETE_LOGP);
         fh.target = sample;
         rc = mq_tc_launch(net, theta, x, row_idx, batch, &fh, 0, out, logp, nullptr, 0, nullptr, stream);
         if (rc != MQ_ERR_UNSUPPORTED) return rc;

@@ -337,3 +337,51 @@ extern "C" int mq_ppo_weight(const float *logp, const float *logp_old, const flo
     MQ_CHECK_LAUNCH("mq_ppo_weight");
     return MQ_OK;
 }
+
+// ---- categorical log-prob: mannequin/distrib.py:24-32 ---------------------------------------------
+// logp[r] = log softmax(logits[r])[sample[r]];  d_logits[r] = g[r] * (onehot(sample[r]) - softmax(logits[r]))
+// (g == NULL: forward only; logp / d_logits may each be NULL).  One thread per row.
+__global__ void __launch_bounds__(MQ_NT)
+discrete_logp_kernel(const float *__restrict__ logits, const int32_t *__restrict__ sample, const float *__restrict__ g,
+                     int64_t rows, int64_t n, float *__restrict__ logp, float *__restrict__ d_logits) {
+    EW_LOOP(r, rows) {
+        const float *y = logits + r * n;
+        float mx = y[0];
+        for (int64_t k = 1; k < n; ++k) mx = fmaxf(mx, y[k]);
+        float sum = 0.0f;
+        for (int64_t k = 0; k < n; ++k) sum += expf(y[k] - mx);
+        const float lse = mx + logf(sum);
+        const int32_t a = sample[r];
+        if (logp) logp[r] = y[a] - lse;
+        if (d_logits) {
+            const float gv = g[r];
+            for (int64_t k = 0; k < n; ++k) d_logits[r * n + k] = gv * ((k == a ? 1.0f : 0.0f) - expf(y[k] - lse));
+        }
+    }
+}
+
+extern "C" int mq_discrete_logprob(const float *logits, const int32_t *sample, const float *g, int64_t rows, int64_t n,
+                                   float *logp, float *d_logits, void *stream) {
+    MQ_REQUIRE(rows >= 0 && n >= 1, MQ_ERR_SHAPE, "mq_discrete_logprob: bad shape");
+    if (rows == 0) return MQ_OK;
+    MQ_REQUIRE(logits && sample && (logp || d_logits) && (!d_logits || g), MQ_ERR_INVALID,
+               "mq_discrete_logprob: null pointer");
+    MQ_LAUNCH(discrete_logp_kernel, ew_blocks(rows), MQ_NT, 0, stream, logits, sample, g, rows, n, logp, d_logits);
+    MQ_CHECK_LAUNCH("mq_discrete_logprob");
+    return MQ_OK;
+}
+
+// onehot[r, idx[r]] = 1 (rows x n, zero elsewhere): actions as the target rows of the categorical heads
+__global__ void __launch_bounds__(MQ_NT)
+onehot_kernel(const int32_t *__restrict__ idx, int64_t rows, int64_t n, float *__restrict__ out) {
+    EW_LOOP(e, rows * n) { out[e] = (e % n == idx[e / n]) ? 1.0f : 0.0f; }
+}
+
+extern "C" int mq_onehot(const int32_t *idx, int64_t rows, int64_t n, float *out, void *stream) {
+    MQ_REQUIRE(rows >= 0 && n >= 1, MQ_ERR_SHAPE, "mq_onehot: bad shape");
+    if (rows == 0) return MQ_OK;
+    MQ_REQUIRE(idx && out, MQ_ERR_INVALID, "mq_onehot: null pointer");
+    MQ_LAUNCH(onehot_kernel, ew_blocks(rows * n), MQ_NT, 0, stream, idx, rows, n, out);
+    MQ_CHECK_LAUNCH("mq_onehot");
+    return MQ_OK;
+}

@@ -382,7 +382,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     const int tr = p.tile_rows;
     const int64_t ntiles = (n_rows + tr - 1) / tr;
     const int dw_ksteps = tr / 16;
-    const bool gauss = head.kind == MQ_HEAD_GAUSS_LOGP || head.kind == MQ_HEAD_GAUSS_PPO;
+    const bool gauss = mq_head_gauss(head.kind), prob = mq_head_prob(head.kind);
     const int lastact = p.net.act[L - 1];
     const float lastleak = p.net.leak[L - 1];
 
@@ -458,10 +458,10 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
             pend_t[j] = v;
         }
         pend_a = 0.0f; pend_l = 0.0f;
-        if (gauss && tid < TC_ROWS) {
+        if (prob && tid < TC_ROWS) {
             const int src = sIdx[slot * TC_ROWS + tid];
             if (src >= 0) {
-                if (head.kind == MQ_HEAD_GAUSS_PPO) { pend_a = tc_ldg_f32(head.adv + src); pend_l = tc_ldg_f32(head.logp_old + src); }
+                if (mq_head_ppo(head.kind)) { pend_a = tc_ldg_f32(head.adv + src); pend_l = tc_ldg_f32(head.logp_old + src); }
                 else if (head.dy) pend_a = tc_ldg_f32(head.dy + src);
             }
         }
@@ -470,7 +470,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
 #pragma unroll
         for (int j = 0; j < HE; ++j)
             if (hrf[j] >= 0) sHin[(hrf[j] >> 8) * TC_HIN + (hrf[j] & 255)] = pend_t[j];
-        if (gauss && tid < TC_ROWS) { sHin[tid * TC_HIN + 16] = pend_a; sHin[tid * TC_HIN + 17] = pend_l; }
+        if (prob && tid < TC_ROWS) { sHin[tid * TC_HIN + 16] = pend_a; sHin[tid * TC_HIN + 17] = pend_l; }
     };
     TC_MARK(25);
     fetch_idx(blockIdx.x); commit_idx(0);
@@ -589,6 +589,30 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
 #pragma unroll
                     for (int n = 0; n < TC_NO; ++n)
                         if (n < n_out) dz[n] = mq_act_grad(y[n], tgt[n] - expf(y[n] - mx) * inv - head.p0 * y[n], lastact, lastleak);
+                } else if (mq_head_discrete(head.kind)) {
+                    // categorical log-prob (distrib.py:24-32): the target row is the one-hot action
+                    float mx = y[0];
+#pragma unroll
+                    for (int n = 1; n < TC_NO; ++n) if (n < n_out) mx = fmaxf(mx, y[n]);
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < TC_NO; ++n) if (n < n_out) sum += expf(y[n] - mx);
+                    const float lse = mx + logf(sum);
+                    float lp = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < TC_NO; ++n) if (n < n_out) lp += tgt[n] * (y[n] - lse);
+                    if (logp_out && cg == 2) logp_out[gr] = lp;
+                    float w;
+                    if (head.kind == MQ_HEAD_DISCRETE_PPO) {
+                        const float ratio = expf(lp - h_lpold);
+                        const bool kill = (ratio > head.p1 && h_adv > 0.0f) || (ratio < head.p0 && h_adv < 0.0f);
+                        w = kill ? 0.0f : ratio * h_adv;
+                    } else {
+                        w = h_adv;
+                    }
+#pragma unroll
+                    for (int n = 0; n < TC_NO; ++n)
+                        if (n < n_out) dz[n] = mq_act_grad(y[n], w * (tgt[n] - expf(y[n] - lse)), lastact, lastleak);
                 } else if (gauss) {
                     // diagonal Gaussian (distrib.py:61-68): n_out <= 8; columns 8.. carry the logstd terms
                     float acc = 0.0f;
@@ -760,7 +784,7 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
         if (net->out[l] > TC_HID) return 0;
         if (net->act[l] != net->act[0] || (net->act[l] != MQ_ACT_TANH && net->act[l] != MQ_ACT_LRELU)) return 0;
     }
-    const bool gauss = head && (head->kind == MQ_HEAD_GAUSS_LOGP || head->kind == MQ_HEAD_GAUSS_PPO);
+    const bool gauss = head && mq_head_gauss(head->kind);
     if ((gauss || net->logstd_off >= 0) && net->n_out > 8) return 0;
     p->L = L;
     p->k0 = net->n_in <= 16 ? 16 : 32;

@@ -6,6 +6,8 @@ derivative of distrib.py:61-68 in device kernels instead of the `autograd`
 package; `sample` is reparameterised with host-drawn N(0,1) noise (the reference
 draws from an OS-seeded RandomState, distrib.py:46, so the draw itself is an
 input of the kernel).
+
+Discrete (distrib.py:8-39): softmax categorical over a logits layer.
 """
 import numpy as np
 import torch
@@ -88,7 +90,45 @@ class Gauss(object):
 class Discrete(object):
     """Softmax categorical head (mannequin/distrib.py:8-39).
 
-    SURVEY.md 8f rank 1 ("next" row): not built in this round."""
+    `logprob(logits; sample)` = log softmax(logits)[sample] with the reference's backward rule
+    g * (onehot(sample) - softmax(logits)) (distrib.py:24-32) in a device kernel; over an MLP chain the
+    plan compiler turns it into the fused categorical head.  `sample(inps)` draws on the host from an
+    OS-seeded RandomState exactly like the reference (distrib.py:21-22): one action per call."""
 
     def __init__(self, *, logits):
-        raise NotImplementedError("Discrete policy head is not implemented yet (SURVEY.md 8f rank 1)")
+        assert len(logits.shape) == 1
+        n = logits.shape[0]
+        rng = np.random.RandomState()
+
+        def softmax(v):
+            v = np.asarray(v, dtype=np.float64).T
+            v = np.exp(v - np.amax(v, axis=0))
+            v /= np.sum(v, axis=0)
+            return v.T
+
+        def sample(inps):
+            return rng.choice(n, p=softmax(logits(inps)))
+
+        def logprob(logits_v, *, sample):
+            s_host = np.asarray(sample, dtype=np.int32).reshape(-1)
+            rows = len(s_host)
+            lg = logits_v.contiguous().reshape(rows, n)
+            s = D.from_host(s_host, np.int32)
+            logp = torch.empty(rows, dtype=torch.float32, device=lg.device)
+            D.call("mq_discrete_logprob", D.ptr(lg), D.ptr(s), None, rows, n, D.ptr(logp), None, D.stream())
+
+            def bpp(g):
+                d = torch.empty_like(lg)
+                D.call("mq_discrete_logprob", D.ptr(lg), D.ptr(s), D.ptr(g.contiguous().reshape(-1)), rows, n,
+                       None, D.ptr(d), D.stream())
+                return (d.reshape(logits_v.shape),)
+            return logp.reshape(tuple(logits_v.shape)[:-1]), bpp
+        logprob._mq_dev = True
+        logprob._mq_op = ("discrete_logprob",)
+
+        self.logits = logits
+        self.sample = sample
+        self.logprob = Function(logits, f=logprob, shape=())
+        self.n_params = self.logprob.n_params
+        self.get_params = self.logprob.get_params
+        self.load_params = self.logprob.load_params

@@ -25,7 +25,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_GAUSS_PPO, MQ_F32, MQ_F64, MqHead
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, MQ_F64, MqHead
 from ._normalize import RunningNormalize
 from .basicnet import normed_columns
 
@@ -109,13 +109,18 @@ class _Net(object):
 class PPOUpdater(object):
     def __init__(self, n_obs, n_act, *, hid=64, n_hid=2, gam=0.99, lam=0.95, pol_lr=3e-4, val_lr=3e-3,
                  horizon=10, clip=(0.8, 1.2), norm_horizon=2, state_dtype="float32",
-                 policy_params=None, value_params=None):
+                 policy_params=None, value_params=None, discrete=False):
         widths = [hid] * n_hid
         acts = [ACT_TANH] * n_hid + [ACT_NONE]
-        pnet = _lib.make_net(n_obs, widths + [n_act], acts, logstd=True)
+        # discrete=True: categorical policy over n_act actions (benchmarks/policy.py:15-17, distrib.Discrete);
+        # `act` is then an int32 vector and travels to the kernels as one-hot rows
+        self.discrete = bool(discrete)
+        pnet = _lib.make_net(n_obs, widths + [n_act], acts, logstd=not self.discrete)
         vnet = _lib.make_net(n_obs, widths + [1], acts)
         if policy_params is None:                                   # policy.py:7-27, Gauss logstd zeros
-            policy_params = np.concatenate([init_mlp(n_obs, widths + [n_act], 0.1), np.zeros(n_act, np.float32)])
+            policy_params = init_mlp(n_obs, widths + [n_act], 0.1)
+            if not self.discrete:
+                policy_params = np.concatenate([policy_params, np.zeros(n_act, np.float32)])
         if value_params is None:                                    # gae.py:12-18
             value_params = init_mlp(n_obs, widths + [1], 0.1)
         assert len(policy_params) == pnet.n_params and len(value_params) == vnet.n_params
@@ -140,7 +145,13 @@ class PPOUpdater(object):
         done u8[N], val_idx / pol_idx i32[steps, mb].  Returns device (adv, ret)."""
         lib = _lib.lib()
         n = rew.numel()
-        assert obs.numel() == (n + 1) * self.n_obs and act.numel() == n * self.n_act
+        assert obs.numel() == (n + 1) * self.n_obs
+        if self.discrete:
+            assert act.numel() == n and act.dtype == torch.int32
+            onehot = self._buf("onehot", n * self.n_act)
+            D.call("mq_onehot", D.ptr(act), n, self.n_act, D.ptr(onehot), D.stream())
+            act = onehot
+        assert act.numel() == n * self.n_act
         pol, val = self.policy, self.value
         value = self._buf("value", n + 1)
         adv, ret = self._buf("adv", n), self._buf("ret", n)
@@ -172,7 +183,7 @@ class PPOUpdater(object):
         D.call("mq_fused_forward", ctypes.byref(pol.net), D.ptr(pol.theta), D.ptr(obs), None, n, None,
                D.ptr(act), D.ptr(logp0), D.stream())
         head = MqHead()
-        head.kind, head.p0, head.p1 = HEAD_GAUSS_PPO, self.clip[0], self.clip[1]
+        head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
         head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
         pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
         if concurrent:
@@ -182,7 +193,7 @@ class PPOUpdater(object):
     def update(self, obs, act, rew, done, val_idx, pol_idx):
         """Host arrays in, new (policy_params, value_params) host arrays out (end-to-end call)."""
         up = lambda a, dt: D.from_host(np.ascontiguousarray(a, dtype=dt))
-        self.update_dev(up(obs, np.float32), up(act, np.float32), up(rew, np.float32),
+        self.update_dev(up(obs, np.float32), up(act, np.int32 if self.discrete else np.float32), up(rew, np.float32),
                         up(np.asarray(done, dtype=np.uint8), np.uint8), up(val_idx, np.int32),
                         up(pol_idx, np.int32))
         return D.to_host(self.policy.theta), D.to_host(self.value.theta)

@@ -470,3 +470,34 @@ def es_generation(theta, spec, opt, norm, noise, obs, ret_coef, lr=0.01):
     grad = (np.asarray(noise, np.float64) * r[:, None]).mean(axis=0)
     opt.apply_gradient(grad, lr=lr)
     return opt.get_value().astype(np.float32), rets, r
+
+
+# ---------------------------------------------------------------------------------------------------
+# Categorical policy head: mannequin/distrib.py:8-39
+def discrete_logprob(logits, sample):
+    """log softmax(logits)[sample] per row and the softmax (distrib.py:15-19,24-30); fp64."""
+    y = np.asarray(logits, dtype=np.float64)
+    y = y.reshape(-1, y.shape[-1])
+    s = np.asarray(sample, dtype=np.int64).reshape(-1)
+    z = y - y.max(axis=1, keepdims=True)
+    p = np.exp(z)
+    p /= p.sum(axis=1, keepdims=True)
+    return np.log(p[np.arange(len(s)), s]), p
+
+
+def discrete_logprob_grad(theta, spec, obs, sample, g, outs=None):
+    """d/dtheta mean_b g_b logp_b for logits = mlp(obs): backward rule g*(onehot - p) (distrib.py:31)."""
+    outs = mlp_forward(theta, spec, obs) if outs is None else outs
+    _, p = discrete_logprob(outs[-1], sample)
+    onehot = np.eye(p.shape[1])[np.asarray(sample, dtype=np.int64).reshape(-1)]
+    dy = np.asarray(g, dtype=np.float64).reshape(-1, 1) * (onehot - p)
+    return mlp_backward(theta, spec, obs, outs, dy)
+
+
+def ppo_discrete_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4, lo=0.8, hi=1.2):
+    """benchmarks/ppo.py:33-40 with the categorical policy of benchmarks/policy.py:15-17."""
+    outs = mlp_forward(theta, spec, obs)
+    logp, _ = discrete_logprob(outs[-1], act)
+    g = ppo_clip_weight(logp, logp_old, adv, lo, hi).astype(np.float32)
+    opt.apply_gradient(discrete_logprob_grad(theta, spec, obs, act, g, outs), lr=lr)
+    return opt.get_value().astype(np.float32)

@@ -285,6 +285,27 @@ def gen_gauss(out):
     out["gauss_sample_g"], out["gauss_sample_grad"] = gs, bpp(gs)
 
 
+def gen_discrete(out):
+    """mannequin.distrib.Discrete over the cartpole-shaped policy of benchmarks/policy.py:14-25 (no autograd needed:
+    the reference's own forward and backward rule, distrib.py:24-32)."""
+    import mannequin.basicnet as bn
+    from mannequin.distrib import Discrete
+    rs = np.random.RandomState(18)
+    np.random.seed(19)
+    p = bn.Input(4)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3, init=0.1)
+    pol = Discrete(logits=p)
+    obs = rs.randn(64, 4).astype(np.float32)
+    act = rs.randint(3, size=64).astype(np.int32)
+    g = rs.randn(64).astype(np.float32)
+    logp, bpp = pol.logprob.evaluate(obs, sample=act)
+    out["disc_theta"], out["disc_obs"], out["disc_act"], out["disc_g"] = pol.get_params(), obs, act, g
+    out["disc_logits"] = np.asarray(pol.logits(obs))
+    out["disc_logp"], out["disc_grad"] = np.asarray(logp), bpp(g)
+
+
 def gen_ppo(out, gym):
     """Run benchmarks/ppo.py:run() itself for two chunks and record everything."""
     import mannequin
@@ -431,7 +452,7 @@ def main():
 
     groups = {}
     for name, fn in (("nets", gen_nets), ("adam", gen_adam), ("norm", gen_norm),
-                     ("trajectory", gen_trajectory), ("gauss", gen_gauss)):
+                     ("trajectory", gen_trajectory), ("gauss", gen_gauss), ("discrete", gen_discrete)):
         d = {}
         fn(d)
         groups[name] = d

@@ -688,5 +688,78 @@ def case_reduce_step(B):
             assert np.array_equal(B.down(a), B.down(b)), "reduce_step fp32 state n=%d" % n
 
 
+def case_discrete(B, batches=(64, 300, 9000)):
+    """Categorical policy head (mannequin/distrib.py:8-39): per-op kernel, fused heads (FFMA and, for the
+    9000-row batch, the tcgen05 kernel) against the reference fixture and the oracle."""
+    lib = B.lib
+    rs = np.random.RandomState(31)
+    g = golden("discrete")
+    spec = O.mlp_spec(4, [64, 64, 3], [1, 1, 0])
+    net = net_of(spec)
+    theta, obs, act, w = g["disc_theta"], g["disc_obs"], g["disc_act"], g["disc_g"]
+    # per-op kernel on the reference's logits
+    hl, ha, hw = B.up(g["disc_logits"].astype(np.float32)), B.up(act.astype(np.int32)), B.up(w)
+    lp, dl = B.zeros(64, np.float32), B.zeros((64, 3), np.float32)
+    ok(B, lib.mq_discrete_logprob(B.ptr(hl), B.ptr(ha), B.ptr(hw), 64, 3, B.ptr(lp), B.ptr(dl), B.stream))
+    close(B.down(lp), g["disc_logp"], rtol=2e-5, what="discrete logp vs reference")
+    wlp, p = O.discrete_logprob(g["disc_logits"], act)
+    close(B.down(dl), w[:, None] * (np.eye(3)[act] - p), what="discrete d_logits")
+    # fused: forward log-prob and the gradient, against the reference's own backprop
+    onehot = B.zeros((64, 3), np.float32)
+    ok(B, lib.mq_onehot(B.ptr(ha), 64, 3, B.ptr(onehot), B.stream))
+    assert np.array_equal(B.down(onehot), np.eye(3, dtype=np.float32)[act])
+    ht, ho = B.up(theta), B.up(obs)
+    ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(ho), None, 64, None, B.ptr(onehot), B.ptr(lp), B.stream))
+    close(B.down(lp), g["disc_logp"], rtol=2e-5, what="fused discrete logp vs reference")
+    wsb = lib.mq_fused_ws_bytes(net, max(batches))
+    ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
+    h = head(B, L.HEAD_DISCRETE_LOGP, dy=hw, target=onehot)
+    ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad), None,
+                            B.ptr(lp), B.ptr(ws), wsb, B.stream))
+    close(B.down(grad), g["disc_grad"], rtol=3e-5, atol_scale=3e-6, what="fused discrete grad vs reference")
+    # PPO clip weights with gathered rows, several batch sizes
+    n = 12000
+    o = rs.randn(n, 4).astype(np.float32)
+    a = rs.randint(3, size=n).astype(np.int32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_all, _ = O.discrete_logprob(O.mlp_forward(theta, spec, o)[-1], a)
+    lp_old = (lp_all + rs.randn(n) * 0.2).astype(np.float32)
+    ho, hoh, hadv, hlp = B.up(o), B.up(np.eye(3, dtype=np.float32)[a]), B.up(adv), B.up(lp_old)
+    for mb in batches:
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        h = head(B, L.HEAD_DISCRETE_PPO, p0=0.8, p1=1.2, target=hoh, adv=hadv, logp_old=hlp)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+        outs = O.mlp_forward(theta, spec, o[idx])
+        lpn, _ = O.discrete_logprob(outs[-1], a[idx])
+        wgt = O.ppo_clip_weight(lpn, lp_old[idx], adv[idx])
+        assert (wgt == 0).any() and (wgt != 0).any()
+        close(B.down(grad), O.discrete_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs), rtol=3e-5,
+              atol_scale=3e-6, what="fused discrete ppo grad mb=%d" % mb)
+    # the persistent chain (benchmarks/ppo.py:29-40 for a cartpole-shaped policy): 5 dependent 64-row steps
+    steps, mbs = 5, 64
+    tab = rs.randint(n, size=(steps, mbs)).astype(np.int32)
+    opt = O.AdamO(theta, horizon=10)
+    th_ref = theta.copy()
+    for s_ in range(steps):
+        th_ref = O.ppo_discrete_policy_step(th_ref, spec, opt, o[tab[s_]], a[tab[s_]], adv[tab[s_]], lp_old[tab[s_]])
+    np_ = spec["n_params"]
+    ht2 = B.up(theta.copy())
+    val, m, v = B.up(theta.astype(np.float64)), B.zeros(np_, np.float64), B.zeros(np_, np.float64)
+    tw = (ctypes.c_double * 2)(0.0, 0.0)
+    h = head(B, L.HEAD_DISCRETE_PPO, p0=0.8, p1=1.2, target=hoh, adv=hadv, logp_old=hlp)
+    ok(B, lib.mq_fused_train(net, B.ptr(ht2), B.ptr(val), B.ptr(m), B.ptr(v), L.MQ_F64, B.ptr(ho), ctypes.byref(h),
+                             B.ptr(B.up(tab)), steps, mbs, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
+    err = np.max(np.abs(B.down(ht2) - th_ref))
+    assert err < 2e-6 * (1 + steps) + 1e-6, err
+    assert np.max(np.abs(B.down(ht2) - theta)) > 1e-4
+    # a categorical head on a net WITH logstd parameters is refused
+    h = head(B, L.HEAD_DISCRETE_LOGP, dy=hw, target=onehot)
+    gnet = L.make_net(4, [64, 64, 3], [1, 1, 0], logstd=True)
+    assert lib.mq_fused_grad(gnet, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0, B.ptr(grad), None, None,
+                             B.ptr(ws), wsb, B.stream) == L.MQ_ERR_INVALID
+
+
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_fused_heads,
-             case_fused_gauss_ppo, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_discrete, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]

@@ -393,6 +393,28 @@ def test_gauss_policy_against_reference_fixture():
     assert_close(grad[-3:], (gs * noise).sum(axis=0) / 5, rtol=1e-4, atol_scale=1e-5)
 
 
+def test_discrete_policy_against_reference_fixture():
+    """Discrete(logits=net).logprob / .sample against the real reference (golden/discrete.npz): the fused plan,
+    the node-by-node graph path (single sample) and the sampler."""
+    import mannequin2_b200.basicnet as bn
+    from mannequin2_b200.distrib import Discrete
+    g = load_golden("discrete")
+    p = bn.Input(4)
+    for _ in range(2):
+        p = bn.Tanh(bn.Affine(p, 64))
+    p = bn.Affine(p, 3, init=0.1)
+    pol = Discrete(logits=p)
+    assert pol.n_params == len(g["disc_theta"])
+    pol.load_params(g["disc_theta"])
+    logp, bpp = pol.logprob.evaluate(g["disc_obs"], sample=g["disc_act"])
+    assert_close(logp, g["disc_logp"], rtol=2e-5, atol_scale=1e-6)
+    assert_close(np.asarray(bpp(g["disc_g"])), g["disc_grad"], rtol=3e-5, atol_scale=3e-6)
+    l1, _ = pol.logprob.evaluate(g["disc_obs"][0], sample=g["disc_act"][0])
+    assert abs(float(l1) - g["disc_logp"][0]) < 1e-4
+    draws = [pol.sample(g["disc_obs"][0]) for _ in range(20)]
+    assert all(0 <= int(a) < 3 for a in draws)
+
+
 def test_trajectory_device_gather_and_discounted():
     from mannequin2_b200 import Trajectory, discounted
     g = load_golden("trajectory")

@@ -195,6 +195,20 @@ def test_gauss_vs_reference_and_fd():
     assert_close(grad, g["gauss_sample_grad"], rtol=3e-5, atol_scale=3e-6)
 
 
+def test_discrete_vs_reference():
+    """Categorical head restatement against mannequin.distrib.Discrete run here (golden/discrete.npz)."""
+    g = load_golden("discrete")
+    spec = O.mlp_spec(4, [64, 64, 3], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    assert spec["n_params"] == len(g["disc_theta"])
+    outs = O.mlp_forward(g["disc_theta"], spec, g["disc_obs"])
+    assert_close(outs[-1], g["disc_logits"], rtol=2e-5, atol_scale=2e-6)
+    logp, p = O.discrete_logprob(outs[-1], g["disc_act"])
+    assert_close(logp, g["disc_logp"], rtol=2e-5, atol_scale=1e-6)
+    assert np.allclose(p.sum(axis=1), 1.0)
+    grad = O.discrete_logprob_grad(g["disc_theta"], spec, g["disc_obs"], g["disc_act"], g["disc_g"], outs)
+    assert_close(grad, g["disc_grad"], rtol=3e-5, atol_scale=3e-6)
+
+
 def test_vae_heads_fd():
     rs = np.random.RandomState(2)
     m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
