@@ -92,6 +92,8 @@ int mq_debug_use_chain_grad(int on);
 int mq_debug_set_chain_warps(int nw);
 /* developer aid: tcgen05 path of mq_fused_grad / mq_fused_forward: 0 never, 1 automatic (batch >= 8192), 2 whenever the net fits */
 int mq_debug_set_tc_mode(int mode);
+/* developer aid: tcgen05 GEMM for wide layers: 0 never, 1 automatic (>= 2^26 multiply-adds), 2 whenever possible */
+int mq_debug_set_gemm_tc_mode(int mode);
 int mq_version(void);
 int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
 

@@ -11,32 +11,7 @@
 //   EPI_SCALE    C = alpha*acc                         (dW = x^T g / B, lines 48-51)
 //   EPI_BIAS_ACT C = act(acc + bias[n])                (add 11-19, relu 53-56, tanh 58-60)
 //   EPI_ACT_GRAD C = act'(Y[m,n]) * acc                (g W^T through the previous activation)
-#include "mq_common.cuh"
-
-#define GEMM_BK 16
-#define EPI_SCALE 0
-#define EPI_BIAS_ACT 1
-#define EPI_ACT_GRAD 2
-
-struct GemmArgs {
-    const float *a; int64_t a_rs, a_cs;
-    const float *b; int64_t b_rs, b_cs;
-    const int32_t *idx;      // gather on the batch axis of A (or NULL)
-    int idx_on_k;            // 0: index applies to A rows (m), 1: to A columns (k)
-    float *c;                // [M,N] row-major (or split-K partials [S,M,N])
-    int64_t m, n, k;
-    int64_t k_per_split;
-    float alpha;
-    int epi, act; float leak;
-    const float *bias;       // EPI_BIAS_ACT
-    const float *y;          // EPI_ACT_GRAD, [M,N] row-major
-};
-
-__device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int64_t m, int64_t n) {
-    if (g.epi == EPI_BIAS_ACT) return mq_act_apply(acc + g.bias[n], g.act, g.leak);
-    if (g.epi == EPI_ACT_GRAD) return mq_act_grad(g.y[m * g.n + n], acc, g.act, g.leak);
-    return g.alpha * acc;
-}
+#include "mq_gemm.cuh"
 
 template <int BM, int BN, bool SPLIT>
 __global__ void __launch_bounds__(MQ_NT)
@@ -146,10 +121,37 @@ gemm_splitk_finish_kernel(GemmArgs g, const float *__restrict__ partial, int spl
     }
 }
 
-// Decide tile size and split-K; `ws` may be NULL (then no split).
+int mq_gemm_tc_launch(const GemmArgs &g, int64_t splits, void *stream);      // mq_gemm_tc.cu
+
+// Decide kernel, tile size and split-K; `ws` may be NULL (then no split).
 static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, void *stream, const char *what) {
     if (g.m <= 0 || g.n <= 0) return MQ_OK;
     const int sms = mq_sm_count();
+    {   // large problems: tcgen05 kernel on 128 x 128 tiles (mq_gemm_tc.cu), same epilogues / gather / split-K
+        GemmArgs gt = g;
+        const int64_t tiles = mq_ceil_div(g.m, 128) * mq_ceil_div(g.n, 128);
+        int64_t splits = 1;
+        if (ws && 2 * tiles <= sms && g.k >= 1024) {
+            splits = sms / tiles;
+            if (splits > g.k / 256) splits = g.k / 256;
+            while (splits > 1 && splits * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) --splits;
+            if (splits < 1) splits = 1;
+        }
+        gt.k_per_split = mq_round_up(mq_ceil_div(g.k > 0 ? g.k : 1, splits), 32);
+        splits = mq_ceil_div(g.k > 0 ? g.k : 1, gt.k_per_split);
+        if (splits > 1) gt.c = (float *)ws;
+        const int rc = mq_gemm_tc_launch(gt, splits, stream);
+        if (rc == MQ_OK) {
+            if (splits > 1) {
+                int64_t nb = mq_ceil_div(g.m * g.n, MQ_NT);
+                if (nb > sms * 8) nb = sms * 8;
+                MQ_LAUNCH(gemm_splitk_finish_kernel, (unsigned)nb, MQ_NT, 0, stream, g, (const float *)ws, (int)splits, g.c);
+            }
+            MQ_CHECK_LAUNCH(what);
+            return MQ_OK;
+        }
+        if (rc != MQ_ERR_UNSUPPORTED) return rc;
+    }
     const bool big = mq_ceil_div(g.m, 64) * mq_ceil_div(g.n, 64) >= sms / 2;
     const int bm = big ? 64 : 32;
     const int64_t tiles = mq_ceil_div(g.m, bm) * mq_ceil_div(g.n, bm);

@@ -127,6 +127,14 @@ def test_large_batch_fused_grad_is_permutation_and_split_consistent(backend):
     assert np.array_equal(full, again)                                  # deterministic reduction order
     halves = 0.5 * (grad_of(0, n // 2).astype(np.float64) + grad_of(n // 2, n))
     K.close(full, halves, rtol=1e-4, atol_scale=1e-5, what="split consistency")
+    # the same batch four times over (262,144 rows: 14 tiles per CTA, so the tensor-core kernel folds its TMEM
+    # accumulators into memory three times on the way) gives the same mean gradient
+    idx4 = B.up(np.tile(np.arange(n, dtype=np.int32), 4))
+    g4 = B.zeros(5126, np.float32)
+    h = K.head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+    K.ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(idx4), 4 * n, ctypes.byref(h), 1.0 / (4 * n), B.ptr(g4),
+                              None, None, B.ptr(ws), wsb, B.stream))
+    K.close(B.down(g4), full, rtol=1e-5, atol_scale=2e-6, what="4x repeated batch")
     # and against the oracle on a 4096-row sample of the same data
     idx = np.arange(4096)
     lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
