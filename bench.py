@@ -250,7 +250,7 @@ class PPOLargeWorkload(object):
         self.torch.cuda.current_stream().synchronize()
 
     def launches_per_step(self):
-        return 11 + 2 * self.steps_per_net * 3      # (+ NCCL all-reduces, not ours, when sharded)
+        return 11 + 2 * self.steps_per_net * 2      # per optimiser step: gradient kernel + reduce/all-reduce/Adam kernel
 
     def dominant_kernel(self, peaks):
         """fused_grad_kernel on one 65,536-row policy minibatch, timed alone on its stream."""
@@ -534,6 +534,23 @@ def kernel_sweep(peaks):
     ms = timeit(nrm)
     out["normalize_update_apply_64Mi"] = dict(bytes_per_elem=16, ms=ms, gbs=16.0 * n / ms / 1e6,
                                               frac=16.0 * n / ms / 1e6 / peaks["hbm"])
+    del r, vv, d, adv, ret, o
+    # wide Affine layers (BASELINE configs[4]: VAE 784-400-...-784 at batch 4096): y = x W, dx = g W^T, dW = x^T g through
+    # mq_gemm -- tcgen05 kernel (three bf16 planes per operand, fp32 parity) vs the FFMA kernel it replaces
+    bsz, kin, nout = 4096, 784, 400
+    x, w, gy = torch.randn(bsz, kin, device=dev), torch.randn(kin, nout, device=dev), torch.randn(bsz, nout, device=dev)
+    y, dx, dw = torch.empty(bsz, nout, device=dev), torch.empty(bsz, kin, device=dev), torch.empty(kin, nout, device=dev)
+    def three():
+        D.call("mq_gemm", D.ptr(x), kin, 1, D.ptr(w), nout, 1, D.ptr(y), bsz, nout, kin, 1.0, D.stream())      # y = x W
+        D.call("mq_gemm", D.ptr(gy), nout, 1, D.ptr(w), 1, nout, D.ptr(dx), bsz, kin, nout, 1.0, D.stream())    # dx = g W^T
+        D.call("mq_gemm", D.ptr(x), 1, kin, D.ptr(gy), nout, 1, D.ptr(dw), kin, nout, bsz, 1.0, D.stream())     # dW = x^T g
+    flops = 3 * 2.0 * bsz * kin * nout
+    for mode, key in ((1, "affine_4096x784x400_fwd_dx_dw_tcgen05"), (0, "affine_4096x784x400_fwd_dx_dw_ffma")):
+        lib.mq_debug_set_gemm_tc_mode(mode)
+        ms = timeit(three, reps=8)
+        out[key] = dict(flop=flops, ms=ms, fp32_tflops=flops / ms / 1e9,
+                        frac_of_bf16_peak=flops / ms / 1e9 / peaks["bf16"], issued_bf16_tflops=(6 * flops / ms / 1e9) if mode else None)
+    lib.mq_debug_set_gemm_tc_mode(1)
     return out
 
 
@@ -615,7 +632,8 @@ def measure(wl, steps, warmup, world, rank, flush):
 
 
 PARALLELISM = {"ppo_large": "dp%d: every rank trains on its own 2^20-transition shard, global minibatch = %d x 65,536 "
-                            "rows, one NCCL all-reduce of the flat gradient per optimiser step",
+                            "rows, the flat gradient is all-reduced over NVLink peer memory inside the reduce+Adam kernel "
+                            "(one exchange per optimiser step, no NCCL call on the step path)",
                "ppo": "%d independent replicas (a 64-row minibatch does not shard)",
                "mlp": "%d independent replicas (batch 128 does not shard)",
                "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce"}

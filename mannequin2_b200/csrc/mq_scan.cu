@@ -148,6 +148,7 @@ scan_carry_kernel(const Lin<T> *__restrict__ agg, int64_t nb, T *__restrict__ ca
 }
 
 // ---- single-pass variant -----------------------------------------------------------------------------
+#ifndef MQ_EMU
 #define SCAN_PAD(i) ((i) + ((i) >> 5))             // conflict-free 8-consecutive-per-thread access
 
 struct GaeStage {
@@ -310,9 +311,14 @@ scan_lookback_kernel(E el, int64_t n, ScanTile<T> *__restrict__ tiles, unsigned 
     el.flush(sm, lo, cnt);
 }
 
+#else
+struct GaeStage { const float *rew, *val; const uint8_t *done; float *adv, *ret; float g, gl; };
+struct DiscStage { const double *in; double *out; double keep, step; };
+#endif
+
 extern "C" int64_t mq_scan_ws_bytes(int64_t n) {
     const int64_t nb = mq_ceil_div(n < 1 ? 1 : n, SCAN_CHUNK);
-    return nb * (int64_t)sizeof(ScanTile<double>) + 64;
+    return nb * 32 + 64;                  // one 32-byte descriptor per chunk (ScanTile<double>)
 }
 
 #ifndef MQ_EMU

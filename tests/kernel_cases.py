@@ -749,8 +749,9 @@ def case_discrete(B, batches=(64, 300, 9000)):
     val, m, v = B.up(theta.astype(np.float64)), B.zeros(np_, np.float64), B.zeros(np_, np.float64)
     tw = (ctypes.c_double * 2)(0.0, 0.0)
     h = head(B, L.HEAD_DISCRETE_PPO, p0=0.8, p1=1.2, target=hoh, adv=hadv, logp_old=hlp)
+    htab = B.up(tab)
     ok(B, lib.mq_fused_train(net, B.ptr(ht2), B.ptr(val), B.ptr(m), B.ptr(v), L.MQ_F64, B.ptr(ho), ctypes.byref(h),
-                             B.ptr(B.up(tab)), steps, mbs, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
+                             B.ptr(htab), steps, mbs, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
     err = np.max(np.abs(B.down(ht2) - th_ref))
     assert err < 2e-6 * (1 + steps) + 1e-6, err
     assert np.max(np.abs(B.down(ht2) - theta)) > 1e-4
