@@ -17,8 +17,8 @@
 // 128 (32 instructions); the blocks are then added in registers (round to nearest) by the warps that own the rows,
 // from the accumulator set the tensor pipe is NOT writing (two sets of 256 TMEM columns alternate).
 //
-// One CTA (256 threads) per 128 x 128 tile of C.  K advances in chunks of 32 through a ring of 3 shared-memory
-// stages (48 KB each): while the tensor pipe works on stage s (tcgen05.commit -> the stage's mbarrier when done),
+// One CTA (512 threads) per 128 x 128 tile of C.  K advances in chunks of 32 through a ring of 3 shared-memory
+// stages (60 KB each): while the tensor pipe works on stage s (tcgen05.commit -> the stage's mbarrier when done),
 // all warps convert the next chunk, whose global loads were issued one chunk earlier.
 #include "mq_gemm.cuh"
 #include "mq_tc.cuh"
@@ -30,12 +30,17 @@
 #define GT_KC 32                      // K per stage: 4 chunks of 8, 2 MMA K steps
 #define GT_STAGES 3
 #define GT_CPB 4                      // chunks per TMEM accumulation block (K = 128)
-#define GT_CHUNK 2048                 // 128 rows x 16 B
-#define GT_A_STAGE (3 * 4 * GT_CHUNK)  // [plane][k chunk][row][8 k]
-#define GT_B_STAGE (4 * 3 * GT_CHUNK)  // [k chunk][plane][n][8 k]
+// operand stage = [plane 3][row group 16][k chunk 4][8 rows][8 k]: core matrices of 128 B, k chunks 160 B apart and
+// row groups 640 B apart (the 32-byte skew makes the 16-byte stores of a quarter warp -- two rows x four k chunks when
+// lanes run along k -- land in eight different bank groups); the planes of B are thereby side by side along N
+#define GT_KCS 160                    // descriptor leading byte offset: between the k chunks of a row group
+#define GT_RGS (4 * GT_KCS)           // descriptor stride byte offset: between 8-row groups
+#define GT_PLANE (16 * GT_RGS)
+#define GT_A_STAGE (3 * GT_PLANE)
+#define GT_B_STAGE (3 * GT_PLANE)
 #define GT_STAGE_BYTES (GT_A_STAGE + GT_B_STAGE)
 #define GT_SMEM (GT_STAGES * GT_STAGE_BYTES)
-#define GT_NT 256
+#define GT_NT 512
 
 // 8 consecutive k of one row / column -> registers.  KFAST: k is the unit-stride axis of the operand.
 template <bool KFAST>
@@ -91,19 +96,22 @@ gemm_tc_kernel(GemmArgs g) {
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
     const uint32_t sbase = tc_smem_u32(smem);
 
-    // this thread's two A items and two B items of a chunk: (outer index within the tile, k chunk 0..3)
-    int a_out[2], a_kc[2], b_out[2], b_kc[2];
+    // this thread's A item and B item of a chunk: (outer index within the tile, k chunk 0..3); lanes run along the
+    // unit-stride axis of the operand so that the global loads are coalesced (ncu: with one row per lane the L1 tag
+    // stage, 64 % busy, was the limiter)
+    constexpr int NI = 128 * 4 / GT_NT;
+    int a_out[NI], a_kc[NI], b_out[NI], b_kc[NI];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NI; ++j) {
         const int it = tid + j * GT_NT;
         if (A_KFAST) { a_out[j] = it >> 2; a_kc[j] = it & 3; } else { a_out[j] = it & 127; a_kc[j] = it >> 7; }
         if (B_KFAST) { b_out[j] = it >> 2; b_kc[j] = it & 3; } else { b_out[j] = it & 127; b_kc[j] = it >> 7; }
     }
     // global row of A after the optional gather on the batch axis; validity of the rows / columns
-    int64_t a_row[2];
-    bool a_ok[2], b_ok[2];
+    int64_t a_row[NI];
+    bool a_ok[NI], b_ok[NI];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NI; ++j) {
         const int64_t gm = m0 + a_out[j];
         a_ok[j] = gm < g.m;
         a_row[j] = (a_ok[j] && g.idx && !g.idx_on_k) ? (int64_t)g.idx[gm] : gm;
@@ -113,11 +121,11 @@ gemm_tc_kernel(GemmArgs g) {
                        (k_begin % 4 == 0);
     const bool b_vec = B_KFAST && (g.b_cs % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.b) & 15) == 0) && (k_begin % 4 == 0);
 
-    float ra[2][8], rb[2][8];
+    float ra[NI][8], rb[NI][8];
     auto load_chunk = [&](int c) {
         const int64_t kt = k_begin + (int64_t)c * GT_KC;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NI; ++j) {
             const int64_t k0 = kt + a_kc[j] * 8;
             if (g.idx && g.idx_on_k) {                  // gather along K (dW = x[idx]^T g): element-wise
 #pragma unroll
@@ -132,27 +140,28 @@ gemm_tc_kernel(GemmArgs g) {
     auto store_chunk = [&](int stage) {
         unsigned char *sa = smem + stage * GT_STAGE_BYTES, *sb = sa + GT_A_STAGE;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            gt_store_item(sa + a_kc[j] * GT_CHUNK + (a_out[j] >> 3) * 128 + (a_out[j] & 7) * 16, 4 * GT_CHUNK, ra[j]);
-            gt_store_item(sb + b_kc[j] * (3 * GT_CHUNK) + (b_out[j] >> 3) * 128 + (b_out[j] & 7) * 16, GT_CHUNK, rb[j]);
+        for (int j = 0; j < NI; ++j) {
+            gt_store_item(sa + (a_out[j] >> 3) * GT_RGS + a_kc[j] * GT_KCS + (a_out[j] & 7) * 16, GT_PLANE, ra[j]);
+            gt_store_item(sb + (b_out[j] >> 3) * GT_RGS + b_kc[j] * GT_KCS + (b_out[j] & 7) * 16, GT_PLANE, rb[j]);
         }
     };
 
-    // register accumulators of this thread: row quarter*32 + lane, 64 columns
+    // register accumulators of this thread: row quarter*32 + lane, GT_CPT columns
+    constexpr int GT_CPT = GT_BN / (GT_NT / 128);
     const int quarter = warp & 3, cgp = warp >> 2;
     const uint32_t tl = tm + ((uint32_t)(quarter * 32) << 16);
-    float acc[64];
+    float acc[GT_CPT];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+    for (int j = 0; j < GT_CPT; ++j) acc[j] = 0.0f;
     uint32_t acc_parity = 0;            // bit s: parity to wait for on accumulator set s
     auto flush_block = [&](int set) {   // acc += the two column blocks of accumulator set `set`
         tc_wait(tc_smem_u32(&s_bar[GT_STAGES + set]), (acc_parity >> set) & 1u);
         acc_parity ^= 1u << set;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < GT_CPT / 16; ++q) {
             float v[16], w[16];
-            tc_ld16(tl + set * 256 + cgp * 64 + q * 16, v);
-            tc_ld16(tl + set * 256 + GT_BN + cgp * 64 + q * 16, w);
+            tc_ld16(tl + set * 256 + cgp * GT_CPT + q * 16, v);
+            tc_ld16(tl + set * 256 + GT_BN + cgp * GT_CPT + q * 16, w);
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[q * 16 + j] += v[j] + w[j];
         }
@@ -178,9 +187,9 @@ gemm_tc_kernel(GemmArgs g) {
         if (warp == 0) {
             if (tc_elect_one()) {
                 const uint32_t a0 = sbase + stage * GT_STAGE_BYTES, b0 = a0 + GT_A_STAGE;
-                const uint32_t ahi = tc_desc_hi(128u), bhi = tc_desc_hi(128u);
-                uint32_t alo = tc_desc_lo(a0, GT_CHUNK), blo = tc_desc_lo(b0, 3 * GT_CHUNK);
-                const uint32_t ap16 = (4 * GT_CHUNK) >> 4, bp16 = GT_CHUNK >> 4;
+                const uint32_t ahi = tc_desc_hi(GT_RGS), bhi = tc_desc_hi(GT_RGS);
+                uint32_t alo = tc_desc_lo(a0, GT_KCS), blo = tc_desc_lo(b0, GT_KCS);
+                const uint32_t ap16 = GT_PLANE >> 4, bp16 = GT_PLANE >> 4;
                 const uint32_t id2 = tc_idesc(GT_BM, 2 * GT_BN, 0, 0), id1 = tc_idesc(GT_BM, GT_BN, 0, 0);
                 const uint32_t d = tm + set * 256;
 #pragma unroll
@@ -189,8 +198,8 @@ gemm_tc_kernel(GemmArgs g) {
                     tc_mma(d, alo + ap16, ahi, blo, bhi, id2, 1u);                                 // A_1 x [B_0|B_1]
                     tc_mma(d, alo, ahi, blo + 2 * bp16, bhi, id1, 1u);                             // A_0 x B_2
                     tc_mma(d, alo + 2 * ap16, ahi, blo, bhi, id1, 1u);                             // A_2 x B_0
-                    alo += (2 * GT_CHUNK) >> 4;
-                    blo += (2 * 3 * GT_CHUNK) >> 4;
+                    alo += (2 * GT_KCS) >> 4;
+                    blo += (2 * GT_KCS) >> 4;
                 }
                 tc_commit(tc_smem_u32(&s_bar[stage]));
                 if (c % GT_CPB == GT_CPB - 1 || c == n_chunks - 1) tc_commit(tc_smem_u32(&s_bar[GT_STAGES + set]));
@@ -209,8 +218,8 @@ gemm_tc_kernel(GemmArgs g) {
         const int64_t gm = m0 + quarter * 32 + lane;
         if (gm < g.m) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int64_t gn = n0 + cgp * 64 + j;
+            for (int j = 0; j < GT_CPT; ++j) {
+                const int64_t gn = n0 + cgp * GT_CPT + j;
                 if (gn >= g.n) continue;
                 if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = acc[j];
                 else g.c[gm * g.n + gn] = gemm_epilogue(g, acc[j], gm, gn);
