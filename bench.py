@@ -482,7 +482,59 @@ class ESWorkload(object):
                                                 self.noise[:256], self.obs, self.coef)
 
 
-WORKLOADS = {"ppo": PPOWorkload, "ppo_large": PPOLargeWorkload, "mlp": MLPWorkload, "es": ESWorkload}
+class VAEWorkload(object):
+    """BASELINE.json configs[4]: mnist/vae.py step at the BASELINE shape -- encoder 784-400-(20+20), decoder
+    20-400-(784+784), Gaussian reparameterisation, batch 4096 -- through the layer graph (mannequin2_b200/vae.py):
+    two evaluations of the shared graph + clipped-momentum ascent (vae.py:57-71).  Its Affine layers are matmul nodes ->
+    mq_gemm -> the tcgen05 GEMM.  The graph API takes host arrays, so `value` already includes the upload of the batch
+    (2 x 12.8 MB per step) and the download of logprob / DKL: value == e2e for this workload."""
+    name = "vae_784-400-20-400-784_batch4096 (configs[4])"
+    metric = "vae_step_samples_per_s"
+    unit = "samples/s"
+    B = 4096
+
+    def __init__(self, seed=1):
+        rs = np.random.RandomState(seed)
+        self.x = rs.rand(self.B, 28, 28).astype(np.float32)
+        self.units_per_step = self.B
+
+    def setup_gpu(self):
+        import torch
+        from mannequin2_b200 import _device as D
+        from mannequin2_b200.vae import VAETrainer
+        np.random.seed(0)
+        self.torch, self.D = torch, D
+        self.tr = VAETrainer(image_shape=(28, 28), hidden=400, latent=20, n_hidden=1, rng=np.random.RandomState(2))
+        self.h2d, self.d2h = 2 * self.x.nbytes, 2 * self.B * 4
+
+    def step_gpu(self, i):
+        self.tr.step(self.x)
+
+    step_e2e = step_gpu
+
+    def launches_per_step(self):
+        return 110                                   # node-by-node graph: forward + backprop kernels of two evaluations
+
+    def dominant_kernel(self, peaks):
+        """gemm_tc_kernel on the widest layer (4096 x 784 x 400, y = x W), timed alone."""
+        t, D = self.torch, self.D
+        x, w = t.randn(4096, 784, device=D.device()), t.randn(784, 400, device=D.device())
+        y = t.empty(4096, 400, device=D.device())
+        times = []
+        for k in range(8):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            D.call("mq_gemm", D.ptr(x), 784, 1, D.ptr(w), 400, 1, D.ptr(y), 4096, 400, 784, 1.0, D.stream())
+            e1.record(); e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[2:]))
+        tf = 2.0 * 4096 * 784 * 400 / (ms * 1e-3) / 1e12
+        return dict(bound="tensor", kernel="gemm_tc_kernel (4096x784x400, three bf16 planes)", achieved=tf, peak=peaks["bf16"],
+                    unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None, peak_source=peaks["source"], ms_per_launch=ms,
+                    note="fp32-exact product = 6 bf16 plane pairs; bound by in-kernel operand staging (DESIGN.md 3.5)")
+
+
+WORKLOADS = {"ppo": PPOWorkload, "ppo_large": PPOLargeWorkload, "mlp": MLPWorkload, "es": ESWorkload, "vae": VAEWorkload}
 
 
 def kernel_sweep(peaks):
@@ -636,7 +688,8 @@ PARALLELISM = {"ppo_large": "dp%d: every rank trains on its own 2^20-transition 
                             "(one exchange per optimiser step, no NCCL call on the step path)",
                "ppo": "%d independent replicas (a 64-row minibatch does not shard)",
                "mlp": "%d independent replicas (batch 128 does not shard)",
-               "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce"}
+               "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce",
+               "vae": "%d independent replicas"}
 
 
 def main():
@@ -658,6 +711,9 @@ def main():
         if rank != 0:
             return 0
         wl = WORKLOADS[args.workload](**CPU_KW.get(args.workload, {}))
+        if not hasattr(wl, "step_cpu"):
+            print(json.dumps(dict(impl="reference", unavailable="no CPU port of the %s step in oracle/ yet" % args.workload)))
+            return 0
         procs = max(1, min(cores, 32))
         steps = max(1, min(args.steps, 3))
         val, wall = time_cpu(args.workload, steps, 1, procs)
@@ -710,7 +766,7 @@ def main():
                     e2e=dict(value=units / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=wl.h2d,
                              d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=wl.launches_per_step() * args.steps, roofline=roof, clocks=clocks)
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and hasattr(wl, "step_cpu"):
             v1, w1 = time_cpu(args.workload, 1, 1, 1)
             line["cpu_baseline"] = dict(
                 value=v1, unit=wl.unit, cores=1, kind="port", host_cores=cores,
@@ -722,7 +778,7 @@ def main():
             del wl
             torch.cuda.empty_cache()
             others = {}
-            for name in ("ppo", "mlp", "es"):
+            for name in ("ppo", "mlp", "es", "vae"):
                 if name == args.workload:
                     continue
                 w2 = WORKLOADS[name](seed=7)
@@ -730,7 +786,7 @@ def main():
                 m1, m2 = measure(w2, 5, 3, 1, 0, flush)
                 u = w2.units_per_step * 5
                 r2 = w2.dominant_kernel(peaks)
-                c1, _ = time_cpu(name, 1, 1, 1)
+                c1 = time_cpu(name, 1, 1, 1)[0] if hasattr(w2, "step_cpu") else None
                 others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
                                     e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,
                                     roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",

@@ -229,6 +229,9 @@ int mq_gauss_logprob(const float *mu, const float *logstd, int64_t logstd_period
 int mq_gauss_logprob_bwd(const float *mu, const float *logstd, int64_t logstd_period,
                          const float *sample, const float *g, int64_t rows, int64_t a, float *d_mu,
                          float *d_logstd_rows, void *stream);
+/* mnist/vae.py:64-69: g = g1 (+ g2 on the first n2 entries); mom = clip(decay*mom + (1-decay)*g, +-clip); theta += lr*mom */
+int mq_momentum_step(float *theta, float *mom, const float *g1, const float *g2, int64_t n2, int64_t n, float decay,
+                     float clip, float lr, void *stream);
 /* categorical log-prob (mannequin/distrib.py:24-32): logp[r] = log softmax(logits[r])[sample[r]] and / or
  * d_logits[r] = g[r] * (onehot(sample[r]) - softmax(logits[r])); g is only read when d_logits != NULL */
 int mq_discrete_logprob(const float *logits, const int32_t *sample, const float *g, int64_t rows, int64_t n,

@@ -93,6 +93,7 @@ SIGNATURES = {
     "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
     "mq_gauss_logprob_bwd": (c_int, [P, P, c_int64, P, P, c_int64, c_int64, P, P, P]),
     "mq_discrete_logprob": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
+    "mq_momentum_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, P]),
     "mq_onehot": (c_int, [P, c_int64, c_int64, P, P]),
     "mq_gauss_sample": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P, P]),
     "mq_dkl_forward": (c_int, [P, P, c_int64, c_int64, P, P]),

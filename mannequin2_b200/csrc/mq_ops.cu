@@ -385,3 +385,29 @@ extern "C" int mq_onehot(const int32_t *idx, int64_t rows, int64_t n, float *out
     MQ_CHECK_LAUNCH("mq_onehot");
     return MQ_OK;
 }
+
+// ---- clipped-momentum ascent of mnist/vae.py:64-69 ------------------------------------------------------
+// g = g1 (+ g2 on the first n2 entries: the encoder parameters come first); mom = clip(decay*mom + (1-decay)*g, +-clip);
+// theta += lr * mom
+__global__ void __launch_bounds__(MQ_NT)
+momentum_step_kernel(float *__restrict__ theta, float *__restrict__ mom, const float *__restrict__ g1,
+                     const float *__restrict__ g2, int64_t n2, int64_t n, float decay, float clip, float lr) {
+    EW_LOOP(e, n) {
+        float g = g1[e];
+        if (g2 && e < n2) g += g2[e];
+        float m = mom[e] * decay + g * (1.0f - decay);
+        m = fminf(fmaxf(m, -clip), clip);
+        mom[e] = m;
+        theta[e] += lr * m;
+    }
+}
+
+extern "C" int mq_momentum_step(float *theta, float *mom, const float *g1, const float *g2, int64_t n2, int64_t n,
+                                float decay, float clip, float lr, void *stream) {
+    MQ_REQUIRE(n >= 0 && n2 >= 0 && n2 <= n, MQ_ERR_SHAPE, "mq_momentum_step: bad sizes");
+    if (n == 0) return MQ_OK;
+    MQ_REQUIRE(theta && mom && g1, MQ_ERR_INVALID, "mq_momentum_step: null pointer");
+    MQ_LAUNCH(momentum_step_kernel, ew_blocks(n), MQ_NT, 0, stream, theta, mom, g1, g2, n2, n, decay, clip, lr);
+    MQ_CHECK_LAUNCH("mq_momentum_step");
+    return MQ_OK;
+}

@@ -33,10 +33,11 @@ def _reduce_to(g, shape):
 
 
 class Gauss(object):
-    def __init__(self, *, mean, logstd=None):
+    def __init__(self, *, mean, logstd=None, rng=None):
+        """`rng` (extension): the RandomState `sample` draws from; the reference always uses an OS-seeded one."""
         logstd = logstd or Params(*mean.shape)
         assert logstd.shape == mean.shape
-        rng = np.random.RandomState()
+        rng = rng or np.random.RandomState()
         n_act = int(np.prod(mean.shape))
 
         def sample(mean_v, logstd_v):

@@ -1,0 +1,96 @@
+"""The VAE step of mnist/vae.py on the layer graph: DKLUninormal and Clip as device ops, and the training loop.
+
+mnist/vae.py defines its two extra nodes inside the script (vae.py:13-34):
+
+    DKLUninormal(mean, logstd) = 0.5 * (sum(exp(logstd) - logstd + mean^2, axis=-1) - D)     (autograd)
+    Clip(v, a, b)              = np.clip forward; backward zeroes g where (v < a and g < 0) or (v > b and g > 0)
+
+Here both are `Function`s whose `f` runs the closed-form kernels of csrc/mq_ops.cu (mq_dkl_*, mq_clip_*), so the
+encoder / decoder graph of vae.py:39-55 evaluates node by node on the device; its Affine layers are `matmul` nodes,
+i.e. mq_gemm, which sends batch-4096 layers (BASELINE configs[4]) to the tcgen05 GEMM (csrc/mq_gemm_tc.cu).
+`VAETrainer.step` is vae.py:57-71: two evaluations of the shared graph, clipped-momentum ascent.
+"""
+import numpy as np
+import torch
+
+from . import _device as D
+from .basicnet import Affine, Function, Input, Tanh
+from .distrib import Gauss
+
+
+def DKLUninormal(*, mean, logstd):
+    """KL(N(mean, exp(logstd)) || N(0, 1)) as written in mnist/vae.py:13-24 (note exp(logstd), not exp(2 logstd))."""
+    def dkl(mean_v, logstd_v):
+        mean_v, logstd_v = mean_v.contiguous(), logstd_v.contiguous()
+        d = int(mean_v.shape[-1])
+        rows = mean_v.numel() // d
+        out = torch.empty(tuple(mean_v.shape)[:-1], dtype=torch.float32, device=mean_v.device)
+        D.call("mq_dkl_forward", D.ptr(mean_v), D.ptr(logstd_v), rows, d, D.ptr(out), D.stream())
+
+        def bpp(g):
+            d_mean, d_ls = torch.empty_like(mean_v), torch.empty_like(mean_v)
+            D.call("mq_dkl_backward", D.ptr(mean_v), D.ptr(logstd_v), D.ptr(g.contiguous()), rows, d, D.ptr(d_mean),
+                   D.ptr(d_ls), D.stream())
+            return (d_mean, d_ls)
+        return out, bpp
+    dkl._mq_dev = True
+    dkl._mq_op = ("dkl_uninormal",)
+    return Function(mean, logstd, f=dkl, shape=())
+
+
+def Clip(inner, a, b):
+    """mnist/vae.py:26-34."""
+    a, b = float(a), float(b)
+
+    def clip(v):
+        v = v.contiguous()
+        y = torch.empty_like(v)
+        D.call("mq_clip_forward", D.ptr(v), D.ptr(y), v.numel(), a, b, D.stream())
+
+        def bpp(g):
+            out = torch.empty_like(v)
+            D.call("mq_clip_backward", D.ptr(v), D.ptr(g.contiguous()), D.ptr(out), v.numel(), a, b, D.stream())
+            return (out,)
+        return y, bpp
+    clip._mq_dev = True
+    clip._mq_op = ("clip", a, b)
+    return Function(inner, f=clip)
+
+
+class VAETrainer(object):
+    """mnist/vae.py:39-71 with the layer sizes as arguments (script: image (28, 28), hidden 256, latent 3;
+    BASELINE configs[4]: hidden 400, latent 20, batch 4096)."""
+
+    def __init__(self, image_shape=(28, 28), hidden=256, latent=3, n_hidden=2, lr=1e-3, rng=None):
+        enc = Input(*image_shape)
+        for _ in range(n_hidden):
+            enc = Tanh(Affine(enc, hidden))
+        self.encoder = Gauss(mean=Affine(enc, latent, init=0.1), logstd=Clip(Affine(enc, latent), -6.0, 0.0), rng=rng)
+        self.dkl = DKLUninormal(mean=self.encoder.mean, logstd=self.encoder.logstd)
+        dec = self.encoder.sample
+        for _ in range(n_hidden):
+            dec = Tanh(Affine(dec, hidden))
+        self.decoder = Gauss(mean=Affine(dec, *image_shape, init=0.1), logstd=Clip(Affine(dec, *image_shape), -6.0, 0.0))
+        self.lr = float(lr)
+        self.momentum = None
+        self.n_params = self.decoder.n_params
+
+    def step(self, inps):
+        """One iteration of vae.py:57-71 on a batch of images; returns (mean logprob, mean DKL)."""
+        n = len(inps)
+        logprob, backprop = self.decoder.logprob.evaluate(inps, sample=inps)
+        grad1 = D.as_dev_f32(backprop(np.ones(n, np.float32)))
+        dkl_value, backprop = self.dkl.evaluate(inps)
+        grad2 = D.as_dev_f32(backprop(-np.ones(n, np.float32)))
+        flat = self.decoder.logprob._flat                              # encoder parameters first (vae.py:66)
+        if self.momentum is None:
+            self.momentum = D.zeros(self.n_params)
+        if flat is not None:
+            D.call("mq_momentum_step", D.ptr(flat), D.ptr(self.momentum), D.ptr(grad1), D.ptr(grad2), grad2.numel(),
+                   self.n_params, 0.9, 1.0, self.lr, D.stream())
+        else:                                                          # parameters not in one arena slice
+            theta = D.as_dev_f32(self.decoder.get_params()).clone()
+            D.call("mq_momentum_step", D.ptr(theta), D.ptr(self.momentum), D.ptr(grad1), D.ptr(grad2), grad2.numel(),
+                   self.n_params, 0.9, 1.0, self.lr, D.stream())
+            self.decoder.load_params(D.DeviceVector(theta, (self.n_params,)))
+        return float(np.mean(logprob)), float(np.mean(dkl_value))

@@ -415,6 +415,56 @@ def test_discrete_policy_against_reference_fixture():
     assert all(0 <= int(a) < 3 for a in draws)
 
 
+def test_vae_step_graph():
+    """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
+    mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
+    a step of the clipped-momentum rule moves the parameters by lr * clip(0.1 * g)."""
+    from mannequin2_b200.vae import VAETrainer
+    from mannequin2_b200 import _device as D
+    np.random.seed(3)
+    rs = np.random.RandomState(4)
+    x = rs.rand(8, 6, 5).astype(np.float32)
+
+    class Replay(object):                                   # the same noise for every evaluation
+        def randn(self, *shape):
+            return np.random.RandomState(77).randn(*shape)
+    tr = VAETrainer(image_shape=(6, 5), hidden=16, latent=3, rng=Replay())
+    dec, dkl = tr.decoder, tr.dkl
+    # keep both logstd heads strictly inside Clip's (-6, 0): its backward rule (vae.py:28-32) is deliberately not
+    # the derivative of np.clip outside the range, so central differences only apply inside
+    for gauss in (tr.encoder, tr.decoder):
+        bias_fn = gauss.logstd.inputs[0]                    # Clip(Bias(Linear(h, W), b))
+        lin, b = bias_fn.inputs
+        b.dev.fill_(-3.0)
+        while len(lin.inputs) == 1:                         # Reshape around the matmul of image-shaped heads
+            lin = lin.inputs[0]
+        lin.inputs[1].dev.mul_(0.1)
+    theta0 = np.asarray(dec.get_params(), dtype=np.float64).copy()
+    n_enc = dkl.n_params
+
+    def loss_and_grad(theta):
+        dec.load_params(theta.astype(np.float32))
+        lp, bpp = dec.logprob.evaluate(x, sample=x)
+        g = np.asarray(bpp(np.ones(8, np.float32)), dtype=np.float64).copy()
+        kl, bpp2 = dkl.evaluate(x)
+        g[:n_enc] += np.asarray(bpp2(-np.ones(8, np.float32)), dtype=np.float64)
+        return float(np.mean(lp)) - float(np.mean(kl)), g
+
+    l0, g0 = loss_and_grad(theta0)
+    assert np.isfinite(l0) and np.isfinite(g0).all() and np.abs(g0).max() > 0
+    for k in range(3):
+        d = np.random.RandomState(10 + k).randn(len(theta0))
+        d /= np.linalg.norm(d)
+        eps = 2e-2
+        fd = (loss_and_grad(theta0 + eps * d)[0] - loss_and_grad(theta0 - eps * d)[0]) / (2 * eps)
+        an = float(g0 @ d)                                   # batch-mean gradients: d mean(...) / d theta
+        assert abs(fd - an) <= 3e-2 * max(1.0, abs(an)), (k, fd, an)
+    dec.load_params(theta0.astype(np.float32))
+    lp, kl = tr.step(x)
+    moved = np.asarray(dec.get_params(), dtype=np.float64) - theta0
+    assert_close(moved, 1e-3 * np.clip(0.1 * g0, -1, 1), rtol=1e-3, atol_scale=1e-3)
+
+
 def test_trajectory_device_gather_and_discounted():
     from mannequin2_b200 import Trajectory, discounted
     g = load_golden("trajectory")
