@@ -241,13 +241,35 @@ class PPOLargeWorkload(object):
     def step_gpu(self, i):
         self.upd.update_dev(*self.dev[i % len(self.dev)])
 
+    def _upload(self):
+        """Pinned host rollout -> device on the copy stream; returns (device tensors, event)."""
+        t = self.torch
+        with t.cuda.stream(self._copy_stream):
+            args = [x.to(self.D.device(), non_blocking=True) for x in self.pinned[0]]
+            ev = t.cuda.Event()
+            ev.record(self._copy_stream)
+        return args, ev
+
     def step_e2e(self, i):
-        dev = self.D.device()
-        args = [x.to(dev, non_blocking=True) for x in self.pinned[0]]
+        """Host buffers in, new parameters out, every step.  The upload of step i+1 (148 MB over PCIe) is issued on a
+        copy stream before step i's kernels are launched, the way a training loop feeds rollouts; every step still
+        copies its own inputs H2D and its results D2H inside the timed region."""
+        t = self.torch
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream, self._next = t.cuda.Stream(), None
+        if self._next is None:
+            self._next = self._upload()
+        args, ev = self._next
+        main = t.cuda.current_stream()
+        main.wait_event(ev)
+        self._copy_stream.wait_stream(main)          # the next upload reuses nothing the running step still reads
+        self._next = self._upload()
         self.upd.update_dev(*args)
+        for a in args:
+            a.record_stream(main)
         self.out_pinned[0].copy_(self.upd.policy.theta, non_blocking=True)
         self.out_pinned[1].copy_(self.upd.value.theta, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
+        main.synchronize()
 
     def launches_per_step(self):
         return 11 + 2 * self.steps_per_net * 2      # per optimiser step: gradient kernel + reduce/all-reduce/Adam kernel

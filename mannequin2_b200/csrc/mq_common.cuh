@@ -30,6 +30,28 @@ static __host__ __device__ inline bool mq_head_discrete(int k) { return k == MQ_
 static __host__ __device__ inline bool mq_head_ppo(int k) { return k == MQ_HEAD_GAUSS_PPO || k == MQ_HEAD_DISCRETE_PPO; }
 static __host__ __device__ inline bool mq_head_prob(int k) { return mq_head_gauss(k) || mq_head_discrete(k); }
 
+#ifndef MQ_EMU
+// Programmatic dependent launch (PDL): a kernel launched with mq_launch_pdl may START while its predecessor in the
+// stream is still running; it must execute mq_pdl_wait() before touching anything the predecessor writes (the wait
+// returns when the predecessor grid has completed and its writes are visible).  mq_pdl_trigger() in the predecessor
+// allows the dependent to be scheduled early.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void mq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mq_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void *stream,
+                                        Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- host-side error plumbing ------------------------------------------------
 void mq_set_error(const char *fmt, ...);
 

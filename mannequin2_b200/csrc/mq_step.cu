@@ -57,6 +57,10 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
     __shared__ float part[8][33];
     const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + jx;
+    // programmatic dependent launch: this grid may already be resident while the gradient kernel finishes, and the
+    // next gradient kernel may start its on-chip prologue while this one runs
+    mq_pdl_trigger();
+    mq_pdl_wait();
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
     if (j < n) {
         int b = gy;
@@ -122,9 +126,10 @@ extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n,
     const unsigned blocks = (unsigned)mq_ceil_div(n, 32);
 #define MQ_STEP_GO(ST, A)                                                                                      \
     do {                                                                                                       \
-        auto kfn = reduce_step_kernel<ST, A>;                                                                  \
-        MQ_LAUNCH(kfn, blocks, MQ_NT, 0, stream, partials, (int)n_parts, (int)n, scale, (ST *)value, (ST *)m, \
-                  (ST *)v, theta_out, grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr);                          \
+        cudaError_t e_ = mq_launch_pdl(reduce_step_kernel<ST, A>, dim3(blocks), dim3(MQ_NT), 0, stream, partials,    \
+                                       (int)n_parts, (int)n, scale, (ST *)value, (ST *)m, (ST *)v, theta_out,       \
+                                       grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr);                              \
+        if (e_ != cudaSuccess) { mq_set_error("mq_reduce_step: %s", cudaGetErrorString(e_)); return MQ_ERR_CUDA; }   \
     } while (0)
     if (state_dtype == MQ_F32) { if (adams) MQ_STEP_GO(float, true); else MQ_STEP_GO(float, false); }
     else if (state_dtype == MQ_F64) { if (adams) MQ_STEP_GO(double, true); else MQ_STEP_GO(double, false); }

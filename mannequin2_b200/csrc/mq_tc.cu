@@ -205,6 +205,9 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     constexpr int XCHUNKS = K0 / 8;
 
     // ---- one-time setup: TMEM, barrier, operand images of the weights --------------------------
+    // (launched with programmatic stream serialisation: everything up to mq_pdl_wait() is on-chip work that overlaps
+    //  with the tail of the previous kernel in the stream -- in the PPO loop the reduce + Adam kernel that writes theta)
+    mq_pdl_trigger();
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -232,6 +235,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     float *sHin = reinterpret_cast<float *>(smem + p.off_hin);        // head inputs of the tile: [128][TC_HIN]
     int *sIdx = reinterpret_cast<int *>(smem + p.off_idx);            // source rows of three consecutive tiles: [3][128]
     TC_MARK(23);
+    mq_pdl_wait();                        // first global read below: the predecessor's writes are complete and visible
     // weight images: one work item = 8 consecutive inputs (one 16-byte chunk) of one output column
     {
         int items[TC_MAXL + 1];
@@ -773,8 +777,8 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
     do {                                                                                                                 \
         e = cudaFuncSetAttribute(tc_grad_kernel<K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
         if (e == cudaSuccess)                                                                                            \
-            tc_grad_kernel<K0_, ACT_><<<grid, TC_NT, p.smem_bytes, (cudaStream_t)stream>>>(                             \
-                p, theta, x, row_idx, batch, *head, (float *)ws, out, logp, mq_phase_prof_ptr());                       \
+            e = mq_launch_pdl(tc_grad_kernel<K0_, ACT_>, dim3(grid), dim3(TC_NT), (size_t)p.smem_bytes, stream, p, theta, \
+                              x, row_idx, batch, *head, (float *)ws, out, logp, mq_phase_prof_ptr());                    \
     } while (0)
     const int hact = net->act[0];
     if (p.k0 == 16 && hact == MQ_ACT_TANH) TC_LAUNCH(16, MQ_ACT_TANH);
