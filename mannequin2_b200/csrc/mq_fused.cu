@@ -868,6 +868,8 @@ int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const
 int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                  int64_t batch, const mq_head_t *head, int with_grad, float *out, float *logp,
                  void *ws, int64_t ws_bytes, int *grid_out, void *stream);
+int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
+                    int64_t n_obs, const float *ret_coef, float *returns, void *stream);
 static int g_use_chain_grad = 1;     // developer knob: 0 forces the tile kernel
 extern "C" int mq_debug_use_chain_grad(int on) { g_use_chain_grad = on; return MQ_OK; }
 
@@ -1119,6 +1121,10 @@ extern "C" int mq_es_eval(const mq_net_t *net, const float *theta, const float *
     MQ_REQUIRE(n_members >= 0 && n_obs >= 1, MQ_ERR_SHAPE, "mq_es_eval: bad sizes");
     if (n_members == 0) return MQ_OK;
     MQ_REQUIRE(theta && noise && obs && ret_coef && returns, MQ_ERR_INVALID, "mq_es_eval: null pointer");
+    {   // long observation batches: population evaluation on the tensor pipe (mq_tc.cu)
+        const int trc = mq_tc_es_launch(net, theta, noise, n_members, obs, n_obs, ret_coef, returns, stream);
+        if (trc != MQ_ERR_UNSUPPORTED) return trc;
+    }
     FusedPlan p;
     MQ_REQUIRE(plan_choose(net, n_obs, 0, &p) > 0, MQ_ERR_UNSUPPORTED,
                "mq_es_eval: net does not fit in shared memory");

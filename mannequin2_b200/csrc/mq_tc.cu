@@ -694,6 +694,180 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
 }
 
+// ---- evolution strategies: population evaluation on the tensor pipe ----------------------------------------
+// benchmarks/mutation.py:33-37 in population form: member p evaluates policy(theta + noise[p]) on the shared
+// observation batch and returns sum_t sum_a action[t][a] * ret_coef[a].  One CTA walks members; per member it builds the
+// bf16 plane images of theta + noise[p] (forward image only), pushes the observation tiles through the same three-plane
+// products and epilogues as tc_grad_kernel, and reduces the return on chip in a fixed order.
+template <int K0, int HACT>
+__global__ void __launch_bounds__(TC_NT, 1)
+tc_es_kernel(TcPlan p, const float *__restrict__ theta, const float *__restrict__ noise, int64_t n_members,
+             const float *__restrict__ obs, int64_t n_obs, const float *__restrict__ ret_coef, float *__restrict__ returns) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ float s_red[TC_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int L = p.L;
+    const int n_in = p.net.n_in, n_out = p.net.n_out;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_mbar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    for (int i = tid; i < p.off_act[1] / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = p.off_wf[0] / 16 + tid; i < p.smem_bytes / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    float *sBias = reinterpret_cast<float *>(smem + p.off_bias);
+    tc_publish();
+    const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
+    const uint32_t mbar = tc_smem_u32(&s_mbar);
+    const uint32_t sbase = tc_smem_u32(smem);
+    uint32_t parity = 0;
+    const int quarter = warp & 3, cg = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
+    const int64_t ntiles = (n_obs + TC_ROWS - 1) / TC_ROWS;
+    const int lastact = p.net.act[L - 1];
+    const float lastleak = p.net.leak[L - 1];
+    float coef[TC_NO];
+#pragma unroll
+    for (int a = 0; a < TC_NO; ++a) coef[a] = a < n_out ? __ldg(ret_coef + a) : 0.0f;
+
+    constexpr int XE = K0 / 4;
+    float xr[XE];
+    int xrf[XE];
+    {
+        int r = tid / n_in, f = tid - r * n_in;
+#pragma unroll
+        for (int j = 0; j < XE; ++j) {
+            xrf[j] = r < TC_ROWS ? ((r << 8) | f) : -1;
+            r += p.x_step_q; f += p.x_step_r;
+            if (f >= n_in) { f -= n_in; ++r; }
+        }
+    }
+    auto load_x = [&](int64_t tile) {
+#pragma unroll
+        for (int j = 0; j < XE; ++j) {
+            float v = 0.0f;
+            if (xrf[j] >= 0) {
+                const int64_t gr = tile * TC_ROWS + (xrf[j] >> 8);
+                if (gr < n_obs) v = __ldg(obs + gr * n_in + (xrf[j] & 255));
+            }
+            xr[j] = v;
+        }
+    };
+    auto store_x = [&]() {
+#pragma unroll
+        for (int j = 0; j < XE; ++j) {
+            if (xrf[j] < 0) continue;
+            const int r = xrf[j] >> 8, f = xrf[j] & 255;
+            uint32_t w0, w1, w2;
+            tc_split_pair(xr[j], 0.0f, w0, w1, w2);
+            unsigned char *d = tc_chunk_ptr(smem + p.off_act[0], p.act_plane[0], f >> 3, r) + (f & 7) * 2;
+            *reinterpret_cast<uint16_t *>(d) = (uint16_t)(w0 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(d - p.act_plane[0]) = (uint16_t)(w1 & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(d - 2 * p.act_plane[0]) = (uint16_t)(w2 & 0xFFFFu);
+        }
+    };
+    int items[TC_MAXL + 1];
+    items[0] = 0;
+    for (int l = 0; l < L; ++l) items[l + 1] = items[l] + (p.kp[l] / 8) * p.net.out[l];
+
+    for (int64_t member = blockIdx.x; member < n_members; member += gridDim.x) {
+        const float *nz = noise + member * p.net.n_params;
+        // ---- forward images of theta + noise[member] (all previous MMAs have been waited for) ---------------
+#pragma unroll 2
+        for (int it = tid; it < items[L]; it += TC_NT) {
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < TC_MAXL; ++q) if (q < L && it >= items[q]) l = q;
+            const int on = p.net.out[l], np = p.np[l], in = p.net.in[l];
+            const int local = it - items[l];
+            const int kc = local / on, n = local - kc * on;
+            const int off = p.net.w_off[l] + (kc * 8) * on + n;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (kc * 8 + j < in) ? __ldg(theta + off + j * on) + __ldg(nz + off + j * on) : 0.0f;
+            uint32_t q[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tc_split_pair(v[2 * j], v[2 * j + 1], q[0][j], q[1][j], q[2][j]);
+            unsigned char *df = smem + p.off_wf[l] + kc * (3 * np * 16) + n * 16;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+                *reinterpret_cast<uint4 *>(df + pl * np * 16) = make_uint4(q[pl][0], q[pl][1], q[pl][2], q[pl][3]);
+        }
+        for (int l = 0; l < L; ++l)
+            for (int n = tid; n < p.net.out[l]; n += TC_NT)
+                sBias[l * 64 + n] = __ldg(theta + p.net.b_off[l] + n) + __ldg(nz + p.net.b_off[l] + n);
+        load_x(0);
+        float acc = 0.0f;
+        for (int64_t tile = 0; tile < ntiles; ++tile) {
+            store_x();
+            tc_publish();                   // also publishes the images / biases on the first tile
+            for (int l = 0; l < L; ++l) {
+                if (warp == 0) {
+                    if (tc_elect_one()) {
+                        tc_rows_product(tm, sbase + p.off_act[l] + 2 * p.act_plane[l], p.act_plane[l],
+                                        tc_wf_k(sbase + p.off_wf[l], p.np[l]), 0, (uint32_t)p.np[l], p.np[l], p.kp[l] / 16);
+                        tc_commit(mbar);
+                    }
+                    __syncwarp();
+                }
+                if (l == 0 && tile + 1 < ntiles) load_x(tile + 1);
+                tc_wait(mbar, parity); parity ^= 1;
+                if (l < L - 1) {
+                    float v[16], v2[16];
+                    tc_ld16(tlane + cg * 16, v);
+                    tc_ld16(tlane + TC_HID + cg * 16, v2);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(sBias + l * 64 + cg * 16);
+                    const float leak = p.net.leak[l];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = b4[j];
+                        v[4 * j + 0] = tc_act<HACT>((v[4 * j + 0] + v2[4 * j + 0]) + bb.x, leak);
+                        v[4 * j + 1] = tc_act<HACT>((v[4 * j + 1] + v2[4 * j + 1]) + bb.y, leak);
+                        v[4 * j + 2] = tc_act<HACT>((v[4 * j + 2] + v2[4 * j + 2]) + bb.z, leak);
+                        v[4 * j + 3] = tc_act<HACT>((v[4 * j + 3] + v2[4 * j + 3]) + bb.w, leak);
+                    }
+                    tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2, row, v);
+                    tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2 + 1, row, v + 8);
+                    tc_publish();
+                }
+            }
+            if (cg == 0) {                  // actions of this row -> its term of the return
+                float y[TC_NO], y2[TC_NO];
+                tc_ld16(tlane, y);
+                tc_ld16(tlane + TC_NO, y2);
+                if (tile * TC_ROWS + row < n_obs) {
+                    const float *b = sBias + (L - 1) * 64;
+#pragma unroll
+                    for (int a = 0; a < TC_NO; ++a)
+                        if (a < n_out) acc = fmaf(mq_act_apply((y[a] + y2[a]) + b[a], lastact, lastleak), coef[a], acc);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        // ---- fixed-order block sum -> returns[member]; the barriers also order the next member's image stores
+        acc = mq_warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.0f;
+            for (int w = 0; w < TC_NT / 32; ++w) s += s_red[w];
+            returns[member] = s;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128u));
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, const mq_head_t *head, TcPlan *p) {
     memset(p, 0, sizeof(*p));
@@ -794,8 +968,43 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
     if (grid_out) *grid_out = grid;
     return MQ_OK;
 }
+
+// Population evaluation on the tensor pipe (mq_es_eval dispatches here); MQ_ERR_UNSUPPORTED if the net does not fit.
+int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
+                    int64_t n_obs, const float *ret_coef, float *returns, void *stream) {
+    if (g_tc_mode == 0) return MQ_ERR_UNSUPPORTED;
+    if (g_tc_mode == 1 && n_obs < 256) return MQ_ERR_UNSUPPORTED;
+    if (net->logstd_off >= 0) return MQ_ERR_UNSUPPORTED;
+    TcPlan p;
+    if (!tc_plan_build(net, n_obs, 0, nullptr, &p)) return MQ_ERR_UNSUPPORTED;
+    p.tile_rows = TC_ROWS;
+    const int64_t sms = mq_sm_count();
+    const int grid = (int)(n_members < sms ? n_members : sms);
+    cudaError_t e = cudaSuccess;
+#define TC_ES_LAUNCH(K0_, ACT_)                                                                                        \
+    do {                                                                                                               \
+        e = cudaFuncSetAttribute(tc_es_kernel<K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
+        if (e == cudaSuccess)                                                                                          \
+            tc_es_kernel<K0_, ACT_><<<grid, TC_NT, p.smem_bytes, (cudaStream_t)stream>>>(p, theta, noise, n_members,  \
+                                                                                        obs, n_obs, ret_coef, returns); \
+    } while (0)
+    const int hact = net->act[0];
+    if (p.k0 == 16 && hact == MQ_ACT_TANH) TC_ES_LAUNCH(16, MQ_ACT_TANH);
+    else if (p.k0 == 16) TC_ES_LAUNCH(16, MQ_ACT_LRELU);
+    else if (hact == MQ_ACT_TANH) TC_ES_LAUNCH(32, MQ_ACT_TANH);
+    else TC_ES_LAUNCH(32, MQ_ACT_LRELU);
+#undef TC_ES_LAUNCH
+    if (e != cudaSuccess) {
+        mq_set_error("mq_tc_es_launch: %s", cudaGetErrorString(e));
+        return MQ_ERR_CUDA;
+    }
+    MQ_CHECK_LAUNCH("mq_tc_es_launch");
+    return MQ_OK;
+}
 #else   // MQ_EMU: the host emulation has no tensor cores
 int mq_tc_launch(const mq_net_t *, const float *, const float *, const int32_t *, int64_t, const mq_head_t *, int,
                  float *, float *, void *, int64_t, int *, void *) { return MQ_ERR_UNSUPPORTED; }
+int mq_tc_es_launch(const mq_net_t *, const float *, const float *, int64_t, const float *, int64_t, const float *, float *,
+                    void *) { return MQ_ERR_UNSUPPORTED; }
 extern "C" int mq_debug_set_tc_mode(int) { return MQ_OK; }
 #endif

@@ -651,6 +651,9 @@ def case_tc_paths(B):
                                     B.ptr(g2), None, None, B.ptr(ws), wsb, B.stream))
             ok(B, lib.mq_debug_set_tc_mode(2))
             close(B.down(grad), B.down(g2), rtol=3e-5, atol_scale=3e-6, what="tc vs ffma mb=%d" % mb)
+        # evolution-strategies population on the tensor pipe (tc_es_kernel): several members per CTA, ragged last tile
+        case_es(B, members=200, n_obs=150)
+        case_es(B, members=9, n_obs=1000)
     finally:
         lib.mq_debug_set_tc_mode(1)
 
