@@ -17,6 +17,7 @@ group (mannequin2_b200.dist) large minibatches are sharded by rows and the flat
 gradient is all-reduced once per optimiser step.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -164,9 +165,12 @@ class PPOUpdater(object):
         ws = D.workspace("scan", wsb)
         D.call("mq_gae", D.ptr(rew), D.ptr(value), D.ptr(done), n, self.gam, self.lam, D.ptr(adv), D.ptr(ret),
                D.ptr(ws), wsb, D.stream())
-        # Small minibatches: the two 300-step chains are single-CTA kernels -> run them side by
-        # side on two streams.  Large / sharded minibatches fill the GPU: run them in sequence.
-        concurrent = val_idx.shape[1] <= CHAIN_MAX_MB and mqdist.world() == 1
+        # The value chain and the policy chain are independent: run them on two streams.  Small minibatches: the two
+        # 300-step chains are single-CTA kernels side by side.  Large minibatches: each gradient kernel fills the GPU,
+        # but the small reduce / Adam kernels and the launch gaps of one chain run under the gradient kernels of the
+        # other: +4 % on one GPU.  Sharded runs keep one stream (measured 3 % faster there: every step already waits for
+        # the slowest rank).  MQ_PPO_SERIAL=1 forces one stream.
+        concurrent = not os.environ.get("MQ_PPO_SERIAL") and (mqdist.world() == 1 or val_idx.shape[1] <= CHAIN_MAX_MB)
         vhead = MqHead()
         vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
         if concurrent:
