@@ -415,6 +415,35 @@ def test_discrete_policy_against_reference_fixture():
     assert all(0 <= int(a) < 3 for a in draws)
 
 
+def test_large_batch_ppo_update_against_oracle():
+    """The measured path end to end: PPOUpdater.update on 16,384 transitions with 8,192-row minibatches (tcgen05
+    gradient kernel, fused reduce / Adam kernel, programmatic dependent launch, value and policy chains on two streams)
+    against the oracle's restatement of benchmarks/ppo.py:22-40 + gae.py:34-75 with the same index tables."""
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import ppo_rollout
+    from oracle import mq_oracle as O
+    from mannequin2_b200.ppo import PPOUpdater, init_mlp
+    rs = np.random.RandomState(41)
+    n, mb, epochs = 16384, 8192, 2
+    o, a, r, d = ppo_rollout(rs, n, p_done=1.0 / 300, cut=700)
+    vi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+    pi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+    np.random.seed(5)
+    pol0 = np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)])
+    val0 = init_mlp(11, [64, 64, 1], 0.1)
+    upd = PPOUpdater(11, 3, policy_params=pol0.copy(), value_params=val0.copy(), state_dtype="float64")
+    pol, val = upd.update(o, a, r, d, vi, pi)
+    pol_spec, val_spec = O.policy_spec(11, 3), O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    want_pol, want_val, _ = O.ppo_update(pol0.copy(), pol_spec, O.AdamO(pol0, horizon=10), val0.copy(), val_spec,
+                                         O.AdamO(val0, horizon=10, lr=0.003), O.RunningNormalizeO(horizon=2),
+                                         o, a, r, d.astype(bool), vi, pi)
+    steps = len(vi)
+    assert np.max(np.abs(pol - pol0)) > 1e-4 and np.max(np.abs(val - val0)) > 1e-4
+    assert np.max(np.abs(pol - want_pol)) < 2e-6 * (1 + steps) + 1e-6, np.max(np.abs(pol - want_pol))
+    assert np.max(np.abs(val - want_val)) < 2e-5 * (1 + steps), np.max(np.abs(val - want_val))
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
