@@ -385,6 +385,8 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     bool pending = false;                               // a committed MMA batch nobody waited for yet
     bool dw_started = false;                            // dW / db accumulators hold data
     load_x(0);
+    fetch_head_inputs(0);
+    commit_head_inputs();
 
     // TMEM accumulators -> this CTA's partial gradient in the workspace (set on the first flush, added afterwards).
     // The tensor pipe truncates when it adds into its fp32 accumulator (see mq_gemm_tc.cu), so a CTA that walks many
@@ -465,10 +467,11 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 __syncwarp();
             }
             TC_MARK(3);
-            if (l == 0) {
-                // overlap the gathers with the first products: this tile's head inputs, the next tile's rows, and the
-                // source rows of the tile after that
-                fetch_head_inputs(ord % 3);
+            if (l == L - 1) {
+                // gathers for the NEXT tile (rows, head inputs) and the source rows of the tile after it: issued here so
+                // that they have the last product and the whole head phase to arrive -- the next publish (a MEMBAR)
+                // would otherwise sit out the HBM latency
+                fetch_head_inputs((ord + 1) % 3);
                 load_x((ord + 1) % 3);
                 fetch_idx(tile + 2 * (int64_t)gridDim.x);
             }
@@ -494,7 +497,6 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 if (p.with_grad) tc_st16(tlane + p.col_save + l * TC_HID + cg * 16, v);
                 tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2, row, v);
                 tc_store_chunk(smem + p.off_act[l + 1], p.act_plane[l + 1], cg * 2 + 1, row, v + 8);
-                if (l == 0) { commit_head_inputs(); commit_idx((ord + 2) % 3); }
                 tc_publish();
                 TC_MARK(8 + l);
             }
@@ -614,6 +616,8 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
             }
         }
         tc_publish();
+        commit_head_inputs();               // the head phase is over: its inputs can be replaced by the next tile's
+        commit_idx((ord + 2) % 3);
         TC_MARK(11);
         if (!p.with_grad) continue;
         // ---- backward -----------------------------------------------------------------------------
