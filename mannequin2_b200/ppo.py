@@ -167,10 +167,9 @@ class PPOUpdater(object):
                D.ptr(ws), wsb, D.stream())
         # The value chain and the policy chain are independent: run them on two streams.  Small minibatches: the two
         # 300-step chains are single-CTA kernels side by side.  Large minibatches: each gradient kernel fills the GPU,
-        # but the small reduce / Adam kernels and the launch gaps of one chain run under the gradient kernels of the
-        # other: +4 % on one GPU.  Sharded runs keep one stream (measured 3 % faster there: every step already waits for
-        # the slowest rank).  MQ_PPO_SERIAL=1 forces one stream.
-        concurrent = not os.environ.get("MQ_PPO_SERIAL") and (mqdist.world() == 1 or val_idx.shape[1] <= CHAIN_MAX_MB)
+        # but the small reduce / Adam kernels, the launch gaps and (sharded) the exchange latency of one chain run under
+        # the gradient kernels of the other: +4 % on one GPU, +3 % on two.  MQ_PPO_SERIAL=1 forces one stream.
+        concurrent = not os.environ.get("MQ_PPO_SERIAL")
         vhead = MqHead()
         vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
         if concurrent:
