@@ -172,7 +172,7 @@ int mq_fused_grad_partials(const mq_net_t *net, const float *theta, const float 
 
 /* Peer-memory descriptor of the in-kernel all-reduce (one exchange of the flat gradient per
  * optimiser step).  grad_bufs / flag_bufs are DEVICE arrays of `world` pointers: rank r's exchange buffer
- * (float[2][buf_stride]) and flag pad (uint32[2][world][mq_step_blocks(n)], zero-initialised), each mapped into
+ * (float[2][world][buf_stride]) and flag pad (uint32[2][world][mq_step_blocks(n)], zero-initialised), each mapped into
  * this process (symmetric memory).  step must be non-zero and increase by one per call on every rank. */
 typedef struct mq_peer {
     int32_t rank, world;

@@ -8,10 +8,11 @@
 // summed gradient.
 //
 // The exchange is a one-shot all-reduce written into the kernel (no NCCL call on this path): a block
-// owns 32 parameters; it writes its 32 local sums into this rank's exchange buffer (symmetric memory,
-// mapped into every peer), releases a flag in every peer's flag pad, waits until every peer's flag for
-// the same block has arrived, then reads the 32 values of every rank through the peer mappings and adds
-// them in RANK ORDER (so all ranks compute bit-identical sums) before the Adam update.  Blocks only wait
+// owns 32 parameters; it STORES its 32 local sums into slot [rank] of every peer's exchange buffer
+// (symmetric memory, mapped into every peer: remote stores over NVLink, no round trip), releases a flag
+// in every peer's flag pad, waits until every peer's flag for the same block has arrived in its own pad,
+// then adds the 32 values of every rank from its OWN memory in RANK ORDER (so all ranks compute
+// bit-identical sums) before the Adam update.  Blocks only wait
 // for the same block index on the other GPUs, never for another block of their own GPU.  Exchange
 // buffers and flags are double-buffered by step parity: a rank can only be one step ahead of the slowest.
 #include "mq_common.cuh"
@@ -79,14 +80,16 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
 #pragma unroll
     for (int k = 1; k < 8; ++k) g += part[k][jx];
     if (peer.world > 1) {
-        // ---- one-shot all-reduce over peer memory ------------------------------------------------
+        // ---- one-shot all-reduce over peer memory (push): every rank STORES its 32 sums into slot [rank] of every
+        // peer's exchange buffer (remote stores need no round trip), then releases one flag per peer; a rank only ever
+        // reads its own memory
         const int par = (int)(peer.step & 1u);
-        float *mine = peer.grad_bufs[peer.rank] + (int64_t)par * peer.buf_stride;
-        if (j < n) mine[j] = g;
-        __threadfence_system();
-        __syncwarp();
+        const int64_t slot = ((int64_t)par * peer.world + peer.rank) * peer.buf_stride;
+        if (j < n)
+            for (int r = 0; r < peer.world; ++r) peer.grad_bufs[r][slot + j] = g;
+        __syncwarp();                   // the lanes' stores happen before the releasing lanes' flag stores (cumulative)
         const int nblk = gridDim.x;
-        if (jx < peer.world)            // lane r tells rank r that this rank's block is ready
+        if (jx < peer.world)            // lane r tells rank r that this rank's block has arrived there
             st_release_sys(peer.flag_bufs[jx] + ((int64_t)par * peer.world + peer.rank) * nblk + blockIdx.x, peer.step);
         if (jx < peer.world) {          // lane r waits for rank r's block
             const uint32_t *f = peer.flag_bufs[peer.rank] + ((int64_t)par * peer.world + jx) * nblk + blockIdx.x;
@@ -94,9 +97,10 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
         }
         __syncwarp();
         g = 0.0f;
-        if (j < n)
-            for (int r = 0; r < peer.world; ++r)
-                g += ld_relaxed_sys(peer.grad_bufs[r] + (int64_t)par * peer.buf_stride + j);
+        if (j < n) {
+            const float *mine = peer.grad_bufs[peer.rank] + (int64_t)par * peer.world * peer.buf_stride;
+            for (int r = 0; r < peer.world; ++r) g += ld_relaxed_sys(mine + (int64_t)r * peer.buf_stride + j);   // rank order
+        }
     }
     if (j >= n) return;
     g *= scale;

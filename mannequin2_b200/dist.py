@@ -78,7 +78,7 @@ class PeerExchange(object):
             self.stride = (int(n_params) + 63) // 64 * 64
             nblk = int(_lib.lib().mq_step_blocks(int(n_params)))
             dev = torch.device("cuda", torch.cuda.current_device())
-            self.buf = symm.empty(2 * self.stride, dtype=torch.float32, device=dev)
+            self.buf = symm.empty(2 * w * self.stride, dtype=torch.float32, device=dev)
             self.flags = symm.empty(2 * w * nblk, dtype=torch.int32, device=dev)
             self.buf.zero_()
             self.flags.zero_()
