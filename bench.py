@@ -144,6 +144,38 @@ class PPOWorkload(object):
         # logp fwd, policy train
         return 13
 
+    def replica_throughput(self, n_replicas, steps=5, warmup=3):
+        """Aggregate transitions/s of n_replicas INDEPENDENT learners (own parameters, normaliser and
+        Adam state) driven concurrently on their own streams of ONE GPU -- the counterpart of the
+        reference arm's one-process-per-core replicas.  One learner's update is a chain of dependent
+        single-CTA launches (latency-bound), so replicas fill the other SMs."""
+        t = self.torch
+        from mannequin2_b200.ppo import PPOUpdater
+        upds = [PPOUpdater(11, 3) for _ in range(n_replicas)]
+        streams = [t.cuda.Stream() for _ in range(n_replicas)]
+        t.cuda.synchronize()
+
+        def one_round(i):
+            for r, (u, s) in enumerate(zip(upds, streams)):
+                with t.cuda.stream(s):
+                    u.update_dev(*self.dev[(i + r) % len(self.dev)])
+        for i in range(warmup):
+            one_round(i)
+        t.cuda.synchronize()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in streams:
+            s.wait_event(e0)
+        for i in range(steps):
+            one_round(i)
+        for s in streams:
+            t.cuda.current_stream().wait_stream(s)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        return dict(replicas=n_replicas, value=n_replicas * steps * self.N / (ms * 1e-3), unit=self.unit,
+                    ms_per_round=ms / steps)
+
     def dominant_kernel(self, peaks):
         """fused_train_kernel<double> (policy chain), timed alone on its launch stream."""
         t, D, upd = self.torch, self.D, self.upd
@@ -830,9 +862,10 @@ def main():
                 u = w2.units_per_step * 5
                 r2 = w2.dominant_kernel(peaks)
                 c1 = time_cpu(name, 1, 1, 1)[0] if hasattr(w2, "step_cpu") else None
+                reps = [w2.replica_throughput(r) for r in (8, 16)] if hasattr(w2, "replica_throughput") else None
                 others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
                                     e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,
-                                    roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",
+                                    independent_replicas=reps, roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",
                                                                              "fp32_tflops", "fp32_frac", "note")})
                 del w2
                 torch.cuda.empty_cache()

@@ -74,8 +74,13 @@ _ws = {}
 
 
 def workspace(key, nbytes):
-    """A cached scratch buffer per (key, current device); grows, never shrinks."""
-    k = (key, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    """A cached scratch buffer per (key, current device, current stream); grows, never shrinks.
+
+    Keyed by stream so that independent learners driven on different streams never share scratch."""
+    if torch.cuda.is_available():
+        k = (key, torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    else:
+        k = (key, -1, 0)
     t = _ws.get(k)
     if t is None or t.numel() < nbytes:
         t = torch.empty(int(max(nbytes, 256)), dtype=torch.uint8, device=device())

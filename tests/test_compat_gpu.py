@@ -444,6 +444,49 @@ def test_large_batch_ppo_update_against_oracle():
     assert np.max(np.abs(val - want_val)) < 2e-5 * (1 + steps), np.max(np.abs(val - want_val))
 
 
+def test_independent_learners_on_concurrent_streams():
+    """Independent PPOUpdater instances driven on different CUDA streams share no scratch: each of three learners
+    running concurrently (both the single-CTA chain path and the large-batch path) ends bit-identical to the same
+    learner run alone."""
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import ppo_rollout
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.ppo import PPOUpdater, init_mlp
+    for n, mb, steps in ((2048, 64, 40), (16384, 8192, 4)):
+        rs = np.random.RandomState(n)
+        data, starts = [], []
+        for _ in range(3):
+            o, a, r, d = ppo_rollout(rs, n)
+            vi = rs.randint(n, size=(steps, mb)).astype(np.int32)
+            pi = rs.randint(n, size=(steps, mb)).astype(np.int32)
+            data.append(tuple(D.from_host(x) for x in (o, a, r, d, vi, pi)))
+            np.random.seed(len(data))
+            starts.append((np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)]),
+                           init_mlp(11, [64, 64, 1], 0.1)))
+
+        def learner(k):
+            return PPOUpdater(11, 3, policy_params=starts[k][0].copy(), value_params=starts[k][1].copy())
+        alone = []
+        for k in range(3):
+            u = learner(k)
+            for _ in range(2):
+                u.update_dev(*data[k])
+            torch.cuda.synchronize()
+            alone.append((u.policy.theta.cpu().numpy().copy(), u.value.theta.cpu().numpy().copy()))
+        upds, streams = [learner(k) for k in range(3)], [torch.cuda.Stream() for _ in range(3)]
+        torch.cuda.synchronize()
+        for _ in range(2):
+            for k in range(3):
+                with torch.cuda.stream(streams[k]):
+                    upds[k].update_dev(*data[k])
+        torch.cuda.synchronize()
+        for k in range(3):
+            assert np.array_equal(upds[k].policy.theta.cpu().numpy(), alone[k][0]), (n, k)
+            assert np.array_equal(upds[k].value.theta.cpu().numpy(), alone[k][1]), (n, k)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
