@@ -70,6 +70,9 @@ typedef struct mq_head {
     int32_t kind;
     float   p0;                /* SOFTMAX_CE: logit L2 coefficient (0.01); GAUSS_PPO: clip low (0.8) */
     float   p1;                /* GAUSS_PPO: clip high (1.2)                                         */
+    float   ent;               /* GAUSS_*: entropy-bonus coefficient c of the objective mean_b(w_b logp_b) + c H,
+                                  H = sum_a logstd_a + A/2 (1 + ln 2 pi) (not in the reference, whose
+                                  comparator runs with entcoeff = 0): adds c to every d/dlogstd_a.  Default 0.    */
     const float *dy;           /* DY: [rows,n_out]; GAUSS_LOGP / DISCRETE_LOGP: weights [rows]        */
     const float *target;       /* DIFF/SOFTMAX_CE: [rows,n_out]; GAUSS_*: sampled actions [rows,A];
                                   DISCRETE_*: one-hot actions [rows,n_out]                            */
@@ -229,6 +232,11 @@ int mq_gauss_logprob(const float *mu, const float *logstd, int64_t logstd_period
 int mq_gauss_logprob_bwd(const float *mu, const float *logstd, int64_t logstd_period,
                          const float *sample, const float *g, int64_t rows, int64_t a, float *d_mu,
                          float *d_logstd_rows, void *stream);
+/* Gaussian entropy, SURVEY a24 (named by the north star; absent from the reference, so pinned analytically and by
+ * finite differences only): h[r] = sum_a logstd[r,a] + A/2 (1 + ln 2 pi) when h != NULL; d_logstd[r,a] = g[r] when
+ * d_logstd != NULL.  logstd is [rows, A] (rows = 1 for a shared Params(A)). */
+int mq_gauss_entropy(const float *logstd, const float *g, int64_t rows, int64_t a, float *h, float *d_logstd,
+                     void *stream);
 /* mnist/vae.py:64-69: g = g1 (+ g2 on the first n2 entries); mom = clip(decay*mom + (1-decay)*g, +-clip); theta += lr*mom */
 int mq_momentum_step(float *theta, float *mom, const float *g1, const float *g2, int64_t n2, int64_t n, float decay,
                      float clip, float lr, void *stream);

@@ -27,7 +27,7 @@ class MqNet(ctypes.Structure):
 
 
 class MqHead(ctypes.Structure):
-    _fields_ = [("kind", c_int32), ("p0", c_float), ("p1", c_float), ("dy", c_void_p),
+    _fields_ = [("kind", c_int32), ("p0", c_float), ("p1", c_float), ("ent", c_float), ("dy", c_void_p),
                 ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p)]
 
 
@@ -91,6 +91,7 @@ SIGNATURES = {
     "mq_clip_forward": (c_int, [P, P, c_int64, c_float, c_float, P]),
     "mq_clip_backward": (c_int, [P, P, P, c_int64, c_float, c_float, P]),
     "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
+    "mq_gauss_entropy": (c_int, [P, P, c_int64, c_int64, P, P, P]),
     "mq_gauss_logprob_bwd": (c_int, [P, P, c_int64, P, P, c_int64, c_int64, P, P, P]),
     "mq_discrete_logprob": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
     "mq_momentum_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, P]),

@@ -112,7 +112,7 @@ class Layer(object):
                 else:
                     pos = 0
                     for l in params:
-                        l.dev.copy_(src[pos:pos + l.n_local_params])
+                        l.dev.copy_(src[pos:pos + l.n_local_params].view(l.dev.shape))
                         pos += l.n_local_params
             self._flat = flat
             self._params = params

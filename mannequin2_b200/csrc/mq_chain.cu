@@ -344,7 +344,7 @@ __device__ __forceinline__ void warp_head(const ChainPlan &p, const mq_head_t &h
             const float inv = expf(-sW[p.sls_off + a]);
             const float y = sAout[a * CH_TBP + r];
             const float z = (tgt[a * CH_TBP + r] - y) * inv;
-            hterm[a * CH_TBP + r] = wgt * (z * z - 1.0f);
+            hterm[a * CH_TBP + r] = wgt * (z * z - 1.0f) + h.ent;
             dzout[a * CH_TBP + r] = mq_act_grad(y, wgt * z * inv, lastact, lastleak);
         }
     }

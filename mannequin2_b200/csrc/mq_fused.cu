@@ -545,7 +545,7 @@ __device__ void head_tile(const FusedPlan &p, const mq_head_t &h, const float *s
                 const float inv = expf(-sW[p.sls_off + a]);
                 const float y = sAout[a * tbp + r];
                 const float z = (tgt[a * tbp + r] - y) * inv;
-                hterm[a * tbp + r] = w * (z * z - 1.0f);
+                hterm[a * tbp + r] = w * (z * z - 1.0f) + h.ent;
                 dzout[a * tbp + r] = mq_act_grad(y, w * z * inv, lastact, lastleak);
             }
         }

@@ -234,6 +234,32 @@ extern "C" int mq_gauss_logprob_bwd(const float *mu, const float *logstd, int64_
     return MQ_OK;
 }
 
+// Gaussian entropy (north_star names it, the reference has no such function):
+// H[r] = sum_a logstd[r,a] + A/2 (1 + ln 2 pi);  dH/dlogstd = 1, dH/dmean = 0.
+__global__ void __launch_bounds__(MQ_NT)
+gauss_entropy_kernel(const float *__restrict__ ls, int64_t rows, int64_t a, float *__restrict__ h) {
+    EW_LOOP(r, rows) {
+        float acc = 0.0f;
+        for (int64_t j = 0; j < a; ++j) acc += ls[r * a + j];
+        h[r] = acc + (float)a * (0.5f + MQ_HALF_LOG_2PI);
+    }
+}
+__global__ void __launch_bounds__(MQ_NT)
+gauss_entropy_bwd_kernel(const float *__restrict__ g, int64_t n, int64_t a, float *__restrict__ d_ls) {
+    EW_LOOP(e, n) d_ls[e] = g[e / a];
+}
+
+extern "C" int mq_gauss_entropy(const float *logstd, const float *g, int64_t rows, int64_t a, float *h,
+                                float *d_logstd, void *stream) {
+    MQ_REQUIRE(rows >= 0 && a >= 1, MQ_ERR_SHAPE, "mq_gauss_entropy: bad shape");
+    if (rows == 0) return MQ_OK;
+    MQ_REQUIRE((h && logstd) || (d_logstd && g), MQ_ERR_INVALID, "mq_gauss_entropy: null pointer");
+    if (h) MQ_LAUNCH(gauss_entropy_kernel, ew_blocks(rows), MQ_NT, 0, stream, logstd, rows, a, h);
+    if (d_logstd) MQ_LAUNCH(gauss_entropy_bwd_kernel, ew_blocks(rows * a), MQ_NT, 0, stream, g, rows * a, a, d_logstd);
+    MQ_CHECK_LAUNCH("mq_gauss_entropy");
+    return MQ_OK;
+}
+
 extern "C" int mq_gauss_sample(const float *mu, const float *logstd, int64_t logstd_period,
                                const float *unit, int64_t rows, int64_t a, float *out, float *noise,
                                void *stream) {

@@ -596,7 +596,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                         if (a < n_out) {
                             const float inv = sMisc[16 + a];
                             const float z = (tgt[a] - y[a]) * inv;
-                            dz[8 + a] = w * (z * z - 1.0f);
+                            dz[8 + a] = w * (z * z - 1.0f) + head.ent;
                             dz[a] = mq_act_grad(y[a], w * z * inv, lastact, lastleak);
                         }
                 }

@@ -79,8 +79,25 @@ class Gauss(object):
         logprob._mq_dev = True
         logprob._mq_op = ("gauss_logprob",)
 
+        def entropy(logstd_v):
+            # extension: the reference's Gauss has no entropy; H = sum(logstd) + A/2 (1 + ln 2 pi)
+            logstd_v = logstd_v.contiguous()
+            rows = logstd_v.numel() // n_act
+            batch_shape = tuple(logstd_v.shape)[:logstd_v.dim() - len(mean.shape)]
+            h = torch.empty(batch_shape, dtype=torch.float32, device=logstd_v.device)
+            D.call("mq_gauss_entropy", D.ptr(logstd_v), None, rows, n_act, D.ptr(h), None, D.stream())
+
+            def bpp(g):
+                d_ls = torch.empty_like(logstd_v)
+                D.call("mq_gauss_entropy", None, D.ptr(g.contiguous()), rows, n_act, None, D.ptr(d_ls), D.stream())
+                return (d_ls,)
+            return h, bpp
+        entropy._mq_dev = True
+        entropy._mq_op = ("gauss_entropy",)
+
         self.mean = mean
         self.logstd = logstd
+        self.entropy = Function(logstd, f=entropy, shape=())
         self.sample = Function(mean, logstd, f=sample, shape=mean.shape)
         self.logprob = Function(mean, logstd, f=logprob, shape=())
         self.n_params = self.logprob.n_params

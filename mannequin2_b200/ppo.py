@@ -110,12 +110,15 @@ class _Net(object):
 class PPOUpdater(object):
     def __init__(self, n_obs, n_act, *, hid=64, n_hid=2, gam=0.99, lam=0.95, pol_lr=3e-4, val_lr=3e-3,
                  horizon=10, clip=(0.8, 1.2), norm_horizon=2, state_dtype="float32",
-                 policy_params=None, value_params=None, discrete=False):
+                 policy_params=None, value_params=None, discrete=False, ent_coef=0.0):
         widths = [hid] * n_hid
         acts = [ACT_TANH] * n_hid + [ACT_NONE]
         # discrete=True: categorical policy over n_act actions (benchmarks/policy.py:15-17, distrib.Discrete);
         # `act` is then an int32 vector and travels to the kernels as one-hot rows
         self.discrete = bool(discrete)
+        # ent_coef (extension): adds ent_coef * Gauss.entropy to the objective; 0 = the reference's rule
+        self.ent_coef = float(ent_coef)
+        assert self.ent_coef == 0.0 or not self.discrete
         pnet = _lib.make_net(n_obs, widths + [n_act], acts, logstd=not self.discrete)
         vnet = _lib.make_net(n_obs, widths + [1], acts)
         if policy_params is None:                                   # policy.py:7-27, Gauss logstd zeros
@@ -187,6 +190,7 @@ class PPOUpdater(object):
                D.ptr(act), D.ptr(logp0), D.stream())
         head = MqHead()
         head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
+        head.ent = self.ent_coef
         head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
         pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
         if concurrent:

@@ -423,17 +423,24 @@ def value_sgd_step(theta, spec, opt, obs, target):
 
 
 def ppo_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4,
-                    lo=0.8, hi=1.2):
-    """benchmarks/ppo.py:33-40 on an already gathered minibatch."""
+                    lo=0.8, hi=1.2, ent_coef=0.0):
+    """benchmarks/ppo.py:33-40 on an already gathered minibatch.
+
+    ent_coef (not in the reference): + ent_coef * gauss_entropy
+    in the objective, i.e. + ent_coef on every logstd gradient entry."""
     logp, outs = policy_logprob(theta, spec, obs, act)
     g = ppo_clip_weight(logp, logp_old, adv, lo, hi).astype(np.float32)
-    opt.apply_gradient(policy_logprob_grad(theta, spec, obs, act, g, outs), lr=lr)
+    grad = policy_logprob_grad(theta, spec, obs, act, g, outs)
+    if ent_coef:
+        grad = np.array(grad, dtype=np.float32)
+        grad[spec["logstd_off"]:spec["logstd_off"] + act.shape[1]] += np.float32(ent_coef)
+    opt.apply_gradient(grad, lr=lr)
     return opt.get_value().astype(np.float32)
 
 
 def ppo_update(pol_theta, pol_spec, pol_opt, val_theta, val_spec, val_opt,
                norm, obs, act, rew, done, val_idx, pol_idx,
-               gam=0.99, lam=0.95, pol_lr=3e-4):
+               gam=0.99, lam=0.95, pol_lr=3e-4, ent_coef=0.0):
     """One chunk of benchmarks/ppo.py:22-40 + benchmarks/gae.py:34-75.
 
     obs[N+1,D], act[N,A], rew[N], done[N]; val_idx/pol_idx are the
@@ -449,7 +456,8 @@ def ppo_update(pol_theta, pol_spec, pol_opt, val_theta, val_spec, val_opt,
     logp_old, _ = policy_logprob(pol_theta, pol_spec, obs[:n], act)
     for idx in pol_idx:                                   # ppo.py:29-40
         pol_theta = ppo_policy_step(pol_theta, pol_spec, pol_opt, obs[:n][idx],
-                                    act[idx], adv_n[idx], logp_old[idx], pol_lr)
+                                    act[idx], adv_n[idx], logp_old[idx], pol_lr,
+                                    ent_coef=ent_coef)
     return pol_theta, val_theta, dict(adv=adv, ret=ret, adv_n=adv_n,
                                       logp_old=logp_old, value=value)
 

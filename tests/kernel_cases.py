@@ -571,6 +571,73 @@ def case_ops(B):
     assert b"broadcast" in lib.mq_last_error()
 
 
+def case_entropy(B, batches=(64, 300, 9000), steps=4):
+    """Gaussian entropy (named by the north star, absent from the reference -> pinned analytically): the
+    per-op kernel, and the entropy coefficient of the Gaussian heads in the FFMA tile kernel, the tcgen05 kernel
+    (9000 rows) and the persistent chain kernel: d/dlogstd gains exactly +ent, nothing else moves."""
+    lib = B.lib
+    rs = np.random.RandomState(47)
+    ls = (rs.randn(37, 5) * 0.3).astype(np.float32)
+    gg = rs.randn(37).astype(np.float32)
+    h, dls = B.zeros(37, np.float32), B.zeros((37, 5), np.float32)
+    hls, hg = B.up(ls), B.up(gg)
+    ok(B, lib.mq_gauss_entropy(B.ptr(hls), None, 37, 5, B.ptr(h), None, B.stream))
+    ok(B, lib.mq_gauss_entropy(None, B.ptr(hg), 37, 5, None, B.ptr(dls), B.stream))
+    close(B.down(h), O.gauss_entropy(ls, 5), what="gauss entropy")
+    assert np.array_equal(B.down(dls), np.repeat(gg[:, None], 5, axis=1))
+    eps = 1e-3                                              # the closed form against central differences
+    fd = (O.gauss_entropy(ls.astype(np.float64) + eps, 5) - O.gauss_entropy(ls.astype(np.float64) - eps, 5)) / (2 * eps)
+    assert np.max(np.abs(fd - 5.0)) < 1e-8                  # d/d(all logstd) = A
+    spec = O.policy_spec(11, 3)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    theta = np.concatenate([O.mlp_init(O._mlp_part(spec), rs, 0.1), (rs.randn(3) * 0.2).astype(np.float32)])
+    n = 12000
+    o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+    a = rs.randn(n, 3).astype(np.float32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
+    ht, ho, ha, hadv, hlp = B.up(theta), B.up(o), B.up(a), B.up(adv), B.up(lp_old)
+    ent = 0.037
+    for mb in batches:
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        wsb = lib.mq_fused_ws_bytes(net, mb)
+        ws = B.zeros(wsb, np.uint8)
+        grads = []
+        for e in (0.0, ent):
+            grad = B.zeros(5126, np.float32)
+            hd = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+            hd.ent = e
+            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(hd), 1.0 / mb,
+                                    B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+            grads.append(B.down(grad))
+        lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
+        want = np.array(O.policy_logprob_grad(theta, spec, o[idx], a[idx], O.ppo_clip_weight(lp, lp_old[idx], adv[idx]),
+                                              outs), dtype=np.float64)
+        close(grads[0], want, rtol=3e-5, atol_scale=3e-6, what="ppo grad, ent=0, mb=%d" % mb)
+        want[5123:] += ent
+        close(grads[1], want, rtol=3e-5, atol_scale=3e-6, what="ppo grad with entropy bonus, mb=%d" % mb)
+        assert np.array_equal(grads[0][:5123], grads[1][:5123])
+        assert np.max(np.abs((grads[1][5123:] - grads[0][5123:]) - ent)) < 1e-6
+    # chain kernel: `steps` Adam steps with the bonus against the oracle
+    mb = 64
+    idx = rs.randint(n, size=(steps, mb)).astype(np.int32)
+    opt = O.AdamO(theta, horizon=10)
+    th_ref = theta.copy()
+    for s_ in range(steps):
+        th_ref = O.ppo_policy_step(th_ref, spec, opt, o[idx[s_]], a[idx[s_]], adv[idx[s_]], lp_old[idx[s_]], ent_coef=ent)
+    ht2, hi = B.up(theta.copy()), B.up(idx)
+    val, m, v = B.up(theta.astype(np.float64)), B.zeros(5126, np.float64), B.zeros(5126, np.float64)
+    tw = (ctypes.c_double * 2)(0.0, 0.0)
+    hd = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
+    hd.ent = ent
+    ok(B, lib.mq_fused_train(net, B.ptr(ht2), B.ptr(val), B.ptr(m), B.ptr(v), L.MQ_F64, B.ptr(ho), ctypes.byref(hd),
+                             B.ptr(hi), steps, mb, 0.9, 0.99, tw, 3e-4, 1e-8, B.stream))
+    got = B.down(ht2)
+    assert np.max(np.abs(got - th_ref)) < 2e-6 * (1 + steps) + 1e-6, np.max(np.abs(got - th_ref))
+    assert np.all(got[5123:] > theta[5123:] - 1e-3)
+
+
 def case_tc_paths(B):
     """tcgen05 / TMEM kernel (mq_tc.cu) forced on (mode 2) for every net it accepts: the same fp32
     bars as the FFMA kernels (three-plane bf16 operands keep 24 mantissa bits)."""
@@ -822,4 +889,4 @@ def case_gemm_tc(B):
 
 
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_gemm_tc, case_fused_heads,
-             case_fused_gauss_ppo, case_discrete, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_discrete, case_entropy, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]

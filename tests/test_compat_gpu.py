@@ -487,6 +487,35 @@ def test_independent_learners_on_concurrent_streams():
             assert np.array_equal(upds[k].value.theta.cpu().numpy(), alone[k][1]), (n, k)
 
 
+def test_gauss_entropy_function():
+    """Gauss.entropy (an extension -- the reference's Gauss exports no entropy, distrib.py:70-76):
+    H = sum(logstd) + A/2 (1 + ln 2 pi) as a Function of the logstd sub-graph, for a per-row logstd network and for
+    the shared Params(A) logstd; the backward pass hands g to every logstd entry."""
+    from mannequin2_b200.basicnet import Input, Affine, Tanh
+    from mannequin2_b200.distrib import Gauss
+    np.random.seed(12)
+    rs = np.random.RandomState(13)
+    x = Input(6)
+    mean = Affine(Tanh(Affine(x, 16)), 4)
+    lsn = Affine(Tanh(Affine(x, 8)), 4)
+    pol = Gauss(mean=mean, logstd=lsn)
+    obs = rs.randn(9, 6).astype(np.float32)
+    h, bpp = pol.entropy.evaluate(obs)
+    const = 0.5 * 4 * (1.0 + np.log(2.0 * np.pi))
+    assert_close(h, np.sum(np.asarray(lsn(obs), dtype=np.float64), axis=-1) + const, rtol=1e-5, atol_scale=1e-6)
+    assert pol.entropy.n_params == lsn.n_params
+    g = rs.randn(9).astype(np.float32)
+    _, b2 = lsn.evaluate(obs)
+    assert_close(np.asarray(bpp(g)), np.asarray(b2(np.repeat(g[:, None], 4, axis=1))), rtol=1e-5, atol_scale=1e-6)
+    pol2 = Gauss(mean=mean)                                   # shared logstd = the last 4 parameters
+    theta = np.array(pol2.get_params())
+    theta[-4:] = [0.3, -0.2, 0.1, 0.05]
+    pol2.load_params(theta)
+    h2, bpp2 = pol2.entropy.evaluate(obs[:1])
+    assert abs(float(np.asarray(h2).reshape(-1)[0]) - (0.25 + const)) < 1e-5
+    assert np.allclose(np.asarray(bpp2(np.float32(1.5))), 1.5)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and

@@ -49,6 +49,7 @@ if __name__ == "__main__":
     # tensor-core (tcgen05) and peer-memory cases have no host emulation: they are checked on a B200 only
     gpu_only = {"case_gemm_tc", "case_tc_paths", "case_reduce_step"}
     small["case_discrete"] = dict(batches=(64, 300))
+    small["case_entropy"] = dict(batches=(64, 300))
     for fn in K.ALL_CASES:
         if fn.__name__ in gpu_only:
             print("--  %-28s (B200 only)" % fn.__name__)
