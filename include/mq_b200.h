@@ -95,6 +95,9 @@ int mq_debug_use_chain_grad(int on);
 int mq_debug_set_chain_warps(int nw);
 /* developer aid: tcgen05 path of mq_fused_grad / mq_fused_forward: 0 never, 1 automatic (batch >= 8192), 2 whenever the net fits */
 int mq_debug_set_tc_mode(int mode);
+/* developer aid: which tcgen05 fused-MLP kernel: 1 (default) one 128-row tile per SM (mq_tc.cu); 0 = two 64-row tiles in
+ * flight per SM (mq_tc2.cu, an experiment that measured slower: DESIGN.md 3.1), falling back to 1 for nets it does not fit */
+int mq_debug_set_tc_variant(int variant);
 /* developer aid: tcgen05 GEMM for wide layers: 0 never, 1 automatic (>= 2^26 multiply-adds), 2 whenever possible */
 int mq_debug_set_gemm_tc_mode(int mode);
 int mq_version(void);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mq_debug_use_chain_grad": (c_int, [c_int]),
     "mq_debug_set_chain_warps": (c_int, [c_int]),
     "mq_debug_set_tc_mode": (c_int, [c_int]),
+    "mq_debug_set_tc_variant": (c_int, [c_int]),
     "mq_debug_set_gemm_tc_mode": (c_int, [c_int]),
     "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,

@@ -40,7 +40,8 @@
 #ifndef MQ_EMU
 
 #define HALF_LOG_2PI 0.91893853320467274178f
-#define TC_NT 512
+#define TC_NT 512                // worker threads (16 warps)
+#define TC_NTI 544               // + one warp that only issues MMAs (tc_grad_kernel)
 #define TC_ROWS 128              // MMA M of the row-major products
 #define TC_HID 64                // padded hidden width
 #define TC_NO 16                 // padded output width
@@ -99,7 +100,6 @@ __device__ __forceinline__ void tc_load_chunk(const unsigned char *buf, int plan
 // ---- MMA issue helpers ----------------------------------------------------------------------------
 // (called by the elected lane of a warp inside warp-uniform control flow, so that descriptors live in
 // uniform registers).  A view is the two descriptor words of its first K step plus the K-step advance.
-struct TcView { uint32_t lo, hi, k16; };
 
 // activation buffer plane at `addr` viewed K-major (M = rows, K = features): LBO = chunk stride, SBO = row-group stride
 __device__ __forceinline__ TcView tc_rows_k(uint32_t addr) {
@@ -109,15 +109,6 @@ __device__ __forceinline__ TcView tc_rows_k(uint32_t addr) {
 __device__ __forceinline__ TcView tc_feat_mn(uint32_t addr) {
     return TcView{tc_desc_lo(addr, 128u), tc_desc_hi(TC_CHUNK_BYTES), 256u >> 4};
 }
-// forward weight image [k chunk][plane][n][8 k] from row `addr` on, K-major (N = plane*np + n, K = in)
-__device__ __forceinline__ TcView tc_wf_k(uint32_t addr, int np) {
-    return TcView{tc_desc_lo(addr, 3u * (uint32_t)np * 16u), tc_desc_hi(128u), (6u * (uint32_t)np * 16u) >> 4};
-}
-// backward weight image [plane][k chunk][n][8 k] from `addr` on, MN-major (N' = plane*kp + k, K' = n)
-__device__ __forceinline__ TcView tc_wb_mn(uint32_t addr, int np) {
-    return TcView{tc_desc_lo(addr, 128u), tc_desc_hi((uint32_t)np * 16u), 256u >> 4};
-}
-
 // D[128 x (two blocks of nb)] = sum over plane pairs of A_i B_j, A row-major planes (2,1,0 in memory, `a_plane`
 // bytes apart, a0 = plane 0), B a weight image whose planes sit side by side along N (b_plane16 = plane stride >> 4
 // in descriptor units).  Four instructions per K step.
@@ -160,35 +151,23 @@ __device__ __forceinline__ void tc_feat_product(uint32_t acc_tmem, uint32_t da_b
     }
 }
 
-// branch-free tanh on raw MUFU ops: 1 - 2/(2^(2 log2(e) |x|) + 1) with the sign of x, odd polynomial below 0.1
-// (same formulation and error, ~2e-7 absolute, as mq_tanh)
-__device__ __forceinline__ float tc_tanh(float x) {
-    float t, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.8853900817779268f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
-    const float big = copysignf(fmaf(r, -2.0f, 1.0f), x);
-    const float x2 = x * x;
-    const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
-    return fabsf(x) < 0.1f ? poly : big;
-}
-
-template <int ACT>
-__device__ __forceinline__ float tc_act(float z, float leak) {
-    if (ACT == MQ_ACT_TANH) return tc_tanh(z);
-    return z < 0.0f ? z * leak : z;
-}
-
 // ---- the kernel ---------------------------------------------------------------------------
 template <int K0, int HACT>
-__global__ void __launch_bounds__(TC_NT, 1)
+__global__ void __launch_bounds__(TC_NTI, 1)
 tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restrict__ x,
                const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
                float *__restrict__ partial, float *__restrict__ out, float *__restrict__ logp_out, long long *prof) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_mbar_dw;      // completion of the dW / db products of a backward phase (see below)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler too
+    // Warps 0..15 are WORKERS (gathers, epilogues, head); warp 16 only ISSUES the MMAs.  A thread that issues MMAs is held up
+    // by the tensor pipe's back-pressure for about as long as the products take, so a worker warp doing it delayed every
+    // epilogue that could have run under the dW products.  The issuer meets the workers at the publish barriers only.
+    const bool worker = warp < TC_NT / 32;
+    const int stid = worker ? tid : (1 << 28);                    // start index of the workers' strided loops
     // developer aid (compile with -DMQ_TC_PROFILE): per-phase cycles of CTA 0 and every CTA's start / end time
 #ifdef MQ_TC_PROFILE
     long long t_last = 0;
@@ -214,12 +193,13 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_mbar)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_mbar_dw)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     TC_MARK(21);
     // clear shared memory except the hidden activation buffers (every tile rewrites all of their rows)
-    for (int i = tid; i < p.off_act[1] / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = p.off_wf[0] / 16 + tid; i < p.smem_bytes / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = stid; i < p.off_act[1] / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = p.off_wf[0] / 16 + stid; i < p.smem_bytes / 16; i += TC_NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     TC_MARK(22);
     {
@@ -227,7 +207,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         const uint32_t ob = *reinterpret_cast<uint16_t *>(&one);
         for (int l = 0; l < L; ++l) {
             uint32_t *ones = reinterpret_cast<uint32_t *>(smem + p.off_act[l] + 3 * p.act_plane[l]);
-            for (int i = tid; i < TC_CHUNK_BYTES / 4; i += TC_NT) ones[i] = ob | (ob << 16);
+            for (int i = stid; i < TC_CHUNK_BYTES / 4; i += TC_NT) ones[i] = ob | (ob << 16);
         }
     }
     float *sBias = reinterpret_cast<float *>(smem + p.off_bias);      // [L][64]
@@ -242,7 +222,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         items[0] = 0;
         for (int l = 0; l < L; ++l) items[l + 1] = items[l] + (p.kp[l] / 8) * p.net.out[l];
 #pragma unroll 2
-        for (int it = tid; it < items[L]; it += TC_NT) {
+        for (int it = stid; it < items[L]; it += TC_NT) {
             int l = 0;
 #pragma unroll
             for (int q = 1; q < TC_MAXL; ++q) if (q < L && it >= items[q]) l = q;
@@ -268,7 +248,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
             }
         }
         for (int l = 0; l < L; ++l)
-            for (int n = tid; n < p.net.out[l]; n += TC_NT) sBias[l * 64 + n] = __ldg(theta + p.net.b_off[l] + n);
+            for (int n = stid; n < p.net.out[l]; n += TC_NT) sBias[l * 64 + n] = __ldg(theta + p.net.b_off[l] + n);
         if (p.net.logstd_off >= 0 && tid < n_out) {
             const float ls = __ldg(theta + p.net.logstd_off + tid);
             sMisc[tid] = ls;
@@ -297,14 +277,14 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         int r = tid / n_in, f = tid - r * n_in;
 #pragma unroll
         for (int j = 0; j < XE; ++j) {                  // e = tid + j * TC_NT, stepped without divisions
-            xrf[j] = r < TC_ROWS ? ((r << 8) | f) : -1;
+            xrf[j] = (worker && r < TC_ROWS) ? ((r << 8) | f) : -1;
             r += p.x_step_q; f += p.x_step_r;
             if (f >= n_in) { f -= n_in; ++r; }
         }
         r = tid / n_out; f = tid - r * n_out;
 #pragma unroll
         for (int j = 0; j < HE; ++j) {
-            hrf[j] = r < TC_ROWS ? ((r << 8) | f) : -1;
+            hrf[j] = (worker && r < TC_ROWS) ? ((r << 8) | f) : -1;
             r += p.h_step_q; f += p.h_step_r;
             if (f >= n_out) { f -= n_out; ++r; }
         }
@@ -379,6 +359,8 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     TC_MARK(0);
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
     const uint32_t mbar = tc_smem_u32(&s_mbar);
+    const uint32_t mbar_dw = tc_smem_u32(&s_mbar_dw);
+    uint32_t parity_dw = 0;
     const uint32_t sbase = tc_smem_u32(smem);
     const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
     uint32_t parity = 0;
@@ -395,6 +377,7 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
     auto flush_grad = [&]() {
         float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
         const bool add = flushed;
+        if (worker) {
         // M = 64 accumulators: row i is lane i%16 of the warps of quarter i/16; the four warps of a quarter
         // split the columns of a block
         const int i = quarter * 16 + lane;
@@ -439,12 +422,73 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
                 }
             }
         }
+        }
         flushed = true;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
+    if (!worker) {
+        // ---- issuer warp: the same barrier sequence as the workers, MMAs instead of epilogues -----------------------
+        int ord = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ord) {
+            tc_publish();                                               // input tile staged
+            for (int l = 0; l < L; ++l) {
+                if (tc_elect_one()) {
+                    tc_rows_product(tm + p.col_za, sbase + p.off_act[l] + 2 * p.act_plane[l], p.act_plane[l],
+                                    tc_wf_k(sbase + p.off_wf[l], p.np[l]), 0, (uint32_t)p.np[l], p.np[l], p.kp[l] / 16);
+                    tc_commit(mbar);
+                }
+                __syncwarp();
+                tc_publish();                                           // A_{l+1} (l < L-1) or dZ_{L-1} (head) published
+            }
+            if (!p.with_grad) continue;
+            for (int l = L - 1; l >= 0; --l) {
+                if (tc_elect_one()) {
+                    if (l == L - 1) {
+                        // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
+                        tc_rows_product(tm + p.col_za, sbase + p.off_dzl + 2 * (2 * TC_CHUNK_BYTES), 2 * TC_CHUNK_BYTES,
+                                        tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l], 1);
+                        tc_commit(mbar);                 // dA alone: the epilogue's arithmetic runs under the dW products
+                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l], p.act_plane[l], sbase + p.off_dzl,
+                                        2 * TC_CHUNK_BYTES, TC_NO, 0, dw_ksteps, dw_started);
+                        const TcView ones = tc_feat_mn(sbase + p.off_act[l] + 3 * p.act_plane[l]);
+                        const TcView dzl = tc_feat_mn(sbase + p.off_dzl);
+                        const uint32_t dzp16 = (2u * TC_CHUNK_BYTES) >> 4;
+                        uint32_t alo = ones.lo, blo = dzl.lo;
+#pragma unroll 1
+                        for (int k = 0; k < dw_ksteps; ++k) {    // rows 0-7 of the result: column sums of [dZ_1|dZ_0] (+ dZ_2)
+                            tc_mma(tm + p.col_rb, alo, ones.hi, blo + dzp16, dzl.hi, tc_idesc(64, 2 * TC_NO, 1, 1), (dw_started || k > 0) ? 1u : 0u);
+                            tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, TC_NO, 1, 1), 1u);
+                            alo += ones.k16;
+                            blo += dzl.k16;
+                        }
+                    } else {
+                        // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
+                        if (l > 0) {
+                            tc_rows_product(tm + p.col_za, sbase + p.off_act[l + 1] + 2 * p.act_plane[l + 1], p.act_plane[l + 1],
+                                            tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l],
+                                            p.np[l] / 16);
+                            tc_commit(mbar);
+                        }
+                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l + 1], p.act_plane[l + 1], sbase + p.off_act[l],
+                                        p.act_plane[l], p.kp[l], 8, dw_ksteps, dw_started);
+                    }
+                    tc_commit(l == 0 ? mbar : mbar_dw);  // l == 0 has no dA: its dW product is the phase
+                }
+                __syncwarp();
+                if (l == 0) break;
+                tc_publish();                                           // dZ_{l-1} published
+            }
+            dw_started = true;
+            if ((ord + 1) % TC_FLUSH_TILES == 0 && tile + gridDim.x < ntiles) {
+                flush_grad();                                           // barrier only
+                dw_started = false;
+            }
+        }
+        if (p.with_grad && dw_started) flush_grad();
+    } else {
     int ord = 0;                                        // ordinal of the tile within this CTA
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ord) {
         const int64_t row0 = tile * tr;
@@ -458,15 +502,6 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         TC_MARK(2);
         // ---- forward ------------------------------------------------------------------------------
         for (int l = 0; l < L; ++l) {
-            if (warp == 0) {
-                if (tc_elect_one()) {
-                    tc_rows_product(tm + p.col_za, sbase + p.off_act[l] + 2 * p.act_plane[l], p.act_plane[l],
-                                    tc_wf_k(sbase + p.off_wf[l], p.np[l]), 0, (uint32_t)p.np[l], p.np[l], p.kp[l] / 16);
-                    tc_commit(mbar);
-                }
-                __syncwarp();
-            }
-            TC_MARK(3);
             if (l == L - 1) {
                 // gathers for the NEXT tile (rows, head inputs) and the source rows of the tile after it: issued here so
                 // that they have the last product and the whole head phase to arrive -- the next publish (a MEMBAR)
@@ -622,52 +657,33 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         if (!p.with_grad) continue;
         // ---- backward -----------------------------------------------------------------------------
         for (int l = L - 1; l >= 0; --l) {
-            if (warp == 0) {
-                if (tc_elect_one()) {
-                    if (l == L - 1) {
-                        // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
-                        tc_rows_product(tm + p.col_za, sbase + p.off_dzl + 2 * (2 * TC_CHUNK_BYTES), 2 * TC_CHUNK_BYTES,
-                                        tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l], 1);
-                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l], p.act_plane[l], sbase + p.off_dzl,
-                                        2 * TC_CHUNK_BYTES, TC_NO, 0, dw_ksteps, dw_started);
-                        const TcView ones = tc_feat_mn(sbase + p.off_act[l] + 3 * p.act_plane[l]);
-                        const TcView dzl = tc_feat_mn(sbase + p.off_dzl);
-                        const uint32_t dzp16 = (2u * TC_CHUNK_BYTES) >> 4;
-                        uint32_t alo = ones.lo, blo = dzl.lo;
-#pragma unroll 1
-                        for (int k = 0; k < dw_ksteps; ++k) {    // rows 0-7 of the result: column sums of [dZ_1|dZ_0] (+ dZ_2)
-                            tc_mma(tm + p.col_rb, alo, ones.hi, blo + dzp16, dzl.hi, tc_idesc(64, 2 * TC_NO, 1, 1), (dw_started || k > 0) ? 1u : 0u);
-                            tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, TC_NO, 1, 1), 1u);
-                            alo += ones.k16;
-                            blo += dzl.k16;
-                        }
-                    } else {
-                        // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
-                        if (l > 0)
-                            tc_rows_product(tm + p.col_za, sbase + p.off_act[l + 1] + 2 * p.act_plane[l + 1], p.act_plane[l + 1],
-                                            tc_wb_mn(sbase + p.off_wb[l], p.np[l]), 1, (uint32_t)p.wb_plane[l] >> 4, p.kp[l],
-                                            p.np[l] / 16);
-                        tc_feat_product(tm + p.col_acc[l], sbase + p.off_act[l + 1], p.act_plane[l + 1], sbase + p.off_act[l],
-                                        p.act_plane[l], p.kp[l], 8, dw_ksteps, dw_started);
-                    }
-                    tc_commit(mbar);
-                }
-                __syncwarp();
-            }
             TC_MARK(12);
             if (l == 0) { pending = true; break; }
             tc_wait(mbar, parity); parity ^= 1;
             TC_MARK(13 + l);
-            // dZ_{l-1} = dA_l * act'(A_l), written over A_l (the fp32 A_l was saved in TMEM by the forward epilogue)
+            // dZ_{l-1} = dA_l * act'(A_l), written over A_l (the fp32 A_l was saved in TMEM by the forward epilogue).
+            // Only dA_l has been waited for: the arithmetic and the split into planes run while the tensor pipe still
+            // works on dW_l / db_l, which READ A_l -- so the stores wait for the second barrier.
             float a[16], g[16], g2[16];
             tc_ld16(tlane + p.col_za + cg * 16, g);
             tc_ld16(tlane + p.col_za + TC_HID + cg * 16, g2);
             tc_ld16(tlane + p.col_save + (l - 1) * TC_HID + cg * 16, a);
             const float leak = p.net.leak[l - 1];
+            uint32_t w[2][3][4];
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], g[j] + g2[j], HACT, leak);
-            tc_store_chunk(smem + p.off_act[l], p.act_plane[l], cg * 2, row, g);
-            tc_store_chunk(smem + p.off_act[l], p.act_plane[l], cg * 2 + 1, row, g + 8);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc_split_pair(g[8 * c + 2 * j], g[8 * c + 2 * j + 1], w[c][0][j], w[c][1][j], w[c][2][j]);
+            tc_wait(mbar_dw, parity_dw); parity_dw ^= 1;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                unsigned char *d = tc_chunk_ptr(smem + p.off_act[l], p.act_plane[l], cg * 2 + c, row);
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+                    *reinterpret_cast<uint4 *>(d - pl * p.act_plane[l]) = make_uint4(w[c][pl][0], w[c][pl][1], w[c][pl][2], w[c][pl][3]);
+            }
             tc_publish();
             TC_MARK(16 + l);
         }
@@ -686,9 +702,10 @@ tc_grad_kernel(TcPlan p, const float *__restrict__ theta, const float *__restric
         if (dw_started) flush_grad();
         else if (!flushed) {
             float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
-            for (int j = tid; j < p.net.n_params; j += TC_NT) dst[j] = 0.0f;
+            for (int j = stid; j < p.net.n_params; j += TC_NT) dst[j] = 0.0f;
         }
     }
+    }   // workers
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     TC_MARK(20);
@@ -933,6 +950,11 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
 long long *mq_phase_prof_ptr();
 static int g_tc_mode = 1;            // 0: never, 1: automatic (large batches), 2: whenever the net fits
 extern "C" int mq_debug_set_tc_mode(int mode) { g_tc_mode = mode; return MQ_OK; }
+static int g_tc_variant = 1;         // 1: one 128-row tile per SM (this file), 0: two 64-row tiles in flight (mq_tc2.cu)
+extern "C" int mq_debug_set_tc_variant(int v) { g_tc_variant = v; return MQ_OK; }
+int mq_tc2_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx, int64_t batch,
+                  const mq_head_t *head, int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes,
+                  int *parts_out, void *stream);
 
 // Launches the tensor-core kernel when the net fits and the batch is large enough.
 // Returns MQ_ERR_UNSUPPORTED (without an error message side effect that matters) otherwise.
@@ -942,6 +964,10 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
                  void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
     if (g_tc_mode == 0) return MQ_ERR_UNSUPPORTED;
     if (g_tc_mode == 1 && batch < 8192) return MQ_ERR_UNSUPPORTED;
+    if (g_tc_variant == 0) {
+        const int rc2 = mq_tc2_launch(net, theta, x, row_idx, batch, head, with_grad, out, logp, ws, ws_bytes, grid_out, stream);
+        if (rc2 != MQ_ERR_UNSUPPORTED) return rc2;
+    }
     TcPlan p;
     if (!tc_plan_build(net, batch, with_grad, head, &p)) return MQ_ERR_UNSUPPORTED;
     const int64_t ntiles = mq_ceil_div(batch, p.tile_rows);
@@ -955,7 +981,7 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
     do {                                                                                                                 \
         e = cudaFuncSetAttribute(tc_grad_kernel<K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
         if (e == cudaSuccess)                                                                                            \
-            e = mq_launch_pdl(tc_grad_kernel<K0_, ACT_>, dim3(grid), dim3(TC_NT), (size_t)p.smem_bytes, stream, p, theta, \
+            e = mq_launch_pdl(tc_grad_kernel<K0_, ACT_>, dim3(grid), dim3(TC_NTI), (size_t)p.smem_bytes, stream, p, theta, \
                               x, row_idx, batch, *head, (float *)ws, out, logp, mq_phase_prof_ptr());                    \
     } while (0)
     const int hact = net->act[0];
@@ -1011,4 +1037,5 @@ int mq_tc_launch(const mq_net_t *, const float *, const float *, const int32_t *
 int mq_tc_es_launch(const mq_net_t *, const float *, const float *, int64_t, const float *, int64_t, const float *, float *,
                     void *) { return MQ_ERR_UNSUPPORTED; }
 extern "C" int mq_debug_set_tc_mode(int) { return MQ_OK; }
+extern "C" int mq_debug_set_tc_variant(int) { return MQ_OK; }
 #endif

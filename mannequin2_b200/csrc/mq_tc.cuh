@@ -109,4 +109,35 @@ __device__ __forceinline__ void tc_split_pair(float a, float b, uint32_t &w0, ui
     w2 = *reinterpret_cast<uint32_t *>(&h2);
 }
 
+// ---- operand views shared by the fused-MLP kernels (mq_tc.cu, mq_tc2.cu) -----------------------
+// A view is the two descriptor words of its first K step plus the K-step advance (descriptor units of 16 bytes).
+struct TcView { uint32_t lo, hi, k16; };
+
+// forward weight image [k chunk][plane][n][8 k] from row `addr` on, K-major (N = plane*np + n, K = in)
+__device__ __forceinline__ TcView tc_wf_k(uint32_t addr, int np) {
+    return TcView{tc_desc_lo(addr, 3u * (uint32_t)np * 16u), tc_desc_hi(128u), (6u * (uint32_t)np * 16u) >> 4};
+}
+// backward weight image [plane][k chunk][n][8 k] from `addr` on, MN-major (N' = plane*kp + k, K' = n)
+__device__ __forceinline__ TcView tc_wb_mn(uint32_t addr, int np) {
+    return TcView{tc_desc_lo(addr, 128u), tc_desc_hi((uint32_t)np * 16u), 256u >> 4};
+}
+
+// branch-free tanh on raw MUFU ops: 1 - 2/(2^(2 log2(e) |x|) + 1) with the sign of x, odd polynomial below 0.1
+// (same formulation and error, ~2e-7 absolute, as mq_tanh)
+__device__ __forceinline__ float tc_tanh(float x) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    const float big = copysignf(fmaf(r, -2.0f, 1.0f), x);
+    const float x2 = x * x;
+    const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
+    return fabsf(x) < 0.1f ? poly : big;
+}
+
+template <int ACT>
+__device__ __forceinline__ float tc_act(float z, float leak) {
+    if (ACT == MQ_ACT_TANH) return tc_tanh(z);
+    return z < 0.0f ? z * leak : z;
+}
+
 #endif  // MQ_EMU

@@ -639,8 +639,18 @@ def case_entropy(B, batches=(64, 300, 9000), steps=4):
 
 
 def case_tc_paths(B):
-    """tcgen05 / TMEM kernel (mq_tc.cu) forced on (mode 2) for every net it accepts: the same fp32
-    bars as the FFMA kernels (three-plane bf16 operands keep 24 mantissa bits)."""
+    """tcgen05 / TMEM kernels forced on (mode 2) for every net they accept -- the one-tile kernel with its issuer warp
+    (mq_tc.cu, the default) and the two-tiles-in-flight variant (mq_tc2.cu): the same fp32 bars as the FFMA kernels
+    (three-plane bf16 operands keep 24 mantissa bits)."""
+    for variant in (1, 0):
+        ok(B, B.lib.mq_debug_set_tc_variant(variant))
+        try:
+            _tc_paths(B)
+        finally:
+            B.lib.mq_debug_set_tc_variant(1)
+
+
+def _tc_paths(B):
     lib = B.lib
     rs = np.random.RandomState(15)
     ok(B, lib.mq_debug_set_tc_mode(2))

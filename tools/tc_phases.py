@@ -19,6 +19,7 @@ net = upd.policy.net
 lib = L.lib()
 wsb = lib.mq_fused_ws_bytes(C.byref(net), MB); ws = D.workspace("t", wsb)
 lib.mq_debug_set_tc_mode(2)
+lib.mq_debug_set_tc_variant(int(os.environ.get("TC_VARIANT", "1")))
 def run():
     D.call("mq_fused_grad", C.byref(net), D.ptr(upd.policy.theta), D.ptr(od), D.ptr(idxd), MB,
            C.byref(head), 1.0 / MB, D.ptr(upd.policy.grad), None, None, D.ptr(ws), wsb, D.stream())
@@ -28,12 +29,15 @@ prof = torch.zeros(512, dtype=torch.int64, device="cuda")
 lib.mq_debug_set_phase_buffer(prof.data_ptr())
 run(); torch.cuda.synchronize()
 lib.mq_debug_set_phase_buffer(None)
-names = {0: "setup", 1: "wait_prev_tile", 2: "stage_x", 3: "issue_fwd", 4: "prefetch", 5: "wait_fwd0", 6: "wait_fwd1", 7: "wait_fwd2",
-         8: "epi0", 9: "epi1", 11: "head", 12: "issue_bwd", 15: "wait_bwd2", 14: "wait_bwd1", 18: "epi_b2", 17: "epi_b1", 19: "wait_last", 20: "final", 21: "setup:alloc", 22: "setup:zero", 23: "setup:ones", 24: "setup:images", 25: "setup:coords"}
+names = {0: "setup", 1: "wait_prev_tile", 2: "stage_x", 4: "prefetch", 5: "wait_fwd0", 6: "wait_fwd1", 7: "wait_fwd2",
+         8: "epi0", 9: "epi1", 11: "head", 12: "bwd_gap", 15: "wait_bwd2", 14: "wait_bwd1", 18: "epi_b2", 17: "epi_b1", 19: "wait_last", 20: "final", 21: "setup:alloc", 22: "setup:zero", 23: "setup:ones", 24: "setup:images", 25: "setup:coords"}
 p = prof.cpu().numpy()
-print("total cycles CTA0: %d (%.1f us at 1.965 GHz)" % (p[:32].sum(), p[:32].sum() / 1965.0))
-for i in range(32):
-    if p[i]: print("  %-16s %8d" % (names.get(i, i), p[i]))
+variant = int(os.environ.get("TC_VARIANT", "1"))      # 1: one-tile kernel (default), 0: two-tile kernel (groups 0 and 1 of CTA 0)
+for grp in range(2 if variant == 0 else 1):
+    q = p[grp * 32:grp * 32 + 32]
+    print("total cycles CTA0 group %d: %d (%.1f us at 1.965 GHz)" % (grp, q.sum(), q.sum() / 1965.0))
+    for i in range(32):
+        if q[i]: print("  %-16s %8d" % (names.get(i, i), q[i]))
 g = p[64:64 + 2 * 148].reshape(148, 2)
 t0 = g[:, 0].min()
 print("CTA start offsets (us): min %.1f median %.1f max %.1f;  CTA end offsets: min %.1f median %.1f max %.1f;  durations: min %.1f median %.1f max %.1f" % (
@@ -44,4 +48,4 @@ for k in range(10):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
 print("launch (incl. reduce) median %.1f us" % (np.median(ts) * 1e3))
-lib.mq_debug_set_tc_mode(1)
+lib.mq_debug_set_tc_mode(1); lib.mq_debug_set_tc_variant(1)

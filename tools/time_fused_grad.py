@@ -19,8 +19,9 @@ net = upd.policy.net
 lib = L.lib()
 wsb = lib.mq_fused_ws_bytes(C.byref(net), MB); ws = D.workspace("t", wsb)
 grads = {}
-for tb in [int(x) for x in (sys.argv[1:] or ["-1", "16", "128"])]:
-    lib.mq_debug_set_tc_mode(2 if tb < 0 else 0)      # -1: tcgen05 kernel
+for tb in [int(x) for x in (sys.argv[1:] or ["-1", "-2", "16", "128"])]:
+    lib.mq_debug_set_tc_mode(2 if tb < 0 else 0)      # -1: tcgen05 kernel (one tile per SM + issuer warp), -2: two-tiles-in-flight variant
+    lib.mq_debug_set_tc_variant(0 if tb == -2 else 1)
     lib.mq_debug_use_chain_grad(0 if tb == 128 else 1)
     lib.mq_debug_set_chain_warps(0 if tb == 128 or tb < 0 else tb)
     lib.mq_debug_set_tile_rows(128 if tb == 128 else 0)
@@ -34,6 +35,6 @@ for tb in [int(x) for x in (sys.argv[1:] or ["-1", "16", "128"])]:
     ms = float(np.median(ts[3:]))
     grads[tb] = upd.policy.grad.cpu().numpy().copy()
     print("tile_rows=%3d  %.1f us  %.2f TFLOP/s fp32 (%.1f%% of 74.4)" % (tb, ms * 1e3, MB * 28544 / ms / 1e9, MB * 28544 / ms / 1e9 / 74.4 * 100))
-lib.mq_debug_set_tile_rows(0); lib.mq_debug_use_chain_grad(1); lib.mq_debug_set_chain_warps(0); lib.mq_debug_set_tc_mode(1)
+lib.mq_debug_set_tile_rows(0); lib.mq_debug_use_chain_grad(1); lib.mq_debug_set_chain_warps(0); lib.mq_debug_set_tc_mode(1); lib.mq_debug_set_tc_variant(1)
 k0 = list(grads)[0]
 for k in grads: print("max |grad(tb=%d) - grad(tb=%d)| = %.2e" % (k, k0, np.abs(grads[k] - grads[k0]).max()))
