@@ -609,7 +609,84 @@ class VAEWorkload(object):
                     note="fp32-exact product = 6 bf16 plane pairs; bound by in-kernel operand staging (DESIGN.md 3.5)")
 
 
-WORKLOADS = {"ppo": PPOWorkload, "ppo_large": PPOLargeWorkload, "mlp": MLPWorkload, "es": ESWorkload, "vae": VAEWorkload}
+class ClosedLoopWorkload(PPOLargeWorkload):
+    """the rollout side and the update path as one closed loop on the device.  One step = 4,096
+    synthetic environments advanced 256 steps in lock step by the current policy (observation normaliser, policy
+    forward, Gaussian sample, environment: three launches per time step, replayed as one CUDA graph) = 2^20 transitions,
+    then the configs[2] update on them (per-segment bootstrap, value forward, GAE, 10 epochs x 16 minibatches of 65,536
+    rows for both nets).  Only the minibatch index tables come from the host (the reference draws them with NumPy)."""
+    name = "ppo_closed_loop_4096envs_x256steps + configs[2] update"
+    metric = "ppo_closed_loop_transitions_per_s"
+    N_ENV, T_LEN = 4096, 256
+    step_cpu = None                                     # the CPU port covers the update path only
+
+    def __init__(self, n_rollouts=2, seed=1):
+        rs = np.random.RandomState(seed)
+        self.N = self.N_ENV * self.T_LEN
+        per = self.N // self.MB
+        self.tables = [tuple(np.concatenate([rs.permutation(self.N).astype(np.int32).reshape(per, self.MB)
+                                             for _e in range(self.EPOCHS)]) for _t in range(2))
+                       for _ in range(n_rollouts)]
+        self.units_per_step = self.N
+        self.steps_per_net = self.EPOCHS * per
+
+    def setup_gpu(self):
+        import torch
+        from mannequin2_b200 import _device as D
+        from mannequin2_b200.ppo import PPOUpdater
+        from mannequin2_b200.rollout import BatchedActor, SyntheticEnv
+        np.random.seed(0)
+        self.torch, self.D = torch, D
+        self.env = SyntheticEnv(self.N_ENV, horizon=256, seed=3)
+        self.upd = PPOUpdater(11, 3)
+        self.actor = BatchedActor(self.env, self.upd.policy, seed=5, use_graph=True)
+        self.dev = [tuple(D.from_host(x) for x in r) for r in self.tables]
+        self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r) for r in self.tables[:1]]
+        self.out_pinned = (torch.empty(5126, dtype=torch.float32).pin_memory(),
+                           torch.empty(4993, dtype=torch.float32).pin_memory())
+        self.h2d = sum(x.nbytes for x in self.tables[0])
+        self.d2h = (5126 + 4993) * 4
+        self.mean_rewards = []
+
+    def step_gpu(self, i):
+        chunk = self.actor.collect(self.T_LEN)
+        self.upd.update_rollout(chunk, self.N_ENV, self.T_LEN, *self.dev[i % len(self.dev)])
+
+    def step_e2e(self, i):
+        t = self.torch
+        main = t.cuda.current_stream()
+        tabs = [x.to(self.D.device(), non_blocking=True) for x in self.pinned[0]]
+        chunk = self.actor.collect(self.T_LEN)
+        self.upd.update_rollout(chunk, self.N_ENV, self.T_LEN, *tabs)
+        self.out_pinned[0].copy_(self.upd.policy.theta, non_blocking=True)
+        self.out_pinned[1].copy_(self.upd.value.theta, non_blocking=True)
+        main.synchronize()
+        self.mean_rewards.append(float(chunk["rew"].mean()))
+
+    def launches_per_step(self):
+        return 3 * self.T_LEN + 3 + 13 + 2 * self.steps_per_net * 2
+
+    def dominant_kernel(self, peaks):
+        self.step_gpu(0)                                # makes the buffers the parent's timing loop reads
+        self.dev = [(self.actor._bufs[self.T_LEN]["obs"], self.actor._bufs[self.T_LEN]["act"], None, None) + d
+                    for d in self.dev]
+        r = PPOLargeWorkload.dominant_kernel(self, peaks)
+        t = self.torch
+        times = []
+        for _ in range(5):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            self.actor.collect(self.T_LEN)
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        r["collect_ms"] = float(np.median(times))
+        r["collect_transitions_per_s"] = self.N / (r["collect_ms"] * 1e-3)
+        r["mean_reward_first_last"] = [self.mean_rewards[0], self.mean_rewards[-1]] if self.mean_rewards else None
+        return r
+
+
+WORKLOADS = {"closed_loop": ClosedLoopWorkload, "ppo": PPOWorkload, "ppo_large": PPOLargeWorkload, "mlp": MLPWorkload, "es": ESWorkload, "vae": VAEWorkload}
 
 
 def kernel_sweep(peaks):
@@ -764,7 +841,8 @@ PARALLELISM = {"ppo_large": "dp%d: every rank trains on its own 2^20-transition 
                "ppo": "%d independent replicas (a 64-row minibatch does not shard)",
                "mlp": "%d independent replicas (batch 128 does not shard)",
                "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce",
-               "vae": "%d independent replicas"}
+               "vae": "%d independent replicas",
+               "closed_loop": "%d independent replicas"}
 
 
 def main():
@@ -841,7 +919,7 @@ def main():
                     e2e=dict(value=units / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=wl.h2d,
                              d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=wl.launches_per_step() * args.steps, roofline=roof, clocks=clocks)
-        if not args.no_cpu_baseline and world == 1 and hasattr(wl, "step_cpu"):
+        if not args.no_cpu_baseline and world == 1 and getattr(wl, "step_cpu", None):
             v1, w1 = time_cpu(args.workload, 1, 1, 1)
             line["cpu_baseline"] = dict(
                 value=v1, unit=wl.unit, cores=1, kind="port", host_cores=cores,
@@ -853,7 +931,7 @@ def main():
             del wl
             torch.cuda.empty_cache()
             others = {}
-            for name in ("ppo", "mlp", "es", "vae"):
+            for name in ("closed_loop", "ppo", "mlp", "es", "vae"):
                 if name == args.workload:
                     continue
                 w2 = WORKLOADS[name](seed=7)
@@ -861,12 +939,14 @@ def main():
                 m1, m2 = measure(w2, 5, 3, 1, 0, flush)
                 u = w2.units_per_step * 5
                 r2 = w2.dominant_kernel(peaks)
-                c1 = time_cpu(name, 1, 1, 1)[0] if hasattr(w2, "step_cpu") else None
+                c1 = time_cpu(name, 1, 1, 1)[0] if getattr(w2, "step_cpu", None) else None
                 reps = [w2.replica_throughput(r) for r in (8, 16)] if hasattr(w2, "replica_throughput") else None
                 others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
                                     e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,
                                     independent_replicas=reps, roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",
-                                                                             "fp32_tflops", "fp32_frac", "note")})
+                                                                             "fp32_tflops", "fp32_frac", "note", "collect_ms",
+                                                                             "collect_transitions_per_s",
+                                                                             "mean_reward_first_last")})
                 del w2
                 torch.cuda.empty_cache()
             line["other_workloads"] = others

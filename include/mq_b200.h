@@ -89,6 +89,43 @@ const char *mq_last_error(void);
 int mq_debug_set_phase_buffer(void *dev_buf);
 /* developer aid: force the row-tile size of the fused kernels (0 = automatic) */
 int mq_debug_set_tile_rows(int tb);
+/* ---- rollout side: many environments stepped in lock step ------------------------------------
+ * NormalizedObservations of mannequin/gym.py:61-84 for the E observations of one time step as ONE batch of
+ * RunningNormalize (mannequin/_normalize.py:34-81; E = 1 is the reference's per-step behaviour): out = clip(normalize(raw),
+ * +-clip).  state = double[2 d + 3]: mean[d], var[d], total weight of the mean, total weight of the variance, samples seen
+ * (all zero initially); horizon <= 0: no forgetting (the reference's choice for observations). */
+int mq_obsnorm_step(const float *raw, int64_t rows, int32_t d, double horizon, double *state, float clip, float *out,
+                    void *stream);
+/* n unit normals of the counter-based Philox4x32-10 stream (seed, stream_a, stream_b): deviate j = element j % 4 of the
+ * Box-Muller pairs of block j / 4.  The rollout kernels draw from the same generator. */
+int mq_randn_philox(uint64_t seed, uint32_t stream_a, uint32_t stream_b, int64_t n, float *out, void *stream);
+/* Synthetic on-device environment (the reference's environments are gym's: out of scope): hidden state x in R^d,
+ * observation = obs_scale * x + obs_shift, x' = x + dt (-damp x + B a) + sigma noise, reward = -|x'|^2 / d - ctrl |a|^2 / A,
+ * episode end after `horizon` steps or with probability p_end per step, restart from x ~ N(0, 1). */
+typedef struct mq_env {
+    int32_t d, a;
+    int32_t horizon;
+    float dt, damp, sigma, ctrl, p_end;
+    const float *b;             /* [d, a] row-major */
+    const float *obs_scale;     /* [d] */
+    const float *obs_shift;     /* [d] */
+} mq_env_t;
+int mq_env_reset(const mq_env_t *env, int64_t n_env, uint64_t seed, float *x, int32_t *ep_step, float *raw, void *stream);
+/* one_step of mannequin/gym.py:115-122 for n_env environments at time t of a rollout of t_len steps: action = mean +
+ * exp(logstd) * noise (mannequin/distrib.py:50-59; noise stream (seed, step_id, env)), records obs_n / action / reward /
+ * done at [env * t_len + t] of the environment-major buffers, advances the environment, restarts finished episodes and
+ * writes the next raw observations.  The step's index in the noise stream is step_id + *step_base (step_base may be
+ * NULL): a device-resident base lets a captured CUDA graph draw fresh noise at every replay. */
+int mq_actor_env_step(const mq_env_t *env, int64_t n_env, int32_t t, int32_t t_len, uint64_t seed, uint32_t step_id,
+                      const int32_t *step_base, const float *obs_n, const float *mean, const float *logstd, float *x,
+                      int32_t *ep_step,
+                      float *obs_buf, float *act_buf, float *rew_buf, uint8_t *done_buf, float *raw_next, void *stream);
+/* chunk boundary of benchmarks/gae.py:43-64 for n_seg segments of seg_len transitions laid end to end: at a segment's
+ * last step, unless the episode really ended there, rew += gam * v_next[seg] and done = 1 (adv = r + gam v(next) - v, the
+ * reference's value at a chunk end where the advantage beyond the chunk is 0). */
+int mq_bootstrap_segments(float *rew, uint8_t *done, const float *v_next, int64_t n_seg, int64_t seg_len, float gam,
+                          void *stream);
+
 /* developer aid: 0 makes mq_fused_grad use the tile kernel instead of the row-owner-warp kernel */
 int mq_debug_use_chain_grad(int on);
 /* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */

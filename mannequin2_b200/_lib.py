@@ -31,6 +31,13 @@ class MqHead(ctypes.Structure):
                 ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p)]
 
 
+class MqEnv(ctypes.Structure):
+    """mq_env_t: the synthetic on-device environment of the rollout kernels."""
+    _fields_ = [("d", c_int32), ("a", c_int32), ("horizon", c_int32), ("dt", c_float), ("damp", c_float),
+                ("sigma", c_float), ("ctrl", c_float), ("p_end", c_float), ("b", c_void_p), ("obs_scale", c_void_p),
+                ("obs_shift", c_void_p)]
+
+
 class MqPeer(ctypes.Structure):
     """mq_peer_t: peer-memory descriptor of the in-kernel gradient all-reduce."""
     _fields_ = [("rank", c_int32), ("world", c_int32), ("grad_bufs", c_void_p), ("flag_bufs", c_void_p),
@@ -92,6 +99,12 @@ SIGNATURES = {
     "mq_clip_forward": (c_int, [P, P, c_int64, c_float, c_float, P]),
     "mq_clip_backward": (c_int, [P, P, P, c_int64, c_float, c_float, P]),
     "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
+    "mq_obsnorm_step": (c_int, [P, c_int64, c_int32, ctypes.c_double, P, c_float, P, P]),
+    "mq_randn_philox": (c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_int64, P, P]),
+    "mq_env_reset": (c_int, [POINTER(MqEnv), c_int64, ctypes.c_uint64, P, P, P, P]),
+    "mq_actor_env_step": (c_int, [POINTER(MqEnv), c_int64, c_int32, c_int32, ctypes.c_uint64, ctypes.c_uint32, P, P, P,
+                                  P, P, P, P, P, P, P, P, P]),
+    "mq_bootstrap_segments": (c_int, [P, P, P, c_int64, c_int64, c_float, P]),
     "mq_gauss_entropy": (c_int, [P, P, c_int64, c_int64, P, P, P]),
     "mq_gauss_logprob_bwd": (c_int, [P, P, c_int64, P, P, c_int64, c_int64, P, P, P]),
     "mq_discrete_logprob": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),

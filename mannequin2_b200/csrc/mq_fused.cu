@@ -98,6 +98,8 @@ static int plan_choose(const mq_net_t *net, int64_t batch, int with_grad, FusedP
     int tb = 128;
     if (batch <= 32) tb = 32; else if (batch <= 64) tb = 64;
     if (g_force_tb && batch > g_force_tb) tb = g_force_tb;
+    // forward only (a few thousand rows per time step of a rollout): smaller tiles until every SM has one
+    else if (!with_grad) while (tb > 32 && batch / tb < mq_sm_count()) tb >>= 1;
     for (; tb >= 32; tb >>= 1)
         if (plan_build(net, tb, with_grad, p, smem_state, nt) <= lim) return tb;
     return 0;

@@ -197,6 +197,22 @@ class PPOUpdater(object):
             main.wait_event(self._ev_val)
         return adv, ret
 
+    def update_rollout(self, chunk, n_seg, seg_len, val_idx, pol_idx):
+        """One update from a chunk collected by rollout.BatchedActor: n_seg per-environment segments of seg_len
+        transitions laid end to end.  Each segment ends like a chunk of benchmarks/gae.py:43-64 (the advantage beyond
+        the chunk is 0, the value of the state after it is bootstrapped): mq_bootstrap_segments turns that into the
+        terminal form, then the update is update_dev unchanged."""
+        n = n_seg * seg_len
+        assert chunk["rew"].numel() == n and chunk["last_obs"].numel() == n_seg * self.n_obs
+        v_next = self._buf("v_next", n_seg)
+        D.call("mq_fused_forward", ctypes.byref(self.value.net), D.ptr(self.value.theta), D.ptr(chunk["last_obs"]), None,
+               n_seg, D.ptr(v_next), None, None, D.stream())
+        rew, done = self._buf("rew_seg", n), self._buf("done_seg", n, torch.uint8)
+        rew.copy_(chunk["rew"])
+        done.copy_(chunk["done"])
+        D.call("mq_bootstrap_segments", D.ptr(rew), D.ptr(done), D.ptr(v_next), n_seg, seg_len, self.gam, D.stream())
+        return self.update_dev(chunk["obs"], chunk["act"], rew, done, val_idx, pol_idx)
+
     def update(self, obs, act, rew, done, val_idx, pol_idx):
         """Host arrays in, new (policy_params, value_params) host arrays out (end-to-end call)."""
         up = lambda a, dt: D.from_host(np.ascontiguousarray(a, dtype=dt))

@@ -509,3 +509,84 @@ def ppo_discrete_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4,
     g = ppo_clip_weight(logp, logp_old, adv, lo, hi).astype(np.float32)
     opt.apply_gradient(discrete_logprob_grad(theta, spec, obs, act, g, outs), lr=lr)
     return opt.get_value().astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
+# Rollout side: NormalizedObservations, batched actor
+# ---------------------------------------------------------------------------
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011; Random123), vectorised
+    over uint32 arrays.  Not part of the reference (its RNG is unseeded
+    np.random); the rollout kernels draw their noise from it."""
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c = [np.asarray(v, dtype=np.uint32) for v in (c0, c1, c2, c3)]
+    c = list(np.broadcast_arrays(*c))
+    k0, k1 = np.uint32(k0), np.uint32(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(rounds):
+        p0 = m0 * c[0].astype(np.uint64)
+        p1 = m1 * c[2].astype(np.uint64)
+        n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c[1] ^ k0
+        n1 = (p1 & mask).astype(np.uint32)
+        n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c[3] ^ k1
+        n3 = (p0 & mask).astype(np.uint32)
+        c = [n0, n1, n2, n3]
+        k0 = np.uint32((int(k0) + 0x9E3779B9) & 0xFFFFFFFF)
+        k1 = np.uint32((int(k1) + 0xBB67AE85) & 0xFFFFFFFF)
+    return c
+
+
+def philox_normals(seed, a, b, j):
+    """Unit normal number(s) `j` of stream (seed, a, b) as mq_rollout.cu draws
+    them: Philox block j // 4 -> two Box-Muller pairs, element j % 4."""
+    j, a, b = np.broadcast_arrays(np.asarray(j, dtype=np.int64), np.asarray(a, dtype=np.uint32),
+                                  np.asarray(b, dtype=np.uint32))
+    r = philox4x32((j >> 2).astype(np.uint32), a, b, np.uint32(0),
+                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    r = [np.asarray(v) for v in np.broadcast_arrays(*r)]
+    z = []
+    for h in range(2):
+        u1 = ((r[2 * h] >> np.uint32(8)).astype(np.float64) + 1.0) / 16777216.0
+        u2 = (r[2 * h + 1] >> np.uint32(8)).astype(np.float64) / 16777216.0
+        rad = np.sqrt(-2.0 * np.log(u1))
+        z += [rad * np.cos(2.0 * np.pi * u2), rad * np.sin(2.0 * np.pi * u2)]
+    z = np.stack(z, axis=-1)
+    return np.take_along_axis(z, (j & 3)[..., None], axis=-1)[..., 0].astype(np.float32)
+
+
+def normalized_observations_step(norm, raw, clip=5.0):
+    """mannequin/gym.py:66-71 on the batch of one time step: `norm` is a
+    RunningNormalizeO (mannequin/_normalize.py:34-81)."""
+    return np.clip(norm(np.asarray(raw, dtype=np.float64)), -clip, clip)
+
+
+def synthetic_env_step(env, x, ep_step, act, seed, step_id):
+    """The synthetic environment of mq_rollout.cu (not the reference's: gym is
+    out of scope).  env: dict(dt, damp, sigma, ctrl, p_end, horizon, b[d,a],
+    obs_scale[d], obs_shift[d]).  Returns (x', ep_step', rew, done, raw')."""
+    n, d = x.shape
+    e = np.arange(n)
+    noise = np.stack([philox_normals(seed, step_id, e, 16 + i) for i in range(d)], axis=1)
+    f = -env["damp"] * x + act @ env["b"].T
+    xn = x + env["dt"] * f + env["sigma"] * noise
+    rew = -(np.sum(xn * xn, axis=1) / d) - env["ctrl"] * np.sum(act * act, axis=1) / act.shape[1]
+    steps = ep_step + 1
+    u = philox4x32(np.uint32(0xFFFFFFFF), np.uint32(step_id), e.astype(np.uint32), np.uint32(1),
+                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0]
+    done = (steps >= env["horizon"]) | ((u >> np.uint32(8)).astype(np.float64) / 16777216.0 < env["p_end"])
+    fresh = np.stack([philox_normals(seed, step_id, e, 16 + 64 + i) for i in range(d)], axis=1)
+    xn = np.where(done[:, None], fresh, xn)
+    raw = env["obs_scale"] * xn + env["obs_shift"]
+    return xn.astype(np.float32), np.where(done, 0, steps).astype(np.int32), rew.astype(np.float32), done, \
+        raw.astype(np.float32)
+
+
+def bootstrap_segments(rew, done, v_next, seg_len, gam):
+    """benchmarks/gae.py:52-61 at a chunk end (adv beyond the chunk is 0) for
+    segments laid end to end: r += gam * v(next), done = True."""
+    rew, done = np.array(rew, dtype=np.float32), np.array(done, dtype=bool)
+    last = np.arange(len(v_next)) * seg_len + seg_len - 1
+    cont = ~done[last]
+    rew[last[cont]] += np.float32(gam) * np.asarray(v_next, dtype=np.float32)[cont]
+    done[last] = True
+    return rew, done

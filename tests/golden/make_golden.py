@@ -306,6 +306,49 @@ def gen_discrete(out):
     out["disc_logp"], out["disc_grad"] = np.asarray(logp), bpp(g)
 
 
+def gen_obsnorm(out, gym):
+    """The REAL mannequin.gym.NormalizedObservations (gym.py:61-84) around a recording environment: the raw observation
+    stream (scaled and shifted so that the statistics matter) and what the wrapper returns, 40 steps incl. a reset; and
+    RunningNormalize fed whole batches (the lock-step form: one update per time step of E environments)."""
+    import mannequin
+    import mannequin.gym as mgym
+
+    class Recorder(SyntheticEnv):
+        def __init__(self, gym, seed):
+            super().__init__(gym, seed)
+            self.raw = []
+            self.scale = np.exp(np.random.RandomState(5).randn(11))
+            self.shift = 3.0 * np.random.RandomState(6).randn(11)
+
+        def reset(self):
+            o = super().reset() * self.scale + self.shift
+            self.raw.append(o.copy())
+            return o
+
+        def step(self, action):
+            o, r, d, i = super().step(action)
+            o = o * self.scale + self.shift
+            self.raw.append(o.copy())
+            return o, r, d, i
+
+    inner = Recorder(gym, seed=31)
+    env = mgym.NormalizedObservations(inner)
+    outs = [env.reset()]
+    rs = np.random.RandomState(32)
+    for t in range(39):
+        if t == 17:
+            outs.append(env.reset())
+        else:
+            outs.append(env.step(rs.randn(3))[0])
+    out["on_raw"], out["on_out"] = np.array(inner.raw), np.array(outs)
+    out["on_mean"], out["on_var"] = env.get_mean(), env.get_var()
+    norm = mannequin.RunningNormalize((11,))
+    batches = (rs.randn(6, 7, 11) * inner.scale + inner.shift).astype(np.float32)
+    out["on_batches"] = batches
+    out["on_batch_out"] = np.array([np.clip(norm(b), -5.0, 5.0) for b in batches])
+    out["on_batch_mean"], out["on_batch_var"] = norm.get_mean(), norm.get_var()
+
+
 def gen_ppo(out, gym):
     """Run benchmarks/ppo.py:run() itself for two chunks and record everything."""
     import mannequin
@@ -462,7 +505,13 @@ def main():
     d = {}
     gen_gae(d, gym)
     groups["gae"] = d
+    d = {}
+    gen_obsnorm(d, gym)
+    groups["obsnorm"] = d
+    only = sys.argv[1:]
     for name, d in groups.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)
         print("%-12s %3d arrays  %7.1f KB" % (name, len(d), os.path.getsize(path) / 1024))

@@ -638,6 +638,108 @@ def case_entropy(B, batches=(64, 300, 9000), steps=4):
     assert np.all(got[5123:] > theta[5123:] - 1e-3)
 
 
+def case_rollout(B, n_env=300):
+    """Rollout-side kernels: Philox normals, the observation normaliser against the real
+    reference's NormalizedObservations / RunningNormalize (golden/obsnorm.npz) and the oracle, the batched actor /
+    synthetic environment step and the segment bootstrap against the oracle."""
+    lib = B.lib
+    rs = np.random.RandomState(53)
+    seed = 0x1234567ABCDEF
+    # ---- Philox normals
+    n = 1003
+    z = B.zeros(n, np.float32)
+    ok(B, lib.mq_randn_philox(seed, 7, 9, n, B.ptr(z), B.stream))
+    want = O.philox_normals(seed, 7, 9, np.arange(n))
+    assert np.max(np.abs(B.down(z) - want)) < 1e-5
+    # ---- NormalizedObservations: the reference's wrapper, one observation per step (E = 1)
+    g = golden("obsnorm")
+    st = B.zeros(2 * 11 + 3, np.float64)
+    for raw, want in zip(g["on_raw"], g["on_out"]):
+        hr, ho = B.up(raw.astype(np.float32).reshape(1, 11)), B.zeros((1, 11), np.float32)
+        ok(B, lib.mq_obsnorm_step(B.ptr(hr), 1, 11, 0.0, B.ptr(st), 5.0, B.ptr(ho), B.stream))
+        ref = O.normalized_observations_step  # noqa: F841  (oracle form checked below)
+        assert np.max(np.abs(B.down(ho).reshape(-1) - want)) < 2e-5 * (1 + np.max(np.abs(want))), "obsnorm E=1"
+    sd = B.down(st)
+    # the reference saw float64 observations, the kernel their float32 roundings: statistics agree to ~1e-7 relative
+    assert np.max(np.abs(sd[:11] - g["on_mean"]) / (1 + np.abs(g["on_mean"]))) < 1e-6
+    assert np.max(np.abs(sd[11:22] - g["on_var"]) / g["on_var"]) < 1e-5
+    # ---- whole batches (the lock-step form), float32 inputs on both sides: fp64 statistics to 1e-12
+    st = B.zeros(2 * 11 + 3, np.float64)
+    for b, want in zip(g["on_batches"], g["on_batch_out"]):
+        hr, ho = B.up(b), B.zeros(b.shape, np.float32)
+        ok(B, lib.mq_obsnorm_step(B.ptr(hr), b.shape[0], 11, 0.0, B.ptr(st), 5.0, B.ptr(ho), B.stream))
+        close(B.down(ho), want, rtol=1e-6, atol_scale=1e-6, what="obsnorm batch vs reference")
+    sd = B.down(st)
+    assert np.max(np.abs(sd[:11] - g["on_batch_mean"])) < 1e-12 * (1 + np.max(np.abs(g["on_batch_mean"])))
+    assert np.max(np.abs(sd[11:22] - g["on_batch_var"]) / g["on_batch_var"]) < 1e-12
+    # ---- oracle: horizons, widths, batch sizes incl. a first batch of one sample
+    for d, horizon, sizes in ((11, None, (1, 1, 5, 4096, 2)), (3, 10.0, (64, 64, 1, 9)), (64, 3.0, (2, 1500))):
+        norm = O.RunningNormalizeO(shape=(d,), horizon=horizon)
+        st = B.zeros(2 * d + 3, np.float64)
+        for m in sizes:
+            raw = (rs.randn(m, d) * 3.0 + 10.0).astype(np.float32)
+            want = O.normalized_observations_step(norm, raw, 5.0)
+            hr, ho = B.up(raw), B.zeros((m, d), np.float32)
+            ok(B, lib.mq_obsnorm_step(B.ptr(hr), m, d, horizon or 0.0, B.ptr(st), 5.0, B.ptr(ho), B.stream))
+            close(B.down(ho), want, rtol=1e-6, atol_scale=1e-6, what="obsnorm vs oracle d=%d m=%d" % (d, m))
+        sd = B.down(st)
+        assert np.max(np.abs(sd[:d] - norm.get_mean())) < 1e-11
+        assert np.max(np.abs(sd[d:2 * d] - norm.get_var()) / norm.get_var()) < 1e-11
+    # ---- actor + synthetic environment
+    d, na, t_len = 11, 3, 5
+    env = dict(dt=0.1, damp=0.5, sigma=0.05, ctrl=0.1, p_end=0.05, horizon=4,
+               b=(rs.randn(d, na) / np.sqrt(na)).astype(np.float32), obs_scale=np.exp(rs.randn(d) * 0.5).astype(np.float32),
+               obs_shift=(rs.randn(d) * 2).astype(np.float32))
+    hb, hs, hh = B.up(env["b"]), B.up(env["obs_scale"]), B.up(env["obs_shift"])
+    ed = L.MqEnv()
+    ed.d, ed.a, ed.horizon, ed.dt, ed.damp, ed.sigma, ed.ctrl, ed.p_end = d, na, 4, 0.1, 0.5, 0.05, 0.1, 0.05
+    ed.b, ed.obs_scale, ed.obs_shift = B.ptr(hb), B.ptr(hs), B.ptr(hh)
+    hx, hep, hraw = B.zeros((n_env, d), np.float32), B.zeros(n_env, np.int32), B.zeros((n_env, d), np.float32)
+    ok(B, lib.mq_env_reset(ctypes.byref(ed), n_env, seed, B.ptr(hx), B.ptr(hep), B.ptr(hraw), B.stream))
+    e_idx = np.arange(n_env)
+    x = np.stack([O.philox_normals(seed, 0xFFFFFFFE, e_idx, i) for i in range(d)], axis=1)
+    assert np.max(np.abs(B.down(hx) - x)) < 1e-5
+    close(B.down(hraw), env["obs_scale"] * x + env["obs_shift"], what="env reset raw")
+    x, ep = B.down(hx).copy(), np.zeros(n_env, np.int32)
+    obs_buf, act_buf = B.zeros((n_env * t_len, d), np.float32), B.zeros((n_env * t_len, na), np.float32)
+    rew_buf, done_buf = B.zeros(n_env * t_len, np.float32), B.zeros(n_env * t_len, np.uint8)
+    base = B.up(np.array([100], np.int32))
+    logstd = (rs.randn(na) * 0.3).astype(np.float32)
+    hls = B.up(logstd)
+    n_done = 0
+    for t in range(t_len):
+        obs_n = rs.randn(n_env, d).astype(np.float32)
+        mean = rs.randn(n_env, na).astype(np.float32)
+        ho, hm = B.up(obs_n), B.up(mean)
+        ok(B, lib.mq_actor_env_step(ctypes.byref(ed), n_env, t, t_len, seed, t, B.ptr(base), B.ptr(ho), B.ptr(hm), B.ptr(hls),
+                                    B.ptr(hx), B.ptr(hep), B.ptr(obs_buf), B.ptr(act_buf), B.ptr(rew_buf), B.ptr(done_buf),
+                                    B.ptr(hraw), B.stream))
+        sid = 100 + t
+        noise = np.stack([O.philox_normals(seed, sid, e_idx, k) for k in range(na)], axis=1)
+        act = (mean + np.exp(logstd) * noise).astype(np.float32)                 # distrib.py:50-59
+        x, ep, rew, done, raw = O.synthetic_env_step(env, x, ep, act, seed, sid)
+        rows = e_idx * t_len + t
+        assert np.array_equal(B.down(obs_buf)[rows], obs_n)
+        assert np.max(np.abs(B.down(act_buf)[rows] - act)) < 1e-5
+        assert np.max(np.abs(B.down(rew_buf)[rows] - rew)) < 1e-4 * (1 + np.max(np.abs(rew)))
+        assert np.array_equal(B.down(done_buf)[rows].astype(bool), done)
+        assert np.array_equal(B.down(hep), ep)
+        assert np.max(np.abs(B.down(hx) - x)) < 2e-5
+        assert np.max(np.abs(B.down(hraw) - raw)) < 1e-4
+        x = B.down(hx).copy()                                                    # no drift between the two sides
+        n_done += int(done.sum())
+    assert 0 < n_done < n_env * t_len                                            # both endings and continuations seen
+    # ---- segment bootstrap
+    n_seg, seg = 37, 6
+    rew = rs.randn(n_seg * seg).astype(np.float32)
+    done = (rs.rand(n_seg * seg) < 0.3)
+    vn = rs.randn(n_seg).astype(np.float32)
+    hr, hd, hv = B.up(rew), B.up(done.astype(np.uint8)), B.up(vn)
+    ok(B, lib.mq_bootstrap_segments(B.ptr(hr), B.ptr(hd), B.ptr(hv), n_seg, seg, 0.99, B.stream))
+    wr, wd = O.bootstrap_segments(rew, done, vn, seg, 0.99)
+    assert np.max(np.abs(B.down(hr) - wr)) < 1e-6 and np.array_equal(B.down(hd).astype(bool), wd)
+
+
 def case_tc_paths(B):
     """tcgen05 / TMEM kernels forced on (mode 2) for every net they accept -- the one-tile kernel with its issuer warp
     (mq_tc.cu, the default) and the two-tiles-in-flight variant (mq_tc2.cu): the same fp32 bars as the FFMA kernels
@@ -899,4 +1001,4 @@ def case_gemm_tc(B):
 
 
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_gemm_tc, case_fused_heads,
-             case_fused_gauss_ppo, case_discrete, case_entropy, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_discrete, case_entropy, case_rollout, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]

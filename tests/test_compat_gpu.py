@@ -516,6 +516,58 @@ def test_gauss_entropy_function():
     assert np.allclose(np.asarray(bpp2(np.float32(1.5))), 1.5)
 
 
+def test_batched_actor_rollouts_and_closed_loop():
+    """Rollout side (mannequin/gym.py:61-84,115-137 for many environments in lock step):
+    (1) collecting through one CUDA graph per chunk gives bit-identical chunks, normaliser statistics and environment
+    states as launching the same kernels one by one, and successive chunks differ (fresh noise per replay);
+    (2) the first observation of a chunk is the carried-over last observation of the previous one (gae.py:64);
+    (3) the closed loop collect -> PPOUpdater.update_rollout learns on the synthetic environment, in the spirit of the
+    reference's convergence tests (tests/predictor1.py)."""
+    import torch
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.ppo import PPOUpdater
+    from mannequin2_b200.rollout import BatchedActor, SyntheticEnv
+    n_env, t_len = 256, 16
+    chunks = {}
+    for graph in (False, True):
+        np.random.seed(2)
+        env = SyntheticEnv(n_env, horizon=10, p_end=0.02, seed=3)
+        upd = PPOUpdater(env.n_obs, env.n_act)
+        actor = BatchedActor(env, upd.policy, seed=5, use_graph=graph)
+        got = []
+        for _ in range(3):
+            c = actor.collect(t_len)
+            torch.cuda.synchronize()
+            got.append({k: D.to_host(v).copy() for k, v in c.items()})
+        chunks[graph] = (got, D.to_host(actor.normalizer._state).copy(), D.to_host(env.x).copy())
+    for a, b in zip(chunks[False][0], chunks[True][0]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(chunks[False][1], chunks[True][1]) and np.array_equal(chunks[False][2], chunks[True][2])
+    c0, c1, c2 = chunks[True][0]
+    assert not np.array_equal(c0["act"], c1["act"]) and not np.array_equal(c1["act"], c2["act"])
+    first_rows = np.arange(n_env) * t_len
+    assert np.array_equal(c1["obs"][first_rows], c0["last_obs"]) and np.array_equal(c2["obs"][first_rows], c1["last_obs"])
+    assert np.max(np.abs(c2["obs"])) <= 5.0 and c0["done"].any() and not c0["done"].all()
+    # closed loop
+    np.random.seed(0)
+    rs = np.random.RandomState(1)
+    n_env, t_len, mb, epochs = 512, 64, 8192, 4
+    n = n_env * t_len
+    env = SyntheticEnv(n_env, horizon=64, seed=3)
+    upd = PPOUpdater(env.n_obs, env.n_act)
+    actor = BatchedActor(env, upd.policy, seed=5, use_graph=True)
+    rewards = []
+    for _ in range(12):
+        chunk = actor.collect(t_len)
+        rewards.append(float(chunk["rew"].mean()))
+        vi = D.from_host(np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)]))
+        pi = D.from_host(np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)]))
+        upd.update_rollout(chunk, n_env, t_len, vi, pi)
+    assert np.mean(rewards[-3:]) > rewards[0] + 0.04, rewards
+    assert np.all(D.to_host(upd.policy.theta)[-3:] < 0.0)          # the policy narrows its noise
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and

@@ -209,6 +209,54 @@ def test_discrete_vs_reference():
     assert_close(grad, g["disc_grad"], rtol=3e-5, atol_scale=3e-6)
 
 
+def test_rollout_side_vs_reference():
+    """Rollout-side restatements: NormalizedObservations against the real wrapper (mannequin/gym.py:61-84) stepping one
+    environment, RunningNormalize fed whole batches (golden/obsnorm.npz, both generated by the reference here), the
+    Philox4x32-10 generator against Random123's known-answer vectors, and the chunk-end bootstrap against the literal
+    loop of benchmarks/gae.py:52-61."""
+    g = load_golden("obsnorm")
+    norm = O.RunningNormalizeO(shape=(11,))
+    for raw, want in zip(g["on_raw"], g["on_out"]):
+        got = O.normalized_observations_step(norm, raw.reshape(1, 11), 5.0).reshape(-1)
+        assert np.max(np.abs(got - want)) < 1e-12
+    assert np.max(np.abs(norm.get_mean() - g["on_mean"])) < 1e-12
+    assert np.max(np.abs(norm.get_var() - g["on_var"])) < 1e-12
+    assert np.all(g["on_out"][0] == 0.0) and np.max(np.abs(g["on_out"])) <= 5.0      # zeros before 2 samples; clipped
+    norm = O.RunningNormalizeO(shape=(11,))
+    for b, want in zip(g["on_batches"], g["on_batch_out"]):
+        assert np.max(np.abs(O.normalized_observations_step(norm, b, 5.0) - want)) < 1e-12
+    assert np.max(np.abs(norm.get_var() - g["on_batch_var"])) < 1e-12
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in O.philox4x32(*ctr, *key)) == want
+    z = O.philox_normals(99, 1, 2, np.arange(100000))
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and abs(np.mean(z ** 4) - 3.0) < 0.1
+    # chunk end: gae.py:52-61 with adv[length] = 0 vs the terminal form on the patched rewards
+    rs = np.random.RandomState(3)
+    n_seg, seg, gam, lam = 5, 7, 0.99, 0.95
+    rew = rs.randn(n_seg * seg).astype(np.float32)
+    done = rs.rand(n_seg * seg) < 0.2
+    v = rs.randn(n_seg, seg + 1).astype(np.float32)
+    want = np.zeros((n_seg, seg))
+    for e in range(n_seg):                                  # the reference loop, one chunk per segment
+        adv = np.zeros(seg + 1)
+        for i in range(seg - 1, -1, -1):
+            k = e * seg + i
+            if done[k]:
+                adv[i] = rew[k] - v[e, i]
+            else:
+                adv[i] = rew[k] + gam * v[e, i + 1] - v[e, i] + gam * lam * adv[i + 1]
+        want[e] = adv[:seg]
+    r2, d2 = O.bootstrap_segments(rew, done, v[:, seg], seg, gam)
+    flat_v = np.concatenate([v[:, :seg].reshape(-1), [0.0]]).astype(np.float32)
+    adv, _ = O.gae_advantages(r2, flat_v, d2, gam, lam)
+    assert np.max(np.abs(adv - want.reshape(-1))) < 1e-5
+
+
 def test_vae_heads_fd():
     rs = np.random.RandomState(2)
     m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
