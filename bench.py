@@ -344,9 +344,17 @@ class PPOLargeWorkload(object):
         executed = tiles * float(per_tile)
         tf = flops / (ms * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        traffic = None                                      # DRAM bytes per launch from the committed ncu capture
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)["tc_grad_kernel_policy_65536rows"]["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         return dict(bound="tensor", kernel="tc_grad_kernel<16,tanh> (policy, 65536 rows, tcgen05 bf16x3 planes; "
                                            "launch includes fused_reduce_kernel)",
-                    achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None,
+                    achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=traffic,
+                    traffic_note="ncu dram__bytes_read+write of one 65,536-row launch (algorithmic gather: 4.2 MB; 44-byte "
+                                 "rows arrive as 32-byte sectors, index and weight reads add the rest)",
                     peak_source=peaks["source"], ms_per_launch=ms,
                     limiter="fp32-exact products = 6 bf16 plane pairs with K = 16..64: the tensor pipe is fed at the "
                             "shared-memory operand rate (measured 128 B/cycle/SM) and waits on the per-layer epilogues; "

@@ -62,18 +62,25 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
     // next gradient kernel may start its on-chip prologue while this one runs
     mq_pdl_trigger();
     mq_pdl_wait();
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    // group gy sums partial rows gy, gy + 8, ...: 20 independent loads in flight per thread (the whole of a 148-CTA
+    // gradient in one round trip to L2), added in a fixed tree
+    float tot = 0.0f;
     if (j < n) {
-        int b = gy;
-        for (; b + 24 < n_parts; b += 32) {
-            s0 += partial[(int64_t)b * n + j];
-            s1 += partial[(int64_t)(b + 8) * n + j];
-            s2 += partial[(int64_t)(b + 16) * n + j];
-            s3 += partial[(int64_t)(b + 24) * n + j];
+        for (int base = gy; base < n_parts; base += 160) {
+            float v[20];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) {
+                const int b = base + 8 * k;
+                v[k] = b < n_parts ? partial[(int64_t)b * n + j] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) v[k] += v[k + 10];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] += v[k + 5];
+            tot += ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
         }
-        for (; b < n_parts; b += 8) s0 += partial[(int64_t)b * n + j];
     }
-    part[gy][jx] = (s0 + s1) + (s2 + s3);
+    part[gy][jx] = tot;
     __syncthreads();
     if (gy != 0) return;
     float g = part[0][jx];
