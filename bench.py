@@ -865,6 +865,14 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE line (rank 0's JSON): anything a library prints there (NCCL announces its version on
+    # stdout) is sent to stderr instead, and the result is written to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
     warmup = max(3, args.warmup)
     cores = os.cpu_count() or 1
 
@@ -873,7 +881,7 @@ def main():
             return 0
         wl = WORKLOADS[args.workload](**CPU_KW.get(args.workload, {}))
         if not hasattr(wl, "step_cpu"):
-            print(json.dumps(dict(impl="reference", unavailable="no CPU port of the %s step in oracle/ yet" % args.workload)))
+            emit(dict(impl="reference", unavailable="no CPU port of the %s step in oracle/ yet" % args.workload))
             return 0
         procs = max(1, min(cores, 32))
         steps = max(1, min(args.steps, 3))
@@ -889,7 +897,7 @@ def main():
                     cpu_baseline=dict(value=val, unit=wl.unit, cores=procs, kind="port",
                                       sample="%d steps x %d replicas; each step: %s" % (steps, procs, sample)),
                     e2e=dict(value=val, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -959,7 +967,7 @@ def main():
                 torch.cuda.empty_cache()
             line["other_workloads"] = others
             line["kernels"] = kernel_sweep(peaks)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -223,6 +223,9 @@ typedef struct mq_peer {
     uint32_t *const *flag_bufs;
     int64_t buf_stride;
     uint32_t step;
+    int32_t pull;                /* 0: push (remote STORES into every peer's slot [rank], local reads; fastest up to 4 GPUs);
+                                    1: pull (local store of the own slot, remote LOADS of every peer's: one release fence
+                                    towards local memory instead of one per peer; faster on 8 GPUs) */
 } mq_peer_t;
 int64_t mq_step_blocks(int64_t n);
 /* One launch: g = scale * sum_k partials[k] (fixed order) [-> sum over ranks through peer memory, rank order]

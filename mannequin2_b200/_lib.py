@@ -41,7 +41,7 @@ class MqEnv(ctypes.Structure):
 class MqPeer(ctypes.Structure):
     """mq_peer_t: peer-memory descriptor of the in-kernel gradient all-reduce."""
     _fields_ = [("rank", c_int32), ("world", c_int32), ("grad_bufs", c_void_p), ("flag_bufs", c_void_p),
-                ("buf_stride", c_int64), ("step", ctypes.c_uint32)]
+                ("buf_stride", c_int64), ("step", ctypes.c_uint32), ("pull", c_int32)]
 
 
 P = c_void_p

@@ -92,8 +92,12 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
         // reads its own memory
         const int par = (int)(peer.step & 1u);
         const int64_t slot = ((int64_t)par * peer.world + peer.rank) * peer.buf_stride;
-        if (j < n)
+        if (peer.pull) {                // pull: the own slot only, made visible to the peers that will load it
+            if (j < n) peer.grad_bufs[peer.rank][slot + j] = g;
+            __threadfence_system();
+        } else if (j < n) {
             for (int r = 0; r < peer.world; ++r) peer.grad_bufs[r][slot + j] = g;
+        }
         __syncwarp();                   // the lanes' stores happen before the releasing lanes' flag stores (cumulative)
         const int nblk = gridDim.x;
         if (jx < peer.world)            // lane r tells rank r that this rank's block has arrived there
@@ -105,8 +109,14 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
         __syncwarp();
         g = 0.0f;
         if (j < n) {
-            const float *mine = peer.grad_bufs[peer.rank] + (int64_t)par * peer.world * peer.buf_stride;
-            for (int r = 0; r < peer.world; ++r) g += ld_relaxed_sys(mine + (int64_t)r * peer.buf_stride + j);   // rank order
+            const int64_t row0 = (int64_t)par * peer.world * peer.buf_stride;
+            if (peer.pull) {            // every rank's own slot, through the peer mappings
+                for (int r = 0; r < peer.world; ++r)
+                    g += ld_relaxed_sys(peer.grad_bufs[r] + row0 + (int64_t)r * peer.buf_stride + j);             // rank order
+            } else {
+                const float *mine = peer.grad_bufs[peer.rank] + row0;
+                for (int r = 0; r < peer.world; ++r) g += ld_relaxed_sys(mine + (int64_t)r * peer.buf_stride + j);   // rank order
+            }
         }
     }
     if (j >= n) return;

@@ -67,6 +67,9 @@ class PeerExchange(object):
     def __init__(self, n_params):
         self.ok = False
         self.step = 0
+        # push (remote stores) wins up to 4 GPUs, pull (remote loads) on 8: measured, profiles/r1_scaling.md
+        mode = os.environ.get("MQ_PEER_MODE", "auto")
+        self.pull = 1 if mode == "pull" or (mode == "auto" and world() >= 8) else 0
         if world() == 1 or not torch.cuda.is_available() or os.environ.get("MQ_NO_PEER_EXCHANGE"):
             return
         if dist.get_backend() != "nccl":
@@ -107,4 +110,5 @@ class PeerExchange(object):
         d.rank, d.world = rank(), world()
         d.grad_bufs, d.flag_bufs = self.grad_ptrs.data_ptr(), self.flag_ptrs.data_ptr()
         d.buf_stride, d.step = self.stride, self.step
+        d.pull = self.pull
         return d
