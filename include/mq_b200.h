@@ -189,11 +189,20 @@ int64_t mq_mlp_acts_floats(const mq_net_t *net, int64_t batch);
 int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch);
 int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                    int64_t batch, float *acts, void *stream);
+/* The same; with a workspace (any size; mq_mlp_ws_bytes is plenty) thin layers with a long contraction are split along K */
+int mq_mlp_forward_ws(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx, int64_t batch,
+                      float *acts, void *ws, int64_t ws_bytes, void *stream);
 /* grad[n_params] = scale * sum over batch (scale = 1/batch is the reference's
  * batch MEAN, basicnet.py:242-249); dy is clobbered; dx (nullable) = grad wrt x. */
 int mq_mlp_backward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                     const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx,
                     void *ws, int64_t ws_bytes, void *stream);
+/* The same with the parameter-gradient products on `side_stream` (NULL: plain mq_mlp_backward), overlapping the chain
+ * g_l -> g_{l-1} on `stream`: events = n_layers + 1 cudaEvent_t handles owned by the caller (events[l] orders dW_l after
+ * g_l, events[n_layers] joins side_stream back into stream).  Capturable in a CUDA graph (fork / join edges). */
+int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                            const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx,
+                            void *ws, int64_t ws_bytes, void *stream, void *side_stream, void *const *events);
 
 /* ---- fused small-MLP path (weights resident in shared memory) -------------- */
 /* rows per tile the fused kernels would use for this net (0 = does not fit). */

@@ -43,8 +43,12 @@ gemm_kernel(GemmArgs g) {
             int64_t gm = m0 + mm, gk = kt + kk;
             float v = 0.0f;
             if (gm < g.m && gk < k_end) {
-                if (g.idx) { if (g.idx_on_k) gk = g.idx[gk]; else gm = g.idx[gm]; }
-                v = g.a[gm * g.a_rs + gk * g.a_cs];
+                if (g.a_ones_row > 0 && gm >= g.a_ones_row) {
+                    v = 1.0f;
+                } else {
+                    if (g.idx) { if (g.idx_on_k) gk = g.idx[gk]; else gm = g.idx[gm]; }
+                    v = g.a[gm * g.a_rs + gk * g.a_cs];
+                }
             }
             ra[i] = v;
         }
@@ -127,7 +131,7 @@ int mq_gemm_tc_launch(const GemmArgs &g, int64_t splits, void *stream);      // 
 static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, void *stream, const char *what) {
     if (g.m <= 0 || g.n <= 0) return MQ_OK;
     const int sms = mq_sm_count();
-    {   // large problems: tcgen05 kernel on 128 x 128 tiles (mq_gemm_tc.cu), same epilogues / gather / split-K
+    if (g.a_ones_row == 0) {   // large problems: tcgen05 kernel on 128 x 128 tiles (mq_gemm_tc.cu), same epilogues / gather / split-K
         GemmArgs gt = g;
         const int64_t tiles = mq_ceil_div(g.m, 128) * mq_ceil_div(g.n, 128);
         int64_t splits = 1;
@@ -229,11 +233,19 @@ extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
         const int64_t w = (int64_t)net->in[l] * net->out[l];
         if (w > max_w) max_w = w;
     }
-    return (2 * batch * net_max_width(net) + 64 * max_w) * (int64_t)sizeof(float) + 256;
+    const int64_t nbuf = net->n_layers > 2 ? net->n_layers : 2;     // one gradient buffer per layer (overlapped backward)
+    return (nbuf * batch * net_max_width(net) + 64 * max_w) * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x,
                               const int32_t *row_idx, int64_t batch, float *acts, void *stream) {
+    return mq_mlp_forward_ws(net, theta, x, row_idx, batch, acts, nullptr, 0, stream);
+}
+
+// The same with a workspace: layers whose output has fewer tiles than the GPU has SMs and a long contraction (the
+// 784 -> 128 layer of mnist/mlp.py at batch 128: 16 tiles) are split along K, deterministically.
+extern "C" int mq_mlp_forward_ws(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                                 int64_t batch, float *acts, void *ws, int64_t ws_bytes, void *stream) {
     int rc = net_check(net, "mq_mlp_forward");
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_mlp_forward: negative batch");
@@ -250,7 +262,7 @@ extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const flo
         g.c = out; g.m = batch; g.n = net->out[l]; g.k = net->in[l];
         g.alpha = 1.0f; g.epi = EPI_BIAS_ACT; g.act = net->act[l]; g.leak = net->leak[l];
         g.bias = theta + net->b_off[l];
-        rc = gemm_run(g, nullptr, 0, stream, "mq_mlp_forward");
+        rc = gemm_run(g, ws, ws ? ws_bytes : 0, stream, "mq_mlp_forward");
         if (rc != MQ_OK) return rc;
         inp = out;
         out += (int64_t)net->out[l] * batch;
@@ -262,6 +274,17 @@ extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const fl
                                const int32_t *row_idx, const float *acts, float *dy, int64_t batch,
                                float scale, float *grad, float *dx, void *ws, int64_t ws_bytes,
                                void *stream) {
+    return mq_mlp_backward_overlap(net, theta, x, row_idx, acts, dy, batch, scale, grad, dx, ws, ws_bytes, stream, nullptr,
+                                   nullptr);
+}
+
+// side_stream != NULL: the parameter-gradient products (dW_l, db_l: nothing downstream but the optimiser needs them) run
+// on side_stream while the chain g_l -> g_{l-1} continues on `stream`; events[l] (l < L) orders dW_l after g_l,
+// events[L] joins side_stream back into `stream`.  Works inside a stream capture (the graph gets the fork / join edges).
+extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, const float *x,
+                                       const int32_t *row_idx, const float *acts, float *dy, int64_t batch,
+                                       float scale, float *grad, float *dx, void *ws, int64_t ws_bytes,
+                                       void *stream, void *side_stream, void *const *events) {
     int rc = net_check(net, "mq_mlp_backward");
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_mlp_backward: empty batch");
@@ -269,9 +292,14 @@ extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const fl
     MQ_REQUIRE(ws_bytes >= mq_mlp_ws_bytes(net, batch), MQ_ERR_SHAPE, "mq_mlp_backward: workspace too small");
     const int L = net->n_layers;
     const int64_t maxw = net_max_width(net);
-    float *gbuf[2] = {(float *)ws, (float *)ws + batch * maxw};
-    float *split_ws = (float *)ws + 2 * batch * maxw;
-    const int64_t split_bytes = ws_bytes - 2 * batch * maxw * (int64_t)sizeof(float);
+    const int64_t nbuf = L > 2 ? L : 2;
+    float *split_ws = (float *)ws + nbuf * batch * maxw;
+    const int64_t split_bytes = ws_bytes - nbuf * batch * maxw * (int64_t)sizeof(float);
+    MQ_REQUIRE(!side_stream || events, MQ_ERR_INVALID, "mq_mlp_backward_overlap: events missing");
+#ifdef MQ_EMU
+    side_stream = nullptr;
+#endif
+    void *w_stream = side_stream ? side_stream : stream;     // where the dW / db products go
 
     // offsets of each layer's saved output inside acts
     int64_t off[MQ_MAX_LAYERS];
@@ -284,9 +312,17 @@ extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const fl
                              net->leak[L - 1], stream);
         if (rc != MQ_OK) return rc;
     }
-    int flip = 0;
     for (int l = L - 1; l >= 0; --l) {
         const float *inp = (l == 0) ? x : acts + off[l - 1];
+#ifndef MQ_EMU
+        if (side_stream) {                                   // g_l is complete on `stream`: let the side stream see it
+            if (cudaEventRecord((cudaEvent_t)events[l], (cudaStream_t)stream) != cudaSuccess ||
+                cudaStreamWaitEvent((cudaStream_t)side_stream, (cudaEvent_t)events[l], 0) != cudaSuccess) {
+                mq_set_error("mq_mlp_backward_overlap: %s", cudaGetErrorString(cudaGetLastError()));
+                return MQ_ERR_CUDA;
+            }
+        }
+#endif
         // dW = scale * inp^T g      A(m=in, k=batch) = inp[k*in + m]
         GemmArgs g;
         memset(&g, 0, sizeof(g));
@@ -295,13 +331,20 @@ extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const fl
         g.b = g_cur; g.b_rs = net->out[l]; g.b_cs = 1;
         g.c = grad + net->w_off[l]; g.m = net->in[l]; g.n = net->out[l]; g.k = batch;
         g.alpha = scale; g.epi = EPI_SCALE;
-        rc = gemm_run(g, split_ws, split_bytes, stream, "mq_mlp_backward(dW)");
+        // small layers (FFMA kernel): the bias gradient 1^T g is one more row of the same product, written straight into
+        // b's slot behind W; large ones keep the tensor-core product and a separate column sum
+        const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l] &&
+                               (int64_t)net->in[l] * net->out[l] * batch < (1LL << 26);
+        if (fuse_bias) { g.m = net->in[l] + 1; g.a_ones_row = net->in[l]; }
+        rc = gemm_run(g, split_ws, split_bytes, w_stream, "mq_mlp_backward(dW)");
         if (rc != MQ_OK) return rc;
-        rc = mq_col_sum(g_cur, nullptr, batch, net->out[l], scale, grad + net->b_off[l], stream);
-        if (rc != MQ_OK) return rc;
+        if (!fuse_bias) {
+            rc = mq_col_sum(g_cur, nullptr, batch, net->out[l], scale, grad + net->b_off[l], w_stream);
+            if (rc != MQ_OK) return rc;
+        }
         if (l > 0 || dx) {
             // g_prev = (g W^T) * act'(saved output of layer l-1)     B(k=out, n=in) = W[n*out + k]
-            float *dst = (l == 0) ? dx : gbuf[flip];
+            float *dst = (l == 0) ? dx : (float *)ws + (int64_t)((l - 1) % nbuf) * batch * maxw;   // g_{l-1}: own buffer
             memset(&g, 0, sizeof(g));
             g.a = g_cur; g.a_rs = net->out[l]; g.a_cs = 1;
             g.b = theta + net->w_off[l]; g.b_rs = 1; g.b_cs = net->out[l];
@@ -316,8 +359,16 @@ extern "C" int mq_mlp_backward(const mq_net_t *net, const float *theta, const fl
             rc = gemm_run(g, nullptr, 0, stream, "mq_mlp_backward(dX)");
             if (rc != MQ_OK) return rc;
             g_cur = dst;
-            flip ^= 1;
         }
     }
+#ifndef MQ_EMU
+    if (side_stream) {
+        if (cudaEventRecord((cudaEvent_t)events[L], (cudaStream_t)side_stream) != cudaSuccess ||
+            cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)events[L], 0) != cudaSuccess) {
+            mq_set_error("mq_mlp_backward_overlap: %s", cudaGetErrorString(cudaGetLastError()));
+            return MQ_ERR_CUDA;
+        }
+    }
+#endif
     return MQ_OK;
 }

@@ -41,20 +41,29 @@ class MLPTrainer(object):
         self.idx = torch.zeros(graph_steps * batch, dtype=torch.int32, device=D.device())
         self.coefs = torch.zeros(graph_steps * 4, dtype=torch.float64, device=D.device())
         self._graph, self._graph_data = None, None
+        # parameter-gradient products on a side stream, overlapping the chain of activation gradients
+        self._side = torch.cuda.Stream()
+        self._events = [torch.cuda.Event() for _ in range(self.net.n_layers + 1)]
+        for ev in self._events:
+            ev.record()                                                # creates the CUDA event behind the handle
+        self._event_ptrs = (ctypes.c_void_p * len(self._events))(*[ev.cuda_event for ev in self._events])
 
     # one step, all pointers fixed except through the idx / coef tables ---------------------
-    def _enqueue_step(self, x, y, s):
+    def _enqueue_step(self, x, y, s, idx_ptr=None, coef_ptr=None):
         nb, B = ctypes.byref(self.net), self.batch
-        idx_ptr = D.ptr(self.idx) + s * B * 4
+        idx_ptr = idx_ptr if idx_ptr is not None else D.ptr(self.idx) + s * B * 4
+        coef_ptr = coef_ptr if coef_ptr is not None else D.ptr(self.coefs) + s * 32
         value, m, v, _ = self.opt.state()
-        D.call("mq_mlp_forward", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, B, D.ptr(self.acts), D.stream())
+        D.call("mq_mlp_forward_ws", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, B, D.ptr(self.acts), D.ptr(self.ws), self.wsb,
+               D.stream())
         logits = self.acts[self.acts.numel() - B * self.n_out:]
         D.call("mq_softmax_ce_grad", D.ptr(logits), D.ptr(y), idx_ptr, B, self.n_out, self.l2,
                D.ptr(self.dy), D.stream())
-        D.call("mq_mlp_backward", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
-               D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, D.ptr(self.ws), self.wsb, D.stream())
+        D.call("mq_mlp_backward_overlap", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
+               D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, D.ptr(self.ws), self.wsb, D.stream(),
+               self._side.cuda_stream, self._event_ptrs)
         D.call("mq_adam_step_dev", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
-               self.net.n_params, self.opt._code, MQ_F32, D.ptr(self.coefs) + s * 32, 0, D.stream())
+               self.net.n_params, self.opt._code, MQ_F32, coef_ptr, 0, D.stream())
 
     def train_block(self, x, y, idx_table):
         """x f32[n,784] and y f32[n,10] device tensors (whole data set), idx_table host or device
@@ -71,10 +80,10 @@ class MLPTrainer(object):
         self.opt._out = None
         key = (D.ptr(x), D.ptr(y), steps)
         if self._graph is None or self._graph_data != key:
-            self._enqueue_step(x, y, 0)                    # warm-up outside capture (sets kernel attributes)
-            torch.cuda.current_stream().synchronize()
             value, m, v, _ = self.opt.state()
             snap = [t.clone() for t in (self.theta, value, m, v)]
+            self._enqueue_step(x, y, 0)                    # warm-up outside capture (sets kernel attributes)
+            torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for s in range(steps):
@@ -84,16 +93,49 @@ class MLPTrainer(object):
             self._graph, self._graph_data = g, key
         self._graph.replay()
 
+    def _sgd_setup(self):
+        """Staging for sgd_step: double-buffered pinned host buffers (batch, labels, Adam coefficients), fixed device
+        buffers, and the step captured once as a CUDA graph on them."""
+        B, dev = self.batch, D.device()
+        st = self._sgd = dict(slot=0)
+        st["pin"] = [(torch.empty(B, self.n_in).pin_memory(), torch.empty(B, self.n_out).pin_memory(),
+                      torch.empty(4, dtype=torch.float64).pin_memory()) for _ in range(2)]
+        st["np"] = [tuple(t.numpy() for t in trio) for trio in st["pin"]]
+        st["ev"] = [torch.cuda.Event() for _ in range(2)]
+        st["x"] = torch.empty(B, self.n_in, dtype=torch.float32, device=dev)
+        st["y"] = torch.empty(B, self.n_out, dtype=torch.float32, device=dev)
+        st["coef"] = torch.zeros(4, dtype=torch.float64, device=dev)
+        st["idx"] = torch.arange(B, dtype=torch.int32, device=dev)
+        st["graph"] = None
+        return st
+
     def sgd_step(self, inps, lbls):
-        """mlp.py:31-35 with host arrays: one H2D copy of the batch, one step, no D2H."""
+        """mlp.py:31-35 with host arrays: the batch goes through pinned staging (one async H2D copy each for images,
+        labels and the step's Adam coefficients), the step itself is one CUDA-graph replay; nothing is copied back."""
+        st = getattr(self, "_sgd", None) or self._sgd_setup()
         B = self.batch
-        x = D.from_host(np.asarray(inps, np.float32).reshape(B, self.n_in))
-        y = D.from_host(np.asarray(lbls, np.float32).reshape(B, self.n_out))
-        self.idx[:B].copy_(torch.arange(B, dtype=torch.int32, device=self.idx.device))
+        slot = st["slot"] = st["slot"] ^ 1
+        st["ev"][slot].synchronize()                       # the upload that last used this staging slot has finished
+        nx, ny, nc = st["np"][slot]
+        np.copyto(nx, np.asarray(inps, np.float32).reshape(B, self.n_in))
+        np.copyto(ny, np.asarray(lbls, np.float32).reshape(B, self.n_out))
         c1, c2 = self.opt.next_coefs()
-        self.coefs[:4].copy_(D.from_host(np.array([c1, c2, self.lr, 1e-8]), np.float64))
+        nc[:] = (c1, c2, self.lr, 1e-8)
+        px, py, pc = st["pin"][slot]
+        st["x"].copy_(px, non_blocking=True)
+        st["y"].copy_(py, non_blocking=True)
+        st["coef"].copy_(pc, non_blocking=True)
+        st["ev"][slot].record()
         self.opt._out = None
-        self._enqueue_step(x, y, 0)
+        if st["graph"] is None:
+            self._enqueue_step(st["x"], st["y"], 0, D.ptr(st["idx"]), D.ptr(st["coef"]))   # eager once (kernel attributes)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                              # capturing runs nothing: this call's step was the eager one
+                self._enqueue_step(st["x"], st["y"], 0, D.ptr(st["idx"]), D.ptr(st["coef"]))
+            st["graph"] = g
+            return
+        st["graph"].replay()
 
     def forward(self, inps):
         x = np.asarray(inps, np.float32).reshape(-1, self.n_in)

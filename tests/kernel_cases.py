@@ -252,6 +252,16 @@ def case_layered_mlp(B):
         for o in outs:
             close(got[pos:pos + o.size].reshape(o.shape), o, what="layered fwd %s" % (widths,))
             pos += o.size
+        # the same forward with a workspace (split-K over the 784-long contraction) and gathered rows
+        wsb = lib.mq_mlp_ws_bytes(net, batch)
+        ws2, acts2 = B.zeros(wsb, np.uint8), B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
+        perm = rs.permutation(batch).astype(np.int32)
+        hp = B.up(perm)
+        ok(B, lib.mq_mlp_forward_ws(net, B.ptr(ht), B.ptr(hx), B.ptr(hp), batch, B.ptr(acts2), B.ptr(ws2), wsb, B.stream))
+        got2, pos = B.down(acts2), 0
+        for o in outs:
+            close(got2[pos:pos + o.size].reshape(o.shape), o[perm], what="layered fwd + workspace %s" % (widths,))
+            pos += o.size
         dy = rs.randn(batch, widths[-1]).astype(np.float32)
         want, wdx = O.mlp_backward(theta, spec, x, outs, dy, want_dx=True)
         wsb = lib.mq_mlp_ws_bytes(net, batch)

@@ -568,6 +568,37 @@ def test_batched_actor_rollouts_and_closed_loop():
     assert np.all(D.to_host(upd.policy.theta)[-3:] < 0.0)          # the policy narrows its noise
 
 
+def test_mlp_trainer_matches_oracle():
+    """mnist/mlp.py:24-43 through MLPTrainer: `sgd_step(host batch, host labels)` (pinned staging + one graph replay per
+    step) and `train_block` (a block of steps as one graph; split-K forward, bias gradients inside the dW products,
+    parameter-gradient products overlapped on a side stream) both follow the oracle's restatement step for step."""
+    from oracle import mq_oracle as O
+    from mannequin2_b200.mlp import MLPTrainer
+    from mannequin2_b200.ppo import init_mlp
+    from mannequin2_b200 import _device as D
+    rs = np.random.RandomState(8)
+    n, steps, B = 600, 7, 128
+    x = rs.rand(n, 784).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rs.randint(10, size=n)]
+    tab = rs.randint(n, size=(steps, B)).astype(np.int32)
+    np.random.seed(4)
+    theta0 = init_mlp(784, [128, 128, 10], 0.1)
+    spec = O.mlp_spec(784, [128, 128, 10], [O.ACT_LRELU, O.ACT_LRELU, O.ACT_NONE])
+    opt = O.AdamO(theta0, horizon=10, lr=1e-3)
+    want = theta0.copy()
+    for s_ in range(steps):
+        want = O.mlp_sgd_step(want, spec, opt, x[tab[s_]], y[tab[s_]])
+    a = MLPTrainer(params=theta0.copy(), graph_steps=steps)
+    for s_ in range(steps):
+        a.sgd_step(x[tab[s_]].reshape(B, 28, 28), y[tab[s_]])
+    b = MLPTrainer(params=theta0.copy(), graph_steps=steps)
+    b.train_block(D.from_host(x), D.from_host(y), tab)
+    for got in (a.get_params(), b.get_params()):
+        assert np.max(np.abs(got - theta0)) > 1e-3
+        assert np.max(np.abs(got - want)) < 2e-6 * (1 + steps) + 1e-6, np.max(np.abs(got - want))
+    assert np.max(np.abs(a.get_params() - b.get_params())) < 2e-6 * (1 + steps)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
