@@ -96,9 +96,11 @@ int mq_debug_set_tile_rows(int tb);
  * (all zero initially); horizon <= 0: no forgetting (the reference's choice for observations). */
 int mq_obsnorm_step(const float *raw, int64_t rows, int32_t d, double horizon, double *state, float clip, float *out,
                     void *stream);
-/* n unit normals of the counter-based Philox4x32-10 stream (seed, stream_a, stream_b): deviate j = element j % 4 of the
- * Box-Muller pairs of block j / 4.  The rollout kernels draw from the same generator. */
-int mq_randn_philox(uint64_t seed, uint32_t stream_a, uint32_t stream_b, int64_t n, float *out, void *stream);
+/* n unit normals of the counter-based Philox4x32-10 stream (seed, stream_a, stream_b + *counter): deviate j = element
+ * j % 4 of the Box-Muller pairs of block j / 4.  counter (nullable) is a device word: a captured CUDA graph that bumps it
+ * draws fresh noise at every replay.  The rollout kernels draw from the same generator. */
+int mq_randn_philox(uint64_t seed, uint32_t stream_a, uint32_t stream_b, const int32_t *counter, int64_t n, float *out,
+                    void *stream);
 /* Synthetic on-device environment (the reference's environments are gym's: out of scope): hidden state x in R^d,
  * observation = obs_scale * x + obs_shift, x' = x + dt (-damp x + B a) + sigma noise, reward = -|x'|^2 / d - ctrl |a|^2 / A,
  * episode end after `horizon` steps or with probability p_end per step, restart from x ~ N(0, 1). */
@@ -266,6 +268,9 @@ int64_t mq_es_ws_bytes(int64_t n_members, int64_t n_params);
 /* C[M,N] = alpha * opA(A)[M,K] @ opB(B)[K,N]; element strides in floats */
 int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs,
             float *c, int64_t m, int64_t n, int64_t k, float alpha, void *stream);
+/* The same; with a workspace, products with few output tiles and a long contraction are split along K (deterministic) */
+int mq_gemm_ws(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs,
+               float *c, int64_t m, int64_t n, int64_t k, float alpha, void *ws, int64_t ws_bytes, void *stream);
 int mq_add_bias(const float *x, const float *b, float *y, int64_t rows, int64_t cols, void *stream);
 int mq_binary(const float *a, const float *b, float *out, int64_t n, int64_t b_period, int op,
               void *stream);                   /* op 0: a+b, 1: a*b; b is broadcast with period */

@@ -199,3 +199,23 @@ def _binop(name):
 for _n in ("add", "sub", "mul", "truediv", "pow", "radd", "rsub", "rmul", "rtruediv", "lt", "le",
            "gt", "ge", "eq", "ne", "matmul", "rmatmul"):
     setattr(DeviceVector, "__%s__" % _n, _binop("__%s__" % _n))
+
+
+class DeviceRNG(object):
+    """Unit normals generated on the device (counter-based Philox4x32-10, csrc/mq_rollout.cu) with the interface piece
+    `Gauss(..., rng=...)` looks for (`randn_dev`).  The stream position lives in device memory and is advanced by a
+    device op, so a CUDA graph that contains the draw produces fresh noise at every replay."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+        self._counter = torch.zeros(1, dtype=torch.int32, device=device())
+        self._draws = 0
+
+    def randn_dev(self, shape):
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=device())
+        call("mq_randn_philox", self.seed, 0x5eed, 0, ptr(self._counter), out.numel(), ptr(out), stream())
+        self._counter.add_(1)
+        return out
+
+    def randn(self, *shape):                 # host interface of np.random.RandomState, for code that wants arrays
+        return to_host(self.randn_dev(shape)).astype(np.float64)

@@ -93,6 +93,7 @@ SIGNATURES = {
     "mq_es_ws_bytes": (c_int64, [c_int64, c_int64]),
     "mq_gemm": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64,
                         c_float, P]),
+    "mq_gemm_ws": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64, c_float, P, c_int64, P]),
     "mq_add_bias": (c_int, [P, P, P, c_int64, c_int64, P]),
     "mq_binary": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "mq_col_sum": (c_int, [P, P, c_int64, c_int64, c_float, P, P]),
@@ -102,7 +103,7 @@ SIGNATURES = {
     "mq_clip_backward": (c_int, [P, P, P, c_int64, c_float, c_float, P]),
     "mq_gauss_logprob": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P]),
     "mq_obsnorm_step": (c_int, [P, c_int64, c_int32, ctypes.c_double, P, c_float, P, P]),
-    "mq_randn_philox": (c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_int64, P, P]),
+    "mq_randn_philox": (c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, P, c_int64, P, P]),
     "mq_env_reset": (c_int, [POINTER(MqEnv), c_int64, ctypes.c_uint64, P, P, P, P]),
     "mq_actor_env_step": (c_int, [POINTER(MqEnv), c_int64, c_int32, c_int32, ctypes.c_uint64, ctypes.c_uint32, P, P, P,
                                   P, P, P, P, P, P, P, P, P]),

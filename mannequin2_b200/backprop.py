@@ -91,7 +91,13 @@ def multiply(a, b):
 
 def _gemm(a, a_rs, a_cs, b, b_rs, b_cs, m, n, k, like):
     c = _new((m, n), like)
-    D.call("mq_gemm", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.stream())
+    if k >= 1024 and m * n <= (1 << 22):
+        # few output tiles, long contraction (dW = x^T g over a large batch): let the GEMM split along K
+        wsb = min(8 * m * n * 4, 64 << 20)
+        ws = D.workspace("gemm", wsb)
+        D.call("mq_gemm_ws", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.ptr(ws), wsb, D.stream())
+    else:
+        D.call("mq_gemm", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.stream())
     return c
 
 

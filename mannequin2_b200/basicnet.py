@@ -301,8 +301,19 @@ class Function(Layer):
             return self._plan.evaluate(array, **kwargs)
         return self._evaluate_graph(array, **kwargs)
 
-    def _evaluate_graph(self, array, **kwargs):
-        x_dev = D.from_host(array)
+    def evaluate_dev(self, x_dev, **kwargs):
+        """Device tensors in, device tensors out: (output, backprop) with backprop(grad_dev) -> DeviceVector.  Always the
+        node-by-node path; nothing synchronises with the host, so a whole step can be captured in a CUDA graph."""
+        return self._evaluate_graph(None, x_dev=x_dev, **kwargs)
+
+    def _evaluate_graph(self, array, x_dev=None, **kwargs):
+        on_dev = x_dev is not None
+        if on_dev:
+            assert D.is_dev(x_dev) and x_dev.dtype == torch.float32
+            x_dev = x_dev.contiguous()
+            array = x_dev                       # only its .shape is used below
+        else:
+            x_dev = D.from_host(array)
         outs, bpps = {}, {}
         for layer in self.prerequisites:
             if isinstance(layer, Function):
@@ -314,6 +325,8 @@ class Function(Layer):
             elif isinstance(layer, (Params, Const)):
                 out, bpp = layer.dev, None
             else:                          # foreign Layer subclass: host evaluate
+                if on_dev:
+                    raise NotImplementedError("evaluate_dev: %r has no device evaluation" % (layer,))
                 hout, hbpp = layer.evaluate(array)
                 out, bpp = D.from_host(np.asarray(hout), np.float32), hbpp
             outs[layer], bpps[layer] = out, bpp
@@ -366,6 +379,8 @@ class Function(Layer):
                 return output
             return D.DeviceVector(flat, (n_params,), writeable=True)
 
+        if on_dev:
+            return out, backprop
         return _readonly(D.to_host(out)), backprop
 
 

@@ -199,6 +199,20 @@ extern "C" int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *
     return gemm_run(g, nullptr, 0, stream, "mq_gemm");
 }
 
+// The same with a workspace: products with few output tiles and a long contraction (dW = x^T g over a batch of
+// thousands) are split along K, deterministically (partials summed in a fixed order).
+extern "C" int mq_gemm_ws(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs,
+                          int64_t b_cs, float *c, int64_t m, int64_t n, int64_t k, float alpha, void *ws,
+                          int64_t ws_bytes, void *stream) {
+    MQ_REQUIRE(m >= 0 && n >= 0 && k >= 0, MQ_ERR_SHAPE, "mq_gemm_ws: negative size");
+    MQ_REQUIRE((m == 0 || n == 0) || (a && b && c), MQ_ERR_INVALID, "mq_gemm_ws: null pointer");
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.a = a; g.a_rs = a_rs; g.a_cs = a_cs; g.b = b; g.b_rs = b_rs; g.b_cs = b_cs;
+    g.c = c; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.epi = EPI_SCALE;
+    return gemm_run(g, ws, ws ? ws_bytes : 0, stream, "mq_gemm_ws");
+}
+
 // ---- layered MLP path --------------------------------------------------------------
 static int net_check(const mq_net_t *net, const char *what) {
     MQ_REQUIRE(net, MQ_ERR_INVALID, "%s: null net", what);

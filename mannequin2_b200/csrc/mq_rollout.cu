@@ -58,7 +58,9 @@ __host__ __device__ __forceinline__ float ro_normal(uint64_t seed, uint32_t a, u
 }
 
 __global__ void __launch_bounds__(MQ_NT)
-randn_philox_kernel(uint64_t seed, uint32_t a, uint32_t b, int64_t n, float *__restrict__ out) {
+randn_philox_kernel(uint64_t seed, uint32_t a, uint32_t b0, const int32_t *__restrict__ counter, int64_t n,
+                    float *__restrict__ out) {
+    const uint32_t b = b0 + (counter ? (uint32_t)counter[0] : 0u);
     const int64_t nblk = (n + 3) / 4;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nblk; q += (int64_t)gridDim.x * blockDim.x) {
         float z[4];
@@ -68,14 +70,15 @@ randn_philox_kernel(uint64_t seed, uint32_t a, uint32_t b, int64_t n, float *__r
     }
 }
 
-extern "C" int mq_randn_philox(uint64_t seed, uint32_t stream_a, uint32_t stream_b, int64_t n, float *out, void *stream) {
+extern "C" int mq_randn_philox(uint64_t seed, uint32_t stream_a, uint32_t stream_b, const int32_t *counter, int64_t n,
+                               float *out, void *stream) {
     MQ_REQUIRE(n >= 0 && n < (1LL << 33), MQ_ERR_SHAPE, "mq_randn_philox: bad size");
     if (n == 0) return MQ_OK;
     MQ_REQUIRE(out, MQ_ERR_INVALID, "mq_randn_philox: null pointer");
     int64_t nb = mq_ceil_div(mq_ceil_div(n, 4), MQ_NT);
     const int64_t cap = (int64_t)mq_sm_count() * 8;
     if (nb > cap) nb = cap;
-    MQ_LAUNCH(randn_philox_kernel, (unsigned)nb, MQ_NT, 0, stream, seed, stream_a, stream_b, n, out);
+    MQ_LAUNCH(randn_philox_kernel, (unsigned)nb, MQ_NT, 0, stream, seed, stream_a, stream_b, counter, n, out);
     MQ_CHECK_LAUNCH("mq_randn_philox");
     return MQ_OK;
 }

@@ -43,7 +43,10 @@ class Gauss(object):
         def sample(mean_v, logstd_v):
             mean_v, logstd_v = mean_v.contiguous(), logstd_v.contiguous()
             period = _period(mean_v, logstd_v)
-            unit = D.from_host(rng.randn(*mean_v.shape), np.float32)
+            if hasattr(rng, "randn_dev"):            # device generator (no host round trip; capturable)
+                unit = rng.randn_dev(tuple(mean_v.shape))
+            else:
+                unit = D.from_host(rng.randn(*mean_v.shape), np.float32)
             out, noise = torch.empty_like(mean_v), torch.empty_like(mean_v)
             D.call("mq_gauss_sample", D.ptr(mean_v), D.ptr(logstd_v), period, D.ptr(unit),
                    mean_v.numel() // n_act, n_act, D.ptr(out), D.ptr(noise), D.stream())
@@ -63,7 +66,10 @@ class Gauss(object):
             period = _period(mean_v, logstd_v)
             rows = mean_v.numel() // n_act
             batch_shape = tuple(mean_v.shape)[:mean_v.dim() - len(mean.shape)]
-            s = D.from_host(np.asarray(sample, dtype=np.float32).reshape(-1))
+            if D.is_dev(sample):
+                s = sample.to(torch.float32).contiguous().reshape(-1)
+            else:
+                s = D.from_host(np.asarray(sample, dtype=np.float32).reshape(-1))
             assert s.numel() == mean_v.numel()
             logp = torch.empty(batch_shape, dtype=torch.float32, device=mean_v.device)
             D.call("mq_gauss_logprob", D.ptr(mean_v), D.ptr(logstd_v), period, D.ptr(s), rows, n_act,

@@ -94,3 +94,44 @@ class VAETrainer(object):
                    self.n_params, 0.9, 1.0, self.lr, D.stream())
             self.decoder.load_params(D.DeviceVector(theta, (self.n_params,)))
         return float(np.mean(logprob)), float(np.mean(dkl_value))
+
+    # -- device-resident step: no host round trip, capturable ----------------------------------------------------
+    def step_dev(self, x_dev):
+        """The same iteration with the batch already on the device (float32 [B, *image_shape]) and the sampling noise
+        drawn on the device (construct the trainer with rng=DeviceRNG(seed)).  Returns device scalars
+        (mean logprob, mean DKL); nothing synchronises with the host."""
+        n = x_dev.shape[0]
+        if getattr(self, "_ones", None) is None or self._ones.numel() != n:
+            self._ones = torch.ones(n, dtype=torch.float32, device=x_dev.device)
+            self._minus = -self._ones
+        logprob, backprop = self.decoder.logprob.evaluate_dev(x_dev, sample=x_dev)
+        grad1 = D.as_dev_f32(backprop(self._ones))
+        dkl_value, backprop = self.dkl.evaluate_dev(x_dev)
+        grad2 = D.as_dev_f32(backprop(self._minus))
+        flat = self.decoder.logprob._flat
+        assert flat is not None, "step_dev needs the parameters in one arena slice"
+        if self.momentum is None:
+            self.momentum = D.zeros(self.n_params)
+        D.call("mq_momentum_step", D.ptr(flat), D.ptr(self.momentum), D.ptr(grad1), D.ptr(grad2), grad2.numel(),
+               self.n_params, 0.9, 1.0, self.lr, D.stream())
+        return logprob.mean(), dkl_value.mean()
+
+    def step_graph(self, x_dev):
+        """step_dev replayed as ONE CUDA graph (~110 kernel launches per step otherwise).  The first call runs eagerly and
+        captures; later calls copy the batch into the captured input buffer and replay.  Returns the device scalars of
+        the replayed step."""
+        g = getattr(self, "_graph", None)
+        if g is None or self._graph_in.shape != x_dev.shape:
+            if self.momentum is None:
+                self.momentum = D.zeros(self.n_params)
+            self._graph_in = x_dev.clone()
+            out = self.step_dev(self._graph_in)            # eager: sets kernel attributes, sizes every workspace
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self.step_dev(self._graph_in)
+            self._graph = g
+            return out
+        self._graph_in.copy_(x_dev, non_blocking=True)
+        g.replay()
+        return self._graph_out

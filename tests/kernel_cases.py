@@ -658,8 +658,11 @@ def case_rollout(B, n_env=300):
     # ---- Philox normals
     n = 1003
     z = B.zeros(n, np.float32)
-    ok(B, lib.mq_randn_philox(seed, 7, 9, n, B.ptr(z), B.stream))
+    ok(B, lib.mq_randn_philox(seed, 7, 9, None, n, B.ptr(z), B.stream))
     want = O.philox_normals(seed, 7, 9, np.arange(n))
+    assert np.max(np.abs(B.down(z) - want)) < 1e-5
+    ctr = B.up(np.array([5], np.int32))                     # device-resident stream offset
+    ok(B, lib.mq_randn_philox(seed, 7, 4, B.ptr(ctr), n, B.ptr(z), B.stream))
     assert np.max(np.abs(B.down(z) - want)) < 1e-5
     # ---- NormalizedObservations: the reference's wrapper, one observation per step (E = 1)
     g = golden("obsnorm")

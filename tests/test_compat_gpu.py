@@ -599,6 +599,34 @@ def test_mlp_trainer_matches_oracle():
     assert np.max(np.abs(a.get_params() - b.get_params())) < 2e-6 * (1 + steps)
 
 
+def test_vae_device_step_and_graph_replay():
+    """VAETrainer.step_dev / step_graph (the whole mnist/vae.py:57-71 iteration without a host round trip, replayed as
+    one CUDA graph, sampling noise from the device Philox generator) follow the host-API `step` exactly: same
+    parameters after three iterations, and the noise differs from replay to replay."""
+    import torch
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.vae import VAETrainer
+    rs = np.random.RandomState(21)
+    xs = [rs.rand(32, 6, 5).astype(np.float32) for _ in range(3)]
+    finals, stats = [], []
+    for mode in ("host", "graph"):
+        np.random.seed(9)
+        tr = VAETrainer(image_shape=(6, 5), hidden=16, latent=3, n_hidden=1, rng=D.DeviceRNG(77))
+        for x in xs:
+            if mode == "host":
+                lp, kl = tr.step(x)
+            else:
+                lp, kl = (float(v) for v in tr.step_graph(D.from_host(x)))
+            stats.append((lp, kl))
+        finals.append(np.array(tr.decoder.get_params()))
+    assert np.max(np.abs(finals[0] - finals[1])) < 1e-6, np.max(np.abs(finals[0] - finals[1]))
+    for a, b in zip(stats[:3], stats[3:]):
+        assert abs(a[0] - b[0]) < 1e-4 * (1 + abs(a[0])) and abs(a[1] - b[1]) < 1e-4 * (1 + abs(a[1]))
+    rng = D.DeviceRNG(5)
+    z1, z2 = D.to_host(rng.randn_dev((4, 3))), D.to_host(rng.randn_dev((4, 3)))
+    assert not np.array_equal(z1, z2) and abs(z1.mean()) < 2.0
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
