@@ -104,10 +104,49 @@ col_sum_kernel(const float *__restrict__ g, const float *__restrict__ a, int64_t
     }
 }
 
+// The same for tall matrices (thousands of rows): block = 8 columns x 32 row-lanes, so that a 4096 x 784 bias gradient is
+// 98 CTAs of 128 independent 32-byte loads per thread instead of 25 CTAs of 512; fixed order (four interleaved partial
+// sums per thread, then the 32 row-lanes in order).
+__global__ void __launch_bounds__(MQ_NT)
+col_sum_tall_kernel(const float *__restrict__ g, const float *__restrict__ a, int64_t rows, int64_t cols,
+                    float scale, float *__restrict__ out) {
+    __shared__ float part[32][9];
+    const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int64_t c = (int64_t)blockIdx.x * 8 + cx;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (c < cols) {
+        int64_t r = ry;
+        for (; r + 96 < rows; r += 128) {
+            const float g0 = g[r * cols + c], g1 = g[(r + 32) * cols + c], g2 = g[(r + 64) * cols + c],
+                        g3 = g[(r + 96) * cols + c];
+            if (a) {
+                s0 += g0 * a[r * cols + c]; s1 += g1 * a[(r + 32) * cols + c];
+                s2 += g2 * a[(r + 64) * cols + c]; s3 += g3 * a[(r + 96) * cols + c];
+            } else {
+                s0 += g0; s1 += g1; s2 += g2; s3 += g3;
+            }
+        }
+        for (; r < rows; r += 32) s0 += a ? g[r * cols + c] * a[r * cols + c] : g[r * cols + c];
+    }
+    part[ry][cx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float s = part[0][cx];
+#pragma unroll
+        for (int k = 1; k < 32; ++k) s += part[k][cx];
+        out[c] = s * scale;
+    }
+}
+
 extern "C" int mq_col_sum(const float *g, const float *a, int64_t rows, int64_t cols, float scale,
                           float *out, void *stream) {
     MQ_REQUIRE(rows >= 0 && cols >= 1, MQ_ERR_SHAPE, "mq_col_sum: bad shape");
     MQ_REQUIRE(g && out, MQ_ERR_INVALID, "mq_col_sum: null pointer");
+    if (rows >= 1024) {
+        MQ_LAUNCH(col_sum_tall_kernel, (unsigned)mq_ceil_div(cols, 8), MQ_NT, 0, stream, g, a, rows, cols, scale, out);
+        MQ_CHECK_LAUNCH("mq_col_sum");
+        return MQ_OK;
+    }
     MQ_LAUNCH(col_sum_kernel, (unsigned)mq_ceil_div(cols, 32), MQ_NT, 0, stream, g, a, rows, cols, scale, out);
     MQ_CHECK_LAUNCH("mq_col_sum");
     return MQ_OK;
@@ -186,6 +225,26 @@ gauss_logp_kernel(const float *__restrict__ mu, const float *__restrict__ ls, in
     }
 }
 
+// wide actions (the 784-pixel decoder of mnist/vae.py): one warp per row, lanes along the action axis
+__global__ void __launch_bounds__(MQ_NT)
+gauss_logp_wide_kernel(const float *__restrict__ mu, const float *__restrict__ ls, int64_t period,
+                       const float *__restrict__ s, int64_t rows, int64_t a, float *__restrict__ logp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        float acc = 0.0f;
+        for (int64_t j = lane; j < a; j += 32) {
+            const int64_t e = r * a + j;
+            const float l = ls[e % period];
+            const float z = (s[e] - mu[e]) * expf(-l);
+            acc += l + 0.5f * z * z;
+        }
+        acc = mq_warp_sum(acc);
+        if (lane == 0) logp[r] = -(float)a * MQ_HALF_LOG_2PI - acc;
+    }
+}
+
 __global__ void __launch_bounds__(MQ_NT)
 gauss_logp_bwd_kernel(const float *__restrict__ mu, const float *__restrict__ ls, int64_t period,
                       const float *__restrict__ s, const float *__restrict__ g, int64_t n, int64_t a,
@@ -216,7 +275,11 @@ extern "C" int mq_gauss_logprob(const float *mu, const float *logstd, int64_t lo
     MQ_REQUIRE(rows >= 0 && a >= 1 && logstd_period >= 1, MQ_ERR_SHAPE, "mq_gauss_logprob: bad shape");
     if (rows == 0) return MQ_OK;
     MQ_REQUIRE(mu && logstd && sample && logp, MQ_ERR_INVALID, "mq_gauss_logprob: null pointer");
-    MQ_LAUNCH(gauss_logp_kernel, ew_blocks(rows), MQ_NT, 0, stream, mu, logstd, logstd_period, sample, rows, a, logp);
+    if (a >= 64)
+        MQ_LAUNCH(gauss_logp_wide_kernel, ew_blocks(rows * 32), MQ_NT, 0, stream, mu, logstd, logstd_period, sample, rows,
+                  a, logp);
+    else
+        MQ_LAUNCH(gauss_logp_kernel, ew_blocks(rows), MQ_NT, 0, stream, mu, logstd, logstd_period, sample, rows, a, logp);
     MQ_CHECK_LAUNCH("mq_gauss_logprob");
     return MQ_OK;
 }

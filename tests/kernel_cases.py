@@ -522,6 +522,11 @@ def case_ops(B):
     hg, hx, out = B.up(g), B.up(x), B.zeros(7, np.float32)
     ok(B, lib.mq_col_sum(B.ptr(hg), B.ptr(hx), 50, 7, 0.5, B.ptr(out), B.stream))
     close(B.down(out), 0.5 * (g * x).sum(axis=0), what="col_sum")
+    for with_a in (True, False):                            # tall matrices: the 8-column x 32-row-lane kernel
+        gt, xt = rs.randn(1500, 77).astype(np.float32), rs.randn(1500, 77).astype(np.float32)
+        hgt, hxt, outt = B.up(gt), B.up(xt), B.zeros(77, np.float32)
+        ok(B, lib.mq_col_sum(B.ptr(hgt), B.ptr(hxt) if with_a else None, 1500, 77, 0.25, B.ptr(outt), B.stream))
+        close(B.down(outt), 0.25 * (gt.astype(np.float64) * (xt if with_a else 1.0)).sum(axis=0), what="col_sum tall")
     y = B.zeros((50, 7), np.float32)
     ok(B, lib.mq_binary(B.ptr(hx), B.ptr(out), B.ptr(y), 350, 7, 1, B.stream))
     assert np.array_equal(B.down(y), x * B.down(out))
@@ -543,6 +548,12 @@ def case_ops(B):
     hmu, hls, hs, lp = B.up(mu), B.up(ls), B.up(s), B.zeros(9, np.float32)
     ok(B, lib.mq_gauss_logprob(B.ptr(hmu), B.ptr(hls), 3, B.ptr(hs), 9, 3, B.ptr(lp), B.stream))
     close(B.down(lp), O.gauss_logprob(mu, ls, s), what="gauss logp")
+    # wide actions with a per-row logstd (the decoder of mnist/vae.py): warp-per-row kernel
+    muw, lsw, sw = rs.randn(21, 100).astype(np.float32), (rs.randn(21, 100) * 0.3).astype(np.float32), \
+        rs.randn(21, 100).astype(np.float32)
+    hmw, hlw, hsw, lpw = B.up(muw), B.up(lsw), B.up(sw), B.zeros(21, np.float32)
+    ok(B, lib.mq_gauss_logprob(B.ptr(hmw), B.ptr(hlw), 2100, B.ptr(hsw), 21, 100, B.ptr(lpw), B.stream))
+    close(B.down(lpw), O.gauss_logprob(muw, lsw, sw), rtol=2e-5, what="gauss logp wide")
     w = rs.randn(9).astype(np.float32)
     hw, dmu, dls = B.up(w), B.zeros((9, 3), np.float32), B.zeros((9, 3), np.float32)
     ok(B, lib.mq_gauss_logprob_bwd(B.ptr(hmu), B.ptr(hls), 3, B.ptr(hs), B.ptr(hw), 9, 3, B.ptr(dmu), B.ptr(dls), B.stream))
