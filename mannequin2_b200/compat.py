@@ -16,3 +16,16 @@ for _name, _mod in (("basicnet", basicnet), ("backprop", backprop), ("distrib", 
                     ("_adam", _adam), ("_normalize", _normalize), ("_trajectory", _trajectory),
                     ("_utils", _utils)):
     sys.modules.setdefault("mannequin." + _name, _mod)
+
+
+def _alias_gym():
+    # mannequin.gym (one_step, episode, NormalizedObservations, PrintRewards) needs a CUDA device behind its normaliser:
+    # aliased lazily so that importing compat on a machine without one still works for everything else
+    from mannequin2_b200 import gym as _gym
+    sys.modules.setdefault("mannequin.gym", _gym)
+
+
+try:
+    _alias_gym()
+except Exception:                                # pragma: no cover
+    pass

@@ -627,6 +627,55 @@ def test_vae_device_step_and_graph_replay():
     assert not np.array_equal(z1, z2) and abs(z1.mean()) < 2.0
 
 
+def test_reinforce_script_loop_and_reward_log():
+    """benchmarks/policy.py:29-47 (plain REINFORCE: episode -> Trajectory.discounted -> RunningNormalize -> tanh ->
+    logprob backprop -> Adam) written against `mannequin` / `mannequin.gym`, on a small NumPy environment wrapped in
+    NormalizedObservations and PrintRewards; the reward log has the format of benchmarks/_env.py:60-63."""
+    import mannequin2_b200.compat  # noqa: F401
+    from mannequin import Adam, RunningNormalize
+    from mannequin.basicnet import Input, Affine, Tanh
+    from mannequin.distrib import Gauss
+    from mannequin.gym import NormalizedObservations, PrintRewards, episode, log_line
+
+    class PointMass(object):                     # reach the origin: reward -|x|^2, 25 steps per episode
+        def __init__(self):
+            self.rs, self.t = np.random.RandomState(0), 0
+
+        def reset(self):
+            self.x, self.t = self.rs.randn(2), 0
+            return self.x * 3.0 + 1.0
+
+        def step(self, action):
+            self.x = self.x + 0.3 * np.clip(np.asarray(action, dtype=np.float64).reshape(2), -1, 1)
+            self.t += 1
+            return self.x * 3.0 + 1.0, -float(np.sum(self.x ** 2)), self.t >= 25, {}
+
+    lines = []
+    env = PrintRewards(NormalizedObservations(PointMass(), shape=(2,)), every=250,
+                       print=lambda s_, r: lines.append(log_line(s_, r)))
+    np.random.seed(1)
+    policy = Input(2)
+    for _ in range(2):
+        policy = Tanh(Affine(policy, 64))
+    policy = Gauss(mean=Affine(policy, 2, init=0.1))
+    opt = Adam(policy.get_params(), horizon=10)
+    normalize = RunningNormalize(horizon=2)
+    start = np.array(policy.get_params())
+    for _ in range(40):
+        traj = episode(env, policy.sample)
+        assert len(traj) == 25
+        traj = traj.discounted(horizon=500)
+        traj = traj.modified(rewards=normalize)
+        traj = traj.modified(rewards=np.tanh)
+        _, backprop = policy.logprob.evaluate(traj.o, sample=traj.a)
+        opt.apply_gradient(backprop(traj.r), lr=0.001)
+        policy.load_params(opt.get_value())
+    assert np.max(np.abs(np.array(policy.get_params()) - start)) > 1e-3
+    assert len(lines) == 4 and all(len(l.split()) == 2 and l.endswith("\n") for l in lines)
+    assert lines[0].split()[0] == "250" and "." in lines[0].split()[1] and len(lines[0].split()[1].split(".")[1]) == 2
+    assert np.all(np.abs(env.env.get_mean() - 1.0) < 3.0) and np.all(env.env.get_std() > 0.1)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
