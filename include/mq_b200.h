@@ -168,6 +168,16 @@ int mq_norm_cov(const void *x, int x_dtype, int64_t rows, int64_t cols, const do
                 const double *mean_new, double scale, double *out, void *ws, int64_t ws_bytes,
                 void *stream);
 /* out = (x-mean)/max(1e-8,sqrt(var)); fuse_tanh applies benchmarks/ppo.py:25 */
+/* ONE statistics pass for RunningNormalize.update (_normalize.py:40-57): out[0..cols) = scale/rows * sum_r (x - shift),
+ * out[cols..2cols) = scale/rows * sum_r (x - shift)^2, fp64, fixed order.  With shift = the running mean before the
+ * update, mean(x) = shift + s1 and mean((x - mean_old)(x - mean_new)) = s2 - (mean_new - mean_old) s1. */
+int64_t mq_norm_stats_ws_bytes(int64_t rows, int64_t cols);
+int mq_norm_stats(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *shift, double scale, double *out,
+                  void *ws, int64_t ws_bytes, void *stream);
+/* stats (taken with shift = mean) -> running state: mean += coef_mean * s1; when coef_var > 0:
+ * var += coef_var * (var_scale * (s2 - (mean_new - mean_old) * s1) - var)   (_normalize.py:9-25,44-57) */
+int mq_norm_update_from_stats(double *mean, double *var, const double *stats, int64_t cols, double coef_mean,
+                              double coef_var, double var_scale, void *stream);
 int mq_norm_apply(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *mean,
                   const double *var, void *out, int out_dtype, int fuse_tanh, void *stream);
 

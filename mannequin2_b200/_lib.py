@@ -63,6 +63,9 @@ SIGNATURES = {
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
                              c_double, c_int, P]),
     "mq_adam_step_dev": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P, c_int, P]),
+    "mq_norm_stats_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "mq_norm_stats": (c_int, [P, c_int, c_int64, c_int64, P, c_double, P, P, c_int64, P]),
+    "mq_norm_update_from_stats": (c_int, [P, P, P, c_int64, c_double, c_double, c_double, P]),
     "mq_running_mean_update": (c_int, [P, P, c_int, c_int64, c_double, P, P]),
     "mq_norm_ws_bytes": (c_int64, [c_int64, c_int64]),
     "mq_col_mean": (c_int, [P, c_int, c_int64, c_int64, c_double, P, P, c_int64, P]),

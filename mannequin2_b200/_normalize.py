@@ -68,8 +68,7 @@ class RunningNormalize(object):
         self._d = int(np.prod(self._shape)) if self._shape else 1
         self._mean = RunningMean(self._shape, horizon=horizon)
         self._var = RunningMean(self._shape, horizon=horizon)
-        self._old = D.zeros(self._d, torch.float64)
-        self._tmp = D.zeros(self._d, torch.float64)
+        self._stats = D.zeros(2 * self._d, torch.float64)
         self._n_samples = 0
 
     # -- device-level API (used by the fused PPO / ES drivers) -------------------
@@ -80,26 +79,26 @@ class RunningNormalize(object):
         lib = D._lib.lib()
         d = self._d
         w = mqdist.world() if sharded else 1
-        wsb = lib.mq_norm_ws_bytes(rows, d)
+        # ONE pass over the data: s1 = mean(x - m), s2 = mean((x - m)^2) with m = the running mean before this update
+        # (csrc/mq_norm.cu); the mean and variance updates of _normalize.py:44-57 follow from them on the device
+        wsb = lib.mq_norm_stats_ws_bytes(rows, d)
         ws = D.workspace("norm", wsb)
-        D.call("mq_col_mean", D.ptr(x), _code(x), rows, d, 1.0 / w, D.ptr(self._tmp), D.ptr(ws), wsb,
-               D.stream())
+        stats = self._stats
+        D.call("mq_norm_stats", D.ptr(x), _code(x), rows, d, D.ptr(self._mean.get_dev()), 1.0 / w, D.ptr(stats),
+               D.ptr(ws), wsb, D.stream())
         if w > 1:
-            mqdist.allreduce_sum_(self._tmp)
-        self._mean.update(self._tmp, _old_out=self._old)          # one weight-1 update per batch
-        local_rows, rows = rows, rows * w
-        weight, scale = None, 1.0
+            mqdist.allreduce_sum_(stats)                                  # 2 x D doubles, once per update
+        coef_mean = self._mean._coef(1.0)                                 # one weight-1 update per batch
+        rows = rows * w
+        coef_var, scale = 0.0, 1.0
         if self._n_samples >= 1:
-            weight = 1.0
+            coef_var = self._var._coef(1.0)
         elif rows >= 2:
-            weight = (rows - 1.0) / rows                          # _normalize.py:50-55
+            weight = (rows - 1.0) / rows                                  # _normalize.py:50-55
             scale = 1.0 / weight
-        if weight is not None:
-            D.call("mq_norm_cov", D.ptr(x), _code(x), local_rows, d, D.ptr(self._old),
-                   D.ptr(self._mean.get_dev()), scale / w, D.ptr(self._tmp), D.ptr(ws), wsb, D.stream())
-            if w > 1:
-                mqdist.allreduce_sum_(self._tmp)
-            self._var.update(self._tmp, weight=weight)
+            coef_var = self._var._coef(weight)
+        D.call("mq_norm_update_from_stats", D.ptr(self._mean.get_dev()), D.ptr(self._var.get_dev()), D.ptr(stats), d,
+               coef_mean, coef_var, scale, D.stream())
         self._n_samples += rows
 
     def apply_dev(self, x, rows, out=None, fuse_tanh=False, out_dtype=torch.float64):

@@ -112,6 +112,147 @@ extern "C" int mq_norm_cov(const void *x, int x_dtype, int64_t rows, int64_t col
     return norm_reduce<float, true>(x, rows, cols, mean_old, mean_new, scale, out, ws, ws_bytes, stream, "mq_norm_cov");
 }
 
+// ---- one statistics pass -----------------------------------------------------------------------------------
+// RunningNormalize.update (_normalize.py:40-57) needs mean(x) and mean((x - mean_old)(x - mean_new)), where mean_new
+// depends on mean(x): two passes as written.  With the shift m = mean_old (known before the pass)
+//     s1 = mean(x - m),  s2 = mean((x - m)^2)
+//     mean(x) = m + s1,  mean((x - mean_old)(x - mean_new)) = s2 - (mean_new - m) s1
+// both come out of ONE pass, in fp64, without the cancellation of raw sum(x^2) (m tracks the data).
+// cols == 1: 128-bit loads, four independent fp64 accumulator pairs per thread, fixed-order two-stage reduction.
+template <typename XT>
+__global__ void __launch_bounds__(MQ_NT)
+norm_stats1_kernel(const XT *__restrict__ x, int64_t rows, const double *__restrict__ shift, double *__restrict__ partial) {
+    __shared__ double red[MQ_NT / 32];
+    const double m = shift[0];
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * MQ_NT + threadIdx.x, nth = (int64_t)gridDim.x * MQ_NT;
+    if (sizeof(XT) == 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        const int64_t nq = rows >> 2;
+        int64_t q = tid;
+        for (; q + nth < nq; q += 2 * nth) {                 // two independent 16-byte loads in flight
+            const float4 u = x4[q], w = x4[q + nth];
+            const double u0 = (double)u.x - m, u1 = (double)u.y - m, u2 = (double)u.z - m, u3 = (double)u.w - m;
+            const double w0 = (double)w.x - m, w1 = (double)w.y - m, w2 = (double)w.z - m, w3 = (double)w.w - m;
+            a0 += (u0 + u1) + (u2 + u3);
+            a1 += (w0 + w1) + (w2 + w3);
+            b0 = fma(u0, u0, fma(u1, u1, fma(u2, u2, fma(u3, u3, b0))));
+            b1 = fma(w0, w0, fma(w1, w1, fma(w2, w2, fma(w3, w3, b1))));
+        }
+        for (; q < nq; q += nth) {
+            const float4 u = x4[q];
+            const double u0 = (double)u.x - m, u1 = (double)u.y - m, u2 = (double)u.z - m, u3 = (double)u.w - m;
+            a0 += (u0 + u1) + (u2 + u3);
+            b0 = fma(u0, u0, fma(u1, u1, fma(u2, u2, fma(u3, u3, b0))));
+        }
+        for (int64_t i = (nq << 2) + tid; i < rows; i += nth) {
+            const double v = (double)x[i] - m;
+            a0 += v; b0 = fma(v, v, b0);
+        }
+    } else {
+        for (int64_t i = tid; i < rows; i += nth) {
+            const double v = (double)x[i] - m;
+            a0 += v; b0 = fma(v, v, b0);
+        }
+    }
+    const double sa = mq_block_sum(a0 + a1, red);
+    const double sb = mq_block_sum(b0 + b1, red);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = sa; partial[gridDim.x + blockIdx.x] = sb; }
+}
+
+// cols > 1: one thread per column, blockIdx.y splits the rows; partial[stat][row block][col]
+template <typename XT>
+__global__ void __launch_bounds__(MQ_NT)
+norm_statsN_kernel(const XT *__restrict__ x, int64_t rows, int64_t cols, const double *__restrict__ shift,
+                   double *__restrict__ partial) {
+    const int64_t c = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per;
+    const int64_t r1 = r0 + per < rows ? r0 + per : rows;
+    const double m = shift[c];
+    double a = 0.0, b = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const double v = (double)x[r * cols + c] - m;
+        a += v; b = fma(v, v, b);
+    }
+    partial[(int64_t)blockIdx.y * cols + c] = a;
+    partial[((int64_t)gridDim.y + blockIdx.y) * cols + c] = b;
+}
+
+// out[stat * cols + c] = scale * sum over row blocks (fixed order)
+__global__ void __launch_bounds__(MQ_NT)
+norm_stats_finish_kernel(const double *__restrict__ partial, int nb, int64_t cols, double scale, double *__restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; e < 2 * cols; e += (int64_t)gridDim.x * MQ_NT) {
+        const int64_t stat = e / cols, c = e - stat * cols;
+        double s = 0.0;
+        for (int b = 0; b < nb; ++b) s += partial[(stat * nb + b) * cols + c];
+        out[e] = s * scale;
+    }
+}
+
+static int64_t norm_stats_blocks(int64_t rows, int64_t cols) {
+    if (cols > 1) return norm_blocks(rows);
+    int64_t nb = mq_ceil_div(rows, (int64_t)MQ_NT * 32);
+    const int64_t cap = (int64_t)mq_sm_count() * 8;
+    if (nb > cap) nb = cap;
+    return nb < 1 ? 1 : nb;
+}
+
+extern "C" int64_t mq_norm_stats_ws_bytes(int64_t rows, int64_t cols) {
+    return 2 * norm_stats_blocks(rows, cols) * (cols < 1 ? 1 : cols) * (int64_t)sizeof(double);
+}
+
+extern "C" int mq_norm_stats(const void *x, int x_dtype, int64_t rows, int64_t cols, const double *shift, double scale,
+                             double *out, void *ws, int64_t ws_bytes, void *stream) {
+    MQ_REQUIRE(x && shift && out && ws, MQ_ERR_INVALID, "mq_norm_stats: null pointer");
+    MQ_REQUIRE(rows >= 1 && cols >= 1, MQ_ERR_SHAPE, "mq_norm_stats: empty input");
+    MQ_REQUIRE(ws_bytes >= mq_norm_stats_ws_bytes(rows, cols), MQ_ERR_SHAPE, "mq_norm_stats: workspace too small");
+    const int nb = (int)norm_stats_blocks(rows, cols);
+    double *partial = (double *)ws;
+    if (cols == 1) {
+        if (x_dtype == MQ_F64) { auto k = norm_stats1_kernel<double>; MQ_LAUNCH(k, (unsigned)nb, MQ_NT, 0, stream, (const double *)x, rows, shift, partial); }
+        else { auto k = norm_stats1_kernel<float>; MQ_LAUNCH(k, (unsigned)nb, MQ_NT, 0, stream, (const float *)x, rows, shift, partial); }
+    } else {
+        const dim3 grid((unsigned)mq_ceil_div(cols, MQ_NT), (unsigned)nb);
+        if (x_dtype == MQ_F64) { auto k = norm_statsN_kernel<double>; MQ_LAUNCH(k, grid, MQ_NT, 0, stream, (const double *)x, rows, cols, shift, partial); }
+        else { auto k = norm_statsN_kernel<float>; MQ_LAUNCH(k, grid, MQ_NT, 0, stream, (const float *)x, rows, cols, shift, partial); }
+    }
+    MQ_LAUNCH(norm_stats_finish_kernel, (unsigned)mq_ceil_div(2 * cols, MQ_NT), MQ_NT, 0, stream, partial, nb, cols,
+              scale / (double)rows, out);
+    MQ_CHECK_LAUNCH("mq_norm_stats");
+    return MQ_OK;
+}
+
+// statistics -> running state (_normalize.py:9-25,44-57): stats = [s1[cols], s2[cols]] taken with shift = mean (the value
+// BEFORE this update).  mean += coef_mean * s1;  var += coef_var * (var_scale * (s2 - (mean_new - mean_old) s1) - var)
+// when coef_var > 0.
+__global__ void __launch_bounds__(MQ_NT)
+norm_update_kernel(double *__restrict__ mean, double *__restrict__ var, const double *__restrict__ stats, int64_t cols,
+                   double coef_mean, double coef_var, double var_scale) {
+    for (int64_t c = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; c < cols; c += (int64_t)gridDim.x * MQ_NT) {
+        const double s1 = stats[c], s2 = stats[cols + c];
+        const double mo = mean[c];
+        const double mn = mo + coef_mean * s1;          // RunningMean.update with the batch mean mo + s1
+        mean[c] = mn;
+        if (coef_var > 0.0) {
+            const double cov = s2 - (mn - mo) * s1;
+            const double v = var[c];
+            var[c] = v + coef_var * (cov * var_scale - v);
+        }
+    }
+}
+
+extern "C" int mq_norm_update_from_stats(double *mean, double *var, const double *stats, int64_t cols, double coef_mean,
+                                         double coef_var, double var_scale, void *stream) {
+    MQ_REQUIRE(mean && var && stats, MQ_ERR_INVALID, "mq_norm_update_from_stats: null pointer");
+    MQ_REQUIRE(cols >= 1, MQ_ERR_SHAPE, "mq_norm_update_from_stats: bad shape");
+    MQ_LAUNCH(norm_update_kernel, (unsigned)mq_ceil_div(cols, MQ_NT), MQ_NT, 0, stream, mean, var, stats, cols, coef_mean,
+              coef_var, var_scale);
+    MQ_CHECK_LAUNCH("mq_norm_update_from_stats");
+    return MQ_OK;
+}
+
 template <typename XT, typename OT>
 __global__ void __launch_bounds__(MQ_NT)
 norm_apply_kernel(const XT *__restrict__ x, int64_t n, int64_t cols, const double *__restrict__ mean,
@@ -125,6 +266,31 @@ norm_apply_kernel(const XT *__restrict__ x, int64_t n, int64_t cols, const doubl
     }
 }
 
+// scalar statistic (the advantage normaliser of ppo.py:24-25), float32 in and out: 128-bit loads / stores, the divisor
+// hoisted out of the loop (as a reciprocal: <= 1 ulp of fp64 before the cast to float32)
+__global__ void __launch_bounds__(MQ_NT)
+norm_apply1_f32_kernel(const float *__restrict__ x, int64_t n, const double *__restrict__ mean,
+                       const double *__restrict__ var, float *__restrict__ out, int fuse_tanh) {
+    const double m = mean[0];
+    const double inv = 1.0 / fmax(1e-8, sqrt(var[0]));
+    const int64_t tid = (int64_t)blockIdx.x * MQ_NT + threadIdx.x, nth = (int64_t)gridDim.x * MQ_NT;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    const int64_t nq = n >> 2;
+    for (int64_t q = tid; q < nq; q += nth) {
+        const float4 u = x4[q];
+        float4 r;
+        r.x = (float)(((double)u.x - m) * inv); r.y = (float)(((double)u.y - m) * inv);
+        r.z = (float)(((double)u.z - m) * inv); r.w = (float)(((double)u.w - m) * inv);
+        if (fuse_tanh) { r.x = tanhf(r.x); r.y = tanhf(r.y); r.z = tanhf(r.z); r.w = tanhf(r.w); }
+        o4[q] = r;
+    }
+    for (int64_t i = (nq << 2) + tid; i < n; i += nth) {
+        const float z = (float)(((double)x[i] - m) * inv);
+        out[i] = fuse_tanh ? tanhf(z) : z;
+    }
+}
+
 extern "C" int mq_norm_apply(const void *x, int x_dtype, int64_t rows, int64_t cols,
                              const double *mean, const double *var, void *out, int out_dtype,
                              int fuse_tanh, void *stream) {
@@ -132,6 +298,16 @@ extern "C" int mq_norm_apply(const void *x, int x_dtype, int64_t rows, int64_t c
     MQ_REQUIRE(rows >= 0 && cols >= 1, MQ_ERR_SHAPE, "mq_norm_apply: bad shape");
     const int64_t n = rows * cols;
     if (n == 0) return MQ_OK;
+    if (cols == 1 && x_dtype == MQ_F32 && out_dtype == MQ_F32 &&
+        (((uintptr_t)x | (uintptr_t)out) & 15) == 0) {
+        int64_t nb1 = mq_ceil_div(n, (int64_t)MQ_NT * 4);
+        const int64_t cap1 = (int64_t)mq_sm_count() * 16;
+        if (nb1 > cap1) nb1 = cap1;
+        MQ_LAUNCH(norm_apply1_f32_kernel, (unsigned)nb1, MQ_NT, 0, stream, (const float *)x, n, mean, var, (float *)out,
+                  fuse_tanh);
+        MQ_CHECK_LAUNCH("mq_norm_apply");
+        return MQ_OK;
+    }
     int64_t nb = mq_ceil_div(n, MQ_NT);
     const int64_t cap = (int64_t)mq_sm_count() * 16;
     if (nb > cap) nb = cap;

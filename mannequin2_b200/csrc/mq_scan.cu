@@ -158,9 +158,37 @@ struct GaeStage {
     float g, gl;
     static constexpr int kSmemBytes = (SCAN_PAD(SCAN_CHUNK) + 1) * 4 * 2 + SCAN_CHUNK + 64;
     // memory rows [lo, lo+cnt) -> shared memory; val also at lo+cnt (bootstrap / next state)
+    int vec;                     // all five arrays are 16-byte aligned: 128-bit loads / stores on the aligned middle
     __device__ __forceinline__ void stage(unsigned char *sm, int64_t lo, int cnt) const {
         float *sr = reinterpret_cast<float *>(sm), *sv = sr + SCAN_PAD(SCAN_CHUNK) + 1;
         uint8_t *sd = reinterpret_cast<uint8_t *>(sv + SCAN_PAD(SCAN_CHUNK) + 1 + 8);
+        if (vec) {
+            // rows lo + head, lo + head + 4, ... start 16-byte groups in every array (same misalignment everywhere)
+            int head = (int)((4 - (lo & 3)) & 3);
+            if (head > cnt) head = cnt;
+            const int nq = (cnt - head) >> 2, nqv = (cnt + 1 - head) >> 2;
+            const float4 *r4 = reinterpret_cast<const float4 *>(rew + lo + head);
+            const float4 *v4 = reinterpret_cast<const float4 *>(val + lo + head);
+            const uchar4 *d4 = reinterpret_cast<const uchar4 *>(done + lo + head);
+            for (int q = threadIdx.x; q < nq; q += MQ_NT) {
+                const float4 a = r4[q];
+                const uchar4 dd = d4[q];
+                const int i = head + 4 * q;
+                sr[SCAN_PAD(i)] = a.x; sr[SCAN_PAD(i + 1)] = a.y; sr[SCAN_PAD(i + 2)] = a.z; sr[SCAN_PAD(i + 3)] = a.w;
+                sd[i] = dd.x; sd[i + 1] = dd.y; sd[i + 2] = dd.z; sd[i + 3] = dd.w;
+            }
+            for (int q = threadIdx.x; q < nqv; q += MQ_NT) {
+                const float4 a = v4[q];
+                const int i = head + 4 * q;
+                sv[SCAN_PAD(i)] = a.x; sv[SCAN_PAD(i + 1)] = a.y; sv[SCAN_PAD(i + 2)] = a.z; sv[SCAN_PAD(i + 3)] = a.w;
+            }
+            // the unaligned ends (at most 3 + 3 rows; 4 + 4 for val)
+            for (int i = threadIdx.x; i < cnt; i += MQ_NT)
+                if (i < head || i >= head + 4 * nq) { sr[SCAN_PAD(i)] = rew[lo + i]; sd[i] = done[lo + i]; }
+            for (int i = threadIdx.x; i <= cnt; i += MQ_NT)
+                if (i < head || i >= head + 4 * nqv) sv[SCAN_PAD(i)] = val[lo + i];
+            return;
+        }
         for (int i = threadIdx.x; i < cnt; i += MQ_NT) { sr[SCAN_PAD(i)] = rew[lo + i]; sd[i] = done[lo + i]; }
         for (int i = threadIdx.x; i <= cnt; i += MQ_NT) sv[SCAN_PAD(i)] = val[lo + i];
     }
@@ -178,6 +206,26 @@ struct GaeStage {
     }
     __device__ __forceinline__ void flush(const unsigned char *sm, int64_t lo, int cnt) const {
         const float *sr = reinterpret_cast<const float *>(sm), *sv = sr + SCAN_PAD(SCAN_CHUNK) + 1;
+        if (vec) {
+            int head = (int)((4 - (lo & 3)) & 3);
+            if (head > cnt) head = cnt;
+            const int nq = (cnt - head) >> 2;
+            float4 *a4 = reinterpret_cast<float4 *>(adv + lo + head), *t4 = reinterpret_cast<float4 *>(ret + lo + head);
+            for (int q = threadIdx.x; q < nq; q += MQ_NT) {
+                const int i = head + 4 * q;
+                const float y0 = sr[SCAN_PAD(i)], y1 = sr[SCAN_PAD(i + 1)], y2 = sr[SCAN_PAD(i + 2)], y3 = sr[SCAN_PAD(i + 3)];
+                a4[q] = make_float4(y0, y1, y2, y3);
+                t4[q] = make_float4(y0 + sv[SCAN_PAD(i)], y1 + sv[SCAN_PAD(i + 1)], y2 + sv[SCAN_PAD(i + 2)],
+                                    y3 + sv[SCAN_PAD(i + 3)]);
+            }
+            for (int i = threadIdx.x; i < cnt; i += MQ_NT)
+                if (i < head || i >= head + 4 * nq) {
+                    const float y = sr[SCAN_PAD(i)];
+                    adv[lo + i] = y;
+                    ret[lo + i] = y + sv[SCAN_PAD(i)];
+                }
+            return;
+        }
         for (int i = threadIdx.x; i < cnt; i += MQ_NT) {
             const float y = sr[SCAN_PAD(i)];
             adv[lo + i] = y;
@@ -212,6 +260,7 @@ struct DiscStage {
 
 // per-chunk descriptor: status 0 = empty, 1 = map of the chunk alone, 2 = value leaving the chunk
 template <typename T> struct ScanTile { T a, b, y; int status; int pad; };
+template <> struct __align__(16) ScanTile<float> { float a, b, y; int status; };
 
 __device__ __forceinline__ int scan_ld_acquire(const int *p) {
     int v;
@@ -220,6 +269,69 @@ __device__ __forceinline__ int scan_ld_acquire(const int *p) {
 }
 __device__ __forceinline__ void scan_st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// A float descriptor {a, b, y, status} is ONE aligned 16-byte word: it is published with a single 128-bit store and read
+// with a single 128-bit load, so data and status travel together and no fence / release-acquire pair is needed
+// (the double descriptor of `discounted` is 32 bytes and keeps the release / acquire protocol).
+__device__ __forceinline__ void scan_tile_store(ScanTile<float> *t, float a, float b, float y, int status) {
+    asm volatile("st.volatile.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(t), "r"(__float_as_int(a)), "r"(__float_as_int(b)),
+                 "r"(__float_as_int(y)), "r"(status) : "memory");
+}
+__device__ __forceinline__ void scan_tile_load(const ScanTile<float> *t, float &a, float &b, float &y, int &status) {
+    int ia, ib, iy;
+    asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ia), "=r"(ib), "=r"(iy), "=r"(status) : "l"(t) : "memory");
+    a = __int_as_float(ia); b = __int_as_float(ib); y = __int_as_float(iy);
+}
+__device__ __forceinline__ void scan_tile_store(ScanTile<double> *t, double a, double b, double y, int status) {
+    t->a = a; t->b = b; t->y = y;
+    __threadfence();
+    scan_st_release(&t->status, status);
+}
+__device__ __forceinline__ void scan_tile_load(const ScanTile<double> *t, double &a, double &b, double &y, int &status) {
+    status = scan_ld_acquire(&t->status);
+    a = t->a; b = t->b; y = t->y;
+}
+
+// Warp 0 of the block that owns chunk c: publish the chunk's map (its leaving value at once if the chunk contains an
+// episode end), look back over the predecessors and return the value ENTERING the chunk (every lane returns it).
+template <typename T>
+__device__ __forceinline__ T scan_publish_and_lookback(ScanTile<T> *__restrict__ tiles, int64_t c, const Lin<T> &total) {
+
+    const int lane = threadIdx.x;
+    // a chunk that contains an episode end (a = 0) leaves the same value whatever enters it: publish that value
+    // at once so that later chunks never wait for this chunk's own look-back
+    const bool closed = total.a == (T)0;
+    if (lane == 0) scan_tile_store(&tiles[c], total.a, total.b, total.b, closed ? 2 : 1);
+    // acc = composition of the chunks already folded in (those nearest to c); identity at first
+    Lin<T> acc; acc.a = (T)1; acc.b = (T)0;
+    bool done = false;
+    int64_t base = c - 1;                          // nearest predecessor not yet folded in
+    while (!done) {
+        const int64_t q = base - lane;             // lane 0 = nearest
+        T qa = (T)0, qb = (T)0;                    // before chunk 0 the recurrence is 0: a terminator
+        if (q >= 0) {
+            int st;
+            T ta, tb, ty;
+            do { scan_tile_load(&tiles[q], ta, tb, ty, st); } while (st == 0);
+            if (st == 2) qb = ty;                  // value LEAVING chunk q: ignores what entered it
+            else { qa = ta; qb = tb; }
+        }
+        const unsigned term = __ballot_sync(0xffffffffu, qa == (T)0);
+        const int stop = term ? __ffs(term) - 1 : 31;
+        Lin<T> win; win.a = (T)1; win.b = (T)0;    // chunks base-stop .. base, oldest applied first
+        for (int l = stop; l >= 0; --l) {
+            Lin<T> e;
+            e.a = __shfl_sync(0xffffffffu, qa, l);
+            e.b = __shfl_sync(0xffffffffu, qb, l);
+            win = lin_then(win, e);
+        }
+        acc = lin_then(win, acc);
+        done = term != 0u;
+        base -= 32;
+    }
+    if (lane == 0 && !closed) scan_tile_store(&tiles[c], total.a, total.b, total.b + total.a * acc.b, 2);
+    return acc.b;
 }
 
 template <typename T, typename E>
@@ -252,49 +364,8 @@ scan_lookback_kernel(E el, int64_t n, ScanTile<T> *__restrict__ tiles, unsigned 
     lin_block_scan(local, excl, total, warp_tot);
     // ---- publish this chunk's map, look back for the value entering it (warp 0) --------------------
     if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        // a chunk that contains an episode end (a = 0) leaves the same value whatever enters it: publish that value
-        // at once so that later chunks never wait for this chunk's own look-back
-        const bool closed = total.a == (T)0;
-        if (lane == 0) {
-            tiles[c].a = total.a; tiles[c].b = total.b; tiles[c].y = total.b;
-            __threadfence();
-            scan_st_release(&tiles[c].status, closed ? 2 : 1);
-        }
-        // acc = composition of the chunks already folded in (those nearest to c); identity at first
-        Lin<T> acc; acc.a = (T)1; acc.b = (T)0;
-        bool done = false;
-        int64_t base = c - 1;                          // nearest predecessor not yet folded in
-        while (!done) {
-            const int64_t q = base - lane;             // lane 0 = nearest
-            T qa = (T)0, qb = (T)0;                    // before chunk 0 the recurrence is 0: a terminator
-            if (q >= 0) {
-                int st;
-                do { st = scan_ld_acquire(&tiles[q].status); } while (st == 0);
-                if (st == 2) qb = tiles[q].y;          // value LEAVING chunk q: ignores what entered it
-                else { qa = tiles[q].a; qb = tiles[q].b; }
-            }
-            const unsigned term = __ballot_sync(0xffffffffu, qa == (T)0);
-            const int stop = term ? __ffs(term) - 1 : 31;
-            Lin<T> win; win.a = (T)1; win.b = (T)0;    // chunks base-stop .. base, oldest applied first
-            for (int l = stop; l >= 0; --l) {
-                Lin<T> e;
-                e.a = __shfl_sync(0xffffffffu, qa, l);
-                e.b = __shfl_sync(0xffffffffu, qb, l);
-                win = lin_then(win, e);
-            }
-            acc = lin_then(win, acc);
-            done = term != 0u;
-            base -= 32;
-        }
-        if (lane == 0) {
-            s_yin = acc.b;
-            if (!closed) {
-                tiles[c].y = total.b + total.a * acc.b;
-                __threadfence();
-                scan_st_release(&tiles[c].status, 2);
-            }
-        }
+        const T yin = scan_publish_and_lookback<T>(tiles, c, total);
+        if (threadIdx.x == 0) s_yin = yin;
     }
     __syncthreads();
     T y = excl.b + excl.a * s_yin;
@@ -311,8 +382,73 @@ scan_lookback_kernel(E el, int64_t n, ScanTile<T> *__restrict__ tiles, unsigned 
     el.flush(sm, lo, cnt);
 }
 
+// GAE with the chunk in REGISTERS (no shared-memory staging): thread t owns the 8 consecutive rows hi - 8t - 7 .. hi - 8t.
+// ncu on the staged kernel above showed it bound by instruction issue (76 % issue-active, 133 thread instructions per
+// transition: padded shared-memory indices, four LDS per element and every element evaluated twice), not by HBM; here an
+// element costs ~20.  Requires 16-byte aligned arrays and n % 8 == 0 (rows of a thread start 128-bit groups); any other
+// call takes the staged kernel.
+__global__ void __launch_bounds__(MQ_NT, 6)
+gae_lookback_kernel(GaeStage el, int64_t n, ScanTile<float> *__restrict__ tiles) {
+    __shared__ Lin<float> warp_tot[MQ_NT / 32];
+    __shared__ float s_yin;
+    const int64_t c = blockIdx.x;
+    const int64_t hi = n - 1 - c * SCAN_CHUNK;
+    const int64_t r1 = hi - (int64_t)threadIdx.x * SCAN_ITEMS, r0 = r1 - (SCAN_ITEMS - 1);   // this thread's rows
+    float rw[SCAN_ITEMS], vl[SCAN_ITEMS + 1];
+    unsigned dn = 0;                                   // bit k: episode ends at row r0 + k
+    if (r0 >= 0) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(el.rew + r0), a1 = *reinterpret_cast<const float4 *>(el.rew + r0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(el.val + r0), b1 = *reinterpret_cast<const float4 *>(el.val + r0 + 4);
+        const uint2 d8 = *reinterpret_cast<const uint2 *>(el.done + r0);
+        vl[8] = el.val[r1 + 1];
+        rw[0] = a0.x; rw[1] = a0.y; rw[2] = a0.z; rw[3] = a0.w; rw[4] = a1.x; rw[5] = a1.y; rw[6] = a1.z; rw[7] = a1.w;
+        vl[0] = b0.x; vl[1] = b0.y; vl[2] = b0.z; vl[3] = b0.w; vl[4] = b1.x; vl[5] = b1.y; vl[6] = b1.z; vl[7] = b1.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dn |= ((d8.x >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+            dn |= ((d8.y >> (8 * k)) & 0xFFu) ? (1u << (4 + k)) : 0u;
+        }
+    } else {                                           // rows before the start of the data: identity maps
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { rw[k] = 0.0f; vl[k] = 0.0f; }
+        vl[8] = 0.0f;
+    }
+    const bool live = r0 >= 0;
+    // maps of the 8 rows, newest row first (reversed positions ascend as rows descend); b_k kept for the output pass
+    float eb[SCAN_ITEMS];
+    Lin<float> local; local.a = 1.0f; local.b = 0.0f;
+#pragma unroll
+    for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+        Lin<float> e;
+        if (dn & (1u << k)) { e.a = 0.0f; e.b = rw[k] - vl[k]; }
+        else { e.a = el.gl; e.b = rw[k] + el.g * vl[k + 1] - vl[k]; }
+        eb[k] = e.b;
+        if (live) local = lin_then(local, e);
+    }
+    Lin<float> excl, total;
+    lin_block_scan(local, excl, total, warp_tot);
+    if (threadIdx.x < 32) {
+        const float yin = scan_publish_and_lookback<float>(tiles, c, total);
+        if (threadIdx.x == 0) s_yin = yin;
+    }
+    __syncthreads();
+    if (!live) return;
+    float y = excl.b + excl.a * s_yin;
+    float av[SCAN_ITEMS], rt[SCAN_ITEMS];
+#pragma unroll
+    for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+        y = eb[k] + ((dn & (1u << k)) ? 0.0f : el.gl) * y;
+        av[k] = y;
+        rt[k] = y + vl[k];
+    }
+    *reinterpret_cast<float4 *>(el.adv + r0) = make_float4(av[0], av[1], av[2], av[3]);
+    *reinterpret_cast<float4 *>(el.adv + r0 + 4) = make_float4(av[4], av[5], av[6], av[7]);
+    *reinterpret_cast<float4 *>(el.ret + r0) = make_float4(rt[0], rt[1], rt[2], rt[3]);
+    *reinterpret_cast<float4 *>(el.ret + r0 + 4) = make_float4(rt[4], rt[5], rt[6], rt[7]);
+}
+
 #else
-struct GaeStage { const float *rew, *val; const uint8_t *done; float *adv, *ret; float g, gl; };
+struct GaeStage { const float *rew, *val; const uint8_t *done; float *adv, *ret; float g, gl; int vec; };
 struct DiscStage { const double *in; double *out; double keep, step; };
 #endif
 
@@ -322,6 +458,13 @@ extern "C" int64_t mq_scan_ws_bytes(int64_t n) {
 }
 
 #ifndef MQ_EMU
+static bool scan_try_register_kernel(const GaeStage &st, int64_t n, ScanTile<float> *tiles, int64_t nb, void *stream) {
+    if (!st.vec || (n & 7) != 0) return false;
+    MQ_LAUNCH(gae_lookback_kernel, (unsigned)nb, MQ_NT, 0, stream, st, n, tiles);
+    return true;
+}
+static bool scan_try_register_kernel(const DiscStage &, int64_t, ScanTile<double> *, int64_t, void *) { return false; }
+
 template <typename T, typename E, typename S>
 static int scan_run(E el, S st, int64_t n, void *ws, int64_t ws_bytes, void *stream, const char *what) {
     if (n == 0) return MQ_OK;
@@ -336,8 +479,10 @@ static int scan_run(E el, S st, int64_t n, void *ws, int64_t ws_bytes, void *str
         if (e != cudaSuccess) { mq_set_error("%s: %s", what, cudaGetErrorString(e)); return MQ_ERR_CUDA; }
         unsigned int *ticket = (unsigned int *)ws;
         ScanTile<T> *tiles = (ScanTile<T> *)((char *)ws + 64);
-        auto k = scan_lookback_kernel<T, S>;
-        MQ_LAUNCH(k, (unsigned)nb, MQ_NT, S::kSmemBytes, stream, st, n, tiles, ticket);
+        if (!scan_try_register_kernel(st, n, tiles, nb, stream)) {
+            auto k = scan_lookback_kernel<T, S>;
+            MQ_LAUNCH(k, (unsigned)nb, MQ_NT, S::kSmemBytes, stream, st, n, tiles, ticket);
+        }
     }
     MQ_CHECK_LAUNCH(what);
     return MQ_OK;
@@ -377,6 +522,7 @@ extern "C" int mq_gae(const float *rew, const float *value, const uint8_t *done,
     el.gl = (float)(gam * lam);           // gae.py:56: python-float product, then fp32
     GaeStage st;
     st.rew = rew; st.val = value; st.done = done; st.adv = adv; st.ret = ret; st.g = el.g; st.gl = el.gl;
+    st.vec = (((uintptr_t)rew | (uintptr_t)value | (uintptr_t)done | (uintptr_t)adv | (uintptr_t)ret) & 15) == 0;
     return scan_run<float, GaeElems, GaeStage>(el, st, n, ws, ws_bytes, stream, "mq_gae");
 }
 

@@ -141,6 +141,36 @@ def case_norm(B):
         ok(B, lib.mq_norm_apply(B.ptr(hx), code, rows, cols, B.ptr(mean), B.ptr(hvar), B.ptr(out64),
                                 L.MQ_F64, 0, B.stream))
         assert np.allclose(B.down(out64), (x.astype(np.float64) - hmean) / np.sqrt(var), rtol=1e-13, atol=1e-13)
+    # one statistics pass + update on the device against RunningNormalize itself (oracle = the reference's code path)
+    for cols, dt, horizon, sizes in ((1, np.float32, 2, (1, 4099, 70001, 3)), (1, np.float64, None, (2, 513)),
+                                     (11, np.float32, 10, (1, 1, 300)), (5, np.float64, 3, (64, 9))):
+        code = L.MQ_F64 if dt == np.float64 else L.MQ_F32
+        norm = O.RunningNormalizeO(shape=() if cols == 1 else (cols,), horizon=horizon)
+        mean, var, stats = B.zeros(cols, np.float64), B.zeros(cols, np.float64), B.zeros(2 * cols, np.float64)
+        tw_m = tw_v = 0.0
+        n_seen = 0
+        decay = 1.0 if horizon is None else 1.0 - 1.0 / horizon
+        for rows in sizes:
+            x = (rs.randn(rows, cols) * 3 + 10).astype(dt)
+            norm.update(x if cols > 1 else x.reshape(-1))
+            wsb = lib.mq_norm_stats_ws_bytes(rows, cols)
+            hx, ws = B.up(x), B.zeros(wsb, np.uint8)
+            ok(B, lib.mq_norm_stats(B.ptr(hx), code, rows, cols, B.ptr(mean), 1.0, B.ptr(stats), B.ptr(ws), wsb, B.stream))
+            tw_m = tw_m * decay + 1.0
+            coef_v, scale = 0.0, 1.0
+            if n_seen >= 1:
+                tw_v = tw_v * decay + 1.0
+                coef_v = 1.0 / tw_v
+            elif rows >= 2:
+                w = (rows - 1.0) / rows
+                tw_v = tw_v * decay ** w + w
+                coef_v, scale = w / tw_v, 1.0 / w
+            ok(B, lib.mq_norm_update_from_stats(B.ptr(mean), B.ptr(var), B.ptr(stats), cols, 1.0 / tw_m, coef_v, scale,
+                                                B.stream))
+            n_seen += rows
+            assert np.allclose(B.down(mean), np.reshape(norm.get_mean(), -1), rtol=1e-12, atol=1e-12), "stats mean"
+            if n_seen >= 2:
+                assert np.allclose(B.down(var), np.reshape(norm.get_var(), -1), rtol=1e-10, atol=1e-12), "stats var"
     mean0, x = rs.randn(7), rs.randn(7)
     mean, hx, old = B.up(mean0.copy()), B.up(x), B.zeros(7, np.float64)
     ok(B, lib.mq_running_mean_update(B.ptr(mean), B.ptr(hx), L.MQ_F64, 7, 0.3, B.ptr(old), B.stream))
