@@ -800,7 +800,13 @@ def kernel_sweep(peaks):
     # 8 B read (one statistics pass + the apply pass) + 4 B write per element
     out["normalize_update_apply_64Mi"] = dict(bytes_per_elem=12, ms=ms, gbs=12.0 * n / ms / 1e6,
                                               frac=12.0 * n / ms / 1e6 / peaks["hbm"])
-    del r, vv, d, adv, ret, o
+    # activations (mannequin/backprop.py:53-60): tanh forward 8 B/element, backward 12 B/element
+    ya, ga = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    ms = timeit(lambda: D.call("mq_act_forward", D.ptr(r), D.ptr(ya), n, L.ACT_TANH, 0.0, D.stream()))
+    out["tanh_forward_64Mi"] = dict(bytes_per_elem=8, ms=ms, gbs=8.0 * n / ms / 1e6, frac=8.0 * n / ms / 1e6 / peaks["hbm"])
+    ms = timeit(lambda: D.call("mq_act_backward", D.ptr(ya), D.ptr(r), D.ptr(ga), n, L.ACT_TANH, 0.0, D.stream()))
+    out["tanh_backward_64Mi"] = dict(bytes_per_elem=12, ms=ms, gbs=12.0 * n / ms / 1e6, frac=12.0 * n / ms / 1e6 / peaks["hbm"])
+    del r, vv, d, adv, ret, o, ya, ga
     # wide Affine layers (BASELINE configs[4]: VAE 784-400-...-784 at batch 4096): y = x W, dx = g W^T, dW = x^T g through
     # mq_gemm -- tcgen05 kernel (three bf16 planes per operand, fp32 parity) vs the FFMA kernel it replaces
     bsz, kin, nout = 4096, 784, 400

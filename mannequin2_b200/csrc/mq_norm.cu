@@ -63,14 +63,17 @@ norm_reduceN_kernel(const XT *__restrict__ x, int64_t rows, int64_t cols,
     partial[(int64_t)blockIdx.y * cols + c] = acc;
 }
 
+// one CTA per output: thread t adds row blocks t, t + 256, ... then the CTA adds its 256 sums, all in a fixed order
+// (one thread walking ~1,000 partials with dependent loads took 34 us: as long as the pass over the data itself)
 __global__ void __launch_bounds__(MQ_NT)
 norm_finish_kernel(const double *__restrict__ partial, int nb, int64_t cols, double scale,
                    double *__restrict__ out) {
-    for (int64_t c = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; c < cols; c += (int64_t)gridDim.x * MQ_NT) {
-        double s = 0.0;
-        for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * cols + c];
-        out[c] = s * scale;
-    }
+    __shared__ double red[MQ_NT / 32];
+    const int64_t c = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nb; b += MQ_NT) s += partial[(int64_t)b * cols + c];
+    s = mq_block_sum(s, red);
+    if (threadIdx.x == 0) out[c] = s * scale;
 }
 
 template <typename XT, bool COV>
@@ -90,7 +93,7 @@ static int norm_reduce(const void *x, int64_t rows, int64_t cols, const double *
         MQ_LAUNCH(kfn, dim3((unsigned)mq_ceil_div(cols, MQ_NT), (unsigned)nb), MQ_NT, 0, stream,
                   (const XT *)x, rows, cols, mo, mn, partial);
     }
-    MQ_LAUNCH(norm_finish_kernel, (unsigned)mq_ceil_div(cols, MQ_NT), MQ_NT, 0, stream, partial, nb,
+    MQ_LAUNCH(norm_finish_kernel, (unsigned)cols, MQ_NT, 0, stream, partial, nb,
               cols, scale / (double)rows, out);
     MQ_CHECK_LAUNCH(what);
     return MQ_OK;
@@ -183,12 +186,13 @@ norm_statsN_kernel(const XT *__restrict__ x, int64_t rows, int64_t cols, const d
 // out[stat * cols + c] = scale * sum over row blocks (fixed order)
 __global__ void __launch_bounds__(MQ_NT)
 norm_stats_finish_kernel(const double *__restrict__ partial, int nb, int64_t cols, double scale, double *__restrict__ out) {
-    for (int64_t e = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; e < 2 * cols; e += (int64_t)gridDim.x * MQ_NT) {
-        const int64_t stat = e / cols, c = e - stat * cols;
-        double s = 0.0;
-        for (int b = 0; b < nb; ++b) s += partial[(stat * nb + b) * cols + c];
-        out[e] = s * scale;
-    }
+    __shared__ double red[MQ_NT / 32];
+    const int64_t e = blockIdx.x;                          // one CTA per (statistic, column)
+    const int64_t stat = e / cols, c = e - stat * cols;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nb; b += MQ_NT) s += partial[(stat * nb + b) * cols + c];
+    s = mq_block_sum(s, red);
+    if (threadIdx.x == 0) out[e] = s * scale;
 }
 
 static int64_t norm_stats_blocks(int64_t rows, int64_t cols) {
@@ -218,7 +222,7 @@ extern "C" int mq_norm_stats(const void *x, int x_dtype, int64_t rows, int64_t c
         if (x_dtype == MQ_F64) { auto k = norm_statsN_kernel<double>; MQ_LAUNCH(k, grid, MQ_NT, 0, stream, (const double *)x, rows, cols, shift, partial); }
         else { auto k = norm_statsN_kernel<float>; MQ_LAUNCH(k, grid, MQ_NT, 0, stream, (const float *)x, rows, cols, shift, partial); }
     }
-    MQ_LAUNCH(norm_stats_finish_kernel, (unsigned)mq_ceil_div(2 * cols, MQ_NT), MQ_NT, 0, stream, partial, nb, cols,
+    MQ_LAUNCH(norm_stats_finish_kernel, (unsigned)(2 * cols), MQ_NT, 0, stream, partial, nb, cols,
               scale / (double)rows, out);
     MQ_CHECK_LAUNCH("mq_norm_stats");
     return MQ_OK;

@@ -163,9 +163,36 @@ act_bwd_kernel(const float *__restrict__ y, const float *__restrict__ g, float *
     EW_LOOP(i, n) out[i] = mq_act_grad(y[i], g[i], act, leak);
 }
 
+// 128-bit versions (16-byte aligned arrays, n % 4 == 0): the elementwise kernels are pure HBM streams
+__global__ void __launch_bounds__(MQ_NT)
+act_fwd4_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int64_t n4, int act, float leak) {
+    EW_LOOP(i, n4) {
+        const float4 v = x[i];
+        y[i] = make_float4(mq_act_apply(v.x, act, leak), mq_act_apply(v.y, act, leak), mq_act_apply(v.z, act, leak),
+                           mq_act_apply(v.w, act, leak));
+    }
+}
+__global__ void __launch_bounds__(MQ_NT)
+act_bwd4_kernel(const float4 *__restrict__ y, const float4 *__restrict__ g, float4 *__restrict__ out, int64_t n4, int act,
+                float leak) {
+    EW_LOOP(i, n4) {
+        const float4 v = y[i], w = g[i];
+        out[i] = make_float4(mq_act_grad(v.x, w.x, act, leak), mq_act_grad(v.y, w.y, act, leak),
+                             mq_act_grad(v.z, w.z, act, leak), mq_act_grad(v.w, w.w, act, leak));
+    }
+}
+static inline bool ew_vec4(int64_t n, const void *a, const void *b, const void *c) {
+    return (n & 3) == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
 extern "C" int mq_act_forward(const float *x, float *y, int64_t n, int act, float leak, void *stream) {
     MQ_REQUIRE(act >= 0 && act <= 2, MQ_ERR_INVALID, "mq_act_forward: unknown activation %d", act);
     if (n <= 0) return MQ_OK;
+    if (ew_vec4(n, x, y, nullptr)) {
+        MQ_LAUNCH(act_fwd4_kernel, ew_blocks(n / 4), MQ_NT, 0, stream, (const float4 *)x, (float4 *)y, n / 4, act, leak);
+        MQ_CHECK_LAUNCH("mq_act_forward");
+        return MQ_OK;
+    }
     MQ_LAUNCH(act_fwd_kernel, ew_blocks(n), MQ_NT, 0, stream, x, y, n, act, leak);
     MQ_CHECK_LAUNCH("mq_act_forward");
     return MQ_OK;
@@ -174,6 +201,12 @@ extern "C" int mq_act_backward(const float *y, const float *g, float *out, int64
                                float leak, void *stream) {
     MQ_REQUIRE(act >= 0 && act <= 2, MQ_ERR_INVALID, "mq_act_backward: unknown activation %d", act);
     if (n <= 0) return MQ_OK;
+    if (ew_vec4(n, y, g, out)) {
+        MQ_LAUNCH(act_bwd4_kernel, ew_blocks(n / 4), MQ_NT, 0, stream, (const float4 *)y, (const float4 *)g, (float4 *)out,
+                  n / 4, act, leak);
+        MQ_CHECK_LAUNCH("mq_act_backward");
+        return MQ_OK;
+    }
     MQ_LAUNCH(act_bwd_kernel, ew_blocks(n), MQ_NT, 0, stream, y, g, out, n, act, leak);
     MQ_CHECK_LAUNCH("mq_act_backward");
     return MQ_OK;

@@ -570,6 +570,12 @@ def case_ops(B):
         ok(B, lib.mq_act_backward(B.ptr(y), B.ptr(hg), B.ptr(gy), 350, act, leak, B.stream))
         wantg = g * (1 - np.tanh(x) ** 2) if act == L.ACT_TANH else np.where(x < 0, g * np.float32(leak), g)
         close(B.down(gy), wantg, what="act bwd")
+    xv, gv = rs.randn(64, 8).astype(np.float32), rs.randn(64, 8).astype(np.float32)      # n % 4 == 0: 128-bit kernels
+    hxv, hgv, yv, ov = B.up(xv), B.up(gv), B.zeros((64, 8), np.float32), B.zeros((64, 8), np.float32)
+    ok(B, lib.mq_act_forward(B.ptr(hxv), B.ptr(yv), 512, L.ACT_TANH, 0.0, B.stream))
+    close(B.down(yv), np.tanh(xv), what="act fwd x4")
+    ok(B, lib.mq_act_backward(B.ptr(yv), B.ptr(hgv), B.ptr(ov), 512, L.ACT_TANH, 0.0, B.stream))
+    close(B.down(ov), gv * (1 - np.tanh(xv) ** 2), what="act bwd x4")
     ok(B, lib.mq_clip_forward(B.ptr(hx), B.ptr(y), 350, -0.5, 0.5, B.stream))
     assert np.array_equal(B.down(y), np.clip(x, -0.5, 0.5))
     ok(B, lib.mq_clip_backward(B.ptr(hx), B.ptr(hg), B.ptr(y), 350, -0.5, 0.5, B.stream))
