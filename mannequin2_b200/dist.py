@@ -42,9 +42,14 @@ def allgather_concat(t, group=None):
     """Concatenate equally sized 1-D shards in rank order."""
     if world() == 1:
         return t
-    out = [torch.empty_like(t) for _ in range(world())]
-    dist.all_gather(out, t, group=group)
-    return torch.cat(out)
+    out = torch.empty(world() * t.numel(), dtype=t.dtype, device=t.device)
+    try:
+        dist.all_gather_into_tensor(out, t.contiguous().reshape(-1), group=group)      # one call, no concatenation
+        return out
+    except (RuntimeError, NotImplementedError):                                        # backend without the fused form
+        parts = [torch.empty_like(t) for _ in range(world())]
+        dist.all_gather(parts, t, group=group)
+        return torch.cat(parts)
 
 
 def shard_range(n_units, r=None, w=None):
