@@ -244,7 +244,10 @@ typedef struct mq_peer {
     uint32_t *const *flag_bufs;
     int64_t buf_stride;
     uint32_t step;
-    int32_t pull;                /* 0: push (remote STORES into every peer's slot [rank], local reads; fastest up to 4 GPUs);
+    int32_t pull;                /* 2: low-latency push: (value, step) as ONE 8-byte word per parameter into every peer's slot [rank],
+                                    the receiver polls the words in its own memory (no flags, no fences); grad_bufs are then
+                                    uint64[2][world][buf_stride];
+                                    0: push (remote STORES into every peer's slot [rank], local reads; fastest up to 4 GPUs);
                                     1: pull (local store of the own slot, remote LOADS of every peer's: one release fence
                                     towards local memory instead of one per peer; faster on 8 GPUs) */
 } mq_peer_t;

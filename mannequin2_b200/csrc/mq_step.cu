@@ -7,14 +7,15 @@
 // rank holds the same parameters and Adam state and applies the identical update to the identical
 // summed gradient.
 //
-// The exchange is a one-shot all-reduce written into the kernel (no NCCL call on this path): a block
-// owns 32 parameters; it STORES its 32 local sums into slot [rank] of every peer's exchange buffer
-// (symmetric memory, mapped into every peer: remote stores over NVLink, no round trip), releases a flag
-// in every peer's flag pad, waits until every peer's flag for the same block has arrived in its own pad,
-// then adds the 32 values of every rank from its OWN memory in RANK ORDER (so all ranks compute
-// bit-identical sums) before the Adam update.  Blocks only wait
-// for the same block index on the other GPUs, never for another block of their own GPU.  Exchange
-// buffers and flags are double-buffered by step parity: a rank can only be one step ahead of the slowest.
+// The exchange is a one-shot all-reduce written into the kernel (no NCCL call on this path): a block owns 32 parameters
+// and only ever waits for the same block index on the other GPUs, never for another block of its own GPU.  Buffers
+// live in symmetric memory mapped into every peer and are double-buffered by step parity (a rank can be at most one
+// step ahead of the slowest).  Three forms, all adding the ranks' values in RANK ORDER (bit-identical sums everywhere):
+//   low-latency (default, peer.pull == 2): (value, step) as ONE 8-byte word per parameter stored into slot [rank] of every
+//       peer's buffer; the receiver polls the words in its own memory until their tag is this step's.  An aligned 8-byte
+//       store is atomic: no flags, no fences, one one-way NVLink trip.
+//   push (0): plain floats into every peer's slot, one st.release.sys flag per peer, ld.acquire.sys spin, local reads.
+//   pull (1): local store + fence, flags, remote loads of every peer's slot.
 #include "mq_common.cuh"
 
 #ifndef MQ_EMU
@@ -86,7 +87,30 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
     float g = part[0][jx];
 #pragma unroll
     for (int k = 1; k < 8; ++k) g += part[k][jx];
-    if (peer.world > 1) {
+    if (peer.world > 1 && peer.pull == 2) {
+        // ---- low-latency form: value and step tag travel together in ONE 8-byte word (an aligned 8-byte store is
+        // atomic), pushed into slot [rank] of every peer's buffer; the receiver polls the words in its own memory until
+        // the tag is this step's.  One one-way NVLink trip: no flags, no fences, no release / acquire.
+        const int par = (int)(peer.step & 1u);
+        const int64_t slot = ((int64_t)par * peer.world + peer.rank) * peer.buf_stride;
+        if (j < n) {
+            const unsigned long long w = ((unsigned long long)peer.step << 32) | (unsigned long long)__float_as_uint(g);
+            for (int r = 0; r < peer.world; ++r) {
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer.grad_bufs[r]) + slot + j;
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
+            }
+            g = 0.0f;
+            const unsigned long long *mine =
+                reinterpret_cast<const unsigned long long *>(peer.grad_bufs[peer.rank]) + (int64_t)par * peer.world * peer.buf_stride;
+            for (int r = 0; r < peer.world; ++r) {                       // rank order: bit-identical on every rank
+                unsigned long long v;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + (int64_t)r * peer.buf_stride + j) : "memory");
+                } while ((unsigned)(v >> 32) != peer.step);
+                g += __uint_as_float((unsigned)v);
+            }
+        }
+    } else if (peer.world > 1) {
         // ---- one-shot all-reduce over peer memory (push): every rank STORES its 32 sums into slot [rank] of every
         // peer's exchange buffer (remote stores need no round trip), then releases one flag per peer; a rank only ever
         // reads its own memory

@@ -72,9 +72,10 @@ class PeerExchange(object):
     def __init__(self, n_params):
         self.ok = False
         self.step = 0
-        # push (remote stores) wins up to 4 GPUs, pull (remote loads) on 8: measured, profiles/r1_scaling.md
-        mode = os.environ.get("MQ_PEER_MODE", "auto")
-        self.pull = 1 if mode == "pull" or (mode == "auto" and world() >= 8) else 0
+        # default: the low-latency form (tagged 8-byte words, one one-way trip); MQ_PEER_MODE=push|pull select the
+        # flag-based forms (measured against each other in profiles/r1_scaling.md)
+        mode = os.environ.get("MQ_PEER_MODE", "ll")
+        self.pull = {"pull": 1, "push": 0, "ll": 2}.get(mode, 2)
         if world() == 1 or not torch.cuda.is_available() or os.environ.get("MQ_NO_PEER_EXCHANGE"):
             return
         if dist.get_backend() != "nccl":
@@ -86,7 +87,8 @@ class PeerExchange(object):
             self.stride = (int(n_params) + 63) // 64 * 64
             nblk = int(_lib.lib().mq_step_blocks(int(n_params)))
             dev = torch.device("cuda", torch.cuda.current_device())
-            self.buf = symm.empty(2 * w * self.stride, dtype=torch.float32, device=dev)
+            # float[2][w][stride] for push / pull; the low-latency form uses 8-byte words: twice the bytes
+            self.buf = symm.empty(2 * w * self.stride * 2, dtype=torch.float32, device=dev)
             self.flags = symm.empty(2 * w * nblk, dtype=torch.int32, device=dev)
             self.buf.zero_()
             self.flags.zero_()

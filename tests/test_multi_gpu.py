@@ -24,8 +24,8 @@ def _worker(rank, world, port, out_dir, peer):
     sys.path.insert(0, ROOT)
     if not peer:
         os.environ["MQ_NO_PEER_EXCHANGE"] = "1"           # NCCL all-reduce + separate Adam launch
-    elif peer == "pull":
-        os.environ["MQ_PEER_MODE"] = "pull"               # remote loads instead of remote stores (default on 8 GPUs)
+    else:
+        os.environ["MQ_PEER_MODE"] = {True: "ll"}.get(peer, peer)      # ll (default): tagged 8-byte words; push / pull: flags
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -44,13 +44,14 @@ def _worker(rank, world, port, out_dir, peer):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", [True, "pull", False], ids=["peer_memory_push", "peer_memory_pull", "nccl_allreduce"])
+@pytest.mark.parametrize("peer", [True, "pull", "push", False],
+                         ids=["peer_memory_ll", "peer_memory_pull", "peer_memory_push", "nccl_allreduce"])
 def test_sharded_update_matches_single_gpu(tmp_path, peer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    port = 29500 + os.getpid() % 2000 + {True: 7, "pull": 13, False: 0}[peer]
+    port = 29500 + os.getpid() % 2000 + {True: 7, "pull": 13, "push": 19, False: 0}[peer]
     mp.spawn(_worker, args=(2, port, str(tmp_path), peer), nprocs=2, join=True)
     pol = [np.load(os.path.join(tmp_path, "pol%d.npy" % r)) for r in range(2)]
     val = [np.load(os.path.join(tmp_path, "val%d.npy" % r)) for r in range(2)]
