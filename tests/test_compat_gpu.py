@@ -676,6 +676,34 @@ def test_reinforce_script_loop_and_reward_log():
     assert np.all(np.abs(env.env.get_mean() - 1.0) < 3.0) and np.all(env.env.get_std() > 0.1)
 
 
+def test_es_population_generations_against_oracle():
+    """benchmarks/mutation.py:33-37 in population form through the ESPopulation driver: three generations
+    (FFMA evaluation for 100 observations; tensor-core evaluation for 300) follow the oracle -- returns, the
+    RunningNormalize(horizon 10) batch update, the mean of noise x normalised return, Adam(lr 0.01)."""
+    from oracle import mq_oracle as O
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.es import ESPopulation
+    from mannequin2_b200.ppo import init_mlp
+    for n_obs_rows in (100, 300):
+        rs = np.random.RandomState(17 + n_obs_rows)
+        np.random.seed(6)
+        theta0 = init_mlp(11, [64, 64, 3], 1.0)
+        spec = O.mlp_spec(11, [64, 64, 3], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+        es = ESPopulation(11, 3, params=theta0.copy())
+        opt, norm = O.AdamO(theta0, horizon=10, lr=0.01), O.RunningNormalizeO(horizon=10)
+        want = theta0.copy()
+        coef = rs.randn(3).astype(np.float32)
+        for _ in range(3):
+            noise = (rs.randn(48, len(theta0)) * 0.1).astype(np.float32)
+            obs = np.clip(rs.randn(n_obs_rows, 11), -5, 5).astype(np.float32)
+            want, rets, _ = O.es_generation(want, spec, opt, norm, noise, obs, coef)
+            got_rets = es.generation(D.from_host(noise), D.from_host(obs), D.from_host(coef))
+            assert_close(D.to_host(got_rets), rets, rtol=2e-4, atol_scale=2e-5)
+        got = es.get_params().astype(np.float32)
+        assert np.max(np.abs(got - theta0)) > 1e-3
+        assert np.max(np.abs(got - want)) < 2e-4, np.max(np.abs(got - want))
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
