@@ -89,3 +89,53 @@ def test_sharded_update_matches_single_gpu(tmp_path, peer):
         l0 = np.concatenate([x[s[5][k]] for s, x in zip(shards, lp0)])
         pol_theta = O.ppo_policy_step(pol_theta, pol_spec, popt, o, a, ad, l0)
     assert np.max(np.abs(pol[0] - pol_theta)) < 2e-5
+
+
+def _es_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.es import ESPopulation
+    noise, obs, coef, theta0 = _es_data()
+    es = ESPopulation(11, 3, params=theta0.copy())
+    m = noise.shape[1] // world
+    for g in range(noise.shape[0]):                          # this rank's members of every generation
+        es.generation(D.from_host(noise[g, rank * m:(rank + 1) * m]), D.from_host(obs[g]), D.from_host(coef))
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, "es%d.npy" % rank), es.get_params().astype(np.float32))
+    dist.destroy_process_group()
+
+
+def _es_data():
+    from mannequin2_b200.ppo import init_mlp
+    rs = np.random.RandomState(23)
+    np.random.seed(6)
+    theta0 = init_mlp(11, [64, 64, 3], 1.0)
+    noise = (rs.randn(3, 48, len(theta0)) * 0.1).astype(np.float32)
+    obs = np.clip(rs.randn(3, 120, 11), -5, 5).astype(np.float32)
+    return noise, obs, rs.randn(3).astype(np.float32), theta0
+
+
+def test_sharded_es_population_matches_oracle(tmp_path):
+    """the ES population sharded over two GPUs (24 members each, no communication during evaluation, returns
+    all-gathered, one all-reduce of the weighted noise sum) takes the same three Adam steps as the oracle on all 48."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_es_worker, args=(2, 29500 + os.getpid() % 2000 + 29, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(tmp_path, "es%d.npy" % r)) for r in range(2)]
+    assert np.array_equal(got[0], got[1])                     # replicas stay identical
+    from oracle import mq_oracle as O
+    noise, obs, coef, theta0 = _es_data()
+    spec = O.mlp_spec(11, [64, 64, 3], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+    opt, norm = O.AdamO(theta0, horizon=10, lr=0.01), O.RunningNormalizeO(horizon=10)
+    want = theta0.copy()
+    for g in range(noise.shape[0]):
+        want, _, _ = O.es_generation(want, spec, opt, norm, noise[g], obs[g], coef)
+    assert np.max(np.abs(got[0] - theta0)) > 1e-3
+    assert np.max(np.abs(got[0] - want)) < 2e-4, np.max(np.abs(got[0] - want))
