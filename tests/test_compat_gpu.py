@@ -704,6 +704,43 @@ def test_es_population_generations_against_oracle():
         assert np.max(np.abs(got - want)) < 2e-4, np.max(np.abs(got - want))
 
 
+def test_full_size_update_is_bit_reproducible():
+    """BASELINE configs[2] at full size (2^20 transitions, 65,536-row minibatches; one epoch to keep it short): the
+    update is a pure function of its inputs -- two learners started from the same parameters end with bit-identical
+    policy and value parameters (fixed-order reductions everywhere: per-CTA partials, the look-back scan, the
+    normaliser), advantages and returns included -- and the result is finite and has moved."""
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import ppo_rollout
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.ppo import PPOUpdater, init_mlp
+    rs = np.random.RandomState(3)
+    n, mb = 1 << 20, 65536
+    o, a, r, d = ppo_rollout(rs, n, p_done=1.0 / 500, cut=1000)
+    vi = rs.permutation(n).astype(np.int32).reshape(n // mb, mb)
+    pi = rs.permutation(n).astype(np.int32).reshape(n // mb, mb)
+    dev = [D.from_host(x) for x in (o, a, r, d, vi, pi)]
+    np.random.seed(1)
+    pol0 = np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)])
+    val0 = init_mlp(11, [64, 64, 1], 0.1)
+    results = []
+    for _ in range(2):
+        upd = PPOUpdater(11, 3, policy_params=pol0.copy(), value_params=val0.copy())
+        adv, ret = upd.update_dev(*dev)
+        torch.cuda.synchronize()
+        results.append([D.to_host(t).copy() for t in (upd.policy.theta, upd.value.theta, adv, ret)])
+    for x, y in zip(*results):
+        assert np.array_equal(x, y)
+    pol, val, adv, ret = results[0]
+    assert np.all(np.isfinite(pol)) and np.all(np.isfinite(val)) and np.all(np.isfinite(adv))
+    assert np.max(np.abs(pol - pol0)) > 1e-4 and np.max(np.abs(val - val0)) > 1e-4
+    # episode segmentation at full size: the advantage at an episode end is r - v there, whatever follows
+    ends = np.nonzero(d)[0][:2000]
+    v_all = ret - adv
+    assert np.max(np.abs(adv[ends] - (r[ends] - v_all[ends]))) < 1e-5
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
