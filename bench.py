@@ -10,7 +10,6 @@ host<->device copies inside the timed region.  `oracle/` is imported only by the
 `cpu_baseline` leg and by `--impl reference`.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess

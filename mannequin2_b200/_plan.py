@@ -14,7 +14,6 @@ the parameters through a single pointer.
 import ctypes
 
 import numpy as np
-import torch
 
 from . import _device as D
 from . import _lib
@@ -67,7 +66,7 @@ def _match_chain(root):
 
 
 def compile_root(root):
-    from .basicnet import Params, _flat_slice
+    from .basicnet import Params
     op = _op(root)
     if op and op[0] == "gauss_logprob":
         mean, logstd = root.inputs

@@ -16,15 +16,13 @@ contiguous device slice.  At the first `evaluate` a root is pattern-matched:
 returns a device-backed flat float32 vector (DeviceVector) holding batch-MEAN
 parameter gradients (basicnet.py:242-249).
 """
-import ctypes
 
 import numpy as np
 import torch
 
 from . import _device as D
-from . import _lib
 from . import backprop
-from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, HEAD_DY, MqHead
+from ._lib import ACT_LRELU, ACT_TANH
 from ._utils import endswith
 
 

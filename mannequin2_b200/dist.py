@@ -12,7 +12,6 @@ On NVLink-connected GPUs the per-step exchange does not go through NCCL at all: 
 small buffer per rank into every peer (torch symmetric memory: plumbing) and csrc/mq_step.cu does the
 all-reduce inside the kernel that also sums the per-CTA partial gradients and applies Adam.
 """
-import ctypes
 import os
 
 import torch

@@ -17,7 +17,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, MQ_F64
+from ._lib import ACT_NONE, ACT_TANH
 from ._normalize import RunningNormalize
 from .ppo import init_mlp
 

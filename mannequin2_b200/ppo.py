@@ -26,7 +26,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, MQ_F64, MqHead
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, MqHead
 from ._normalize import RunningNormalize
 from .basicnet import normed_columns
 

@@ -26,7 +26,6 @@ import numpy as np
 import torch
 
 from . import _device as D
-from . import _lib
 from ._lib import MqEnv
 
 
