@@ -387,7 +387,7 @@ scan_lookback_kernel(E el, int64_t n, ScanTile<T> *__restrict__ tiles, unsigned 
 // transition: padded shared-memory indices, four LDS per element and every element evaluated twice), not by HBM; here an
 // element costs ~20.  Requires 16-byte aligned arrays and n % 8 == 0 (rows of a thread start 128-bit groups); any other
 // call takes the staged kernel.
-__global__ void __launch_bounds__(MQ_NT, 6)
+__global__ void __launch_bounds__(MQ_NT, 8)
 gae_lookback_kernel(GaeStage el, int64_t n, ScanTile<float> *__restrict__ tiles) {
     __shared__ Lin<float> warp_tot[MQ_NT / 32];
     __shared__ float s_yin;
