@@ -82,3 +82,34 @@ def test_shard_ranges_cover_everything():
         assert parts[0][0] == 0 and parts[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
         assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+def test_gym_helpers_host_side():
+    """mannequin/gym.py:86-137 without gym: one_step / episode bookkeeping (next_obs carry-over, done handling),
+    PrintRewards' running mean of finished episodes and the reward-log line of benchmarks/_env.py:60-63.  Host logic
+    only: no device is touched (the observation normaliser is tested on the GPU)."""
+    from mannequin2_b200.gym import PrintRewards, episode, log_line, one_step
+
+    class Counter(object):
+        def __init__(self):
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return np.array([0.0, 1.0])
+
+        def step(self, action):
+            self.t += 1
+            return np.array([float(self.t), 1.0]), 2.0, self.t >= 5, {}
+
+    lines = []
+    env = PrintRewards(Counter(), every=4, print=lambda s, r: lines.append(log_line(s, r)))
+    traj = episode(env, lambda obs: obs[:1] * 0.5)
+    assert len(traj) == 5 and np.array_equal(traj.o[:, 0], np.arange(5.0)) and np.all(traj.r == 2.0)
+    assert env.next_obs is None                                   # the episode ended: the next one_step resets
+    obs, act, rew, done = one_step(env, lambda obs: obs[:1])
+    assert obs[0] == 0.0 and rew == 2.0 and not done and env.next_obs[0] == 1.0
+    for _ in range(6):
+        one_step(env, lambda obs: obs[:1])
+    assert lines == ["4 0.00\n", "8 10.00\n", "12 10.00\n"]
+    assert log_line(1000, -3.14159) == "1000 -3.14\n"
