@@ -349,6 +349,44 @@ def gen_obsnorm(out, gym):
     out["on_batch_mean"], out["on_batch_var"] = norm.get_mean(), norm.get_var()
 
 
+def gen_vae(out):
+    """mnist/vae.py:13-34 itself: DKLUninormal and Clip are module-level constructors there, so the module is imported
+    (matplotlib replaced by an empty stand-in; the autograd stand-in differentiates the reference's own dkl expression)
+    and the two are evaluated inside a small encoder graph: forward values and the flat parameter gradient."""
+    import importlib.util
+    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", plt)
+    spec = importlib.util.spec_from_file_location("ref_vae", os.path.join(REF, "mnist", "vae.py"))
+    vae = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vae)
+    import mannequin.basicnet as bn
+    rs = np.random.RandomState(41)
+    np.random.seed(42)
+    x = bn.Input(5)
+    h = bn.Tanh(bn.Affine(x, 8))
+    mean = bn.Affine(h, 3, init=0.1)
+    logstd = vae.Clip(bn.Affine(h, 3), -6.0, 0.0)
+    dkl = vae.DKLUninormal(mean=mean, logstd=logstd)
+    theta = dkl.get_params() + rs.randn(dkl.n_params).astype(np.float32) * 0.3
+    dkl.load_params(theta)
+    inp = rs.randn(7, 5).astype(np.float32)
+    val, bpp = dkl.evaluate(inp)
+    g = rs.randn(7).astype(np.float32)
+    out["vae_theta"], out["vae_x"], out["vae_g"] = theta, inp, g
+    out["vae_dkl"], out["vae_grad"] = np.asarray(val), bpp(g)
+    out["vae_mean"], out["vae_logstd"] = np.asarray(mean(inp)), np.asarray(logstd(inp))
+    # Clip on its own: values on both sides of the range, gradients of both signs
+    c_in = bn.Input(6)
+    clip = vae.Clip(c_in, -2.5, 2.5)
+    v = (rs.randn(4, 6) * 3).astype(np.float32)
+    cg = rs.randn(4, 6).astype(np.float32)
+    y, cb = clip.evaluate(v)
+    cb(cg)
+    out["clip_v"], out["clip_g"], out["clip_y"], out["clip_dx"] = v, cg, np.asarray(y), np.asarray(c_in.last_gradient)
+
+
 def gen_ppo(out, gym):
     """Run benchmarks/ppo.py:run() itself for two chunks and record everything."""
     import mannequin
@@ -508,6 +546,9 @@ def main():
     d = {}
     gen_obsnorm(d, gym)
     groups["obsnorm"] = d
+    d = {}
+    gen_vae(d)
+    groups["vae"] = d
     only = sys.argv[1:]
     for name, d in groups.items():
         if only and name not in only:

@@ -741,6 +741,33 @@ def test_full_size_update_is_bit_reproducible():
     assert np.max(np.abs(adv[ends] - (r[ends] - v_all[ends]))) < 1e-5
 
 
+def test_vae_heads_against_reference_fixture():
+    """DKLUninormal and Clip as device ops inside a two-headed encoder graph against mnist/vae.py:13-34 itself
+    (golden/vae.npz, generated by importing the reference module): DKL values, the flat parameter gradient (shared
+    trunk, fan-out accumulation, batch mean, Clip's gradient gate at the range boundary) and Clip alone."""
+    from mannequin2_b200.basicnet import Input, Affine, Tanh
+    from mannequin2_b200.vae import DKLUninormal, Clip
+    g = load_golden("vae")
+    np.random.seed(42)
+    x = Input(5)
+    h = Tanh(Affine(x, 8))
+    mean = Affine(h, 3, init=0.1)
+    logstd = Clip(Affine(h, 3), -6.0, 0.0)
+    dkl = DKLUninormal(mean=mean, logstd=logstd)
+    assert dkl.n_params == len(g["vae_theta"])
+    dkl.load_params(g["vae_theta"])
+    val, bpp = dkl.evaluate(g["vae_x"])
+    assert_close(val, g["vae_dkl"], rtol=2e-5, atol_scale=2e-6)
+    assert_close(np.asarray(bpp(g["vae_g"])), g["vae_grad"], rtol=3e-5, atol_scale=3e-6)
+    assert_close(np.asarray(logstd(g["vae_x"])), g["vae_logstd"], rtol=2e-5, atol_scale=2e-6)
+    c_in = Input(6)
+    clip = Clip(c_in, -2.5, 2.5)
+    y, cb = clip.evaluate(g["clip_v"])
+    cb(g["clip_g"])
+    assert np.array_equal(np.asarray(y), g["clip_y"])
+    assert np.array_equal(np.asarray(c_in.last_gradient), g["clip_dx"])
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and

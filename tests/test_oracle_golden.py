@@ -257,6 +257,32 @@ def test_rollout_side_vs_reference():
     assert np.max(np.abs(adv - want.reshape(-1))) < 1e-5
 
 
+def test_vae_heads_vs_reference_module():
+    """DKLUninormal and Clip against mnist/vae.py:13-34 ITSELF (the module imported in the build container with
+    matplotlib and autograd replaced by stand-ins, golden/vae.npz): forward values and the flat gradient of a small
+    encoder graph whose clipped logstd head touches the range boundary; Clip alone on both sides of its range."""
+    g = load_golden("vae")
+    th, x, gg = g["vae_theta"].astype(np.float64), g["vae_x"].astype(np.float64), g["vae_g"].astype(np.float64)
+    w1, b1 = th[:40].reshape(5, 8), th[40:48]
+    w2, b2 = th[48:72].reshape(8, 3), th[72:75]
+    w3, b3 = th[75:99].reshape(8, 3), th[99:102]
+    h = np.tanh(x @ w1 + b1)
+    mean, ls_raw = h @ w2 + b2, h @ w3 + b3
+    ls = O.clip_forward(ls_raw, -6.0, 0.0)
+    assert np.max(np.abs(mean - g["vae_mean"])) < 1e-5 and np.max(np.abs(ls - g["vae_logstd"])) < 1e-5
+    assert (ls == 0.0).any() and (ls < 0.0).any()
+    assert_close(O.dkl_uninormal(mean, ls), g["vae_dkl"], rtol=2e-5, atol_scale=2e-6)
+    d_mean, d_ls = O.dkl_uninormal_grads(mean, ls, gg)
+    d_raw = O.clip_backward(ls_raw, d_ls, -6.0, 0.0)
+    n = len(x)
+    d_h = (d_mean @ w2.T + d_raw @ w3.T) * (1.0 - h * h)
+    grad = np.concatenate([(x.T @ d_h).ravel(), d_h.sum(0), (h.T @ d_mean).ravel(), d_mean.sum(0),
+                           (h.T @ d_raw).ravel(), d_raw.sum(0)]) / n          # batch-mean rule, basicnet.py:242-249
+    assert_close(grad, g["vae_grad"], rtol=3e-5, atol_scale=3e-6)
+    assert np.array_equal(O.clip_forward(g["clip_v"], -2.5, 2.5), g["clip_y"])
+    assert np.array_equal(O.clip_backward(g["clip_v"], g["clip_g"], -2.5, 2.5).astype(np.float32), g["clip_dx"])
+
+
 def test_vae_heads_fd():
     rs = np.random.RandomState(2)
     m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
