@@ -16,6 +16,10 @@ Parity status (see DESIGN.md section "Oracle"):
     The forward expressions are pinned by running the reference code with a
     complex-step stand-in for ``autograd`` (make_golden.py); the closed-form
     derivatives are additionally checked by finite differences;
+  * ``dkl_uninormal`` / ``clip_*`` against mnist/vae.py imported as a module,
+    ``es_apply_returns`` against benchmarks/mutation.py:run() itself,
+    ``normalized_observations_step`` against mannequin/gym.py's wrapper
+    (golden/vae.npz, es.npz, obsnorm.npz);
   * ``gauss_entropy`` has no reference code at all: "parity unpinned".
 
 All citations are relative to /root/reference.
@@ -474,10 +478,18 @@ def es_generation(theta, spec, opt, norm, noise, obs, ret_coef, lr=0.01):
         th = (np.asarray(theta, np.float64) + noise[p]).astype(np.float32)
         a = mlp_forward(th, spec, obs, dtype=np.float32)[-1]
         rets[p] = np.sum(a.astype(np.float64) @ np.asarray(ret_coef, np.float64))
-    r = norm(rets.astype(np.float32))
+    r = es_apply_returns(opt, norm, noise, rets.astype(np.float32), lr)
+    return opt.get_value().astype(np.float32), rets, r
+
+
+def es_apply_returns(opt, norm, noise, rets, lr=0.01):
+    """benchmarks/mutation.py:35-37 for a population: the returns go through the
+    normaliser as ONE batch, Adam ascends mean_p noise_p * r_p (population 1:
+    exactly `r = normalize(R); opt.apply_gradient(diff * r, lr=0.01)`)."""
+    r = np.reshape(norm(np.asarray(rets)), -1)
     grad = (np.asarray(noise, np.float64) * r[:, None]).mean(axis=0)
     opt.apply_gradient(grad, lr=lr)
-    return opt.get_value().astype(np.float32), rets, r
+    return r
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -525,6 +525,83 @@ def gen_gae(out, gym):
     out["gae_o2_first"] = t2.o[0]
 
 
+def gen_es(out, gym):
+    """benchmarks/mutation.py:run() itself for 12 generations (fake env factory; episodes cut after 40 steps): every
+    perturbation, episode return and the optimiser value after each step are recorded."""
+    import mannequin
+    bench_dir = os.path.join(REF, "benchmarks")
+    sys.path.insert(0, bench_dir)
+    n_gen = 12
+
+    class ShortEnv(SyntheticEnv):
+        def __init__(self, gym, seed):
+            super().__init__(gym, seed)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return super().reset()
+
+        def step(self, action):
+            o, r, d, i = super().step(action)
+            self.t += 1
+            return o, r, d or self.t >= 40, i
+
+    env_mod = types.ModuleType("_env")
+    calls = {"n": 0}
+
+    def get_progress():
+        calls["n"] += 1
+        return 0.0 if calls["n"] <= n_gen else 1.0
+
+    env_mod.build_env = lambda: ShortEnv(gym, seed=91)
+    env_mod.get_progress = get_progress
+    saved_env = sys.modules.get("_env")
+    sys.modules["_env"] = env_mod
+    adams, rets = [], []
+    RealAdam, RealNorm = mannequin.Adam, mannequin.RunningNormalize
+
+    def rec_adam(*a, **k):
+        opt = RealAdam(*a, **k)
+        adams.append(opt)
+        real_apply = opt.apply_gradient
+        opt.trace = [np.array(opt.get_value())]
+
+        def apply(grad, **kw):
+            opt.grads = getattr(opt, "grads", []) + [np.array(grad)]
+            real_apply(grad, **kw)
+            opt.trace.append(np.array(opt.get_value()))
+        opt.apply_gradient = apply
+        return opt
+
+    class RecNorm(RealNorm):
+        def __call__(self, value):
+            rets.append(float(value))
+            return super().__call__(value)
+    mannequin.Adam, mannequin.RunningNormalize = rec_adam, RecNorm
+    try:
+        import importlib
+        np.random.seed(93)
+        mut = importlib.import_module("mutation")
+        mut.run()
+    finally:
+        mannequin.Adam, mannequin.RunningNormalize = RealAdam, RealNorm
+        sys.path.remove(bench_dir)
+        if saved_env is not None:
+            sys.modules["_env"] = saved_env
+        else:
+            del sys.modules["_env"]
+    opt = adams[0]
+    # the perturbations are np.random.randn(P) * 0.1 drawn from the global generator seeded above, after the three
+    # normed_columns draws of build_policy: the test replays them instead of storing 12 x 5123 doubles
+    keep = [0, 1, 2, 3, 6, n_gen]
+    out["es_seed"] = np.array([93])
+    out["es_keep"] = np.array(keep)
+    out["es_trace"] = np.array([opt.trace[k] for k in keep])    # optimiser value (fp64) after `keep` generations
+    out["es_grad_norms"] = np.array([np.linalg.norm(x) for x in opt.grads])
+    out["es_returns"] = np.array(rets)                          # episode returns fed to the normaliser
+
+
 def main():
     sys.path.insert(0, REF)
     install_fake_autograd()
@@ -549,6 +626,9 @@ def main():
     d = {}
     gen_vae(d)
     groups["vae"] = d
+    d = {}
+    gen_es(d, gym)
+    groups["es"] = d
     only = sys.argv[1:]
     for name, d in groups.items():
         if only and name not in only:

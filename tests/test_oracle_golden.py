@@ -283,6 +283,33 @@ def test_vae_heads_vs_reference_module():
     assert np.array_equal(O.clip_backward(g["clip_v"], g["clip_g"], -2.5, 2.5).astype(np.float32), g["clip_dx"])
 
 
+def test_es_update_rule_vs_reference_run():
+    """benchmarks/mutation.py:run() itself, 12 generations on a stand-in environment (golden/es.npz): with a population
+    of one the oracle's ES update (returns through RunningNormalize(horizon 10) as a batch, Adam(horizon 10, lr 0.01) on
+    mean_p noise_p r_p) reproduces the script's optimiser values.  The perturbations are replayed from the global
+    NumPy generator exactly as the script drew them."""
+    g = load_golden("es")
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(g["es_seed"][0]))
+        for shape in ((11, 64), (64, 64), (64, 3)):            # build_policy's normed_columns draws (basicnet.py:265-267)
+            np.random.randn(*shape)
+        n_gen = len(g["es_returns"])
+        diffs = [np.random.randn(5123) * 0.1 for _ in range(n_gen)]
+    finally:
+        np.random.set_state(state)
+    keep = [int(k) for k in g["es_keep"]]
+    theta0 = g["es_trace"][0]
+    opt, norm = O.AdamO(theta0.astype(np.float32), horizon=10), O.RunningNormalizeO(horizon=10)
+    for gen in range(n_gen):
+        r = O.es_apply_returns(opt, norm, diffs[gen][None, :], np.array([g["es_returns"][gen]]), lr=0.01)
+        assert abs(np.linalg.norm(diffs[gen] * r[0]) - g["es_grad_norms"][gen]) < 1e-9 * (1 + g["es_grad_norms"][gen])
+        if gen + 1 in keep:
+            want = g["es_trace"][keep.index(gen + 1)]
+            assert np.max(np.abs(opt.get_value() - want)) < 1e-10, (gen, np.max(np.abs(opt.get_value() - want)))
+    assert g["es_grad_norms"][0] == 0.0 and np.all(g["es_grad_norms"][1:] > 0)     # zeros until two returns were seen
+
+
 def test_vae_heads_fd():
     rs = np.random.RandomState(2)
     m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
