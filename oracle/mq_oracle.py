@@ -18,8 +18,10 @@ Parity status (see DESIGN.md section "Oracle"):
     derivatives are additionally checked by finite differences;
   * ``dkl_uninormal`` / ``clip_*`` against mnist/vae.py imported as a module,
     ``es_apply_returns`` against benchmarks/mutation.py:run() itself,
-    ``normalized_observations_step`` against mannequin/gym.py's wrapper
-    (golden/vae.npz, es.npz, obsnorm.npz);
+    ``normalized_observations_step`` against mannequin/gym.py's wrapper, the
+    REINFORCE chain (discounted, normalise, logprob gradient, Adam) against
+    benchmarks/policy.py:run() (golden/vae.npz, es.npz, obsnorm.npz,
+    reinforce.npz);
   * ``gauss_entropy`` has no reference code at all: "parity unpinned".
 
 All citations are relative to /root/reference.

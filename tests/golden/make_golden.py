@@ -602,6 +602,95 @@ def gen_es(out, gym):
     out["es_returns"] = np.array(rets)                          # episode returns fed to the normaliser
 
 
+def gen_reinforce(out, gym):
+    """benchmarks/policy.py:run() itself (plain REINFORCE, policy.py:29-47) for 6 episodes of <= 30 steps on a stand-in
+    environment with a Box action space (Gauss policy): the trajectories it sampled and the optimiser values."""
+    import mannequin
+    import mannequin.gym as mgym
+    bench_dir = os.path.join(REF, "benchmarks")
+    sys.path.insert(0, bench_dir)
+    n_ep = 6
+
+    class ShortEnv(SyntheticEnv):
+        def __init__(self, gym, seed):
+            super().__init__(gym, seed)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return super().reset()
+
+        def step(self, action):
+            o, r, d, i = super().step(action)
+            self.t += 1
+            return o, r, d or self.t >= 30, i
+
+    env_mod = types.ModuleType("_env")
+    calls = {"n": 0}
+
+    def get_progress():
+        calls["n"] += 1
+        return 0.0 if calls["n"] <= n_ep else 1.0
+
+    env_mod.build_env = lambda: ShortEnv(gym, seed=61)
+    env_mod.get_progress = get_progress
+    saved_env = sys.modules.get("_env")
+    sys.modules["_env"] = env_mod
+    adams, trajs = [], []
+    RealAdam = mannequin.Adam
+
+    def rec_adam(*a, **k):
+        opt = RealAdam(*a, **k)
+        adams.append(opt)
+        real_apply = opt.apply_gradient
+        opt.trace = [np.array(opt.get_value())]
+
+        def apply(grad, **kw):
+            real_apply(grad, **kw)
+            opt.trace.append(np.array(opt.get_value()))
+        opt.apply_gradient = apply
+        return opt
+
+    real_episode = mgym.episode
+
+    def rec_episode(env, policy, **kw):
+        t = real_episode(env, policy, **kw)
+        trajs.append((np.array(t.o), np.array(t.a), np.array(t.r)))
+        return t
+    RealRS = np.random.RandomState
+    seeds = {"n": 300}
+
+    class SeededRS(RealRS):
+        def __new__(cls, *a, **k):
+            return RealRS.__new__(cls)
+
+        def __init__(self, seed=None):
+            if seed is None:
+                seeds["n"] += 1
+                seed = seeds["n"]
+            super().__init__(seed)
+    mannequin.Adam, mgym.episode, np.random.RandomState = rec_adam, rec_episode, SeededRS
+    try:
+        import importlib
+        np.random.seed(63)
+        pol = importlib.import_module("policy")
+        importlib.reload(pol)
+        pol.run()
+    finally:
+        mannequin.Adam, mgym.episode, np.random.RandomState = RealAdam, real_episode, RealRS
+        sys.path.remove(bench_dir)
+        if saved_env is not None:
+            sys.modules["_env"] = saved_env
+        else:
+            del sys.modules["_env"]
+    opt = adams[0]
+    out["rf_trace"] = np.array(opt.trace).astype(np.float32)      # [n_ep + 1, 5126] optimiser values
+    out["rf_len"] = np.array([len(t[0]) for t in trajs])
+    out["rf_obs"] = np.concatenate([t[0] for t in trajs]).astype(np.float32)
+    out["rf_act"] = np.concatenate([t[1] for t in trajs]).astype(np.float32)
+    out["rf_rew"] = np.concatenate([t[2] for t in trajs]).astype(np.float32)
+
+
 def main():
     sys.path.insert(0, REF)
     install_fake_autograd()
@@ -629,6 +718,9 @@ def main():
     d = {}
     gen_es(d, gym)
     groups["es"] = d
+    d = {}
+    gen_reinforce(d, gym)
+    groups["reinforce"] = d
     only = sys.argv[1:]
     for name, d in groups.items():
         if only and name not in only:

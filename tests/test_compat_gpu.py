@@ -768,6 +768,36 @@ def test_vae_heads_against_reference_fixture():
     assert np.array_equal(np.asarray(c_in.last_gradient), g["clip_dx"])
 
 
+def test_reinforce_steps_against_reference_run():
+    """The trajectories benchmarks/policy.py:run() itself sampled (golden/reinforce.npz), pushed through this package's
+    API exactly as the script does (policy.py:40-47: Trajectory.discounted -> RunningNormalize -> tanh -> Gauss.logprob
+    backprop -> Adam -> load_params): the optimiser values follow the script's, episode by episode."""
+    from mannequin2_b200 import Adam, RunningNormalize, Trajectory
+    from mannequin2_b200.basicnet import Input, Affine, Tanh
+    from mannequin2_b200.distrib import Gauss
+    g = load_golden("reinforce")
+    np.random.seed(0)
+    policy = Input(11)
+    for _ in range(2):
+        policy = Tanh(Affine(policy, 64))
+    policy = Gauss(mean=Affine(policy, 3, init=0.1))
+    policy.load_params(g["rf_trace"][0])
+    opt = Adam(policy.get_params(), horizon=10)
+    normalize = RunningNormalize(horizon=2)
+    pos = 0
+    for ep, n in enumerate(int(v) for v in g["rf_len"]):
+        traj = Trajectory(g["rf_obs"][pos:pos + n], g["rf_act"][pos:pos + n], g["rf_rew"][pos:pos + n])
+        pos += n
+        traj = traj.discounted(horizon=500)
+        traj = traj.modified(rewards=normalize)
+        traj = traj.modified(rewards=np.tanh)
+        _, backprop = policy.logprob.evaluate(traj.o, sample=traj.a)
+        opt.apply_gradient(backprop(traj.r), lr=0.001)
+        policy.load_params(opt.get_value())
+        err = np.max(np.abs(np.asarray(opt.get_value(), dtype=np.float64) - g["rf_trace"][ep + 1]))
+        assert err < 5e-6, (ep, err)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and

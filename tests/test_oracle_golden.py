@@ -310,6 +310,29 @@ def test_es_update_rule_vs_reference_run():
     assert g["es_grad_norms"][0] == 0.0 and np.all(g["es_grad_norms"][1:] > 0)     # zeros until two returns were seen
 
 
+def test_reinforce_loop_vs_reference_run():
+    """benchmarks/policy.py:run() itself (plain REINFORCE, policy.py:29-47) for 6 episodes (golden/reinforce.npz): from
+    the trajectories the script sampled, the oracle's discounted() -> RunningNormalize(horizon 2) -> tanh ->
+    Gauss.logprob gradient (batch mean) -> Adam(horizon 10, lr 0.001) reproduces the script's optimiser values."""
+    g = load_golden("reinforce")
+    spec = O.policy_spec(11, 3)
+    theta = g["rf_trace"][0].astype(np.float32)
+    opt, norm = O.AdamO(theta, horizon=10), O.RunningNormalizeO(horizon=2)
+    pos = 0
+    for ep, n in enumerate(g["rf_len"]):
+        o, a, r = g["rf_obs"][pos:pos + n], g["rf_act"][pos:pos + n], g["rf_rew"][pos:pos + n]
+        pos += n
+        r = O.discounted(r, horizon=500).astype(np.float32)            # Trajectory stores float32 rewards
+        r = np.asarray(norm(r)).astype(np.float32)
+        r = np.tanh(r).astype(np.float32)
+        grad = O.policy_logprob_grad(theta, spec, o, a, r)
+        opt.apply_gradient(grad, lr=0.001)
+        theta = opt.get_value().astype(np.float32)
+        err = np.max(np.abs(opt.get_value() - g["rf_trace"][ep + 1]))
+        assert err < 2e-6, (ep, err)
+    assert np.max(np.abs(g["rf_trace"][-1] - g["rf_trace"][0])) > 1e-3
+
+
 def test_vae_heads_fd():
     rs = np.random.RandomState(2)
     m, l, w = rs.randn(5, 3), rs.randn(5, 3) * 0.5, rs.randn(5)
