@@ -691,6 +691,70 @@ def gen_reinforce(out, gym):
     out["rf_rew"] = np.concatenate([t[2] for t in trajs]).astype(np.float32)
 
 
+def mlp_script_data():
+    """Synthetic MNIST-shaped data for mnist/mlp.py (regenerated identically by the test)."""
+    rs = np.random.RandomState(5)
+    train_x = rs.rand(384, 28, 28).astype(np.float32)
+    train_y = np.eye(10, dtype=np.float32)[rs.randint(10, size=384)]
+    test_x = rs.rand(64, 28, 28).astype(np.float32)
+    test_y = np.eye(10, dtype=np.float32)[rs.randint(10, size=64)]
+    return dict(train_x=train_x, train_y=train_y, test_x=test_x, test_y=test_y)
+
+
+def gen_mlp_script(out):
+    """mnist/mlp.py:run() itself (30 optimiser steps: 10 "epochs" of 3 on a 384-sample synthetic __mnist.npz in a scratch
+    directory): the minibatch index draws and a strided subset of the optimiser value after chosen steps."""
+    import contextlib
+    import importlib.util
+    import io
+    import tempfile
+    import mannequin
+    idx_log, adams = [], []
+    RealAdam = mannequin.Adam
+
+    def rec_adam(*a, **k):
+        opt = RealAdam(*a, **k)
+        adams.append(opt)
+        real_apply = opt.apply_gradient
+        opt.trace = [np.array(opt.get_value())]
+
+        def apply(grad, **kw):
+            real_apply(grad, **kw)
+            opt.trace.append(np.array(opt.get_value()))
+        opt.apply_gradient = apply
+        return opt
+    real_randint = np.random.randint
+
+    def rec_randint(*a, **k):
+        r = real_randint(*a, **k)
+        if k.get("size") == 128:
+            idx_log.append(np.array(r))
+        return r
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(os.path.join(tmp, "__mnist.npz"), **mlp_script_data())
+        os.chdir(tmp)
+        mannequin.Adam, np.random.randint = rec_adam, rec_randint
+        try:
+            spec = importlib.util.spec_from_file_location("ref_mlp", os.path.join(REF, "mnist", "mlp.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            np.random.seed(71)
+            with contextlib.redirect_stdout(io.StringIO()) as printed:
+                mod.run()
+        finally:
+            mannequin.Adam, np.random.randint = RealAdam, real_randint
+            os.chdir(cwd)
+    opt = adams[0]
+    keep = [0, 1, 2, 3, 6, 10, 15, 20]              # beyond ~20 steps rounding-level differences grow (chaotic on 384 samples)
+    out["mlps_seed"] = np.array([71])
+    out["mlps_idx"] = np.array(idx_log).astype(np.int16)          # [30, 128]
+    out["mlps_keep"] = np.array(keep)
+    out["mlps_stride"] = np.array([37])
+    out["mlps_trace"] = np.array([opt.trace[k][::37] for k in keep]).astype(np.float32)
+    out["mlps_bars"] = np.array(printed.getvalue().splitlines())
+
+
 def main():
     sys.path.insert(0, REF)
     install_fake_autograd()
@@ -721,6 +785,9 @@ def main():
     d = {}
     gen_reinforce(d, gym)
     groups["reinforce"] = d
+    d = {}
+    gen_mlp_script(d)
+    groups["mlp_script"] = d
     only = sys.argv[1:]
     for name, d in groups.items():
         if only and name not in only:
