@@ -798,6 +798,50 @@ def test_reinforce_steps_against_reference_run():
         assert err < 5e-6, (ep, err)
 
 
+def test_mlp_script_steps_against_reference_run():
+    """mnist/mlp.py:21-43 written against `mannequin` (compat alias) with the minibatches mnist/mlp.py:run() itself drew
+    (golden/mlp_script.npz): same initial weights from the same global generator, and the optimiser values of the first
+    ten steps follow the script's."""
+    import os
+    import mannequin2_b200.compat  # noqa: F401
+    from mannequin import Adam
+    from mannequin.basicnet import Input, Affine, LReLU
+    g = load_golden("mlp_script")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    try:
+        from make_golden import mlp_script_data
+    finally:
+        sys.path.pop(0)
+    data = mlp_script_data()
+
+    def softmax(v):
+        v = v.T
+        v = np.exp(v - np.amax(v, axis=0))
+        v /= np.sum(v, axis=0)
+        return v.T
+
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(g["mlps_seed"][0]))
+        model = Input(28, 28)
+        for _ in range(2):
+            model = LReLU(Affine(model, 128))
+        model = Affine(model, 10, init=0.1)
+    finally:
+        np.random.set_state(state)
+    stride, keep = int(g["mlps_stride"][0]), [int(k) for k in g["mlps_keep"]]
+    assert np.max(np.abs(np.asarray(model.get_params())[::stride] - g["mlps_trace"][0])) < 1e-6
+    opt = Adam(model.get_params(), horizon=10, lr=0.001)
+    for step, idx in enumerate(g["mlps_idx"][:10].astype(np.int64)):
+        outs, backprop = model.evaluate(data["train_x"][idx])
+        grad = data["train_y"][idx] - softmax(outs) - outs * 0.01
+        opt.apply_gradient(backprop(grad))
+        model.load_params(opt.get_value())
+        if step + 1 in keep:
+            err = np.max(np.abs(np.asarray(opt.get_value(), dtype=np.float64)[::stride] - g["mlps_trace"][keep.index(step + 1)]))
+            assert err < 1e-5, (step, err)
+
+
 def test_vae_step_graph():
     """mnist/vae.py:39-71 on the device graph (DKLUninormal, Clip, Gauss.sample fan-out, matmul nodes): the gradient of
     mean(logprob) - mean(DKL) agrees with central differences along random directions (sampling noise held fixed), and
