@@ -78,7 +78,28 @@ typedef struct mq_head {
                                   DISCRETE_*: one-hot actions [rows,n_out]                            */
     const float *adv;          /* *_PPO: advantages [rows]                                           */
     const float *logp_old;     /* *_PPO: log-probabilities under the pre-update policy [rows]        */
+    /* ---- per-call options of the tensor-core (tcgen05) kernels; all zero = automatic, exact ---- */
+    const float *records;      /* packed rows written by mq_pack_records: [rows][rec_w] floats, row =
+                                  x[n_in] | target[n_out] | w0 | w1 (w0 = adv or the LOGP weight, w1 = logp_old).
+                                  When set, the tensor-core gradient kernel gathers ONE aligned record per minibatch
+                                  row (two 32-byte sectors for the 11-obs / 3-act policy) instead of reading x and the
+                                  head arrays separately; kernels that do not support records ignore it.            */
+    int32_t rec_w;             /* floats per record: mq_record_width(net)                                           */
+    int32_t tc;                /* MQ_TC_* flags                                                                      */
+    const void *tc_image;      /* operand image of theta (mq_tc_image_build / mq_reduce_step_image) for the planes
+                                  selected in `tc`; NULL: the launch builds it from theta into the workspace         */
 } mq_head_t;
+/* Precision of the tensor-core path (north_star: "a stated looser tolerance for TF32/bf16 tensor-core paths").
+ * An fp32 operand is split into bf16 planes x = x0 + x1 + x2; a product uses the plane pairs i + j < planes:
+ *   3 planes (default): exact fp32 products, 6 pairs            -- same bar as the FFMA kernels (rtol 1e-5)
+ *   2 planes: 16 mantissa bits per operand, 3 pairs             -- |err| <= 3e-5 max|grad|
+ *   1 plane : plain bf16 operands, 1 pair, MUFU tanh            -- |err| <= 2e-2 max|grad|
+ * The tolerances are the ones tests/kernel_cases.py: case_tc_modes asserts. */
+#define MQ_TC_PLANES_MASK 0x3   /* 0 = default (3) */
+#define MQ_TC_FORCE       0x10  /* use the tensor-core kernel whenever the net fits (default: batch >= 8192) */
+#define MQ_TC_OFF         0x20  /* never use it (FFMA kernels)                                                */
+#define MQ_TC_HALF        0x40  /* developer aid: prefer two 64-row tile slots (the default for 3 planes)         */
+#define MQ_TC_FULL        0x80  /* developer aid: 128-row tile slots only                                         */
 /* When row_idx != NULL, x and every head array are indexed by row_idx[i] (they
  * are whole-rollout arrays, mannequin/_trajectory.py:79-86 fused into the load);
  * otherwise by the minibatch position i. */
@@ -132,11 +153,6 @@ int mq_bootstrap_segments(float *rew, uint8_t *done, const float *v_next, int64_
 int mq_debug_use_chain_grad(int on);
 /* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */
 int mq_debug_set_chain_warps(int nw);
-/* developer aid: tcgen05 path of mq_fused_grad / mq_fused_forward: 0 never, 1 automatic (batch >= 8192), 2 whenever the net fits */
-int mq_debug_set_tc_mode(int mode);
-/* developer aid: which tcgen05 fused-MLP kernel: 1 (default) one 128-row tile per SM (mq_tc.cu); 0 = two 64-row tiles in
- * flight per SM (mq_tc2.cu, an experiment that measured slower: DESIGN.md 3.1), falling back to 1 for nets it does not fit */
-int mq_debug_set_tc_variant(int variant);
 /* developer aid: tcgen05 GEMM for wide layers: 0 never, 1 automatic (>= 2^26 multiply-adds), 2 whenever possible */
 int mq_debug_set_gemm_tc_mode(int mode);
 int mq_version(void);
@@ -224,6 +240,9 @@ int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch);
  * has logstd parameters (Gaussian), one-hot actions [batch,n_out] otherwise (categorical, distrib.py:24-30). */
 int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                      int64_t batch, float *out, const float *sample, float *logp, void *stream);
+/* The same with per-call MQ_TC_* flags (mq_fused_forward = flags 0). */
+int mq_fused_forward_tc(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                        int64_t batch, float *out, const float *sample, float *logp, int32_t tc, void *stream);
 /* forward + head + backward in one launch; grad[n_params] = scale * sum_batch */
 int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                   int64_t batch, const mq_head_t *head, float scale, float *grad, float *out,
@@ -233,6 +252,19 @@ int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x, const
 int mq_fused_grad_partials(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                            int64_t batch, const mq_head_t *head, float *out, float *logp, void *ws,
                            int64_t ws_bytes, int32_t *n_parts_out, void *stream);
+
+/* ---- packed minibatch records and operand images of the tensor-core gradient kernel (csrc/mq_tc3.cu) --------------
+ * Records replace the four separate gathers of benchmarks/ppo.py:30-37 (traj.o[idx], traj.a[idx], traj.r[idx],
+ * baseline[idx]; mannequin/_trajectory.py:79-86) by one aligned row per transition, packed once per update. */
+int32_t mq_record_width(const mq_net_t *net);           /* floats per record: n_in + n_out + 2 rounded up to 16 */
+/* rec[r] = x[r, :n_in] | tgt[r, :n_out] | w0[r] | w1[r] | 0...; tgt / w0 / w1 may be NULL (zeros). */
+int mq_pack_records(const mq_net_t *net, const float *x, const float *tgt, const float *w0, const float *w1,
+                    int64_t rows, float *rec, void *stream);
+/* bytes of the operand image of `net` for the planes in `tc` (0 when the net does not fit the kernel) */
+int64_t mq_tc_image_bytes(const mq_net_t *net, int32_t tc);
+/* image <- bf16 planes of theta in the kernel's shared-memory layout (weights of basicnet.py:288-311 as K-major /
+ * MN-major core matrices, biases, logstd, exp(-logstd)); the gradient kernel copies it with ONE bulk copy. */
+int mq_tc_image_build(const mq_net_t *net, const float *theta, int32_t tc, void *image, void *stream);
 
 /* Peer-memory descriptor of the in-kernel all-reduce (one exchange of the flat gradient per
  * optimiser step).  grad_bufs / flag_bufs are DEVICE arrays of `world` pointers: rank r's exchange buffer
@@ -258,6 +290,20 @@ int64_t mq_step_blocks(int64_t n);
 int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m, void *v,
                    float *theta_out, float *grad_out, int state_dtype, double c1, double c2, double lr,
                    double eps, int adams, const mq_peer_t *peer, void *stream);
+/* The same, and the blocks that own a parameter also refresh its entries in the operand image (`image` built for
+ * `net` and the planes in `tc`), so that the next gradient launch needs no weight conversion at all. */
+int mq_reduce_step_image(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m, void *v,
+                         float *theta_out, float *grad_out, int state_dtype, double c1, double c2, double lr,
+                         double eps, int adams, const mq_peer_t *peer, const mq_net_t *net, int32_t tc, void *image,
+                         void *stream);
+/* n_steps dependent large-minibatch steps {mq_fused_grad_partials, mq_reduce_step_image} issued by one call
+ * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73 at 65,536-row minibatches): idx_table[n_steps, mb], coefs_host =
+ * [n_steps][2] host doubles (c1, c2), peer (nullable) = descriptor of the FIRST step (its tag counts up per step),
+ * head->tc_image (nullable) is refreshed by every step. */
+int mq_train_steps(const mq_net_t *net, float *theta, const float *x, const mq_head_t *head,
+                   const int32_t *idx_table, int32_t n_steps, int64_t mb, float scale, void *value, void *m, void *v,
+                   int state_dtype, const double *coefs_host, double lr, double eps, int adams, const mq_peer_t *peer,
+                   void *ws, int64_t ws_bytes, void *stream);
 /* n_steps dependent {gather, forward, head, backward, Adam} steps in ONE launch
  * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73).  idx_table[n_steps,mb].
  * Adam state (value,m,v: state_dtype) and theta are updated in place; tw[2]

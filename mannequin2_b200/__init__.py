@@ -14,9 +14,8 @@ Adam, Adams = _a.Adam, _a.Adams                                   # optimisers (
 RunningMean, RunningNormalize = _n.RunningMean, _n.RunningNormalize
 Trajectory = _t.Trajectory
 endswith, discounted = _u.endswith, _u.discounted
-bar, plot_function_2d = _u.bar, _u.plot_function_2d
+bar = _u.bar
 
-__all__ = ["Adam", "Adams", "RunningMean", "RunningNormalize", "Trajectory", "endswith", "discounted", "bar",
-           "plot_function_2d", "version"]
+__all__ = ["Adam", "Adams", "RunningMean", "RunningNormalize", "Trajectory", "endswith", "discounted", "bar", "version"]
 
 version = (2, 7, 2)                                               # the reference version this API mirrors

@@ -28,7 +28,14 @@ class MqNet(ctypes.Structure):
 
 class MqHead(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("p0", c_float), ("p1", c_float), ("ent", c_float), ("dy", c_void_p),
-                ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p)]
+                ("target", c_void_p), ("adv", c_void_p), ("logp_old", c_void_p),
+                # per-call options of the tensor-core kernels (all zero = automatic, exact): packed records, MQ_TC_* flags,
+                # operand image
+                ("records", c_void_p), ("rec_w", c_int32), ("tc", c_int32), ("tc_image", c_void_p)]
+
+
+TC_FORCE, TC_OFF = 0x10, 0x20          # MQ_TC_* flags; the low two bits select the bf16 planes (0 = 3 = exact)
+TC_MODES = {"exact": 3, "bf16x3": 3, "bf16x2": 2, "bf16": 1}
 
 
 class MqEnv(ctypes.Structure):
@@ -56,8 +63,6 @@ SIGNATURES = {
     "mq_debug_set_tile_rows": (c_int, [c_int]),
     "mq_debug_use_chain_grad": (c_int, [c_int]),
     "mq_debug_set_chain_warps": (c_int, [c_int]),
-    "mq_debug_set_tc_mode": (c_int, [c_int]),
-    "mq_debug_set_tc_variant": (c_int, [c_int]),
     "mq_debug_set_gemm_tc_mode": (c_int, [c_int]),
     "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
@@ -84,11 +89,20 @@ SIGNATURES = {
     "mq_fused_tile_rows": (c_int, [NETP, c_int]),
     "mq_fused_ws_bytes": (c_int64, [NETP, c_int64]),
     "mq_fused_forward": (c_int, [NETP, P, P, P, c_int64, P, P, P, P]),
+    "mq_fused_forward_tc": (c_int, [NETP, P, P, P, c_int64, P, P, P, c_int32, P]),
+    "mq_record_width": (c_int32, [NETP]),
+    "mq_pack_records": (c_int, [NETP, P, P, P, P, c_int64, P, P]),
+    "mq_tc_image_bytes": (c_int64, [NETP, c_int32]),
+    "mq_tc_image_build": (c_int, [NETP, P, c_int32, P, P]),
     "mq_fused_grad": (c_int, [NETP, P, P, P, c_int64, HEADP, c_float, P, P, P, P, c_int64, P]),
     "mq_fused_grad_partials": (c_int, [NETP, P, P, P, c_int64, HEADP, P, P, P, c_int64, POINTER(c_int32), P]),
     "mq_step_blocks": (c_int64, [c_int64]),
     "mq_reduce_step": (c_int, [P, c_int32, c_int64, c_float, P, P, P, P, P, c_int, c_double, c_double, c_double,
                                c_double, c_int, PEERP, P]),
+    "mq_reduce_step_image": (c_int, [P, c_int32, c_int64, c_float, P, P, P, P, P, c_int, c_double, c_double, c_double,
+                                     c_double, c_int, PEERP, NETP, c_int32, P, P]),
+    "mq_train_steps": (c_int, [NETP, P, P, HEADP, P, c_int32, c_int64, c_float, P, P, P, c_int, POINTER(c_double), c_double,
+                               c_double, c_int, PEERP, P, c_int64, P]),
     "mq_fused_train": (c_int, [NETP, P, P, P, P, c_int, P, HEADP, P, c_int32, c_int32, c_double,
                                c_double, POINTER(c_double), c_double, c_double, P]),
     "mq_es_eval": (c_int, [NETP, P, P, c_int64, P, c_int64, P, P, P]),

@@ -46,23 +46,3 @@ def bar(value, max_value=100.0, *, length=50):
     width = len("-%.2f" % max_value)
     text = ("%%%d.2f " % width) % value
     return text[0:width + 1] + "[" + body + "]"
-
-
-def plot_function_2d(function, *, xlim=(-2.0, 2.0), ylim=(-2.0, 2.0), vlim=(None, None), grid=20,
-                     file_name=None):
-    """Heat-map helper (mannequin/_utils.py:48-73); needs matplotlib, not on the hot path."""
-    import matplotlib.pyplot as plt
-    pts = np.mgrid[0:grid + 1, 0:grid + 1].reshape(2, -1).T / grid
-    pts = pts * [xlim[1] - xlim[0], ylim[1] - ylim[0]] + [xlim[0], ylim[0]]
-    vals = np.array([float(function(*c)) for c in pts]).reshape((grid + 1, grid + 1))
-    plt.clf()
-    plt.imshow(vals.T[::-1, :], vmin=vlim[0], vmax=vlim[1], zorder=0, aspect="auto", cmap="inferno",
-               interpolation="bicubic", extent=[xlim[0], xlim[1], xlim[0], ylim[1]])
-    plt.colorbar()
-    if file_name is None:
-        plt.ion()
-        plt.show()
-        plt.pause(0.0001)
-    else:
-        plt.gcf().set_size_inches(10, 8)
-        plt.gcf().savefig(file_name, dpi=100)

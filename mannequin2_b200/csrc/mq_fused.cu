@@ -870,6 +870,7 @@ int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const
 int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                  int64_t batch, const mq_head_t *head, int with_grad, float *out, float *logp,
                  void *ws, int64_t ws_bytes, int *grid_out, void *stream);
+int64_t mq_tc3_scratch_bytes();
 int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
                     int64_t n_obs, const float *ret_coef, float *returns, void *stream);
 static int g_use_chain_grad = 1;     // developer knob: 0 forces the tile kernel
@@ -952,12 +953,13 @@ static int64_t fused_grid(int64_t ntiles, int64_t smem_bytes) {
 
 extern "C" int64_t mq_fused_ws_bytes(const mq_net_t *net, int64_t batch) {
     (void)batch;
-    return (2 * (int64_t)mq_sm_count() + 1) * (net->n_params + 64) * (int64_t)sizeof(float) + 256;
+    // per-CTA partial gradients (up to two CTAs per SM) + room for an operand image the tensor-core launch builds itself
+    return (2 * (int64_t)mq_sm_count() + 1) * (net->n_params + 64) * (int64_t)sizeof(float) + 256 + mq_tc3_scratch_bytes();
 }
 
-extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x,
-                                const int32_t *row_idx, int64_t batch, float *out, const float *sample,
-                                float *logp, void *stream) {
+extern "C" int mq_fused_forward_tc(const mq_net_t *net, const float *theta, const float *x,
+                                   const int32_t *row_idx, int64_t batch, float *out, const float *sample,
+                                   float *logp, int32_t tc, void *stream) {
     int rc = fused_net_check(net, "mq_fused_forward");
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_fused_forward: negative batch");
@@ -969,6 +971,7 @@ extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const f
         memset(&fh, 0, sizeof(fh));
         fh.kind = !logp ? MQ_HEAD_DY : (net->logstd_off >= 0 ? MQ_HEAD_GAUSS_LOGP : MQ_HEAD_DISCRETE_LOGP);
         fh.target = sample;
+        fh.tc = tc;
         rc = mq_tc_launch(net, theta, x, row_idx, batch, &fh, 0, out, logp, nullptr, 0, nullptr, stream);
         if (rc != MQ_ERR_UNSUPPORTED) return rc;
     }
@@ -982,6 +985,12 @@ extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const f
               batch, out, sample, logp);
     MQ_CHECK_LAUNCH("mq_fused_forward");
     return MQ_OK;
+}
+
+extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x,
+                                const int32_t *row_idx, int64_t batch, float *out, const float *sample,
+                                float *logp, void *stream) {
+    return mq_fused_forward_tc(net, theta, x, row_idx, batch, out, sample, logp, 0, stream);
 }
 
 extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x,

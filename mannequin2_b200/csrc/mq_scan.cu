@@ -260,7 +260,7 @@ struct DiscStage {
 
 // per-chunk descriptor: status 0 = empty, 1 = map of the chunk alone, 2 = value leaving the chunk
 template <typename T> struct ScanTile { T a, b, y; int status; int pad; };
-template <> struct __align__(16) ScanTile<float> { float a, b, y; int status; };
+template <> struct __align__(16) ScanTile<float> { float a; int tag_a; float y; int tag_y; };   // {a, tag}, {b or y, tag}
 
 __device__ __forceinline__ int scan_ld_acquire(const int *p) {
     int v;
@@ -271,17 +271,31 @@ __device__ __forceinline__ void scan_st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// A float descriptor {a, b, y, status} is ONE aligned 16-byte word: it is published with a single 128-bit store and read
-// with a single 128-bit load, so data and status travel together and no fence / release-acquire pair is needed
-// (the double descriptor of `discounted` is 32 bytes and keeps the release / acquire protocol).
+// A float descriptor is TWO aligned 8-byte words, each carrying its own copy of the status: {a, status} and {b or y, status}.
+// An aligned 8-byte scalar access is single-copy atomic in the PTX memory model (a 16-byte .v4 access is four scalar
+// accesses and may tear), so a word and its tag always travel together and no fence / release-acquire pair is needed:
+// status 2 only needs the second word (the value leaving the chunk); status 1 is accepted when BOTH words carry tag 1 --
+// the map (a, b) is published exactly once per chunk and launch, so two tag-1 words belong to the same publication.
+// (The double descriptor of `discounted` is 32 bytes and keeps the release / acquire protocol.)
+__device__ __forceinline__ void scan_st64(void *p, float v, int tag) {
+    const unsigned long long w = ((unsigned long long)(unsigned)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long scan_ld64(const void *p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
 __device__ __forceinline__ void scan_tile_store(ScanTile<float> *t, float a, float b, float y, int status) {
-    asm volatile("st.volatile.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(t), "r"(__float_as_int(a)), "r"(__float_as_int(b)),
-                 "r"(__float_as_int(y)), "r"(status) : "memory");
+    if (status == 1) scan_st64(&t->a, a, 1);
+    scan_st64(&t->y, status == 1 ? b : y, status);
 }
 __device__ __forceinline__ void scan_tile_load(const ScanTile<float> *t, float &a, float &b, float &y, int &status) {
-    int ia, ib, iy;
-    asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ia), "=r"(ib), "=r"(iy), "=r"(status) : "l"(t) : "memory");
-    a = __int_as_float(ia); b = __int_as_float(ib); y = __int_as_float(iy);
+    const unsigned long long w1 = scan_ld64(&t->a), w2 = scan_ld64(&t->y);
+    const int s1 = (int)(w1 >> 32), s2 = (int)(w2 >> 32);
+    a = __uint_as_float((unsigned)w1);
+    b = y = __uint_as_float((unsigned)w2);
+    status = (s2 == 2) ? 2 : ((s2 == 1 && s1 == 1) ? 1 : 0);
 }
 __device__ __forceinline__ void scan_tile_store(ScanTile<double> *t, double a, double b, double y, int status) {
     t->a = a; t->b = b; t->y = y;

@@ -16,7 +16,7 @@
 //       store is atomic: no flags, no fences, one one-way NVLink trip.
 //   push (0): plain floats into every peer's slot, one st.release.sys flag per peer, ld.acquire.sys spin, local reads.
 //   pull (1): local store + fence, flags, remote loads of every peer's slot.
-#include "mq_common.cuh"
+#include "mq_tc3.cuh"
 
 #ifndef MQ_EMU
 
@@ -55,7 +55,7 @@ template <typename ST, bool ADAMS>
 __global__ void __launch_bounds__(MQ_NT)
 reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float scale, ST *__restrict__ value,
                    ST *__restrict__ m, ST *__restrict__ v, float *__restrict__ theta_out, float *__restrict__ grad_out,
-                   ST c1, ST c2, ST lr, ST eps, mq_peer_t peer) {
+                   ST c1, ST c2, ST lr, ST eps, mq_peer_t peer, T3Img img, unsigned char *__restrict__ image) {
     __shared__ float part[8][33];
     const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + jx;
@@ -150,13 +150,16 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
     step_elem<ADAMS>(a, b, c, (ST)g, c1, c2, lr, eps);
     value[j] = a; m[j] = b; v[j] = c;
     if (theta_out) theta_out[j] = (float)a;
+    // the operand image of the tensor-core gradient kernel follows theta: the next launch copies it, converts nothing
+    if (image) t3_img_store_param_rt(img, image, j, (float)a);
 }
 
 extern "C" int64_t mq_step_blocks(int64_t n) { return mq_ceil_div(n, 32); }
 
-extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
-                              void *v, float *theta_out, float *grad_out, int state_dtype, double c1, double c2,
-                              double lr, double eps, int adams, const mq_peer_t *peer, void *stream) {
+extern "C" int mq_reduce_step_image(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
+                                    void *v, float *theta_out, float *grad_out, int state_dtype, double c1, double c2,
+                                    double lr, double eps, int adams, const mq_peer_t *peer, const mq_net_t *net,
+                                    int32_t tc, void *image, void *stream) {
     MQ_REQUIRE(partials && value && m && v, MQ_ERR_INVALID, "mq_reduce_step: null pointer");
     MQ_REQUIRE(n_parts >= 1 && n >= 1 && n < (1LL << 31), MQ_ERR_SHAPE, "mq_reduce_step: sizes");
     mq_peer_t pr;
@@ -168,12 +171,19 @@ extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n,
                        pr.buf_stride >= n && pr.step != 0,
                    MQ_ERR_INVALID, "mq_reduce_step: bad peer descriptor");
     }
+    T3Img img;
+    memset(&img, 0, sizeof(img));
+    if (image) {
+        const int planes = (tc & MQ_TC_PLANES_MASK) ? (tc & MQ_TC_PLANES_MASK) : 3;
+        MQ_REQUIRE(net && net->n_params == n && t3_img_build_layout(net, planes, &img), MQ_ERR_INVALID,
+                   "mq_reduce_step_image: the net does not match the parameter vector or does not fit the tensor-core kernel");
+    }
     const unsigned blocks = (unsigned)mq_ceil_div(n, 32);
 #define MQ_STEP_GO(ST, A)                                                                                      \
     do {                                                                                                       \
         cudaError_t e_ = mq_launch_pdl(reduce_step_kernel<ST, A>, dim3(blocks), dim3(MQ_NT), 0, stream, partials,    \
                                        (int)n_parts, (int)n, scale, (ST *)value, (ST *)m, (ST *)v, theta_out,       \
-                                       grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr);                              \
+                                       grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr, img, (unsigned char *)image); \
         if (e_ != cudaSuccess) { mq_set_error("mq_reduce_step: %s", cudaGetErrorString(e_)); return MQ_ERR_CUDA; }   \
     } while (0)
     if (state_dtype == MQ_F32) { if (adams) MQ_STEP_GO(float, true); else MQ_STEP_GO(float, false); }
@@ -184,8 +194,46 @@ extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n,
     return MQ_OK;
 }
 
+extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
+                              void *v, float *theta_out, float *grad_out, int state_dtype, double c1, double c2,
+                              double lr, double eps, int adams, const mq_peer_t *peer, void *stream) {
+    return mq_reduce_step_image(partials, n_parts, n, scale, value, m, v, theta_out, grad_out, state_dtype, c1, c2, lr, eps,
+                                adams, peer, nullptr, 0, nullptr, stream);
+}
+
 #else   // MQ_EMU
 extern "C" int64_t mq_step_blocks(int64_t n) { return mq_ceil_div(n, 32); }
 extern "C" int mq_reduce_step(const float *, int32_t, int64_t, float, void *, void *, void *, float *, float *, int, double,
                               double, double, double, int, const mq_peer_t *, void *) { return MQ_ERR_UNSUPPORTED; }
+extern "C" int mq_reduce_step_image(const float *, int32_t, int64_t, float, void *, void *, void *, float *, float *, int,
+                                    double, double, double, double, int, const mq_peer_t *, const mq_net_t *, int32_t, void *,
+                                    void *) { return MQ_ERR_UNSUPPORTED; }
 #endif
+
+// ---- a block of dependent optimiser steps issued by ONE call ------------------------------------------------------------
+// benchmarks/ppo.py:29-40 / benchmarks/gae.py:71-73 at large minibatches: per step one gradient launch (per-CTA partials)
+// and one reduce / exchange / Adam launch.  The loop lives here so that a 160-step epoch block costs one trip through
+// the Python binding instead of 320 (at 8,192 rows per GPU a step is ~25 us of GPU time: the host has to keep ahead).
+// coefs_host = [n_steps][2] running-mean coefficients (c1, c2) of mannequin/_normalize.py:18-25; peer (nullable) carries the
+// tag of the FIRST step, later steps count up; image (nullable): operand image kept in step with theta (mq_tc3.cuh).
+extern "C" int mq_train_steps(const mq_net_t *net, float *theta, const float *x, const mq_head_t *head,
+                              const int32_t *idx_table, int32_t n_steps, int64_t mb, float scale, void *value, void *m,
+                              void *v, int state_dtype, const double *coefs_host, double lr, double eps, int adams,
+                              const mq_peer_t *peer, void *ws, int64_t ws_bytes, void *stream) {
+    MQ_REQUIRE(net && theta && x && head && idx_table && coefs_host && ws, MQ_ERR_INVALID, "mq_train_steps: null pointer");
+    MQ_REQUIRE(n_steps >= 0 && mb >= 1, MQ_ERR_SHAPE, "mq_train_steps: sizes");
+    mq_peer_t pr;
+    if (peer) pr = *peer;
+    for (int s = 0; s < n_steps; ++s) {
+        int32_t n_parts = 0;
+        int rc = mq_fused_grad_partials(net, theta, x, idx_table + (int64_t)s * mb, mb, head, nullptr, nullptr, ws, ws_bytes,
+                                        &n_parts, stream);
+        if (rc != MQ_OK) return rc;
+        if (peer) pr.step = peer->step + (uint32_t)s;
+        rc = mq_reduce_step_image(ws == nullptr ? nullptr : (const float *)ws, n_parts, net->n_params, scale, value, m, v, theta,
+                                  nullptr, state_dtype, coefs_host[2 * s], coefs_host[2 * s + 1], lr, eps, adams,
+                                  peer ? &pr : nullptr, head->tc_image ? net : nullptr, head->tc, (void *)head->tc_image, stream);
+        if (rc != MQ_OK) return rc;
+    }
+    return MQ_OK;
+}

@@ -948,26 +948,27 @@ static int tc_plan_build(const mq_net_t *net, int64_t batch, int with_grad, cons
 }
 
 long long *mq_phase_prof_ptr();
-static int g_tc_mode = 1;            // 0: never, 1: automatic (large batches), 2: whenever the net fits
-extern "C" int mq_debug_set_tc_mode(int mode) { g_tc_mode = mode; return MQ_OK; }
-static int g_tc_variant = 1;         // 1: one 128-row tile per SM (this file), 0: two 64-row tiles in flight (mq_tc2.cu)
-extern "C" int mq_debug_set_tc_variant(int v) { g_tc_variant = v; return MQ_OK; }
-int mq_tc2_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx, int64_t batch,
-                  const mq_head_t *head, int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes,
-                  int *parts_out, void *stream);
+int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
+                  int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream);
 
-// Launches the tensor-core kernel when the net fits and the batch is large enough.
+// Launches a tensor-core kernel when the net fits and the batch is large enough (or head->tc says MQ_TC_FORCE).
+// Calls that carry packed records (head->records) go to the record-fed kernel of mq_tc3.cu, which also implements the
+// reduced-precision modes; calls with separate arrays keep this file's kernel (exact mode only).
 // Returns MQ_ERR_UNSUPPORTED (without an error message side effect that matters) otherwise.
 // with_grad: partials go to ws ([grid][n_params]); *grid_out = CTAs launched.
 int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                  int64_t batch, const mq_head_t *head, int with_grad, float *out, float *logp,
                  void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
-    if (g_tc_mode == 0) return MQ_ERR_UNSUPPORTED;
-    if (g_tc_mode == 1 && batch < 8192) return MQ_ERR_UNSUPPORTED;
-    if (g_tc_variant == 0) {
-        const int rc2 = mq_tc2_launch(net, theta, x, row_idx, batch, head, with_grad, out, logp, ws, ws_bytes, grid_out, stream);
-        if (rc2 != MQ_ERR_UNSUPPORTED) return rc2;
+    const int32_t tc = head->tc;
+    if (tc & MQ_TC_OFF) return MQ_ERR_UNSUPPORTED;
+    if (!(tc & MQ_TC_FORCE) && batch < 8192) return MQ_ERR_UNSUPPORTED;
+    if (head->records && with_grad) {
+        const int rc3 = mq_tc3_launch(net, row_idx, batch, head, theta, with_grad, out, logp, ws, ws_bytes, grid_out, stream);
+        if (rc3 != MQ_ERR_UNSUPPORTED) return rc3;
     }
+    const int planes = tc & MQ_TC_PLANES_MASK;
+    MQ_REQUIRE(planes == 0 || planes == 3, MQ_ERR_INVALID,
+               "mq_tc_launch: the reduced-precision tensor-core modes need packed records (mq_pack_records)");
     TcPlan p;
     if (!tc_plan_build(net, batch, with_grad, head, &p)) return MQ_ERR_UNSUPPORTED;
     const int64_t ntiles = mq_ceil_div(batch, p.tile_rows);
@@ -1002,8 +1003,7 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
 // Population evaluation on the tensor pipe (mq_es_eval dispatches here); MQ_ERR_UNSUPPORTED if the net does not fit.
 int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
                     int64_t n_obs, const float *ret_coef, float *returns, void *stream) {
-    if (g_tc_mode == 0) return MQ_ERR_UNSUPPORTED;
-    if (g_tc_mode == 1 && n_obs < 256) return MQ_ERR_UNSUPPORTED;
+    if (n_obs < 256) return MQ_ERR_UNSUPPORTED;
     if (net->logstd_off >= 0) return MQ_ERR_UNSUPPORTED;
     TcPlan p;
     if (!tc_plan_build(net, n_obs, 0, nullptr, &p)) return MQ_ERR_UNSUPPORTED;
@@ -1036,6 +1036,4 @@ int mq_tc_launch(const mq_net_t *, const float *, const float *, const int32_t *
                  float *, float *, void *, int64_t, int *, void *) { return MQ_ERR_UNSUPPORTED; }
 int mq_tc_es_launch(const mq_net_t *, const float *, const float *, int64_t, const float *, int64_t, const float *, float *,
                     void *) { return MQ_ERR_UNSUPPORTED; }
-extern "C" int mq_debug_set_tc_mode(int) { return MQ_OK; }
-extern "C" int mq_debug_set_tc_variant(int) { return MQ_OK; }
 #endif

@@ -1,0 +1,987 @@
+// Tensor-core (tcgen05 / TMEM) fused forward + head + backward for small MLPs at LARGE batch, third generation.
+//
+// Same reference sequence as mq_fused.cu / mq_tc.cu, for a whole minibatch in one launch:
+//   gather                mannequin/_trajectory.py:79-86 (traj.o[idx], traj.a[idx], traj.r[idx]), benchmarks/ppo.py:30-33
+//   Function.evaluate     mannequin/basicnet.py:192-207
+//   head                  benchmarks/gae.py:22, benchmarks/ppo.py:34-37, mannequin/distrib.py:24-32,61-68
+//   backprop              mannequin/basicnet.py:209-257 + mannequin/backprop.py:11-60
+//
+// What is new against mq_tc.cu (which stays for calls that pass separate arrays and for the forward-only passes):
+//   * PRECISION MODES (template P = bf16 planes per operand, selected per call through mq_head_t.tc): 3 planes = exact
+//     fp32 products (six plane pairs), 2 planes = 16 mantissa bits (three pairs), 1 plane = plain bf16 (one pair, MUFU
+//     tanh).  The tolerances are stated in include/mq_b200.h and asserted by tests/kernel_cases.py: case_tc_modes.
+//   * TWO TILES IN FLIGHT per SM (template NS = 2, for P <= 2 where two 128-row tiles fit in shared memory): the 16
+//     worker warps are two groups of 8, each group owns a tile SLOT (its own operand buffers and Z / dA columns in
+//     TMEM); the issuer warp alternates between the slots, so one slot's products run under the other slot's
+//     epilogue.  Hand-offs are mbarriers only (workers -> issuer: one arrive per warp; tensor pipe -> workers:
+//     tcgen05.commit), there is no CTA-wide barrier inside a tile.  Both slots accumulate dW / db into the SAME TMEM
+//     accumulators (MMAs execute in issue order, one issuing thread: bit-reproducible).
+//   * PACKED RECORDS: a minibatch row is ONE aligned record x | target | w0 | w1 (mq_pack_records; 64 bytes = two
+//     sectors for the 11-obs / 3-act policy) fetched with 128-bit loads one tile ahead, instead of four gathers of 44 + 12
+//     + 4 + 4 bytes at sector granularity.
+//   * OPERAND IMAGE: the bf16 planes of the weights, the biases and the Gaussian head parameters arrive as ONE bulk
+//     copy (cp.async.bulk on the TMA engine, completion counted on an mbarrier) of an image kept up to date by the
+//     optimiser-step kernel (mq_tc3.cuh), instead of being converted from theta by every CTA of every launch.
+//   * the fp32 activations for the backward pass are rebuilt from their planes in shared memory (no TMEM copy).
+#include "mq_tc3.cuh"
+
+#ifndef MQ_EMU
+
+#define HALF_LOG_2PI 0.91893853320467274178f
+#define T3_NT 512                // worker threads (16 warps)
+#define T3_NTI 544               // + the issuer warp
+#define T3_ROWS 128
+#define T3_CB 2048               // one 8-feature chunk of all 128 rows (128 rows x 16 B)
+#define T3_FLUSH_TILES 4         // tiles accumulated in TMEM before the dW accumulators are folded into memory (the tensor
+                                 // pipe truncates when it adds into its accumulator: mq_gemm_tc.cu)
+#define T3_MAXLD 2               // 128-bit record loads per thread and tile
+
+struct T3Plan {
+    mq_net_t net;
+    T3Img img;
+    int L, tile_rows, with_grad;
+    int rec_w, q4, hin_w;
+    // byte offsets inside a slot (slot s starts at s * slot_bytes); act[l]: planes P-1 .. 0, then the ones chunk
+    int off_dzl, dzl_plane, off_act[T3_MAXL], act_plane[T3_MAXL], off_hin, slot_bytes;
+    int off_const, smem_bytes;
+    // TMEM columns
+    int col_za[2], col_acc[T3_MAXL], col_rb;
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void t3_ld16_nowait(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void t3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void t3_mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void t3_mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// generic-proxy shared-memory writes and TMEM reads of this warp are done: tell the issuer (one arrive per warp)
+__device__ __forceinline__ void t3_warp_ready(uint32_t mbar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) t3_mbar_arrive(mbar);
+}
+__device__ __forceinline__ float4 t3_ldg128(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float t3_tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- plane arithmetic ----------------------------------------------------------------------------------------
+// two values -> P words of packed bf16 pairs (low half = a), w[0] + w[1] + .. = the values (exact for P = 3)
+template <int P>
+__device__ __forceinline__ void t3_split_pair(float a, float b, uint32_t *w) {
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[pl] = *reinterpret_cast<const uint32_t *>(&h);
+        if (pl + 1 < P) {
+            a -= __uint_as_float(w[pl] << 16);
+            b -= __uint_as_float(w[pl] & 0xFFFF0000u);
+        }
+    }
+}
+
+// address of (chunk, row) in plane 0 of a buffer whose planes are stored P-1 .. 0
+template <int P, int CB>
+__device__ __forceinline__ unsigned char *t3_chunk_ptr(unsigned char *buf, int plane_bytes, int chunk, int row) {
+    return buf + (P - 1) * plane_bytes + chunk * CB + (row >> 3) * 128 + (row & 7) * 16;
+}
+
+// 8 consecutive features of one row -> one 16-byte chunk in each plane
+template <int P, int CB>
+__device__ __forceinline__ void t3_store_chunk(unsigned char *buf, int plane_bytes, int chunk, int row, const float *v) {
+    uint32_t w[4][P];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t3_split_pair<P>(v[2 * j], v[2 * j + 1], w[j]);
+    unsigned char *q = t3_chunk_ptr<P, CB>(buf, plane_bytes, chunk, row);
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl)
+        *reinterpret_cast<uint4 *>(q - pl * plane_bytes) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+}
+
+// the value the planes represent (exact fp32 for P = 3, the rounded operand otherwise)
+template <int P, int CB>
+__device__ __forceinline__ void t3_load_chunk(unsigned char *buf, int plane_bytes, int chunk, int row, float *v) {
+    const unsigned char *q = t3_chunk_ptr<P, CB>(buf, plane_bytes, chunk, row);
+    uint4 w[P];
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) w[pl] = *reinterpret_cast<const uint4 *>(q - pl * plane_bytes);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+            const uint32_t x = j == 0 ? w[pl].x : (j == 1 ? w[pl].y : (j == 2 ? w[pl].z : w[pl].w));
+            lo = pl == 0 ? __uint_as_float(x << 16) : lo + __uint_as_float(x << 16);
+            hi = pl == 0 ? __uint_as_float(x & 0xFFFF0000u) : hi + __uint_as_float(x & 0xFFFF0000u);
+        }
+        v[2 * j] = lo;
+        v[2 * j + 1] = hi;
+    }
+}
+
+template <int P, int ACT>
+__device__ __forceinline__ float t3_act(float z, float leak) {
+    if (ACT == MQ_ACT_TANH) {
+        if (P == 1) return t3_tanh_fast(z);             // MUFU.TANH: 2^-11, the size of a bf16 rounding
+        if (P == 2) {                                   // 1 - 2 / (2^(2 log2(e) |z|) + 1): ~1.2e-7 ABSOLUTE (no small-|z| branch),
+            float t, r;                                 // well inside the 16-bit operands of this mode
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.8853900817779268f));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+            return copysignf(fmaf(r, -2.0f, 1.0f), z);
+        }
+        return tc_tanh(z);
+    }
+    return z < 0.0f ? z * leak : z;
+}
+
+// ---- MMA issue helpers (elected lane of the issuer warp, warp-uniform control flow) ---------------------------------
+// activation plane at `addr` viewed K-major (M = rows, K = features)
+__device__ __forceinline__ TcView t3_rows_k(uint32_t addr, uint32_t cb) {
+    return TcView{tc_desc_lo(addr, cb), tc_desc_hi(128u), (2u * cb) >> 4};
+}
+// activation buffer from `addr` on viewed MN-major (M or N = features, planes side by side; K = rows)
+__device__ __forceinline__ TcView t3_feat_mn(uint32_t addr, uint32_t cb) {
+    return TcView{tc_desc_lo(addr, 128u), tc_desc_hi(cb), 256u >> 4};
+}
+
+// D[128 x (NB blocks of nb)] = sum over plane pairs i + j < P of A_i B_j.  A: row-major planes (plane 0 at a0_addr, plane i
+// i * a_plane bytes BELOW it); B: an image whose planes 0, 1, .. sit side by side along N (b_plane16 = stride >> 4).
+template <int P>
+__device__ __forceinline__ void t3_rows_product(uint32_t d_tmem, uint32_t a0_addr, uint32_t a_plane, uint32_t cb, const TcView &b,
+                                                int b_mn, uint32_t b_plane16, int nb, int ksteps) {
+    const TcView a0 = t3_rows_k(a0_addr, cb);
+    const uint32_t ap16 = a_plane >> 4;
+    const uint32_t id2 = tc_idesc(T3_ROWS, 2 * nb, 0, b_mn);
+    const uint32_t id1 = tc_idesc(T3_ROWS, nb, 0, b_mn);
+    uint32_t alo = a0.lo, blo = b.lo;
+#pragma unroll 1
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t acc = k > 0 ? 1u : 0u;
+        if (P == 1) {
+            tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id1, acc);                              // A_0 x B_0
+        } else if (P == 2) {
+            tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id2, acc);                              // A_0 x [B_0|B_1]
+            tc_mma(d_tmem, alo - ap16, a0.hi, blo, b.hi, id1, 1u);                        // A_1 x B_0
+        } else {
+            tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id2, acc);                              // A_0 x [B_0|B_1]
+            tc_mma(d_tmem, alo - ap16, a0.hi, blo, b.hi, id2, 1u);                        // A_1 x [B_0|B_1]
+            tc_mma(d_tmem, alo, a0.hi, blo + 2 * b_plane16, b.hi, id1, 1u);               // A_0 x B_2
+            tc_mma(d_tmem, alo - 2 * ap16, a0.hi, blo, b.hi, id1, 1u);                    // A_2 x B_0
+        }
+        alo += a0.k16;
+        blo += b.k16;
+    }
+}
+
+// acc[64 x (NB blocks of nb, + extra)] (+)= sum over plane pairs of Da_i^T Db_j over the rows of the tile.  Da, Db:
+// activation buffers (planes P-1 .. 0 in memory, buffer start at *_base); Da's features are M, Db's planes side by side
+// (+ `extra` columns behind plane 0: the ones chunk) are N.  Column blocks for P >= 2: [Db_1 | Db_0 | extra].
+template <int P>
+__device__ __forceinline__ void t3_feat_product(uint32_t acc_tmem, uint32_t da_base, uint32_t da_plane, uint32_t db_base,
+                                                uint32_t db_plane, uint32_t cb, int nb, int extra, int ksteps, bool accumulate) {
+    const TcView a = t3_feat_mn(da_base, cb), b = t3_feat_mn(db_base, cb);
+    const uint32_t ap16 = da_plane >> 4, bp16 = db_plane >> 4;
+    const uint32_t id_all = tc_idesc(64, 2 * nb + extra, 1, 1), id_one = tc_idesc(64, nb + extra, 1, 1), id_blk = tc_idesc(64, nb, 1, 1);
+    uint32_t alo = a.lo, blo = b.lo;
+#pragma unroll 1
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
+        if (P == 1) {
+            tc_mma(acc_tmem, alo, a.hi, blo, b.hi, id_one, acc);                                        // Da_0 x [Db_0|e]
+        } else if (P == 2) {
+            tc_mma(acc_tmem, alo + ap16, a.hi, blo, b.hi, id_all, acc);                                 // Da_0 x [Db_1|Db_0|e]
+            tc_mma(acc_tmem + nb, alo, a.hi, blo + bp16, b.hi, id_one, 1u);                             // Da_1 x [Db_0|e]
+        } else {
+            tc_mma(acc_tmem, alo + 2 * ap16, a.hi, blo + bp16, b.hi, id_all, acc);                      // Da_0 x [Db_1|Db_0|e]
+            tc_mma(acc_tmem, alo + ap16, a.hi, blo + bp16, b.hi, id_all, 1u);                           // Da_1 x [Db_1|Db_0|e]
+            tc_mma(acc_tmem + nb, alo, a.hi, blo + 2 * bp16, b.hi, id_one, 1u);                         // Da_2 x [Db_0|e]
+            tc_mma(acc_tmem, alo + 2 * ap16, a.hi, blo, b.hi, id_blk, 1u);                              // Da_0 x Db_2
+        }
+        alo += a.k16;
+        blo += b.k16;
+    }
+}
+
+// forward weight image [k chunk][plane][n][8 k] of P planes from `addr` on, K-major (N = plane * np + n, K = in)
+template <int P>
+__device__ __forceinline__ TcView t3_wf_k(uint32_t addr, int np) {
+    return TcView{tc_desc_lo(addr, (uint32_t)P * (uint32_t)np * 16u), tc_desc_hi(128u), (2u * (uint32_t)P * (uint32_t)np * 16u) >> 4};
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------
+template <int P, int NS, int HR, int K0, int HACT>
+__global__ void __launch_bounds__(T3_NTI, 1)
+tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *__restrict__ rec,
+                const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
+                float *__restrict__ partial, float *__restrict__ out, float *__restrict__ logp_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[2], s_dw[2], s_ready[2], s_img;
+    // HR = 1 (two slots only): a slot is 64 rows.  Its products are still M = 128 instructions -- slot 0's rows are rows 0-63
+    // of the instruction (TMEM lanes 0-63, warps of lane quarters 0 and 1), slot 1's are rows 64-127 (operand base moved back
+    // by 64 rows; lane quarters 2 and 3); the other half of each instruction reads neighbouring shared memory and writes
+    // TMEM lanes nobody reads.  Half of the tensor work is wasted, but the tensor pipe is idle most of the time anyway,
+    // all 32 lanes of every warp own a row, and two exact three-plane tiles fit in shared memory.
+    constexpr int ROWS = HR ? 64 : T3_ROWS;   // rows of a slot
+    constexpr int CB = ROWS * 16;             // one 8-feature chunk of all rows of a slot
+    constexpr int GT = T3_NT / NS;            // threads of a slot group
+    constexpr int GW = GT / 32;               // warps of a slot group
+    constexpr int TPR = HR ? GW / 2 : GW / 4; // threads per tile row
+    constexpr int CPT = T3_HID / TPR;         // hidden columns per thread
+    constexpr int DPT = T3_NO / TPR;          // dZ columns of the output layer per thread
+    constexpr int NB = P > 1 ? 2 : 1;         // column blocks the epilogue adds
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const bool worker = warp < T3_NT / 32;
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int slot = !worker ? 0 : (HR ? quarter >> 1 : warp / GW);
+    const int cgi = HR ? warp >> 2 : (warp - slot * GW) >> 2;        // which CPT of the 64 columns this thread owns
+    const int row = HR ? (quarter & 1) * 32 + lane : quarter * 32 + lane;      // row of the slot's tile (TMEM lane = quarter * 32 + lane)
+    const int gtid = HR ? ((warp >> 2) * 2 + (quarter & 1)) * 32 + lane : tid - slot * GT;   // index within the slot group
+    const int L = p.L;
+    const int n_in = p.net.n_in, n_out = p.net.n_out;
+
+    // ---- one-time setup (on-chip work that overlaps the tail of the previous kernel: PDL) ----------------------
+    mq_pdl_trigger();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { t3_mbar_init(&s_full[s], 1); t3_mbar_init(&s_dw[s], 1); t3_mbar_init(&s_ready[s], GW); }
+        t3_mbar_init(&s_img, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    // clear the slots except the hidden activation buffers (every tile rewrites all of their rows)
+    if (worker) {
+        for (int s = 0; s < NS; ++s) {
+            uint4 *z = reinterpret_cast<uint4 *>(smem + s * p.slot_bytes);
+            for (int i = tid; i < p.off_act[1] / 16; i += T3_NT) z[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    if (worker) {
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+        const uint32_t ob = *reinterpret_cast<const uint16_t *>(&one);
+        for (int s = 0; s < NS; ++s)
+            for (int l = 0; l < L; ++l) {
+                uint32_t *ones = reinterpret_cast<uint32_t *>(smem + s * p.slot_bytes + p.off_act[l] + P * p.act_plane[l]);
+                for (int i = tid; i < CB / 4; i += T3_NT) ones[i] = ob | (ob << 16);
+            }
+    }
+    const uint32_t sbase = tc_smem_u32(smem);
+    const uint32_t img_bar = tc_smem_u32(&s_img);
+    mq_pdl_wait();                        // the predecessor's writes (image, records) are complete and visible
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(img_bar), "r"((uint32_t)p.img.bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sbase + p.off_const), "l"(image), "r"((uint32_t)p.img.bytes), "r"(img_bar) : "memory");
+    }
+    const float *sBias = reinterpret_cast<const float *>(smem + p.off_const + p.img.off_bias);      // [L][64]
+    const float *sMisc = reinterpret_cast<const float *>(smem + p.off_const + p.img.off_misc);      // logstd[16], exp(-logstd)[16]
+    unsigned char *sl = smem + slot * p.slot_bytes;                                                 // this group's slot
+    float *sHin = reinterpret_cast<float *>(sl + p.off_hin);                                        // [128][hin_w]
+    const int tr = p.tile_rows;
+    const int64_t ntiles = (n_rows + tr - 1) / tr;
+    const int dw_ksteps = tr / 16;
+    const bool gauss = mq_head_gauss(head.kind), prob = mq_head_prob(head.kind);
+    const int lastact = p.net.act[L - 1];
+    const float lastleak = p.net.leak[L - 1];
+    const int jobs = p.with_grad ? 2 * L : L;
+    // tiles of this CTA: ordinal i is tile blockIdx.x + i * gridDim.x; slot s takes the ordinals i % NS == s
+    const int n_i = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    tc_publish();                                       // zeroed buffers / ones chunks visible to the tensor pipe, TMEM address
+    const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
+    tc_wait(img_bar, 0);                                // weights, biases, head parameters have landed
+
+    if (!worker) {
+        // ---- issuer warp ---------------------------------------------------------------------------------------
+        uint32_t rdy_par[2] = {0u, 0u};
+        for (int i0 = 0; i0 < n_i; i0 += T3_FLUSH_TILES) {
+            const int i1 = i0 + T3_FLUSH_TILES < n_i ? i0 + T3_FLUSH_TILES : n_i;
+            int cnt[2];
+            cnt[0] = (i1 - i0 + NS - 1) / NS;
+            cnt[1] = NS == 2 ? (i1 - i0) / 2 : 0;
+            bool acc_started[T3_MAXL] = {false, false, false};
+            bool rb_started = false;                                            // the ones-row product
+            for (int k = 0; k < cnt[0] * jobs; ++k) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    if (k >= cnt[s] * jobs) continue;
+                    const int job = k % jobs;
+                    const uint32_t sb = sbase + s * p.slot_bytes;
+                    const uint32_t ash = (HR && s == 1) ? 1024u : 0u;       // row-major operands of slot 1 start 64 rows back
+                    const uint32_t za = tm + p.col_za[s];
+                    const uint32_t full = tc_smem_u32(&s_full[s]), dwb = tc_smem_u32(&s_dw[s]);
+                    tc_wait(tc_smem_u32(&s_ready[s]), rdy_par[s]); rdy_par[s] ^= 1u;
+                    if (tc_elect_one()) {
+                        if (job < L) {
+                            const int l = job;
+                            t3_rows_product<P>(za, sb + p.off_act[l] + (P - 1) * p.act_plane[l] - ash, p.act_plane[l], CB,
+                                               t3_wf_k<P>(sbase + p.off_const + p.img.off_wf[l], p.img.np[l]), 0, (uint32_t)p.img.np[l],
+                                               p.img.np[l], p.img.kp[l] / 16);
+                            tc_commit(full);
+                        } else {
+                            const int l = 2 * L - 1 - job;
+                            if (l == L - 1) {
+                                // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
+                                t3_rows_product<P>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane - ash, p.dzl_plane, CB,
+                                                   tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
+                                                   (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], 1);
+                                tc_commit(full);             // dA alone: the epilogue's arithmetic runs under the dW products
+                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l], p.act_plane[l], sb + p.off_dzl,
+                                                   p.dzl_plane, CB, T3_NO, 0, dw_ksteps, acc_started[l]);
+                                acc_started[l] = true;
+                                const TcView ones = t3_feat_mn(sb + p.off_act[l] + P * p.act_plane[l], CB);
+                                const TcView dzl = t3_feat_mn(sb + p.off_dzl, CB);
+                                const uint32_t dzp16 = (uint32_t)p.dzl_plane >> 4;
+                                uint32_t alo = ones.lo, blo = dzl.lo;
+#pragma unroll 1
+                                for (int kk = 0; kk < dw_ksteps; ++kk) {     // rows 0-7 of the result: column sums of the dZ planes
+                                    const uint32_t acc = (rb_started || kk > 0) ? 1u : 0u;
+                                    if (P == 1) {
+                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, T3_NO, 1, 1), acc);
+                                    } else if (P == 2) {
+                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, 2 * T3_NO, 1, 1), acc);
+                                    } else {
+                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo + dzp16, dzl.hi, tc_idesc(64, 2 * T3_NO, 1, 1), acc);
+                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, T3_NO, 1, 1), 1u);
+                                    }
+                                    alo += ones.k16;
+                                    blo += dzl.k16;
+                                }
+                                rb_started = true;
+                                tc_commit(dwb);
+                            } else {
+                                // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
+                                if (l > 0) {
+                                    t3_rows_product<P>(za, sb + p.off_act[l + 1] + (P - 1) * p.act_plane[l + 1] - ash, p.act_plane[l + 1], CB,
+                                                       tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
+                                                       (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], p.img.np[l] / 16);
+                                    tc_commit(full);
+                                }
+                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l + 1], p.act_plane[l + 1], sb + p.off_act[l],
+                                                   p.act_plane[l], CB, p.img.kp[l], 8, dw_ksteps, acc_started[l]);
+                                acc_started[l] = true;
+                                tc_commit(l == 0 ? full : dwb);  // l == 0 has no dA: its dW product is the phase
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (p.with_grad) {
+                // flush: the workers fold the accumulators into memory between these two barriers
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                __syncthreads();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+        }
+    } else {
+        // ---- worker warps -----------------------------------------------------------------------------------
+        const uint32_t full = tc_smem_u32(&s_full[slot]), dwb = tc_smem_u32(&s_dw[slot]), rdy = tc_smem_u32(&s_ready[slot]);
+        uint32_t par_full = 0u, par_dw = 0u;
+        const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t za = tlane + p.col_za[slot];
+        const bool wlive = row - lane < tr;             // this warp owns rows of the tile
+        // gather bookkeeping: this thread's (row, 128-bit word) items of a tile
+        int item_rq[T3_MAXLD];
+#pragma unroll
+        for (int j = 0; j < T3_MAXLD; ++j) {
+            const int item = gtid + j * GT;
+            const int r = item / p.q4, q = item - r * p.q4;
+            item_rq[j] = r < ROWS ? ((r << 8) | q) : -1;
+        }
+        int cur_idx[T3_MAXLD];
+        float4 recs[T3_MAXLD];
+        auto fetch_idx = [&](int ord) {                 // source row (or -1) of this thread's items of tile ordinal `ord`
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)ord * gridDim.x;
+#pragma unroll
+            for (int j = 0; j < T3_MAXLD; ++j) {
+                int v = -1;
+                if (item_rq[j] >= 0 && ord < n_i) {
+                    const int r = item_rq[j] >> 8;
+                    const int64_t gr = tile * tr + r;
+                    if (r < tr && gr < n_rows) v = idx ? tc_ldg_s32(idx + gr) : (int)gr;
+                }
+                cur_idx[j] = v;
+            }
+        };
+        auto load_recs = [&]() {
+#pragma unroll
+            for (int j = 0; j < T3_MAXLD; ++j) {
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (cur_idx[j] >= 0) v = t3_ldg128(rec + (int64_t)cur_idx[j] * p.rec_w + 4 * (item_rq[j] & 255));
+                recs[j] = v;
+            }
+        };
+        unsigned char *xbuf = sl + p.off_act[0];
+        auto stage = [&]() {                            // records -> X operand planes and head inputs
+#pragma unroll
+            for (int j = 0; j < T3_MAXLD; ++j) {
+                if (item_rq[j] < 0) continue;
+                const int r = item_rq[j] >> 8, e0 = 4 * (item_rq[j] & 255);
+                const float v[4] = {recs[j].x, recs[j].y, recs[j].z, recs[j].w};
+                if (e0 + 3 < n_in) {
+                    uint32_t w0[P], w1[P];
+                    t3_split_pair<P>(v[0], v[1], w0);
+                    t3_split_pair<P>(v[2], v[3], w1);
+                    unsigned char *d = t3_chunk_ptr<P, CB>(xbuf, p.act_plane[0], e0 >> 3, r) + (e0 & 7) * 2;
+#pragma unroll
+                    for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2 *>(d - pl * p.act_plane[0]) = make_uint2(w0[pl], w1[pl]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int f = e0 + e;
+                        if (f < n_in) {
+                            uint32_t w[P];
+                            t3_split_pair<P>(v[e], 0.0f, w);
+                            unsigned char *d = t3_chunk_ptr<P, CB>(xbuf, p.act_plane[0], f >> 3, r) + (f & 7) * 2;
+#pragma unroll
+                            for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint16_t *>(d - pl * p.act_plane[0]) = (uint16_t)(w[pl] & 0xFFFFu);
+                        } else if (f - n_in < p.hin_w) {
+                            sHin[r * p.hin_w + f - n_in] = v[e];
+                        }
+                    }
+                }
+            }
+        };
+
+        bool pending = false;                           // a committed dW_0 product nobody waited for yet
+        bool flushed = false;
+        auto flush_grad = [&]() {
+            // TMEM accumulators -> this CTA's partial gradient (set on the first flush, added afterwards).  M = 64
+            // accumulators: row i is lane i % 16 of the warps of quarter i / 16; the four warps of a quarter split the columns
+            float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
+            const bool add = flushed;
+            const int cg4 = warp >> 2;
+            const int i = quarter * 16 + lane;
+            const bool lv = lane < 16;
+            for (int l = 0; l < L; ++l) {
+                const int in = p.net.in[l], on = p.net.out[l];
+                const int nb = (l == L - 1) ? T3_NO : p.img.kp[l];
+                for (int c0 = cg4 * 16; c0 < nb; c0 += 64) {
+                    float v0[16], v1[16];
+                    t3_ld16_nowait(tlane + p.col_acc[l] + c0, v0);
+                    if (NB == 2) t3_ld16_nowait(tlane + p.col_acc[l] + nb + c0, v1);
+                    t3_ld_wait();
+                    if (!lv) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // l < L-1: acc[o][k] = dW_l[k][o]; last layer: acc[k][o]
+                        const bool ok = (l < L - 1) ? (i < on && c0 + j < in) : (i < in && c0 + j < on);
+                        if (!ok) continue;
+                        float *q = dst + p.net.w_off[l] + ((l < L - 1) ? (c0 + j) * on + i : i * on + c0 + j);
+                        const float val = NB == 2 ? v0[j] + v1[j] : v0[j];
+                        *q = add ? *q + val : val;
+                    }
+                }
+                if (l < L - 1 && cg4 == 1) {    // the ones column behind the blocks
+                    float v[16];
+                    t3_ld16_nowait(tlane + p.col_acc[l] + NB * nb - 8, v);
+                    t3_ld_wait();
+                    if (lv && i < on) { float *q = dst + p.net.b_off[l] + i; *q = add ? *q + v[8] : v[8]; }
+                }
+            }
+            if (cg4 == 2 && quarter == 0) {     // last layer: row 0 of the ones product = column sums of dZ
+                float v0[16], v1[16];
+                t3_ld16_nowait(tlane + p.col_rb, v0);
+                if (NB == 2) t3_ld16_nowait(tlane + p.col_rb + T3_NO, v1);
+                t3_ld_wait();
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float sv = NB == 2 ? v0[j] + v1[j] : v0[j];
+                        if (j < n_out) { float *q = dst + p.net.b_off[L - 1] + j; *q = add ? *q + sv : sv; }
+                        if (p.net.logstd_off >= 0 && j >= 8 && j < 8 + n_out) {
+                            float *q = dst + p.net.logstd_off + j - 8;
+                            *q = !gauss ? 0.0f : (add ? *q + sv : sv);
+                        }
+                    }
+                }
+            }
+            flushed = true;
+        };
+
+        fetch_idx(slot);
+        load_recs();
+        fetch_idx(slot + NS);
+        for (int i0 = 0; i0 < n_i; i0 += T3_FLUSH_TILES) {
+            const int i1 = i0 + T3_FLUSH_TILES < n_i ? i0 + T3_FLUSH_TILES : n_i;
+            for (int ord = i0 + slot; ord < i1; ord += NS) {
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)ord * gridDim.x;
+                const int64_t gr = tile * tr + row;
+                const bool rvalid = row < tr && gr < n_rows;
+                if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
+                // ---- stage the input tile --------------------------------------------------------------------
+                stage();
+                t3_warp_ready(rdy, lane);
+                // ---- forward -----------------------------------------------------------------------------------
+                for (int l = 0; l < L - 1; ++l) {
+                    if (l == L - 2) {
+                        // records of this slot's NEXT tile and the source rows of the one after: issued here so that they
+                        // have the remaining phases of this tile to arrive
+                        load_recs();
+                        fetch_idx(ord + 2 * NS);
+                    }
+                    tc_wait(full, par_full); par_full ^= 1u;
+                    if (wlive) {
+                        // A_{l+1} = act(Z_l + b_l) as bf16 planes
+                        const float leak = p.net.leak[l];
+                        unsigned char *abuf = sl + p.off_act[l + 1];
+#pragma unroll
+                        for (int h = 0; h < CPT / 16; ++h) {
+                            const int c0 = cgi * CPT + 16 * h;
+                            float v[16], v2[16];
+                            t3_ld16_nowait(za + c0, v);
+                            if (NB == 2) t3_ld16_nowait(za + T3_HID + c0, v2);
+                            t3_ld_wait();
+                            const float4 *b4 = reinterpret_cast<const float4 *>(sBias + l * 64 + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 bb = b4[j];
+                                v[4 * j + 0] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 0] + v2[4 * j + 0] : v[4 * j + 0]) + bb.x, leak);
+                                v[4 * j + 1] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 1] + v2[4 * j + 1] : v[4 * j + 1]) + bb.y, leak);
+                                v[4 * j + 2] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 2] + v2[4 * j + 2] : v[4 * j + 2]) + bb.z, leak);
+                                v[4 * j + 3] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 3] + v2[4 * j + 3] : v[4 * j + 3]) + bb.w, leak);
+                            }
+                            t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8, row, v);
+                            t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8 + 1, row, v + 8);
+                        }
+                    }
+                    t3_warp_ready(rdy, lane);
+                }
+                // ---- head: loss-gradient rule on the output row.  All TPR threads of a row evaluate it (inputs come
+                // from shared memory) and each splits / stores its own DPT of the 16 dZ columns.
+                tc_wait(full, par_full); par_full ^= 1u;
+                if (wlive) {
+                    float y[T3_NO], dz[T3_NO];
+                    {
+                        float y2[T3_NO];
+                        t3_ld16_nowait(za, y);
+                        if (NB == 2) t3_ld16_nowait(za + T3_NO, y2);
+                        t3_ld_wait();
+                        const float *b = sBias + (L - 1) * 64;
+#pragma unroll
+                        for (int n = 0; n < T3_NO; ++n) {
+                            y[n] = (n < n_out) ? mq_act_apply((NB == 2 ? y[n] + y2[n] : y[n]) + b[n], lastact, lastleak) : 0.0f;
+                            dz[n] = 0.0f;
+                        }
+                    }
+                    float tgt[T3_NO];
+                    {
+                        const float4 *h4 = reinterpret_cast<const float4 *>(sHin + row * p.hin_w);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (4 * q < p.hin_w) t = h4[q];
+                            tgt[4 * q] = t.x; tgt[4 * q + 1] = t.y; tgt[4 * q + 2] = t.z; tgt[4 * q + 3] = t.w;
+                        }
+                    }
+                    const float h_adv = sHin[row * p.hin_w + n_out], h_lpold = sHin[row * p.hin_w + n_out + 1];
+                    if (rvalid && out && cgi == 0) {
+#pragma unroll
+                        for (int n = 0; n < T3_NO; ++n) if (n < n_out) out[gr * n_out + n] = y[n];
+                    }
+                    if (rvalid) {
+                        if (head.kind == MQ_HEAD_DY) {
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) if (n < n_out) dz[n] = mq_act_grad(y[n], tgt[n], lastact, lastleak);
+                        } else if (head.kind == MQ_HEAD_DIFF) {
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) if (n < n_out) dz[n] = mq_act_grad(y[n], tgt[n] - y[n], lastact, lastleak);
+                        } else if (head.kind == MQ_HEAD_SOFTMAX_CE) {
+                            float mx = y[0];
+#pragma unroll
+                            for (int n = 1; n < T3_NO; ++n) if (n < n_out) mx = fmaxf(mx, y[n]);
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) if (n < n_out) sum += expf(y[n] - mx);
+                            const float inv = 1.0f / sum;
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n)
+                                if (n < n_out) dz[n] = mq_act_grad(y[n], tgt[n] - expf(y[n] - mx) * inv - head.p0 * y[n], lastact, lastleak);
+                        } else if (mq_head_discrete(head.kind)) {
+                            // categorical log-prob (distrib.py:24-32): the target row is the one-hot action
+                            float mx = y[0];
+#pragma unroll
+                            for (int n = 1; n < T3_NO; ++n) if (n < n_out) mx = fmaxf(mx, y[n]);
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) if (n < n_out) sum += expf(y[n] - mx);
+                            const float lse = mx + logf(sum);
+                            float lp = 0.0f;
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) if (n < n_out) lp += tgt[n] * (y[n] - lse);
+                            if (logp_out && cgi == TPR - 1) logp_out[gr] = lp;
+                            float w;
+                            if (head.kind == MQ_HEAD_DISCRETE_PPO) {
+                                const float ratio = expf(lp - h_lpold);
+                                const bool kill = (ratio > head.p1 && h_adv > 0.0f) || (ratio < head.p0 && h_adv < 0.0f);
+                                w = kill ? 0.0f : ratio * h_adv;
+                            } else {
+                                w = h_adv;
+                            }
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n)
+                                if (n < n_out) dz[n] = mq_act_grad(y[n], w * (tgt[n] - expf(y[n] - lse)), lastact, lastleak);
+                        } else if (gauss) {
+                            // diagonal Gaussian (distrib.py:61-68): n_out <= 8; columns 8.. carry the logstd terms
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int a = 0; a < 8; ++a)
+                                if (a < n_out) {
+                                    const float z = (tgt[a] - y[a]) * sMisc[16 + a];
+                                    acc += sMisc[a] + 0.5f * z * z;
+                                }
+                            const float lp = -(float)n_out * HALF_LOG_2PI - acc;
+                            if (logp_out && cgi == TPR - 1) logp_out[gr] = lp;
+                            float w;
+                            if (head.kind == MQ_HEAD_GAUSS_PPO) {
+                                const float ratio = expf(lp - h_lpold);
+                                const bool kill = (ratio > head.p1 && h_adv > 0.0f) || (ratio < head.p0 && h_adv < 0.0f);
+                                w = kill ? 0.0f : ratio * h_adv;
+                            } else {
+                                w = h_adv;
+                            }
+#pragma unroll
+                            for (int a = 0; a < 8; ++a)
+                                if (a < n_out) {
+                                    const float inv = sMisc[16 + a];
+                                    const float z = (tgt[a] - y[a]) * inv;
+                                    dz[8 + a] = w * (z * z - 1.0f) + head.ent;
+                                    dz[a] = mq_act_grad(y[a], w * z * inv, lastact, lastleak);
+                                }
+                        }
+                    }
+                    if (p.with_grad) {
+                        float sv[DPT];
+#pragma unroll
+                        for (int k = 0; k < DPT; ++k) sv[k] = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < TPR; ++q)
+                            if (cgi == q) {
+#pragma unroll
+                                for (int k = 0; k < DPT; ++k) sv[k] = dz[DPT * q + k];
+                            }
+                        unsigned char *dbuf = sl + p.off_dzl;
+                        if (DPT == 8) {
+                            t3_store_chunk<P, CB>(dbuf, p.dzl_plane, cgi, row, sv);
+                        } else {
+                            uint32_t wa[P], wb[P];
+                            t3_split_pair<P>(sv[0], sv[1], wa);
+                            t3_split_pair<P>(sv[2], sv[3], wb);
+                            unsigned char *d = t3_chunk_ptr<P, CB>(dbuf, p.dzl_plane, cgi >> 1, row) + (cgi & 1) * 8;
+#pragma unroll
+                            for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2 *>(d - pl * p.dzl_plane) = make_uint2(wa[pl], wb[pl]);
+                        }
+                    }
+                }
+                if (!p.with_grad) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    continue;
+                }
+                t3_warp_ready(rdy, lane);
+                // ---- backward ----------------------------------------------------------------------------------
+                for (int l = L - 1; l >= 1; --l) {
+                    tc_wait(full, par_full); par_full ^= 1u;
+                    // dZ_{l-1} = dA_l * act'(A_l), written over A_l.  Only dA_l has been waited for: the arithmetic and
+                    // the split into planes run while the tensor pipe still works on dW_l / db_l, which READ A_l -- so the
+                    // stores wait for the second barrier.
+                    uint32_t w[CPT / 8][4][P];
+                    unsigned char *abuf = sl + p.off_act[l];
+                    if (wlive) {
+                        const float leak = p.net.leak[l - 1];
+#pragma unroll
+                        for (int h = 0; h < CPT / 16; ++h) {
+                            const int c0 = cgi * CPT + 16 * h;
+                            float a[16], g[16], g2[16];
+                            t3_ld16_nowait(za + c0, g);
+                            if (NB == 2) t3_ld16_nowait(za + T3_HID + c0, g2);
+                            t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8, row, a);
+                            t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8 + 1, row, a + 8);
+                            t3_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], NB == 2 ? g[j] + g2[j] : g[j], HACT, leak);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) t3_split_pair<P>(g[8 * c + 2 * j], g[8 * c + 2 * j + 1], w[2 * h + c][j]);
+                        }
+                    }
+                    tc_wait(dwb, par_dw); par_dw ^= 1u;
+                    if (wlive) {
+#pragma unroll
+                        for (int c = 0; c < CPT / 8; ++c) {
+                            unsigned char *d = t3_chunk_ptr<P, CB>(abuf, p.act_plane[l], cgi * (CPT / 8) + c, row);
+#pragma unroll
+                            for (int pl = 0; pl < P; ++pl)
+                                *reinterpret_cast<uint4 *>(d - pl * p.act_plane[l]) = make_uint4(w[c][0][pl], w[c][1][pl], w[c][2][pl], w[c][3][pl]);
+                        }
+                    }
+                    t3_warp_ready(rdy, lane);
+                }
+                pending = true;                         // dW_0 is in flight
+            }
+            if (p.with_grad) {
+                if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                flush_grad();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+            }
+        }
+        if (p.with_grad && !flushed) {                  // a CTA without tiles still owns a partial vector
+            float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
+            for (int j = tid; j < p.net.n_params; j += T3_NT) dst[j] = 0.0f;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
+}
+
+// ---- operand image and records ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MQ_NT)
+tc3_image_kernel(T3Img g, const float *__restrict__ theta, unsigned char *__restrict__ image) {
+    const int j = blockIdx.x * MQ_NT + threadIdx.x;
+    if (j < g.n_params) t3_img_store_param_rt(g, image, j, theta[j]);
+}
+
+// rec[r] = x[r, :n_in] | tgt[r, :n_out] | w0[r] | w1[r] | 0 ...   (one thread per 128-bit word of a record)
+__global__ void __launch_bounds__(MQ_NT)
+pack_records_kernel(const float *__restrict__ x, const float *__restrict__ tgt, const float *__restrict__ w0,
+                    const float *__restrict__ w1, int64_t rows, int n_in, int n_out, int rec_w, float *__restrict__ rec) {
+    const int q4 = rec_w / 4;
+    const int64_t item = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
+    if (item >= rows * q4) return;
+    const int64_t r = item / q4;
+    const int q = (int)(item - r * q4);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int f = 4 * q + e;
+        float val = 0.0f;
+        if (f < n_in) val = x[r * n_in + f];
+        else if (f < n_in + n_out) val = tgt ? tgt[r * n_out + f - n_in] : 0.0f;
+        else if (f == n_in + n_out) val = w0 ? w0[r] : 0.0f;
+        else if (f == n_in + n_out + 1) val = w1 ? w1[r] : 0.0f;
+        v[e] = val;
+    }
+    reinterpret_cast<float4 *>(rec)[item] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+static int t3_planes(int32_t tc) { const int pl = tc & MQ_TC_PLANES_MASK; return pl == 0 ? 3 : pl; }
+
+extern "C" int32_t mq_record_width(const mq_net_t *net) {
+    if (!net) return 0;
+    return (int32_t)mq_round_up(net->n_in + net->n_out + 2, 16);
+}
+
+// rows = 128: one (ns = 1) or two (ns = 2) 128-row slots; rows = 64: two 64-row slots (kernel template HR = 1)
+static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int rows, int ns, T3Plan *p) {
+    memset(p, 0, sizeof(*p));
+    p->net = *net;
+    if (!t3_img_build_layout(net, planes, &p->img)) return 0;
+    const int L = net->n_layers, k0 = p->img.k0;
+    const int cb = rows * 16;
+    p->L = L;
+    p->with_grad = with_grad;
+    p->rec_w = rec_w; p->q4 = rec_w / 4;
+    if (rec_w != mq_record_width(net) || rec_w > 64) return 0;
+    if (rows == 64 && ns != 2) return 0;
+    if (ns == 2 && k0 != 16) return 0;
+    if (rows * p->q4 > T3_MAXLD * (T3_NT / ns)) return 0;     // every thread's record words fit its registers
+    p->hin_w = (int)mq_round_up(net->n_out + 2, 4);
+    // per-slot layout: [dzl][act0 + ones][hin] cleared once, then [act1 + ones][act2 + ones]
+    int off = 0;
+    p->dzl_plane = 2 * cb;
+    p->off_dzl = off; off += planes * p->dzl_plane;
+    p->act_plane[0] = (k0 / 8) * cb;
+    p->off_act[0] = off; off += planes * p->act_plane[0] + cb;
+    p->off_hin = off; off += rows * p->hin_w * 4;
+    off = (int)mq_round_up(off, 1024);
+    for (int l = 1; l < L; ++l) {
+        p->act_plane[l] = (T3_HID / 8) * cb;
+        p->off_act[l] = off; off += planes * p->act_plane[l] + cb;
+    }
+    p->slot_bytes = (int)mq_round_up(off, 1024);
+    const int64_t limit = mq_smem_optin() - 256;         // static shared memory: TMEM address + seven mbarriers
+    p->off_const = ns * p->slot_bytes;
+    // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] of the last slot on, and a
+    // 64-row slot's M = 128 products read one chunk past their operand
+    int total = p->off_const + p->img.bytes;
+    const int need = (ns - 1) * p->slot_bytes + p->off_act[L - 1] + planes * p->act_plane[L - 1] + 9 * cb;
+    if (total < need) total = need;
+    p->smem_bytes = (int)mq_round_up(total, 16);
+    if (p->smem_bytes > limit) return 0;
+    // TMEM columns: Z / dA of each slot (NB blocks of 64), then the shared dW / db accumulators
+    const int nbk = planes > 1 ? 2 : 1;
+    int col = 0;
+    for (int s = 0; s < ns; ++s) { p->col_za[s] = col; col += nbk * T3_HID; }
+    for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8; }
+    p->col_rb = col; col += nbk * T3_NO;
+    if (col > 512) return 0;
+    // balance: every tile slot of a full wave gets the same number of rows
+    const int64_t sms = mq_sm_count();
+    const int64_t waves = mq_ceil_div(batch, sms * ns * rows);
+    int64_t tr = mq_round_up(mq_ceil_div(batch, sms * ns * waves), 16);
+    if (tr > rows) tr = rows;
+    if (tr < 16) tr = 16;
+    p->tile_rows = (int)tr;
+    return 1;
+}
+
+// Chooses the schedule: two tiles in flight whenever they fit -- 128-row slots for one and two planes, 64-row slots for
+// the exact three-plane mode -- else one 128-row tile.  MQ_TC_HALF / MQ_TC_FULL (developer aids) force the slot size.
+static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, T3Plan *p, int *ns_out,
+                         int *half_out) {
+    const int planes = t3_planes(tc);
+    const int order_default[3][2] = {{128, 2}, {64, 2}, {128, 1}};
+    const int order_half[3][2] = {{64, 2}, {128, 2}, {128, 1}};
+    const int order_full[3][2] = {{128, 2}, {128, 1}, {128, 1}};
+    const int (*order)[2] = (tc & MQ_TC_HALF) ? order_half : ((tc & MQ_TC_FULL) ? order_full : order_default);
+    for (int k = 0; k < 3; ++k)
+        if (t3_plan_try(net, batch, with_grad, planes, rec_w, order[k][0], order[k][1], p)) {
+            *ns_out = order[k][1];
+            *half_out = order[k][0] == 64;
+            return 1;
+        }
+    return 0;
+}
+
+extern "C" int64_t mq_tc_image_bytes(const mq_net_t *net, int32_t tc) {
+    T3Img g;
+    if (!net || !t3_img_build_layout(net, t3_planes(tc), &g)) return 0;
+    return g.bytes;
+}
+
+static int t3_image_build(const T3Img &g, const float *theta, void *image, void *stream) {
+    cudaError_t e = cudaMemsetAsync(image, 0, (size_t)g.bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) { mq_set_error("mq_tc_image_build: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
+    MQ_LAUNCH(tc3_image_kernel, (unsigned)mq_ceil_div(g.n_params, MQ_NT), MQ_NT, 0, stream, g, theta, (unsigned char *)image);
+    MQ_CHECK_LAUNCH("mq_tc_image_build");
+    return MQ_OK;
+}
+
+extern "C" int mq_tc_image_build(const mq_net_t *net, const float *theta, int32_t tc, void *image, void *stream) {
+    MQ_REQUIRE(net && theta && image, MQ_ERR_INVALID, "mq_tc_image_build: null pointer");
+    MQ_REQUIRE(((uintptr_t)image & 15) == 0, MQ_ERR_INVALID, "mq_tc_image_build: image must be 16-byte aligned");
+    T3Img g;
+    MQ_REQUIRE(t3_img_build_layout(net, t3_planes(tc), &g), MQ_ERR_UNSUPPORTED, "mq_tc_image_build: net does not fit the tensor-core kernel");
+    return t3_image_build(g, theta, image, stream);
+}
+
+extern "C" int mq_pack_records(const mq_net_t *net, const float *x, const float *tgt, const float *w0, const float *w1,
+                               int64_t rows, float *rec, void *stream) {
+    MQ_REQUIRE(net && x && rec, MQ_ERR_INVALID, "mq_pack_records: null pointer");
+    MQ_REQUIRE(rows >= 0, MQ_ERR_SHAPE, "mq_pack_records: negative row count");
+    MQ_REQUIRE(((uintptr_t)rec & 15) == 0, MQ_ERR_INVALID, "mq_pack_records: records must be 16-byte aligned");
+    if (rows == 0) return MQ_OK;
+    const int rec_w = mq_record_width(net);
+    const int64_t items = rows * (rec_w / 4);
+    MQ_LAUNCH(pack_records_kernel, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, x, tgt, w0, w1, rows, net->n_in,
+              net->n_out, rec_w, rec);
+    MQ_CHECK_LAUNCH("mq_pack_records");
+    return MQ_OK;
+}
+
+// bytes mq_tc3_launch may use behind the partial gradients for an image it has to build itself
+int64_t mq_tc3_scratch_bytes() { return 96 * 1024; }
+
+// Launches the record-fed tensor-core gradient kernel.  MQ_ERR_UNSUPPORTED when the net does not fit.
+// Partials go to ws ([grid][n_params]); *grid_out = CTAs launched.
+int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
+                  int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
+    const int planes = t3_planes(head->tc);
+    T3Plan p;
+    int ns = 1, half = 0;
+    if (!t3_plan_build(net, batch, with_grad, head->tc, head->rec_w, &p, &ns, &half)) return MQ_ERR_UNSUPPORTED;
+    MQ_REQUIRE(((uintptr_t)head->records & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: records must be 16-byte aligned");
+    const int64_t ntiles = mq_ceil_div(batch, p.tile_rows);
+    const int64_t sms = mq_sm_count();
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const int64_t part_bytes = with_grad ? mq_round_up((int64_t)grid * net->n_params * (int64_t)sizeof(float), 256) : 0;
+    if (with_grad) MQ_REQUIRE(ws && ws_bytes >= part_bytes, MQ_ERR_INVALID, "mq_tc3_launch: workspace too small");
+    const void *image = head->tc_image;
+    if (!image) {
+        MQ_REQUIRE(theta && ws && ws_bytes >= part_bytes + p.img.bytes, MQ_ERR_INVALID,
+                   "mq_tc3_launch: no operand image and no room in the workspace to build one");
+        void *scratch = (char *)ws + part_bytes;
+        const int rc = t3_image_build(p.img, theta, scratch, stream);
+        if (rc != MQ_OK) return rc;
+        image = scratch;
+    }
+    MQ_REQUIRE(((uintptr_t)image & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: image must be 16-byte aligned");
+    cudaError_t e = cudaSuccess;
+#define T3_LAUNCH(P_, NS_, HR_, K0_, ACT_)                                                                                   \
+    do {                                                                                                                     \
+        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, HR_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
+        if (e == cudaSuccess)                                                                                                \
+            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, HR_, K0_, ACT_>, dim3(grid), dim3(T3_NTI), (size_t)p.smem_bytes, stream, p, \
+                              (const unsigned char *)image, head->records, row_idx, batch, *head, (float *)ws, out, logp);   \
+    } while (0)
+#define T3_LAUNCH_ACT(P_, NS_, HR_, K0_)                                          \
+    do {                                                                          \
+        if (net->act[0] == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, HR_, K0_, MQ_ACT_TANH); \
+        else T3_LAUNCH(P_, NS_, HR_, K0_, MQ_ACT_LRELU);                          \
+    } while (0)
+#define T3_LAUNCH_P(P_)                                              \
+    do {                                                             \
+        if (ns == 2 && half) T3_LAUNCH_ACT(P_, 2, 1, 16);            \
+        else if (ns == 2) T3_LAUNCH_ACT(P_, 2, 0, 16);               \
+        else if (p.img.k0 == 16) T3_LAUNCH_ACT(P_, 1, 0, 16);        \
+        else T3_LAUNCH_ACT(P_, 1, 0, 32);                            \
+    } while (0)
+    if (planes == 3) T3_LAUNCH_P(3);
+    else if (planes == 2) T3_LAUNCH_P(2);
+    else T3_LAUNCH_P(1);
+#undef T3_LAUNCH_P
+#undef T3_LAUNCH_ACT
+#undef T3_LAUNCH
+    if (e != cudaSuccess) {
+        mq_set_error("mq_tc3_launch: %s", cudaGetErrorString(e));
+        return MQ_ERR_CUDA;
+    }
+    MQ_CHECK_LAUNCH("mq_tc3_launch");
+    if (grid_out) *grid_out = grid;
+    return MQ_OK;
+}
+
+#else   // MQ_EMU: the host emulation has no tensor cores
+extern "C" int32_t mq_record_width(const mq_net_t *net) { return net ? (int32_t)mq_round_up(net->n_in + net->n_out + 2, 16) : 0; }
+extern "C" int64_t mq_tc_image_bytes(const mq_net_t *, int32_t) { return 0; }
+extern "C" int mq_tc_image_build(const mq_net_t *, const float *, int32_t, void *, void *) { return MQ_ERR_UNSUPPORTED; }
+extern "C" int mq_pack_records(const mq_net_t *, const float *, const float *, const float *, const float *, int64_t, float *,
+                               void *) { return MQ_ERR_UNSUPPORTED; }
+int64_t mq_tc3_scratch_bytes() { return 0; }
+int mq_tc3_launch(const mq_net_t *, const int32_t *, int64_t, const mq_head_t *, const float *, int, float *, float *, void *,
+                  int64_t, int *, void *) { return MQ_ERR_UNSUPPORTED; }
+#endif

@@ -26,7 +26,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, MqHead
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, TC_MODES, MqHead
 from ._normalize import RunningNormalize
 from .basicnet import normed_columns
 
@@ -49,13 +49,30 @@ CHAIN_MAX_MB = 256        # minibatches up to this size run inside the persisten
 class _Net(object):
     """Parameters + Adam state of one net, all device resident."""
 
-    def __init__(self, net, theta_host, horizon, state_dtype):
+    def __init__(self, net, theta_host, horizon, state_dtype, tc_mode="exact"):
         self.net = net
         self.theta = D.from_host(theta_host, np.float32)
         self.opt = Adam(theta_host, horizon=horizon, state_dtype=state_dtype)
         self.code = self.opt._code
         self.grad = D.zeros(net.n_params)
         self._peer = None
+        # tensor-core path of the large-minibatch steps (csrc/mq_tc3.cu): precision mode, packed records, operand image
+        self.planes = TC_MODES[tc_mode]
+        img_bytes = int(_lib.lib().mq_tc_image_bytes(ctypes.byref(net), self.planes))
+        self.image = torch.zeros(img_bytes, dtype=torch.uint8, device=D.device()) if img_bytes else None
+        self.rec_w = int(_lib.lib().mq_record_width(ctypes.byref(net)))
+        self.records = None
+
+    def pack(self, x, tgt, w0, w1, rows):
+        """One aligned record per transition (x | target | w0 | w1): the four gathers of benchmarks/ppo.py:30-37 become one."""
+        if self.image is None:
+            self.records = None
+            return
+        if self.records is None or self.records.numel() != rows * self.rec_w:
+            self.records = torch.empty(rows * self.rec_w, dtype=torch.float32, device=D.device())
+        D.call("mq_pack_records", ctypes.byref(self.net), D.ptr(x), D.ptr(tgt) if tgt is not None else None,
+               D.ptr(w0) if w0 is not None else None, D.ptr(w1) if w1 is not None else None, rows, D.ptr(self.records),
+               D.stream())
 
     def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8):
         """n_steps optimiser steps; idx_table is i32[n_steps, mb] (rows of THIS rank)."""
@@ -74,43 +91,61 @@ class _Net(object):
         self.opt._out = None
 
     # -- large minibatches: all SMs per step, one gradient exchange across GPUs ----------------
-    def _one_step(self, x, head, idx_ptr, mb, scale, ws, wsb, c1, c2, lr, eps):
-        value, m, v, _ = self.opt.state()
-        if self._peer is None:
-            self._peer = mqdist.PeerExchange(self.net.n_params)
-        if mqdist.world() == 1 or self._peer.available():
-            # 2 launches: gradient kernel (per-CTA partials), then ONE kernel that sums them in fixed order,
-            # all-reduces over NVLink peer memory when sharded, and applies Adam (csrc/mq_step.cu)
-            n_parts = ctypes.c_int32(0)
-            D.call("mq_fused_grad_partials", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), idx_ptr, mb,
-                   ctypes.byref(head), None, None, D.ptr(ws), wsb, ctypes.byref(n_parts), D.stream())
-            peer = ctypes.byref(self._peer.descriptor()) if mqdist.world() > 1 else None
-            D.call("mq_reduce_step", D.ptr(ws), n_parts.value, self.net.n_params, scale, D.ptr(value), D.ptr(m),
-                   D.ptr(v), D.ptr(self.theta), None, self.code, c1, c2, lr, eps, 0, peer, D.stream())
-            return
-        # fallback (no peer mapping): gradient, NCCL / gloo all-reduce, Adam
-        D.call("mq_fused_grad", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), idx_ptr, mb,
-               ctypes.byref(head), scale, D.ptr(self.grad), None, None, D.ptr(ws), wsb, D.stream())
-        mqdist.allreduce_sum_(self.grad)
-        D.call("mq_adam_step", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
-               self.net.n_params, self.code, MQ_F32, c1, c2, lr, eps, 0, D.stream())
-
     def _train_loop(self, x, head, idx_table, n_steps, mb, lr, eps):
         lib = _lib.lib()
         wsb = lib.mq_fused_ws_bytes(ctypes.byref(self.net), mb)
         ws = D.workspace(("fused", id(self)), wsb)
         scale = 1.0 / float(mb * mqdist.world())            # batch MEAN over the GLOBAL minibatch
-        coefs = [self.opt.next_coefs() for _ in range(n_steps)]
+        coefs = (ctypes.c_double * (2 * n_steps))()
+        for s in range(n_steps):
+            coefs[2 * s], coefs[2 * s + 1] = self.opt.next_coefs()
         self.opt._out = None
+        value, m, v, _ = self.opt.state()
+        if self._peer is None:
+            self._peer = mqdist.PeerExchange(self.net.n_params)
+        head.tc = (head.tc & ~3) | self.planes
+        if self.image is not None and self.records is not None and mb >= 8192:
+            # record-fed tensor-core kernel: its operand image is built once here and then follows theta step by step
+            head.records, head.rec_w, head.tc_image = D.ptr(self.records), self.rec_w, D.ptr(self.image)
+            D.call("mq_tc_image_build", ctypes.byref(self.net), D.ptr(self.theta), self.planes, D.ptr(self.image), D.stream())
+        else:
+            head.records, head.rec_w, head.tc_image = None, 0, None
+            head.tc = head.tc & ~3
+        if mqdist.world() == 1 or self._peer.available():
+            # per step 2 launches: gradient kernel (per-CTA partials), then ONE kernel that sums them in fixed order,
+            # all-reduces over NVLink peer memory when sharded, applies Adam and refreshes the operand image
+            # (csrc/mq_step.cu); the loop over steps runs inside the library
+            peer = None
+            if mqdist.world() > 1:
+                peer = ctypes.byref(self._peer.descriptor())
+                self._peer.step += n_steps - 1
+            D.call("mq_train_steps", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), ctypes.byref(head), D.ptr(idx_table),
+                   n_steps, mb, scale, D.ptr(value), D.ptr(m), D.ptr(v), self.code, coefs, lr, eps, 0, peer, D.ptr(ws), wsb,
+                   D.stream())
+            return
+        # fallback (no peer mapping): gradient, NCCL / gloo all-reduce, Adam
+        head.tc_image = None
         base, stride = D.ptr(idx_table), mb * 4
         for s in range(n_steps):
-            self._one_step(x, head, base + s * stride, mb, scale, ws, wsb, coefs[s][0], coefs[s][1], lr, eps)
+            D.call("mq_fused_grad", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), base + s * stride, mb,
+                   ctypes.byref(head), scale, D.ptr(self.grad), None, None, D.ptr(ws), wsb, D.stream())
+            mqdist.allreduce_sum_(self.grad)
+            D.call("mq_adam_step", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
+                   self.net.n_params, self.code, MQ_F32, coefs[2 * s], coefs[2 * s + 1], lr, eps, 0, D.stream())
+
+    def exchange(self):
+        """Which gradient exchange the sharded steps use: "ll" | "push" | "pull" (in-kernel, peer memory) or "nccl"."""
+        if mqdist.world() == 1:
+            return "none"
+        if self._peer is None:
+            self._peer = mqdist.PeerExchange(self.net.n_params)
+        return {2: "ll", 0: "push", 1: "pull"}[self._peer.pull] if self._peer.available() else "nccl"
 
 
 class PPOUpdater(object):
     def __init__(self, n_obs, n_act, *, hid=64, n_hid=2, gam=0.99, lam=0.95, pol_lr=3e-4, val_lr=3e-3,
                  horizon=10, clip=(0.8, 1.2), norm_horizon=2, state_dtype="float32",
-                 policy_params=None, value_params=None, discrete=False, ent_coef=0.0):
+                 policy_params=None, value_params=None, discrete=False, ent_coef=0.0, tc_mode="exact"):
         widths = [hid] * n_hid
         acts = [ACT_TANH] * n_hid + [ACT_NONE]
         # discrete=True: categorical policy over n_act actions (benchmarks/policy.py:15-17, distrib.Discrete);
@@ -130,8 +165,13 @@ class PPOUpdater(object):
         assert len(policy_params) == pnet.n_params and len(value_params) == vnet.n_params
         self.n_obs, self.n_act = n_obs, n_act
         self.gam, self.lam, self.pol_lr, self.val_lr, self.clip = gam, lam, pol_lr, val_lr, clip
-        self.policy = _Net(pnet, np.asarray(policy_params, np.float32), horizon, state_dtype)
-        self.value = _Net(vnet, np.asarray(value_params, np.float32), horizon, state_dtype)
+        # tc_mode: precision of the tensor-core gradient kernel that serves minibatches >= 8,192 rows: "exact" (three bf16
+        # planes, the fp32 bar of the FFMA kernels), "bf16x2" (|err| <= 3e-5 max|grad|) or "bf16" (<= 2e-2): north_star's
+        # "stated looser tolerance for bf16 tensor-core paths".  Smaller minibatches always run the fp32 FFMA kernels.
+        assert tc_mode in TC_MODES, tc_mode
+        self.tc_mode = tc_mode
+        self.policy = _Net(pnet, np.asarray(policy_params, np.float32), horizon, state_dtype, tc_mode)
+        self.value = _Net(vnet, np.asarray(value_params, np.float32), horizon, state_dtype, tc_mode)
         self.normalize = RunningNormalize(horizon=norm_horizon)
         self._side = torch.cuda.Stream()
         self._ev_gae, self._ev_val = torch.cuda.Event(), torch.cuda.Event()
@@ -172,9 +212,15 @@ class PPOUpdater(object):
         # 300-step chains are single-CTA kernels side by side.  Large minibatches: each gradient kernel fills the GPU,
         # but the small reduce / Adam kernels, the launch gaps and (sharded) the exchange latency of one chain run under
         # the gradient kernels of the other: +4 % on one GPU, +3 % on two.  MQ_PPO_SERIAL=1 forces one stream.
-        concurrent = not os.environ.get("MQ_PPO_SERIAL")
+        # Sharded (world > 1) the two chains share ONE stream: the step kernels spin on peer memory, and a spinning grid of one
+        # chain can keep the other chain's gradient kernel (52 K registers per CTA) from becoming resident; with the chains
+        # interleaved differently on two ranks neither would progress.  One stream = one fixed order on every rank.
+        concurrent = not os.environ.get("MQ_PPO_SERIAL") and mqdist.world() == 1
         vhead = MqHead()
         vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
+        big = val_idx.shape[1] >= 8192 or pol_idx.shape[1] >= 8192
+        if big:
+            val.pack(obs, ret, None, None, n)
         if concurrent:
             self._ev_gae.record(main)
             with torch.cuda.stream(self._side):              # value predictor chain (gae.py:66-73)
@@ -192,6 +238,8 @@ class PPOUpdater(object):
         head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
         head.ent = self.ent_coef
         head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
+        if big:
+            pol.pack(obs, act, adv_n, logp0, n)
         pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
         if concurrent:
             main.wait_event(self._ev_val)

@@ -48,11 +48,13 @@ def net_of(spec, logstd=False):
                       leak=[l["leak"] for l in Ls], logstd=logstd)
 
 
-def head(B, kind, p0=0.0, p1=0.0, dy=None, target=None, adv=None, logp_old=None):
+def head(B, kind, p0=0.0, p1=0.0, dy=None, target=None, adv=None, logp_old=None, tc=0, records=None, rec_w=0,
+         image=None):
     h = L.MqHead()
     h.kind, h.p0, h.p1 = kind, p0, p1
     h.dy, h.target, h.adv, h.logp_old = B.ptr(dy), B.ptr(target), B.ptr(adv), B.ptr(logp_old)
-    h._keep = (dy, target, adv, logp_old)
+    h.tc, h.records, h.rec_w, h.tc_image = tc, B.ptr(records), rec_w, B.ptr(image)
+    h._keep = (dy, target, adv, logp_old, records, image)
     return h
 
 
@@ -801,100 +803,254 @@ def case_rollout(B, n_env=300):
 
 
 def case_tc_paths(B):
-    """tcgen05 / TMEM kernels forced on (mode 2) for every net they accept -- the one-tile kernel with its issuer warp
-    (mq_tc.cu, the default) and the two-tiles-in-flight variant (mq_tc2.cu): the same fp32 bars as the FFMA kernels
-    (three-plane bf16 operands keep 24 mantissa bits)."""
-    for variant in (1, 0):
-        ok(B, B.lib.mq_debug_set_tc_variant(variant))
-        try:
-            _tc_paths(B)
-        finally:
-            B.lib.mq_debug_set_tc_variant(1)
-
-
-def _tc_paths(B):
+    """tcgen05 / TMEM kernel of mq_tc.cu (separate arrays, exact mode) forced on per call (MQ_TC_FORCE) for every net it
+    accepts: the same fp32 bars as the FFMA kernels (three-plane bf16 operands keep 24 mantissa bits)."""
     lib = B.lib
     rs = np.random.RandomState(15)
-    ok(B, lib.mq_debug_set_tc_mode(2))
-    try:
-        cases = [(11, [64, 64, 3], [1, 1, 0], 64), (11, [64, 64, 3], [1, 1, 0], 1000),
-                 (11, [64, 64, 1], [1, 1, 0], 40000), (20, [16, 16, 5], [2, 2, 0], 777),
-                 (6, [32, 10], [2, 0], 333), (17, [64, 48, 6], [1, 2, 1], 2500), (20, [48, 7], [1, 0], 1500)]
-        for n_in, widths, acts, batch in cases:
-            spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
-            net = net_of(spec)
-            n_out = widths[-1]
-            ht, hx = B.up(theta), B.up(x)
-            out = B.zeros((batch, n_out), np.float32)
-            ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(out), None, None, B.stream))
-            outs = O.mlp_forward(theta, spec, x)
-            close(B.down(out), outs[-1], what="tc fwd %s b=%d" % (widths, batch))
-            wsb = lib.mq_fused_ws_bytes(net, batch)
-            ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
-            dy = rs.randn(batch, n_out).astype(np.float32)
-            h = head(B, L.HEAD_DY, dy=B.up(dy))
-            out2 = B.zeros((batch, n_out), np.float32)
-            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
-                                    B.ptr(grad), B.ptr(out2), None, B.ptr(ws), wsb, B.stream))
-            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, dy), what="tc grad DY %s b=%d" % (widths, batch))
-            close(B.down(out2), outs[-1], what="tc grad out")
-            tgt = rs.randn(batch, n_out).astype(np.float32)
-            h = head(B, L.HEAD_DIFF, target=B.up(tgt))
+    F = L.TC_FORCE
+    cases = [(11, [64, 64, 3], [1, 1, 0], 64), (11, [64, 64, 3], [1, 1, 0], 1000),
+             (11, [64, 64, 1], [1, 1, 0], 40000), (20, [16, 16, 5], [2, 2, 0], 777),
+             (6, [32, 10], [2, 0], 333), (17, [64, 48, 6], [1, 2, 1], 2500), (20, [48, 7], [1, 0], 1500)]
+    for n_in, widths, acts, batch in cases:
+        spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
+        net = net_of(spec)
+        n_out = widths[-1]
+        ht, hx = B.up(theta), B.up(x)
+        out = B.zeros((batch, n_out), np.float32)
+        ok(B, lib.mq_fused_forward_tc(net, B.ptr(ht), B.ptr(hx), None, batch, B.ptr(out), None, None, F, B.stream))
+        outs = O.mlp_forward(theta, spec, x)
+        close(B.down(out), outs[-1], what="tc fwd %s b=%d" % (widths, batch))
+        wsb = lib.mq_fused_ws_bytes(net, batch)
+        ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
+        dy = rs.randn(batch, n_out).astype(np.float32)
+        h = head(B, L.HEAD_DY, dy=B.up(dy), tc=F)
+        out2 = B.zeros((batch, n_out), np.float32)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                B.ptr(grad), B.ptr(out2), None, B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), O.mlp_backward(theta, spec, x, outs, dy), what="tc grad DY %s b=%d" % (widths, batch))
+        close(B.down(out2), outs[-1], what="tc grad out")
+        tgt = rs.randn(batch, n_out).astype(np.float32)
+        h = head(B, L.HEAD_DIFF, target=B.up(tgt), tc=F)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
+                                B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), O.mlp_backward(theta, spec, x, outs, tgt - outs[-1]), what="tc grad DIFF %s" % (widths,))
+        if n_out >= 2 and acts[-1] == 0:
+            onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
+            h = head(B, L.HEAD_SOFTMAX_CE, p0=0.01, target=B.up(onehot), tc=F)
             ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
                                     B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
-            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, tgt - outs[-1]), what="tc grad DIFF %s" % (widths,))
-            if n_out >= 2 and acts[-1] == 0:
-                onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
-                h = head(B, L.HEAD_SOFTMAX_CE, p0=0.01, target=B.up(onehot))
+            close(B.down(grad), O.mlp_backward(theta, spec, x, outs, O.softmax_ce_grad(outs[-1], onehot)),
+                  what="tc grad CE %s" % (widths,))
+    # Gaussian policy: reference fixtures, then the PPO head with gathered rows
+    g = golden("gauss")
+    spec = O.policy_spec(11, 3)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    theta, obs, act, w = g["gauss_theta"], g["gauss_obs"], g["gauss_act"], g["gauss_g"]
+    ht, ho, ha, hw = B.up(theta), B.up(obs), B.up(act), B.up(w)
+    logp = B.zeros(64, np.float32)
+    ok(B, lib.mq_fused_forward_tc(net, B.ptr(ht), B.ptr(ho), None, 64, None, B.ptr(ha), B.ptr(logp), F, B.stream))
+    close(B.down(logp), g["gauss_logp"], what="tc logp vs reference")
+    wsb = lib.mq_fused_ws_bytes(net, 1 << 16)
+    ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
+    h = head(B, L.HEAD_GAUSS_LOGP, dy=hw, target=ha, tc=F)
+    logp2 = B.zeros(64, np.float32)
+    ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad), None,
+                            B.ptr(logp2), B.ptr(ws), wsb, B.stream))
+    close(B.down(grad), g["gauss_grad"], rtol=3e-5, atol_scale=3e-6, what="tc gauss grad vs reference")
+    close(B.down(logp2), g["gauss_logp"], what="tc grad logp vs reference")
+    n = 30000
+    o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+    a = rs.randn(n, 3).astype(np.float32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
+    ho, ha, hadv, hlp = B.up(o), B.up(a), B.up(adv), B.up(lp_old)
+    for mb in (64, 200, 20000):
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp, tc=F)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
+        lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
+        wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
+        close(B.down(grad), O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs), rtol=3e-5,
+              atol_scale=3e-6, what="tc ppo grad mb=%d" % mb)
+        # the tensor-core and the FFMA kernel agree with each other at the same bar
+        h2 = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp, tc=L.TC_OFF)
+        g2 = B.zeros(5126, np.float32)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h2), 1.0 / mb,
+                                B.ptr(g2), None, None, B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), B.down(g2), rtol=3e-5, atol_scale=3e-6, what="tc vs ffma mb=%d" % mb)
+    # evolution-strategies population on the tensor pipe (tc_es_kernel, >= 256 observations): several members per CTA,
+    # ragged last tile
+    case_es(B, members=200, n_obs=300)
+    case_es(B, members=9, n_obs=1000)
+
+
+# stated tolerances of the tensor-core precision modes (include/mq_b200.h): |err| <= rtol |ref| + atol_scale max|ref|
+TC_MODE_TOL = {3: (3e-5, 3e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}
+
+
+def pack_records(B, net, x, tgt=None, w0=None, w1=None):
+    rows = x.shape[0]
+    rec_w = B.lib.mq_record_width(net)
+    rec = B.zeros((rows, rec_w), np.float32)
+    keep = [B.up(x)] + [None if a is None else B.up(a) for a in (tgt, w0, w1)]
+    ok(B, B.lib.mq_pack_records(net, B.ptr(keep[0]), B.ptr(keep[1]), B.ptr(keep[2]), B.ptr(keep[3]), rows, B.ptr(rec),
+                                B.stream))
+    return rec, rec_w
+
+
+def case_tc_modes(B):
+    """Record-fed tensor-core gradient kernel (mq_tc3.cu) in its three precision modes -- 3 bf16 planes (exact products),
+    2 planes, 1 plane -- against the oracle, each at its STATED tolerance (include/mq_b200.h), for every head, ragged
+    batches, gathered rows, one and two hidden layers; packed records against the source arrays (bit-exact); operand
+    image built by the launch, built ahead (mq_tc_image_build) and refreshed by the optimiser step
+    (mq_reduce_step_image) are byte-identical."""
+    lib = B.lib
+    rs = np.random.RandomState(31)
+    F = L.TC_FORCE
+    measured = {}
+    # ---- records are a bit-exact repacking (mannequin/_trajectory.py:79-86 semantics: float32 rows)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    x = rs.randn(1000, 11).astype(np.float32); t = rs.randn(1000, 3).astype(np.float32)
+    a0 = rs.randn(1000).astype(np.float32); a1 = rs.randn(1000).astype(np.float32)
+    rec, rec_w = pack_records(B, net, x, t, a0, a1)
+    assert rec_w == 16
+    r = B.down(rec)
+    assert np.array_equal(r[:, :11], x) and np.array_equal(r[:, 11:14], t) and np.array_equal(r[:, 14], a0) \
+        and np.array_equal(r[:, 15], a1)
+    # ---- plain nets, heads DY / DIFF / SOFTMAX_CE
+    cases = [(11, [64, 64, 3], [1, 1, 0], 64), (11, [64, 64, 1], [1, 1, 0], 1000), (11, [64, 64, 1], [1, 1, 0], 40000),
+             (13, [16, 16, 5], [2, 2, 0], 777), (6, [32, 10], [2, 0], 333), (12, [48, 2], [1, 0], 1500),
+             (20, [64, 64, 4], [1, 1, 0], 3000)]
+    for n_in, widths, acts, batch in cases:
+        spec, theta, x = mlp_case(rs, n_in, widths, acts, batch)
+        net = net_of(spec)
+        n_out = widths[-1]
+        ht = B.up(theta)
+        outs = O.mlp_forward(theta, spec, x)
+        wsb = lib.mq_fused_ws_bytes(net, batch)
+        ws, grad = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32)
+        dy = rs.randn(batch, n_out).astype(np.float32)
+        tgt = rs.randn(batch, n_out).astype(np.float32)
+        onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
+        hx = B.up(x)
+        for planes in (3, 2, 1):
+            rtol, atol = TC_MODE_TOL[planes]
+            for kind, mat, dyo in ((L.HEAD_DY, dy, dy), (L.HEAD_DIFF, tgt, tgt - outs[-1]),
+                                   (L.HEAD_SOFTMAX_CE, onehot, None)):
+                if kind == L.HEAD_SOFTMAX_CE:
+                    if not (n_out >= 2 and acts[-1] == 0):
+                        continue
+                    dyo = O.softmax_ce_grad(outs[-1], onehot)
+                rec, rec_w = pack_records(B, net, x, mat)
+                hm = B.up(mat)
+                h = head(B, kind, p0=0.01 if kind == L.HEAD_SOFTMAX_CE else 0.0, dy=hm if kind == L.HEAD_DY else None,
+                         target=None if kind == L.HEAD_DY else hm, tc=F | planes, records=rec, rec_w=rec_w)
+                out2 = B.zeros((batch, n_out), np.float32)
                 ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(hx), None, batch, ctypes.byref(h), 1.0 / batch,
-                                        B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
-                close(B.down(grad), O.mlp_backward(theta, spec, x, outs, O.softmax_ce_grad(outs[-1], onehot)),
-                      what="tc grad CE %s" % (widths,))
-        # Gaussian policy: reference fixtures, then the PPO head with gathered rows
-        g = golden("gauss")
-        spec = O.policy_spec(11, 3)
-        net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
-        theta, obs, act, w = g["gauss_theta"], g["gauss_obs"], g["gauss_act"], g["gauss_g"]
-        ht, ho, ha, hw = B.up(theta), B.up(obs), B.up(act), B.up(w)
-        logp = B.zeros(64, np.float32)
-        ok(B, lib.mq_fused_forward(net, B.ptr(ht), B.ptr(ho), None, 64, None, B.ptr(ha), B.ptr(logp), B.stream))
-        close(B.down(logp), g["gauss_logp"], what="tc logp vs reference")
-        wsb = lib.mq_fused_ws_bytes(net, 1 << 16)
-        ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
-        h = head(B, L.HEAD_GAUSS_LOGP, dy=hw, target=ha)
-        logp2 = B.zeros(64, np.float32)
-        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), None, 64, ctypes.byref(h), 1.0 / 64, B.ptr(grad), None,
-                                B.ptr(logp2), B.ptr(ws), wsb, B.stream))
-        close(B.down(grad), g["gauss_grad"], rtol=3e-5, atol_scale=3e-6, what="tc gauss grad vs reference")
-        close(B.down(logp2), g["gauss_logp"], what="tc grad logp vs reference")
-        n = 30000
-        o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
-        a = rs.randn(n, 3).astype(np.float32)
-        adv = np.tanh(rs.randn(n)).astype(np.float32)
-        lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
-        ho, ha, hadv, hlp = B.up(o), B.up(a), B.up(adv), B.up(lp_old)
-        for mb in (64, 200, 20000):
-            idx = rs.randint(n, size=mb).astype(np.int32)
-            hi = B.up(idx)
-            h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp)
-            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
-                                    B.ptr(grad), None, None, B.ptr(ws), wsb, B.stream))
-            lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
-            wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
-            close(B.down(grad), O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs), rtol=3e-5,
-                  atol_scale=3e-6, what="tc ppo grad mb=%d" % mb)
-            # the tensor-core and the FFMA kernel agree with each other at the same bar
-            ok(B, lib.mq_debug_set_tc_mode(0))
-            g2 = B.zeros(5126, np.float32)
-            ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
-                                    B.ptr(g2), None, None, B.ptr(ws), wsb, B.stream))
-            ok(B, lib.mq_debug_set_tc_mode(2))
-            close(B.down(grad), B.down(g2), rtol=3e-5, atol_scale=3e-6, what="tc vs ffma mb=%d" % mb)
-        # evolution-strategies population on the tensor pipe (tc_es_kernel): several members per CTA, ragged last tile
-        case_es(B, members=200, n_obs=150)
-        case_es(B, members=9, n_obs=1000)
-    finally:
-        lib.mq_debug_set_tc_mode(1)
+                                        B.ptr(grad), B.ptr(out2), None, B.ptr(ws), wsb, B.stream))
+                want = O.mlp_backward(theta, spec, x, outs, dyo)
+                got = B.down(grad)
+                close(got, want, rtol=rtol, atol_scale=atol, what="tc3 P=%d kind=%d %s b=%d" % (planes, kind, widths, batch))
+                close(B.down(out2), outs[-1], rtol=rtol, atol_scale=atol, what="tc3 out P=%d" % planes)
+                e = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+                measured[planes] = max(measured.get(planes, 0.0), e)
+    # ---- Gaussian PPO head with gathered rows (the configs[2] step), categorical PPO head
+    spec = O.policy_spec(11, 3)
+    net = L.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
+    theta = golden("gauss")["gauss_theta"]
+    n = 70000
+    o = np.clip(rs.randn(n, 11), -5, 5).astype(np.float32)
+    a = rs.randn(n, 3).astype(np.float32)
+    adv = np.tanh(rs.randn(n)).astype(np.float32)
+    lp_old = (O.policy_logprob(theta, spec, o, a)[0] + rs.randn(n) * 0.2).astype(np.float32)
+    ht, ho, ha, hadv, hlp = B.up(theta), B.up(o), B.up(a), B.up(adv), B.up(lp_old)
+    rec, rec_w = pack_records(B, net, o, a, adv, lp_old)
+    wsb = lib.mq_fused_ws_bytes(net, 1 << 16)
+    ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
+    img_bytes = {pl: lib.mq_tc_image_bytes(net, pl) for pl in (1, 2, 3)}
+    assert 0 < img_bytes[1] < img_bytes[2] < img_bytes[3] <= 96 * 1024
+    for mb in (64, 200, 8192, 20000, 65536):
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        lp, outs = O.policy_logprob(theta, spec, o[idx], a[idx])
+        wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
+        assert (wgt == 0).any() and (wgt != 0).any()                       # both branches of the clip rule
+        want = O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs)
+        # reference point: the array-fed exact kernel
+        h0 = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp, tc=F)
+        g0 = B.zeros(5126, np.float32)
+        ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h0), 1.0 / mb, B.ptr(g0), None,
+                                None, B.ptr(ws), wsb, B.stream))
+        g0 = B.down(g0)
+        close(g0, want, rtol=3e-5, atol_scale=3e-6, what="array-fed tc ppo grad mb=%d vs oracle on all rows" % mb)
+        for planes in (3, 2, 1):
+            rtol, atol = TC_MODE_TOL[planes]
+            image = B.zeros(img_bytes[planes], np.uint8)
+            ok(B, lib.mq_tc_image_build(net, B.ptr(ht), planes, B.ptr(image), B.stream))
+            for img in (None, image):
+                h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp, tc=F | planes,
+                         records=rec, rec_w=rec_w, image=img)
+                lpo = B.zeros(mb, np.float32)
+                ok(B, lib.mq_fused_grad(net, B.ptr(ht), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), 1.0 / mb,
+                                        B.ptr(grad), None, B.ptr(lpo), B.ptr(ws), wsb, B.stream))
+                got = B.down(grad)
+                close(got, want, rtol=rtol, atol_scale=atol, what="tc3 ppo P=%d mb=%d img=%s" % (planes, mb, img is not None))
+                close(B.down(lpo), lp, rtol=rtol, atol_scale=max(atol, 3e-6), what="tc3 logp P=%d mb=%d" % (planes, mb))
+                if planes == 3:
+                    close(got, g0, rtol=3e-5, atol_scale=3e-6, what="tc3 exact vs array-fed kernel mb=%d" % mb)
+                e = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+                measured["ppo%d" % planes] = max(measured.get("ppo%d" % planes, 0.0), e)
+    # categorical policy (benchmarks/policy.py:15-17): one-hot targets
+    spec_d = O.mlp_spec(11, [64, 64, 4], [1, 1, 0])
+    net_d = net_of(spec_d)
+    theta_d = O.mlp_init(spec_d, rs, head_scale=0.1) + rs.randn(spec_d["n_params"]).astype(np.float32) * 0.05
+    acts_d = rs.randint(4, size=n)
+    onehot = np.eye(4, dtype=np.float32)[acts_d]
+    lpo_d = (O.discrete_logprob(O.mlp_forward(theta_d, spec_d, o)[-1], acts_d)[0] + rs.randn(n) * 0.2).astype(np.float32)
+    rec_d, rw_d = pack_records(B, net_d, o, onehot, adv, lpo_d)
+    htd, hoh, hlpd = B.up(theta_d), B.up(onehot), B.up(lpo_d)
+    gd = B.zeros(spec_d["n_params"], np.float32)
+    wsb_d = lib.mq_fused_ws_bytes(net_d, 1 << 16)
+    wsd = B.zeros(wsb_d, np.uint8)
+    idx = rs.randint(n, size=9000).astype(np.int32)
+    hi = B.up(idx)
+    outs_d = O.mlp_forward(theta_d, spec_d, o[idx])
+    lp_d = O.discrete_logprob(outs_d[-1], acts_d[idx])[0]
+    wgt = O.ppo_clip_weight(lp_d, lpo_d[idx], adv[idx])
+    want = O.discrete_logprob_grad(theta_d, spec_d, o[idx], acts_d[idx], wgt, outs_d)
+    for planes in (3, 2, 1):
+        rtol, atol = TC_MODE_TOL[planes]
+        h = head(B, L.HEAD_DISCRETE_PPO, p0=0.8, p1=1.2, target=hoh, adv=hadv, logp_old=hlpd, tc=F | planes,
+                 records=rec_d, rec_w=rw_d)
+        ok(B, lib.mq_fused_grad(net_d, B.ptr(htd), B.ptr(ho), B.ptr(hi), 9000, ctypes.byref(h), 1.0 / 9000, B.ptr(gd), None,
+                                None, B.ptr(wsd), wsb_d, B.stream))
+        close(B.down(gd), want, rtol=rtol, atol_scale=atol, what="tc3 discrete ppo P=%d" % planes)
+    # ---- the optimiser step keeps the operand image in step with theta (mq_reduce_step_image)
+    for planes in (3, 2, 1):
+        mb = 8192
+        idx = rs.randint(n, size=mb).astype(np.int32)
+        hi = B.up(idx)
+        th = B.up(theta.copy())
+        image = B.zeros(img_bytes[planes], np.uint8)
+        ok(B, lib.mq_tc_image_build(net, B.ptr(th), planes, B.ptr(image), B.stream))
+        val, m, v = B.up(theta.copy()), B.zeros(5126, np.float32), B.zeros(5126, np.float32)
+        h = head(B, L.HEAD_GAUSS_PPO, p0=0.8, p1=1.2, target=ha, adv=hadv, logp_old=hlp, tc=planes, records=rec,
+                 rec_w=rec_w, image=image)
+        n_parts = ctypes.c_int32(0)
+        for step in range(3):
+            ok(B, lib.mq_fused_grad_partials(net, B.ptr(th), B.ptr(ho), B.ptr(hi), mb, ctypes.byref(h), None, None,
+                                             B.ptr(ws), wsb, ctypes.byref(n_parts), B.stream))
+            assert n_parts.value > 1
+            ok(B, lib.mq_reduce_step_image(B.ptr(ws), n_parts.value, 5126, 1.0 / mb, B.ptr(val), B.ptr(m), B.ptr(v), B.ptr(th),
+                                           None, L.MQ_F32, 1.0 / (step + 1), 1.0 / (step + 1), 3e-3, 1e-8, 0, None, net, planes,
+                                           B.ptr(image), B.stream))
+        fresh = B.zeros(img_bytes[planes], np.uint8)
+        ok(B, lib.mq_tc_image_build(net, B.ptr(th), planes, B.ptr(fresh), B.stream))
+        assert np.array_equal(B.down(image), B.down(fresh)), "refreshed operand image differs from a fresh build (P=%d)" % planes
+        assert np.max(np.abs(B.down(th) - theta)) > 1e-4
+    return measured
 
 
 def case_reduce_step(B):
@@ -1061,4 +1217,4 @@ def case_gemm_tc(B):
 
 
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_gemm_tc, case_fused_heads,
-             case_fused_gauss_ppo, case_discrete, case_entropy, case_rollout, case_tc_paths, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]
+             case_fused_gauss_ppo, case_discrete, case_entropy, case_rollout, case_tc_paths, case_tc_modes, case_reduce_step, case_fused_train, case_ppo_reference_replay, case_es, case_ops]

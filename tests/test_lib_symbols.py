@@ -29,7 +29,7 @@ def test_header_and_binding_agree(lib):
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MqNet) == 4 * 5 + 4 * 8 * 6
-    assert ctypes.sizeof(_lib.MqHead) == 16 + 4 * 8
+    assert ctypes.sizeof(_lib.MqHead) == 16 + 4 * 8 + 8 + 4 + 4 + 8
     net = _lib.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
     assert net.n_params == 5126 and net.logstd_off == 5123
     assert list(net.w_off)[:3] == [0, 768, 4928] and list(net.b_off)[:3] == [704, 4864, 5120]
@@ -42,6 +42,11 @@ def test_sizes_and_error_codes_without_gpu(lib):
     net = _lib.make_net(11, [64, 64, 3], [1, 1, 0], logstd=True)
     assert lib.mq_mlp_acts_floats(ctypes.byref(net), 10) == 10 * (64 + 64 + 3)
     assert lib.mq_scan_ws_bytes(1 << 20) > 0 and lib.mq_norm_ws_bytes(2048, 1) > 0
+    # packed records and operand images of the tensor-core gradient kernel: sizes are host arithmetic
+    assert lib.mq_record_width(ctypes.byref(net)) == 16                      # 11 obs + 3 act + adv + logp_old = 64 bytes
+    sizes = [lib.mq_tc_image_bytes(ctypes.byref(net), pl) for pl in (1, 2, 3, 0)]
+    assert 0 < sizes[0] < sizes[1] < sizes[2] == sizes[3] and all(b % 16 == 0 for b in sizes)
+    assert lib.mq_tc_image_bytes(ctypes.byref(_lib.make_net(784, [128, 10], [2, 0])), 0) == 0     # does not fit the kernel
     # argument validation happens before any CUDA call
     assert lib.mq_adam_step(None, None, None, None, None, 4, 1, 0, 0.1, 0.1, 0.1, 1e-8, 0, None) == _lib.MQ_ERR_INVALID
     with pytest.raises(ValueError):
