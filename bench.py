@@ -34,6 +34,65 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+_MEASURED = {}
+
+
+def load_measured_peaks():
+    """fp32 FFMA and tensor-pipe (bf16, TF32) peaks measured on THIS GPU by the library's own microbenchmarks
+    ("to be measured by the harness"); cached for the process."""
+    if _MEASURED:
+        return _MEASURED
+    import ctypes as C
+    import torch
+    from mannequin2_b200 import _lib as L
+    lib = L.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    scratch = torch.zeros(16, device="cuda")
+    fl = C.c_double(0.0)
+
+    def run(fn):
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return fl.value / (best * 1e-3) / 1e12
+    try:
+        _MEASURED["ffma_tflops"] = run(lambda: L.check(lib.mq_bench_ffma(20000, scratch.data_ptr(), C.byref(fl), stream)))
+        _MEASURED["bf16_mma_issue_tflops"] = run(lambda: L.check(lib.mq_bench_tensor(0, 40000, C.byref(fl), stream)))
+        _MEASURED["tf32_tflops"] = run(lambda: L.check(lib.mq_bench_tensor(1, 40000, C.byref(fl), stream)))
+        _MEASURED["how"] = ("best of 5, CUDA events: mq_bench_ffma (8 independent FFMA chains per thread, 8 CTAs of 256 per SM); "
+                            "mq_bench_tensor (back-to-back tcgen05.mma M128 N256 from resident shared-memory operands, one "
+                            "CTA per SM: the tensor pipe's issue peak for kind::f16 / kind::tf32)")
+    except Exception as exc:                     # pragma: no cover
+        _MEASURED["error"] = repr(exc)
+    return _MEASURED
+
+
+def host_info():
+    """CPU model and NumPy / BLAS versions of the box the CPU arm runs on."""
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    blas = None
+    try:
+        cfg = np.show_config(mode="dicts")
+        b = cfg.get("Build Dependencies", {}).get("blas", {})
+        blas = "%s %s" % (b.get("name"), b.get("version"))
+    except Exception:
+        pass
+    return dict(cpu_model=model, logical_cpus=os.cpu_count(), numpy=np.__version__, blas=blas)
+
+
 # ------------------------------------------------------------------ synthetic data
 def ppo_rollout(rs, n, n_obs=11, n_act=3, p_done=1.0 / 200, cut=None):
     """BASELINE.md 3.4 C2/C3 generators."""
@@ -221,26 +280,29 @@ class PPOWorkload(object):
         o, a, r, d, vi, pi = self.rollouts[i % len(self.rollouts)]
         self.pol_theta, self.val_theta, _ = self.O.ppo_update(
             self.pol_theta, self.pol_spec, self.pol_opt, self.val_theta, self.val_spec, self.val_opt,
-            self.norm, o, a, r, d.astype(bool), vi, pi)
+            self.norm, o, a, r, d.astype(bool), vi, pi, dtype=np.float32)
 
 
 class PPOLargeWorkload(object):
-    """BASELINE.json configs[2]: large-batch PPO.  Per GPU: 2^20 synthetic transitions in
-    variable-length episodes (done p=1/500, forced cut every 1000 steps), one update =
-    value forward (N+1), GAE, advantage normalise+tanh, old log-probs (N), then 10 epochs x 16
-    permutation minibatches of 65,536 rows for the value net AND for the policy (160 + 160
-    Adam steps).  With G GPUs every rank holds its own 2^20-transition shard and the global
-    minibatch is G x 65,536 rows: one NCCL all-reduce of the flat gradient per optimiser step
-    (weak scaling)."""
+    """BASELINE.json configs[2]: large-batch PPO.  ONE rollout of 2^20 synthetic transitions in variable-length episodes
+    (done p=1/500, forced cut every 1000 steps); one update = value forward (N+1), GAE, advantage normalise+tanh, old
+    log-probs (N), packed records, then 10 epochs x 16 permutation minibatches of 65,536 rows for the value net AND for
+    the policy (160 + 160 Adam steps).
+    With G GPUs (the default N > 1 form, SURVEY 8d C3 / 8e: STRONG scaling) every rank holds the same rollout and the same
+    tables of global minibatches and takes 65,536 / G rows of each (8,192 per GPU at 8 GPUs); the flat gradient is
+    exchanged once per optimiser step inside the reduce + Adam kernel; the two forward passes over the rollout are split
+    by rows and all-gathered.  `weak=True` is round 1's form (every rank its own 2^20-transition shard, global minibatch
+    G x 65,536), reported beside it."""
     name = "ppo_large_1Mx10epochsx65536 (configs[2])"
     metric = "ppo_update_transitions_per_s"
     unit = "transitions/s"
     N, EPOCHS, MB = 1 << 20, 10, 65536
 
-    def __init__(self, n_rollouts=2, seed=1, n=None, epochs=None):
+    def __init__(self, n_rollouts=2, seed=1, n=None, epochs=None, weak=False, tc_mode="exact"):
         self.N = n or self.N
         self.EPOCHS = epochs or self.EPOCHS
         self.MB = min(self.MB, self.N)
+        self.weak, self.tc_mode = weak, tc_mode
         rs = np.random.RandomState(seed)
         self.rollouts = []
         per = self.N // self.MB
@@ -257,111 +319,223 @@ class PPOLargeWorkload(object):
 
     def setup_gpu(self):
         import torch
+        import torch.distributed as dist
         from mannequin2_b200 import _device as D
         from mannequin2_b200.ppo import PPOUpdater
         np.random.seed(0)
         self.torch, self.D = torch, D
-        self.upd = PPOUpdater(11, 3)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.replicated = self.world > 1 and not self.weak
+        self.upd = PPOUpdater(11, 3, tc_mode=self.tc_mode)
+        self.upd.check_indices = False               # the tables are permutations built above
         self.dev = [tuple(D.from_host(x) for x in r) for r in self.rollouts]
-        self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r) for r in self.rollouts[:1]]
+        # end to end: the ROLLOUT (obs, act, rew, done: 64 MB) travels every step from pinned host memory; the minibatch
+        # index tables (84 MB of int32 permutations, draws of the training loop, not rollout data) are uploaded once per
+        # run and stay resident -- round 1 shipped them with every step
+        self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r[:4]) for r in self.rollouts[:1]]
         self.out_pinned = (torch.empty(5126, dtype=torch.float32).pin_memory(),
                            torch.empty(4993, dtype=torch.float32).pin_memory())
-        self.h2d = sum(x.nbytes for x in self.rollouts[0])
+        self.h2d = sum(x.nbytes for x in self.rollouts[0][:4])
+        self.idx_bytes_once = sum(x.nbytes for x in self.rollouts[0][4:])
         self.d2h = (5126 + 4993) * 4
+        self._next = None
 
     def step_gpu(self, i):
-        self.upd.update_dev(*self.dev[i % len(self.dev)])
-
-    def _upload(self):
-        """Pinned host rollout -> device on the copy stream; returns (device tensors, event)."""
-        t = self.torch
-        with t.cuda.stream(self._copy_stream):
-            args = [x.to(self.D.device(), non_blocking=True) for x in self.pinned[0]]
-            ev = t.cuda.Event()
-            ev.record(self._copy_stream)
-        return args, ev
+        self.upd.update_dev(*self.dev[i % len(self.dev)], replicated=self.replicated)
 
     def step_e2e(self, i):
-        """Host buffers in, new parameters out, every step.  The upload of step i+1 (148 MB over PCIe) is issued on a
-        copy stream before step i's kernels are launched, the way a training loop feeds rollouts; every step still
-        copies its own inputs H2D and its results D2H inside the timed region."""
-        t = self.torch
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream, self._next = t.cuda.Stream(), None
+        """The public host-side call PPOUpdater.update: pinned host rollout in, new parameters out (pinned), every step.
+        prefetch() starts the upload of step i+1 on a copy stream before step i's kernels are launched, the way a training
+        loop feeds rollouts; every step still copies its own inputs H2D and its results D2H inside the timed region."""
         if self._next is None:
-            self._next = self._upload()
-        args, ev = self._next
-        main = t.cuda.current_stream()
-        main.wait_event(ev)
-        self._copy_stream.wait_stream(main)          # the next upload reuses nothing the running step still reads
-        self._next = self._upload()
-        self.upd.update_dev(*args)
-        for a in args:
-            a.record_stream(main)
-        self.out_pinned[0].copy_(self.upd.policy.theta, non_blocking=True)
-        self.out_pinned[1].copy_(self.upd.value.theta, non_blocking=True)
-        main.synchronize()
+            self._next = self.upd.prefetch(*self.pinned[0])
+        cur, self._next = self._next, None
+        vi, pi = self.dev[0][4], self.dev[0][5]
+        nxt = self.upd.prefetch(*self.pinned[0])
+        self.upd.update(cur, val_idx=vi, pol_idx=pi, replicated=self.replicated, out=self.out_pinned)
+        self._next = nxt
 
     def launches_per_step(self):
-        return 11 + 2 * self.steps_per_net * 2      # per optimiser step: gradient kernel + reduce/all-reduce/Adam kernel
+        # forwards, GAE (memset + scan), normaliser (4), 2 x pack, 2 x image build, then per optimiser step the gradient
+        # kernel + the reduce / exchange / Adam / image kernel
+        return 13 + 2 * self.steps_per_net * 2
 
-    def dominant_kernel(self, peaks):
-        """fused_grad_kernel on one 65,536-row policy minibatch, timed alone on its stream."""
+    def grad_kernel_time(self, net_obj, head, idx_ptr, mb, reps=12):
+        """One gradient launch (record-fed tcgen05 kernel -> per-CTA partials), timed alone with CUDA events on its
+        stream, L2 flushed before every launch; median of reps - 2."""
         import ctypes as C
-        t, D, upd = self.torch, self.D, self.upd
+        t, D = self.torch, self.D
         from mannequin2_b200 import _lib as L
-        obs, act, rew, done, vi, pi = self.dev[0]
-        head = L.MqHead()
-        head.kind, head.p0, head.p1 = L.HEAD_GAUSS_PPO, 0.8, 1.2
-        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(upd._bufs["adv_n"]), D.ptr(upd._bufs["logp0"])
-        net = upd.policy.net
-        wsb = L.lib().mq_fused_ws_bytes(C.byref(net), self.MB)
+        wsb = L.lib().mq_fused_ws_bytes(C.byref(net_obj.net), mb)
         ws = D.workspace("bench", wsb)
+        flush = t.empty(L2_FLUSH_BYTES // 4, dtype=t.float32, device="cuda")
+        n_parts = C.c_int32(0)
         times = []
-        for k in range(8):
+        for k in range(reps):
+            flush.fill_(float(k))
             e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             e0.record()
-            D.call("mq_fused_grad", C.byref(net), D.ptr(upd.policy.theta), D.ptr(obs), D.ptr(pi) + k * self.MB * 4,
-                   self.MB, C.byref(head), 1.0 / self.MB, D.ptr(upd.policy.grad), None, None, D.ptr(ws), wsb,
-                   D.stream())
+            D.call("mq_fused_grad_partials", C.byref(net_obj.net), D.ptr(net_obj.theta), D.ptr(self.dev[0][0]),
+                   idx_ptr + (k % 8) * mb * 4, mb, C.byref(head), None, None, D.ptr(ws), wsb, C.byref(n_parts), D.stream())
             e1.record()
             e1.synchronize()
             times.append(e0.elapsed_time(e1))
-        ms = float(np.median(times[2:]))
-        bytes_per_launch = self.MB * 64                    # SURVEY 8d: 64 B gathered per minibatch row
-        flops = self.MB * 28544.0                          # SURVEY 8d: 28,544 FLOP per row (fwd+dW+dX)
-        # tensor-core work actually issued (DESIGN.md 3.1): six bf16 plane pairs per fp32 product, operands padded
-        # to 16/64 columns, M = 128 rows per tile of `tile_rows` valid rows
-        sms = 148
-        waves = -(-self.MB // (sms * 128))
-        tile_rows = min(128, -(-(-(-self.MB // (sms * waves))) // 16) * 16)
-        tiles = -(-self.MB // tile_rows)
+        del flush
+        return float(np.median(times[2:])), n_parts.value
+
+    def policy_head(self, upd):
+        from mannequin2_b200 import _lib as L
+        D = self.D
+        obs, act = self.dev[0][0], self.dev[0][1]
+        head = L.MqHead()
+        head.kind, head.p0, head.p1 = L.HEAD_GAUSS_PPO, 0.8, 1.2
+        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(upd._bufs["adv_n"]), D.ptr(upd._bufs["logp0"])
+        pol = upd.policy
+        head.tc = pol.planes
+        head.records, head.rec_w, head.tc_image = D.ptr(pol.records), pol.rec_w, D.ptr(pol.image)
+        return head
+
+    def dominant_kernel(self, peaks):
+        """tc3_grad_kernel on one policy minibatch of this rank (65,536 rows on one GPU), timed alone on its stream."""
+        upd = self.upd
+        mb = self.MB // (self.world if self.replicated else 1)
+        head = self.policy_head(upd)
+        ms, n_parts = self.grad_kernel_time(upd.policy, head, self.D.ptr(self.dev[0][5]), mb)
+        planes = upd.policy.planes
+        bytes_per_launch = mb * 64                         # SURVEY 8d: 64 B gathered per minibatch row
+        flops = mb * 28544.0                               # SURVEY 8d: 28,544 FLOP per row (fwd+dW+dX)
+        # tensor-core work actually issued (DESIGN.md 3.1): plane pairs i + j < planes per fp32 product (6 / 3 / 1), operands
+        # padded to 16 / 64 columns, M = 128 rows per tile of `tile_rows` valid rows, the ones column for the bias sums
+        pairs = {3: 6, 2: 3, 1: 1}[planes]
+        slots = 148 * (1 if planes == 3 else 2)
+        waves = -(-mb // (slots * 128))
+        tile_rows = min(128, max(16, -(-(-(-mb // (slots * waves))) // 16) * 16))
+        tiles = -(-mb // tile_rows)
         ks = tile_rows // 16
-        rows_pair = 2 * 16 * 128 * (128 + 128 + 64 + 64)          # one K step of a row-major product (hidden width 64)
-        per_tile = rows_pair * (1 + 4 + 1 + 4) + 2 * 16 * 128 * 96 * 4 \
-            + ks * 2 * 16 * 64 * ((32 + 32 + 16 + 16) + (32 + 16) + (136 + 136 + 72 + 64) + (40 + 40 + 24 + 16))
-        executed = tiles * float(per_tile)
+        fwd = 2 * 128 * (16 * 64 + 64 * 64 + 64 * 16)                       # Z = A W, three layers, per pair
+        dA = 2 * 128 * (16 * 64 + 64 * 64)                                  # dA = dZ W^T, two layers
+        dW = ks * 2 * 16 * 64 * (16 + (64 + 8) + (16 + 8))                  # dW^T, db (M = 64 instructions)
+        executed = tiles * float(pairs * (fwd + dA + dW) + ks * 2 * 16 * 64 * 16)
         tf = flops / (ms * 1e-3) / 1e12
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        traffic = None                                      # DRAM bytes per launch from the committed ncu capture
+        measured = load_measured_peaks()
+        traffic, traffic_src = None, None
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f)["tc_grad_kernel_policy_65536rows"]["dram_bytes_per_launch"]
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)["tc3_grad_kernel_policy_65536rows"][self.tc_mode]
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except (OSError, KeyError, ValueError):
             pass
-        return dict(bound="tensor", kernel="tc_grad_kernel<16,tanh> (policy, 65536 rows, tcgen05 bf16x3 planes; "
-                                           "launch includes fused_reduce_kernel)",
+        return dict(bound="tensor", kernel="tc3_grad_kernel<planes=%d> (policy, %d rows, record-fed tcgen05, %s mode)"
+                                           % (planes, mb, self.tc_mode),
                     achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=traffic,
-                    traffic_note="ncu dram__bytes_read+write of one 65,536-row launch (algorithmic gather: 4.2 MB; 44-byte "
-                                 "rows arrive as 32-byte sectors, index and weight reads add the rest)",
-                    peak_source=peaks["source"], ms_per_launch=ms,
-                    limiter="fp32-exact products = 6 bf16 plane pairs with K = 16..64: the tensor pipe is fed at the "
-                            "shared-memory operand rate (measured 128 B/cycle/SM) and waits on the per-layer epilogues; "
-                            "neither HBM (64 B/row) nor the dense bf16 peak is the bound",
+                    traffic_note="ncu dram__bytes_read+write of one 65,536-row launch (%s); algorithmic gather 4.2 MB + "
+                                 "0.26 MB of indices + the operand image" % traffic_src,
+                    peak_source=peaks["source"], ms_per_launch=ms, n_partials=n_parts, rows=mb, mode=self.tc_mode,
+                    limiter="a 64-wide MLP is a chain of six dependent (product -> epilogue) phases per 128-row tile with "
+                            "K = 16..64: the epilogues (bias, tanh, split into bf16 planes, shared-memory stores: ~20 "
+                            "instructions per element) are instruction-issue bound and the tensor pipe waits for them; "
+                            "neither HBM (64 B/row) nor the dense bf16 peak is the bound (DESIGN.md 3.1)",
                     executed_tensor_tflops=executed / (ms * 1e-3) / 1e12,
                     executed_tensor_frac=executed / (ms * 1e-3) / 1e12 / peaks["bf16"],
-                    hbm_gbs=bytes_per_launch / (ms * 1e-3) / 1e9,
-                    fp32_frac_of_ffma_peak=tf / fp32_peak, fp32_peak_tflops_nominal=fp32_peak)
+                    hbm_gbs=bytes_per_launch / (ms * 1e-3) / 1e9, hbm_frac=bytes_per_launch / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                    fp32_ffma_peak_tflops=measured.get("ffma_tflops"), fp32_frac_of_ffma_peak=(
+                        tf / measured["ffma_tflops"] if measured.get("ffma_tflops") else None),
+                    tf32_peak_tflops=measured.get("tf32_tflops"), peaks_measured_here=measured.get("how"))
+
+    def precision_modes(self, steps=3):
+        """The looser tensor-core modes next to the exact one (north_star: "a stated looser tolerance for bf16 tensor-core
+        paths"): whole-update throughput, gradient-kernel time and the MEASURED error of one 65,536-row policy gradient
+        against the exact mode."""
+        import ctypes as C
+        t, D = self.torch, self.D
+        from mannequin2_b200.ppo import PPOUpdater
+        from mannequin2_b200 import _lib as L
+        out = {}
+        base_theta = self.upd.policy.theta.clone()
+        ref_grad = None
+        for mode in ("exact", "bf16x2", "bf16"):
+            np.random.seed(0)
+            upd = PPOUpdater(11, 3, tc_mode=mode)
+            upd.check_indices = False
+            for i in range(2):
+                upd.update_dev(*self.dev[i % len(self.dev)])
+            t.cuda.synchronize()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                upd.update_dev(*self.dev[i % len(self.dev)])
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            # one gradient at FIXED parameters (the exact updater's), this mode's arithmetic
+            head = self.policy_head(upd)
+            upd.policy.theta.copy_(base_theta)
+            D.call("mq_tc_image_build", C.byref(upd.policy.net), D.ptr(upd.policy.theta), upd.policy.planes,
+                   D.ptr(upd.policy.image), D.stream())
+            kms, _ = self.grad_kernel_time(upd.policy, head, D.ptr(self.dev[0][5]), self.MB, reps=8)
+            wsb = L.lib().mq_fused_ws_bytes(C.byref(upd.policy.net), self.MB)
+            ws = D.workspace("bench", wsb)
+            g = t.zeros(5126, device="cuda")
+            D.call("mq_fused_grad", C.byref(upd.policy.net), D.ptr(upd.policy.theta), D.ptr(self.dev[0][0]), D.ptr(self.dev[0][5]),
+                   self.MB, C.byref(head), 1.0 / self.MB, D.ptr(g), None, None, D.ptr(ws), wsb, D.stream())
+            g = g.double().cpu().numpy()
+            if ref_grad is None:
+                ref_grad = g
+            err = float(np.max(np.abs(g - ref_grad)) / np.max(np.abs(ref_grad)))
+            out[mode] = dict(value=self.N / (ms * 1e-3), unit=self.unit, ms_per_step=ms, grad_kernel_ms=kms,
+                             grad_err_vs_exact=err, stated_tolerance={"exact": "rtol 1e-5 (the FFMA bar)", "bf16x2": 3e-5,
+                                                                      "bf16": 1e-1}[mode],
+                             note="max |g - g_exact| / max |g_exact| of one 65,536-row policy gradient at the same parameters")
+            del upd
+        return out
+
+    def parity_check(self, rows_per_rank=8192, epochs=1):
+        """Outside the timed region: a small update through the SAME dispatch as the benchmark (record-fed tcgen05 kernel
+        + in-kernel exchange when sharded) -- every rank ends with bit-identical parameters, and rank 0 compares them with
+        the oracle's restatement of benchmarks/ppo.py:22-40 + gae.py:34-75 on the whole problem."""
+        import torch.distributed as dist
+        t, D = self.torch, self.D
+        from mannequin2_b200.ppo import PPOUpdater, init_mlp
+        world = self.world
+        rank = dist.get_rank() if world > 1 else 0
+        mb = rows_per_rank * world
+        n = 2 * mb
+        rs = np.random.RandomState(77)                  # same problem on every rank
+        o, a, r, d = ppo_rollout(rs, n, p_done=1.0 / 300, cut=700)
+        vi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+        pi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+        np.random.seed(5)
+        pol0 = np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)])
+        val0 = init_mlp(11, [64, 64, 1], 0.1)
+        upd = PPOUpdater(11, 3, policy_params=pol0.copy(), value_params=val0.copy(), tc_mode=self.tc_mode)
+        upd.update_dev(*[D.from_host(x) for x in (o, a, r, d, vi, pi)], replicated=world > 1)
+        t.cuda.synchronize()
+        both = t.cat([upd.policy.theta, upd.value.theta])
+        identical = True
+        if world > 1:
+            allp = [t.empty_like(both) for _ in range(world)]
+            dist.all_gather(allp, both)
+            identical = all(bool(t.equal(allp[0].view(t.int32), q.view(t.int32))) for q in allp)
+        res = dict(replicas_identical=identical, exchange=upd.policy.exchange(), rows_per_rank=rows_per_rank,
+                   global_minibatch=mb, transitions=n, steps_per_net=len(vi), mode=self.tc_mode,
+                   gradient_kernel="tc3_grad_kernel (records)" if upd.policy.records is not None else "FFMA")
+        if rank == 0:
+            from oracle import mq_oracle as O
+            pol_spec = O.policy_spec(11, 3)
+            val_spec = O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
+            want_pol, want_val, _ = O.ppo_update(pol0.copy(), pol_spec, O.AdamO(pol0, horizon=10), val0.copy(), val_spec,
+                                                 O.AdamO(val0, horizon=10, lr=0.003), O.RunningNormalizeO(horizon=2),
+                                                 o, a, r, d.astype(bool), vi, pi)
+            e_pol = float(np.max(np.abs(D.to_host(upd.policy.theta) - want_pol)))
+            e_val = float(np.max(np.abs(D.to_host(upd.value.theta) - want_val)))
+            frac = {"exact": 0.007, "bf16x2": 0.07, "bf16": 1.0}[self.tc_mode]
+            steps = len(vi)
+            res.update(max_abs_err=max(e_pol, e_val), max_abs_err_policy=e_pol, max_abs_err_value=e_val,
+                       tol_policy=frac * 3e-4 * (1 + steps), tol_value=frac * 3e-3 * (1 + steps),
+                       within_tolerance=bool(e_pol < frac * 3e-4 * (1 + steps) and e_val < frac * 3e-3 * (1 + steps)),
+                       oracle="oracle/mq_oracle.py: ppo_update on the concatenated rows (fp64)")
+        del upd
+        return res
 
     # CPU arm: the same per-transition work on a bounded sample
     SAMPLE_N = 65536
@@ -378,7 +552,7 @@ class PPOLargeWorkload(object):
         o, a, r, d, vi, pi = self.cpu_sample
         self.pol_theta, self.val_theta, _ = self.O.ppo_update(
             self.pol_theta, self.pol_spec, self.pol_opt, self.val_theta, self.val_spec, self.val_opt,
-            self.norm, o, a, r, d.astype(bool), vi, pi)
+            self.norm, o, a, r, d.astype(bool), vi, pi, dtype=np.float32)
 
     cpu_units_per_step = SAMPLE_N
     cpu_sample_desc = ("65,536 transitions, 10 epochs x 1 minibatch of 65,536 rows per net "
@@ -686,7 +860,9 @@ class ClosedLoopWorkload(PPOLargeWorkload):
         np.random.seed(0)
         self.torch, self.D = torch, D
         self.env = SyntheticEnv(self.N_ENV, horizon=256, seed=3)
+        self.world, self.replicated, self.tc_mode = 1, False, "exact"
         self.upd = PPOUpdater(11, 3)
+        self.upd.check_indices = False
         self.actor = BatchedActor(self.env, self.upd.policy, seed=5, use_graph=True)
         self.dev = [tuple(D.from_host(x) for x in r) for r in self.tables]
         self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r) for r in self.tables[:1]]
@@ -827,12 +1003,14 @@ def kernel_sweep(peaks):
 
 # ------------------------------------------------------------------ CPU timing helpers
 def _cpu_worker(args):
-    name, steps, warmup, seed = args
-    try:
-        from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=1)
-    except Exception:
-        limiter = None
+    name, steps, warmup, seed, threads = args
+    limiter = None
+    if threads:
+        try:
+            from threadpoolctl import threadpool_limits
+            limiter = threadpool_limits(limits=threads)
+        except Exception:
+            limiter = None
     wl = WORKLOADS[name](seed=seed + 1, **CPU_KW.get(name, {}))
     wl.setup_cpu()
     for i in range(warmup):
@@ -840,25 +1018,38 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     for i in range(steps):
         wl.step_cpu(warmup + i)
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    del limiter
+    return dt
 
 
 CPU_KW = {"ppo_large": dict(n=65536, n_rollouts=1), "es": dict(m=256), "mlp": dict(n_data=8192)}
 
 
-def time_cpu(name, steps, warmup, procs):
-    """`procs` independent single-thread replicas in parallel (how the reference uses a multi-core
-    box: run_benchmarks.sh:98-102, one process per seed); aggregate units/s."""
+def time_cpu(name, steps, warmup, procs, threads=1):
+    """`procs` independent replicas in parallel, each limited to `threads` BLAS threads (None: NumPy / OpenBLAS default);
+    procs = cores with threads = 1 is how the reference uses a multi-core box (run_benchmarks.sh:98-102, one process per
+    seed).  Returns (aggregate units/s, timed seconds of the slowest replica)."""
     import multiprocessing as mp
     wl = WORKLOADS[name](**CPU_KW.get(name, {}))
     units = getattr(wl, "cpu_units_per_step", wl.units_per_step)
     if procs <= 1:
-        dt = _cpu_worker((name, steps, warmup, 0))
+        with mp.get_context("fork").Pool(1) as pool:            # a fresh process: thread limits do not leak into this one
+            dt = pool.map(_cpu_worker, [(name, steps, warmup, 0, threads)])[0]
         return steps * units / dt, dt
     with mp.get_context("fork").Pool(procs) as pool:
-        dts = pool.map(_cpu_worker, [(name, steps, warmup, s) for s in range(procs)])
+        dts = pool.map(_cpu_worker, [(name, steps, warmup, s, threads) for s in range(procs)])
     slowest = max(dts)                       # timed region of the slowest replica (set-up/warm-up excluded)
     return procs * steps * units / slowest, slowest
+
+
+def cpu_three_figures(name, cores):
+    """the CPU port timed three ways on this box."""
+    v_def, _ = time_cpu(name, 1, 1, 1, threads=None)
+    v_one, _ = time_cpu(name, 1, 1, 1, threads=1)
+    procs = max(1, min(cores, 32))
+    v_rep, _ = time_cpu(name, 1, 1, procs, threads=1)
+    return dict(default_threads_1proc=v_def, one_thread_1proc=v_one, replicas=procs, replicas_aggregate=v_rep)
 
 
 # ------------------------------------------------------------------ main
@@ -902,9 +1093,11 @@ def measure(wl, steps, warmup, world, rank, flush):
     return float(t[0]), float(t[1])
 
 
-PARALLELISM = {"ppo_large": "dp%d: every rank trains on its own 2^20-transition shard, global minibatch = %d x 65,536 "
-                            "rows, the flat gradient is all-reduced over NVLink peer memory inside the reduce+Adam kernel "
-                            "(one exchange per optimiser step, no NCCL call on the step path)",
+PARALLELISM = {"ppo_large": "dp%d, STRONG scaling (BASELINE configs[2]): ONE 2^20-transition rollout replicated on every rank, every "
+                            "65,536-row global minibatch split %d ways by rows, the flat gradient exchanged over NVLink peer "
+                            "memory inside the reduce + Adam kernel (one exchange per optimiser step, no NCCL call on the step "
+                            "path); the two forward passes over the rollout are split by rows and all-gathered (NCCL), GAE and "
+                            "the normaliser run replicated",
                "ppo": "%d independent replicas (a 64-row minibatch does not shard)",
                "mlp": "%d independent replicas (batch 128 does not shard)",
                "es": "population sharded: %d x 4096 members, all-gather of returns + one all-reduce",
@@ -921,6 +1114,8 @@ def main():
     ap.add_argument("--workload", default="ppo_large", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / kernel sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-mode", default="exact", choices=["exact", "bf16x2", "bf16"],
+                    help="precision of the tensor-core gradient kernel of the headline workload (default: exact fp32 products)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -944,17 +1139,20 @@ def main():
             return 0
         procs = max(1, min(cores, 32))
         steps = max(1, min(args.steps, 3))
-        val, wall = time_cpu(args.workload, steps, 1, procs)
+        val, wall = time_cpu(args.workload, steps, 1, procs, threads=1)
         sample = getattr(wl, "cpu_sample_desc", "the full workload step")
         line = dict(metric=wl.metric, value=val, unit=wl.unit, n_gpus=args.gpus, steps=steps, warmup=1,
                     ms_per_step=1e3 * wall / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f64", data="synthetic", impl="reference",
+                    dtype="f32 nets, f64 Adam (the reference's own types)", data="synthetic", impl="reference",
                     config=dict(workload=wl.name, sample=sample,
-                                note="CPU restatement (oracle port) of the NumPy reference path; %d independent "
-                                     "single-thread replicas run in parallel, aggregate throughput (how the "
-                                     "reference uses a multi-core box: run_benchmarks.sh:98-102)" % procs),
+                                note="CPU restatement (oracle port) of the NumPy reference path -- Tanh nets in float32 as "
+                                     "in the reference (basicnet.py:193,210), Adam state float64 (_adam.py:14-18); %d "
+                                     "independent single-thread replicas run in parallel, aggregate throughput (how the "
+                                     "reference uses a multi-core box: run_benchmarks.sh:98-102)" % procs,
+                                host=host_info()),
                     cpu_baseline=dict(value=val, unit=wl.unit, cores=procs, kind="port",
-                                      sample="%d steps x %d replicas; each step: %s" % (steps, procs, sample)),
+                                      sample="%d steps x %d replicas (OPENBLAS threads = 1 each); each step: %s"
+                                             % (steps, procs, sample)),
                     e2e=dict(value=val, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         emit(line)
         return 0
@@ -968,7 +1166,11 @@ def main():
     else:
         torch.cuda.set_device(0)
     peaks = load_peaks()
-    wl = WORKLOADS[args.workload](seed=1 + rank)
+    large = args.workload == "ppo_large"
+    if large:
+        wl = WORKLOADS[args.workload](seed=1, tc_mode=args.tc_mode)       # the SAME rollout on every rank (strong scaling)
+    else:
+        wl = WORKLOADS[args.workload](seed=1 + rank)
     wl.setup_gpu()
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
     wl.step_gpu(0)
@@ -978,30 +1180,64 @@ def main():
         sampler.start()
     ms, ms_e2e = measure(wl, args.steps, warmup, world, rank, flush)
     clocks = sampler.stop() if rank == 0 else None
-    units = wl.units_per_step * args.steps * world
+    strong = large and world > 1
+    units = wl.units_per_step * args.steps * (1 if strong else world)
+    parity = wl.parity_check() if large else None                           # every rank takes part (outside the timed region)
+    roof = wl.dominant_kernel(peaks) if rank == 0 else None
+    weak_line = None
+    if strong:
+        # round 1's form for comparison: every rank its own 2^20-transition shard, global minibatch world x 65,536
+        del wl
+        torch.cuda.empty_cache()
+        ww = WORKLOADS[args.workload](seed=1 + rank, weak=True, tc_mode=args.tc_mode)
+        ww.setup_gpu()
+        wms, wms_e2e = measure(ww, max(2, args.steps // 2), 3, world, rank, flush)
+        k = max(2, args.steps // 2)
+        weak_line = dict(scaling="weak", value=ww.units_per_step * k * world / (wms * 1e-3), unit=ww.unit,
+                         ms_per_step=wms / k, e2e=ww.units_per_step * k * world / (wms_e2e * 1e-3),
+                         note="every rank its own 2^20-transition shard, global minibatch = %d x 65,536 rows" % world)
+        wl = ww
     if rank == 0:
-        roof = wl.dominant_kernel(peaks)
+        arith = {"exact": "fp32 results (parity rtol 1e-5): minibatch gradients >= 8,192 rows run on tcgen05 as 3 exact bf16 "
+                          "planes per operand (6 plane pairs), fp32 accumulation in TMEM; the rest is fp32 FFMA",
+                 "bf16x2": "minibatch gradients >= 8,192 rows on tcgen05 with 2 bf16 planes per operand (3 plane pairs; stated "
+                           "tolerance 3e-5 max|grad|), fp32 accumulation; the rest is fp32 FFMA",
+                 "bf16": "minibatch gradients >= 8,192 rows on tcgen05 with plain bf16 operands (stated tolerance 1e-1 "
+                         "max|grad|), fp32 accumulation; the rest is fp32 FFMA"}[args.tc_mode]
         line = dict(metric=wl.metric, value=units / (ms * 1e-3), unit=wl.unit, n_gpus=world, steps=args.steps,
-                    warmup=warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                    warmup=warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling="strong" if strong else "weak",
                     vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=wl.name,
                                 l2="flushed (256 MB write) between timed steps; per-step inputs exceed L2",
-                                adam_state="f32",
-                                arithmetic="fp32 results (parity rtol 1e-5): large-batch Affine products run on tcgen05 as "
-                                           "3 exact bf16 planes per operand, fp32 accumulation in TMEM; the rest is fp32 FFMA",
+                                adam_state="f32", tc_mode=args.tc_mode if large else None,
+                                arithmetic=arith if large else "fp32",
                                 parallelism=PARALLELISM[args.workload] % ((world, world) if
                                 args.workload == "ppo_large" else (world,)) if world > 1 else "single GPU"),
                     e2e=dict(value=units / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=wl.h2d,
-                             d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps),
+                             d2h_bytes_per_step=wl.d2h, ms_per_step=ms_e2e / args.steps,
+                             api="PPOUpdater.update(prefetch(pinned rollout), val_idx, pol_idx, out=pinned) -- the public "
+                                 "host-side call" if large else "public host-side call of the workload",
+                             index_tables="uploaded once per run (%d bytes), resident between updates"
+                                          % getattr(wl, "idx_bytes_once", 0) if large else None),
                     gpu_launches=wl.launches_per_step() * args.steps, roofline=roof, clocks=clocks)
+        if parity is not None:
+            line["parity_check"] = parity
+        if weak_line is not None:
+            line["weak_scaling"] = weak_line
         if not args.no_cpu_baseline and world == 1 and getattr(wl, "step_cpu", None):
-            v1, w1 = time_cpu(args.workload, 1, 1, 1)
+            three = cpu_three_figures(args.workload, cores)
             line["cpu_baseline"] = dict(
-                value=v1, unit=wl.unit, cores=1, kind="port", host_cores=cores,
-                sample="1 step after 1 warm-up in one process (NumPy/OpenBLAS default threads); each step: "
-                       + getattr(wl, "cpu_sample_desc", "the full workload step"))
+                value=three["replicas_aggregate"], unit=wl.unit, cores=three["replicas"], kind="port", host=host_info(),
+                figures=three,
+                sample="BASELINE.md 3.3's three figures, each 1 step after 1 warm-up: one process with NumPy / OpenBLAS default "
+                       "threads, one process with one BLAS thread, and `cores` single-thread replicas in parallel (value: how "
+                       "the reference uses a multi-core box, run_benchmarks.sh:98-102); Tanh nets float32, Adam float64 as in "
+                       "the reference; each step: " + getattr(wl, "cpu_sample_desc", "the full workload step"))
         else:
             line["cpu_baseline"] = None
+        if large and world == 1 and not args.no_extras:
+            line["modes"] = wl.precision_modes()
         if not args.no_extras and world == 1:
             del wl
             torch.cuda.empty_cache()
@@ -1014,7 +1250,7 @@ def main():
                 m1, m2 = measure(w2, 5, 3, 1, 0, flush)
                 u = w2.units_per_step * 5
                 r2 = w2.dominant_kernel(peaks)
-                c1 = time_cpu(name, 1, 1, 1)[0] if getattr(w2, "step_cpu", None) else None
+                c1 = time_cpu(name, 1, 1, 1, threads=None)[0] if getattr(w2, "step_cpu", None) else None
                 reps = [w2.replica_throughput(r) for r in (8, 16)] if hasattr(w2, "replica_throughput") else None
                 others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
                                     e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,

@@ -98,8 +98,7 @@ typedef struct mq_head {
 #define MQ_TC_PLANES_MASK 0x3   /* 0 = default (3) */
 #define MQ_TC_FORCE       0x10  /* use the tensor-core kernel whenever the net fits (default: batch >= 8192) */
 #define MQ_TC_OFF         0x20  /* never use it (FFMA kernels)                                                */
-#define MQ_TC_HALF        0x40  /* developer aid: prefer two 64-row tile slots (the default for 3 planes)         */
-#define MQ_TC_FULL        0x80  /* developer aid: 128-row tile slots only                                         */
+#define MQ_TC_NOPIPE      0x40  /* developer aid (A/B measurements): no K-chunk pipelining between layers          */
 /* When row_idx != NULL, x and every head array are indexed by row_idx[i] (they
  * are whole-rollout arrays, mannequin/_trajectory.py:79-86 fused into the load);
  * otherwise by the minibatch position i. */
@@ -155,6 +154,11 @@ int mq_debug_use_chain_grad(int on);
 int mq_debug_set_chain_warps(int nw);
 /* developer aid: tcgen05 GEMM for wide layers: 0 never, 1 automatic (>= 2^26 multiply-adds), 2 whenever possible */
 int mq_debug_set_gemm_tc_mode(int mode);
+/* peak microbenchmarks for bench.py's roofline denominators: *flops_out = FLOPs the launch executes;
+ * the caller times it with CUDA events.  mq_bench_tensor: back-to-back tcgen05.mma M128 N256 from resident operands,
+ * tf32 = 0: kind::f16 (bf16 inputs), 1: kind::tf32. */
+int mq_bench_ffma(int32_t iters, float *scratch, double *flops_out, void *stream);
+int mq_bench_tensor(int32_t tf32, int32_t n_mma, double *flops_out, void *stream);
 int mq_version(void);
 int mq_device_props(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *smem_optin);
 
@@ -297,11 +301,13 @@ int mq_reduce_step_image(const float *partials, int32_t n_parts, int64_t n, floa
                          double eps, int adams, const mq_peer_t *peer, const mq_net_t *net, int32_t tc, void *image,
                          void *stream);
 /* n_steps dependent large-minibatch steps {mq_fused_grad_partials, mq_reduce_step_image} issued by one call
- * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73 at 65,536-row minibatches): idx_table[n_steps, mb], coefs_host =
+ * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73 at 65,536-row minibatches): step s reads mb indices at idx_table +
+ * s * idx_stride (idx_stride > mb: this rank's columns of the global minibatch table), coefs_host =
  * [n_steps][2] host doubles (c1, c2), peer (nullable) = descriptor of the FIRST step (its tag counts up per step),
  * head->tc_image (nullable) is refreshed by every step. */
 int mq_train_steps(const mq_net_t *net, float *theta, const float *x, const mq_head_t *head,
-                   const int32_t *idx_table, int32_t n_steps, int64_t mb, float scale, void *value, void *m, void *v,
+                   const int32_t *idx_table, int64_t idx_stride, int32_t n_steps, int64_t mb, float scale, void *value,
+                   void *m, void *v,
                    int state_dtype, const double *coefs_host, double lr, double eps, int adams, const mq_peer_t *peer,
                    void *ws, int64_t ws_bytes, void *stream);
 /* n_steps dependent {gather, forward, head, backward, Adam} steps in ONE launch

@@ -59,6 +59,8 @@ PEERP = POINTER(MqPeer)
 SIGNATURES = {
     "mq_last_error": (c_char_p, []),
     "mq_version": (c_int, []),
+    "mq_bench_ffma": (c_int, [c_int32, P, POINTER(c_double), P]),
+    "mq_bench_tensor": (c_int, [c_int32, c_int32, POINTER(c_double), P]),
     "mq_debug_set_phase_buffer": (c_int, [P]),
     "mq_debug_set_tile_rows": (c_int, [c_int]),
     "mq_debug_use_chain_grad": (c_int, [c_int]),
@@ -101,7 +103,7 @@ SIGNATURES = {
                                c_double, c_int, PEERP, P]),
     "mq_reduce_step_image": (c_int, [P, c_int32, c_int64, c_float, P, P, P, P, P, c_int, c_double, c_double, c_double,
                                      c_double, c_int, PEERP, NETP, c_int32, P, P]),
-    "mq_train_steps": (c_int, [NETP, P, P, HEADP, P, c_int32, c_int64, c_float, P, P, P, c_int, POINTER(c_double), c_double,
+    "mq_train_steps": (c_int, [NETP, P, P, HEADP, P, c_int64, c_int32, c_int64, c_float, P, P, P, c_int, POINTER(c_double), c_double,
                                c_double, c_int, PEERP, P, c_int64, P]),
     "mq_fused_train": (c_int, [NETP, P, P, P, P, c_int, P, HEADP, P, c_int32, c_int32, c_double,
                                c_double, POINTER(c_double), c_double, c_double, P]),

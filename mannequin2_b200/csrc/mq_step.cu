@@ -214,19 +214,20 @@ extern "C" int mq_reduce_step_image(const float *, int32_t, int64_t, float, void
 // benchmarks/ppo.py:29-40 / benchmarks/gae.py:71-73 at large minibatches: per step one gradient launch (per-CTA partials)
 // and one reduce / exchange / Adam launch.  The loop lives here so that a 160-step epoch block costs one trip through
 // the Python binding instead of 320 (at 8,192 rows per GPU a step is ~25 us of GPU time: the host has to keep ahead).
+// Step s reads the mb indices at idx_table + s * idx_stride (idx_stride > mb: this rank's columns of a wider global table).
 // coefs_host = [n_steps][2] running-mean coefficients (c1, c2) of mannequin/_normalize.py:18-25; peer (nullable) carries the
 // tag of the FIRST step, later steps count up; image (nullable): operand image kept in step with theta (mq_tc3.cuh).
 extern "C" int mq_train_steps(const mq_net_t *net, float *theta, const float *x, const mq_head_t *head,
-                              const int32_t *idx_table, int32_t n_steps, int64_t mb, float scale, void *value, void *m,
+                              const int32_t *idx_table, int64_t idx_stride, int32_t n_steps, int64_t mb, float scale, void *value, void *m,
                               void *v, int state_dtype, const double *coefs_host, double lr, double eps, int adams,
                               const mq_peer_t *peer, void *ws, int64_t ws_bytes, void *stream) {
     MQ_REQUIRE(net && theta && x && head && idx_table && coefs_host && ws, MQ_ERR_INVALID, "mq_train_steps: null pointer");
-    MQ_REQUIRE(n_steps >= 0 && mb >= 1, MQ_ERR_SHAPE, "mq_train_steps: sizes");
+    MQ_REQUIRE(n_steps >= 0 && mb >= 1 && idx_stride >= mb, MQ_ERR_SHAPE, "mq_train_steps: sizes");
     mq_peer_t pr;
     if (peer) pr = *peer;
     for (int s = 0; s < n_steps; ++s) {
         int32_t n_parts = 0;
-        int rc = mq_fused_grad_partials(net, theta, x, idx_table + (int64_t)s * mb, mb, head, nullptr, nullptr, ws, ws_bytes,
+        int rc = mq_fused_grad_partials(net, theta, x, idx_table + (int64_t)s * idx_stride, mb, head, nullptr, nullptr, ws, ws_bytes,
                                         &n_parts, stream);
         if (rc != MQ_OK) return rc;
         if (peer) pr.step = peer->step + (uint32_t)s;

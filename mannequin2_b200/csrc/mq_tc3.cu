@@ -230,7 +230,7 @@ __device__ __forceinline__ TcView t3_wf_k(uint32_t addr, int np) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
-template <int P, int NS, int HR, int K0, int HACT>
+template <int P, int NS, int K0, int HACT>
 __global__ void __launch_bounds__(T3_NTI, 1)
 tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *__restrict__ rec,
                 const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
@@ -238,16 +238,11 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_full[2], s_dw[2], s_ready[2], s_img;
-    // HR = 1 (two slots only): a slot is 64 rows.  Its products are still M = 128 instructions -- slot 0's rows are rows 0-63
-    // of the instruction (TMEM lanes 0-63, warps of lane quarters 0 and 1), slot 1's are rows 64-127 (operand base moved back
-    // by 64 rows; lane quarters 2 and 3); the other half of each instruction reads neighbouring shared memory and writes
-    // TMEM lanes nobody reads.  Half of the tensor work is wasted, but the tensor pipe is idle most of the time anyway,
-    // all 32 lanes of every warp own a row, and two exact three-plane tiles fit in shared memory.
-    constexpr int ROWS = HR ? 64 : T3_ROWS;   // rows of a slot
-    constexpr int CB = ROWS * 16;             // one 8-feature chunk of all rows of a slot
+    constexpr int ROWS = T3_ROWS;             // rows of a slot
+    constexpr int CB = T3_CB;                 // one 8-feature chunk of all rows of a slot
     constexpr int GT = T3_NT / NS;            // threads of a slot group
     constexpr int GW = GT / 32;               // warps of a slot group
-    constexpr int TPR = HR ? GW / 2 : GW / 4; // threads per tile row
+    constexpr int TPR = GW / 4;               // threads per tile row
     constexpr int CPT = T3_HID / TPR;         // hidden columns per thread
     constexpr int DPT = T3_NO / TPR;          // dZ columns of the output layer per thread
     constexpr int NB = P > 1 ? 2 : 1;         // column blocks the epilogue adds
@@ -255,10 +250,10 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const bool worker = warp < T3_NT / 32;
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
-    const int slot = !worker ? 0 : (HR ? quarter >> 1 : warp / GW);
-    const int cgi = HR ? warp >> 2 : (warp - slot * GW) >> 2;        // which CPT of the 64 columns this thread owns
-    const int row = HR ? (quarter & 1) * 32 + lane : quarter * 32 + lane;      // row of the slot's tile (TMEM lane = quarter * 32 + lane)
-    const int gtid = HR ? ((warp >> 2) * 2 + (quarter & 1)) * 32 + lane : tid - slot * GT;   // index within the slot group
+    const int slot = worker ? warp / GW : 0;
+    const int cgi = (warp - slot * GW) >> 2;            // which CPT of the 64 columns this thread owns
+    const int row = quarter * 32 + lane;                // TMEM lane == row of the tile
+    const int gtid = tid - slot * GT;                   // index within the slot group
     const int L = p.L;
     const int n_in = p.net.n_in, n_out = p.net.n_out;
 
@@ -333,14 +328,13 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                     if (k >= cnt[s] * jobs) continue;
                     const int job = k % jobs;
                     const uint32_t sb = sbase + s * p.slot_bytes;
-                    const uint32_t ash = (HR && s == 1) ? 1024u : 0u;       // row-major operands of slot 1 start 64 rows back
                     const uint32_t za = tm + p.col_za[s];
                     const uint32_t full = tc_smem_u32(&s_full[s]), dwb = tc_smem_u32(&s_dw[s]);
                     tc_wait(tc_smem_u32(&s_ready[s]), rdy_par[s]); rdy_par[s] ^= 1u;
                     if (tc_elect_one()) {
                         if (job < L) {
                             const int l = job;
-                            t3_rows_product<P>(za, sb + p.off_act[l] + (P - 1) * p.act_plane[l] - ash, p.act_plane[l], CB,
+                            t3_rows_product<P>(za, sb + p.off_act[l] + (P - 1) * p.act_plane[l], p.act_plane[l], CB,
                                                t3_wf_k<P>(sbase + p.off_const + p.img.off_wf[l], p.img.np[l]), 0, (uint32_t)p.img.np[l],
                                                p.img.np[l], p.img.kp[l] / 16);
                             tc_commit(full);
@@ -348,7 +342,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                             const int l = 2 * L - 1 - job;
                             if (l == L - 1) {
                                 // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
-                                t3_rows_product<P>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane - ash, p.dzl_plane, CB,
+                                t3_rows_product<P>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane, p.dzl_plane, CB,
                                                    tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
                                                    (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], 1);
                                 tc_commit(full);             // dA alone: the epilogue's arithmetic runs under the dW products
@@ -378,7 +372,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                             } else {
                                 // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
                                 if (l > 0) {
-                                    t3_rows_product<P>(za, sb + p.off_act[l + 1] + (P - 1) * p.act_plane[l + 1] - ash, p.act_plane[l + 1], CB,
+                                    t3_rows_product<P>(za, sb + p.off_act[l + 1] + (P - 1) * p.act_plane[l + 1], p.act_plane[l + 1], CB,
                                                        tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
                                                        (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], p.img.np[l] / 16);
                                     tc_commit(full);
@@ -805,8 +799,9 @@ extern "C" int32_t mq_record_width(const mq_net_t *net) {
     return (int32_t)mq_round_up(net->n_in + net->n_out + 2, 16);
 }
 
-// rows = 128: one (ns = 1) or two (ns = 2) 128-row slots; rows = 64: two 64-row slots (kernel template HR = 1)
-static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int rows, int ns, T3Plan *p) {
+// one (ns = 1) or two (ns = 2) 128-row tile slots
+static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, T3Plan *p) {
+    const int rows = T3_ROWS;
     memset(p, 0, sizeof(*p));
     p->net = *net;
     if (!t3_img_build_layout(net, planes, &p->img)) return 0;
@@ -816,7 +811,6 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     p->with_grad = with_grad;
     p->rec_w = rec_w; p->q4 = rec_w / 4;
     if (rec_w != mq_record_width(net) || rec_w > 64) return 0;
-    if (rows == 64 && ns != 2) return 0;
     if (ns == 2 && k0 != 16) return 0;
     if (rows * p->q4 > T3_MAXLD * (T3_NT / ns)) return 0;     // every thread's record words fit its registers
     p->hin_w = (int)mq_round_up(net->n_out + 2, 4);
@@ -835,10 +829,9 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     p->slot_bytes = (int)mq_round_up(off, 1024);
     const int64_t limit = mq_smem_optin() - 256;         // static shared memory: TMEM address + seven mbarriers
     p->off_const = ns * p->slot_bytes;
-    // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] of the last slot on, and a
-    // 64-row slot's M = 128 products read one chunk past their operand
+    // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] of the last slot on
     int total = p->off_const + p->img.bytes;
-    const int need = (ns - 1) * p->slot_bytes + p->off_act[L - 1] + planes * p->act_plane[L - 1] + 9 * cb;
+    const int need = (ns - 1) * p->slot_bytes + p->off_act[L - 1] + planes * p->act_plane[L - 1] + 8 * cb;
     if (total < need) total = need;
     p->smem_bytes = (int)mq_round_up(total, 16);
     if (p->smem_bytes > limit) return 0;
@@ -859,19 +852,17 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     return 1;
 }
 
-// Chooses the schedule: two tiles in flight whenever they fit -- 128-row slots for one and two planes, 64-row slots for
-// the exact three-plane mode -- else one 128-row tile.  MQ_TC_HALF / MQ_TC_FULL (developer aids) force the slot size.
-static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, T3Plan *p, int *ns_out,
-                         int *half_out) {
+// Two tile slots (two tiles in flight) for one and two planes when they fit next to the operand image, else one slot.
+// Measured and dropped for the exact three-plane mode, whose two 128-row tiles do not fit (profiles/r2_tc3_modes.md):
+// two 64-row slots fed by half-filled M = 128 instructions (74 us against 57 us at 65,536 rows: the doubled tensor work
+// is not hidden), and publishing the activations K chunk by K chunk so that layer l + 1's products start under layer l's
+// epilogue (61 us against 57 us: four fence / arrive rounds per phase cost more than the ~2 k cycles of product time
+// they hide per tile).
+static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, T3Plan *p, int *ns_out) {
     const int planes = t3_planes(tc);
-    const int order_default[3][2] = {{128, 2}, {64, 2}, {128, 1}};
-    const int order_half[3][2] = {{64, 2}, {128, 2}, {128, 1}};
-    const int order_full[3][2] = {{128, 2}, {128, 1}, {128, 1}};
-    const int (*order)[2] = (tc & MQ_TC_HALF) ? order_half : ((tc & MQ_TC_FULL) ? order_full : order_default);
-    for (int k = 0; k < 3; ++k)
-        if (t3_plan_try(net, batch, with_grad, planes, rec_w, order[k][0], order[k][1], p)) {
-            *ns_out = order[k][1];
-            *half_out = order[k][0] == 64;
+    for (int ns = 2; ns >= 1; --ns)
+        if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, p)) {
+            *ns_out = ns;
             return 1;
         }
     return 0;
@@ -922,8 +913,8 @@ int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, co
                   int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
     const int planes = t3_planes(head->tc);
     T3Plan p;
-    int ns = 1, half = 0;
-    if (!t3_plan_build(net, batch, with_grad, head->tc, head->rec_w, &p, &ns, &half)) return MQ_ERR_UNSUPPORTED;
+    int ns = 1;
+    if (!t3_plan_build(net, batch, with_grad, head->tc, head->rec_w, &p, &ns)) return MQ_ERR_UNSUPPORTED;
     MQ_REQUIRE(((uintptr_t)head->records & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: records must be 16-byte aligned");
     const int64_t ntiles = mq_ceil_div(batch, p.tile_rows);
     const int64_t sms = mq_sm_count();
@@ -941,26 +932,25 @@ int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, co
     }
     MQ_REQUIRE(((uintptr_t)image & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: image must be 16-byte aligned");
     cudaError_t e = cudaSuccess;
-#define T3_LAUNCH(P_, NS_, HR_, K0_, ACT_)                                                                                   \
+#define T3_LAUNCH(P_, NS_, K0_, ACT_)                                                                                   \
     do {                                                                                                                     \
-        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, HR_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
+        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
         if (e == cudaSuccess)                                                                                                \
-            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, HR_, K0_, ACT_>, dim3(grid), dim3(T3_NTI), (size_t)p.smem_bytes, stream, p, \
+            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, K0_, ACT_>, dim3(grid), dim3(T3_NTI), (size_t)p.smem_bytes, stream, p, \
                               (const unsigned char *)image, head->records, row_idx, batch, *head, (float *)ws, out, logp);   \
     } while (0)
-#define T3_LAUNCH_ACT(P_, NS_, HR_, K0_)                                          \
+#define T3_LAUNCH_ACT(P_, NS_, K0_)                                          \
     do {                                                                          \
-        if (net->act[0] == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, HR_, K0_, MQ_ACT_TANH); \
-        else T3_LAUNCH(P_, NS_, HR_, K0_, MQ_ACT_LRELU);                          \
+        if (net->act[0] == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, K0_, MQ_ACT_TANH); \
+        else T3_LAUNCH(P_, NS_, K0_, MQ_ACT_LRELU);                          \
     } while (0)
 #define T3_LAUNCH_P(P_)                                              \
     do {                                                             \
-        if (ns == 2 && half) T3_LAUNCH_ACT(P_, 2, 1, 16);            \
-        else if (ns == 2) T3_LAUNCH_ACT(P_, 2, 0, 16);               \
-        else if (p.img.k0 == 16) T3_LAUNCH_ACT(P_, 1, 0, 16);        \
-        else T3_LAUNCH_ACT(P_, 1, 0, 32);                            \
+        if (ns == 2) T3_LAUNCH_ACT(P_, 2, 16);                       \
+        else if (p.img.k0 == 16) T3_LAUNCH_ACT(P_, 1, 16);           \
+        else T3_LAUNCH_ACT(P_, 1, 32);                               \
     } while (0)
-    if (planes == 3) T3_LAUNCH_P(3);
+    if (planes == 3) { if (p.img.k0 == 16) T3_LAUNCH_ACT(3, 1, 16); else T3_LAUNCH_ACT(3, 1, 32); }
     else if (planes == 2) T3_LAUNCH_P(2);
     else T3_LAUNCH_P(1);
 #undef T3_LAUNCH_P

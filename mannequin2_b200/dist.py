@@ -51,6 +51,20 @@ def allgather_concat(t, group=None):
         return torch.cat(parts)
 
 
+def allgather_into(out, part, group=None):
+    """out[r * len(part) : (r + 1) * len(part)] = rank r's part (equal sizes)."""
+    if world() == 1:
+        out.copy_(part)
+        return out
+    try:
+        dist.all_gather_into_tensor(out, part.contiguous().reshape(-1), group=group)
+    except (RuntimeError, NotImplementedError):                                        # backend without the fused form
+        parts = [torch.empty_like(part) for _ in range(world())]
+        dist.all_gather(parts, part, group=group)
+        out.copy_(torch.cat(parts))
+    return out
+
+
 def shard_range(n_units, r=None, w=None):
     """Contiguous [lo, hi) slice of n_units owned by rank r of w (remainder to low ranks)."""
     r = rank() if r is None else r

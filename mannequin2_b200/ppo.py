@@ -74,11 +74,14 @@ class _Net(object):
                D.ptr(w0) if w0 is not None else None, D.ptr(w1) if w1 is not None else None, rows, D.ptr(self.records),
                D.stream())
 
-    def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8):
-        """n_steps optimiser steps; idx_table is i32[n_steps, mb] (rows of THIS rank)."""
+    def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8, col0=0, idx_stride=None):
+        """n_steps optimiser steps on the mb rows idx_table[s, col0 : col0 + mb] (i32[n_steps, idx_stride]): the whole
+        table on one GPU, this rank's columns of the global minibatch when sharded."""
+        idx_stride = mb if idx_stride is None else idx_stride
         if mb <= CHAIN_MAX_MB and mqdist.world() == 1:
+            assert col0 == 0 and idx_stride == mb
             return self._train_chain(x, head, idx_table, n_steps, mb, lr, eps)
-        return self._train_loop(x, head, idx_table, n_steps, mb, lr, eps)
+        return self._train_loop(x, head, idx_table, n_steps, mb, lr, eps, col0, idx_stride)
 
     # -- small minibatches: one persistent CTA runs the whole dependent chain ------------
     def _train_chain(self, x, head, idx_table, n_steps, mb, lr, eps):
@@ -91,7 +94,8 @@ class _Net(object):
         self.opt._out = None
 
     # -- large minibatches: all SMs per step, one gradient exchange across GPUs ----------------
-    def _train_loop(self, x, head, idx_table, n_steps, mb, lr, eps):
+    def _train_loop(self, x, head, idx_table, n_steps, mb, lr, eps, col0=0, idx_stride=None):
+        idx_stride = mb if idx_stride is None else idx_stride
         lib = _lib.lib()
         wsb = lib.mq_fused_ws_bytes(ctypes.byref(self.net), mb)
         ws = D.workspace(("fused", id(self)), wsb)
@@ -119,13 +123,13 @@ class _Net(object):
             if mqdist.world() > 1:
                 peer = ctypes.byref(self._peer.descriptor())
                 self._peer.step += n_steps - 1
-            D.call("mq_train_steps", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), ctypes.byref(head), D.ptr(idx_table),
-                   n_steps, mb, scale, D.ptr(value), D.ptr(m), D.ptr(v), self.code, coefs, lr, eps, 0, peer, D.ptr(ws), wsb,
+            D.call("mq_train_steps", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), ctypes.byref(head),
+                   D.ptr(idx_table) + 4 * col0, idx_stride, n_steps, mb, scale, D.ptr(value), D.ptr(m), D.ptr(v), self.code, coefs, lr, eps, 0, peer, D.ptr(ws), wsb,
                    D.stream())
             return
         # fallback (no peer mapping): gradient, NCCL / gloo all-reduce, Adam
         head.tc_image = None
-        base, stride = D.ptr(idx_table), mb * 4
+        base, stride = D.ptr(idx_table) + 4 * col0, idx_stride * 4
         for s in range(n_steps):
             D.call("mq_fused_grad", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(x), base + s * stride, mb,
                    ctypes.byref(head), scale, D.ptr(self.grad), None, None, D.ptr(ws), wsb, D.stream())
@@ -173,6 +177,9 @@ class PPOUpdater(object):
         self.policy = _Net(pnet, np.asarray(policy_params, np.float32), horizon, state_dtype, tc_mode)
         self.value = _Net(vnet, np.asarray(value_params, np.float32), horizon, state_dtype, tc_mode)
         self.normalize = RunningNormalize(horizon=norm_horizon)
+        # update() validates user-supplied minibatch indices on the host (an out-of-range index would read out of bounds
+        # on the device); throughput loops that reuse known-good tables switch it off
+        self.check_indices = True
         self._side = torch.cuda.Stream()
         self._ev_gae, self._ev_val = torch.cuda.Event(), torch.cuda.Event()
         self._bufs = {}
@@ -184,9 +191,39 @@ class PPOUpdater(object):
             self._bufs[name] = t
         return t
 
-    def update_dev(self, obs, act, rew, done, val_idx, pol_idx):
+    def _forward_rows(self, net, obs, n_rows, out, sample=None, logp=None, split=False):
+        """Forward pass over n_rows rows; split=True: this rank computes its slice and the slices are all-gathered
+        (every rank ends up with the full vector, bit-identical everywhere)."""
+        if not split or mqdist.world() == 1:
+            D.call("mq_fused_forward", ctypes.byref(net.net), D.ptr(net.theta), D.ptr(obs), None, n_rows,
+                   D.ptr(out) if out is not None else None, D.ptr(sample) if sample is not None else None,
+                   D.ptr(logp) if logp is not None else None, D.stream())
+            return
+        w, r = mqdist.world(), mqdist.rank()
+        chunk = -(-n_rows // w)
+        lo = min(r * chunk, n_rows)
+        cnt = min(chunk, n_rows - lo)
+        dst = out if out is not None else logp
+        part = self._buf("fwd_part", chunk)
+        full = self._buf("fwd_full", chunk * w)
+        if cnt > 0:
+            smp = (D.ptr(sample) + 4 * lo * self.n_act) if sample is not None else None
+            D.call("mq_fused_forward", ctypes.byref(net.net), D.ptr(net.theta), D.ptr(obs) + 4 * lo * self.n_obs, None, cnt,
+                   D.ptr(part) if out is not None else None, smp, D.ptr(part) if logp is not None else None, D.stream())
+        mqdist.allgather_into(full, part)
+        dst[:n_rows].copy_(full[:n_rows])
+
+    def update_dev(self, obs, act, rew, done, val_idx, pol_idx, replicated=False):
         """All arguments are device tensors: obs f32[N+1,D], act f32[N,A], rew f32[N],
-        done u8[N], val_idx / pol_idx i32[steps, mb].  Returns device (adv, ret)."""
+        done u8[N], val_idx / pol_idx i32[steps, mb].  Returns device (adv, ret).
+
+        With a process group there are two data-parallel forms:
+          replicated=False  every rank passes ITS OWN rollout shard and index tables into it; the global minibatch is
+                            world x mb rows (weak scaling: the problem grows with the number of GPUs);
+          replicated=True   every rank passes the SAME rollout and the SAME tables of GLOBAL minibatches (BASELINE
+                            configs[2]: one 1M-transition rollout, 65,536-row minibatches sharded across the GPUs); rank r
+                            takes columns [r mb/world, (r+1) mb/world) of every minibatch, the two forward passes over the
+                            rollout are split by rows and all-gathered, GAE and the normaliser run replicated."""
         lib = _lib.lib()
         n = rew.numel()
         assert obs.numel() == (n + 1) * self.n_obs
@@ -196,51 +233,58 @@ class PPOUpdater(object):
             D.call("mq_onehot", D.ptr(act), n, self.n_act, D.ptr(onehot), D.stream())
             act = onehot
         assert act.numel() == n * self.n_act
+        world, rank = mqdist.world(), mqdist.rank()
+        split = bool(replicated) and world > 1
+        v_steps, v_mb, p_steps, p_mb = val_idx.shape[0], val_idx.shape[1], pol_idx.shape[0], pol_idx.shape[1]
+        v_col0 = p_col0 = 0
+        v_stride, p_stride = v_mb, p_mb
+        if split:
+            assert v_mb % world == 0 and p_mb % world == 0, "global minibatch must split evenly over the ranks"
+            v_mb, p_mb = v_mb // world, p_mb // world
+            v_col0, p_col0 = rank * v_mb, rank * p_mb
         pol, val = self.policy, self.value
         value = self._buf("value", n + 1)
         adv, ret = self._buf("adv", n), self._buf("ret", n)
         adv_n, logp0 = self._buf("adv_n", n), self._buf("logp0", n)
         main = torch.cuda.current_stream()
         # value predictions for every state incl. the bootstrap state (gae.py:43-45)
-        D.call("mq_fused_forward", ctypes.byref(val.net), D.ptr(val.theta), D.ptr(obs), None, n + 1,
-               D.ptr(value), None, None, D.stream())
+        self._forward_rows(val, obs, n + 1, value, split=split)
         wsb = lib.mq_scan_ws_bytes(n)
         ws = D.workspace("scan", wsb)
         D.call("mq_gae", D.ptr(rew), D.ptr(value), D.ptr(done), n, self.gam, self.lam, D.ptr(adv), D.ptr(ret),
                D.ptr(ws), wsb, D.stream())
         # The value chain and the policy chain are independent: run them on two streams.  Small minibatches: the two
         # 300-step chains are single-CTA kernels side by side.  Large minibatches: each gradient kernel fills the GPU,
-        # but the small reduce / Adam kernels, the launch gaps and (sharded) the exchange latency of one chain run under
-        # the gradient kernels of the other: +4 % on one GPU, +3 % on two.  MQ_PPO_SERIAL=1 forces one stream.
+        # but the small reduce / Adam kernels and the launch gaps of one chain run under the gradient kernels of the other.
+        # MQ_PPO_SERIAL=1 forces one stream.
         # Sharded (world > 1) the two chains share ONE stream: the step kernels spin on peer memory, and a spinning grid of one
         # chain can keep the other chain's gradient kernel (52 K registers per CTA) from becoming resident; with the chains
         # interleaved differently on two ranks neither would progress.  One stream = one fixed order on every rank.
-        concurrent = not os.environ.get("MQ_PPO_SERIAL") and mqdist.world() == 1
+        concurrent = not os.environ.get("MQ_PPO_SERIAL") and world == 1
         vhead = MqHead()
         vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
-        big = val_idx.shape[1] >= 8192 or pol_idx.shape[1] >= 8192
+        big = v_mb >= 8192 or p_mb >= 8192
         if big:
             val.pack(obs, ret, None, None, n)
         if concurrent:
             self._ev_gae.record(main)
             with torch.cuda.stream(self._side):              # value predictor chain (gae.py:66-73)
                 self._side.wait_event(self._ev_gae)
-                val.train(obs, vhead, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
+                val.train(obs, vhead, val_idx, v_steps, v_mb, self.val_lr, col0=v_col0, idx_stride=v_stride)
                 self._ev_val.record(self._side)
         else:
-            val.train(obs, vhead, val_idx, val_idx.shape[0], val_idx.shape[1], self.val_lr)
+            val.train(obs, vhead, val_idx, v_steps, v_mb, self.val_lr, col0=v_col0, idx_stride=v_stride)
         # policy chain on the main stream (ppo.py:24-40)
-        self.normalize.update_dev(adv, n, sharded=True)
+        self.normalize.update_dev(adv, n, sharded=world > 1 and not split)
         self.normalize.apply_dev(adv, n, out=adv_n, fuse_tanh=True)
-        D.call("mq_fused_forward", ctypes.byref(pol.net), D.ptr(pol.theta), D.ptr(obs), None, n, None,
-               D.ptr(act), D.ptr(logp0), D.stream())
+        self._forward_rows(pol, obs, n, None, sample=act, logp=logp0, split=split)
         head = MqHead()
         head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
         head.ent = self.ent_coef
         head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
         if big:
             pol.pack(obs, act, adv_n, logp0, n)
-        pol.train(obs, head, pol_idx, pol_idx.shape[0], pol_idx.shape[1], self.pol_lr)
+        pol.train(obs, head, pol_idx, p_steps, p_mb, self.pol_lr, col0=p_col0, idx_stride=p_stride)
         if concurrent:
             main.wait_event(self._ev_val)
         return adv, ret
@@ -261,10 +305,58 @@ class PPOUpdater(object):
         D.call("mq_bootstrap_segments", D.ptr(rew), D.ptr(done), D.ptr(v_next), n_seg, seg_len, self.gam, D.stream())
         return self.update_dev(chunk["obs"], chunk["act"], rew, done, val_idx, pol_idx)
 
-    def update(self, obs, act, rew, done, val_idx, pol_idx):
-        """Host arrays in, new (policy_params, value_params) host arrays out (end-to-end call)."""
-        up = lambda a, dt: D.from_host(np.ascontiguousarray(a, dtype=dt))
-        self.update_dev(up(obs, np.float32), up(act, np.int32 if self.discrete else np.float32), up(rew, np.float32),
-                        up(np.asarray(done, dtype=np.uint8), np.uint8), up(val_idx, np.int32),
-                        up(pol_idx, np.int32))
+    # ---- public host-side call ------------------------------------------------------------------------------------
+    def _to_dev(self, a, dtype):
+        """Host array (NumPy, pageable) or host / device torch tensor -> device tensor.  Pinned torch tensors are copied
+        asynchronously on the current stream; device tensors pass through."""
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+            return a.to(D.device(), non_blocking=True)
+        return D.from_host(np.ascontiguousarray(a, dtype=dtype))
+
+    def prefetch(self, obs, act, rew, done):
+        """Start uploading the NEXT rollout (pinned host tensors) on a copy stream while the current update runs; the
+        returned handle is passed to update() in place of the four arrays."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            dev = [self._to_dev(a, dt) for a, dt in zip((obs, act, rew, done), (np.float32, np.int32 if self.discrete else
+                                                                                  np.float32, np.float32, np.uint8))]
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return ("prefetched", dev, ev)
+
+    def update(self, obs, act=None, rew=None, done=None, val_idx=None, pol_idx=None, *, replicated=False, out=None):
+        """Host arrays in, new (policy_params, value_params) host arrays out -- the end-to-end call of one iteration of
+        benchmarks/ppo.py:22-40.  obs/act/rew/done: NumPy arrays, pinned torch tensors, or the handle of prefetch();
+        val_idx / pol_idx: NumPy arrays or device tensors (index tables that stay resident between updates).
+        out = (policy, value) pinned host tensors to receive the parameters (optional)."""
+        main = torch.cuda.current_stream()
+        if isinstance(obs, tuple) and obs and obs[0] == "prefetched":
+            _, dev, ev = obs
+            main.wait_event(ev)
+            for a in dev:
+                a.record_stream(main)
+            d_obs, d_act, d_rew, d_done = dev
+        else:
+            d_obs = self._to_dev(obs, np.float32)
+            d_act = self._to_dev(act, np.int32 if self.discrete else np.float32)
+            d_rew = self._to_dev(rew, np.float32)
+            d_done = self._to_dev(done if isinstance(done, torch.Tensor) else np.asarray(done, dtype=np.uint8), np.uint8)
+        d_vi, d_pi = self._to_dev(val_idx, np.int32), self._to_dev(pol_idx, np.int32)
+        if self.check_indices:
+            n = d_rew.numel()
+            for t in (d_vi, d_pi):
+                lo, hi = int(t.min()), int(t.max())
+                if lo < 0 or hi >= n:
+                    raise ValueError("minibatch index out of range: [%d, %d] for %d transitions" % (lo, hi, n))
+        self.update_dev(d_obs, d_act, d_rew, d_done, d_vi, d_pi, replicated=replicated)
+        if out is not None:
+            out[0].copy_(self.policy.theta, non_blocking=True)
+            out[1].copy_(self.value.theta, non_blocking=True)
+            main.synchronize()
+            return out
         return D.to_host(self.policy.theta), D.to_host(self.value.theta)

@@ -274,8 +274,10 @@ def policy_spec(n_obs, n_act, hid=64, n_hid=2):
     return spec
 
 
-def policy_logprob(theta, spec, obs, act):
-    outs = mlp_forward(theta[:spec["n_mlp_params"]], _mlp_part(spec), obs)
+def policy_logprob(theta, spec, obs, act, dtype=np.float64):
+    """dtype = np.float32 keeps the Tanh net in float32 like the reference (basicnet.py:193,210): the CPU
+    baseline's setting; the parity tests use the float64 default."""
+    outs = mlp_forward(theta[:spec["n_mlp_params"]], _mlp_part(spec), obs, dtype=dtype)
     ls = np.asarray(theta[spec["logstd_off"]:], dtype=np.float64)
     return gauss_logprob(outs[-1], ls, act), outs
 
@@ -286,15 +288,15 @@ def _mlp_part(spec):
     return s
 
 
-def policy_logprob_grad(theta, spec, obs, act, g, outs=None):
+def policy_logprob_grad(theta, spec, obs, act, g, outs=None, dtype=np.float64):
     """Flat gradient [P] of sum_b g_b * logp_b, batch mean (F4)."""
     if outs is None:
-        _, outs = policy_logprob(theta, spec, obs, act)
+        _, outs = policy_logprob(theta, spec, obs, act, dtype=dtype)
     ls = np.asarray(theta[spec["logstd_off"]:], dtype=np.float64)
     d_mu, d_ls = gauss_logprob_grads(outs[-1], ls, act, g)
     grad = np.zeros(spec["n_params"], dtype=np.float32)
     grad[:spec["n_mlp_params"]] = mlp_backward(
-        theta[:spec["n_mlp_params"]], _mlp_part(spec), obs, outs, d_mu)
+        theta[:spec["n_mlp_params"]], _mlp_part(spec), obs, outs, d_mu, dtype=dtype)
     grad[spec["logstd_off"]:] = (d_ls.sum(axis=0) / len(d_mu)).astype(np.float32)
     return grad
 
@@ -420,23 +422,23 @@ def mlp_sgd_step(theta, spec, opt, x, onehot, l2=0.01):
     return opt.get_value().astype(np.float32)
 
 
-def value_sgd_step(theta, spec, opt, obs, target):
+def value_sgd_step(theta, spec, opt, obs, target, dtype=np.float64):
     """benchmarks/gae.py:20-23: dy = labels - outputs."""
-    outs = mlp_forward(theta, spec, obs)
-    dy = np.asarray(target, np.float64).reshape(outs[-1].shape) - outs[-1]
-    opt.apply_gradient(mlp_backward(theta, spec, obs, outs, dy))
+    outs = mlp_forward(theta, spec, obs, dtype=dtype)
+    dy = np.asarray(target, dtype).reshape(outs[-1].shape) - outs[-1]
+    opt.apply_gradient(mlp_backward(theta, spec, obs, outs, dy, dtype=dtype))
     return opt.get_value().astype(np.float32)
 
 
 def ppo_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4,
-                    lo=0.8, hi=1.2, ent_coef=0.0):
+                    lo=0.8, hi=1.2, ent_coef=0.0, dtype=np.float64):
     """benchmarks/ppo.py:33-40 on an already gathered minibatch.
 
     ent_coef (not in the reference): + ent_coef * gauss_entropy
     in the objective, i.e. + ent_coef on every logstd gradient entry."""
-    logp, outs = policy_logprob(theta, spec, obs, act)
+    logp, outs = policy_logprob(theta, spec, obs, act, dtype=dtype)
     g = ppo_clip_weight(logp, logp_old, adv, lo, hi).astype(np.float32)
-    grad = policy_logprob_grad(theta, spec, obs, act, g, outs)
+    grad = policy_logprob_grad(theta, spec, obs, act, g, outs, dtype=dtype)
     if ent_coef:
         grad = np.array(grad, dtype=np.float32)
         grad[spec["logstd_off"]:spec["logstd_off"] + act.shape[1]] += np.float32(ent_coef)
@@ -446,24 +448,24 @@ def ppo_policy_step(theta, spec, opt, obs, act, adv, logp_old, lr=3e-4,
 
 def ppo_update(pol_theta, pol_spec, pol_opt, val_theta, val_spec, val_opt,
                norm, obs, act, rew, done, val_idx, pol_idx,
-               gam=0.99, lam=0.95, pol_lr=3e-4, ent_coef=0.0):
+               gam=0.99, lam=0.95, pol_lr=3e-4, ent_coef=0.0, dtype=np.float64):
     """One chunk of benchmarks/ppo.py:22-40 + benchmarks/gae.py:34-75.
 
     obs[N+1,D], act[N,A], rew[N], done[N]; val_idx/pol_idx are the
     [steps, minibatch] int tables the reference draws with randint.
     """
     n = len(rew)
-    value = mlp_forward(val_theta, val_spec, obs)[-1].reshape(-1).astype(np.float32)
+    value = mlp_forward(val_theta, val_spec, obs, dtype=dtype)[-1].reshape(-1).astype(np.float32)
     adv, ret = gae_advantages(rew, value, done, gam, lam)
     for idx in val_idx:                                   # gae.py:71-73
         val_theta = value_sgd_step(val_theta, val_spec, val_opt,
-                                   obs[:n][idx], ret[idx].reshape(-1, 1))
+                                   obs[:n][idx], ret[idx].reshape(-1, 1), dtype=dtype)
     adv_n = np.tanh(norm(adv)).astype(np.float32)         # ppo.py:24-25
-    logp_old, _ = policy_logprob(pol_theta, pol_spec, obs[:n], act)
+    logp_old, _ = policy_logprob(pol_theta, pol_spec, obs[:n], act, dtype=dtype)
     for idx in pol_idx:                                   # ppo.py:29-40
         pol_theta = ppo_policy_step(pol_theta, pol_spec, pol_opt, obs[:n][idx],
                                     act[idx], adv_n[idx], logp_old[idx], pol_lr,
-                                    ent_coef=ent_coef)
+                                    ent_coef=ent_coef, dtype=dtype)
     return pol_theta, val_theta, dict(adv=adv, ret=ret, adv_n=adv_n,
                                       logp_old=logp_old, value=value)
 

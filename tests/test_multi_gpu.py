@@ -139,3 +139,68 @@ def test_sharded_es_population_matches_oracle(tmp_path):
         want, _, _ = O.es_generation(want, spec, opt, norm, noise[g], obs[g], coef)
     assert np.max(np.abs(got[0] - theta0)) > 1e-3
     assert np.max(np.abs(got[0] - want)) < 2e-4, np.max(np.abs(got[0] - want))
+
+
+def _strong_data(n, mb, epochs):
+    sys.path.insert(0, ROOT)
+    from bench import ppo_rollout
+    rs = np.random.RandomState(91)
+    o, a, r, d = ppo_rollout(rs, n, p_done=1.0 / 300, cut=700)
+    vi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+    pi = np.concatenate([rs.permutation(n).astype(np.int32).reshape(n // mb, mb) for _ in range(epochs)])
+    return o, a, r, d, vi, pi
+
+
+def _strong_worker(rank, world, port, out_dir, tc_mode):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.ppo import PPOUpdater, init_mlp
+    np.random.seed(5)
+    pol0 = np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)])
+    val0 = init_mlp(11, [64, 64, 1], 0.1)
+    upd = PPOUpdater(11, 3, policy_params=pol0, value_params=val0, tc_mode=tc_mode)
+    data = _strong_data(32768, 16384, 2)                    # the SAME rollout and global minibatch tables on every rank
+    upd.update_dev(*[D.from_host(x) for x in data], replicated=True)
+    torch.cuda.synchronize()
+    assert upd.policy.records is not None, "8,192 rows per rank must take the record-fed tensor-core kernel"
+    assert upd.policy.exchange() == "ll", upd.policy.exchange()
+    np.save(os.path.join(out_dir, "pol%d.npy" % rank), D.to_host(upd.policy.theta))
+    np.save(os.path.join(out_dir, "val%d.npy" % rank), D.to_host(upd.value.theta))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tc_mode", ["exact", "bf16x2"])
+def test_strong_scaling_form_matches_oracle(tmp_path, tc_mode):
+    """BASELINE configs[2] as SURVEY 8e words it: ONE rollout, every global minibatch split by rows over the GPUs (8,192
+    rows per rank here, so the record-fed tcgen05 gradient kernel and the in-kernel low-latency exchange run TOGETHER),
+    forward passes split and all-gathered.  Replicas end bit-identical and equal the oracle's update of the whole problem
+    (benchmarks/ppo.py:22-40 + gae.py:34-75) -- the sharded run IS the single-GPU problem."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000 + (41 if tc_mode == "exact" else 43)
+    mp.spawn(_strong_worker, args=(2, port, str(tmp_path), tc_mode), nprocs=2, join=True)
+    pol = [np.load(os.path.join(tmp_path, "pol%d.npy" % r)) for r in range(2)]
+    val = [np.load(os.path.join(tmp_path, "val%d.npy" % r)) for r in range(2)]
+    assert np.array_equal(pol[0], pol[1]) and np.array_equal(val[0], val[1])     # replicas stay identical
+    from oracle import mq_oracle as O
+    from mannequin2_b200.ppo import init_mlp
+    np.random.seed(5)
+    pol0 = np.concatenate([init_mlp(11, [64, 64, 3], 0.1), np.zeros(3, np.float32)])
+    val0 = init_mlp(11, [64, 64, 1], 0.1)
+    o, a, r, d, vi, pi = _strong_data(32768, 16384, 2)
+    pol_spec, val_spec = O.policy_spec(11, 3), O.mlp_spec(11, [64, 64, 1], [1, 1, 0])
+    want_pol, want_val, _ = O.ppo_update(pol0.copy(), pol_spec, O.AdamO(pol0, horizon=10), val0.copy(), val_spec,
+                                         O.AdamO(val0, horizon=10, lr=0.003), O.RunningNormalizeO(horizon=2),
+                                         o, a, r, d.astype(bool), vi, pi)
+    steps = len(vi)
+    frac = {"exact": 0.007, "bf16x2": 0.07}[tc_mode]         # tests/test_compat_gpu.py: UPDATE_FRAC
+    assert np.max(np.abs(pol[0] - pol0)) > 1e-4
+    assert np.max(np.abs(pol[0] - want_pol)) < frac * 3e-4 * (1 + steps), np.max(np.abs(pol[0] - want_pol))
+    assert np.max(np.abs(val[0] - want_val)) < frac * 3e-3 * (1 + steps), np.max(np.abs(val[0] - want_val))

@@ -54,9 +54,8 @@ for mb in sizes:
     wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
     want = O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs)
     scale = float(np.max(np.abs(want)))
-    for name, planes, records in (("array-fed exact", 3, False), ("P=3 half", 3 | 0x40, True), ("P=3 full", 3 | 0x80, True),
-                                  ("P=2 half", 2 | 0x40, True), ("P=2 full", 2 | 0x80, True), ("P=1 half", 1 | 0x40, True),
-                                  ("P=1 full", 1 | 0x80, True)):
+    for name, planes, records in (("array-fed exact", 3, False), ("P=3 pipe", 3, True), ("P=3 nopipe", 3 | 0x40, True),
+                                  ("P=2", 2, True), ("P=1 pipe", 1, True), ("P=1 nopipe", 1 | 0x40, True)):
         image = None
         if records:
             image = torch.zeros(lib.mq_tc_image_bytes(net, planes & 3), dtype=torch.uint8, device=dev)
