@@ -46,6 +46,7 @@ struct T3Plan {
     int off_const, smem_bytes;
     // TMEM columns
     int col_za[2], col_acc[T3_MAXL], col_rb;
+    int col_save[2];             // fp32 hidden activations kept in TMEM for the backward pass (-1: rebuilt from the planes)
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------
@@ -61,6 +62,17 @@ __device__ __forceinline__ void t3_ld16_nowait(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void t3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t3_st16_nowait(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void t3_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void t3_mbar_init(uint64_t *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(b)), "r"(count));
@@ -563,9 +575,11 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                                 v[4 * j + 2] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 2] + v2[4 * j + 2] : v[4 * j + 2]) + bb.z, leak);
                                 v[4 * j + 3] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 3] + v2[4 * j + 3] : v[4 * j + 3]) + bb.w, leak);
                             }
+                            if (p.with_grad && p.col_save[slot] >= 0) t3_st16_nowait(tlane + p.col_save[slot] + l * T3_HID + c0, v);
                             t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8, row, v);
                             t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8 + 1, row, v + 8);
                         }
+                        if (p.with_grad && p.col_save[slot] >= 0) t3_st_wait();
                     }
                     t3_warp_ready(rdy, lane);
                 }
@@ -716,8 +730,12 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                             float a[16], g[16], g2[16];
                             t3_ld16_nowait(za + c0, g);
                             if (NB == 2) t3_ld16_nowait(za + T3_HID + c0, g2);
-                            t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8, row, a);
-                            t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8 + 1, row, a + 8);
+                            if (p.col_save[slot] >= 0) {
+                                t3_ld16_nowait(tlane + p.col_save[slot] + (l - 1) * T3_HID + c0, a);
+                            } else {
+                                t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8, row, a);
+                                t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8 + 1, row, a + 8);
+                            }
                             t3_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], NB == 2 ? g[j] + g2[j] : g[j], HACT, leak);
@@ -839,6 +857,14 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     const int nbk = planes > 1 ? 2 : 1;
     int col = 0;
     for (int s = 0; s < ns; ++s) { p->col_za[s] = col; col += nbk * T3_HID; }
+    {   // fp32 copy of the hidden activations for the backward pass, when the columns are there
+        int acc_cols = nbk * T3_NO;
+        for (int l = 0; l < L; ++l) acc_cols += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8;
+        const bool fits = with_grad && col + ns * (L - 1) * T3_HID + acc_cols <= 512;
+        for (int s = 0; s < 2; ++s) p->col_save[s] = -1;
+        if (fits)
+            for (int s = 0; s < ns; ++s) { p->col_save[s] = col; col += (L - 1) * T3_HID; }
+    }
     for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8; }
     p->col_rb = col; col += nbk * T3_NO;
     if (col > 512) return 0;
