@@ -451,7 +451,6 @@ class PPOLargeWorkload(object):
         from mannequin2_b200.ppo import PPOUpdater
         from mannequin2_b200 import _lib as L
         out = {}
-        base_theta = self.upd.policy.theta.clone()
         ref_grad = None
         for mode in ("exact", "bf16x2", "bf16"):
             np.random.seed(0)
@@ -467,17 +466,18 @@ class PPOLargeWorkload(object):
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            # one gradient at FIXED parameters (the exact updater's), this mode's arithmetic
-            head = self.policy_head(upd)
-            upd.policy.theta.copy_(base_theta)
-            D.call("mq_tc_image_build", C.byref(upd.policy.net), D.ptr(upd.policy.theta), upd.policy.planes,
-                   D.ptr(upd.policy.image), D.stream())
-            kms, _ = self.grad_kernel_time(upd.policy, head, D.ptr(self.dev[0][5]), self.MB, reps=8)
-            wsb = L.lib().mq_fused_ws_bytes(C.byref(upd.policy.net), self.MB)
+            # one gradient on IDENTICAL inputs (the exact updater's parameters and packed records), this mode's arithmetic
+            planes = upd.policy.planes
+            head = self.policy_head(self.upd)
+            image = t.zeros(int(L.lib().mq_tc_image_bytes(C.byref(self.upd.policy.net), planes)), dtype=t.uint8, device="cuda")
+            D.call("mq_tc_image_build", C.byref(self.upd.policy.net), D.ptr(self.upd.policy.theta), planes, D.ptr(image), D.stream())
+            head.tc, head.tc_image = planes, D.ptr(image)
+            kms, _ = self.grad_kernel_time(self.upd.policy, head, D.ptr(self.dev[0][5]), self.MB, reps=8)
+            wsb = L.lib().mq_fused_ws_bytes(C.byref(self.upd.policy.net), self.MB)
             ws = D.workspace("bench", wsb)
             g = t.zeros(5126, device="cuda")
-            D.call("mq_fused_grad", C.byref(upd.policy.net), D.ptr(upd.policy.theta), D.ptr(self.dev[0][0]), D.ptr(self.dev[0][5]),
-                   self.MB, C.byref(head), 1.0 / self.MB, D.ptr(g), None, None, D.ptr(ws), wsb, D.stream())
+            D.call("mq_fused_grad", C.byref(self.upd.policy.net), D.ptr(self.upd.policy.theta), D.ptr(self.dev[0][0]),
+                   D.ptr(self.dev[0][5]), self.MB, C.byref(head), 1.0 / self.MB, D.ptr(g), None, None, D.ptr(ws), wsb, D.stream())
             g = g.double().cpu().numpy()
             if ref_grad is None:
                 ref_grad = g
@@ -813,22 +813,27 @@ class VAEWorkload(object):
         return 110                                   # node-by-node graph: forward + backprop kernels of two evaluations
 
     def dominant_kernel(self, peaks):
-        """gemm_tc_kernel on the widest layer (4096 x 784 x 400, y = x W), timed alone."""
+        """pack + gemm_tma_kernel on the widest layer (4096 x 784 x 400, y = x W), timed alone."""
         t, D = self.torch, self.D
+        from mannequin2_b200 import _lib as L
         x, w = t.randn(4096, 784, device=D.device()), t.randn(784, 400, device=D.device())
         y = t.empty(4096, 400, device=D.device())
+        wsb = int(L.lib().mq_gemm_ws_bytes(4096, 400, 784))
+        ws = t.empty(wsb, dtype=t.uint8, device=D.device())
         times = []
         for k in range(8):
             e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             e0.record()
-            D.call("mq_gemm", D.ptr(x), 784, 1, D.ptr(w), 400, 1, D.ptr(y), 4096, 400, 784, 1.0, D.stream())
+            D.call("mq_gemm_ws", D.ptr(x), 784, 1, D.ptr(w), 400, 1, D.ptr(y), 4096, 400, 784, 1.0, D.ptr(ws), wsb, D.stream())
             e1.record(); e1.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = float(np.median(times[2:]))
         tf = 2.0 * 4096 * 784 * 400 / (ms * 1e-3) / 1e12
-        return dict(bound="tensor", kernel="gemm_tc_kernel (4096x784x400, three bf16 planes)", achieved=tf, peak=peaks["bf16"],
-                    unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None, peak_source=peaks["source"], ms_per_launch=ms,
-                    note="fp32-exact product = 6 bf16 plane pairs; bound by in-kernel operand staging (DESIGN.md 3.5)")
+        return dict(bound="tensor", kernel="pack_planes + gemm_tma_kernel<3> (4096x784x400, three bf16 planes, TMA-fed)", achieved=tf,
+                    peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None, peak_source=peaks["source"],
+                    ms_per_launch=ms, issued_bf16_tflops=6 * tf, issued_frac=6 * tf / peaks["bf16"],
+                    note="fp32-exact product = 6 bf16 plane pairs issued as wide tcgen05 instructions from TMA-loaded, "
+                         "128-byte-swizzled planes (DESIGN.md 3.5)")
 
 
 class ClosedLoopWorkload(PPOLargeWorkload):
@@ -987,17 +992,40 @@ def kernel_sweep(peaks):
     bsz, kin, nout = 4096, 784, 400
     x, w, gy = torch.randn(bsz, kin, device=dev), torch.randn(kin, nout, device=dev), torch.randn(bsz, nout, device=dev)
     y, dx, dw = torch.empty(bsz, nout, device=dev), torch.empty(bsz, kin, device=dev), torch.empty(kin, nout, device=dev)
-    def three():
-        D.call("mq_gemm", D.ptr(x), kin, 1, D.ptr(w), nout, 1, D.ptr(y), bsz, nout, kin, 1.0, D.stream())      # y = x W
-        D.call("mq_gemm", D.ptr(gy), nout, 1, D.ptr(w), 1, nout, D.ptr(dx), bsz, kin, nout, 1.0, D.stream())    # dx = g W^T
-        D.call("mq_gemm", D.ptr(x), 1, kin, D.ptr(gy), nout, 1, D.ptr(dw), kin, nout, bsz, 1.0, D.stream())     # dW = x^T g
+    wsb = max(int(lib.mq_gemm_ws_bytes(bsz, nout, kin)), int(lib.mq_gemm_ws_bytes(bsz, kin, nout)), int(lib.mq_gemm_ws_bytes(kin, nout, bsz)))
+    gws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+
+    def three(tc):
+        D.call("mq_gemm_ex", D.ptr(x), kin, 1, D.ptr(w), nout, 1, D.ptr(y), bsz, nout, kin, 1.0, tc, D.ptr(gws), wsb, D.stream())    # y = x W
+        D.call("mq_gemm_ex", D.ptr(gy), nout, 1, D.ptr(w), 1, nout, D.ptr(dx), bsz, kin, nout, 1.0, tc, D.ptr(gws), wsb, D.stream())  # dx = g W^T
+        D.call("mq_gemm_ex", D.ptr(x), 1, kin, D.ptr(gy), nout, 1, D.ptr(dw), kin, nout, bsz, 1.0, tc, D.ptr(gws), wsb, D.stream())   # dW = x^T g
     flops = 3 * 2.0 * bsz * kin * nout
-    for mode, key in ((1, "affine_4096x784x400_fwd_dx_dw_tcgen05"), (0, "affine_4096x784x400_fwd_dx_dw_ffma")):
-        lib.mq_debug_set_gemm_tc_mode(mode)
-        ms = timeit(three, reps=8)
+    pairs = {3: 6, 2: 3, 1: 1}
+    for tc, key in ((3, "affine_4096x784x400_fwd_dx_dw_tcgen05_exact"), (2, "affine_4096x784x400_fwd_dx_dw_tcgen05_bf16x2"),
+                    (1, "affine_4096x784x400_fwd_dx_dw_tcgen05_bf16"), (L.TC_OFF, "affine_4096x784x400_fwd_dx_dw_ffma")):
+        ms = timeit(lambda: three(tc), reps=8)
         out[key] = dict(flop=flops, ms=ms, fp32_tflops=flops / ms / 1e9,
-                        frac_of_bf16_peak=flops / ms / 1e9 / peaks["bf16"], issued_bf16_tflops=(6 * flops / ms / 1e9) if mode else None)
-    lib.mq_debug_set_gemm_tc_mode(1)
+                        frac_of_bf16_peak=flops / ms / 1e9 / peaks["bf16"],
+                        issued_bf16_tflops=(pairs[tc] * flops / ms / 1e9) if tc in pairs else None,
+                        note="pack of both operands into bf16 planes + TMA-fed tcgen05 GEMM (+ split-K finish for dW), three products")
+    # the forward product alone, and a square 4096^3 product, per precision mode (kernel + pack, CUDA events)
+    big = 4096
+    xa, xb, xc = torch.randn(big, big, device=dev), torch.randn(big, big, device=dev), torch.empty(big, big, device=dev)
+    wsb2 = int(lib.mq_gemm_ws_bytes(big, big, big))
+    gws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
+    for tc, name in ((3, "exact"), (2, "bf16x2"), (1, "bf16")):
+        ms = timeit(lambda: D.call("mq_gemm_ex", D.ptr(x), kin, 1, D.ptr(w), nout, 1, D.ptr(y), bsz, nout, kin, 1.0, tc, D.ptr(gws),
+                                   wsb, D.stream()), reps=8)
+        fl = 2.0 * bsz * kin * nout
+        out["gemm_4096x784x400_%s" % name] = dict(ms=ms, fp32_tflops=fl / ms / 1e9, frac_of_bf16_peak=fl / ms / 1e9 / peaks["bf16"],
+                                                  issued_bf16_tflops=pairs[tc] * fl / ms / 1e9)
+        ms = timeit(lambda: D.call("mq_gemm_ex", D.ptr(xa), big, 1, D.ptr(xb), big, 1, D.ptr(xc), big, big, big, 1.0, tc, D.ptr(gws2),
+                                   wsb2, D.stream()), reps=5)
+        fl = 2.0 * big ** 3
+        out["gemm_4096cubed_%s" % name] = dict(ms=ms, fp32_tflops=fl / ms / 1e9, frac_of_bf16_peak=fl / ms / 1e9 / peaks["bf16"],
+                                               issued_bf16_tflops=pairs[tc] * fl / ms / 1e9,
+                                               frac_issued_of_bf16_peak=pairs[tc] * fl / ms / 1e9 / peaks["bf16"])
+    del xa, xb, xc, gws2
     return out
 
 

@@ -152,8 +152,6 @@ int mq_bootstrap_segments(float *rew, uint8_t *done, const float *v_next, int64_
 int mq_debug_use_chain_grad(int on);
 /* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */
 int mq_debug_set_chain_warps(int nw);
-/* developer aid: tcgen05 GEMM for wide layers: 0 never, 1 automatic (>= 2^26 multiply-adds), 2 whenever possible */
-int mq_debug_set_gemm_tc_mode(int mode);
 /* peak microbenchmarks for bench.py's roofline denominators: *flops_out = FLOPs the launch executes;
  * the caller times it with CUDA events.  mq_bench_tensor: back-to-back tcgen05.mma M128 N256 from resident operands,
  * tf32 = 0: kind::f16 (bf16 inputs), 1: kind::tf32. */
@@ -336,6 +334,13 @@ int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t 
 /* The same; with a workspace, products with few output tiles and a long contraction are split along K (deterministic) */
 int mq_gemm_ws(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs,
                float *c, int64_t m, int64_t n, int64_t k, float alpha, void *ws, int64_t ws_bytes, void *stream);
+/* workspace with which mq_gemm_ws / mq_gemm_ex take the TMA-fed tcgen05 path for this shape (packed bf16 planes of both
+ * operands + split-K partials) */
+int64_t mq_gemm_ws_bytes(int64_t m, int64_t n, int64_t k);
+/* The same with per-call MQ_TC_* flags: planes (precision mode), MQ_TC_FORCE (tensor-core kernel whatever the size),
+ * MQ_TC_OFF (FFMA kernel). */
+int mq_gemm_ex(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs, float *c,
+               int64_t m, int64_t n, int64_t k, float alpha, int32_t tc, void *ws, int64_t ws_bytes, void *stream);
 int mq_add_bias(const float *x, const float *b, float *y, int64_t rows, int64_t cols, void *stream);
 int mq_binary(const float *a, const float *b, float *out, int64_t n, int64_t b_period, int op,
               void *stream);                   /* op 0: a+b, 1: a*b; b is broadcast with period */

@@ -65,7 +65,6 @@ SIGNATURES = {
     "mq_debug_set_tile_rows": (c_int, [c_int]),
     "mq_debug_use_chain_grad": (c_int, [c_int]),
     "mq_debug_set_chain_warps": (c_int, [c_int]),
-    "mq_debug_set_gemm_tc_mode": (c_int, [c_int]),
     "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
                              c_double, c_int, P]),
@@ -113,6 +112,9 @@ SIGNATURES = {
     "mq_gemm": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64,
                         c_float, P]),
     "mq_gemm_ws": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64, c_float, P, c_int64, P]),
+    "mq_gemm_ws_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "mq_gemm_ex": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, c_int64, c_float, c_int32, P, c_int64,
+                           P]),
     "mq_add_bias": (c_int, [P, P, P, c_int64, c_int64, P]),
     "mq_binary": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "mq_col_sum": (c_int, [P, P, c_int64, c_int64, c_float, P, P]),

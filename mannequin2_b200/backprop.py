@@ -91,9 +91,10 @@ def multiply(a, b):
 
 def _gemm(a, a_rs, a_cs, b, b_rs, b_cs, m, n, k, like):
     c = _new((m, n), like)
-    if k >= 1024 and m * n <= (1 << 22):
-        # few output tiles, long contraction (dW = x^T g over a large batch): let the GEMM split along K
-        wsb = min(8 * m * n * 4, 64 << 20)
+    if m * n * k >= (1 << 26) or (k >= 1024 and m * n <= (1 << 22)):
+        # large products: TMA-fed tcgen05 kernel (needs room for the packed bf16 planes); few output tiles with a long
+        # contraction (dW = x^T g over a large batch): split along K
+        wsb = int(D._lib.lib().mq_gemm_ws_bytes(m, n, k))
         ws = D.workspace("gemm", wsb)
         D.call("mq_gemm_ws", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.ptr(ws), wsb, D.stream())
     else:

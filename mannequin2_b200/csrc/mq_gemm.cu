@@ -125,37 +125,69 @@ gemm_splitk_finish_kernel(GemmArgs g, const float *__restrict__ partial, int spl
     }
 }
 
-int mq_gemm_tc_launch(const GemmArgs &g, int64_t splits, void *stream);      // mq_gemm_tc.cu
+int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack, void *stream);      // mq_gemm_tma.cu
+int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes);
 
-// Decide kernel, tile size and split-K; `ws` may be NULL (then no split).
-static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, void *stream, const char *what) {
+// split-K of the tensor-core GEMM: products with few 128 x 128 output tiles and a long contraction (dW = x^T g)
+static int64_t gemm_tc_splits(int64_t m, int64_t n, int64_t k, int64_t *k_per_split) {
+    const int sms = mq_sm_count();
+    const int64_t tiles = mq_ceil_div(m, 128) * mq_ceil_div(n, 128);
+    int64_t splits = 1;
+    if (2 * tiles <= sms && k >= 1024) {
+        splits = sms / tiles;
+        if (splits > k / 256) splits = k / 256;
+        if (splits < 1) splits = 1;
+    }
+    *k_per_split = mq_round_up(mq_ceil_div(k > 0 ? k : 1, splits), 64);
+    return mq_ceil_div(k > 0 ? k : 1, *k_per_split);
+}
+
+static bool gemm_tc_wanted(const GemmArgs &g, int32_t tc) {
+    if ((tc & MQ_TC_OFF) || g.a_ones_row != 0 || g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
+    if (tc & MQ_TC_FORCE) return true;
+    return g.m * g.n * g.k >= (1LL << 26) && g.n >= 64 && g.k >= 64 && g.m >= 128;
+}
+
+// bytes of workspace with which gemm_run can take the tensor-core path for this shape (packed planes + split-K partials)
+static int64_t gemm_tc_ws_bytes(int64_t m, int64_t n, int64_t k, int planes) {
+    int64_t kps;
+    const int64_t splits = gemm_tc_splits(m, n, k, &kps);
+    return mq_gemm_tma_pack_bytes(m, n, k, planes) + (splits > 1 ? mq_round_up(splits * m * n * (int64_t)sizeof(float), 256) : 0);
+}
+
+extern "C" int64_t mq_gemm_ws_bytes(int64_t m, int64_t n, int64_t k) {
+    if (m <= 0 || n <= 0 || k <= 0) return 256;
+    // FFMA split-K partials (at most 64 splits, only for few-tile products) or the tensor-core path, whichever is larger
+    const int64_t ffma = (mq_ceil_div(m, 32) * mq_ceil_div(n, 32) < mq_sm_count() && k >= 512) ? 64 * m * n * (int64_t)sizeof(float) : 0;
+    const int64_t tc = gemm_tc_ws_bytes(m, n, k, 3);
+    return (ffma > tc ? ffma : tc) + 256;
+}
+
+// Decide kernel, tile size and split-K; `ws` may be NULL (then no split and no tensor-core path).
+static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, int32_t tc, void *stream, const char *what) {
     if (g.m <= 0 || g.n <= 0) return MQ_OK;
     const int sms = mq_sm_count();
-    if (g.a_ones_row == 0) {   // large problems: tcgen05 kernel on 128 x 128 tiles (mq_gemm_tc.cu), same epilogues / gather / split-K
+    const int planes = (tc & MQ_TC_PLANES_MASK) ? (tc & MQ_TC_PLANES_MASK) : 3;
+    if (ws && gemm_tc_wanted(g, tc) && ws_bytes >= gemm_tc_ws_bytes(g.m, g.n, g.k, planes)) {
+        // large problems: TMA-fed tcgen05 kernel on 128 x 128 tiles (mq_gemm_tma.cu), same epilogues / gather / split-K
         GemmArgs gt = g;
-        const int64_t tiles = mq_ceil_div(g.m, 128) * mq_ceil_div(g.n, 128);
-        int64_t splits = 1;
-        if (ws && 2 * tiles <= sms && g.k >= 1024) {
-            splits = sms / tiles;
-            if (splits > g.k / 256) splits = g.k / 256;
-            while (splits > 1 && splits * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) --splits;
-            if (splits < 1) splits = 1;
-        }
-        gt.k_per_split = mq_round_up(mq_ceil_div(g.k > 0 ? g.k : 1, splits), 32);
-        splits = mq_ceil_div(g.k > 0 ? g.k : 1, gt.k_per_split);
-        if (splits > 1) gt.c = (float *)ws;
-        const int rc = mq_gemm_tc_launch(gt, splits, stream);
+        const int64_t splits = gemm_tc_splits(g.m, g.n, g.k, &gt.k_per_split);
+        const int64_t pack_bytes = mq_gemm_tma_pack_bytes(g.m, g.n, g.k, planes);
+        float *partials = (float *)((char *)ws + pack_bytes);
+        if (splits > 1) gt.c = partials;
+        const int rc = mq_gemm_tma_launch(gt, planes, splits, ws, stream);
         if (rc == MQ_OK) {
             if (splits > 1) {
                 int64_t nb = mq_ceil_div(g.m * g.n, MQ_NT);
                 if (nb > sms * 8) nb = sms * 8;
-                MQ_LAUNCH(gemm_splitk_finish_kernel, (unsigned)nb, MQ_NT, 0, stream, g, (const float *)ws, (int)splits, g.c);
+                MQ_LAUNCH(gemm_splitk_finish_kernel, (unsigned)nb, MQ_NT, 0, stream, g, (const float *)partials, (int)splits, g.c);
             }
             MQ_CHECK_LAUNCH(what);
             return MQ_OK;
         }
         if (rc != MQ_ERR_UNSUPPORTED) return rc;
     }
+    MQ_REQUIRE(!(tc & MQ_TC_FORCE), MQ_ERR_INVALID, "%s: MQ_TC_FORCE needs a workspace of mq_gemm_ws_bytes()", what);
     const bool big = mq_ceil_div(g.m, 64) * mq_ceil_div(g.n, 64) >= sms / 2;
     const int bm = big ? 64 : 32;
     const int64_t tiles = mq_ceil_div(g.m, bm) * mq_ceil_div(g.n, bm);
@@ -187,30 +219,29 @@ static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, void *stream, const 
     return MQ_OK;
 }
 
-extern "C" int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs,
-                       int64_t b_cs, float *c, int64_t m, int64_t n, int64_t k, float alpha,
-                       void *stream) {
+extern "C" int mq_gemm_ex(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs, float *c,
+                          int64_t m, int64_t n, int64_t k, float alpha, int32_t tc, void *ws, int64_t ws_bytes, void *stream) {
     MQ_REQUIRE(m >= 0 && n >= 0 && k >= 0, MQ_ERR_SHAPE, "mq_gemm: negative size");
     MQ_REQUIRE((m == 0 || n == 0) || (a && b && c), MQ_ERR_INVALID, "mq_gemm: null pointer");
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.a = a; g.a_rs = a_rs; g.a_cs = a_cs; g.b = b; g.b_rs = b_rs; g.b_cs = b_cs;
     g.c = c; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.epi = EPI_SCALE;
-    return gemm_run(g, nullptr, 0, stream, "mq_gemm");
+    return gemm_run(g, ws, ws ? ws_bytes : 0, tc, stream, "mq_gemm");
 }
 
-// The same with a workspace: products with few output tiles and a long contraction (dW = x^T g over a batch of
-// thousands) are split along K, deterministically (partials summed in a fixed order).
+extern "C" int mq_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs,
+                       int64_t b_cs, float *c, int64_t m, int64_t n, int64_t k, float alpha,
+                       void *stream) {
+    return mq_gemm_ex(a, a_rs, a_cs, b, b_rs, b_cs, c, m, n, k, alpha, 0, nullptr, 0, stream);
+}
+
+// The same with a workspace (mq_gemm_ws_bytes): large products run on the TMA-fed tcgen05 kernel, products with few output
+// tiles and a long contraction (dW = x^T g over a batch of thousands) are split along K, deterministically.
 extern "C" int mq_gemm_ws(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs,
                           int64_t b_cs, float *c, int64_t m, int64_t n, int64_t k, float alpha, void *ws,
                           int64_t ws_bytes, void *stream) {
-    MQ_REQUIRE(m >= 0 && n >= 0 && k >= 0, MQ_ERR_SHAPE, "mq_gemm_ws: negative size");
-    MQ_REQUIRE((m == 0 || n == 0) || (a && b && c), MQ_ERR_INVALID, "mq_gemm_ws: null pointer");
-    GemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.a = a; g.a_rs = a_rs; g.a_cs = a_cs; g.b = b; g.b_rs = b_rs; g.b_cs = b_cs;
-    g.c = c; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.epi = EPI_SCALE;
-    return gemm_run(g, ws, ws ? ws_bytes : 0, stream, "mq_gemm_ws");
+    return mq_gemm_ex(a, a_rs, a_cs, b, b_rs, b_cs, c, m, n, k, alpha, 0, ws, ws_bytes, stream);
 }
 
 // ---- layered MLP path --------------------------------------------------------------
@@ -241,14 +272,24 @@ extern "C" int64_t mq_mlp_acts_floats(const mq_net_t *net, int64_t batch) {
     return s;
 }
 
-extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
-    int64_t max_w = 0;
+// per-product workspace of the layered path: the largest of forward / dW / dX over the layers
+static int64_t mlp_gemm_ws(const mq_net_t *net, int64_t batch) {
+    int64_t w = 256;
     for (int l = 0; l < net->n_layers; ++l) {
-        const int64_t w = (int64_t)net->in[l] * net->out[l];
-        if (w > max_w) max_w = w;
+        const int64_t f = mq_gemm_ws_bytes(batch, net->out[l], net->in[l]);
+        const int64_t dw = mq_gemm_ws_bytes(net->in[l] + 1, net->out[l], batch);
+        const int64_t dx = mq_gemm_ws_bytes(batch, net->in[l], net->out[l]);
+        if (f > w) w = f;
+        if (dw > w) w = dw;
+        if (dx > w) w = dx;
     }
+    return mq_round_up(w, 1024);
+}
+
+// [gradient buffers: nbuf x batch x max width floats][workspace of the dW products][workspace of the forward / dX products]
+extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
     const int64_t nbuf = net->n_layers > 2 ? net->n_layers : 2;     // one gradient buffer per layer (overlapped backward)
-    return (nbuf * batch * net_max_width(net) + 64 * max_w) * (int64_t)sizeof(float) + 256;
+    return mq_round_up(nbuf * batch * net_max_width(net) * (int64_t)sizeof(float), 1024) + 2 * mlp_gemm_ws(net, batch) + 256;
 }
 
 extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x,
@@ -276,7 +317,7 @@ extern "C" int mq_mlp_forward_ws(const mq_net_t *net, const float *theta, const 
         g.c = out; g.m = batch; g.n = net->out[l]; g.k = net->in[l];
         g.alpha = 1.0f; g.epi = EPI_BIAS_ACT; g.act = net->act[l]; g.leak = net->leak[l];
         g.bias = theta + net->b_off[l];
-        rc = gemm_run(g, ws, ws ? ws_bytes : 0, stream, "mq_mlp_forward");
+        rc = gemm_run(g, ws, ws ? ws_bytes : 0, 0, stream, "mq_mlp_forward");
         if (rc != MQ_OK) return rc;
         inp = out;
         out += (int64_t)net->out[l] * batch;
@@ -307,8 +348,10 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
     const int L = net->n_layers;
     const int64_t maxw = net_max_width(net);
     const int64_t nbuf = L > 2 ? L : 2;
-    float *split_ws = (float *)ws + nbuf * batch * maxw;
-    const int64_t split_bytes = ws_bytes - nbuf * batch * maxw * (int64_t)sizeof(float);
+    const int64_t per = mlp_gemm_ws(net, batch);
+    char *split_ws = (char *)ws + mq_round_up(nbuf * batch * maxw * (int64_t)sizeof(float), 1024);     // dW products (side stream)
+    char *main_ws = split_ws + per;                                                                     // dX products
+    const int64_t split_bytes = per;
     MQ_REQUIRE(!side_stream || events, MQ_ERR_INVALID, "mq_mlp_backward_overlap: events missing");
 #ifdef MQ_EMU
     side_stream = nullptr;
@@ -350,7 +393,7 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
         const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l] &&
                                (int64_t)net->in[l] * net->out[l] * batch < (1LL << 26);
         if (fuse_bias) { g.m = net->in[l] + 1; g.a_ones_row = net->in[l]; }
-        rc = gemm_run(g, split_ws, split_bytes, w_stream, "mq_mlp_backward(dW)");
+        rc = gemm_run(g, split_ws, split_bytes, 0, w_stream, "mq_mlp_backward(dW)");
         if (rc != MQ_OK) return rc;
         if (!fuse_bias) {
             rc = mq_col_sum(g_cur, nullptr, batch, net->out[l], scale, grad + net->b_off[l], w_stream);
@@ -370,7 +413,7 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
             } else {
                 g.epi = EPI_SCALE;
             }
-            rc = gemm_run(g, nullptr, 0, stream, "mq_mlp_backward(dX)");
+            rc = gemm_run(g, main_ws, per, 0, stream, "mq_mlp_backward(dX)");
             if (rc != MQ_OK) return rc;
             g_cur = dst;
         }

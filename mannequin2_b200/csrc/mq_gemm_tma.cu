@@ -1,0 +1,348 @@
+// tcgen05 / TMEM GEMM for WIDE Affine layers, fed by TMA (north_star: "tensor-core tiles ... for Affine layers wide and
+// batched enough to be real dense contractions"): the 784x400 / 400x784 layers of mnist/vae.py at batch 4096, the 784x128
+// layer of mnist/mlp.py at large batch, and large `matmul` nodes of the general graph (mannequin/backprop.py:45-51:
+// y = x W, dx = g W^T, dW = x^T g).
+//
+// C[M,N] = epilogue(A[M,K] B[K,N]) with fp32 operands of any stride, the epilogues of mq_gemm.cuh and the optional row
+// gather / split-K of the FFMA kernel it stands in for (mq_gemm.cu dispatches here for large problems).
+//
+// Two launches per product:
+//   1. pack_planes_kernel: each fp32 operand is converted ONCE into P bf16 planes (x = x0 + x1 + x2, as in mq_tc.cu),
+//      stored as plain K-contiguous bf16 matrices [plane][rows padded to 128][K padded to 64] in the workspace.  (Round 1
+//      converted fp32 -> planes through registers inside every CTA that touched a tile: 3.9x the algorithmic DRAM reads
+//      and the shared-memory bandwidth the tensor pipe needs.)
+//   2. gemm_tma_kernel: one CTA per 128 x 128 tile of C, warp-specialised:
+//        warp 0    TMA producer: cp.async.bulk.tensor.2d loads of 128 x 64 bf16 boxes (128-byte swizzle) of every plane of
+//                  A and B into a ring of shared-memory stages, completion counted in bytes on the stage's mbarrier
+//        warp 1    MMA issuer: per K step of 16 the plane pairs i + j < P as wide instructions
+//                      P = 3: A_0 x [B_0|B_1] (N = 256), A_1 x [B_0|B_1], A_0 x B_2 (N = 128), A_2 x B_0
+//                      P = 2: A_0 x [B_0|B_1], A_1 x B_0          P = 1: A_0 x B_0
+//                  (the planes of B are consecutive tiles in a stage, so [B_0|B_1] is one descriptor), tcgen05.commit
+//                  frees the stage
+//        warps 2-9 accumulator owners: the tensor pipe TRUNCATES when it adds into its fp32 accumulator (a K = 2003
+//                  product accumulated entirely in TMEM was low by 1.2e-4 relative), so for P >= 2 TMEM only ever
+//                  accumulates one K block of 128; the owners add each finished block into registers (round to nearest)
+//                  from the accumulator set the tensor pipe is NOT writing (two sets of 256 columns alternate), then
+//                  apply the epilogue.  P = 1 (plain bf16, error 2^-9 per operand) accumulates all of K in TMEM.
+// The precision modes are those of the fused kernel (include/mq_b200.h MQ_TC_*): 3 planes = fp32 products (the FFMA
+// bar), 2 planes = 16-bit operands, 1 plane = bf16.
+#include <cuda.h>
+
+#include "mq_gemm.cuh"
+#include "mq_tc.cuh"
+
+#ifndef MQ_EMU
+
+#define GM_BM 128
+#define GM_BN 128
+#define GM_BK 64                       // K per stage: one 128-byte swizzle atom of bf16
+#define GM_TILE_BYTES (128 * 128)      // one 128 x 64 bf16 box
+#define GM_NT 320                      // producer warp, issuer warp, 8 accumulator-owner warps
+#define GM_KBLOCK 2                    // stages per TMEM accumulation block (K = 128)
+
+// ---- operand packing -------------------------------------------------------------------------------------------
+// out[pl][r][k] (bf16, r < rows_pad, k < k_pad; zero outside the operand) = plane pl of src(r, k), where
+// src(r, k) = base[row(r) * rs + col(k) * cs] with an optional gather on the rows (idx_on_k = 0) or on k (idx_on_k = 1).
+// One thread converts 8 consecutive k of one row; lanes run along the unit-stride axis of the source.
+template <int P>
+__global__ void __launch_bounds__(MQ_NT)
+pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k,
+                   int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad, int rows_fast, __nv_bfloat16 *__restrict__ out) {
+    const int64_t kc_n = k_pad / 8;
+    const int64_t item = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
+    if (item >= rows_pad * kc_n) return;
+    int64_t r, kc;
+    if (rows_fast) { kc = item / rows_pad; r = item - kc * rows_pad; }
+    else { r = item / kc_n; kc = item - r * kc_n; }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (r < rows) {
+        const int64_t sr = (idx && !idx_on_k) ? (int64_t)idx[r] : r;
+        const int64_t k0 = kc * 8;
+        if (cs == 1 && !(idx && idx_on_k) && k0 + 8 <= k && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(rs * 4)) & 15) == 0) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(base + sr * rs + k0));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(base + sr * rs + k0) + 1);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (k0 + j < k) {
+                    const int64_t sk = (idx && idx_on_k) ? (int64_t)idx[k0 + j] : k0 + j;
+                    v[j] = __ldg(base + sr * rs + sk * cs);
+                }
+        }
+    }
+    uint32_t w[4][P];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            w[j][pl] = *reinterpret_cast<const uint32_t *>(&h);
+            a -= __uint_as_float(w[j][pl] << 16);
+            b -= __uint_as_float(w[j][pl] & 0xFFFF0000u);
+        }
+    }
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl)
+        *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + kc * 8) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+}
+
+// ---- PTX helpers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gm_tma_load(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void gm_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gm_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// K-major operand tile with 128-byte swizzle: 8-row groups 1024 bytes apart; layout type 2 (SWIZZLE_128B) in bits 61-63
+__device__ __forceinline__ uint32_t gm_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t gm_desc_hi() { return ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+
+template <int P>
+struct GmCfg {
+    static constexpr int STAGES = P == 3 ? 2 : (P == 2 ? 3 : 5);
+    static constexpr int STAGE_BYTES = 2 * P * GM_TILE_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;       // + slack for the 1024-byte alignment
+    static constexpr bool FOLD = P > 1;
+    static constexpr int NB = P > 1 ? 2 : 1;                       // column blocks of an accumulator set
+    static constexpr int TMEM_COLS = P > 1 ? 512 : 128;
+};
+
+template <int P, bool SPLIT>
+__global__ void __launch_bounds__(GM_NT, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g,
+                int a_rows_pad, int b_rows_pad) {
+    using Cfg = GmCfg<P>;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[Cfg::STAGES], s_empty[Cfg::STAGES], s_accfull[2], s_accempty[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t sbase = (tc_smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    const int64_t k_begin = (int64_t)blockIdx.z * g.k_per_split;
+    const int64_t k_end = (k_begin + g.k_per_split < g.k) ? k_begin + g.k_per_split : g.k;
+    const int n_chunks = (int)((k_end - k_begin + GM_BK - 1) / GM_BK);
+    const int n_blocks = Cfg::FOLD ? (n_chunks + GM_KBLOCK - 1) / GM_KBLOCK : (n_chunks > 0 ? 1 : 0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"((uint32_t)Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_full[s])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_empty[s])), "r"(1u));
+        }
+        for (int s = 0; s < 2; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_accfull[s])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&s_accempty[s])), "r"(8u));     // one arrive per owner warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
+    tc_publish();
+    const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
+
+    if (warp == 0) {
+        // ---- TMA producer ----------------------------------------------------------------------------------------
+        if (tc_elect_one()) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % Cfg::STAGES;
+                if (c >= Cfg::STAGES) tc_wait(tc_smem_u32(&s_empty[s]), (uint32_t)((c / Cfg::STAGES - 1) & 1));
+                const uint32_t full = tc_smem_u32(&s_full[s]);
+                gm_expect_tx(full, (uint32_t)Cfg::STAGE_BYTES);
+                const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
+                const int kc = (int)(k_begin + (int64_t)c * GM_BK);
+#pragma unroll
+                for (int pl = 0; pl < P; ++pl) {
+                    gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, kc, pl * a_rows_pad + m0, full);
+                    gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, kc, pl * b_rows_pad + n0, full);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---- MMA issuer --------------------------------------------------------------------------------------------
+        const uint32_t hi = gm_desc_hi();
+        const uint32_t id2 = tc_idesc(GM_BM, 2 * GM_BN, 0, 0), id1 = tc_idesc(GM_BM, GM_BN, 0, 0);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c % Cfg::STAGES;
+            const int blk = Cfg::FOLD ? c / GM_KBLOCK : 0, set = blk & 1;
+            tc_wait(tc_smem_u32(&s_full[s]), (uint32_t)((c / Cfg::STAGES) & 1));
+            if (Cfg::FOLD && c % GM_KBLOCK == 0 && blk >= 2) tc_wait(tc_smem_u32(&s_accempty[set]), (uint32_t)((blk / 2 - 1) & 1));
+            if (tc_elect_one()) {
+                const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
+                const uint32_t d = tm + set * 256;
+                const uint32_t pl16 = GM_TILE_BYTES >> 4;
+#pragma unroll
+                for (int ks = 0; ks < GM_BK / 16; ++ks) {
+                    const uint32_t alo = gm_desc_lo(sa) + 2 * ks, blo = gm_desc_lo(sb) + 2 * ks;     // 32 bytes per K step
+                    const uint32_t first = Cfg::FOLD ? ((c % GM_KBLOCK > 0 || ks > 0) ? 1u : 0u) : ((c > 0 || ks > 0) ? 1u : 0u);
+                    if (P == 1) {
+                        tc_mma(d, alo, hi, blo, hi, id1, first);                              // A_0 x B_0
+                    } else if (P == 2) {
+                        tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
+                        tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
+                    } else {
+                        // block 0 receives ONLY the leading term A_0 B_0 (one truncating add per K step), block 1 all the
+                        // correction terms (<= 2^-8 of it): the accumulator's round-towards-zero bias is 4x smaller than
+                        // with the corrections spread over both blocks, at the same tensor-pipe time (128 + 4 x 64 cycles)
+                        tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
+                        tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
+                        tc_mma(d + GM_BN, alo + pl16, hi, blo + pl16, hi, id1, 1u);           // A_1 x B_1       -> block 1
+                        tc_mma(d + GM_BN, alo, hi, blo + 2 * pl16, hi, id1, 1u);              // A_0 x B_2       -> block 1
+                        tc_mma(d + GM_BN, alo + 2 * pl16, hi, blo, hi, id1, 1u);              // A_2 x B_0       -> block 1
+                    }
+                }
+                tc_commit(tc_smem_u32(&s_empty[s]));
+                if (c == n_chunks - 1 || (Cfg::FOLD && c % GM_KBLOCK == GM_KBLOCK - 1)) tc_commit(tc_smem_u32(&s_accfull[set]));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- accumulator owners: row = TMEM lane, 64 columns each ----------------------------------------------------
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t tl = tm + ((uint32_t)(quarter * 32) << 16) + half * 64;
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+        for (int blk = 0; blk < n_blocks; ++blk) {
+            const int set = blk & 1;
+            tc_wait(tc_smem_u32(&s_accfull[set]), (uint32_t)((blk / 2) & 1));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[16], w[16];
+                tc_ld16(tl + set * 256 + q * 16, v);
+                if (Cfg::NB == 2) tc_ld16(tl + set * 256 + GM_BN + q * 16, w);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[q * 16 + j] += Cfg::NB == 2 ? v[j] + w[j] : v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) gm_arrive(tc_smem_u32(&s_accempty[set]));
+        }
+        const int64_t gm = m0 + quarter * 32 + lane;
+        if (gm < g.m) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int64_t gn = n0 + half * 64 + j;
+                if (gn >= g.n) continue;
+                if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = acc[j];
+                else g.c[gm * g.n + gn] = gemm_epilogue(g, acc[j], gm, gn);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)Cfg::TMEM_COLS));
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*gm_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static gm_encode_fn gm_encoder() {
+    static gm_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+            st == cudaDriverEntryPointSuccess)
+            fn = (gm_encode_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// planes stacked along the rows: [P * rows_pad][k_pad] bf16, box 64 (k) x 128 (rows), 128-byte swizzle
+static int gm_make_map(CUtensorMap *map, void *base, int64_t rows_total, int64_t k_pad) {
+    gm_encode_fn enc = gm_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows_total};
+    const cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    const cuuint32_t box[2] = {GM_BK, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int64_t gm_pack_bytes(int planes, int64_t rows, int64_t k) {
+    return (int64_t)planes * mq_round_up(rows, 128) * mq_round_up(k, GM_BK) * 2;
+}
+
+// workspace the packed-operand GEMM needs for an m x n x k product with `planes` planes (without split-K partials)
+int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes) {
+    return mq_round_up(gm_pack_bytes(planes, m, k), 1024) + mq_round_up(gm_pack_bytes(planes, n, k), 1024) + 1024;
+}
+
+template <int P>
+static int gm_pack(const float *base, int64_t rs, int64_t cs, const int32_t *idx, int idx_on_k, int64_t rows, int64_t k,
+                   void *out, void *stream) {
+    const int64_t rows_pad = mq_round_up(rows, 128), k_pad = mq_round_up(k, GM_BK);
+    const int64_t items = rows_pad * (k_pad / 8);
+    const int rows_fast = (rs == 1 && cs != 1) ? 1 : 0;
+    MQ_LAUNCH(pack_planes_kernel<P>, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, base, rs, cs, idx, idx_on_k, rows, k,
+              rows_pad, k_pad, rows_fast, (__nv_bfloat16 *)out);
+    return MQ_OK;
+}
+
+// Launches pack + GEMM.  g.c points at the split-K partial buffer when splits > 1 (g.k_per_split a multiple of 64).
+// `pack` = workspace of mq_gemm_tma_pack_bytes() bytes.  MQ_ERR_UNSUPPORTED when tensor maps are not available.
+int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack, void *stream) {
+    if (g.m <= 0 || g.n <= 0 || g.k <= 0 || g.a_ones_row != 0) return MQ_ERR_UNSUPPORTED;
+    if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
+    if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
+    const int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128), k_pad = mq_round_up(g.k, GM_BK);
+    unsigned char *pa = (unsigned char *)(((uintptr_t)pack + 1023) & ~(uintptr_t)1023);
+    unsigned char *pb = pa + mq_round_up(gm_pack_bytes(planes, g.m, g.k), 1024);
+    // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
+    int rc;
+    if (planes == 3) {
+        rc = gm_pack<3>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
+        rc = gm_pack<3>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+    } else if (planes == 2) {
+        rc = gm_pack<2>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
+        rc = gm_pack<2>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+    } else {
+        rc = gm_pack<1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
+        rc = gm_pack<1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+    }
+    (void)rc;
+    alignas(64) CUtensorMap map_a, map_b;
+    if (!gm_make_map(&map_a, pa, planes * a_rows_pad, k_pad) || !gm_make_map(&map_b, pb, planes * b_rows_pad, k_pad)) {
+        mq_set_error("mq_gemm_tma: cuTensorMapEncodeTiled failed");
+        return MQ_ERR_CUDA;
+    }
+    dim3 grid((unsigned)mq_ceil_div(g.n, GM_BN), (unsigned)mq_ceil_div(g.m, GM_BM), (unsigned)splits);
+    cudaError_t e = cudaSuccess;
+#define GM_GO(P_, SP_)                                                                                                     \
+    do {                                                                                                                   \
+        e = cudaFuncSetAttribute(gemm_tma_kernel<P_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
+        if (e == cudaSuccess)                                                                                              \
+            gemm_tma_kernel<P_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, (int)a_rows_pad, \
+                                                                                            (int)b_rows_pad);              \
+    } while (0)
+    if (splits > 1) { if (planes == 3) GM_GO(3, true); else if (planes == 2) GM_GO(2, true); else GM_GO(1, true); }
+    else { if (planes == 3) GM_GO(3, false); else if (planes == 2) GM_GO(2, false); else GM_GO(1, false); }
+#undef GM_GO
+    if (e != cudaSuccess) { mq_set_error("mq_gemm_tma: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
+    return MQ_OK;
+}
+
+#else
+int64_t mq_gemm_tma_pack_bytes(int64_t, int64_t, int64_t, int) { return 0; }
+int mq_gemm_tma_launch(const GemmArgs &, int, int64_t, void *, void *) { return MQ_ERR_UNSUPPORTED; }
+#endif

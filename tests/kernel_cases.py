@@ -1160,60 +1160,69 @@ def case_discrete(B, batches=(64, 300, 9000)):
                              B.ptr(ws), wsb, B.stream) == L.MQ_ERR_INVALID
 
 
+# stated tolerances of the GEMM precision modes: |err| <= rtol |ref| + atol_scale max|ref|
+GEMM_MODE_TOL = {3: (1e-5, 2e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}
+
+
 def case_gemm_tc(B):
-    """tcgen05 GEMM for wide layers (mq_gemm_tc.cu), forced on (mode 2): every operand layout, ragged sizes, the
-    fused epilogues, row gather and split-K of the layered MLP path, at the fp32 FFMA parity bar."""
+    """TMA-fed tcgen05 GEMM for wide layers (mq_gemm_tma.cu), forced on per call (MQ_TC_FORCE): every operand layout,
+    ragged sizes (rows, columns and K not multiples of the tiles), long contractions (split-K, the K = 128 accumulator
+    fold), the three precision modes at their stated tolerances; then the fused epilogues, row gather and split-K of the
+    layered MLP path at the fp32 FFMA parity bar."""
     lib = B.lib
     rs = np.random.RandomState(41)
-    ok(B, lib.mq_debug_set_gemm_tc_mode(2))
-    try:
-        for m, n, k in ((128, 128, 32), (256, 64, 64), (300, 200, 100), (130, 70, 2003), (1024, 400, 784)):
-            a = rs.randn(m, k).astype(np.float32)
-            b = rs.randn(k, n).astype(np.float32)
-            want = 0.5 * (a.astype(np.float64) @ b.astype(np.float64))
-            for a_t in (False, True):
-                for b_t in (False, True):
-                    ha = B.up(np.ascontiguousarray(a.T) if a_t else a)
-                    hb = B.up(np.ascontiguousarray(b.T) if b_t else b)
-                    a_rs, a_cs = (1, m) if a_t else (k, 1)
-                    b_rs, b_cs = (1, k) if b_t else (n, 1)
-                    c = B.zeros((m, n), np.float32)
-                    ok(B, lib.mq_gemm(B.ptr(ha), a_rs, a_cs, B.ptr(hb), b_rs, b_cs, B.ptr(c), m, n, k, 0.5, B.stream))
-                    close(B.down(c), want, what="gemm_tc %dx%dx%d aT=%d bT=%d" % (m, n, k, a_t, b_t))
-        # the tensor-core and the FFMA kernel agree element by element at the same bar
-        a, b = rs.randn(512, 300).astype(np.float32), rs.randn(300, 256).astype(np.float32)
-        ha, hb = B.up(a), B.up(b)
-        c1, c2 = B.zeros((512, 256), np.float32), B.zeros((512, 256), np.float32)
-        ok(B, lib.mq_gemm(B.ptr(ha), 300, 1, B.ptr(hb), 256, 1, B.ptr(c1), 512, 256, 300, 1.0, B.stream))
-        ok(B, lib.mq_debug_set_gemm_tc_mode(0))
-        ok(B, lib.mq_gemm(B.ptr(ha), 300, 1, B.ptr(hb), 256, 1, B.ptr(c2), 512, 256, 300, 1.0, B.stream))
-        ok(B, lib.mq_debug_set_gemm_tc_mode(2))
-        close(B.down(c1), B.down(c2), what="gemm tc vs ffma")
-        # layered MLP (mnist/mlp.py and mnist/vae.py encoder shapes) at a batch where every layer is a real contraction:
-        # bias + activation epilogue, act' epilogue, gathered rows, split-K weight gradients
-        for n_in, widths, acts, batch, n_src in ((784, [128, 128, 10], [2, 2, 0], 2048, 3000), (784, [400, 40], [1, 0], 1024, 1024)):
-            spec, theta, x = mlp_case(rs, n_in, widths, acts, n_src)
-            idx = rs.randint(n_src, size=batch).astype(np.int32)
-            net = net_of(spec)
-            ht, hx, hi = B.up(theta), B.up(x), B.up(idx)
-            acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
-            ok(B, lib.mq_mlp_forward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), batch, B.ptr(acts_buf), B.stream))
-            outs = O.mlp_forward(theta, spec, x[idx])
-            got, pos = B.down(acts_buf), 0
-            for o in outs:
-                close(got[pos:pos + o.size].reshape(o.shape), o, what="layered tc fwd %s" % (widths,))
-                pos += o.size
-            dy = rs.randn(batch, widths[-1]).astype(np.float32)
-            want, wdx = O.mlp_backward(theta, spec, x[idx], outs, dy, want_dx=True)
-            wsb = lib.mq_mlp_ws_bytes(net, batch)
-            ws, grad, dx, hdy = B.zeros(wsb, np.uint8), B.zeros(spec["n_params"], np.float32), \
-                B.zeros((batch, n_in), np.float32), B.up(dy.copy())
-            ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), batch,
-                                      1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
-            close(B.down(grad), want, what="layered tc grad %s" % (widths,))
-            close(B.down(dx), wdx, what="layered tc dx %s" % (widths,))
-    finally:
-        lib.mq_debug_set_gemm_tc_mode(1)
+    F = L.TC_FORCE
+
+    def gemm(ha, a_rs, a_cs, hb, b_rs, b_cs, m, n, k, alpha, tc):
+        c = B.zeros((m, n), np.float32)
+        wsb = lib.mq_gemm_ws_bytes(m, n, k)
+        ws = B.zeros(wsb, np.uint8)
+        ok(B, lib.mq_gemm_ex(B.ptr(ha), a_rs, a_cs, B.ptr(hb), b_rs, b_cs, B.ptr(c), m, n, k, alpha, tc, B.ptr(ws), wsb, B.stream))
+        return B.down(c)
+
+    for m, n, k in ((128, 128, 32), (256, 64, 64), (300, 200, 100), (130, 70, 2003), (1024, 400, 784), (784, 400, 4096)):
+        a = rs.randn(m, k).astype(np.float32)
+        b = rs.randn(k, n).astype(np.float32)
+        want = 0.5 * (a.astype(np.float64) @ b.astype(np.float64))
+        for a_t in (False, True):
+            for b_t in (False, True):
+                ha = B.up(np.ascontiguousarray(a.T) if a_t else a)
+                hb = B.up(np.ascontiguousarray(b.T) if b_t else b)
+                a_rs, a_cs = (1, m) if a_t else (k, 1)
+                b_rs, b_cs = (1, k) if b_t else (n, 1)
+                for planes in (3, 2, 1):
+                    rtol, atol = GEMM_MODE_TOL[planes]
+                    got = gemm(ha, a_rs, a_cs, hb, b_rs, b_cs, m, n, k, 0.5, F | planes)
+                    close(got, want, rtol=rtol, atol_scale=atol, what="gemm_tma P=%d %dx%dx%d aT=%d bT=%d" % (planes, m, n, k, a_t, b_t))
+    # the tensor-core and the FFMA kernel agree element by element at the same bar
+    a, b = rs.randn(512, 300).astype(np.float32), rs.randn(300, 256).astype(np.float32)
+    ha, hb = B.up(a), B.up(b)
+    c1 = gemm(ha, 300, 1, hb, 256, 1, 512, 256, 300, 1.0, F)
+    c2 = gemm(ha, 300, 1, hb, 256, 1, 512, 256, 300, 1.0, L.TC_OFF)
+    close(c1, c2, what="gemm tc vs ffma")
+    # layered MLP (mnist/mlp.py and mnist/vae.py encoder shapes) at a batch where every layer is a real contraction:
+    # bias + activation epilogue, act' epilogue, gathered rows, split-K weight gradients
+    for n_in, widths, acts, batch, n_src in ((784, [128, 128, 10], [2, 2, 0], 2048, 3000), (784, [400, 40], [1, 0], 4096, 4096)):
+        spec, theta, x = mlp_case(rs, n_in, widths, acts, n_src)
+        idx = rs.randint(n_src, size=batch).astype(np.int32)
+        net = net_of(spec)
+        ht, hx, hi = B.up(theta), B.up(x), B.up(idx)
+        acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
+        wsb = lib.mq_mlp_ws_bytes(net, batch)
+        ws = B.zeros(wsb, np.uint8)
+        ok(B, lib.mq_mlp_forward_ws(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), batch, B.ptr(acts_buf), B.ptr(ws), wsb, B.stream))
+        outs = O.mlp_forward(theta, spec, x[idx])
+        got, pos = B.down(acts_buf), 0
+        for o in outs:
+            close(got[pos:pos + o.size].reshape(o.shape), o, what="layered tc fwd %s" % (widths,))
+            pos += o.size
+        dy = rs.randn(batch, widths[-1]).astype(np.float32)
+        want, wdx = O.mlp_backward(theta, spec, x[idx], outs, dy, want_dx=True)
+        grad, dx, hdy = B.zeros(spec["n_params"], np.float32), B.zeros((batch, n_in), np.float32), B.up(dy.copy())
+        ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), batch,
+                                  1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
+        close(B.down(grad), want, what="layered tc grad %s" % (widths,))
+        close(B.down(dx), wdx, what="layered tc dx %s" % (widths,))
 
 
 ALL_CASES = [case_adam, case_norm, case_gather, case_scan, case_layered_mlp, case_gemm_tc, case_fused_heads,
