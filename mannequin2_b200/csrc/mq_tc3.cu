@@ -246,8 +246,20 @@ template <int P, int NS, int K0, int HACT>
 __global__ void __launch_bounds__(T3_NTI, 1)
 tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *__restrict__ rec,
                 const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
-                float *__restrict__ partial, float *__restrict__ out, float *__restrict__ logp_out) {
+                float *__restrict__ partial, float *__restrict__ out, float *__restrict__ logp_out, long long *prof) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    // developer aid (build with MQ_TC_PROFILE=1, tools/tc3_trace.py): time stamps of CTA 0 -- worker thread 0 logs into
+    // prof[0..255], the issuing lane into prof[256..511]
+#ifdef MQ_TC_PROFILE
+    int prof_n = 0;
+    const bool prof_on = prof != nullptr && blockIdx.x == 0;
+#define T3_MARK(tag) do { if (prof_on && (threadIdx.x == 0 || threadIdx.x == T3_NT) && prof_n < 127) { \
+        long long *q_ = prof + (threadIdx.x == 0 ? 0 : 256) + 2 * prof_n; q_[0] = (tag); q_[1] = clock64(); ++prof_n; } } while (0)
+#else
+    (void)prof;
+#define T3_MARK(tag) do { } while (0)
+#endif
+    T3_MARK(1);
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_full[2], s_dw[2], s_ready[2], s_img;
     constexpr int ROWS = T3_ROWS;             // rows of a slot
@@ -300,7 +312,9 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
     }
     const uint32_t sbase = tc_smem_u32(smem);
     const uint32_t img_bar = tc_smem_u32(&s_img);
+    T3_MARK(2);
     mq_pdl_wait();                        // the predecessor's writes (image, records) are complete and visible
+    T3_MARK(3);
     if (tid == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(img_bar), "r"((uint32_t)p.img.bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -323,6 +337,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
     tc_publish();                                       // zeroed buffers / ones chunks visible to the tensor pipe, TMEM address
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
     tc_wait(img_bar, 0);                                // weights, biases, head parameters have landed
+    T3_MARK(4);
 
     if (!worker) {
         // ---- issuer warp ---------------------------------------------------------------------------------------
@@ -343,6 +358,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                     const uint32_t za = tm + p.col_za[s];
                     const uint32_t full = tc_smem_u32(&s_full[s]), dwb = tc_smem_u32(&s_dw[s]);
                     tc_wait(tc_smem_u32(&s_ready[s]), rdy_par[s]); rdy_par[s] ^= 1u;
+                    T3_MARK(100 + 10 * s + job);
                     if (tc_elect_one()) {
                         if (job < L) {
                             const int l = job;
@@ -396,6 +412,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                             }
                         }
                     }
+                    T3_MARK(200 + 10 * s + job);
                     __syncwarp();
                 }
             }
@@ -544,8 +561,10 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                 const bool rvalid = row < tr && gr < n_rows;
                 if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
                 // ---- stage the input tile --------------------------------------------------------------------
+                T3_MARK(10);
                 stage();
                 t3_warp_ready(rdy, lane);
+                T3_MARK(11);
                 // ---- forward -----------------------------------------------------------------------------------
                 for (int l = 0; l < L - 1; ++l) {
                     if (l == L - 2) {
@@ -555,6 +574,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                         fetch_idx(ord + 2 * NS);
                     }
                     tc_wait(full, par_full); par_full ^= 1u;
+                    T3_MARK(20 + l);
                     if (wlive) {
                         // A_{l+1} = act(Z_l + b_l) as bf16 planes
                         const float leak = p.net.leak[l];
@@ -582,10 +602,12 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                         if (p.with_grad && p.col_save[slot] >= 0) t3_st_wait();
                     }
                     t3_warp_ready(rdy, lane);
+                    T3_MARK(30 + l);
                 }
                 // ---- head: loss-gradient rule on the output row.  All TPR threads of a row evaluate it (inputs come
                 // from shared memory) and each splits / stores its own DPT of the 16 dZ columns.
                 tc_wait(full, par_full); par_full ^= 1u;
+                T3_MARK(40);
                 if (wlive) {
                     float y[T3_NO], dz[T3_NO];
                     {
@@ -714,9 +736,11 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                     continue;
                 }
                 t3_warp_ready(rdy, lane);
+                T3_MARK(41);
                 // ---- backward ----------------------------------------------------------------------------------
                 for (int l = L - 1; l >= 1; --l) {
                     tc_wait(full, par_full); par_full ^= 1u;
+                    T3_MARK(50 + l);
                     // dZ_{l-1} = dA_l * act'(A_l), written over A_l.  Only dA_l has been waited for: the arithmetic and
                     // the split into planes run while the tensor pipe still works on dW_l / db_l, which READ A_l -- so the
                     // stores wait for the second barrier.
@@ -745,7 +769,9 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                                 for (int j = 0; j < 4; ++j) t3_split_pair<P>(g[8 * c + 2 * j], g[8 * c + 2 * j + 1], w[2 * h + c][j]);
                         }
                     }
+                    T3_MARK(60 + l);
                     tc_wait(dwb, par_dw); par_dw ^= 1u;
+                    T3_MARK(70 + l);
                     if (wlive) {
 #pragma unroll
                         for (int c = 0; c < CPT / 8; ++c) {
@@ -756,6 +782,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                         }
                     }
                     t3_warp_ready(rdy, lane);
+                    T3_MARK(80 + l);
                 }
                 pending = true;                         // dW_0 is in flight
             }
@@ -764,7 +791,9 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                T3_MARK(90);
                 flush_grad();
+                T3_MARK(91);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
             }
@@ -810,6 +839,7 @@ pack_records_kernel(const float *__restrict__ x, const float *__restrict__ tgt, 
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
+long long *mq_phase_prof_ptr();
 static int t3_planes(int32_t tc) { const int pl = tc & MQ_TC_PLANES_MASK; return pl == 0 ? 3 : pl; }
 
 extern "C" int32_t mq_record_width(const mq_net_t *net) {
@@ -963,7 +993,8 @@ int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, co
         e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
         if (e == cudaSuccess)                                                                                                \
             e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, K0_, ACT_>, dim3(grid), dim3(T3_NTI), (size_t)p.smem_bytes, stream, p, \
-                              (const unsigned char *)image, head->records, row_idx, batch, *head, (float *)ws, out, logp);   \
+                              (const unsigned char *)image, head->records, row_idx, batch, *head, (float *)ws, out, logp, \
+                              mq_phase_prof_ptr());   \
     } while (0)
 #define T3_LAUNCH_ACT(P_, NS_, K0_)                                          \
     do {                                                                          \
