@@ -298,6 +298,37 @@ int mq_reduce_step_image(const float *partials, int32_t n_parts, int64_t n, floa
                          float *theta_out, float *grad_out, int state_dtype, double c1, double c2, double lr,
                          double eps, int adams, const mq_peer_t *peer, const mq_net_t *net, int32_t tc, void *image,
                          void *stream);
+/* One parameter vector's optimiser step for mq_reduce_step2 (the arguments of mq_reduce_step_image as a struct). */
+typedef struct mq_step {
+    const float *partials; int32_t n_parts; int64_t n; float scale;
+    void *value, *m, *v; float *theta_out, *grad_out;
+    double c1, c2, lr, eps;
+    const mq_peer_t *peer;      /* nullable */
+    const mq_net_t *net; int32_t tc; void *image;      /* operand image to refresh (image nullable) */
+} mq_step_t;
+/* mq_reduce_step_image for TWO parameter vectors in ONE launch (b nullable): the value and the policy net of one PPO
+ * update step -- sharded, the pair pays one exchange latency instead of two. */
+int mq_reduce_step2(const mq_step_t *a, const mq_step_t *b, int state_dtype, int adams, void *stream);
+/* Two independent minibatch gradients (benchmarks/gae.py:71-73 and benchmarks/ppo.py:29-40 of the same update) as ONE
+ * launch of the record-fed tensor-core kernel, each net on half of the SMs; both heads must carry packed records and the
+ * nets must agree in planes, padded input width and hidden activation, else MQ_ERR_UNSUPPORTED.  ws_x receives net x's
+ * per-CTA partials ([*n_parts_x][n_params]). */
+int mq_fused_grad_partials2(const mq_net_t *net_a, const float *theta_a, const int32_t *idx_a, const mq_head_t *head_a,
+                            void *ws_a, int64_t ws_a_bytes, int32_t *n_parts_a, const mq_net_t *net_b, const float *theta_b,
+                            const int32_t *idx_b, const mq_head_t *head_b, void *ws_b, int64_t ws_b_bytes, int32_t *n_parts_b,
+                            int64_t batch, void *stream);
+/* One net's side of mq_train_steps2 (the arguments of mq_train_steps as a struct). */
+typedef struct mq_train {
+    const mq_net_t *net; float *theta; const float *x; const mq_head_t *head;
+    const int32_t *idx_table; int64_t idx_stride; float scale;
+    void *value, *m, *v; const double *coefs_host; double lr, eps;
+    const mq_peer_t *peer;      /* nullable: descriptor of the FIRST step */
+    void *ws; int64_t ws_bytes;
+} mq_train_t;
+/* mq_train_steps for two nets on the same minibatch schedule: per step one paired gradient launch and one paired
+ * reduce / exchange / Adam launch. */
+int mq_train_steps2(const mq_train_t *a, const mq_train_t *b, int32_t n_steps, int64_t mb, int state_dtype, int adams,
+                    void *stream);
 /* n_steps dependent large-minibatch steps {mq_fused_grad_partials, mq_reduce_step_image} issued by one call
  * (benchmarks/ppo.py:29-40, benchmarks/gae.py:71-73 at 65,536-row minibatches): step s reads mb indices at idx_table +
  * s * idx_stride (idx_stride > mb: this rank's columns of the global minibatch table), coefs_host =

@@ -51,6 +51,22 @@ class MqPeer(ctypes.Structure):
                 ("buf_stride", c_int64), ("step", ctypes.c_uint32), ("pull", c_int32)]
 
 
+class MqStep(ctypes.Structure):
+    """mq_step_t: one parameter vector's optimiser step (mq_reduce_step2)."""
+    _fields_ = [("partials", c_void_p), ("n_parts", c_int32), ("n", c_int64), ("scale", c_float), ("value", c_void_p),
+                ("m", c_void_p), ("v", c_void_p), ("theta_out", c_void_p), ("grad_out", c_void_p), ("c1", c_double),
+                ("c2", c_double), ("lr", c_double), ("eps", c_double), ("peer", c_void_p), ("net", c_void_p), ("tc", c_int32),
+                ("image", c_void_p)]
+
+
+class MqTrain(ctypes.Structure):
+    """mq_train_t: one net's side of mq_train_steps2."""
+    _fields_ = [("net", c_void_p), ("theta", c_void_p), ("x", c_void_p), ("head", c_void_p), ("idx_table", c_void_p),
+                ("idx_stride", c_int64), ("scale", c_float), ("value", c_void_p), ("m", c_void_p), ("v", c_void_p),
+                ("coefs_host", c_void_p), ("lr", c_double), ("eps", c_double), ("peer", c_void_p), ("ws", c_void_p),
+                ("ws_bytes", c_int64)]
+
+
 P = c_void_p
 NETP = POINTER(MqNet)
 HEADP = POINTER(MqHead)
@@ -102,6 +118,10 @@ SIGNATURES = {
                                c_double, c_int, PEERP, P]),
     "mq_reduce_step_image": (c_int, [P, c_int32, c_int64, c_float, P, P, P, P, P, c_int, c_double, c_double, c_double,
                                      c_double, c_int, PEERP, NETP, c_int32, P, P]),
+    "mq_reduce_step2": (c_int, [POINTER(MqStep), POINTER(MqStep), c_int, c_int, P]),
+    "mq_fused_grad_partials2": (c_int, [NETP, P, P, HEADP, P, c_int64, POINTER(c_int32), NETP, P, P, HEADP, P, c_int64,
+                                        POINTER(c_int32), c_int64, P]),
+    "mq_train_steps2": (c_int, [POINTER(MqTrain), POINTER(MqTrain), c_int32, c_int64, c_int, c_int, P]),
     "mq_train_steps": (c_int, [NETP, P, P, HEADP, P, c_int64, c_int32, c_int64, c_float, P, P, P, c_int, POINTER(c_double), c_double,
                                c_double, c_int, PEERP, P, c_int64, P]),
     "mq_fused_train": (c_int, [NETP, P, P, P, P, c_int, P, HEADP, P, c_int32, c_int32, c_double,

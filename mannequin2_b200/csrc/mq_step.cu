@@ -50,15 +50,36 @@ __device__ __forceinline__ float ld_relaxed_sys(const float *p) {
     return v;
 }
 
+// One parameter vector's step.  A launch carries up to TWO (blocks [0, nblk) of job 0, then job 1's): the value and the
+// policy net of a PPO update step together -- one launch and, sharded, ONE exchange latency per pair of steps.
+template <typename ST>
+struct StepJob {
+    const float *partial; int n_parts, n; float scale;
+    ST *value, *m, *v; float *theta_out, *grad_out;
+    ST c1, c2, lr, eps;
+    mq_peer_t peer; T3Img img; unsigned char *image;
+    int nblk;
+};
+template <typename ST> struct StepJobs { StepJob<ST> job[2]; };
+
 // 32 parameters x 8 groups of partial vectors per block; group sums combined in fixed order.
 template <typename ST, bool ADAMS>
 __global__ void __launch_bounds__(MQ_NT)
-reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float scale, ST *__restrict__ value,
-                   ST *__restrict__ m, ST *__restrict__ v, float *__restrict__ theta_out, float *__restrict__ grad_out,
-                   ST c1, ST c2, ST lr, ST eps, mq_peer_t peer, T3Img img, unsigned char *__restrict__ image) {
+reduce_step_kernel(const __grid_constant__ StepJobs<ST> launch) {
+    const bool second = blockIdx.x >= (unsigned)launch.job[0].nblk;
+    const StepJob<ST> &J = second ? launch.job[1] : launch.job[0];
+    const int bid = (int)blockIdx.x - (second ? launch.job[0].nblk : 0);
+    const float *__restrict__ partial = J.partial;
+    const int n_parts = J.n_parts, n = J.n;
+    const float scale = J.scale;
+    ST *__restrict__ value = J.value, *__restrict__ m = J.m, *__restrict__ v = J.v;
+    float *__restrict__ theta_out = J.theta_out, *__restrict__ grad_out = J.grad_out;
+    const ST c1 = J.c1, c2 = J.c2, lr = J.lr, eps = J.eps;
+    const mq_peer_t &peer = J.peer;
+    unsigned char *__restrict__ image = J.image;
     __shared__ float part[8][33];
     const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + jx;
+    const int j = bid * 32 + jx;
     // programmatic dependent launch: this grid may already be resident while the gradient kernel finishes, and the
     // next gradient kernel may start its on-chip prologue while this one runs
     mq_pdl_trigger();
@@ -123,11 +144,11 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
             for (int r = 0; r < peer.world; ++r) peer.grad_bufs[r][slot + j] = g;
         }
         __syncwarp();                   // the lanes' stores happen before the releasing lanes' flag stores (cumulative)
-        const int nblk = gridDim.x;
+        const int nblk = J.nblk;
         if (jx < peer.world)            // lane r tells rank r that this rank's block has arrived there
-            st_release_sys(peer.flag_bufs[jx] + ((int64_t)par * peer.world + peer.rank) * nblk + blockIdx.x, peer.step);
+            st_release_sys(peer.flag_bufs[jx] + ((int64_t)par * peer.world + peer.rank) * nblk + bid, peer.step);
         if (jx < peer.world) {          // lane r waits for rank r's block
-            const uint32_t *f = peer.flag_bufs[peer.rank] + ((int64_t)par * peer.world + jx) * nblk + blockIdx.x;
+            const uint32_t *f = peer.flag_bufs[peer.rank] + ((int64_t)par * peer.world + jx) * nblk + bid;
             while (ld_acquire_sys(f) != peer.step) { }
         }
         __syncwarp();
@@ -151,47 +172,75 @@ reduce_step_kernel(const float *__restrict__ partial, int n_parts, int n, float 
     value[j] = a; m[j] = b; v[j] = c;
     if (theta_out) theta_out[j] = (float)a;
     // the operand image of the tensor-core gradient kernel follows theta: the next launch copies it, converts nothing
-    if (image) t3_img_store_param_rt(img, image, j, (float)a);
+    if (image) t3_img_store_param_rt(J.img, image, j, (float)a);
 }
 
 extern "C" int64_t mq_step_blocks(int64_t n) { return mq_ceil_div(n, 32); }
+
+template <typename ST>
+static int step_job_fill(const mq_step_t *t, StepJob<ST> *j) {
+    MQ_REQUIRE(t->partials && t->value && t->m && t->v, MQ_ERR_INVALID, "mq_reduce_step: null pointer");
+    MQ_REQUIRE(t->n_parts >= 1 && t->n >= 1 && t->n < (1LL << 31), MQ_ERR_SHAPE, "mq_reduce_step: sizes");
+    memset(j, 0, sizeof(*j));
+    j->peer.world = 1;
+    if (t->peer && t->peer->world > 1) {
+        j->peer = *t->peer;
+        MQ_REQUIRE(j->peer.world <= 32 && j->peer.rank >= 0 && j->peer.rank < j->peer.world && j->peer.grad_bufs && j->peer.flag_bufs &&
+                       j->peer.buf_stride >= t->n && j->peer.step != 0,
+                   MQ_ERR_INVALID, "mq_reduce_step: bad peer descriptor");
+    }
+    if (t->image) {
+        const int planes = (t->tc & MQ_TC_PLANES_MASK) ? (t->tc & MQ_TC_PLANES_MASK) : 3;
+        MQ_REQUIRE(t->net && t->net->n_params == t->n && t3_img_build_layout(t->net, planes, &j->img), MQ_ERR_INVALID,
+                   "mq_reduce_step: the net does not match the parameter vector or does not fit the tensor-core kernel");
+    }
+    j->partial = t->partials; j->n_parts = t->n_parts; j->n = (int)t->n; j->scale = t->scale;
+    j->value = (ST *)t->value; j->m = (ST *)t->m; j->v = (ST *)t->v;
+    j->theta_out = t->theta_out; j->grad_out = t->grad_out;
+    j->c1 = (ST)t->c1; j->c2 = (ST)t->c2; j->lr = (ST)t->lr; j->eps = (ST)t->eps;
+    j->image = (unsigned char *)t->image;
+    j->nblk = (int)mq_ceil_div(t->n, 32);
+    return MQ_OK;
+}
+
+template <typename ST>
+static int step_launch(const mq_step_t *a, const mq_step_t *b, int adams, void *stream) {
+    StepJobs<ST> jobs;
+    int rc = step_job_fill<ST>(a, &jobs.job[0]);
+    if (rc != MQ_OK) return rc;
+    int blocks = jobs.job[0].nblk;
+    if (b) {
+        rc = step_job_fill<ST>(b, &jobs.job[1]);
+        if (rc != MQ_OK) return rc;
+        blocks += jobs.job[1].nblk;
+    } else {
+        memset(&jobs.job[1], 0, sizeof(jobs.job[1]));
+    }
+    cudaError_t e = adams ? mq_launch_pdl(reduce_step_kernel<ST, true>, dim3(blocks), dim3(MQ_NT), 0, stream, jobs)
+                          : mq_launch_pdl(reduce_step_kernel<ST, false>, dim3(blocks), dim3(MQ_NT), 0, stream, jobs);
+    if (e != cudaSuccess) { mq_set_error("mq_reduce_step: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
+    MQ_CHECK_LAUNCH("mq_reduce_step");
+    return MQ_OK;
+}
+
+extern "C" int mq_reduce_step2(const mq_step_t *a, const mq_step_t *b, int state_dtype, int adams, void *stream) {
+    MQ_REQUIRE(a, MQ_ERR_INVALID, "mq_reduce_step2: null step");
+    if (state_dtype == MQ_F32) return step_launch<float>(a, b, adams, stream);
+    if (state_dtype == MQ_F64) return step_launch<double>(a, b, adams, stream);
+    mq_set_error("mq_reduce_step: state dtype %d", state_dtype);
+    return MQ_ERR_INVALID;
+}
 
 extern "C" int mq_reduce_step_image(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
                                     void *v, float *theta_out, float *grad_out, int state_dtype, double c1, double c2,
                                     double lr, double eps, int adams, const mq_peer_t *peer, const mq_net_t *net,
                                     int32_t tc, void *image, void *stream) {
-    MQ_REQUIRE(partials && value && m && v, MQ_ERR_INVALID, "mq_reduce_step: null pointer");
-    MQ_REQUIRE(n_parts >= 1 && n >= 1 && n < (1LL << 31), MQ_ERR_SHAPE, "mq_reduce_step: sizes");
-    mq_peer_t pr;
-    memset(&pr, 0, sizeof(pr));
-    pr.world = 1;
-    if (peer && peer->world > 1) {
-        pr = *peer;
-        MQ_REQUIRE(pr.world <= 32 && pr.rank >= 0 && pr.rank < pr.world && pr.grad_bufs && pr.flag_bufs &&
-                       pr.buf_stride >= n && pr.step != 0,
-                   MQ_ERR_INVALID, "mq_reduce_step: bad peer descriptor");
-    }
-    T3Img img;
-    memset(&img, 0, sizeof(img));
-    if (image) {
-        const int planes = (tc & MQ_TC_PLANES_MASK) ? (tc & MQ_TC_PLANES_MASK) : 3;
-        MQ_REQUIRE(net && net->n_params == n && t3_img_build_layout(net, planes, &img), MQ_ERR_INVALID,
-                   "mq_reduce_step_image: the net does not match the parameter vector or does not fit the tensor-core kernel");
-    }
-    const unsigned blocks = (unsigned)mq_ceil_div(n, 32);
-#define MQ_STEP_GO(ST, A)                                                                                      \
-    do {                                                                                                       \
-        cudaError_t e_ = mq_launch_pdl(reduce_step_kernel<ST, A>, dim3(blocks), dim3(MQ_NT), 0, stream, partials,    \
-                                       (int)n_parts, (int)n, scale, (ST *)value, (ST *)m, (ST *)v, theta_out,       \
-                                       grad_out, (ST)c1, (ST)c2, (ST)lr, (ST)eps, pr, img, (unsigned char *)image); \
-        if (e_ != cudaSuccess) { mq_set_error("mq_reduce_step: %s", cudaGetErrorString(e_)); return MQ_ERR_CUDA; }   \
-    } while (0)
-    if (state_dtype == MQ_F32) { if (adams) MQ_STEP_GO(float, true); else MQ_STEP_GO(float, false); }
-    else if (state_dtype == MQ_F64) { if (adams) MQ_STEP_GO(double, true); else MQ_STEP_GO(double, false); }
-    else { mq_set_error("mq_reduce_step: state dtype %d", state_dtype); return MQ_ERR_INVALID; }
-#undef MQ_STEP_GO
-    MQ_CHECK_LAUNCH("mq_reduce_step");
-    return MQ_OK;
+    mq_step_t t;
+    memset(&t, 0, sizeof(t));
+    t.partials = partials; t.n_parts = n_parts; t.n = n; t.scale = scale; t.value = value; t.m = m; t.v = v;
+    t.theta_out = theta_out; t.grad_out = grad_out; t.c1 = c1; t.c2 = c2; t.lr = lr; t.eps = eps; t.peer = peer;
+    t.net = net; t.tc = tc; t.image = image;
+    return mq_reduce_step2(&t, nullptr, state_dtype, adams, stream);
 }
 
 extern "C" int mq_reduce_step(const float *partials, int32_t n_parts, int64_t n, float scale, void *value, void *m,
@@ -208,6 +257,7 @@ extern "C" int mq_reduce_step(const float *, int32_t, int64_t, float, void *, vo
 extern "C" int mq_reduce_step_image(const float *, int32_t, int64_t, float, void *, void *, void *, float *, float *, int,
                                     double, double, double, double, int, const mq_peer_t *, const mq_net_t *, int32_t, void *,
                                     void *) { return MQ_ERR_UNSUPPORTED; }
+extern "C" int mq_reduce_step2(const mq_step_t *, const mq_step_t *, int, int, void *) { return MQ_ERR_UNSUPPORTED; }
 #endif
 
 // ---- a block of dependent optimiser steps issued by ONE call ------------------------------------------------------------
@@ -234,6 +284,46 @@ extern "C" int mq_train_steps(const mq_net_t *net, float *theta, const float *x,
         rc = mq_reduce_step_image(ws == nullptr ? nullptr : (const float *)ws, n_parts, net->n_params, scale, value, m, v, theta,
                                   nullptr, state_dtype, coefs_host[2 * s], coefs_host[2 * s + 1], lr, eps, adams,
                                   peer ? &pr : nullptr, head->tc_image ? net : nullptr, head->tc, (void *)head->tc_image, stream);
+        if (rc != MQ_OK) return rc;
+    }
+    return MQ_OK;
+}
+
+// The same for TWO nets trained side by side on the same minibatch schedule (the value predictor and the policy of one PPO
+// update): per step ONE gradient launch (each net on half of the SMs, mq_fused_grad_partials2) and ONE reduce / exchange /
+// Adam launch (mq_reduce_step2).  Falls back to alternating single launches when the nets cannot share a launch.
+extern "C" int mq_train_steps2(const mq_train_t *a, const mq_train_t *b, int32_t n_steps, int64_t mb, int state_dtype, int adams,
+                               void *stream) {
+    MQ_REQUIRE(a && b && a->net && b->net && a->theta && b->theta && a->head && b->head && a->idx_table && b->idx_table &&
+                   a->coefs_host && b->coefs_host && a->ws && b->ws,
+               MQ_ERR_INVALID, "mq_train_steps2: null pointer");
+    MQ_REQUIRE(n_steps >= 0 && mb >= 1 && a->idx_stride >= mb && b->idx_stride >= mb, MQ_ERR_SHAPE, "mq_train_steps2: sizes");
+    mq_peer_t pa, pb;
+    if (a->peer) pa = *a->peer;
+    if (b->peer) pb = *b->peer;
+    const mq_train_t *t[2] = {a, b};
+    for (int s = 0; s < n_steps; ++s) {
+        int32_t parts[2] = {0, 0};
+        int rc = mq_fused_grad_partials2(a->net, a->theta, a->idx_table + (int64_t)s * a->idx_stride, a->head, a->ws, a->ws_bytes,
+                                         &parts[0], b->net, b->theta, b->idx_table + (int64_t)s * b->idx_stride, b->head, b->ws,
+                                         b->ws_bytes, &parts[1], mb, stream);
+        if (rc == MQ_ERR_UNSUPPORTED) {
+            for (int k = 0; k < 2 && (rc == MQ_OK || rc == MQ_ERR_UNSUPPORTED); ++k)
+                rc = mq_fused_grad_partials(t[k]->net, t[k]->theta, t[k]->x, t[k]->idx_table + (int64_t)s * t[k]->idx_stride, mb,
+                                            t[k]->head, nullptr, nullptr, t[k]->ws, t[k]->ws_bytes, &parts[k], stream);
+        }
+        if (rc != MQ_OK) return rc;
+        mq_step_t st[2];
+        for (int k = 0; k < 2; ++k) {
+            memset(&st[k], 0, sizeof(st[k]));
+            st[k].partials = (const float *)t[k]->ws; st[k].n_parts = parts[k]; st[k].n = t[k]->net->n_params; st[k].scale = t[k]->scale;
+            st[k].value = t[k]->value; st[k].m = t[k]->m; st[k].v = t[k]->v; st[k].theta_out = t[k]->theta;
+            st[k].c1 = t[k]->coefs_host[2 * s]; st[k].c2 = t[k]->coefs_host[2 * s + 1]; st[k].lr = t[k]->lr; st[k].eps = t[k]->eps;
+            if (t[k]->head->tc_image) { st[k].net = t[k]->net; st[k].tc = t[k]->head->tc; st[k].image = (void *)t[k]->head->tc_image; }
+        }
+        if (a->peer) { pa.step = a->peer->step + (uint32_t)s; st[0].peer = &pa; }
+        if (b->peer) { pb.step = b->peer->step + (uint32_t)s; st[1].peer = &pb; }
+        rc = mq_reduce_step2(&st[0], &st[1], state_dtype, adams, stream);
         if (rc != MQ_OK) return rc;
     }
     return MQ_OK;

@@ -49,6 +49,22 @@ struct T3Plan {
     int col_save[2];             // fp32 hidden activations kept in TMEM for the backward pass (-1: rebuilt from the planes)
 };
 
+// One net's share of a launch.  A launch carries up to TWO jobs (CTAs [0, grid) run job 0, the rest job 1): the value and
+// the policy minibatch gradient of one PPO step (benchmarks/gae.py:71-73 and benchmarks/ppo.py:29-40 are independent of
+// each other) as ONE grid, each on half of the SMs -- at 8,192 rows per GPU a net has one tile per SM and a launch is one
+// tile's chain of dependent phases long, so two nets side by side cost the time of one.
+struct T3Job {
+    T3Plan p;
+    const unsigned char *image;
+    const float *rec;
+    const int32_t *idx;
+    int64_t n_rows;
+    mq_head_t head;
+    float *partial, *out, *logp_out;
+    int grid;
+};
+struct T3Jobs { T3Job job[2]; };
+
 // ---- small PTX helpers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void t3_ld16_nowait(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -244,15 +260,23 @@ __device__ __forceinline__ TcView t3_wf_k(uint32_t addr, int np) {
 // ---- the kernel ------------------------------------------------------------------------------------------------
 template <int P, int NS, int K0, int HACT>
 __global__ void __launch_bounds__(T3_NTI, 1)
-tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *__restrict__ rec,
-                const int32_t *__restrict__ idx, int64_t n_rows, mq_head_t head,
-                float *__restrict__ partial, float *__restrict__ out, float *__restrict__ logp_out, long long *prof) {
+tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
+    const bool second = blockIdx.x >= (unsigned)launch.job[0].grid;
+    const T3Job &J = second ? launch.job[1] : launch.job[0];
+    const T3Plan &p = J.p;
+    const mq_head_t &head = J.head;
+    const unsigned char *__restrict__ image = J.image;
+    const float *__restrict__ rec = J.rec;
+    const int32_t *__restrict__ idx = J.idx;
+    const int64_t n_rows = J.n_rows;
+    float *__restrict__ partial = J.partial, *__restrict__ out = J.out, *__restrict__ logp_out = J.logp_out;
+    const int bid = (int)blockIdx.x - (second ? launch.job[0].grid : 0), gdim = J.grid;       // this CTA within its job
     extern __shared__ __align__(1024) unsigned char smem[];
     // developer aid (build with MQ_TC_PROFILE=1, tools/tc3_trace.py): time stamps of CTA 0 -- worker thread 0 logs into
     // prof[0..255], the issuing lane into prof[256..511]
 #ifdef MQ_TC_PROFILE
     int prof_n = 0;
-    const bool prof_on = prof != nullptr && blockIdx.x == 0;
+    const bool prof_on = prof != nullptr && blockIdx.x == 0;   // (first CTA of the launch)
 #define T3_MARK(tag) do { if (prof_on && (threadIdx.x == 0 || threadIdx.x == T3_NT) && prof_n < 127) { \
         long long *q_ = prof + (threadIdx.x == 0 ? 0 : 256) + 2 * prof_n; q_[0] = (tag); q_[1] = clock64(); ++prof_n; } } while (0)
 #else
@@ -331,8 +355,8 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
     const int lastact = p.net.act[L - 1];
     const float lastleak = p.net.leak[L - 1];
     const int jobs = p.with_grad ? 2 * L : L;
-    // tiles of this CTA: ordinal i is tile blockIdx.x + i * gridDim.x; slot s takes the ordinals i % NS == s
-    const int n_i = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    // tiles of this CTA: ordinal i is tile blockIdx.x + i * gdim; slot s takes the ordinals i % NS == s
+    const int n_i = bid < ntiles ? (int)((ntiles - bid + gdim - 1) / gdim) : 0;
 
     tc_publish();                                       // zeroed buffers / ones chunks visible to the tensor pipe, TMEM address
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
@@ -442,7 +466,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
         int cur_idx[T3_MAXLD];
         float4 recs[T3_MAXLD];
         auto fetch_idx = [&](int ord) {                 // source row (or -1) of this thread's items of tile ordinal `ord`
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)ord * gridDim.x;
+            const int64_t tile = (int64_t)bid + (int64_t)ord * gdim;
 #pragma unroll
             for (int j = 0; j < T3_MAXLD; ++j) {
                 int v = -1;
@@ -499,7 +523,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
         auto flush_grad = [&]() {
             // TMEM accumulators -> this CTA's partial gradient (set on the first flush, added afterwards).  M = 64
             // accumulators: row i is lane i % 16 of the warps of quarter i / 16; the four warps of a quarter split the columns
-            float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
+            float *dst = partial + (int64_t)bid * p.net.n_params;
             const bool add = flushed;
             const int cg4 = warp >> 2;
             const int i = quarter * 16 + lane;
@@ -556,7 +580,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
         for (int i0 = 0; i0 < n_i; i0 += T3_FLUSH_TILES) {
             const int i1 = i0 + T3_FLUSH_TILES < n_i ? i0 + T3_FLUSH_TILES : n_i;
             for (int ord = i0 + slot; ord < i1; ord += NS) {
-                const int64_t tile = (int64_t)blockIdx.x + (int64_t)ord * gridDim.x;
+                const int64_t tile = (int64_t)bid + (int64_t)ord * gdim;
                 const int64_t gr = tile * tr + row;
                 const bool rvalid = row < tr && gr < n_rows;
                 if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
@@ -799,7 +823,7 @@ tc3_grad_kernel(T3Plan p, const unsigned char *__restrict__ image, const float *
             }
         }
         if (p.with_grad && !flushed) {                  // a CTA without tiles still owns a partial vector
-            float *dst = partial + (int64_t)blockIdx.x * p.net.n_params;
+            float *dst = partial + (int64_t)bid * p.net.n_params;
             for (int j = tid; j < p.net.n_params; j += T3_NT) dst[j] = 0.0f;
         }
     }
@@ -848,7 +872,7 @@ extern "C" int32_t mq_record_width(const mq_net_t *net) {
 }
 
 // one (ns = 1) or two (ns = 2) 128-row tile slots
-static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, T3Plan *p) {
+static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, int64_t sms, T3Plan *p) {
     const int rows = T3_ROWS;
     memset(p, 0, sizeof(*p));
     p->net = *net;
@@ -899,7 +923,6 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     p->col_rb = col; col += nbk * T3_NO;
     if (col > 512) return 0;
     // balance: every tile slot of a full wave gets the same number of rows
-    const int64_t sms = mq_sm_count();
     const int64_t waves = mq_ceil_div(batch, sms * ns * rows);
     int64_t tr = mq_round_up(mq_ceil_div(batch, sms * ns * waves), 16);
     if (tr > rows) tr = rows;
@@ -914,10 +937,11 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
 // is not hidden), and publishing the activations K chunk by K chunk so that layer l + 1's products start under layer l's
 // epilogue (61 us against 57 us: four fence / arrive rounds per phase cost more than the ~2 k cycles of product time
 // they hide per tile).
-static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, T3Plan *p, int *ns_out) {
+static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, int64_t sms, T3Plan *p,
+                         int *ns_out) {
     const int planes = t3_planes(tc);
     for (int ns = 2; ns >= 1; --ns)
-        if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, p)) {
+        if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, sms, p)) {
             *ns_out = ns;
             return 1;
         }
@@ -963,51 +987,53 @@ extern "C" int mq_pack_records(const mq_net_t *net, const float *x, const float 
 // bytes mq_tc3_launch may use behind the partial gradients for an image it has to build itself
 int64_t mq_tc3_scratch_bytes() { return 96 * 1024; }
 
-// Launches the record-fed tensor-core gradient kernel.  MQ_ERR_UNSUPPORTED when the net does not fit.
-// Partials go to ws ([grid][n_params]); *grid_out = CTAs launched.
-int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
-                  int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
-    const int planes = t3_planes(head->tc);
-    T3Plan p;
-    int ns = 1;
-    if (!t3_plan_build(net, batch, with_grad, head->tc, head->rec_w, &p, &ns)) return MQ_ERR_UNSUPPORTED;
+// One net's job on `sms` SMs: plan, grid, operand image (built into the workspace when the caller has none).
+static int t3_job_build(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
+                        int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int64_t sms, T3Job *j, int *ns_out,
+                        void *stream) {
+    if (!t3_plan_build(net, batch, with_grad, head->tc, head->rec_w, sms, &j->p, ns_out)) return MQ_ERR_UNSUPPORTED;
     MQ_REQUIRE(((uintptr_t)head->records & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: records must be 16-byte aligned");
-    const int64_t ntiles = mq_ceil_div(batch, p.tile_rows);
-    const int64_t sms = mq_sm_count();
-    const int grid = (int)(ntiles < sms ? ntiles : sms);
-    const int64_t part_bytes = with_grad ? mq_round_up((int64_t)grid * net->n_params * (int64_t)sizeof(float), 256) : 0;
+    const int64_t ntiles = mq_ceil_div(batch, j->p.tile_rows);
+    j->grid = (int)(ntiles < sms ? ntiles : sms);
+    const int64_t part_bytes = with_grad ? mq_round_up((int64_t)j->grid * net->n_params * (int64_t)sizeof(float), 256) : 0;
     if (with_grad) MQ_REQUIRE(ws && ws_bytes >= part_bytes, MQ_ERR_INVALID, "mq_tc3_launch: workspace too small");
     const void *image = head->tc_image;
     if (!image) {
-        MQ_REQUIRE(theta && ws && ws_bytes >= part_bytes + p.img.bytes, MQ_ERR_INVALID,
+        MQ_REQUIRE(theta && ws && ws_bytes >= part_bytes + j->p.img.bytes, MQ_ERR_INVALID,
                    "mq_tc3_launch: no operand image and no room in the workspace to build one");
         void *scratch = (char *)ws + part_bytes;
-        const int rc = t3_image_build(p.img, theta, scratch, stream);
+        const int rc = t3_image_build(j->p.img, theta, scratch, stream);
         if (rc != MQ_OK) return rc;
         image = scratch;
     }
     MQ_REQUIRE(((uintptr_t)image & 15) == 0, MQ_ERR_INVALID, "mq_tc3_launch: image must be 16-byte aligned");
+    j->image = (const unsigned char *)image;
+    j->rec = head->records; j->idx = row_idx; j->n_rows = batch; j->head = *head;
+    j->partial = (float *)ws; j->out = out; j->logp_out = logp;
+    return MQ_OK;
+}
+
+static int t3_launch_jobs(const T3Jobs &jobs, int total_grid, int planes, int ns, int k0, int act, int smem_bytes, void *stream) {
     cudaError_t e = cudaSuccess;
-#define T3_LAUNCH(P_, NS_, K0_, ACT_)                                                                                   \
-    do {                                                                                                                     \
-        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes); \
-        if (e == cudaSuccess)                                                                                                \
-            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, K0_, ACT_>, dim3(grid), dim3(T3_NTI), (size_t)p.smem_bytes, stream, p, \
-                              (const unsigned char *)image, head->records, row_idx, batch, *head, (float *)ws, out, logp, \
-                              mq_phase_prof_ptr());   \
+#define T3_LAUNCH(P_, NS_, K0_, ACT_)                                                                                       \
+    do {                                                                                                                    \
+        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+        if (e == cudaSuccess)                                                                                               \
+            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, K0_, ACT_>, dim3(total_grid), dim3(T3_NTI), (size_t)smem_bytes, stream, \
+                              jobs, mq_phase_prof_ptr());                                                                   \
     } while (0)
-#define T3_LAUNCH_ACT(P_, NS_, K0_)                                          \
-    do {                                                                          \
-        if (net->act[0] == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, K0_, MQ_ACT_TANH); \
-        else T3_LAUNCH(P_, NS_, K0_, MQ_ACT_LRELU);                          \
+#define T3_LAUNCH_ACT(P_, NS_, K0_)                                      \
+    do {                                                                 \
+        if (act == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, K0_, MQ_ACT_TANH);    \
+        else T3_LAUNCH(P_, NS_, K0_, MQ_ACT_LRELU);                      \
     } while (0)
 #define T3_LAUNCH_P(P_)                                              \
     do {                                                             \
         if (ns == 2) T3_LAUNCH_ACT(P_, 2, 16);                       \
-        else if (p.img.k0 == 16) T3_LAUNCH_ACT(P_, 1, 16);           \
+        else if (k0 == 16) T3_LAUNCH_ACT(P_, 1, 16);                 \
         else T3_LAUNCH_ACT(P_, 1, 32);                               \
     } while (0)
-    if (planes == 3) { if (p.img.k0 == 16) T3_LAUNCH_ACT(3, 1, 16); else T3_LAUNCH_ACT(3, 1, 32); }
+    if (planes == 3) { if (k0 == 16) T3_LAUNCH_ACT(3, 1, 16); else T3_LAUNCH_ACT(3, 1, 32); }
     else if (planes == 2) T3_LAUNCH_P(2);
     else T3_LAUNCH_P(1);
 #undef T3_LAUNCH_P
@@ -1018,7 +1044,52 @@ int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, co
         return MQ_ERR_CUDA;
     }
     MQ_CHECK_LAUNCH("mq_tc3_launch");
-    if (grid_out) *grid_out = grid;
+    return MQ_OK;
+}
+
+// Launches the record-fed tensor-core gradient kernel.  MQ_ERR_UNSUPPORTED when the net does not fit.
+// Partials go to ws ([grid][n_params]); *grid_out = CTAs launched.
+int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
+                  int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream) {
+    T3Jobs local;
+    memset(&local, 0, sizeof(local));
+    int ns = 1;
+    const int rc = t3_job_build(net, row_idx, batch, head, theta, with_grad, out, logp, ws, ws_bytes, mq_sm_count(), &local.job[0],
+                                &ns, stream);
+    if (rc != MQ_OK) return rc;
+    const int rc2 = t3_launch_jobs(local, local.job[0].grid, t3_planes(head->tc), ns, local.job[0].p.img.k0, net->act[0],
+                                   local.job[0].p.smem_bytes, stream);
+    if (rc2 == MQ_OK && grid_out) *grid_out = local.job[0].grid;
+    return rc2;
+}
+
+// Two independent minibatch gradients (two nets of the same shape class: planes, slots, padded input width and hidden
+// activation must agree) as ONE launch, each on half of the SMs.  MQ_ERR_UNSUPPORTED when they cannot share a launch.
+extern "C" int mq_fused_grad_partials2(const mq_net_t *net_a, const float *theta_a, const int32_t *idx_a, const mq_head_t *head_a,
+                                       void *ws_a, int64_t ws_a_bytes, int32_t *n_parts_a, const mq_net_t *net_b,
+                                       const float *theta_b, const int32_t *idx_b, const mq_head_t *head_b, void *ws_b,
+                                       int64_t ws_b_bytes, int32_t *n_parts_b, int64_t batch, void *stream) {
+    MQ_REQUIRE(net_a && net_b && head_a && head_b && ws_a && ws_b && n_parts_a && n_parts_b, MQ_ERR_INVALID,
+               "mq_fused_grad_partials2: null pointer");
+    MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_fused_grad_partials2: empty batch");
+    if (!head_a->records || !head_b->records || ((head_a->tc | head_b->tc) & MQ_TC_OFF)) return MQ_ERR_UNSUPPORTED;
+    if (t3_planes(head_a->tc) != t3_planes(head_b->tc) || net_a->act[0] != net_b->act[0]) return MQ_ERR_UNSUPPORTED;
+    T3Jobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    const int64_t sms = mq_sm_count();
+    const int64_t half = sms / 2 > 0 ? sms / 2 : 1;
+    int ns_a = 1, ns_b = 1;
+    int rc = t3_job_build(net_a, idx_a, batch, head_a, theta_a, 1, nullptr, nullptr, ws_a, ws_a_bytes, half, &jobs.job[0], &ns_a, stream);
+    if (rc != MQ_OK) return rc;
+    rc = t3_job_build(net_b, idx_b, batch, head_b, theta_b, 1, nullptr, nullptr, ws_b, ws_b_bytes, sms - half, &jobs.job[1], &ns_b, stream);
+    if (rc != MQ_OK) return rc;
+    if (ns_a != ns_b || jobs.job[0].p.img.k0 != jobs.job[1].p.img.k0) return MQ_ERR_UNSUPPORTED;
+    const int smem = jobs.job[0].p.smem_bytes > jobs.job[1].p.smem_bytes ? jobs.job[0].p.smem_bytes : jobs.job[1].p.smem_bytes;
+    rc = t3_launch_jobs(jobs, jobs.job[0].grid + jobs.job[1].grid, t3_planes(head_a->tc), ns_a, jobs.job[0].p.img.k0, net_a->act[0],
+                        smem, stream);
+    if (rc != MQ_OK) return rc;
+    *n_parts_a = jobs.job[0].grid;
+    *n_parts_b = jobs.job[1].grid;
     return MQ_OK;
 }
 
@@ -1031,4 +1102,7 @@ extern "C" int mq_pack_records(const mq_net_t *, const float *, const float *, c
 int64_t mq_tc3_scratch_bytes() { return 0; }
 int mq_tc3_launch(const mq_net_t *, const int32_t *, int64_t, const mq_head_t *, const float *, int, float *, float *, void *,
                   int64_t, int *, void *) { return MQ_ERR_UNSUPPORTED; }
+extern "C" int mq_fused_grad_partials2(const mq_net_t *, const float *, const int32_t *, const mq_head_t *, void *, int64_t, int32_t *,
+                                       const mq_net_t *, const float *, const int32_t *, const mq_head_t *, void *, int64_t, int32_t *,
+                                       int64_t, void *) { return MQ_ERR_UNSUPPORTED; }
 #endif

@@ -26,7 +26,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, TC_MODES, MqHead
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, TC_MODES, MqHead, MqTrain
 from ._normalize import RunningNormalize
 from .basicnet import normed_columns
 
@@ -136,6 +136,41 @@ class _Net(object):
             mqdist.allreduce_sum_(self.grad)
             D.call("mq_adam_step", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
                    self.net.n_params, self.code, MQ_F32, coefs[2 * s], coefs[2 * s + 1], lr, eps, 0, D.stream())
+
+    def prepare_pair(self, x, head, idx_table, n_steps, mb, lr, eps, col0, idx_stride):
+        """This net's side of a paired training loop (mq_train_steps2); returns (MqTrain, keep-alive objects) or None when
+        the net cannot take the record-fed tensor-core path."""
+        if self.image is None or self.records is None or mb < 8192:
+            return None
+        if self._peer is None:
+            self._peer = mqdist.PeerExchange(self.net.n_params)
+        if mqdist.world() > 1 and not self._peer.available():
+            return None
+        lib = _lib.lib()
+        wsb = lib.mq_fused_ws_bytes(ctypes.byref(self.net), mb)
+        ws = D.workspace(("fused", id(self)), wsb)
+        coefs = (ctypes.c_double * (2 * n_steps))()
+        for s in range(n_steps):
+            coefs[2 * s], coefs[2 * s + 1] = self.opt.next_coefs()
+        self.opt._out = None
+        value, m, v, _ = self.opt.state()
+        head.tc = (head.tc & ~3) | self.planes
+        head.records, head.rec_w, head.tc_image = D.ptr(self.records), self.rec_w, D.ptr(self.image)
+        D.call("mq_tc_image_build", ctypes.byref(self.net), D.ptr(self.theta), self.planes, D.ptr(self.image), D.stream())
+        t = MqTrain()
+        t.net, t.theta, t.x, t.head = ctypes.addressof(self.net), D.ptr(self.theta), D.ptr(x), ctypes.addressof(head)
+        t.idx_table, t.idx_stride = D.ptr(idx_table) + 4 * col0, idx_stride
+        t.scale = 1.0 / float(mb * mqdist.world())
+        t.value, t.m, t.v = D.ptr(value), D.ptr(m), D.ptr(v)
+        t.coefs_host, t.lr, t.eps = ctypes.addressof(coefs), lr, eps
+        keep = [coefs, head, ws]
+        if mqdist.world() > 1:
+            peer = self._peer.descriptor()
+            self._peer.step += n_steps - 1
+            t.peer = ctypes.addressof(peer)
+            keep.append(peer)
+        t.ws, t.ws_bytes = D.ptr(ws), wsb
+        return t, keep
 
     def exchange(self):
         """Which gradient exchange the sharded steps use: "ll" | "push" | "pull" (in-kernel, peer memory) or "nccl"."""
@@ -263,9 +298,33 @@ class PPOUpdater(object):
         concurrent = not os.environ.get("MQ_PPO_SERIAL") and world == 1
         vhead = MqHead()
         vhead.kind, vhead.target = HEAD_DIFF, D.ptr(ret)
+        head = MqHead()
+        head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
+        head.ent = self.ent_coef
+        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
+        # Large minibatches on the same schedule (BASELINE configs[2]): the two nets' steps are PAIRED -- per step one
+        # gradient launch with each net on half of the SMs and one reduce / exchange / Adam launch for both (csrc/mq_tc3.cu,
+        # csrc/mq_step.cu) -- in one stream, hence in one fixed order on every rank.  MQ_PPO_UNPAIRED=1: the two chains apart.
+        paired = (v_mb >= 8192 and v_mb == p_mb and v_steps == p_steps and val.code == pol.code and
+                  not os.environ.get("MQ_PPO_UNPAIRED"))
         big = v_mb >= 8192 or p_mb >= 8192
         if big:
             val.pack(obs, ret, None, None, n)
+        if paired:
+            self.normalize.update_dev(adv, n, sharded=world > 1 and not split)
+            self.normalize.apply_dev(adv, n, out=adv_n, fuse_tanh=True)
+            self._forward_rows(pol, obs, n, None, sample=act, logp=logp0, split=split)
+            pol.pack(obs, act, adv_n, logp0, n)
+            ta = val.prepare_pair(obs, vhead, val_idx, v_steps, v_mb, self.val_lr, 1e-8, v_col0, v_stride)
+            tb = pol.prepare_pair(obs, head, pol_idx, p_steps, p_mb, self.pol_lr, 1e-8, p_col0, p_stride) if ta else None
+            if ta and tb:
+                D.call("mq_train_steps2", ctypes.byref(ta[0]), ctypes.byref(tb[0]), v_steps, v_mb, val.code, 0, D.stream())
+                return adv, ret
+            assert ta is None and tb is None, "only one net of a pair can take the paired path"
+            # (neither took it: fall through to the separate chains; the normaliser and logp0 above are already done)
+            val.train(obs, vhead, val_idx, v_steps, v_mb, self.val_lr, col0=v_col0, idx_stride=v_stride)
+            pol.train(obs, head, pol_idx, p_steps, p_mb, self.pol_lr, col0=p_col0, idx_stride=p_stride)
+            return adv, ret
         if concurrent:
             self._ev_gae.record(main)
             with torch.cuda.stream(self._side):              # value predictor chain (gae.py:66-73)
@@ -278,10 +337,6 @@ class PPOUpdater(object):
         self.normalize.update_dev(adv, n, sharded=world > 1 and not split)
         self.normalize.apply_dev(adv, n, out=adv_n, fuse_tanh=True)
         self._forward_rows(pol, obs, n, None, sample=act, logp=logp0, split=split)
-        head = MqHead()
-        head.kind, head.p0, head.p1 = (HEAD_DISCRETE_PPO if self.discrete else HEAD_GAUSS_PPO), self.clip[0], self.clip[1]
-        head.ent = self.ent_coef
-        head.target, head.adv, head.logp_old = D.ptr(act), D.ptr(adv_n), D.ptr(logp0)
         if big:
             pol.pack(obs, act, adv_n, logp0, n)
         pol.train(obs, head, pol_idx, p_steps, p_mb, self.pol_lr, col0=p_col0, idx_stride=p_stride)
