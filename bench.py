@@ -335,7 +335,7 @@ class PPOLargeWorkload(object):
         self.pinned = [tuple(torch.from_numpy(x).pin_memory() for x in r[:4]) for r in self.rollouts[:1]]
         self.out_pinned = (torch.empty(5126, dtype=torch.float32).pin_memory(),
                            torch.empty(4993, dtype=torch.float32).pin_memory())
-        self.h2d = sum(x.nbytes for x in self.rollouts[0][:4])
+        self.h2d = sum(x.nbytes for x in self.rollouts[0][:4]) // (self.world if self.replicated else 1)
         self.idx_bytes_once = sum(x.nbytes for x in self.rollouts[0][4:])
         self.d2h = (5126 + 4993) * 4
         self._next = None
@@ -348,10 +348,10 @@ class PPOLargeWorkload(object):
         prefetch() starts the upload of step i+1 on a copy stream before step i's kernels are launched, the way a training
         loop feeds rollouts; every step still copies its own inputs H2D and its results D2H inside the timed region."""
         if self._next is None:
-            self._next = self.upd.prefetch(*self.pinned[0])
+            self._next = self.upd.prefetch(*self.pinned[0], replicated=self.replicated)
         cur, self._next = self._next, None
         vi, pi = self.dev[0][4], self.dev[0][5]
-        nxt = self.upd.prefetch(*self.pinned[0])
+        nxt = self.upd.prefetch(*self.pinned[0], replicated=self.replicated)
         self.upd.update(cur, val_idx=vi, pol_idx=pi, replicated=self.replicated, out=self.out_pinned)
         self._next = nxt
 
@@ -653,6 +653,48 @@ class MLPWorkload(object):
                     achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
                     peak_source=peaks["source"], ms_per_launch=ms,
                     note="latency-bound at batch 128: 3.25 MB / 65 MFLOP per step is 0.5 us at roofline")
+
+    def sweep(self, peaks):
+        """BASELINE.md 3.4 / SURVEY 8d: the batch sweep B in {128, 1024, 8192, 65536} for the script's net (784-128-128-10,
+        mnist/mlp.py:24-27) and BASELINE.json's wording (784-128-10), fwd + bwd + Adam per step, each with its roofline:
+        HBM (3,216 B per sample + 24 B per parameter) where the step is memory / latency bound, the measured dense bf16
+        peak where the Affine layers are real contractions (from batch ~1k they run on the TMA-fed tcgen05 GEMM)."""
+        t = self.torch
+        from mannequin2_b200.mlp import MLPTrainer
+        from mannequin2_b200 import _lib as L
+        rs = np.random.RandomState(11)
+        out = {}
+        for widths, acts, tag in (((128, 128, 10), (L.ACT_LRELU, L.ACT_LRELU, L.ACT_NONE), "784-128-128-10"),
+                                  ((128, 10), (L.ACT_LRELU, L.ACT_NONE), "784-128-10")):
+            s_all = sum(a * b for a, b in zip((784,) + widths[:-1], widths))
+            s_rest = s_all - 784 * widths[0]
+            flop_per_sample = 4 * s_all + 2 * s_rest                     # SURVEY 8d: 2S fwd + 2S dW + 2S' dX
+            n_params = s_all + sum(widths)
+            for B in (128, 1024, 8192, 65536):
+                block = 32 if B <= 1024 else (8 if B <= 8192 else 3)
+                np.random.seed(0)
+                tr = MLPTrainer(784, widths, acts, batch=B, graph_steps=block)
+                tab = self.D.from_host(rs.randint(len(self.x), size=(block, B)).astype(np.int32))
+                times = []
+                for k in range(5):
+                    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                    e0.record()
+                    tr.train_block(self.xd, self.yd, tab)
+                    e1.record()
+                    e1.synchronize()
+                    times.append(e0.elapsed_time(e1))
+                ms = float(np.median(times[2:])) / block
+                bytes_per_step = B * 3216 + 24 * n_params
+                gbs = bytes_per_step / (ms * 1e-3) / 1e9
+                tf = B * flop_per_sample / (ms * 1e-3) / 1e12
+                bound = "tensor" if tf / peaks["bf16"] > gbs / peaks["hbm"] else "hbm"
+                out["%s_B%d" % (tag, B)] = dict(samples_per_s=B / (ms * 1e-3), ms_per_step=ms, fp32_tflops=tf,
+                                                frac_of_bf16_peak=tf / peaks["bf16"], issued_bf16_frac=6 * tf / peaks["bf16"],
+                                                hbm_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm"], bound=bound,
+                                                roofline_frac=max(tf / peaks["bf16"], gbs / peaks["hbm"]))
+                del tr, tab
+                t.cuda.empty_cache()
+        return out
 
     def setup_cpu(self):
         from oracle import mq_oracle as O
@@ -1280,7 +1322,8 @@ def main():
                 r2 = w2.dominant_kernel(peaks)
                 c1 = time_cpu(name, 1, 1, 1, threads=None)[0] if getattr(w2, "step_cpu", None) else None
                 reps = [w2.replica_throughput(r) for r in (8, 16)] if hasattr(w2, "replica_throughput") else None
-                others[name] = dict(workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
+                extra = {"sweep": w2.sweep(peaks)} if hasattr(w2, "sweep") else {}
+                others[name] = dict(extra, workload=w2.name, metric=w2.metric, unit=w2.unit, value=u / (m1 * 1e-3),
                                     e2e=u / (m2 * 1e-3), ms_per_step=m1 / 5, cpu_port_1proc=c1,
                                     independent_replicas=reps, roofline={k: r2[k] for k in r2 if k in ("kernel", "achieved", "frac", "ms_per_launch",
                                                                              "fp32_tflops", "fp32_frac", "note", "collect_ms",

@@ -143,7 +143,7 @@ static int64_t gemm_tc_splits(int64_t m, int64_t n, int64_t k, int64_t *k_per_sp
 }
 
 static bool gemm_tc_wanted(const GemmArgs &g, int32_t tc) {
-    if ((tc & MQ_TC_OFF) || g.a_ones_row != 0 || g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
+    if ((tc & MQ_TC_OFF) || g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
     if (tc & MQ_TC_FORCE) return true;
     return g.m * g.n * g.k >= (1LL << 26) && g.n >= 64 && g.k >= 64 && g.m >= 128;
 }
@@ -388,10 +388,9 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
         g.b = g_cur; g.b_rs = net->out[l]; g.b_cs = 1;
         g.c = grad + net->w_off[l]; g.m = net->in[l]; g.n = net->out[l]; g.k = batch;
         g.alpha = scale; g.epi = EPI_SCALE;
-        // small layers (FFMA kernel): the bias gradient 1^T g is one more row of the same product, written straight into
-        // b's slot behind W; large ones keep the tensor-core product and a separate column sum
-        const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l] &&
-                               (int64_t)net->in[l] * net->out[l] * batch < (1LL << 26);
+        // the bias gradient 1^T g is one more row of the same product (a row of ones appended to x^T), written straight
+        // into b's slot behind W
+        const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l];
         if (fuse_bias) { g.m = net->in[l] + 1; g.a_ones_row = net->in[l]; }
         rc = gemm_run(g, split_ws, split_bytes, 0, w_stream, "mq_mlp_backward(dW)");
         if (rc != MQ_OK) return rc;

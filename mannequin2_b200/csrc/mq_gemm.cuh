@@ -20,7 +20,7 @@ struct GemmArgs {
     const float *bias;       // EPI_BIAS_ACT
     const float *y;          // EPI_ACT_GRAD, [M,N] row-major
     int64_t a_ones_row;      // > 0: rows m >= a_ones_row of A read as 1.0 (dW = x^T g with the bias gradient 1^T g as
-                             // one more output row: W and b are adjacent in the flat parameter vector).  FFMA kernel only.
+                             // one more output row: W and b are adjacent in the flat parameter vector).
 };
 
 __device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int64_t m, int64_t n) {

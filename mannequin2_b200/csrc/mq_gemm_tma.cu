@@ -47,7 +47,8 @@
 template <int P>
 __global__ void __launch_bounds__(MQ_NT)
 pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k,
-                   int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad, int rows_fast, __nv_bfloat16 *__restrict__ out) {
+                   int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad, int rows_fast, int64_t ones_row,
+                   __nv_bfloat16 *__restrict__ out) {
     const int64_t kc_n = k_pad / 8;
     const int64_t item = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
     if (item >= rows_pad * kc_n) return;
@@ -57,7 +58,10 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-    if (r < rows) {
+    if (ones_row > 0 && r >= ones_row && r < rows) {         // rows that read as 1.0 (the bias-gradient row of dW = x^T g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (kc * 8 + j < k) ? 1.0f : 0.0f;
+    } else if (r < rows) {
         const int64_t sr = (idx && !idx_on_k) ? (int64_t)idx[r] : r;
         const int64_t k0 = kc * 8;
         if (cs == 1 && !(idx && idx_on_k) && k0 + 8 <= k && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(rs * 4)) & 15) == 0) {
@@ -88,6 +92,54 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
 #pragma unroll
     for (int pl = 0; pl < P; ++pl)
         *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + kc * 8) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+}
+
+// The same for operands whose ROWS are the unit-stride axis of the source (A = x^T of dW = x^T g: src(r, k) = x[k][r]),
+// through a shared-memory tile: reads run along r (coalesced), writes along k (128 contiguous bytes per row and plane
+// instead of 16-byte pieces a whole packed row apart).  Tile = 32 rows x 64 k per CTA of 256 threads.
+template <int P>
+__global__ void __launch_bounds__(MQ_NT)
+pack_planes_t_kernel(const float *__restrict__ base, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k, int64_t rows,
+                     int64_t k, int64_t rows_pad, int64_t k_pad, int64_t ones_row, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float tile[64][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 64;
+    const int tr = threadIdx.x & 31, tk = threadIdx.x >> 5;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+        const int kk = pass * 8 + tk;
+        const int64_t r = r0 + tr, kg = k0 + kk;
+        float v = 0.0f;
+        if (r < rows && kg < k) {
+            if (ones_row > 0 && r >= ones_row) v = 1.0f;
+            else {
+                const int64_t sr = (idx && !idx_on_k) ? (int64_t)idx[r] : r;
+                const int64_t sk = (idx && idx_on_k) ? (int64_t)idx[kg] : kg;
+                v = __ldg(base + sr + sk * cs);
+            }
+        }
+        tile[kk][tr] = v;
+    }
+    __syncthreads();
+    const int m = threadIdx.x >> 3, kc = threadIdx.x & 7;
+    uint32_t w[4][P];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = tile[kc * 8 + 2 * j][m], b = tile[kc * 8 + 2 * j + 1][m];
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            w[j][pl] = *reinterpret_cast<const uint32_t *>(&h);
+            a -= __uint_as_float(w[j][pl] << 16);
+            b -= __uint_as_float(w[j][pl] & 0xFFFF0000u);
+        }
+    }
+    const int64_t r = r0 + m;
+    if (r < rows_pad && k0 + kc * 8 < k_pad) {
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl)
+            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + k0 + kc * 8) =
+                make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+    }
 }
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
@@ -230,14 +282,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             __syncwarp();
             if (lane == 0) gm_arrive(tc_smem_u32(&s_accempty[set]));
         }
-        const int64_t gm = m0 + quarter * 32 + lane;
-        if (gm < g.m) {
+        // registers -> C through shared memory (the operand stages are free: every product that read them has completed
+        // and every TMA load has been consumed), so that a warp writes whole 256-byte row segments instead of 32 rows x 4
+        // bytes per instruction -- and reads bias / the saved activations of the act' epilogue the same way
+        float *stage = reinterpret_cast<float *>(smem_raw + (sbase - tc_smem_u32(smem_raw))) + (warp - 2) * (32 * 65);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int64_t gn = n0 + half * 64 + j;
+        for (int j = 0; j < 64; ++j) stage[lane * 65 + j] = acc[j];
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int64_t gm = m0 + quarter * 32 + r;
+            if (gm >= g.m) break;
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+                const int64_t gn = n0 + half * 64 + hc * 32 + lane;
                 if (gn >= g.n) continue;
-                if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = acc[j];
-                else g.c[gm * g.n + gn] = gemm_epilogue(g, acc[j], gm, gn);
+                const float v = stage[r * 65 + hc * 32 + lane];
+                if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
+                else g.c[gm * g.n + gn] = gemm_epilogue(g, v, gm, gn);
             }
         }
     }
@@ -290,19 +351,24 @@ int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes) {
 
 template <int P>
 static int gm_pack(const float *base, int64_t rs, int64_t cs, const int32_t *idx, int idx_on_k, int64_t rows, int64_t k,
-                   void *out, void *stream) {
+                   int64_t ones_row, void *out, void *stream) {
     const int64_t rows_pad = mq_round_up(rows, 128), k_pad = mq_round_up(k, GM_BK);
+    if (rs == 1 && cs != 1) {          // rows are the unit-stride axis: transpose through shared memory
+        dim3 grid((unsigned)(rows_pad / 32), (unsigned)(k_pad / 64));
+        MQ_LAUNCH(pack_planes_t_kernel<P>, grid, MQ_NT, 0, stream, base, cs, idx, idx_on_k, rows, k, rows_pad, k_pad, ones_row,
+                  (__nv_bfloat16 *)out);
+        return MQ_OK;
+    }
     const int64_t items = rows_pad * (k_pad / 8);
-    const int rows_fast = (rs == 1 && cs != 1) ? 1 : 0;
     MQ_LAUNCH(pack_planes_kernel<P>, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, base, rs, cs, idx, idx_on_k, rows, k,
-              rows_pad, k_pad, rows_fast, (__nv_bfloat16 *)out);
+              rows_pad, k_pad, 0, ones_row, (__nv_bfloat16 *)out);
     return MQ_OK;
 }
 
 // Launches pack + GEMM.  g.c points at the split-K partial buffer when splits > 1 (g.k_per_split a multiple of 64).
 // `pack` = workspace of mq_gemm_tma_pack_bytes() bytes.  MQ_ERR_UNSUPPORTED when tensor maps are not available.
 int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack, void *stream) {
-    if (g.m <= 0 || g.n <= 0 || g.k <= 0 || g.a_ones_row != 0) return MQ_ERR_UNSUPPORTED;
+    if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
     if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
     const int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128), k_pad = mq_round_up(g.k, GM_BK);
@@ -311,14 +377,14 @@ int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack
     // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
     int rc;
     if (planes == 3) {
-        rc = gm_pack<3>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
-        rc = gm_pack<3>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+        rc = gm_pack<3>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<3>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     } else if (planes == 2) {
-        rc = gm_pack<2>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
-        rc = gm_pack<2>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+        rc = gm_pack<2>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<2>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     } else {
-        rc = gm_pack<1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, pa, stream);
-        rc = gm_pack<1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, pb, stream);
+        rc = gm_pack<1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     }
     (void)rc;
     alignas(64) CUtensorMap map_a, map_b;

@@ -370,16 +370,41 @@ class PPOUpdater(object):
             return a.to(D.device(), non_blocking=True)
         return D.from_host(np.ascontiguousarray(a, dtype=dtype))
 
-    def prefetch(self, obs, act, rew, done):
+    def _upload_split(self, t, dtype):
+        """Replicated data-parallel form: this rank uploads 1/world of the rows of a host tensor and the ranks all-gather the
+        pieces over NVLink, instead of every rank pulling the whole rollout through its own PCIe link."""
+        w, r = mqdist.world(), mqdist.rank()
+        if not isinstance(t, torch.Tensor):
+            t = torch.from_numpy(np.ascontiguousarray(t, dtype=dtype))
+        if t.is_cuda:
+            return t
+        rows = t.shape[0]
+        rowlen = t.numel() // max(rows, 1)
+        chunk = -(-rows // w)
+        lo = min(r * chunk, rows)
+        cnt = min(chunk, rows - lo)
+        part = torch.zeros(chunk * rowlen, dtype=t.dtype, device=D.device())
+        if cnt > 0:
+            part[:cnt * rowlen].copy_(t.reshape(-1)[lo * rowlen:(lo + cnt) * rowlen], non_blocking=True)
+        full = torch.empty(chunk * w * rowlen, dtype=t.dtype, device=D.device())
+        mqdist.allgather_into(full, part)
+        return full[:rows * rowlen].view(t.shape)
+
+    def prefetch(self, obs, act, rew, done, replicated=False):
         """Start uploading the NEXT rollout (pinned host tensors) on a copy stream while the current update runs; the
-        returned handle is passed to update() in place of the four arrays."""
+        returned handle is passed to update() in place of the four arrays.  replicated=True (every rank holds the same
+        rollout): each rank uploads its share of the rows and the shares are all-gathered."""
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
         self._copy_stream.wait_stream(main)
+        split = bool(replicated) and mqdist.world() > 1
         with torch.cuda.stream(self._copy_stream):
-            dev = [self._to_dev(a, dt) for a, dt in zip((obs, act, rew, done), (np.float32, np.int32 if self.discrete else
-                                                                                  np.float32, np.float32, np.uint8))]
+            dts = (np.float32, np.int32 if self.discrete else np.float32, np.float32, np.uint8)
+            if split:
+                dev = [self._upload_split(a, dt) for a, dt in zip((obs, act, rew, done), dts)]
+            else:
+                dev = [self._to_dev(a, dt) for a, dt in zip((obs, act, rew, done), dts)]
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return ("prefetched", dev, ev)
