@@ -43,9 +43,10 @@ struct T3Plan {
     int rec_w, q4, hin_w;
     // byte offsets inside a slot (slot s starts at s * slot_bytes); act[l]: planes P-1 .. 0, then the ones chunk
     int off_dzl, dzl_plane, off_act[T3_MAXL], act_plane[T3_MAXL], off_hin, slot_bytes;
+    int x_bufs, x_stride, hin_stride;   // input tile (operand planes + head inputs) double-buffered when shared memory allows
     int off_const, smem_bytes;
     // TMEM columns
-    int col_za[2], col_acc[T3_MAXL], col_rb;
+    int col_za[2], col_acc[T3_MAXL];
     int col_save[2];             // fp32 hidden activations kept in TMEM for the backward pass (-1: rebuilt from the planes)
 };
 
@@ -285,7 +286,8 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
 #endif
     T3_MARK(1);
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint64_t s_full[2], s_dw[2], s_ready[2], s_img;
+    __shared__ __align__(8) uint64_t s_full[2], s_dw[2], s_ready[2], s_readyx[2], s_img;
+    __shared__ float s_rb[T3_NT / 32][8];               // per-warp column sums of the output layer's dZ (bias / logstd gradients)
     constexpr int ROWS = T3_ROWS;             // rows of a slot
     constexpr int CB = T3_CB;                 // one 8-feature chunk of all rows of a slot
     constexpr int GT = T3_NT / NS;            // threads of a slot group
@@ -313,10 +315,13 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) { t3_mbar_init(&s_full[s], 1); t3_mbar_init(&s_dw[s], 1); t3_mbar_init(&s_ready[s], GW); }
+        for (int s = 0; s < 2; ++s) {
+            t3_mbar_init(&s_full[s], 1); t3_mbar_init(&s_dw[s], 1); t3_mbar_init(&s_ready[s], GW); t3_mbar_init(&s_readyx[s], GW);
+        }
         t3_mbar_init(&s_img, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
+    if (tid < (T3_NT / 32) * 8) (&s_rb[0][0])[tid] = 0.0f;
     // clear the slots except the hidden activation buffers (every tile rewrites all of their rows)
     if (worker) {
         for (int s = 0; s < NS; ++s) {
@@ -329,25 +334,33 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
         const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
         const uint32_t ob = *reinterpret_cast<const uint16_t *>(&one);
         for (int s = 0; s < NS; ++s)
-            for (int l = 0; l < L; ++l) {
-                uint32_t *ones = reinterpret_cast<uint32_t *>(smem + s * p.slot_bytes + p.off_act[l] + P * p.act_plane[l]);
-                for (int i = tid; i < CB / 4; i += T3_NT) ones[i] = ob | (ob << 16);
-            }
+            for (int l = 0; l < L; ++l)
+                for (int xb = 0; xb < (l == 0 ? p.x_bufs : 1); ++xb) {
+                    uint32_t *ones = reinterpret_cast<uint32_t *>(smem + s * p.slot_bytes + p.off_act[l] + xb * p.x_stride + P * p.act_plane[l]);
+                    for (int i = tid; i < CB / 4; i += T3_NT) ones[i] = ob | (ob << 16);
+                }
     }
     const uint32_t sbase = tc_smem_u32(smem);
     const uint32_t img_bar = tc_smem_u32(&s_img);
     T3_MARK(2);
-    mq_pdl_wait();                        // the predecessor's writes (image, records) are complete and visible
-    T3_MARK(3);
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(img_bar), "r"((uint32_t)p.img.bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(sbase + p.off_const), "l"(image), "r"((uint32_t)p.img.bytes), "r"(img_bar) : "memory");
-    }
+    // The operand image is written by the predecessor (the optimiser-step kernel): it is fetched after griddepcontrol.wait.
+    // The minibatch indices and the packed records are NOT (they date from before the update's first step), so the workers
+    // start their first gathers before waiting -- under the tail of the step kernel.
+    auto wait_and_fetch_image = [&]() {
+        mq_pdl_wait();
+        T3_MARK(3);
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(img_bar), "r"((uint32_t)p.img.bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + p.off_const), "l"(image), "r"((uint32_t)p.img.bytes), "r"(img_bar) : "memory");
+        }
+        tc_wait(img_bar, 0);                            // weights, biases, head parameters have landed
+        T3_MARK(4);
+    };
     const float *sBias = reinterpret_cast<const float *>(smem + p.off_const + p.img.off_bias);      // [L][64]
     const float *sMisc = reinterpret_cast<const float *>(smem + p.off_const + p.img.off_misc);      // logstd[16], exp(-logstd)[16]
     unsigned char *sl = smem + slot * p.slot_bytes;                                                 // this group's slot
-    float *sHin = reinterpret_cast<float *>(sl + p.off_hin);                                        // [128][hin_w]
+    float *sHin0 = reinterpret_cast<float *>(sl + p.off_hin);                                       // [x_bufs][128][hin_w]
     const int tr = p.tile_rows;
     const int64_t ntiles = (n_rows + tr - 1) / tr;
     const int dw_ksteps = tr / 16;
@@ -360,19 +373,18 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
 
     tc_publish();                                       // zeroed buffers / ones chunks visible to the tensor pipe, TMEM address
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
-    tc_wait(img_bar, 0);                                // weights, biases, head parameters have landed
-    T3_MARK(4);
 
     if (!worker) {
         // ---- issuer warp ---------------------------------------------------------------------------------------
-        uint32_t rdy_par[2] = {0u, 0u};
+        wait_and_fetch_image();
+        uint32_t rdy_par[2] = {0u, 0u}, rdx_par[2] = {0u, 0u};
+        int tcount[2] = {0, 0};                          // tiles issued per slot: selects the input buffer
         for (int i0 = 0; i0 < n_i; i0 += T3_FLUSH_TILES) {
             const int i1 = i0 + T3_FLUSH_TILES < n_i ? i0 + T3_FLUSH_TILES : n_i;
             int cnt[2];
             cnt[0] = (i1 - i0 + NS - 1) / NS;
             cnt[1] = NS == 2 ? (i1 - i0) / 2 : 0;
             bool acc_started[T3_MAXL] = {false, false, false};
-            bool rb_started = false;                                            // the ones-row product
             for (int k = 0; k < cnt[0] * jobs; ++k) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
@@ -381,19 +393,24 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                     const uint32_t sb = sbase + s * p.slot_bytes;
                     const uint32_t za = tm + p.col_za[s];
                     const uint32_t full = tc_smem_u32(&s_full[s]), dwb = tc_smem_u32(&s_dw[s]);
-                    tc_wait(tc_smem_u32(&s_ready[s]), rdy_par[s]); rdy_par[s] ^= 1u;
+                    const uint32_t xo = (p.x_bufs == 2 && (tcount[s] & 1)) ? (uint32_t)p.x_stride : 0u;     // this tile's input buffer
+                    // job 0 waits for the staged input tile (its own barrier: with two input buffers the next tile is staged
+                    // right behind the last backward epilogue, and two arrivals of one warp must not fall into one phase)
+                    if (job == 0) { tc_wait(tc_smem_u32(&s_readyx[s]), rdx_par[s]); rdx_par[s] ^= 1u; }
+                    else { tc_wait(tc_smem_u32(&s_ready[s]), rdy_par[s]); rdy_par[s] ^= 1u; }
                     T3_MARK(100 + 10 * s + job);
                     if (tc_elect_one()) {
                         if (job < L) {
                             const int l = job;
-                            t3_rows_product<P>(za, sb + p.off_act[l] + (P - 1) * p.act_plane[l], p.act_plane[l], CB,
+                            t3_rows_product<P>(za, sb + p.off_act[l] + (l == 0 ? xo : 0u) + (P - 1) * p.act_plane[l], p.act_plane[l], CB,
                                                t3_wf_k<P>(sbase + p.off_const + p.img.off_wf[l], p.img.np[l]), 0, (uint32_t)p.img.np[l],
                                                p.img.np[l], p.img.kp[l] / 16);
                             tc_commit(full);
                         } else {
                             const int l = 2 * L - 1 - job;
                             if (l == L - 1) {
-                                // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form), db_l / dlogstd (+)= 1^T dZ_l
+                                // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form); db_l / dlogstd = 1^T dZ_l are
+                                // summed by the workers (warp shuffles in the head phase), not by the tensor pipe
                                 t3_rows_product<P>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane, p.dzl_plane, CB,
                                                    tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
                                                    (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], 1);
@@ -401,25 +418,6 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                                 t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l], p.act_plane[l], sb + p.off_dzl,
                                                    p.dzl_plane, CB, T3_NO, 0, dw_ksteps, acc_started[l]);
                                 acc_started[l] = true;
-                                const TcView ones = t3_feat_mn(sb + p.off_act[l] + P * p.act_plane[l], CB);
-                                const TcView dzl = t3_feat_mn(sb + p.off_dzl, CB);
-                                const uint32_t dzp16 = (uint32_t)p.dzl_plane >> 4;
-                                uint32_t alo = ones.lo, blo = dzl.lo;
-#pragma unroll 1
-                                for (int kk = 0; kk < dw_ksteps; ++kk) {     // rows 0-7 of the result: column sums of the dZ planes
-                                    const uint32_t acc = (rb_started || kk > 0) ? 1u : 0u;
-                                    if (P == 1) {
-                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, T3_NO, 1, 1), acc);
-                                    } else if (P == 2) {
-                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, 2 * T3_NO, 1, 1), acc);
-                                    } else {
-                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo + dzp16, dzl.hi, tc_idesc(64, 2 * T3_NO, 1, 1), acc);
-                                        tc_mma(tm + p.col_rb, alo, ones.hi, blo, dzl.hi, tc_idesc(64, T3_NO, 1, 1), 1u);
-                                    }
-                                    alo += ones.k16;
-                                    blo += dzl.k16;
-                                }
-                                rb_started = true;
                                 tc_commit(dwb);
                             } else {
                                 // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
@@ -429,14 +427,16 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                                                        (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], p.img.np[l] / 16);
                                     tc_commit(full);
                                 }
-                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l + 1], p.act_plane[l + 1], sb + p.off_act[l],
-                                                   p.act_plane[l], CB, p.img.kp[l], 8, dw_ksteps, acc_started[l]);
+                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l + 1], p.act_plane[l + 1],
+                                                   sb + p.off_act[l] + (l == 0 ? xo : 0u), p.act_plane[l], CB, p.img.kp[l], 8, dw_ksteps,
+                                                   acc_started[l]);
                                 acc_started[l] = true;
                                 tc_commit(l == 0 ? full : dwb);  // l == 0 has no dA: its dW product is the phase
                             }
                         }
                     }
                     T3_MARK(200 + 10 * s + job);
+                    if (job == jobs - 1) ++tcount[s];
                     __syncwarp();
                 }
             }
@@ -450,7 +450,8 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
         }
     } else {
         // ---- worker warps -----------------------------------------------------------------------------------
-        const uint32_t full = tc_smem_u32(&s_full[slot]), dwb = tc_smem_u32(&s_dw[slot]), rdy = tc_smem_u32(&s_ready[slot]);
+        const uint32_t full = tc_smem_u32(&s_full[slot]), dwb = tc_smem_u32(&s_dw[slot]), rdy = tc_smem_u32(&s_ready[slot]),
+                       rdx = tc_smem_u32(&s_readyx[slot]);
         uint32_t par_full = 0u, par_dw = 0u;
         const uint32_t tlane = tm + ((uint32_t)(quarter * 32) << 16);
         const uint32_t za = tlane + p.col_za[slot];
@@ -486,8 +487,9 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                 recs[j] = v;
             }
         };
-        unsigned char *xbuf = sl + p.off_act[0];
-        auto stage = [&]() {                            // records -> X operand planes and head inputs
+        auto stage = [&](int buf) {                     // records -> X operand planes and head inputs of input buffer `buf`
+            unsigned char *xbuf = sl + p.off_act[0] + buf * p.x_stride;
+            float *sHin = sHin0 + buf * p.hin_stride;
 #pragma unroll
             for (int j = 0; j < T3_MAXLD; ++j) {
                 if (item_rq[j] < 0) continue;
@@ -554,22 +556,15 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                     if (lv && i < on) { float *q = dst + p.net.b_off[l] + i; *q = add ? *q + v[8] : v[8]; }
                 }
             }
-            if (cg4 == 2 && quarter == 0) {     // last layer: row 0 of the ones product = column sums of dZ
-                float v0[16], v1[16];
-                t3_ld16_nowait(tlane + p.col_rb, v0);
-                if (NB == 2) t3_ld16_nowait(tlane + p.col_rb + T3_NO, v1);
-                t3_ld_wait();
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float sv = NB == 2 ? v0[j] + v1[j] : v0[j];
-                        if (j < n_out) { float *q = dst + p.net.b_off[L - 1] + j; *q = add ? *q + sv : sv; }
-                        if (p.net.logstd_off >= 0 && j >= 8 && j < 8 + n_out) {
-                            float *q = dst + p.net.logstd_off + j - 8;
-                            *q = !gauss ? 0.0f : (add ? *q + sv : sv);
-                        }
-                    }
-                }
+            if (warp == 0 && lane < T3_NO) {    // last layer: column sums of dZ, gathered per warp in the head phases
+                // column j belongs to the warps whose column group is j / DPT (every slot, every lane quarter): fixed order
+                const int j = lane, cgj = j / DPT, kj = j - cgj * DPT;
+                float sv = 0.0f;
+                for (int w = 0; w < T3_NT / 32; ++w)
+                    if (((w % GW) >> 2) == cgj) sv += s_rb[w][kj];
+                // (s_rb holds running totals over all tiles of the CTA: written, not added)
+                if (j < n_out) dst[p.net.b_off[L - 1] + j] = sv;
+                if (p.net.logstd_off >= 0 && j >= 8 && j < 8 + n_out) dst[p.net.logstd_off + j - 8] = gauss ? sv : 0.0f;
             }
             flushed = true;
         };
@@ -577,17 +572,28 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
         fetch_idx(slot);
         load_recs();
         fetch_idx(slot + NS);
+        wait_and_fetch_image();
+        int tcount = 0;                                 // tiles this slot has started: selects the input buffer
+        bool staged = false;                            // this tile's input was staged (and announced) behind the previous tile
         for (int i0 = 0; i0 < n_i; i0 += T3_FLUSH_TILES) {
             const int i1 = i0 + T3_FLUSH_TILES < n_i ? i0 + T3_FLUSH_TILES : n_i;
             for (int ord = i0 + slot; ord < i1; ord += NS) {
                 const int64_t tile = (int64_t)bid + (int64_t)ord * gdim;
                 const int64_t gr = tile * tr + row;
                 const bool rvalid = row < tr && gr < n_rows;
-                if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
-                // ---- stage the input tile --------------------------------------------------------------------
+                // ---- stage the input tile (unless it already was: two input buffers) ---------------------------------
+                const int buf = p.x_bufs == 2 ? (tcount & 1) : 0;
+                const float *sHin = sHin0 + buf * p.hin_stride;
                 T3_MARK(10);
-                stage();
-                t3_warp_ready(rdy, lane);
+                if (!staged) {
+                    if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }     // dW_0 read the buffer
+                    stage(buf);
+                    t3_warp_ready(rdx, lane);
+                } else if (pending) {                   // (consume dW_0's phase of the barrier: at most one phase behind)
+                    tc_wait(full, par_full); par_full ^= 1u; pending = false;
+                }
+                staged = false;
+                ++tcount;
                 T3_MARK(11);
                 // ---- forward -----------------------------------------------------------------------------------
                 for (int l = 0; l < L - 1; ++l) {
@@ -610,6 +616,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                             t3_ld16_nowait(za + c0, v);
                             if (NB == 2) t3_ld16_nowait(za + T3_HID + c0, v2);
                             t3_ld_wait();
+                            T3_MARK(300 + l);
                             const float4 *b4 = reinterpret_cast<const float4 *>(sBias + l * 64 + c0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -620,8 +627,10 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                                 v[4 * j + 3] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 3] + v2[4 * j + 3] : v[4 * j + 3]) + bb.w, leak);
                             }
                             if (p.with_grad && p.col_save[slot] >= 0) t3_st16_nowait(tlane + p.col_save[slot] + l * T3_HID + c0, v);
+                            T3_MARK(310 + l);
                             t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8, row, v);
                             t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8 + 1, row, v + 8);
+                            T3_MARK(320 + l);
                         }
                         if (p.with_grad && p.col_save[slot] >= 0) t3_st_wait();
                     }
@@ -639,11 +648,20 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                         t3_ld16_nowait(za, y);
                         if (NB == 2) t3_ld16_nowait(za + T3_NO, y2);
                         t3_ld_wait();
+                        T3_MARK(330);
                         const float *b = sBias + (L - 1) * 64;
+                        if (lastact == MQ_ACT_NONE) {          // (the usual case, decided once: no per-element activation code)
 #pragma unroll
-                        for (int n = 0; n < T3_NO; ++n) {
-                            y[n] = (n < n_out) ? mq_act_apply((NB == 2 ? y[n] + y2[n] : y[n]) + b[n], lastact, lastleak) : 0.0f;
-                            dz[n] = 0.0f;
+                            for (int n = 0; n < T3_NO; ++n) {
+                                y[n] = (n < n_out) ? (NB == 2 ? y[n] + y2[n] : y[n]) + b[n] : 0.0f;
+                                dz[n] = 0.0f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int n = 0; n < T3_NO; ++n) {
+                                y[n] = (n < n_out) ? mq_act_apply((NB == 2 ? y[n] + y2[n] : y[n]) + b[n], lastact, lastleak) : 0.0f;
+                                dz[n] = 0.0f;
+                            }
                         }
                     }
                     float tgt[T3_NO];
@@ -732,6 +750,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                                 }
                         }
                     }
+                    T3_MARK(331);
                     if (p.with_grad) {
                         float sv[DPT];
 #pragma unroll
@@ -742,6 +761,14 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
 #pragma unroll
                                 for (int k = 0; k < DPT; ++k) sv[k] = dz[DPT * q + k];
                             }
+                        // db_{L-1} / dlogstd = column sums of dZ over the rows: this warp's 32 rows by shuffles, accumulated per
+                        // warp in shared memory in tile order (fixed order: bit-reproducible); invalid rows hold zeros
+#pragma unroll
+                        for (int k = 0; k < DPT; ++k) {
+                            const float cs = mq_warp_sum(sv[k]);
+                            if (lane == 0) s_rb[warp][k] += cs;
+                        }
+                        T3_MARK(332);
                         unsigned char *dbuf = sl + p.off_dzl;
                         if (DPT == 8) {
                             t3_store_chunk<P, CB>(dbuf, p.dzl_plane, cgi, row, sv);
@@ -759,6 +786,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     continue;
                 }
+                T3_MARK(333);
                 t3_warp_ready(rdy, lane);
                 T3_MARK(41);
                 // ---- backward ----------------------------------------------------------------------------------
@@ -809,6 +837,13 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                     T3_MARK(80 + l);
                 }
                 pending = true;                         // dW_0 is in flight
+                // two input buffers: the slot's next tile of this round is staged now, under dW_0 -- its F0 queues right
+                // behind dW_0 on the tensor pipe and nobody waits for dW_0 by itself
+                if (p.x_bufs == 2 && ord + NS < i1) {
+                    stage(tcount & 1);
+                    t3_warp_ready(rdx, lane);
+                    staged = true;
+                }
             }
             if (p.with_grad) {
                 if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
@@ -872,7 +907,8 @@ extern "C" int32_t mq_record_width(const mq_net_t *net) {
 }
 
 // one (ns = 1) or two (ns = 2) 128-row tile slots
-static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, int64_t sms, T3Plan *p) {
+static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, int x_bufs, int64_t sms,
+                       T3Plan *p) {
     const int rows = T3_ROWS;
     memset(p, 0, sizeof(*p));
     p->net = *net;
@@ -891,8 +927,11 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     p->dzl_plane = 2 * cb;
     p->off_dzl = off; off += planes * p->dzl_plane;
     p->act_plane[0] = (k0 / 8) * cb;
-    p->off_act[0] = off; off += planes * p->act_plane[0] + cb;
-    p->off_hin = off; off += rows * p->hin_w * 4;
+    p->x_bufs = x_bufs;
+    p->x_stride = planes * p->act_plane[0] + cb;
+    p->hin_stride = rows * p->hin_w;                          // floats
+    p->off_act[0] = off; off += x_bufs * p->x_stride;
+    p->off_hin = off; off += x_bufs * rows * p->hin_w * 4;
     off = (int)mq_round_up(off, 1024);
     for (int l = 1; l < L; ++l) {
         p->act_plane[l] = (T3_HID / 8) * cb;
@@ -912,7 +951,7 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     int col = 0;
     for (int s = 0; s < ns; ++s) { p->col_za[s] = col; col += nbk * T3_HID; }
     {   // fp32 copy of the hidden activations for the backward pass, when the columns are there
-        int acc_cols = nbk * T3_NO;
+        int acc_cols = 0;
         for (int l = 0; l < L; ++l) acc_cols += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8;
         const bool fits = with_grad && col + ns * (L - 1) * T3_HID + acc_cols <= 512;
         for (int s = 0; s < 2; ++s) p->col_save[s] = -1;
@@ -920,7 +959,6 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
             for (int s = 0; s < ns; ++s) { p->col_save[s] = col; col += (L - 1) * T3_HID; }
     }
     for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8; }
-    p->col_rb = col; col += nbk * T3_NO;
     if (col > 512) return 0;
     // balance: every tile slot of a full wave gets the same number of rows
     const int64_t waves = mq_ceil_div(batch, sms * ns * rows);
@@ -940,11 +978,14 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
 static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, int64_t sms, T3Plan *p,
                          int *ns_out) {
     const int planes = t3_planes(tc);
+    // preference: two slots; within a slot count, two input buffers (the next tile is staged under the current tile's last
+    // product) when shared memory allows
     for (int ns = 2; ns >= 1; --ns)
-        if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, sms, p)) {
-            *ns_out = ns;
-            return 1;
-        }
+        for (int xb = 2; xb >= 1; --xb)
+            if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, xb, sms, p)) {
+                *ns_out = ns;
+                return 1;
+            }
     return 0;
 }
 
