@@ -406,8 +406,8 @@ class PPOLargeWorkload(object):
         flops = mb * 28544.0                               # 28,544 FLOP per row (fwd+dW+dX)
         # tensor-core work actually issued: plane pairs i + j < planes per fp32 product (6 / 3 / 1), operands
         # padded to 16 / 64 columns, M = 128 rows per tile of `tile_rows` valid rows, the ones column for the bias sums
-        pairs = {3: 6, 2: 3, 1: 1}[planes]
-        slots = 148 * (1 if planes == 3 else 2)
+        pairs = {3: 6, 2: 3, 1: 1}[planes & 3]
+        slots = 148 * (1 if (planes & 3) == 3 else 2)
         waves = -(-mb // (slots * 128))
         tile_rows = min(128, max(16, -(-(-(-mb // (slots * waves))) // 16) * 16))
         tiles = -(-mb // tile_rows)
@@ -425,14 +425,14 @@ class PPOLargeWorkload(object):
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except (OSError, KeyError, ValueError):
             pass
-        return dict(bound="tensor", kernel="tc3_grad_kernel<planes=%d> (policy, %d rows, record-fed tcgen05, %s mode)"
-                                           % (planes, mb, self.tc_mode),
+        return dict(bound="tensor", kernel="tc3_grad_kernel<planes=%d%s> (policy, %d rows, record-fed tcgen05, %s mode)"
+                                           % (planes & 3, ", fp16 scaled" if planes & 0x80 else "", mb, self.tc_mode),
                     achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=traffic,
                     traffic_note="ncu dram__bytes_read+write of one 65,536-row launch (%s); algorithmic gather 4.2 MB + "
                                  "0.26 MB of indices + the operand image" % traffic_src,
                     peak_source=peaks["source"], ms_per_launch=ms, n_partials=n_parts, rows=mb, mode=self.tc_mode,
                     limiter="a 64-wide MLP is a chain of six dependent (product -> epilogue) phases per 128-row tile with "
-                            "K = 16..64: the epilogues (bias, tanh, split into bf16 planes, shared-memory stores: ~20 "
+                            "K = 16..64: the epilogues (bias, tanh, split into operand planes, shared-memory stores: ~20 "
                             "instructions per element) are instruction-issue bound and the tensor pipe waits for them; "
                             "neither HBM (64 B/row) nor the dense bf16 peak is the bound (DESIGN.md 3.1)",
                     executed_tensor_tflops=executed / (ms * 1e-3) / 1e12,
@@ -451,8 +451,8 @@ class PPOLargeWorkload(object):
         from mannequin2_b200.ppo import PPOUpdater
         from mannequin2_b200 import _lib as L
         out = {}
-        ref_grad = None
-        for mode in ("exact", "bf16x2", "bf16"):
+        grads = {}
+        for mode in ("fp16x2", "exact", "bf16x2", "bf16"):
             np.random.seed(0)
             upd = PPOUpdater(11, 3, tc_mode=mode)
             upd.check_indices = False
@@ -479,14 +479,15 @@ class PPOLargeWorkload(object):
             D.call("mq_fused_grad", C.byref(self.upd.policy.net), D.ptr(self.upd.policy.theta), D.ptr(self.dev[0][0]),
                    D.ptr(self.dev[0][5]), self.MB, C.byref(head), 1.0 / self.MB, D.ptr(g), None, None, D.ptr(ws), wsb, D.stream())
             g = g.double().cpu().numpy()
-            if ref_grad is None:
-                ref_grad = g
-            err = float(np.max(np.abs(g - ref_grad)) / np.max(np.abs(ref_grad)))
+            grads[mode] = g
             out[mode] = dict(value=self.N / (ms * 1e-3), unit=self.unit, ms_per_step=ms, grad_kernel_ms=kms,
-                             grad_err_vs_exact=err, stated_tolerance={"exact": "rtol 1e-5 (the FFMA bar)", "bf16x2": 3e-5,
-                                                                      "bf16": 1e-1}[mode],
-                             note="max |g - g_exact| / max |g_exact| of one 65,536-row policy gradient at the same parameters")
+                             stated_tolerance={"exact": "rtol 1e-5 (the FFMA bar)", "fp16x2": "rtol 1e-5 (the FFMA bar)",
+                                               "bf16x2": 3e-5, "bf16": 1e-1}[mode],
+                             note="grad_err_vs_exact = max |g - g_exact| / max |g_exact| of one 65,536-row policy gradient at "
+                                  "the same parameters (g_exact: the three-plane bf16 mode)")
             del upd
+        for mode in out:
+            out[mode]["grad_err_vs_exact"] = float(np.max(np.abs(grads[mode] - grads["exact"])) / np.max(np.abs(grads["exact"])))
         return out
 
     def parity_check(self, rows_per_rank=8192, epochs=1):
@@ -528,7 +529,7 @@ class PPOLargeWorkload(object):
                                                  o, a, r, d.astype(bool), vi, pi)
             e_pol = float(np.max(np.abs(D.to_host(upd.policy.theta) - want_pol)))
             e_val = float(np.max(np.abs(D.to_host(upd.value.theta) - want_val)))
-            frac = {"exact": 0.007, "bf16x2": 0.07, "bf16": 1.0}[self.tc_mode]
+            frac = {"exact": 0.007, "fp16x2": 0.007, "bf16x2": 0.07, "bf16": 1.0}[self.tc_mode]
             steps = len(vi)
             res.update(max_abs_err=max(e_pol, e_val), max_abs_err_policy=e_pol, max_abs_err_value=e_val,
                        tol_policy=frac * 3e-4 * (1 + steps), tol_value=frac * 3e-3 * (1 + steps),
@@ -1184,8 +1185,9 @@ def main():
     ap.add_argument("--workload", default="ppo_large", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / kernel sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tc-mode", default="exact", choices=["exact", "bf16x2", "bf16"],
-                    help="precision of the tensor-core gradient kernel of the headline workload (default: exact fp32 products)")
+    ap.add_argument("--tc-mode", default="fp16x2", choices=["fp16x2", "exact", "bf16x2", "bf16"],
+                    help="operand format of the tensor-core gradient kernel of the headline workload.  fp16x2 (default) and exact "
+                         "(three bf16 planes) both meet the fp32 parity bar (rtol 1e-5); bf16x2 / bf16 are the looser modes")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1270,6 +1272,9 @@ def main():
     if rank == 0:
         arith = {"exact": "fp32 results (parity rtol 1e-5): minibatch gradients >= 8,192 rows run on tcgen05 as 3 exact bf16 "
                           "planes per operand (6 plane pairs), fp32 accumulation in TMEM; the rest is fp32 FFMA",
+                 "fp16x2": "fp32 results (parity rtol 1e-5): minibatch gradients >= 8,192 rows run on tcgen05 as 2 fp16 planes per "
+                           "operand, the low plane scaled by 2^11 (x = x0 + 2^-11 x1 carries fp32 to 2^-24 for |x| < 65504; 3 plane "
+                           "pairs), fp32 accumulation in TMEM; the rest is fp32 FFMA",
                  "bf16x2": "minibatch gradients >= 8,192 rows on tcgen05 with 2 bf16 planes per operand (3 plane pairs; stated "
                            "tolerance 3e-5 max|grad|), fp32 accumulation; the rest is fp32 FFMA",
                  "bf16": "minibatch gradients >= 8,192 rows on tcgen05 with plain bf16 operands (stated tolerance 1e-1 "

@@ -94,8 +94,13 @@ typedef struct mq_head {
  *   3 planes (default): exact fp32 products, 6 pairs            -- same bar as the FFMA kernels (rtol 1e-5)
  *   2 planes: 16 mantissa bits per operand, 3 pairs             -- |err| <= 3e-5 max|grad|
  *   1 plane : plain bf16 operands, 1 pair, MUFU tanh            -- |err| <= 2e-2 max|grad|
+ * MQ_TC_FP16 with 2 planes selects fp16 planes with the low one scaled by 2^11 (x = x0 + 2^-11 x1): 22 significant
+ * bits and a sign, i.e. fp32 operands to 2^-24, in THREE pairs -- the exact mode's bar (rtol 1e-5) at the two-plane
+ * cost.  Precondition: |operand| < 65504 (inputs, weights, activations, output-layer gradients); beyond it the planes
+ * are +-inf and the gradient comes back non-finite (never silently wrong).
  * The tolerances are the ones tests/kernel_cases.py: case_tc_modes asserts. */
 #define MQ_TC_PLANES_MASK 0x3   /* 0 = default (3) */
+#define MQ_TC_FP16        0x80  /* with 2 planes: fp16 planes, scaled low plane ("fp16x2")                         */
 #define MQ_TC_FORCE       0x10  /* use the tensor-core kernel whenever the net fits (default: batch >= 8192) */
 #define MQ_TC_OFF         0x20  /* never use it (FFMA kernels)                                                */
 #define MQ_TC_NOPIPE      0x40  /* developer aid (A/B measurements): no K-chunk pipelining between layers          */

@@ -191,7 +191,7 @@ static int step_job_fill(const mq_step_t *t, StepJob<ST> *j) {
     }
     if (t->image) {
         const int planes = (t->tc & MQ_TC_PLANES_MASK) ? (t->tc & MQ_TC_PLANES_MASK) : 3;
-        MQ_REQUIRE(t->net && t->net->n_params == t->n && t3_img_build_layout(t->net, planes, &j->img), MQ_ERR_INVALID,
+        MQ_REQUIRE(t->net && t->net->n_params == t->n && t3_img_build_layout(t->net, planes, (t->tc & MQ_TC_FP16) ? 1 : 0, &j->img), MQ_ERR_INVALID,
                    "mq_reduce_step: the net does not match the parameter vector or does not fit the tensor-core kernel");
     }
     j->partial = t->partials; j->n_parts = t->n_parts; j->n = (int)t->n; j->scale = t->scale;

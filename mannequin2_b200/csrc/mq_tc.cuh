@@ -20,6 +20,12 @@ __device__ __forceinline__ uint32_t tc_idesc(int m, int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// the same with fp16 operands (A / B format 0) when half != 0
+__device__ __forceinline__ uint32_t tc_idesc_fmt(int m, int n, int a_mn, int b_mn, int half) {
+    const uint32_t ab = half ? 0u : ((1u << 7) | (1u << 10));
+    return (1u << 4) | ab | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 __device__ __forceinline__ bool tc_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

@@ -117,8 +117,16 @@ __device__ __forceinline__ float t3_tanh_fast(float x) {
 
 // ---- plane arithmetic ----------------------------------------------------------------------------------------
 // two values -> P words of packed bf16 pairs (low half = a), w[0] + w[1] + .. = the values (exact for P = 3)
-template <int P>
+template <int P, int F>
 __device__ __forceinline__ void t3_split_pair(float a, float b, uint32_t *w) {
+    if (F == 1) {                                       // fp16 planes, the low one scaled by 2^11 (mq_tc3.cuh)
+        const __half2 h0 = __floats2half2_rn(a, b);
+        const float2 f0 = __half22float2(h0);
+        const __half2 h1 = __floats2half2_rn((a - f0.x) * T3_LOW_SCALE, (b - f0.y) * T3_LOW_SCALE);
+        w[0] = *reinterpret_cast<const uint32_t *>(&h0);
+        w[1] = *reinterpret_cast<const uint32_t *>(&h1);
+        return;
+    }
 #pragma unroll
     for (int pl = 0; pl < P; ++pl) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -137,11 +145,11 @@ __device__ __forceinline__ unsigned char *t3_chunk_ptr(unsigned char *buf, int p
 }
 
 // 8 consecutive features of one row -> one 16-byte chunk in each plane
-template <int P, int CB>
+template <int P, int F, int CB>
 __device__ __forceinline__ void t3_store_chunk(unsigned char *buf, int plane_bytes, int chunk, int row, const float *v) {
     uint32_t w[4][P];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t3_split_pair<P>(v[2 * j], v[2 * j + 1], w[j]);
+    for (int j = 0; j < 4; ++j) t3_split_pair<P, F>(v[2 * j], v[2 * j + 1], w[j]);
     unsigned char *q = t3_chunk_ptr<P, CB>(buf, plane_bytes, chunk, row);
 #pragma unroll
     for (int pl = 0; pl < P; ++pl)
@@ -149,12 +157,24 @@ __device__ __forceinline__ void t3_store_chunk(unsigned char *buf, int plane_byt
 }
 
 // the value the planes represent (exact fp32 for P = 3, the rounded operand otherwise)
-template <int P, int CB>
+template <int P, int F, int CB>
 __device__ __forceinline__ void t3_load_chunk(unsigned char *buf, int plane_bytes, int chunk, int row, float *v) {
     const unsigned char *q = t3_chunk_ptr<P, CB>(buf, plane_bytes, chunk, row);
     uint4 w[P];
 #pragma unroll
     for (int pl = 0; pl < P; ++pl) w[pl] = *reinterpret_cast<const uint4 *>(q - pl * plane_bytes);
+    if (F == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x0 = j == 0 ? w[0].x : (j == 1 ? w[0].y : (j == 2 ? w[0].z : w[0].w));
+            const uint32_t x1 = j == 0 ? w[P - 1].x : (j == 1 ? w[P - 1].y : (j == 2 ? w[P - 1].z : w[P - 1].w));
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&x0));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&x1));
+            v[2 * j] = fmaf(f1.x, T3_LOW_UNSCALE, f0.x);
+            v[2 * j + 1] = fmaf(f1.y, T3_LOW_UNSCALE, f0.y);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float lo = 0.0f, hi = 0.0f;
@@ -169,11 +189,11 @@ __device__ __forceinline__ void t3_load_chunk(unsigned char *buf, int plane_byte
     }
 }
 
-template <int P, int ACT>
+template <int P, int F, int ACT>
 __device__ __forceinline__ float t3_act(float z, float leak) {
     if (ACT == MQ_ACT_TANH) {
         if (P == 1) return t3_tanh_fast(z);             // MUFU.TANH: 2^-11, the size of a bf16 rounding
-        if (P == 2) {                                   // 1 - 2 / (2^(2 log2(e) |z|) + 1): ~1.2e-7 ABSOLUTE (no small-|z| branch),
+        if (P == 2 && F == 0) {                                   // 1 - 2 / (2^(2 log2(e) |z|) + 1): ~1.2e-7 ABSOLUTE (no small-|z| branch),
             float t, r;                                 // well inside the 16-bit operands of this mode
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.8853900817779268f));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
@@ -182,6 +202,13 @@ __device__ __forceinline__ float t3_act(float z, float leak) {
         return tc_tanh(z);
     }
     return z < 0.0f ? z * leak : z;
+}
+
+// the value of an accumulator spread over NB column blocks: block 0 (+ block 1, scaled back for the fp16 format)
+template <int NB, int F>
+__device__ __forceinline__ float t3_blocks(float b0, float b1) {
+    if (NB == 1) return b0;
+    return F == 1 ? fmaf(b1, T3_LOW_UNSCALE, b0) : b0 + b1;
 }
 
 // ---- MMA issue helpers (elected lane of the issuer warp, warp-uniform control flow) ---------------------------------
@@ -196,13 +223,14 @@ __device__ __forceinline__ TcView t3_feat_mn(uint32_t addr, uint32_t cb) {
 
 // D[128 x (NB blocks of nb)] = sum over plane pairs i + j < P of A_i B_j.  A: row-major planes (plane 0 at a0_addr, plane i
 // i * a_plane bytes BELOW it); B: an image whose planes 0, 1, .. sit side by side along N (b_plane16 = stride >> 4).
-template <int P>
+// F = 1 (fp16, scaled low planes): column block 0 = A_0 B_0, block 1 = A_0 B_1' + A_1' B_0 (to be scaled by 2^-11).
+template <int P, int F>
 __device__ __forceinline__ void t3_rows_product(uint32_t d_tmem, uint32_t a0_addr, uint32_t a_plane, uint32_t cb, const TcView &b,
                                                 int b_mn, uint32_t b_plane16, int nb, int ksteps) {
     const TcView a0 = t3_rows_k(a0_addr, cb);
     const uint32_t ap16 = a_plane >> 4;
-    const uint32_t id2 = tc_idesc(T3_ROWS, 2 * nb, 0, b_mn);
-    const uint32_t id1 = tc_idesc(T3_ROWS, nb, 0, b_mn);
+    const uint32_t id2 = tc_idesc_fmt(T3_ROWS, 2 * nb, 0, b_mn, F);
+    const uint32_t id1 = tc_idesc_fmt(T3_ROWS, nb, 0, b_mn, F);
     uint32_t alo = a0.lo, blo = b.lo;
 #pragma unroll 1
     for (int k = 0; k < ksteps; ++k) {
@@ -211,7 +239,7 @@ __device__ __forceinline__ void t3_rows_product(uint32_t d_tmem, uint32_t a0_add
             tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id1, acc);                              // A_0 x B_0
         } else if (P == 2) {
             tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id2, acc);                              // A_0 x [B_0|B_1]
-            tc_mma(d_tmem, alo - ap16, a0.hi, blo, b.hi, id1, 1u);                        // A_1 x B_0
+            tc_mma(d_tmem + (F == 1 ? nb : 0), alo - ap16, a0.hi, blo, b.hi, id1, 1u);    // A_1 x B_0
         } else {
             tc_mma(d_tmem, alo, a0.hi, blo, b.hi, id2, acc);                              // A_0 x [B_0|B_1]
             tc_mma(d_tmem, alo - ap16, a0.hi, blo, b.hi, id2, 1u);                        // A_1 x [B_0|B_1]
@@ -226,18 +254,24 @@ __device__ __forceinline__ void t3_rows_product(uint32_t d_tmem, uint32_t a0_add
 // acc[64 x (NB blocks of nb, + extra)] (+)= sum over plane pairs of Da_i^T Db_j over the rows of the tile.  Da, Db:
 // activation buffers (planes P-1 .. 0 in memory, buffer start at *_base); Da's features are M, Db's planes side by side
 // (+ `extra` columns behind plane 0: the ones chunk) are N.  Column blocks for P >= 2: [Db_1 | Db_0 | extra].
-template <int P>
+// F = 1: block [0, nb) = Da_0 Db_1' + Da_1' Db_0 (scaled), [nb, 2 nb) = Da_0 Db_0, [2 nb, +8) = Da_0 e, [2 nb + 8, +8) = Da_1' e.
+template <int P, int F>
 __device__ __forceinline__ void t3_feat_product(uint32_t acc_tmem, uint32_t da_base, uint32_t da_plane, uint32_t db_base,
                                                 uint32_t db_plane, uint32_t cb, int nb, int extra, int ksteps, bool accumulate) {
     const TcView a = t3_feat_mn(da_base, cb), b = t3_feat_mn(db_base, cb);
     const uint32_t ap16 = da_plane >> 4, bp16 = db_plane >> 4;
-    const uint32_t id_all = tc_idesc(64, 2 * nb + extra, 1, 1), id_one = tc_idesc(64, nb + extra, 1, 1), id_blk = tc_idesc(64, nb, 1, 1);
+    const uint32_t id_all = tc_idesc_fmt(64, 2 * nb + extra, 1, 1, F), id_one = tc_idesc_fmt(64, nb + extra, 1, 1, F),
+                   id_blk = tc_idesc_fmt(64, nb, 1, 1, F), id_ex = tc_idesc_fmt(64, 8, 1, 1, F);
     uint32_t alo = a.lo, blo = b.lo;
 #pragma unroll 1
     for (int k = 0; k < ksteps; ++k) {
         const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
         if (P == 1) {
             tc_mma(acc_tmem, alo, a.hi, blo, b.hi, id_one, acc);                                        // Da_0 x [Db_0|e]
+        } else if (P == 2 && F == 1) {
+            tc_mma(acc_tmem, alo + ap16, a.hi, blo, b.hi, id_all, acc);                                 // Da_0 x [Db_1'|Db_0|e]
+            tc_mma(acc_tmem, alo, a.hi, blo + bp16, b.hi, id_blk, 1u);                                  // Da_1' x Db_0
+            if (extra) tc_mma(acc_tmem + 2 * nb + 8, alo, a.hi, blo + 2 * bp16, b.hi, id_ex, acc);      // Da_1' x e
         } else if (P == 2) {
             tc_mma(acc_tmem, alo + ap16, a.hi, blo, b.hi, id_all, acc);                                 // Da_0 x [Db_1|Db_0|e]
             tc_mma(acc_tmem + nb, alo, a.hi, blo + bp16, b.hi, id_one, 1u);                             // Da_1 x [Db_0|e]
@@ -259,7 +293,7 @@ __device__ __forceinline__ TcView t3_wf_k(uint32_t addr, int np) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
-template <int P, int NS, int K0, int HACT>
+template <int P, int F, int NS, int K0, int HACT>
 __global__ void __launch_bounds__(T3_NTI, 1)
 tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
     const bool second = blockIdx.x >= (unsigned)launch.job[0].grid;
@@ -331,8 +365,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
     }
     __syncthreads();
     if (worker) {
-        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
-        const uint32_t ob = *reinterpret_cast<const uint16_t *>(&one);
+        const uint32_t ob = F == 1 ? 0x3C00u : 0x3F80u;                // 1.0 as fp16 / bf16
         for (int s = 0; s < NS; ++s)
             for (int l = 0; l < L; ++l)
                 for (int xb = 0; xb < (l == 0 ? p.x_bufs : 1); ++xb) {
@@ -402,7 +435,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                     if (tc_elect_one()) {
                         if (job < L) {
                             const int l = job;
-                            t3_rows_product<P>(za, sb + p.off_act[l] + (l == 0 ? xo : 0u) + (P - 1) * p.act_plane[l], p.act_plane[l], CB,
+                            t3_rows_product<P, F>(za, sb + p.off_act[l] + (l == 0 ? xo : 0u) + (P - 1) * p.act_plane[l], p.act_plane[l], CB,
                                                t3_wf_k<P>(sbase + p.off_const + p.img.off_wf[l], p.img.np[l]), 0, (uint32_t)p.img.np[l],
                                                p.img.np[l], p.img.kp[l] / 16);
                             tc_commit(full);
@@ -411,23 +444,23 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                             if (l == L - 1) {
                                 // dA_l = dZ_l W_l^T (K = 16 outputs), dW_l (+)= A_l^T dZ_l (direct form); db_l / dlogstd = 1^T dZ_l are
                                 // summed by the workers (warp shuffles in the head phase), not by the tensor pipe
-                                t3_rows_product<P>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane, p.dzl_plane, CB,
+                                t3_rows_product<P, F>(za, sb + p.off_dzl + (P - 1) * p.dzl_plane, p.dzl_plane, CB,
                                                    tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
                                                    (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], 1);
                                 tc_commit(full);             // dA alone: the epilogue's arithmetic runs under the dW products
-                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l], p.act_plane[l], sb + p.off_dzl,
+                                t3_feat_product<P, F>(tm + p.col_acc[l], sb + p.off_act[l], p.act_plane[l], sb + p.off_dzl,
                                                    p.dzl_plane, CB, T3_NO, 0, dw_ksteps, acc_started[l]);
                                 acc_started[l] = true;
                                 tc_commit(dwb);
                             } else {
                                 // dZ_l sits in act[l+1].  dA_l = dZ_l W_l^T (l > 0); dW_l^T, db_l (+)= dZ_l^T [A_l | 1]
                                 if (l > 0) {
-                                    t3_rows_product<P>(za, sb + p.off_act[l + 1] + (P - 1) * p.act_plane[l + 1], p.act_plane[l + 1], CB,
+                                    t3_rows_product<P, F>(za, sb + p.off_act[l + 1] + (P - 1) * p.act_plane[l + 1], p.act_plane[l + 1], CB,
                                                        tc_wb_mn(sbase + p.off_const + p.img.off_wb[l], p.img.np[l]), 1,
                                                        (uint32_t)p.img.wb_plane[l] >> 4, p.img.kp[l], p.img.np[l] / 16);
                                     tc_commit(full);
                                 }
-                                t3_feat_product<P>(tm + p.col_acc[l], sb + p.off_act[l + 1], p.act_plane[l + 1],
+                                t3_feat_product<P, F>(tm + p.col_acc[l], sb + p.off_act[l + 1], p.act_plane[l + 1],
                                                    sb + p.off_act[l] + (l == 0 ? xo : 0u), p.act_plane[l], CB, p.img.kp[l], 8, dw_ksteps,
                                                    acc_started[l]);
                                 acc_started[l] = true;
@@ -497,8 +530,8 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                 const float v[4] = {recs[j].x, recs[j].y, recs[j].z, recs[j].w};
                 if (e0 + 3 < n_in) {
                     uint32_t w0[P], w1[P];
-                    t3_split_pair<P>(v[0], v[1], w0);
-                    t3_split_pair<P>(v[2], v[3], w1);
+                    t3_split_pair<P, F>(v[0], v[1], w0);
+                    t3_split_pair<P, F>(v[2], v[3], w1);
                     unsigned char *d = t3_chunk_ptr<P, CB>(xbuf, p.act_plane[0], e0 >> 3, r) + (e0 & 7) * 2;
 #pragma unroll
                     for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2 *>(d - pl * p.act_plane[0]) = make_uint2(w0[pl], w1[pl]);
@@ -508,7 +541,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                         const int f = e0 + e;
                         if (f < n_in) {
                             uint32_t w[P];
-                            t3_split_pair<P>(v[e], 0.0f, w);
+                            t3_split_pair<P, F>(v[e], 0.0f, w);
                             unsigned char *d = t3_chunk_ptr<P, CB>(xbuf, p.act_plane[0], f >> 3, r) + (f & 7) * 2;
 #pragma unroll
                             for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint16_t *>(d - pl * p.act_plane[0]) = (uint16_t)(w[pl] & 0xFFFFu);
@@ -545,15 +578,16 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                         const bool ok = (l < L - 1) ? (i < on && c0 + j < in) : (i < in && c0 + j < on);
                         if (!ok) continue;
                         float *q = dst + p.net.w_off[l] + ((l < L - 1) ? (c0 + j) * on + i : i * on + c0 + j);
-                        const float val = NB == 2 ? v0[j] + v1[j] : v0[j];
+                        const float val = NB == 2 ? t3_blocks<NB, F>(v1[j], v0[j]) : v0[j];    // (fp16 format: block 0 is the scaled one)
                         *q = add ? *q + val : val;
                     }
                 }
-                if (l < L - 1 && cg4 == 1) {    // the ones column behind the blocks
+                if (l < L - 1 && cg4 == 1) {    // the ones column(s) behind the blocks
                     float v[16];
-                    t3_ld16_nowait(tlane + p.col_acc[l] + NB * nb - 8, v);
+                    t3_ld16_nowait(tlane + p.col_acc[l] + NB * nb - (F == 1 ? 0 : 8), v);
                     t3_ld_wait();
-                    if (lv && i < on) { float *q = dst + p.net.b_off[l] + i; *q = add ? *q + v[8] : v[8]; }
+                    const float bsum = F == 1 ? fmaf(v[8], T3_LOW_UNSCALE, v[0]) : v[8];
+                    if (lv && i < on) { float *q = dst + p.net.b_off[l] + i; *q = add ? *q + bsum : bsum; }
                 }
             }
             if (warp == 0 && lane < T3_NO) {    // last layer: column sums of dZ, gathered per warp in the head phases
@@ -621,15 +655,15 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 bb = b4[j];
-                                v[4 * j + 0] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 0] + v2[4 * j + 0] : v[4 * j + 0]) + bb.x, leak);
-                                v[4 * j + 1] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 1] + v2[4 * j + 1] : v[4 * j + 1]) + bb.y, leak);
-                                v[4 * j + 2] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 2] + v2[4 * j + 2] : v[4 * j + 2]) + bb.z, leak);
-                                v[4 * j + 3] = t3_act<P, HACT>((NB == 2 ? v[4 * j + 3] + v2[4 * j + 3] : v[4 * j + 3]) + bb.w, leak);
+                                v[4 * j + 0] = t3_act<P, F, HACT>(t3_blocks<NB, F>(v[4 * j + 0], v2[4 * j + 0]) + bb.x, leak);
+                                v[4 * j + 1] = t3_act<P, F, HACT>(t3_blocks<NB, F>(v[4 * j + 1], v2[4 * j + 1]) + bb.y, leak);
+                                v[4 * j + 2] = t3_act<P, F, HACT>(t3_blocks<NB, F>(v[4 * j + 2], v2[4 * j + 2]) + bb.z, leak);
+                                v[4 * j + 3] = t3_act<P, F, HACT>(t3_blocks<NB, F>(v[4 * j + 3], v2[4 * j + 3]) + bb.w, leak);
                             }
                             if (p.with_grad && p.col_save[slot] >= 0) t3_st16_nowait(tlane + p.col_save[slot] + l * T3_HID + c0, v);
                             T3_MARK(310 + l);
-                            t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8, row, v);
-                            t3_store_chunk<P, CB>(abuf, p.act_plane[l + 1], c0 / 8 + 1, row, v + 8);
+                            t3_store_chunk<P, F, CB>(abuf, p.act_plane[l + 1], c0 / 8, row, v);
+                            t3_store_chunk<P, F, CB>(abuf, p.act_plane[l + 1], c0 / 8 + 1, row, v + 8);
                             T3_MARK(320 + l);
                         }
                         if (p.with_grad && p.col_save[slot] >= 0) t3_st_wait();
@@ -653,13 +687,13 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                         if (lastact == MQ_ACT_NONE) {          // (the usual case, decided once: no per-element activation code)
 #pragma unroll
                             for (int n = 0; n < T3_NO; ++n) {
-                                y[n] = (n < n_out) ? (NB == 2 ? y[n] + y2[n] : y[n]) + b[n] : 0.0f;
+                                y[n] = (n < n_out) ? t3_blocks<NB, F>(y[n], y2[n]) + b[n] : 0.0f;
                                 dz[n] = 0.0f;
                             }
                         } else {
 #pragma unroll
                             for (int n = 0; n < T3_NO; ++n) {
-                                y[n] = (n < n_out) ? mq_act_apply((NB == 2 ? y[n] + y2[n] : y[n]) + b[n], lastact, lastleak) : 0.0f;
+                                y[n] = (n < n_out) ? mq_act_apply(t3_blocks<NB, F>(y[n], y2[n]) + b[n], lastact, lastleak) : 0.0f;
                                 dz[n] = 0.0f;
                             }
                         }
@@ -771,11 +805,11 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                         T3_MARK(332);
                         unsigned char *dbuf = sl + p.off_dzl;
                         if (DPT == 8) {
-                            t3_store_chunk<P, CB>(dbuf, p.dzl_plane, cgi, row, sv);
+                            t3_store_chunk<P, F, CB>(dbuf, p.dzl_plane, cgi, row, sv);
                         } else {
                             uint32_t wa[P], wb[P];
-                            t3_split_pair<P>(sv[0], sv[1], wa);
-                            t3_split_pair<P>(sv[2], sv[3], wb);
+                            t3_split_pair<P, F>(sv[0], sv[1], wa);
+                            t3_split_pair<P, F>(sv[2], sv[3], wb);
                             unsigned char *d = t3_chunk_ptr<P, CB>(dbuf, p.dzl_plane, cgi >> 1, row) + (cgi & 1) * 8;
 #pragma unroll
                             for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2 *>(d - pl * p.dzl_plane) = make_uint2(wa[pl], wb[pl]);
@@ -809,16 +843,16 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                             if (p.col_save[slot] >= 0) {
                                 t3_ld16_nowait(tlane + p.col_save[slot] + (l - 1) * T3_HID + c0, a);
                             } else {
-                                t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8, row, a);
-                                t3_load_chunk<P, CB>(abuf, p.act_plane[l], c0 / 8 + 1, row, a + 8);
+                                t3_load_chunk<P, F, CB>(abuf, p.act_plane[l], c0 / 8, row, a);
+                                t3_load_chunk<P, F, CB>(abuf, p.act_plane[l], c0 / 8 + 1, row, a + 8);
                             }
                             t3_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], NB == 2 ? g[j] + g2[j] : g[j], HACT, leak);
+                            for (int j = 0; j < 16; ++j) g[j] = mq_act_grad(a[j], t3_blocks<NB, F>(g[j], g2[j]), HACT, leak);
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) t3_split_pair<P>(g[8 * c + 2 * j], g[8 * c + 2 * j + 1], w[2 * h + c][j]);
+                                for (int j = 0; j < 4; ++j) t3_split_pair<P, F>(g[8 * c + 2 * j], g[8 * c + 2 * j + 1], w[2 * h + c][j]);
                         }
                     }
                     T3_MARK(60 + l);
@@ -900,6 +934,7 @@ pack_records_kernel(const float *__restrict__ x, const float *__restrict__ tgt, 
 // ---- host side ----------------------------------------------------------------------------------------------------
 long long *mq_phase_prof_ptr();
 static int t3_planes(int32_t tc) { const int pl = tc & MQ_TC_PLANES_MASK; return pl == 0 ? 3 : pl; }
+static int t3_fmt(int32_t tc) { return (tc & MQ_TC_FP16) ? 1 : 0; }
 
 extern "C" int32_t mq_record_width(const mq_net_t *net) {
     if (!net) return 0;
@@ -907,12 +942,12 @@ extern "C" int32_t mq_record_width(const mq_net_t *net) {
 }
 
 // one (ns = 1) or two (ns = 2) 128-row tile slots
-static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int rec_w, int ns, int x_bufs, int64_t sms,
-                       T3Plan *p) {
+static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int planes, int fmt, int rec_w, int ns, int x_bufs,
+                       int64_t sms, T3Plan *p) {
     const int rows = T3_ROWS;
     memset(p, 0, sizeof(*p));
     p->net = *net;
-    if (!t3_img_build_layout(net, planes, &p->img)) return 0;
+    if (!t3_img_build_layout(net, planes, fmt, &p->img)) return 0;
     const int L = net->n_layers, k0 = p->img.k0;
     const int cb = rows * 16;
     p->L = L;
@@ -940,25 +975,22 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
     p->slot_bytes = (int)mq_round_up(off, 1024);
     const int64_t limit = mq_smem_optin() - 256;         // static shared memory: TMEM address + seven mbarriers
     p->off_const = ns * p->slot_bytes;
-    // the ones-row product of the last layer reads 8 chunks from the ones chunk of act[L-1] of the last slot on
-    int total = p->off_const + p->img.bytes;
-    const int need = (ns - 1) * p->slot_bytes + p->off_act[L - 1] + planes * p->act_plane[L - 1] + 8 * cb;
-    if (total < need) total = need;
-    p->smem_bytes = (int)mq_round_up(total, 16);
+    p->smem_bytes = (int)mq_round_up(p->off_const + p->img.bytes, 16);
     if (p->smem_bytes > limit) return 0;
     // TMEM columns: Z / dA of each slot (NB blocks of 64), then the shared dW / db accumulators
     const int nbk = planes > 1 ? 2 : 1;
+    const int ones_cols = fmt == 1 ? 16 : 8;              // bias-gradient columns behind the dW blocks (fp16: main + scaled)
     int col = 0;
     for (int s = 0; s < ns; ++s) { p->col_za[s] = col; col += nbk * T3_HID; }
     {   // fp32 copy of the hidden activations for the backward pass, when the columns are there
         int acc_cols = 0;
-        for (int l = 0; l < L; ++l) acc_cols += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8;
+        for (int l = 0; l < L; ++l) acc_cols += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + ones_cols;
         const bool fits = with_grad && col + ns * (L - 1) * T3_HID + acc_cols <= 512;
         for (int s = 0; s < 2; ++s) p->col_save[s] = -1;
         if (fits)
             for (int s = 0; s < ns; ++s) { p->col_save[s] = col; col += (L - 1) * T3_HID; }
     }
-    for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + 8; }
+    for (int l = 0; l < L; ++l) { p->col_acc[l] = col; col += (l == L - 1) ? nbk * T3_NO : nbk * p->img.kp[l] + ones_cols; }
     if (col > 512) return 0;
     // balance: every tile slot of a full wave gets the same number of rows
     const int64_t waves = mq_ceil_div(batch, sms * ns * rows);
@@ -977,21 +1009,26 @@ static int t3_plan_try(const mq_net_t *net, int64_t batch, int with_grad, int pl
 // they hide per tile).
 static int t3_plan_build(const mq_net_t *net, int64_t batch, int with_grad, int32_t tc, int rec_w, int64_t sms, T3Plan *p,
                          int *ns_out) {
-    const int planes = t3_planes(tc);
+    const int planes = t3_planes(tc), fmt = t3_fmt(tc);
     // preference: two slots; within a slot count, two input buffers (the next tile is staged under the current tile's last
     // product) when shared memory allows
-    for (int ns = 2; ns >= 1; --ns)
+    // A batch of at most one 128-row tile per SM gains nothing from a second slot (there is no second tile to overlap with)
+    // and would split its tile into two half-filled ones: one slot, all 16 warps on the tile's epilogues.
+    const bool single_wave = mq_ceil_div(batch, T3_ROWS) <= sms;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ns = (pass == 0) == single_wave ? 1 : 2;
         for (int xb = 2; xb >= 1; --xb)
-            if (t3_plan_try(net, batch, with_grad, planes, rec_w, ns, xb, sms, p)) {
+            if (t3_plan_try(net, batch, with_grad, planes, fmt, rec_w, ns, xb, sms, p)) {
                 *ns_out = ns;
                 return 1;
             }
+    }
     return 0;
 }
 
 extern "C" int64_t mq_tc_image_bytes(const mq_net_t *net, int32_t tc) {
     T3Img g;
-    if (!net || !t3_img_build_layout(net, t3_planes(tc), &g)) return 0;
+    if (!net || !t3_img_build_layout(net, t3_planes(tc), t3_fmt(tc), &g)) return 0;
     return g.bytes;
 }
 
@@ -1007,7 +1044,8 @@ extern "C" int mq_tc_image_build(const mq_net_t *net, const float *theta, int32_
     MQ_REQUIRE(net && theta && image, MQ_ERR_INVALID, "mq_tc_image_build: null pointer");
     MQ_REQUIRE(((uintptr_t)image & 15) == 0, MQ_ERR_INVALID, "mq_tc_image_build: image must be 16-byte aligned");
     T3Img g;
-    MQ_REQUIRE(t3_img_build_layout(net, t3_planes(tc), &g), MQ_ERR_UNSUPPORTED, "mq_tc_image_build: net does not fit the tensor-core kernel");
+    MQ_REQUIRE(t3_img_build_layout(net, t3_planes(tc), t3_fmt(tc), &g), MQ_ERR_UNSUPPORTED,
+               "mq_tc_image_build: net does not fit the tensor-core kernel (or MQ_TC_FP16 without two planes)");
     return t3_image_build(g, theta, image, stream);
 }
 
@@ -1054,29 +1092,31 @@ static int t3_job_build(const mq_net_t *net, const int32_t *row_idx, int64_t bat
     return MQ_OK;
 }
 
-static int t3_launch_jobs(const T3Jobs &jobs, int total_grid, int planes, int ns, int k0, int act, int smem_bytes, void *stream) {
+static int t3_launch_jobs(const T3Jobs &jobs, int total_grid, int planes, int fmt, int ns, int k0, int act, int smem_bytes,
+                          void *stream) {
     cudaError_t e = cudaSuccess;
-#define T3_LAUNCH(P_, NS_, K0_, ACT_)                                                                                       \
+#define T3_LAUNCH(P_, F_, NS_, K0_, ACT_)                                                                                   \
     do {                                                                                                                    \
-        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+        e = cudaFuncSetAttribute(tc3_grad_kernel<P_, F_, NS_, K0_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
         if (e == cudaSuccess)                                                                                               \
-            e = mq_launch_pdl(tc3_grad_kernel<P_, NS_, K0_, ACT_>, dim3(total_grid), dim3(T3_NTI), (size_t)smem_bytes, stream, \
+            e = mq_launch_pdl(tc3_grad_kernel<P_, F_, NS_, K0_, ACT_>, dim3(total_grid), dim3(T3_NTI), (size_t)smem_bytes, stream, \
                               jobs, mq_phase_prof_ptr());                                                                   \
     } while (0)
-#define T3_LAUNCH_ACT(P_, NS_, K0_)                                      \
+#define T3_LAUNCH_ACT(P_, F_, NS_, K0_)                                      \
+    do {                                                                     \
+        if (act == MQ_ACT_TANH) T3_LAUNCH(P_, F_, NS_, K0_, MQ_ACT_TANH);    \
+        else T3_LAUNCH(P_, F_, NS_, K0_, MQ_ACT_LRELU);                      \
+    } while (0)
+#define T3_LAUNCH_P(P_, F_)                                              \
     do {                                                                 \
-        if (act == MQ_ACT_TANH) T3_LAUNCH(P_, NS_, K0_, MQ_ACT_TANH);    \
-        else T3_LAUNCH(P_, NS_, K0_, MQ_ACT_LRELU);                      \
+        if (ns == 2) T3_LAUNCH_ACT(P_, F_, 2, 16);                       \
+        else if (k0 == 16) T3_LAUNCH_ACT(P_, F_, 1, 16);                 \
+        else T3_LAUNCH_ACT(P_, F_, 1, 32);                               \
     } while (0)
-#define T3_LAUNCH_P(P_)                                              \
-    do {                                                             \
-        if (ns == 2) T3_LAUNCH_ACT(P_, 2, 16);                       \
-        else if (k0 == 16) T3_LAUNCH_ACT(P_, 1, 16);                 \
-        else T3_LAUNCH_ACT(P_, 1, 32);                               \
-    } while (0)
-    if (planes == 3) { if (k0 == 16) T3_LAUNCH_ACT(3, 1, 16); else T3_LAUNCH_ACT(3, 1, 32); }
-    else if (planes == 2) T3_LAUNCH_P(2);
-    else T3_LAUNCH_P(1);
+    if (planes == 3) { if (k0 == 16) T3_LAUNCH_ACT(3, 0, 1, 16); else T3_LAUNCH_ACT(3, 0, 1, 32); }
+    else if (planes == 2 && fmt == 1) T3_LAUNCH_P(2, 1);
+    else if (planes == 2) T3_LAUNCH_P(2, 0);
+    else T3_LAUNCH_P(1, 0);
 #undef T3_LAUNCH_P
 #undef T3_LAUNCH_ACT
 #undef T3_LAUNCH
@@ -1098,7 +1138,7 @@ int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, co
     const int rc = t3_job_build(net, row_idx, batch, head, theta, with_grad, out, logp, ws, ws_bytes, mq_sm_count(), &local.job[0],
                                 &ns, stream);
     if (rc != MQ_OK) return rc;
-    const int rc2 = t3_launch_jobs(local, local.job[0].grid, t3_planes(head->tc), ns, local.job[0].p.img.k0, net->act[0],
+    const int rc2 = t3_launch_jobs(local, local.job[0].grid, t3_planes(head->tc), t3_fmt(head->tc), ns, local.job[0].p.img.k0, net->act[0],
                                    local.job[0].p.smem_bytes, stream);
     if (rc2 == MQ_OK && grid_out) *grid_out = local.job[0].grid;
     return rc2;
@@ -1114,7 +1154,8 @@ extern "C" int mq_fused_grad_partials2(const mq_net_t *net_a, const float *theta
                "mq_fused_grad_partials2: null pointer");
     MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_fused_grad_partials2: empty batch");
     if (!head_a->records || !head_b->records || ((head_a->tc | head_b->tc) & MQ_TC_OFF)) return MQ_ERR_UNSUPPORTED;
-    if (t3_planes(head_a->tc) != t3_planes(head_b->tc) || net_a->act[0] != net_b->act[0]) return MQ_ERR_UNSUPPORTED;
+    if (t3_planes(head_a->tc) != t3_planes(head_b->tc) || t3_fmt(head_a->tc) != t3_fmt(head_b->tc) || net_a->act[0] != net_b->act[0])
+        return MQ_ERR_UNSUPPORTED;
     T3Jobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     const int64_t sms = mq_sm_count();
@@ -1126,7 +1167,7 @@ extern "C" int mq_fused_grad_partials2(const mq_net_t *net_a, const float *theta
     if (rc != MQ_OK) return rc;
     if (ns_a != ns_b || jobs.job[0].p.img.k0 != jobs.job[1].p.img.k0) return MQ_ERR_UNSUPPORTED;
     const int smem = jobs.job[0].p.smem_bytes > jobs.job[1].p.smem_bytes ? jobs.job[0].p.smem_bytes : jobs.job[1].p.smem_bytes;
-    rc = t3_launch_jobs(jobs, jobs.job[0].grid + jobs.job[1].grid, t3_planes(head_a->tc), ns_a, jobs.job[0].p.img.k0, net_a->act[0],
+    rc = t3_launch_jobs(jobs, jobs.job[0].grid + jobs.job[1].grid, t3_planes(head_a->tc), t3_fmt(head_a->tc), ns_a, jobs.job[0].p.img.k0, net_a->act[0],
                         smem, stream);
     if (rc != MQ_OK) return rc;
     *n_parts_a = jobs.job[0].grid;

@@ -4,7 +4,14 @@
 // every CTA of every launch; mq_tc_image_build writes it from theta, and the optimiser step kernel (mq_step.cu)
 // refreshes the entries of the parameters it updates, so in the PPO loop no launch converts weights at all.
 //
-// Layout for P planes (x = x0 + .. + x_{P-1}, bf16 each), layer l with padded sizes kp (inputs) x np (outputs):
+// Operand formats (T3Img::F, selected per call by MQ_TC_FP16): F = 0, bf16 planes x = x0 + .. + x_{P-1}; F = 1 (two planes
+// only), fp16 planes with the LOW plane scaled: x = x0 + 2^-11 x1, x0 = fp16(x), x1 = fp16(2^11 (x - x0)).  An fp16 keeps
+// 11 significant bits, the residual x - x0 is exact in fp32 and its scaled copy keeps 11 more bits and a sign, so the
+// two planes carry x to 2^-24 relative (fp32 itself) for |x| < 65504 (above: +-inf, the gradient turns non-finite), and
+// a product needs three plane pairs where three bf16 planes need six.  The scaled pairs accumulate in their own TMEM
+// columns and are folded in with one FMA by the epilogues.
+//
+// Layout for P planes, layer l with padded sizes kp (inputs) x np (outputs):
 //   forward image   [k chunk of 8][plane][n][8 k]   K-major B operand of Z = A W, planes side by side along N
 //   backward image  [plane][k chunk of 8][n][8 k]   MN-major B operand of dA = dZ W^T, planes side by side along N'
 //                   (layers l >= 1 only)
@@ -12,13 +19,19 @@
 //   misc            float[32]: logstd[16], exp(-logstd)[16]
 #pragma once
 #include "mq_tc.cuh"
+#ifndef MQ_EMU
+#include <cuda_fp16.h>
+#endif
 
 #define T3_MAXL 3
 #define T3_HID 64
 #define T3_NO 16
 
+#define T3_LOW_SCALE 2048.0f               // 2^11: scale of the low fp16 plane
+#define T3_LOW_UNSCALE 4.8828125e-4f       // 2^-11
+
 struct T3Img {
-    int P, L, k0;
+    int P, F, L, k0;
     int kp[T3_MAXL], np[T3_MAXL];
     int in[T3_MAXL], out[T3_MAXL], w_off[T3_MAXL], b_off[T3_MAXL];
     int logstd_off, n_out, n_params;
@@ -27,17 +40,18 @@ struct T3Img {
 };
 
 // 0 when the net does not fit the kernel
-static inline int t3_img_build_layout(const mq_net_t *net, int planes, T3Img *g) {
+static inline int t3_img_build_layout(const mq_net_t *net, int planes, int fmt, T3Img *g) {
     memset(g, 0, sizeof(*g));
     const int L = net->n_layers;
     if (L < 2 || L > T3_MAXL) return 0;
+    if (fmt != 0 && (fmt != 1 || planes != 2)) return 0;
     if (net->n_in > 32 || net->n_out > T3_NO) return 0;
     for (int l = 0; l + 1 < L; ++l) {
         if (net->out[l] > T3_HID) return 0;
         if (net->act[l] != net->act[0] || (net->act[l] != MQ_ACT_TANH && net->act[l] != MQ_ACT_LRELU)) return 0;
     }
     if (net->logstd_off >= 0 && net->n_out > 8) return 0;
-    g->P = planes; g->L = L; g->k0 = net->n_in <= 16 ? 16 : 32;
+    g->P = planes; g->F = fmt; g->L = L; g->k0 = net->n_in <= 16 ? 16 : 32;
     g->logstd_off = net->logstd_off; g->n_out = net->n_out; g->n_params = net->n_params;
     int off = 0;
     for (int l = 0; l < L; ++l) {
@@ -57,9 +71,16 @@ static inline int t3_img_build_layout(const mq_net_t *net, int planes, T3Img *g)
 }
 
 #ifndef MQ_EMU
-// bf16 planes of one value: w[0] + w[1] + .. (round to nearest, residuals exact in fp32)
-template <int P>
+// planes of one value: bf16 w[0] + w[1] + .. (round to nearest, residuals exact in fp32), or fp16 w[0] + 2^-11 w[1]
+template <int P, int F>
 __device__ __forceinline__ void t3_split1(float v, uint16_t *w) {
+    if (F == 1) {
+        const __half h0 = __float2half_rn(v);
+        const __half h1 = __float2half_rn((v - __half2float(h0)) * T3_LOW_SCALE);
+        w[0] = *reinterpret_cast<const uint16_t *>(&h0);
+        w[1] = *reinterpret_cast<const uint16_t *>(&h1);
+        return;
+    }
 #pragma unroll
     for (int pl = 0; pl < P; ++pl) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -69,7 +90,7 @@ __device__ __forceinline__ void t3_split1(float v, uint16_t *w) {
 }
 
 // entries of parameter j (value val) in the image
-template <int P>
+template <int P, int F>
 __device__ __forceinline__ void t3_img_store_param(const T3Img &g, unsigned char *img, int j, float val) {
     if (g.logstd_off >= 0 && j >= g.logstd_off) {
         const int a = j - g.logstd_off;
@@ -85,7 +106,7 @@ __device__ __forceinline__ void t3_img_store_param(const T3Img &g, unsigned char
         if (wj >= 0 && wj < g.in[l] * g.out[l]) {
             const int k = wj / g.out[l], n = wj - k * g.out[l];
             uint16_t w[P];
-            t3_split1<P>(val, w);
+            t3_split1<P, F>(val, w);
             const int np = g.np[l];
             unsigned char *df = img + g.off_wf[l] + (k >> 3) * (P * np * 16) + n * 16 + (k & 7) * 2;
 #pragma unroll
@@ -106,8 +127,9 @@ __device__ __forceinline__ void t3_img_store_param(const T3Img &g, unsigned char
 }
 
 __device__ __forceinline__ void t3_img_store_param_rt(const T3Img &g, unsigned char *img, int j, float val) {
-    if (g.P == 3) t3_img_store_param<3>(g, img, j, val);
-    else if (g.P == 2) t3_img_store_param<2>(g, img, j, val);
-    else t3_img_store_param<1>(g, img, j, val);
+    if (g.P == 3) t3_img_store_param<3, 0>(g, img, j, val);
+    else if (g.P == 2 && g.F == 1) t3_img_store_param<2, 1>(g, img, j, val);
+    else if (g.P == 2) t3_img_store_param<2, 0>(g, img, j, val);
+    else t3_img_store_param<1, 0>(g, img, j, val);
 }
 #endif

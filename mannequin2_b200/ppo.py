@@ -26,7 +26,7 @@ from . import _device as D
 from . import _lib
 from . import dist as mqdist
 from ._adam import Adam
-from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, TC_MODES, MqHead, MqTrain
+from ._lib import ACT_NONE, ACT_TANH, HEAD_DIFF, HEAD_DISCRETE_PPO, HEAD_GAUSS_PPO, MQ_F32, TC_MODE_BITS, TC_MODES, MqHead, MqTrain
 from ._normalize import RunningNormalize
 from .basicnet import normed_columns
 
@@ -107,14 +107,14 @@ class _Net(object):
         value, m, v, _ = self.opt.state()
         if self._peer is None:
             self._peer = mqdist.PeerExchange(self.net.n_params)
-        head.tc = (head.tc & ~3) | self.planes
+        head.tc = (head.tc & ~TC_MODE_BITS) | self.planes
         if self.image is not None and self.records is not None and mb >= 8192:
             # record-fed tensor-core kernel: its operand image is built once here and then follows theta step by step
             head.records, head.rec_w, head.tc_image = D.ptr(self.records), self.rec_w, D.ptr(self.image)
             D.call("mq_tc_image_build", ctypes.byref(self.net), D.ptr(self.theta), self.planes, D.ptr(self.image), D.stream())
         else:
             head.records, head.rec_w, head.tc_image = None, 0, None
-            head.tc = head.tc & ~3
+            head.tc = head.tc & ~TC_MODE_BITS
         if mqdist.world() == 1 or self._peer.available():
             # per step 2 launches: gradient kernel (per-CTA partials), then ONE kernel that sums them in fixed order,
             # all-reduces over NVLink peer memory when sharded, applies Adam and refreshes the operand image
@@ -154,7 +154,7 @@ class _Net(object):
             coefs[2 * s], coefs[2 * s + 1] = self.opt.next_coefs()
         self.opt._out = None
         value, m, v, _ = self.opt.state()
-        head.tc = (head.tc & ~3) | self.planes
+        head.tc = (head.tc & ~TC_MODE_BITS) | self.planes
         head.records, head.rec_w, head.tc_image = D.ptr(self.records), self.rec_w, D.ptr(self.image)
         D.call("mq_tc_image_build", ctypes.byref(self.net), D.ptr(self.theta), self.planes, D.ptr(self.image), D.stream())
         t = MqTrain()
@@ -205,7 +205,8 @@ class PPOUpdater(object):
         self.n_obs, self.n_act = n_obs, n_act
         self.gam, self.lam, self.pol_lr, self.val_lr, self.clip = gam, lam, pol_lr, val_lr, clip
         # tc_mode: precision of the tensor-core gradient kernel that serves minibatches >= 8,192 rows: "exact" (three bf16
-        # planes, the fp32 bar of the FFMA kernels), "bf16x2" (|err| <= 3e-5 max|grad|) or "bf16" (<= 2e-2): north_star's
+        # planes, the fp32 bar of the FFMA kernels), "fp16x2" (two fp16 planes, the low one scaled: the same bar at the two-plane cost, operands must stay below 65504),
+        # "bf16x2" (|err| <= 3e-5 max|grad|) or "bf16" (<= 2e-2): north_star's
         # "stated looser tolerance for bf16 tensor-core paths".  Smaller minibatches always run the fp32 FFMA kernels.
         assert tc_mode in TC_MODES, tc_mode
         self.tc_mode = tc_mode

@@ -887,7 +887,8 @@ def case_tc_paths(B):
 
 
 # stated tolerances of the tensor-core precision modes (include/mq_b200.h): |err| <= rtol |ref| + atol_scale max|ref|
-TC_MODE_TOL = {3: (3e-5, 3e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}
+TC_MODE_TOL = {3: (3e-5, 3e-6), 0x82: (3e-5, 3e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}      # 0x82: fp16x2 = the exact bar
+TC_MODE_LIST = (3, 0x82, 2, 1)
 
 
 def pack_records(B, net, x, tgt=None, w0=None, w1=None):
@@ -901,8 +902,8 @@ def pack_records(B, net, x, tgt=None, w0=None, w1=None):
 
 
 def case_tc_modes(B):
-    """Record-fed tensor-core gradient kernel (mq_tc3.cu) in its three precision modes -- 3 bf16 planes (exact products),
-    2 planes, 1 plane -- against the oracle, each at its STATED tolerance (include/mq_b200.h), for every head, ragged
+    """Record-fed tensor-core gradient kernel (mq_tc3.cu) in its precision modes -- 3 bf16 planes (exact products), 2 fp16
+    planes with the low one scaled (the same bar), 2 bf16 planes, 1 plane -- against the oracle, each at its STATED tolerance (include/mq_b200.h), for every head, ragged
     batches, gathered rows, one and two hidden layers; packed records against the source arrays (bit-exact); operand
     image built by the launch, built ahead (mq_tc_image_build) and refreshed by the optimiser step
     (mq_reduce_step_image) are byte-identical."""
@@ -935,7 +936,7 @@ def case_tc_modes(B):
         tgt = rs.randn(batch, n_out).astype(np.float32)
         onehot = np.eye(n_out, dtype=np.float32)[rs.randint(n_out, size=batch)]
         hx = B.up(x)
-        for planes in (3, 2, 1):
+        for planes in TC_MODE_LIST:
             rtol, atol = TC_MODE_TOL[planes]
             for kind, mat, dyo in ((L.HEAD_DY, dy, dy), (L.HEAD_DIFF, tgt, tgt - outs[-1]),
                                    (L.HEAD_SOFTMAX_CE, onehot, None)):
@@ -969,8 +970,9 @@ def case_tc_modes(B):
     rec, rec_w = pack_records(B, net, o, a, adv, lp_old)
     wsb = lib.mq_fused_ws_bytes(net, 1 << 16)
     ws, grad = B.zeros(wsb, np.uint8), B.zeros(5126, np.float32)
-    img_bytes = {pl: lib.mq_tc_image_bytes(net, pl) for pl in (1, 2, 3)}
-    assert 0 < img_bytes[1] < img_bytes[2] < img_bytes[3] <= 96 * 1024
+    img_bytes = {pl: lib.mq_tc_image_bytes(net, pl) for pl in TC_MODE_LIST}
+    assert 0 < img_bytes[1] < img_bytes[2] < img_bytes[3] <= 96 * 1024 and img_bytes[0x82] == img_bytes[2]
+    assert lib.mq_tc_image_bytes(net, 3 | L.TC_FP16) == 0               # the fp16 format exists with two planes only
     for mb in (64, 200, 8192, 20000, 65536):
         idx = rs.randint(n, size=mb).astype(np.int32)
         hi = B.up(idx)
@@ -985,7 +987,7 @@ def case_tc_modes(B):
                                 None, B.ptr(ws), wsb, B.stream))
         g0 = B.down(g0)
         close(g0, want, rtol=3e-5, atol_scale=3e-6, what="array-fed tc ppo grad mb=%d vs oracle on all rows" % mb)
-        for planes in (3, 2, 1):
+        for planes in TC_MODE_LIST:
             rtol, atol = TC_MODE_TOL[planes]
             image = B.zeros(img_bytes[planes], np.uint8)
             ok(B, lib.mq_tc_image_build(net, B.ptr(ht), planes, B.ptr(image), B.stream))
@@ -1020,7 +1022,7 @@ def case_tc_modes(B):
     lp_d = O.discrete_logprob(outs_d[-1], acts_d[idx])[0]
     wgt = O.ppo_clip_weight(lp_d, lpo_d[idx], adv[idx])
     want = O.discrete_logprob_grad(theta_d, spec_d, o[idx], acts_d[idx], wgt, outs_d)
-    for planes in (3, 2, 1):
+    for planes in TC_MODE_LIST:
         rtol, atol = TC_MODE_TOL[planes]
         h = head(B, L.HEAD_DISCRETE_PPO, p0=0.8, p1=1.2, target=hoh, adv=hadv, logp_old=hlpd, tc=F | planes,
                  records=rec_d, rec_w=rw_d)
@@ -1028,7 +1030,7 @@ def case_tc_modes(B):
                                 None, B.ptr(wsd), wsb_d, B.stream))
         close(B.down(gd), want, rtol=rtol, atol_scale=atol, what="tc3 discrete ppo P=%d" % planes)
     # ---- the optimiser step keeps the operand image in step with theta (mq_reduce_step_image)
-    for planes in (3, 2, 1):
+    for planes in TC_MODE_LIST:
         mb = 8192
         idx = rs.randint(n, size=mb).astype(np.int32)
         hi = B.up(idx)

@@ -174,7 +174,7 @@ def _strong_worker(rank, world, port, out_dir, tc_mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("tc_mode", ["exact", "bf16x2"])
+@pytest.mark.parametrize("tc_mode", ["exact", "fp16x2", "bf16x2"])
 def test_strong_scaling_form_matches_oracle(tmp_path, tc_mode):
     """BASELINE configs[2] as SURVEY 8e words it: ONE rollout, every global minibatch split by rows over the GPUs (8,192
     rows per rank here, so the record-fed tcgen05 gradient kernel and the in-kernel low-latency exchange run TOGETHER),
@@ -200,7 +200,7 @@ def test_strong_scaling_form_matches_oracle(tmp_path, tc_mode):
                                          O.AdamO(val0, horizon=10, lr=0.003), O.RunningNormalizeO(horizon=2),
                                          o, a, r, d.astype(bool), vi, pi)
     steps = len(vi)
-    frac = {"exact": 0.007, "bf16x2": 0.07}[tc_mode]         # tests/test_compat_gpu.py: UPDATE_FRAC
+    frac = {"exact": 0.007, "fp16x2": 0.007, "bf16x2": 0.07}[tc_mode]         # tests/test_compat_gpu.py: UPDATE_FRAC
     assert np.max(np.abs(pol[0] - pol0)) > 1e-4
     assert np.max(np.abs(pol[0] - want_pol)) < frac * 3e-4 * (1 + steps), np.max(np.abs(pol[0] - want_pol))
     assert np.max(np.abs(val[0] - want_val)) < frac * 3e-3 * (1 + steps), np.max(np.abs(val[0] - want_val))

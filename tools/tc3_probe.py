@@ -54,12 +54,12 @@ for mb in sizes:
     wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
     want = O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs)
     scale = float(np.max(np.abs(want)))
-    for name, planes, records in (("array-fed exact", 3, False), ("P=3 pipe", 3, True), ("P=3 nopipe", 3 | 0x40, True),
-                                  ("P=2", 2, True), ("P=1 pipe", 1, True), ("P=1 nopipe", 1 | 0x40, True)):
+    for name, planes, records in (("array-fed exact", 3, False), ("bf16x3 (exact)", 3, True), ("fp16x2", 0x82, True),
+                                  ("bf16x2", 2, True), ("bf16", 1, True)):
         image = None
         if records:
-            image = torch.zeros(lib.mq_tc_image_bytes(net, planes & 3), dtype=torch.uint8, device=dev)
-            L.check(lib.mq_tc_image_build(net, ht.data_ptr(), planes & 3, image.data_ptr(), stream))
+            image = torch.zeros(lib.mq_tc_image_bytes(net, planes), dtype=torch.uint8, device=dev)
+            L.check(lib.mq_tc_image_build(net, ht.data_ptr(), planes, image.data_ptr(), stream))
         h = head(planes, records, image)
         g = torch.zeros(5126, device=dev)
         L.check(lib.mq_fused_grad(net, ht.data_ptr(), ho.data_ptr(), hi.data_ptr(), mb, ctypes.byref(h), 1.0 / mb, g.data_ptr(),
