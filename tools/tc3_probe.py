@@ -54,8 +54,11 @@ for mb in sizes:
     wgt = O.ppo_clip_weight(lp, lp_old[idx], adv[idx])
     want = O.policy_logprob_grad(theta, spec, o[idx], a[idx], wgt, outs)
     scale = float(np.max(np.abs(want)))
+    only = os.environ.get("PROBE_ONLY")
     for name, planes, records in (("array-fed exact", 3, False), ("bf16x3 (exact)", 3, True), ("fp16x2", 0x82, True),
                                   ("bf16x2", 2, True), ("bf16", 1, True)):
+        if only and name not in only.split(","):
+            continue
         image = None
         if records:
             image = torch.zeros(lib.mq_tc_image_bytes(net, planes), dtype=torch.uint8, device=dev)
