@@ -193,8 +193,9 @@ template <int P, int F, int ACT>
 __device__ __forceinline__ float t3_act(float z, float leak) {
     if (ACT == MQ_ACT_TANH) {
         if (P == 1) return t3_tanh_fast(z);             // MUFU.TANH: 2^-11, the size of a bf16 rounding
-        if (P == 2 && F == 0) {                                   // 1 - 2 / (2^(2 log2(e) |z|) + 1): ~1.2e-7 ABSOLUTE (no small-|z| branch),
-            float t, r;                                 // well inside the 16-bit operands of this mode
+        if (P == 2) {                                   // 1 - 2 / (2^(2 log2(e) |z|) + 1): ~1.2e-7 ABSOLUTE (no small-|z| branch):
+            float t, r;                                 // inside the 16-bit operands of bf16x2; for fp16x2 it is the fp32 bar's
+                                                        // absolute term (tests/kernel_cases.py: atol 3e-6 max|ref|), half the work
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.8853900817779268f));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
             return copysignf(fmaf(r, -2.0f, 1.0f), z);
@@ -564,6 +565,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
             const int i = quarter * 16 + lane;
             const bool lv = lane < 16;
             for (int l = 0; l < L; ++l) {
+                T3_MARK(92 + l);
                 const int in = p.net.in[l], on = p.net.out[l];
                 const int nb = (l == L - 1) ? T3_NO : p.img.kp[l];
                 for (int c0 = cg4 * 16; c0 < nb; c0 += 64) {
@@ -797,10 +799,30 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                             }
                         // db_{L-1} / dlogstd = column sums of dZ over the rows: this warp's 32 rows by shuffles, accumulated per
                         // warp in shared memory in tile order (fixed order: bit-reproducible); invalid rows hold zeros
+                        // (transposing butterfly: every exchange halves the columns a lane still carries -- DPT - 1 + the
+                        // remaining steps shuffles instead of 5 DPT)
+                        {
+                            float cs[DPT];
 #pragma unroll
-                        for (int k = 0; k < DPT; ++k) {
-                            const float cs = mq_warp_sum(sv[k]);
-                            if (lane == 0) s_rb[warp][k] += cs;
+                            for (int k = 0; k < DPT; ++k) cs[k] = sv[k];
+                            int col = 0;
+#pragma unroll
+                            for (int o = 16, nn = DPT; o > 0; o >>= 1) {
+                                if (nn > 1) {
+                                    nn >>= 1;
+                                    const bool up = (lane & o) != 0;
+#pragma unroll
+                                    for (int k = 0; k < DPT / 2; ++k)
+                                        if (k < nn) {
+                                            const float keep = up ? cs[k + nn] : cs[k], give = up ? cs[k] : cs[k + nn];
+                                            cs[k] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+                                        }
+                                    col += up ? nn : 0;
+                                } else {
+                                    cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], o);
+                                }
+                            }
+                            if ((lane & (32 / DPT - 1)) == 0) s_rb[warp][col] += cs[0];
                         }
                         T3_MARK(332);
                         unsigned char *dbuf = sl + p.off_dzl;
