@@ -452,7 +452,7 @@ class PPOLargeWorkload(object):
         from mannequin2_b200 import _lib as L
         out = {}
         grads = {}
-        for mode in ("fp16x2", "exact", "bf16x2", "bf16"):
+        for mode in os.environ.get("BENCH_MODES", "fp16x2,exact,bf16x2,bf16").split(","):
             np.random.seed(0)
             upd = PPOUpdater(11, 3, tc_mode=mode)
             upd.check_indices = False
@@ -487,7 +487,8 @@ class PPOLargeWorkload(object):
                                   "the same parameters (g_exact: the three-plane bf16 mode)")
             del upd
         for mode in out:
-            out[mode]["grad_err_vs_exact"] = float(np.max(np.abs(grads[mode] - grads["exact"])) / np.max(np.abs(grads["exact"])))
+            if "exact" in grads:
+                out[mode]["grad_err_vs_exact"] = float(np.max(np.abs(grads[mode] - grads["exact"])) / np.max(np.abs(grads["exact"])))
         return out
 
     def parity_check(self, rows_per_rank=8192, epochs=1):
@@ -604,7 +605,7 @@ class MLPWorkload(object):
         self.torch.cuda.current_stream().synchronize()
 
     def launches_per_step(self):
-        return self.BLOCK * 11
+        return 1 if self.tr.fused else self.BLOCK * 11           # fused: ONE persistent launch per block of 32 steps
 
     def replica_throughput(self, n_replicas, steps=5, warmup=3):
         """Aggregate samples/s of n_replicas INDEPENDENT trainers (own parameters and Adam state) whose graph replays
@@ -650,10 +651,18 @@ class MLPWorkload(object):
         ms = float(np.median(times[2:])) / self.BLOCK
         bytes_per_step = self.B * 3216 + 24 * 118282        # 3.25 MB per step
         ach = bytes_per_step / (ms * 1e-3) / 1e9
-        return dict(bound="hbm", kernel="one optimiser step (11 launches: split-K fwd GEMM + finish, 2 fwd GEMMs, head, 5 bwd GEMMs with the bias gradients as an extra output row, Adam)",
-                    achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
-                    peak_source=peaks["source"], ms_per_launch=ms,
-                    note="latency-bound at batch 128: 3.25 MB / 65 MFLOP per step is 0.5 us at roofline")
+        if self.tr.fused:
+            kern = ("mlp_block_kernel (csrc/mq_mlp_fused.cu): 32 optimiser steps in ONE persistent launch of 128 CTAs = 16 clusters "
+                    "of 8; first layer and its Adam moments resident in shared memory, K-slice partials reduced through "
+                    "distributed shared memory, two grid-wide barriers per step; ms_per_launch is per STEP")
+            note = ("latency-bound at batch 128 (3.25 MB / 65 MFLOP per step is 0.5 us at roofline): a step is two grid barriers, "
+                    "one cluster barrier and a 64 KB reload of W1 per CTA")
+        else:
+            kern = ("one optimiser step (11 launches: split-K fwd GEMM + finish, 2 fwd GEMMs, head, 5 bwd GEMMs with the bias "
+                    "gradients as an extra output row, Adam)")
+            note = "latency-bound at batch 128: 3.25 MB / 65 MFLOP per step is 0.5 us at roofline"
+        return dict(bound="hbm", kernel=kern, achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], traffic=None,
+                    peak_source=peaks["source"], ms_per_launch=ms, note=note)
 
     def sweep(self, peaks):
         """BASELINE.md 3.4 / SURVEY 8d: the batch sweep B in {128, 1024, 8192, 65536} for the script's net (784-128-128-10,
@@ -1124,6 +1133,15 @@ def cpu_three_figures(name, cores):
 
 
 # ------------------------------------------------------------------ main
+_T0 = time.time()
+
+
+def progress(msg):
+    """Progress line on stderr (stdout carries only the JSON line)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
+    sys.stderr.flush()
+
+
 def measure(wl, steps, warmup, world, rank, flush):
     """W untimed steps, then K steps each timed on the device with its own CUDA-event pair on the
     launching stream; L2 is flushed (256 MB write) between steps, outside the timed intervals.
@@ -1189,6 +1207,9 @@ def main():
                     help="operand format of the tensor-core gradient kernel of the headline workload.  fp16x2 (default) and exact "
                          "(three bf16 planes) both meet the fp32 parity bar (rtol 1e-5); bf16x2 / bf16 are the looser modes")
     args = ap.parse_args()
+    if os.environ.get("BENCH_WATCHDOG"):                # developer aid: dump every thread's stack after N seconds and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_WATCHDOG"]), exit=True, file=sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # stdout carries exactly ONE line (rank 0's JSON): anything a library prints there (NCCL announces its version on
@@ -1243,10 +1264,12 @@ def main():
         wl = WORKLOADS[args.workload](seed=1, tc_mode=args.tc_mode)       # the SAME rollout on every rank (strong scaling)
     else:
         wl = WORKLOADS[args.workload](seed=1 + rank)
+    progress("setup %s" % args.workload)
     wl.setup_gpu()
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
     wl.step_gpu(0)
     torch.cuda.synchronize()
+    progress("timing %d + %d steps" % (warmup, args.steps))
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
@@ -1254,7 +1277,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     strong = large and world > 1
     units = wl.units_per_step * args.steps * (1 if strong else world)
+    progress("timed region done; parity check")
     parity = wl.parity_check() if large else None                           # every rank takes part (outside the timed region)
+    progress("dominant kernel")
     roof = wl.dominant_kernel(peaks) if rank == 0 else None
     weak_line = None
     if strong:
@@ -1301,6 +1326,7 @@ def main():
         if weak_line is not None:
             line["weak_scaling"] = weak_line
         if not args.no_cpu_baseline and world == 1 and getattr(wl, "step_cpu", None):
+            progress("cpu baseline (three figures)")
             three = cpu_three_figures(args.workload, cores)
             line["cpu_baseline"] = dict(
                 value=three["replicas_aggregate"], unit=wl.unit, cores=three["replicas"], kind="port", host=host_info(),
@@ -1312,6 +1338,7 @@ def main():
         else:
             line["cpu_baseline"] = None
         if large and world == 1 and not args.no_extras:
+            progress("precision modes")
             line["modes"] = wl.precision_modes()
         if not args.no_extras and world == 1:
             del wl
@@ -1320,6 +1347,7 @@ def main():
             for name in ("closed_loop", "ppo", "mlp", "es", "vae"):
                 if name == args.workload:
                     continue
+                progress("other workload: %s" % name)
                 w2 = WORKLOADS[name](seed=7)
                 w2.setup_gpu()
                 m1, m2 = measure(w2, 5, 3, 1, 0, flush)
@@ -1337,7 +1365,9 @@ def main():
                 del w2
                 torch.cuda.empty_cache()
             line["other_workloads"] = others
+            progress("kernel sweep")
             line["kernels"] = kernel_sweep(peaks)
+            progress("done")
         emit(line)
     if world > 1:
         dist.barrier()

@@ -239,6 +239,20 @@ int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, const float
                             const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx,
                             void *ws, int64_t ws_bytes, void *stream, void *side_stream, void *const *events);
 
+/* mnist/mlp.py:24-43 at the reference's batch size as ONE persistent launch for a block of optimiser steps
+ * (csrc/mq_mlp_fused.cu): 128 CTAs = 16 clusters of 8; the first layer stays split over the CTAs' shared memory with its
+ * Adam moments, the 8 K-slice partials of a column slice meet through distributed shared memory, the middle of the net is
+ * row-local, two grid-wide barriers per step.  Replaces per step: the gather (mlp.py:31-32), Function.evaluate
+ * (basicnet.py:192-207), the softmax / L2 head (mlp.py:10-14,33), backprop with the batch mean (basicnet.py:209-257) and
+ * Adam.apply_gradient (_adam.py:23-53).  idx_table: device int32 [steps][batch]; coefs_dev: device double [steps][4] =
+ * {c1, c2, lr, eps}; y_onehot: float [rows][n_out]; value / m / v: optimiser state (MQ_F32 or MQ_F64), theta: fp32 copy.
+ * MQ_ERR_UNSUPPORTED unless batch == 128, two or three layers, hidden width 128, n_in % 4 == 0, n_in <= 800,
+ * n_out <= 16, linear output layer (mq_mlp_train_block_ws_bytes returns 0 for such nets). */
+int64_t mq_mlp_train_block_ws_bytes(const mq_net_t *net, int64_t batch);
+int mq_mlp_train_block(const mq_net_t *net, float *theta, void *value, void *m, void *v, int state_dtype,
+                       const float *x, const float *y_onehot, const int32_t *idx_table, int64_t batch, int32_t steps,
+                       const double *coefs_dev, float l2, void *ws, int64_t ws_bytes, void *stream);
+
 /* ---- fused small-MLP path (weights resident in shared memory) -------------- */
 /* rows per tile the fused kernels would use for this net (0 = does not fit). */
 int mq_fused_tile_rows(const mq_net_t *net, int with_grad);

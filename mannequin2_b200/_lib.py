@@ -105,6 +105,8 @@ SIGNATURES = {
     "mq_mlp_forward_ws": (c_int, [NETP, P, P, P, c_int64, P, P, c_int64, P]),
     "mq_mlp_backward": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, P, c_int64, P]),
     "mq_mlp_backward_overlap": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, P, c_int64, P, P, P]),
+    "mq_mlp_train_block_ws_bytes": (c_int64, [NETP, c_int64]),
+    "mq_mlp_train_block": (c_int, [NETP, P, P, P, P, c_int, P, P, P, c_int64, c_int32, P, c_float, P, c_int64, P]),
     "mq_fused_tile_rows": (c_int, [NETP, c_int]),
     "mq_fused_ws_bytes": (c_int64, [NETP, c_int64]),
     "mq_fused_forward": (c_int, [NETP, P, P, P, c_int64, P, P, P, P]),

@@ -465,7 +465,10 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                                                    sb + p.off_act[l] + (l == 0 ? xo : 0u), p.act_plane[l], CB, p.img.kp[l], 8, dw_ksteps,
                                                    acc_started[l]);
                                 acc_started[l] = true;
-                                tc_commit(l == 0 ? full : dwb);  // l == 0 has no dA: its dW product is the phase
+                                // dW_0 (no dA) also completes on the dW barrier, NOT on `full`: with two input buffers the next
+                                // tile's F0 may be committed before a slow warp has looked at dW_0's completion, and two
+                                // completions of one barrier inside one wait would leave that warp waiting for a third
+                                tc_commit(dwb);
                             }
                         }
                     }
@@ -622,11 +625,11 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                 const float *sHin = sHin0 + buf * p.hin_stride;
                 T3_MARK(10);
                 if (!staged) {
-                    if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }     // dW_0 read the buffer
+                    if (pending) { tc_wait(dwb, par_dw); par_dw ^= 1u; pending = false; }          // dW_0 read the buffer
                     stage(buf);
                     t3_warp_ready(rdx, lane);
-                } else if (pending) {                   // (consume dW_0's phase of the barrier: at most one phase behind)
-                    tc_wait(full, par_full); par_full ^= 1u; pending = false;
+                } else if (pending) {                   // (consume dW_0's phase of the dW barrier: its next phase is a whole
+                    tc_wait(dwb, par_dw); par_dw ^= 1u; pending = false;       // forward pass away)
                 }
                 staged = false;
                 ++tcount;
@@ -902,7 +905,7 @@ tc3_grad_kernel(const __grid_constant__ T3Jobs launch, long long *prof) {
                 }
             }
             if (p.with_grad) {
-                if (pending) { tc_wait(full, par_full); par_full ^= 1u; pending = false; }
+                if (pending) { tc_wait(dwb, par_dw); par_dw ^= 1u; pending = false; }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

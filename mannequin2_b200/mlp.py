@@ -1,13 +1,17 @@
 """Fused training loop of mnist/mlp.py:24-43: Input(28,28) -> 2 x LReLU(Affine 128) -> Affine(10),
 dy = onehot - softmax(out) - 0.01*out, Adam(horizon 10, lr 1e-3), batch 128 drawn by index.
 
-The 784x128 first layer (401 KB) does not fit in one SM's shared memory, so this net runs on
-the layered path: one GEMM launch per layer with fused bias/activation epilogues
-(csrc/mq_gemm.cu), the softmax head, the backward GEMMs and the fused Adam step.  A whole block
-of steps is captured ONCE in a CUDA graph (Adam coefficients and minibatch indices are read
-from device tables), so a training block is a single graph launch.
+Two paths.  At the reference's batch size (128; hidden width 128) a block of steps is ONE persistent
+launch (csrc/mq_mlp_fused.cu, `fused=True`, the default when the net fits): the 784x128 first layer
+(401 KB, more than one SM's shared memory) stays split over 128 CTAs with its Adam moments, the
+K-slice partial sums meet through distributed shared memory, two grid-wide barriers per step.
+Any other batch runs on the layered path: one GEMM launch per layer with fused bias/activation
+epilogues (csrc/mq_gemm.cu, the TMA-fed tcgen05 GEMM for large batches), the softmax head, the
+backward GEMMs and the fused Adam step, a whole block of steps captured ONCE in a CUDA graph
+(Adam coefficients and minibatch indices are read from device tables).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -22,7 +26,7 @@ from .ppo import init_mlp
 class MLPTrainer(object):
     def __init__(self, n_in=784, widths=(128, 128, 10), acts=(ACT_LRELU, ACT_LRELU, ACT_NONE), *,
                  leak=0.1, batch=128, horizon=10, lr=1e-3, l2=0.01, params=None, state_dtype="float32",
-                 graph_steps=32):
+                 graph_steps=32, fused=True):
         self.net = _lib.make_net(n_in, list(widths), list(acts), leak=leak)
         if params is None:
             params = init_mlp(n_in, list(widths), 0.1)                # mlp.py:24-27 (init=0.1 head)
@@ -38,6 +42,10 @@ class MLPTrainer(object):
         self.wsb = lib.mq_mlp_ws_bytes(nb, batch)
         self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=D.device())
         self.graph_steps = graph_steps
+        # one persistent launch per block of steps when the net fits (batch 128, hidden width 128)
+        self._fused_wsb = int(lib.mq_mlp_train_block_ws_bytes(nb, batch)) if fused else 0
+        self.fused = self._fused_wsb > 0
+        self._fused_ws = torch.empty(max(self._fused_wsb, 16), dtype=torch.uint8, device=D.device())
         self.idx = torch.zeros(graph_steps * batch, dtype=torch.int32, device=D.device())
         self.coefs = torch.zeros(graph_steps * 4, dtype=torch.float64, device=D.device())
         self._graph, self._graph_data = None, None
@@ -61,7 +69,7 @@ class MLPTrainer(object):
                D.ptr(self.dy), D.stream())
         D.call("mq_mlp_backward_overlap", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
                D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, D.ptr(self.ws), self.wsb, D.stream(),
-               self._side.cuda_stream, self._event_ptrs)
+               None if os.environ.get("MQ_MLP_NO_OVERLAP") else self._side.cuda_stream, self._event_ptrs)
         D.call("mq_adam_step_dev", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
                self.net.n_params, self.opt._code, MQ_F32, coef_ptr, 0, D.stream())
 
@@ -78,6 +86,9 @@ class MLPTrainer(object):
             co[s] = (c1, c2, self.lr, 1e-8)
         self.coefs.copy_(D.from_host(co.reshape(-1), np.float64), non_blocking=True)
         self.opt._out = None
+        if self.fused:
+            self._fused_steps(x, y, D.ptr(self.idx), D.ptr(self.coefs), steps)
+            return
         key = (D.ptr(x), D.ptr(y), steps)
         if self._graph is None or self._graph_data != key:
             value, m, v, _ = self.opt.state()
@@ -92,6 +103,12 @@ class MLPTrainer(object):
                 t.copy_(c)
             self._graph, self._graph_data = g, key
         self._graph.replay()
+
+    def _fused_steps(self, x, y, idx_ptr, coef_ptr, steps):
+        value, m, v, _ = self.opt.state()
+        D.call("mq_mlp_train_block", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(value), D.ptr(m), D.ptr(v), self.opt._code,
+               D.ptr(x), D.ptr(y), idx_ptr, self.batch, steps, coef_ptr, self.l2, D.ptr(self._fused_ws), self._fused_wsb,
+               D.stream())
 
     def _sgd_setup(self):
         """Staging for sgd_step: double-buffered pinned host buffers (batch, labels, Adam coefficients), fixed device
@@ -127,6 +144,9 @@ class MLPTrainer(object):
         st["coef"].copy_(pc, non_blocking=True)
         st["ev"][slot].record()
         self.opt._out = None
+        if self.fused:
+            self._fused_steps(st["x"], st["y"], D.ptr(st["idx"]), D.ptr(st["coef"]), 1)
+            return
         if st["graph"] is None:
             self._enqueue_step(st["x"], st["y"], 0, D.ptr(st["idx"]), D.ptr(st["coef"]))   # eager once (kernel attributes)
             torch.cuda.current_stream().synchronize()

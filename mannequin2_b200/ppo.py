@@ -181,6 +181,9 @@ class _Net(object):
         return {2: "ll", 0: "push", 1: "pull"}[self._peer.pull] if self._peer.available() else "nccl"
 
 
+PAIR_MAX_ROWS = 16384          # per-GPU minibatch rows up to which the value and the policy step share launches
+
+
 class PPOUpdater(object):
     def __init__(self, n_obs, n_act, *, hid=64, n_hid=2, gam=0.99, lam=0.95, pol_lr=3e-4, val_lr=3e-3,
                  horizon=10, clip=(0.8, 1.2), norm_horizon=2, state_dtype="float32",
@@ -306,8 +309,11 @@ class PPOUpdater(object):
         # Large minibatches on the same schedule (BASELINE configs[2]): the two nets' steps are PAIRED -- per step one
         # gradient launch with each net on half of the SMs and one reduce / exchange / Adam launch for both (csrc/mq_tc3.cu,
         # csrc/mq_step.cu) -- in one stream, hence in one fixed order on every rank.  MQ_PPO_UNPAIRED=1: the two chains apart.
+        # Pairing pays while a net has about one tile per SM (a launch is then one tile's chain of dependent phases long
+        # whatever the row count: 5.45 against 9.83 ms per update at 8,192 rows per GPU); with several tiles per SM each net
+        # is faster on all SMs by itself (12.2 against 13.1 ms at 65,536 rows).  MQ_PPO_PAIRED=1 / MQ_PPO_UNPAIRED=1 force.
         paired = (v_mb >= 8192 and v_mb == p_mb and v_steps == p_steps and val.code == pol.code and
-                  not os.environ.get("MQ_PPO_UNPAIRED"))
+                  (v_mb <= PAIR_MAX_ROWS or os.environ.get("MQ_PPO_PAIRED")) and not os.environ.get("MQ_PPO_UNPAIRED"))
         big = v_mb >= 8192 or p_mb >= 8192
         if big:
             val.pack(obs, ret, None, None, n)

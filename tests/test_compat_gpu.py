@@ -993,3 +993,89 @@ def test_unmodified_script_loop_via_compat_alias():
     acc = np.mean(np.argmax(model(x[:512]), axis=-1) == labels[:512])
     assert acc > 0.9, acc
     assert bar(100.0 * acc).startswith(" ")
+
+@pytest.mark.gpu
+def test_mlp_fused_block_matches_oracle_and_reference_run():
+    """csrc/mq_mlp_fused.cu -- a block of mnist/mlp.py:31-35 steps as ONE persistent launch (batch 128): against the oracle's
+    restatement step for step (train_block and sgd_step, fp32 and fp64 optimiser state, the 784-128-128-10 and 784-128-10
+    nets, a narrow ragged-slice net), bit-reproducible, and against the optimiser values that
+    mnist/mlp.py:run() ITSELF produced on the same minibatches (golden/mlp_script.npz)."""
+    import os
+    from oracle import mq_oracle as O
+    from mannequin2_b200.mlp import MLPTrainer
+    from mannequin2_b200.ppo import init_mlp
+    from mannequin2_b200 import _device as D
+    rs = np.random.RandomState(18)
+    n, steps, B = 700, 9, 128
+    for n_in, widths in ((784, [128, 128, 10]), (784, [128, 10]), (36, [128, 128, 3])):
+        acts = [O.ACT_LRELU] * (len(widths) - 1) + [O.ACT_NONE]
+        x = rs.rand(n, n_in).astype(np.float32)
+        y = np.eye(widths[-1], dtype=np.float32)[rs.randint(widths[-1], size=n)]
+        tab = rs.randint(n, size=(steps, B)).astype(np.int32)
+        np.random.seed(4)
+        theta0 = init_mlp(n_in, widths, 0.1)
+        spec = O.mlp_spec(n_in, widths, acts)
+        opt = O.AdamO(theta0, horizon=10, lr=1e-3)
+        want = theta0.copy()
+        for s_ in range(steps):
+            want = O.mlp_sgd_step(want, spec, opt, x[tab[s_]], y[tab[s_]])
+        kw = dict(n_in=n_in, widths=tuple(widths), acts=tuple([2] * (len(widths) - 1) + [0]), graph_steps=steps)
+        xd, yd = D.from_host(x), D.from_host(y)
+        got = {}
+        # (the layered path has its own test above; held to the same bar here it depends on the draw: a parameter whose batch
+        # gradient is rounding noise gets a full-size Adam step of either sign -- tools/mlp_blocks_check.py)
+        for name, state, fused in (("fused32", "float32", True), ("fused64", "float64", True)):
+            tr = MLPTrainer(params=theta0.copy(), state_dtype=state, fused=fused, **kw)
+            assert tr.fused == fused
+            tr.train_block(xd, yd, tab[:5])            # two blocks: the moments survive the launch boundary
+            tr.train_block(xd, yd, tab[5:])
+            got[name] = tr.get_params()
+            err = np.max(np.abs(got[name] - want))
+            assert np.max(np.abs(got[name] - theta0)) > 1e-3
+            assert err < 2e-6 * (1 + steps) + 1e-6, (n_in, widths, name, err)
+            val = D.to_host(tr.opt.state()[0])
+            assert np.max(np.abs(val - got[name])) < 1e-6          # optimiser value and model copy agree
+        again = MLPTrainer(params=theta0.copy(), **kw)
+        again.train_block(xd, yd, tab[:5])
+        again.train_block(xd, yd, tab[5:])
+        assert np.array_equal(again.get_params(), got["fused32"]), "fused block is not bit-reproducible"
+        one = MLPTrainer(params=theta0.copy(), **kw)     # host-side batches, one step per launch
+        for s_ in range(steps):
+            one.sgd_step(x[tab[s_]], y[tab[s_]])
+        assert np.max(np.abs(one.get_params() - want)) < 2e-6 * (1 + steps) + 1e-6
+    # the reference script's own run: same initial weights, its minibatches, its optimiser trace
+    g = load_golden("mlp_script")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    try:
+        from make_golden import mlp_script_data
+    finally:
+        sys.path.pop(0)
+    data = mlp_script_data()
+    import mannequin2_b200.compat  # noqa: F401
+    from mannequin.basicnet import Input, Affine, LReLU
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(g["mlps_seed"][0]))
+        model = Input(28, 28)
+        for _ in range(2):
+            model = LReLU(Affine(model, 128))
+        model = Affine(model, 10, init=0.1)
+    finally:
+        np.random.set_state(state)
+    stride, keep = int(g["mlps_stride"][0]), [int(k) for k in g["mlps_keep"]]
+    theta0 = np.asarray(model.get_params(), np.float32)
+    tr = MLPTrainer(params=theta0.copy(), state_dtype="float64", graph_steps=32)
+    xd = D.from_host(np.ascontiguousarray(data["train_x"], np.float32).reshape(len(data["train_x"]), 784))
+    yd = D.from_host(np.ascontiguousarray(data["train_y"], np.float32))
+    idx = g["mlps_idx"].astype(np.int32)
+    done = 0
+    for k in keep:
+        if k == 0 or k > len(idx):
+            continue
+        tr.train_block(xd, yd, idx[done:k])
+        done = k
+        val = D.to_host(tr.opt.state()[0]).astype(np.float64)
+        err = np.max(np.abs(val[::stride] - g["mlps_trace"][keep.index(k)]))
+        assert err < 1e-5 if k <= 10 else err < 1e-4, (k, err)
+    assert done >= 10
+

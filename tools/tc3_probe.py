@@ -56,7 +56,7 @@ for mb in sizes:
     scale = float(np.max(np.abs(want)))
     only = os.environ.get("PROBE_ONLY")
     for name, planes, records in (("array-fed exact", 3, False), ("bf16x3 (exact)", 3, True), ("fp16x2", 0x82, True),
-                                  ("bf16x2", 2, True), ("bf16", 1, True)):
+                                  ("bf16x2", 2, True), ("bf16", 1, True), ("fp16x2 static", 0xC2, True), ("bf16 static", 0x41, True)):
         if only and name not in only.split(","):
             continue
         image = None
@@ -81,5 +81,14 @@ for mb in sizes:
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts = sorted(ts[2:])
-        print("mb=%6d %-16s max|err|/max|grad| = %.2e   kernel %.1f us (median of 10, L2 flushed), %d partials"
-              % (mb, name, err, ts[len(ts) // 2], n_parts.value), flush=True)
+        reps = 50                                      # event resolution is ~2 us here: also time a back-to-back train
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(reps):
+            L.check(lib.mq_fused_grad_partials(net, ht.data_ptr(), ho.data_ptr(), hi.data_ptr(), mb, ctypes.byref(h), None, None,
+                                               ws.data_ptr(), wsb, ctypes.byref(n_parts), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        train = e0.elapsed_time(e1) * 1e3 / reps
+        print("mb=%6d %-16s max|err|/max|grad| = %.2e   kernel %.1f us (median of 10, L2 flushed), %.2f us (50 back to back), %d partials"
+              % (mb, name, err, ts[len(ts) // 2], train, n_parts.value), flush=True)
