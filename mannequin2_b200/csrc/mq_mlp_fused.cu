@@ -48,6 +48,7 @@ struct MfArgs {
     float *pg;                      // [8][128][128] K-slice partial sums of the first layer
     float *h1, *h2, *dy, *dh2, *dh1;
     unsigned int *bar;
+    long long *prof;                // developer aid (mq_debug_set_phase_buffer): time stamps of the last step, CTAs 0 and 127
 };
 
 template <typename ST>
@@ -74,21 +75,48 @@ __device__ __forceinline__ void mf_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void mf_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// bulk asynchronous copies (TMA engine): one thread issues, completion is counted in bytes on an mbarrier -- no per-thread
+// load/store-unit slots are held while the data is in flight (W1: one 64 KB copy instead of 4,096 cp.async of 16 bytes)
+__device__ __forceinline__ uint32_t mf_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mf_mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mf_s32(b)), "r"(count));
+}
+__device__ __forceinline__ void mf_mbar_expect(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mf_s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mf_bulk(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(mf_s32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mf_s32(b)) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_wait(uint64_t *b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mf_s32(b)), "r"(parity) : "memory");
+    }
+}
+// loads that must be ISSUED where they are written (ptxas otherwise sinks them next to their first use, a phase later)
+__device__ __forceinline__ int32_t mf_ldg_s32(const int32_t *p) { int32_t v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ float mf_ldg_f32(const float *p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+
 // all CTAs of the launch have arrived (and their global writes are visible) -- monotonic counter, target = arrivals so far
 __device__ __forceinline__ void mf_grid_barrier(unsigned int *bar, unsigned int &epoch) {
     __syncthreads();
     epoch += MF_G;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        // arrive without waiting for the old value (one L2 round trip less than atomicAdd); release is cumulative over the
+        // writes of the whole CTA ordered before it by the barrier above
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
         } while (seen < epoch);
-        __threadfence();
     }
     __syncthreads();
 }
+
+__device__ __forceinline__ long long mf_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MF_MARK(i) do { if (a.prof && tid == 0 && (g == 0 || g == MF_G - 1) && s == a.steps / 2) a.prof[(g ? 16 : 0) + (i)] = mf_now(); } while (0)
 
 template <typename ST>
 __global__ void __launch_bounds__(MF_NT, 1)
@@ -119,6 +147,7 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
     float *h2r = (float *)take(MF_H * 4);
     float *dh2r = (float *)take(MF_H * 4);
     float *tmp = (float *)take(MF_NT * 4);
+    float *part8 = (float *)take(8 * MF_H * 4);                       // [8][128] partial h2 sums of the 8 k groups
     float *lg = (float *)take(MF_NO * 4);
     float *dyr = (float *)take(MF_NO * 4);
     // operands of phase D live in the W1 buffer (MID is done with it by then, the next MID reloads it)
@@ -127,6 +156,7 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
     float *dj = hk + MF_B * 16;                                      // [128][8] dh2 columns of the W1 block
     float *dys = dj + MF_B * MF_NS;                                  // [128][16] dy
     float *hcol = dys + MF_B * MF_NO;                                // column g of the last hidden layer
+    float *c1s = hcol + MF_B, *c2s = c1s + MF_B;                     // column g of dh1 / dh2 (bias gradients)
     // optimiser state of the parameters this CTA owns: value, m, v
     ST *sW0 = (ST *)take(3 * MF_KW * MF_NS * sizeof(ST));            // [3][kw * 8]
     ST *sB0 = (ST *)take(3 * sizeof(ST) * 2);                        // [3]: b0[g]
@@ -164,25 +194,42 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
     }
 
     // minibatch slice of step s -> xs[s & 1] (16-byte asynchronous copies; rows are 16-byte aligned: n_in % 4 == 0)
-    auto prefetch_x = [&](int s) {
-        float *dst = xs + (s & 1) * MF_B * MF_KW;
-        const int32_t *ix = a.idx + (int64_t)s * MF_B;
+    // minibatch slice of step s -> xs[s & 1]: thread (row, half) copies <= 13 chunks of 16 bytes with cp.async (rows are
+    // 16-byte aligned: n_in % 4 == 0); the row's gather index was loaded a phase earlier.  (One bulk copy per row on the TMA
+    // engine was measured slower: 128 copies of 400 bytes per CTA queue up behind each other.)
+    __shared__ __align__(8) uint64_t bar_w;
+    if (tid == 0) {
+        mf_mbar_init(&bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    auto prefetch_x = [&](int s, int32_t src_row) {
+        const int r = tid >> 1, half = tid & 1;
         const int cpr = kn >> 2;                        // 16-byte chunks per row
-        for (int i = tid; i < MF_B * cpr; i += MF_NT) {
-            const int r = i / cpr, ch = i - r * cpr;
-            mf_cp16(dst + r * MF_KW + 4 * ch, a.x + (int64_t)ix[r] * n_in + k0 + 4 * ch);
-        }
+        const int ch0 = half * ((cpr + 1) >> 1), ch1 = half ? cpr : ((cpr + 1) >> 1);
+        float *dst = xs + (s & 1) * MF_B * MF_KW + r * MF_KW;
+        const float *src = a.x + (int64_t)src_row * n_in + k0;
+        for (int ch = ch0; ch < ch1; ++ch) mf_cp16(dst + 4 * ch, src + 4 * ch);
         mf_cp_commit();
     };
+    prefetch_x(0, mf_ldg_s32(a.idx + (tid >> 1)));
+    int32_t next_row = a.steps > 1 ? mf_ldg_s32(a.idx + MF_B + (tid >> 1)) : 0;     // gather index of this thread's row, next step
+    uint32_t par_w = 0u;
     unsigned int epoch = 0;
-    prefetch_x(0);
 
     for (int s = 0; s < a.steps; ++s) {
         const ST c1 = (ST)a.coefs[4 * s], c2 = (ST)a.coefs[4 * s + 1], lr = (ST)a.coefs[4 * s + 2], eps = (ST)a.coefs[4 * s + 3];
         const float *xcur = xs + (s & 1) * MF_B * MF_KW;
         float *h1g = a.h1;
-        if (s + 1 < a.steps) { prefetch_x(s + 1); mf_cp_wait<1>(); } else { mf_cp_wait<0>(); }
+        MF_MARK(0);
+        if (a.prof && tid == 0 && g == 0 && s == 0) a.prof[14] = mf_now();
+        if (s + 1 < a.steps) { prefetch_x(s + 1, next_row); mf_cp_wait<1>(); } else { mf_cp_wait<0>(); }
+        // label entry of row g (lane = output) for the head, and the gather index of the step after the next: both far ahead of use
+        float ylab = 0.0f;
+        if (warp == 0 && lane < n_out) ylab = mf_ldg_f32(a.y + (int64_t)mf_ldg_s32(a.idx + (int64_t)s * MF_B + g) * n_out + lane);
+        if (s + 2 < a.steps) next_row = mf_ldg_s32(a.idx + (int64_t)(s + 2) * MF_B + (tid >> 1));
         __syncthreads();
+        MF_MARK(1);
 
         // ---- F0: partial[r][n] = sum_k x[r][k0 + k] W0[k0 + k][8 c + n] ------------------------------------------------
         {
@@ -201,13 +248,15 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
             }
             *reinterpret_cast<float4 *>(a.pg + ((int64_t)q * MF_B + r) * MF_H + c * MF_NS + nh) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
+        MF_MARK(2);
         mf_grid_barrier(a.bar, epoch);
+        MF_MARK(3);
 
         // ---- MID: row g through the rest of the net and back (row-local) ---------------------------------------------
-        if (L == 3) {
-            const float *src = a.theta + w1o;
-            for (int i = tid; i < MF_H * MF_H / 4; i += MF_NT) mf_cp16(W1s + 4 * i, src + 4 * i);
-            mf_cp_commit();
+        if (L == 3 && tid == 0) {                       // W1 (64 KB, published by its owners before the barrier): one bulk copy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // (the buffer was read / written by ordinary accesses)
+            mf_mbar_expect(&bar_w, (uint32_t)(MF_H * MF_H * 4));
+            mf_bulk(W1s, a.theta + w1o, (uint32_t)(MF_H * MF_H * 4), &bar_w);
         }
         if (tid < MF_H) {                                // the 8 K-slice partials of row g, in slice order
             float sum = 0.0f;
@@ -220,20 +269,34 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
         }
         for (int i = tid; i < MF_H * n_out; i += MF_NT) W2s[i] = __ldcg(a.theta + wlo + i);
         if (tid < n_out) b2s[tid] = __ldcg(a.theta + blo + tid);
-        mf_cp_wait<0>();                                 // (also the prefetch of the next minibatch slice: long since landed)
+        if (L == 3) { mf_mbar_wait(&bar_w, par_w); par_w ^= 1u; }
         __syncthreads();
+        MF_MARK(7);
         const float *hl = h1r;                           // last hidden activations of this row
         if (L == 3) {
-            const int j = tid & 127, half = tid >> 7;
-            float acc = 0.0f;
-#pragma unroll 8
-            for (int k = half * 64; k < half * 64 + 64; ++k) acc = fmaf(h1r[k], W1s[k * MF_H + j], acc);
-            tmp[tid] = acc;
+            // h2 = act(h1 W1 + b1): thread (chunk j4 of 4 outputs, group of 16 k) -- a warp reads the 32 chunks of a row
+            const int j4 = tid & 31, kg = tid >> 5;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kg * 16 + i;
+                const float4 w = *reinterpret_cast<const float4 *>(W1s + k * MF_H + 4 * j4);
+                const float hv = h1r[k];
+                acc[0] = fmaf(hv, w.x, acc[0]); acc[1] = fmaf(hv, w.y, acc[1]);
+                acc[2] = fmaf(hv, w.z, acc[2]); acc[3] = fmaf(hv, w.w, acc[3]);
+            }
+            *reinterpret_cast<float4 *>(part8 + kg * MF_H + 4 * j4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             __syncthreads();
-            if (tid < MF_H) h2r[tid] = mq_act_apply(tmp[tid] + tmp[tid + 128] + b1s[tid], act1, leak1);
+            if (tid < MF_H) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) sum += part8[q8 * MF_H + tid];
+                h2r[tid] = mq_act_apply(sum + b1s[tid], act1, leak1);
+            }
             __syncthreads();
             hl = h2r;
         }
+        MF_MARK(8);
         for (int o = warp; o < n_out; o += MF_NT / 32) {  // logits: one warp per output
             float acc = 0.0f;
 #pragma unroll
@@ -242,18 +305,23 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
             if (lane == 0) lg[o] = acc + b2s[o];
         }
         __syncthreads();
-        if (tid < n_out) {                               // mnist/mlp.py:10-14: dy = onehot - softmax(out) - l2 out
-            float mx = lg[0];
-            for (int o = 1; o < n_out; ++o) mx = fmaxf(mx, lg[o]);
-            float sum = 0.0f;
-            for (int o = 0; o < n_out; ++o) sum += expf(lg[o] - mx);
-            const float inv = 1.0f / sum;
-            const int32_t row = a.idx[(int64_t)s * MF_B + g];
-            const float d = a.y[(int64_t)row * n_out + tid] - expf(lg[tid] - mx) * inv - a.l2 * lg[tid];
-            dyr[tid] = d;
-            a.dy[g * MF_NO + tid] = d;
+        MF_MARK(9);
+        if (warp == 0) {                                 // mnist/mlp.py:10-14: dy = onehot - softmax(out) - l2 out (lane = output)
+            const bool on = lane < n_out;
+            const float z = on ? lg[lane] : -INFINITY;
+            float mx = z;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float e = on ? expf(z - mx) : 0.0f;
+            const float sum = mq_warp_sum(e);
+            if (on) {
+                const float d = ylab - e * (1.0f / sum) - a.l2 * z;
+                dyr[lane] = d;
+                a.dy[g * MF_NO + lane] = d;
+            }
         }
         __syncthreads();
+        MF_MARK(10);
         if (tid < MF_H) {                                // gradient at the last hidden layer's pre-activation
             float acc = 0.0f;
             for (int o = 0; o < n_out; ++o) acc = fmaf(dyr[o], W2s[tid * n_out + o], acc);
@@ -263,15 +331,26 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
         }
         if (L == 3) {
             __syncthreads();
-            for (int k = warp * 16; k < warp * 16 + 16; ++k) {   // dh1[k] = act'(h1[k]) sum_j dh2[j] W1[k][j]: a warp per row of W1
+            MF_MARK(11);
+            {   // dh1[k] = act'(h1[k]) sum_j dh2[j] W1[k][j]: thread (k, half) walks half of row k in 16-byte chunks, starting at
+                // chunk k (rows are 512 bytes apart: eight consecutive k starting at the same chunk would share a bank group)
+                const int k = tid & 127, half = tid >> 7;
                 float acc = 0.0f;
-#pragma unroll
-                for (int j = lane; j < MF_H; j += 32) acc = fmaf(dh2r[j], W1s[k * MF_H + j], acc);
-                acc = mq_warp_sum(acc);
-                if (lane == 0) a.dh1[g * MF_H + k] = mq_act_grad(h1r[k], acc, act0, leak0);
+#pragma unroll 4
+                for (int i = half * 16; i < half * 16 + 16; ++i) {
+                    const int j4 = (i + k) & 31;
+                    const float4 w = *reinterpret_cast<const float4 *>(W1s + k * MF_H + 4 * j4);
+                    const float4 d = *reinterpret_cast<const float4 *>(dh2r + 4 * j4);
+                    acc = fmaf(d.x, w.x, acc); acc = fmaf(d.y, w.y, acc); acc = fmaf(d.z, w.z, acc); acc = fmaf(d.w, w.w, acc);
+                }
+                tmp[tid] = acc;
+                __syncthreads();
+                if (tid < MF_H) a.dh1[g * MF_H + tid] = mq_act_grad(h1r[tid], tmp[tid] + tmp[tid + 128], act0, leak0);
             }
         }
+        MF_MARK(4);
         mf_grid_barrier(a.bar, epoch);
+        MF_MARK(5);
 
         // ---- D: parameter gradients (batch mean, basicnet.py:219) + Adam, by owner ------------------------------------
         {   // operands of the three products
@@ -287,13 +366,18 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
             }
             for (int i = tid; i < MF_B * MF_NO / 4; i += MF_NT)
                 *reinterpret_cast<float4 *>(dys + 4 * i) = __ldcg(reinterpret_cast<const float4 *>(a.dy + 4 * i));
-            if (tid < MF_B) hcol[tid] = __ldcg((L == 3 ? a.h2 : h1g) + tid * MF_H + g);
+            if (tid < MF_B) {
+                hcol[tid] = __ldcg((L == 3 ? a.h2 : h1g) + tid * MF_H + g);
+                c1s[tid] = __ldcg(a.dh1 + tid * MF_H + g);
+                if (L == 3) c2s[tid] = __ldcg(a.dh2 + tid * MF_H + g);
+            }
         }
         __syncthreads();
+        MF_MARK(12);
         if (tid < 2 * kn) {                              // dW0[k][4 nh ..] = (1/B) sum_r x[r][k] dh1[r][..]
             const int k = tid >> 1, nh = (tid & 1) * 4;
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
+#pragma unroll 8
             for (int r = 0; r < MF_B; ++r) {
                 const float xv = xcur[r * MF_KW + k];
                 const float4 d = *reinterpret_cast<const float4 *>(d1s + r * MF_NS + nh);
@@ -309,10 +393,11 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
                 w0f[i] = (float)val;
             }
         }
+        MF_MARK(13);
         if (L == 3 && tid < 128) {                       // the 16 x 8 block of W1: dW1[k][j] = (1/B) sum_r h1[r][k] dh2[r][j]
             const int kk = tid >> 3, jj = tid & 7;
             float acc = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
             for (int r = 0; r < MF_B; ++r) acc = fmaf(hk[r * 16 + kk], dj[r * MF_NS + jj], acc);
             ST val = sW1[tid], mm = sW1[128 + tid], vv = sW1[256 + tid];
             mf_adam<ST>(val, mm, vv, acc * inv_b, c1, c2, lr, eps);
@@ -321,7 +406,7 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
         } else if (tid >= 128 && tid < 128 + n_out) {    // row g of the output layer: dW[g][o] = (1/B) sum_r hl[r][g] dy[r][o]
             const int o = tid - 128;
             float acc = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
             for (int r = 0; r < MF_B; ++r) acc = fmaf(hcol[r], dys[r * MF_NO + o], acc);
             ST val = sWl[o], mm = sWl[MF_NO + o], vv = sWl[2 * MF_NO + o];
             mf_adam<ST>(val, mm, vv, acc * inv_b, c1, c2, lr, eps);
@@ -330,7 +415,7 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
         } else if (tid >= 160 && tid < 192) {            // b1[g] = (1/B) sum_r dh2[r][g]  (one warp)
             if (L == 3) {
                 float acc = 0.0f;
-                for (int r = lane; r < MF_B; r += 32) acc += __ldcg(a.dh2 + r * MF_H + g);
+                for (int r = lane; r < MF_B; r += 32) acc += c2s[r];
                 acc = mq_warp_sum(acc);
                 if (lane == 0) {
                     ST val = sB1[0], mm = sB1[1], vv = sB1[2];
@@ -341,7 +426,7 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
             }
         } else if (tid >= 192 && tid < 224) {            // b0[g] = (1/B) sum_r dh1[r][g]  (one warp)
             float acc = 0.0f;
-            for (int r = lane; r < MF_B; r += 32) acc += __ldcg(a.dh1 + r * MF_H + g);
+            for (int r = lane; r < MF_B; r += 32) acc += c1s[r];
             acc = mq_warp_sum(acc);
             if (lane == 0) {
                 ST val = sB0[0], mm = sB0[1], vv = sB0[2];
@@ -359,6 +444,8 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
             a.theta[blo + o] = (float)val;
         }
         __syncthreads();
+        MF_MARK(6);
+        if (a.prof && tid == 0 && g == 0 && s == a.steps - 1) a.prof[15] = mf_now();
     }
 
     // ---- write the owned parameters and moments back -------------------------------------------------------------------
@@ -381,11 +468,13 @@ mlp_block_kernel(const __grid_constant__ MfArgs a) {
     }
 }
 
+long long *mq_phase_prof_ptr();
+
 static size_t mf_smem_bytes(size_t st) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t b = 0;
     b += r16(2 * MF_B * MF_KW * 4) + r16(MF_KW * MF_NS * 4) + r16(MF_H * MF_H * 4) + r16(MF_H * MF_NO * 4);
-    b += r16(MF_H * 4) + r16(MF_NO * 4) + 3 * r16(MF_H * 4) + r16(MF_NT * 4) + 2 * r16(MF_NO * 4);
+    b += r16(MF_H * 4) + r16(MF_NO * 4) + 3 * r16(MF_H * 4) + r16(MF_NT * 4) + r16(8 * MF_H * 4) + 2 * r16(MF_NO * 4);
     b += r16(3 * MF_KW * MF_NS * st) + r16(3 * st * 2) + r16(3 * 128 * st) + r16(3 * MF_NO * st) + r16(3 * st * 2) + r16(3 * MF_NO * st);
     return b;
 }
@@ -439,6 +528,7 @@ extern "C" int mq_mlp_train_block(const mq_net_t *net, float *theta, void *value
     a.dh1 = w; w += MF_B * MF_H;
     a.dy = w; w += MF_B * MF_NO;
     a.bar = (unsigned int *)w;
+    a.prof = mq_phase_prof_ptr();
     cudaError_t e = cudaMemsetAsync(a.bar, 0, 256, (cudaStream_t)stream);
     if (e != cudaSuccess) { mq_set_error("mq_mlp_train_block: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
     const size_t smem = mf_smem_bytes(state_dtype == MQ_F64 ? 8 : 4);

@@ -48,6 +48,9 @@ class MLPTrainer(object):
         self._fused_ws = torch.empty(max(self._fused_wsb, 16), dtype=torch.uint8, device=D.device())
         self.idx = torch.zeros(graph_steps * batch, dtype=torch.int32, device=D.device())
         self.coefs = torch.zeros(graph_steps * 4, dtype=torch.float64, device=D.device())
+        self._coef_pin = torch.zeros(graph_steps * 4, dtype=torch.float64).pin_memory()      # staging for the coefficient table
+        self._coef_ev = torch.cuda.Event()
+        self._coef_ev.record()
         self._graph, self._graph_data = None, None
         # parameter-gradient products on a side stream, overlapping the chain of activation gradients
         self._side = torch.cuda.Stream()
@@ -80,11 +83,13 @@ class MLPTrainer(object):
         assert steps <= self.graph_steps and idx_table.shape[1] == self.batch
         idx_d = idx_table if D.is_dev(idx_table) else D.from_host(np.ascontiguousarray(idx_table, np.int32))
         self.idx[:steps * self.batch].copy_(idx_d.reshape(-1), non_blocking=True)
-        co = np.zeros((self.graph_steps, 4))
+        self._coef_ev.synchronize()                        # the previous block's upload has left the staging buffer
+        co = self._coef_pin.numpy().reshape(self.graph_steps, 4)
         for s in range(steps):
             c1, c2 = self.opt.next_coefs()
             co[s] = (c1, c2, self.lr, 1e-8)
-        self.coefs.copy_(D.from_host(co.reshape(-1), np.float64), non_blocking=True)
+        self.coefs.copy_(self._coef_pin, non_blocking=True)
+        self._coef_ev.record()
         self.opt._out = None
         if self.fused:
             self._fused_steps(x, y, D.ptr(self.idx), D.ptr(self.coefs), steps)
@@ -144,9 +149,8 @@ class MLPTrainer(object):
         st["coef"].copy_(pc, non_blocking=True)
         st["ev"][slot].record()
         self.opt._out = None
-        if self.fused:
-            self._fused_steps(st["x"], st["y"], D.ptr(st["idx"]), D.ptr(st["coef"]), 1)
-            return
+        # (one step per call stays on the layered graph: a fused launch loads and stores the optimiser state of the whole net,
+        # which pays off over a block of steps, not over one -- 153 against 89 us per host-fed step)
         if st["graph"] is None:
             self._enqueue_step(st["x"], st["y"], 0, D.ptr(st["idx"]), D.ptr(st["coef"]))   # eager once (kernel attributes)
             torch.cuda.current_stream().synchronize()
