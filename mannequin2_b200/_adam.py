@@ -6,6 +6,8 @@ fused kernel (csrc/mq_adam.cu) replaces RunningMean.update x2 + update_rule +
 fp64 and follows the reference's operation order bit for bit; pass
 `state_dtype="float32"` for the 24 B/param fast variant.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -15,6 +17,7 @@ from ._lib import MQ_F32, MQ_F64
 
 class BaseTwoMoments(object):
     _adams = 0
+    _out_ref = None
 
     def __init__(self, value, *, horizon, var_horizon=100, print_norm=False, state_dtype="float64",
                  **global_params):
@@ -66,19 +69,36 @@ class BaseTwoMoments(object):
         gcode = MQ_F64 if g.dtype == torch.float64 else MQ_F32
         prev = self._value.clone() if self._print_norm else None
         c1, c2 = self.next_coefs()
+        self._out = None                          # (detaches a handle somebody still holds BEFORE the in-place update)
         D.call("mq_adam_step", D.ptr(self._value), D.ptr(self._m), D.ptr(self._v), D.ptr(self._theta32),
                D.ptr(g), self._n, self._code, gcode, c1, c2, lr, eps, self._adams, D.stream())
-        self._out = None
         if self._print_norm:
             add = D.to_host(self._value).astype(np.float64) - D.to_host(prev).astype(np.float64)
             print("Update norm: %10.4f" % np.sqrt(np.sum(np.square(add))))
 
     def get_value(self):
-        """The optimiser's value (read-only, like the reference's array); device backed."""
-        if self._out is None:
-            self._out = D.DeviceVector(self._value, self._shape)
-            self._out.f32 = self._theta32         # float32 mirror written by the same kernel
-        return self._out
+        """The optimiser's value (read-only, like the reference's array); device backed.  The reference returns an immutable
+        SNAPSHOT (value = value + add, _adam.py:47-53): a handle the caller still holds when the next step is applied is
+        detached onto a copy first (`_out = None`), so `old = get_value(); apply_gradient(g); old` still reads the old value."""
+        out = self._out
+        if out is None:
+            out = D.DeviceVector(self._value, self._shape)
+            out.f32 = self._theta32               # float32 mirror written by the same kernel
+            self._out_ref = weakref.ref(out)
+        return out
+
+    @property
+    def _out(self):
+        return self._out_ref() if self._out_ref is not None else None
+
+    @_out.setter
+    def _out(self, handle):
+        assert handle is None                     # the drivers invalidate the cached handle before they update in place
+        old = self._out_ref() if self._out_ref is not None else None
+        if old is not None and old._t is self._value:        # somebody still holds it: give it its own storage
+            old._t = self._value.clone()
+            old.f32 = self._theta32.clone()
+        self._out_ref = None
 
     # device handles for the fused drivers
     def state(self):

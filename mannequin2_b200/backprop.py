@@ -85,6 +85,9 @@ def multiply(a, b):
     elif endswith(ash, bsh):
         return _binary(a, b, 1), lambda g: (_binary(g, b, 1), _reduce_leading(g, a, bsh))
     elif endswith(bsh, ash):
+        # (a of lower rank: d/da = sum over the leading axes of g * b, d/db = g * a.  The reference, backprop.py:35-39, returns
+        # (sum(g * a), g * b) here -- the two factors swapped, which is not the derivative; this branch follows the mathematics
+        # and tests/test_host_logic.py pins the difference)
         return _binary(b, a, 1), lambda g: (_reduce_leading(g, b, ash), _binary(g, a, 1))
     raise ValueError("Invalid shapes: %s, %s" % (ash, bsh))
 

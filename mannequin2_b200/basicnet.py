@@ -189,6 +189,8 @@ class Input(Layer):
             self._grad_dev, self._grad_fn = self._grad_fn(), None
         if self._grad_dev is None:
             return None
+        if not D.is_dev(self._grad_dev):                 # a bare Input back-propagated with a host array: grad[:] (basicnet.py:94-99)
+            return _readonly(np.array(self._grad_dev, dtype=np.float32))
         return _readonly(D.to_host(self._grad_dev))
 
 

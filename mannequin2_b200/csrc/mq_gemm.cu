@@ -125,7 +125,7 @@ gemm_splitk_finish_kernel(GemmArgs g, const float *__restrict__ partial, int spl
     }
 }
 
-int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack, void *stream);      // mq_gemm_tma.cu
+int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, void *stream);        // mq_gemm_tma.cu (mode = planes | MQ_TC_FP16)
 int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes);
 
 // split-K of the tensor-core GEMM: products with few 128 x 128 output tiles and a long contraction (dW = x^T g)
@@ -175,7 +175,7 @@ static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, int32_t tc, void *st
         const int64_t pack_bytes = mq_gemm_tma_pack_bytes(g.m, g.n, g.k, planes);
         float *partials = (float *)((char *)ws + pack_bytes);
         if (splits > 1) gt.c = partials;
-        const int rc = mq_gemm_tma_launch(gt, planes, splits, ws, stream);
+        const int rc = mq_gemm_tma_launch(gt, planes | (tc & MQ_TC_FP16), splits, ws, stream);
         if (rc == MQ_OK) {
             if (splits > 1) {
                 int64_t nb = mq_ceil_div(g.m * g.n, MQ_NT);

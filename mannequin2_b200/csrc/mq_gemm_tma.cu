@@ -25,13 +25,39 @@
 //                  from the accumulator set the tensor pipe is NOT writing (two sets of 256 columns alternate), then
 //                  apply the epilogue.  P = 1 (plain bf16, error 2^-9 per operand) accumulates all of K in TMEM.
 // The precision modes are those of the fused kernel (include/mq_b200.h MQ_TC_*): 3 planes = fp32 products (the FFMA
-// bar), 2 planes = 16-bit operands, 1 plane = bf16.
+// bar), 2 planes = 16-bit operands, 1 plane = bf16; 2 planes with MQ_TC_FP16 = fp16 planes with the low one scaled by 2^11
+// (x = x0 + 2^-11 x1: fp32 operands to 2^-24, the FFMA bar again, in three plane pairs instead of six -- block 1 of an
+// accumulator set holds exactly the scaled pairs A_0 B_1' + A_1' B_0 and is folded in with one FMA by the owners).
 #include <cuda.h>
 
 #include "mq_gemm.cuh"
 #include "mq_tc.cuh"
 
 #ifndef MQ_EMU
+#include <cuda_fp16.h>
+
+#define GM_LOW_SCALE 2048.0f
+#define GM_LOW_UNSCALE 4.8828125e-4f
+
+// P words of packed 16-bit pairs from two values: bf16 planes (F = 0) or fp16 with the scaled low plane (F = 1, P = 2)
+template <int P, int F>
+__device__ __forceinline__ void gm_split_pair(float a, float b, uint32_t *w) {
+    if (F == 1) {
+        const __half2 h0 = __floats2half2_rn(a, b);
+        const float2 f0 = __half22float2(h0);
+        const __half2 h1 = __floats2half2_rn((a - f0.x) * GM_LOW_SCALE, (b - f0.y) * GM_LOW_SCALE);
+        w[0] = *reinterpret_cast<const uint32_t *>(&h0);
+        w[1] = *reinterpret_cast<const uint32_t *>(&h1);
+        return;
+    }
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[pl] = *reinterpret_cast<const uint32_t *>(&h);
+        a -= __uint_as_float(w[pl] << 16);
+        b -= __uint_as_float(w[pl] & 0xFFFF0000u);
+    }
+}
 
 #define GM_BM 128
 #define GM_BN 128
@@ -44,7 +70,7 @@
 // out[pl][r][k] (bf16, r < rows_pad, k < k_pad; zero outside the operand) = plane pl of src(r, k), where
 // src(r, k) = base[row(r) * rs + col(k) * cs] with an optional gather on the rows (idx_on_k = 0) or on k (idx_on_k = 1).
 // One thread converts 8 consecutive k of one row; lanes run along the unit-stride axis of the source.
-template <int P>
+template <int P, int F>
 __global__ void __launch_bounds__(MQ_NT)
 pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k,
                    int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad, int rows_fast, int64_t ones_row,
@@ -79,16 +105,7 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
     }
     uint32_t w[4][P];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a = v[2 * j], b = v[2 * j + 1];
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            w[j][pl] = *reinterpret_cast<const uint32_t *>(&h);
-            a -= __uint_as_float(w[j][pl] << 16);
-            b -= __uint_as_float(w[j][pl] & 0xFFFF0000u);
-        }
-    }
+    for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(v[2 * j], v[2 * j + 1], w[j]);
 #pragma unroll
     for (int pl = 0; pl < P; ++pl)
         *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + kc * 8) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
@@ -97,7 +114,7 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
 // The same for operands whose ROWS are the unit-stride axis of the source (A = x^T of dW = x^T g: src(r, k) = x[k][r]),
 // through a shared-memory tile: reads run along r (coalesced), writes along k (128 contiguous bytes per row and plane
 // instead of 16-byte pieces a whole packed row apart).  Tile = 32 rows x 64 k per CTA of 256 threads.
-template <int P>
+template <int P, int F>
 __global__ void __launch_bounds__(MQ_NT)
 pack_planes_t_kernel(const float *__restrict__ base, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k, int64_t rows,
                      int64_t k, int64_t rows_pad, int64_t k_pad, int64_t ones_row, __nv_bfloat16 *__restrict__ out) {
@@ -123,16 +140,7 @@ pack_planes_t_kernel(const float *__restrict__ base, int64_t cs, const int32_t *
     const int m = threadIdx.x >> 3, kc = threadIdx.x & 7;
     uint32_t w[4][P];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a = tile[kc * 8 + 2 * j][m], b = tile[kc * 8 + 2 * j + 1][m];
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            w[j][pl] = *reinterpret_cast<const uint32_t *>(&h);
-            a -= __uint_as_float(w[j][pl] << 16);
-            b -= __uint_as_float(w[j][pl] & 0xFFFF0000u);
-        }
-    }
+    for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(tile[kc * 8 + 2 * j][m], tile[kc * 8 + 2 * j + 1][m], w[j]);
     const int64_t r = r0 + m;
     if (r < rows_pad && k0 + kc * 8 < k_pad) {
 #pragma unroll
@@ -167,7 +175,7 @@ struct GmCfg {
     static constexpr int TMEM_COLS = P > 1 ? 512 : 128;
 };
 
-template <int P, bool SPLIT>
+template <int P, int F, bool SPLIT>
 __global__ void __launch_bounds__(GM_NT, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g,
                 int a_rows_pad, int b_rows_pad) {
@@ -225,7 +233,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp == 1) {
         // ---- MMA issuer --------------------------------------------------------------------------------------------
         const uint32_t hi = gm_desc_hi();
-        const uint32_t id2 = tc_idesc(GM_BM, 2 * GM_BN, 0, 0), id1 = tc_idesc(GM_BM, GM_BN, 0, 0);
+        const uint32_t id2 = tc_idesc_fmt(GM_BM, 2 * GM_BN, 0, 0, F), id1 = tc_idesc_fmt(GM_BM, GM_BN, 0, 0, F);
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c % Cfg::STAGES;
             const int blk = Cfg::FOLD ? c / GM_KBLOCK : 0, set = blk & 1;
@@ -276,7 +284,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_ld16(tl + set * 256 + q * 16, v);
                 if (Cfg::NB == 2) tc_ld16(tl + set * 256 + GM_BN + q * 16, w);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[q * 16 + j] += Cfg::NB == 2 ? v[j] + w[j] : v[j];
+                for (int j = 0; j < 16; ++j) acc[q * 16 + j] += Cfg::NB == 2 ? (F == 1 ? fmaf(w[j], GM_LOW_UNSCALE, v[j]) : v[j] + w[j]) : v[j];
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -349,25 +357,29 @@ int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes) {
     return mq_round_up(gm_pack_bytes(planes, m, k), 1024) + mq_round_up(gm_pack_bytes(planes, n, k), 1024) + 1024;
 }
 
-template <int P>
+template <int P, int F>
 static int gm_pack(const float *base, int64_t rs, int64_t cs, const int32_t *idx, int idx_on_k, int64_t rows, int64_t k,
                    int64_t ones_row, void *out, void *stream) {
     const int64_t rows_pad = mq_round_up(rows, 128), k_pad = mq_round_up(k, GM_BK);
     if (rs == 1 && cs != 1) {          // rows are the unit-stride axis: transpose through shared memory
         dim3 grid((unsigned)(rows_pad / 32), (unsigned)(k_pad / 64));
-        MQ_LAUNCH(pack_planes_t_kernel<P>, grid, MQ_NT, 0, stream, base, cs, idx, idx_on_k, rows, k, rows_pad, k_pad, ones_row,
+        auto kt = pack_planes_t_kernel<P, F>;
+        MQ_LAUNCH(kt, grid, MQ_NT, 0, stream, base, cs, idx, idx_on_k, rows, k, rows_pad, k_pad, ones_row,
                   (__nv_bfloat16 *)out);
         return MQ_OK;
     }
     const int64_t items = rows_pad * (k_pad / 8);
-    MQ_LAUNCH(pack_planes_kernel<P>, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, base, rs, cs, idx, idx_on_k, rows, k,
+    auto kp = pack_planes_kernel<P, F>;
+    MQ_LAUNCH(kp, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, base, rs, cs, idx, idx_on_k, rows, k,
               rows_pad, k_pad, 0, ones_row, (__nv_bfloat16 *)out);
     return MQ_OK;
 }
 
 // Launches pack + GEMM.  g.c points at the split-K partial buffer when splits > 1 (g.k_per_split a multiple of 64).
 // `pack` = workspace of mq_gemm_tma_pack_bytes() bytes.  MQ_ERR_UNSUPPORTED when tensor maps are not available.
-int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack, void *stream) {
+int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, void *stream) {
+    const int planes = mode & MQ_TC_PLANES_MASK, fmt = (mode & MQ_TC_FP16) ? 1 : 0;      // mode = planes | MQ_TC_FP16
+    if (fmt && planes != 2) return MQ_ERR_UNSUPPORTED;
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
     if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
@@ -377,14 +389,17 @@ int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack
     // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
     int rc;
     if (planes == 3) {
-        rc = gm_pack<3>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<3>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
+        rc = gm_pack<3, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<3, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
+    } else if (planes == 2 && fmt) {
+        rc = gm_pack<2, 1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<2, 1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     } else if (planes == 2) {
-        rc = gm_pack<2>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<2>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
+        rc = gm_pack<2, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<2, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     } else {
-        rc = gm_pack<1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
+        rc = gm_pack<1, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
+        rc = gm_pack<1, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
     }
     (void)rc;
     alignas(64) CUtensorMap map_a, map_b;
@@ -394,15 +409,22 @@ int mq_gemm_tma_launch(const GemmArgs &g, int planes, int64_t splits, void *pack
     }
     dim3 grid((unsigned)mq_ceil_div(g.n, GM_BN), (unsigned)mq_ceil_div(g.m, GM_BM), (unsigned)splits);
     cudaError_t e = cudaSuccess;
-#define GM_GO(P_, SP_)                                                                                                     \
+#define GM_GO(P_, F_, SP_)                                                                                                 \
     do {                                                                                                                   \
-        e = cudaFuncSetAttribute(gemm_tma_kernel<P_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
+        e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
         if (e == cudaSuccess)                                                                                              \
-            gemm_tma_kernel<P_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, (int)a_rows_pad, \
-                                                                                            (int)b_rows_pad);              \
+            gemm_tma_kernel<P_, F_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, (int)a_rows_pad, \
+                                                                                                (int)b_rows_pad);          \
     } while (0)
-    if (splits > 1) { if (planes == 3) GM_GO(3, true); else if (planes == 2) GM_GO(2, true); else GM_GO(1, true); }
-    else { if (planes == 3) GM_GO(3, false); else if (planes == 2) GM_GO(2, false); else GM_GO(1, false); }
+#define GM_GO_P(SP_)                                              \
+    do {                                                          \
+        if (planes == 3) GM_GO(3, 0, SP_);                        \
+        else if (planes == 2 && fmt) GM_GO(2, 1, SP_);            \
+        else if (planes == 2) GM_GO(2, 0, SP_);                   \
+        else GM_GO(1, 0, SP_);                                    \
+    } while (0)
+    if (splits > 1) GM_GO_P(true); else GM_GO_P(false);
+#undef GM_GO_P
 #undef GM_GO
     if (e != cudaSuccess) { mq_set_error("mq_gemm_tma: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
     return MQ_OK;

@@ -1163,13 +1163,13 @@ def case_discrete(B, batches=(64, 300, 9000)):
 
 
 # stated tolerances of the GEMM precision modes: |err| <= rtol |ref| + atol_scale max|ref|
-GEMM_MODE_TOL = {3: (1e-5, 2e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}
+GEMM_MODE_TOL = {3: (1e-5, 2e-6), 0x82: (1e-5, 2e-6), 2: (1e-4, 3e-5), 1: (5e-2, 2e-2)}      # 0x82: fp16x2 = the exact bar
 
 
 def case_gemm_tc(B):
     """TMA-fed tcgen05 GEMM for wide layers (mq_gemm_tma.cu), forced on per call (MQ_TC_FORCE): every operand layout,
     ragged sizes (rows, columns and K not multiples of the tiles), long contractions (split-K, the K = 128 accumulator
-    fold), the three precision modes at their stated tolerances; then the fused epilogues, row gather and split-K of the
+    fold), the precision modes (three bf16 planes, two scaled fp16 planes, two bf16 planes, one) at their stated tolerances; then the fused epilogues, row gather and split-K of the
     layered MLP path at the fp32 FFMA parity bar."""
     lib = B.lib
     rs = np.random.RandomState(41)
@@ -1192,7 +1192,7 @@ def case_gemm_tc(B):
                 hb = B.up(np.ascontiguousarray(b.T) if b_t else b)
                 a_rs, a_cs = (1, m) if a_t else (k, 1)
                 b_rs, b_cs = (1, k) if b_t else (n, 1)
-                for planes in (3, 2, 1):
+                for planes in (3, 0x82, 2, 1):
                     rtol, atol = GEMM_MODE_TOL[planes]
                     got = gemm(ha, a_rs, a_cs, hb, b_rs, b_cs, m, n, k, 0.5, F | planes)
                     close(got, want, rtol=rtol, atol_scale=atol, what="gemm_tma P=%d %dx%dx%d aT=%d bT=%d" % (planes, m, n, k, a_t, b_t))

@@ -994,6 +994,32 @@ def test_unmodified_script_loop_via_compat_alias():
     assert acc > 0.9, acc
     assert bar(100.0 * acc).startswith(" ")
 
+
+@pytest.mark.gpu
+def test_adam_get_value_is_a_snapshot():
+    """mannequin/_adam.py:47-53 hands out an immutable snapshot: a value handle kept across apply_gradient still reads the
+    OLD value (the device state is updated in place, so a held handle is detached onto its own copy first); a handle that
+    was dropped costs nothing; a bare Input back-propagated with a host array returns it (basicnet.py:94-99)."""
+    import mannequin2_b200.compat  # noqa: F401
+    from mannequin import Adam
+    from mannequin.basicnet import Input
+    rs = np.random.RandomState(3)
+    v0 = rs.randn(1000)
+    opt = Adam(v0, horizon=10, lr=0.01)
+    old = opt.get_value()
+    g = rs.randn(1000)
+    opt.apply_gradient(g)
+    new = opt.get_value()
+    assert np.allclose(np.asarray(old), v0) and not np.allclose(np.asarray(new), v0)
+    assert np.max(np.abs(np.asarray(new) - np.asarray(old))) > 1e-3
+    held = opt.get_value()
+    opt.apply_gradient(g)
+    assert np.array_equal(np.asarray(held), np.asarray(new))
+    inp = Input(3)
+    out, backprop = inp.evaluate(np.ones((2, 3), np.float32))
+    backprop(np.full((2, 3), 2.0, np.float32))
+    assert np.array_equal(inp.last_gradient, np.full((2, 3), 2.0, np.float32))
+
 @pytest.mark.gpu
 def test_mlp_fused_block_matches_oracle_and_reference_run():
     """csrc/mq_mlp_fused.cu -- a block of mnist/mlp.py:31-35 steps as ONE persistent launch (batch 128): against the oracle's

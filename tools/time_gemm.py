@@ -38,7 +38,7 @@ for name, m, n, k, a_t, b_t in shapes:
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     fl = 2.0 * m * n * k
     line = "%-28s" % name
-    for tc, nm in ((3, "exact"), (2, "bf16x2"), (1, "bf16"), (L.TC_OFF, "ffma")):
+    for tc, nm in ((3, "exact"), (0x82, "fp16x2"), (2, "bf16x2"), (1, "bf16"), (L.TC_OFF, "ffma")):
         ms = timeit(lambda: D.call("mq_gemm_ex", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, tc, D.ptr(ws), wsb,
                                    D.stream()))
         line += "  %s %.1f us = %.0f TF" % (nm, ms * 1e3, fl / ms / 1e9)
