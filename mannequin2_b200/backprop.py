@@ -92,6 +92,25 @@ def multiply(a, b):
     raise ValueError("Invalid shapes: %s, %s" % (ash, bsh))
 
 
+# Operand format of the LARGE matmul products (the TMA-fed tcgen05 GEMM): 0 = three bf16 planes (exact, any range); trainers
+# whose operands are bounded (images, tanh activations, clipped log-deviations) select "fp16x2" for their own steps -- the
+# same fp32 bar in half the tensor work, operands must stay below 65504 (include/mq_b200.h, MQ_TC_FP16).
+_GEMM_TC = [0]
+
+
+class gemm_mode(object):
+    """with gemm_mode("fp16x2"): ... -- operand format of the large matmul products evaluated inside the block."""
+
+    def __init__(self, mode):
+        self.tc = D._lib.TC_MODES[mode] if mode != "exact" else 0
+
+    def __enter__(self):
+        self.prev, _GEMM_TC[0] = _GEMM_TC[0], self.tc
+
+    def __exit__(self, *exc):
+        _GEMM_TC[0] = self.prev
+
+
 def _gemm(a, a_rs, a_cs, b, b_rs, b_cs, m, n, k, like):
     c = _new((m, n), like)
     if m * n * k >= (1 << 26) or (k >= 1024 and m * n <= (1 << 22)):
@@ -99,7 +118,8 @@ def _gemm(a, a_rs, a_cs, b, b_rs, b_cs, m, n, k, like):
         # contraction (dW = x^T g over a large batch): split along K
         wsb = int(D._lib.lib().mq_gemm_ws_bytes(m, n, k))
         ws = D.workspace("gemm", wsb)
-        D.call("mq_gemm_ws", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.ptr(ws), wsb, D.stream())
+        D.call("mq_gemm_ex", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, _GEMM_TC[0], D.ptr(ws), wsb,
+               D.stream())
     else:
         D.call("mq_gemm", D.ptr(a), a_rs, a_cs, D.ptr(b), b_rs, b_cs, D.ptr(c), m, n, k, 1.0, D.stream())
     return c

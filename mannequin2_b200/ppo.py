@@ -310,10 +310,12 @@ class PPOUpdater(object):
         # gradient launch with each net on half of the SMs and one reduce / exchange / Adam launch for both (csrc/mq_tc3.cu,
         # csrc/mq_step.cu) -- in one stream, hence in one fixed order on every rank.  MQ_PPO_UNPAIRED=1: the two chains apart.
         # Pairing pays while a net has about one tile per SM (a launch is then one tile's chain of dependent phases long
-        # whatever the row count: 5.45 against 9.83 ms per update at 8,192 rows per GPU); with several tiles per SM each net
-        # is faster on all SMs by itself (12.2 against 13.1 ms at 65,536 rows).  MQ_PPO_PAIRED=1 / MQ_PPO_UNPAIRED=1 force.
+        # whatever the row count: 5.2 against 8.1 ms per update at 16,384 rows per GPU) and whenever the two chains have to
+        # share a stream anyway (sharded: 7.0 against 9.4 ms at 32,768 rows per GPU).  On ONE GPU with several tiles per SM the
+        # two chains side by side on two streams, each kernel on all SMs, are faster (12.2 against 13.1 ms at 65,536 rows).
+        # MQ_PPO_PAIRED=1 / MQ_PPO_UNPAIRED=1 force either form.
         paired = (v_mb >= 8192 and v_mb == p_mb and v_steps == p_steps and val.code == pol.code and
-                  (v_mb <= PAIR_MAX_ROWS or os.environ.get("MQ_PPO_PAIRED")) and not os.environ.get("MQ_PPO_UNPAIRED"))
+                  (v_mb <= PAIR_MAX_ROWS or world > 1 or os.environ.get("MQ_PPO_PAIRED")) and not os.environ.get("MQ_PPO_UNPAIRED"))
         big = v_mb >= 8192 or p_mb >= 8192
         if big:
             val.pack(obs, ret, None, None, n)

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _device as D
+from .backprop import gemm_mode
 from .basicnet import Affine, Function, Input, Tanh
 from .distrib import Gauss
 
@@ -61,7 +62,11 @@ class VAETrainer(object):
     """mnist/vae.py:39-71 with the layer sizes as arguments (script: image (28, 28), hidden 256, latent 3;
     BASELINE configs[4]: hidden 400, latent 20, batch 4096)."""
 
-    def __init__(self, image_shape=(28, 28), hidden=256, latent=3, n_hidden=2, lr=1e-3, rng=None):
+    def __init__(self, image_shape=(28, 28), hidden=256, latent=3, n_hidden=2, lr=1e-3, rng=None, gemm_mode="fp16x2"):
+        # gemm_mode: operand format of the batch-4096-sized Affine products on the tcgen05 GEMM.  "fp16x2" meets the same fp32
+        # bar as "exact" (three bf16 planes) in half the tensor work; its range precondition (|operand| < 65504) holds for
+        # images, tanh activations, clipped log-deviations and their gradients.
+        self.gemm_mode = gemm_mode
         enc = Input(*image_shape)
         for _ in range(n_hidden):
             enc = Tanh(Affine(enc, hidden))
@@ -78,10 +83,11 @@ class VAETrainer(object):
     def step(self, inps):
         """One iteration of vae.py:57-71 on a batch of images; returns (mean logprob, mean DKL)."""
         n = len(inps)
-        logprob, backprop = self.decoder.logprob.evaluate(inps, sample=inps)
-        grad1 = D.as_dev_f32(backprop(np.ones(n, np.float32)))
-        dkl_value, backprop = self.dkl.evaluate(inps)
-        grad2 = D.as_dev_f32(backprop(-np.ones(n, np.float32)))
+        with gemm_mode(self.gemm_mode):
+            logprob, backprop = self.decoder.logprob.evaluate(inps, sample=inps)
+            grad1 = D.as_dev_f32(backprop(np.ones(n, np.float32)))
+            dkl_value, backprop = self.dkl.evaluate(inps)
+            grad2 = D.as_dev_f32(backprop(-np.ones(n, np.float32)))
         flat = self.decoder.logprob._flat                              # encoder parameters first (vae.py:66)
         if self.momentum is None:
             self.momentum = D.zeros(self.n_params)
@@ -104,10 +110,11 @@ class VAETrainer(object):
         if getattr(self, "_ones", None) is None or self._ones.numel() != n:
             self._ones = torch.ones(n, dtype=torch.float32, device=x_dev.device)
             self._minus = -self._ones
-        logprob, backprop = self.decoder.logprob.evaluate_dev(x_dev, sample=x_dev)
-        grad1 = D.as_dev_f32(backprop(self._ones))
-        dkl_value, backprop = self.dkl.evaluate_dev(x_dev)
-        grad2 = D.as_dev_f32(backprop(self._minus))
+        with gemm_mode(self.gemm_mode):
+            logprob, backprop = self.decoder.logprob.evaluate_dev(x_dev, sample=x_dev)
+            grad1 = D.as_dev_f32(backprop(self._ones))
+            dkl_value, backprop = self.dkl.evaluate_dev(x_dev)
+            grad2 = D.as_dev_f32(backprop(self._minus))
         flat = self.decoder.logprob._flat
         assert flat is not None, "step_dev needs the parameters in one arena slice"
         if self.momentum is None:
