@@ -823,11 +823,11 @@ class ESWorkload(object):
 
 class VAEWorkload(object):
     """BASELINE.json configs[4]: mnist/vae.py step at the BASELINE shape -- encoder 784-400-(20+20), decoder
-    20-400-(784+784), Gaussian reparameterisation, batch 4096 -- through the layer graph (mannequin2_b200/vae.py):
-    two evaluations of the shared graph + clipped-momentum ascent (vae.py:57-71).  Its Affine layers are matmul nodes ->
-    mq_gemm -> the tcgen05 GEMM.  `value`: batch resident on the device, the ~110 launches of the step replayed as ONE CUDA
-    graph, sampling noise from the device Philox generator (VAETrainer.step_graph).  `e2e`: the batch comes from pinned
-    host memory every step (12.8 MB) and the step's mean log-likelihood / DKL are read back."""
+    20-400-(784+784), Gaussian reparameterisation, batch 4096 -- as the fused plan of csrc/mq_vae.cu (mq_vae_step: one
+    forward and one backward pass for the two evaluations of vae.py:57-66, every product on the TMA-fed tcgen05 GEMM with
+    its operands kept as packed fp16x2 planes, clipped-momentum ascent).  `value`: batch resident on the device, the step
+    replayed as ONE CUDA graph, sampling noise from the device Philox generator (VAETrainer.step_graph).  `e2e`: the batch
+    comes from pinned host memory every step (12.8 MB) and the step's mean log-likelihood / DKL are read back."""
     name = "vae_784-400-20-400-784_batch4096 (configs[4])"
     metric = "vae_step_samples_per_s"
     unit = "samples/s"
@@ -862,7 +862,9 @@ class VAEWorkload(object):
         t.cuda.current_stream().synchronize()
 
     def launches_per_step(self):
-        return 110                                   # node-by-node graph: forward + backprop kernels of two evaluations
+        # fused plan (csrc/mq_vae.cu, one hidden layer per side): 5 packs, 9 products, 4 split-K dW products + their 4
+        # finishes, latent forward / backward, head, momentum step = 24 kernels of this library + the Philox draw
+        return 25
 
     def dominant_kernel(self, peaks):
         """pack + gemm_tma_kernel on the widest layer (4096 x 784 x 400, y = x W), timed alone."""

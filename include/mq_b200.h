@@ -417,6 +417,34 @@ int mq_gauss_entropy(const float *logstd, const float *g, int64_t rows, int64_t 
 /* mnist/vae.py:64-69: g = g1 (+ g2 on the first n2 entries); mom = clip(decay*mom + (1-decay)*g, +-clip); theta += lr*mom */
 int mq_momentum_step(float *theta, float *mom, const float *g1, const float *g2, int64_t n2, int64_t n, float decay,
                      float clip, float lr, void *stream);
+/* ---- fused training step of mnist/vae.py (csrc/mq_vae.cu) -------------------------------------------------------------
+ * Replaces, for the net of /root/reference/mnist/vae.py:39-55 (n_hidden tanh layers of `hidden` units per side, `latent`
+ * Gaussian heads, clipped log-deviations), the two graph evaluations and the update of vae.py:57-71:
+ *     logprob, bp = decoder.logprob.evaluate(x, sample=x); grad1 = bp(ones)          (vae.py:60-61)
+ *     dkl, bp = dkl.evaluate(x);                           grad2 = bp(-ones)         (vae.py:63-64)
+ *     grad1[:len(grad2)] += grad2; momentum = clip(0.9 momentum + 0.1 grad1, -1, 1); theta += 0.001 momentum
+ * as one forward and one backward pass (the two upstream gradients meet at the encoder heads; every product on the TMA-fed
+ * tcgen05 GEMM with its operands kept as packed planes between products).  theta is the flat parameter vector of
+ * decoder.logprob (basicnet.py:66-77 order: encoder hidden (W, b) ..., W_mean, b_mean, W_logstd, b_logstd, decoder hidden
+ * (W, b) ..., W_mean, b_mean, W_logstd, b_logstd); x is [batch, d_img] row-major; unit is the N(0,1) draw of
+ * distrib.py:49 for the latent sample, [batch, latent].  hidden % 8 == 0, 1 <= n_hidden <= 4, else MQ_ERR_UNSUPPORTED. */
+typedef struct mq_vae_t {
+    int64_t batch, d_img, hidden, latent;
+    int32_t n_hidden;          /* tanh layers per side (vae.py: 2; BASELINE configs[4]: 1)                         */
+    int32_t tc;                /* operand format, MQ_TC_* planes (| MQ_TC_FP16); 0 = fp16x2 (fp32 products)        */
+    float   clip_lo, clip_hi;  /* Clip of both logstd heads (vae.py:43,54: -6, 0)                                  */
+} mq_vae_t;
+int64_t mq_vae_n_params(const mq_vae_t *v);                                        /* < 0: bad descriptor */
+int64_t mq_vae_ws_bytes(const mq_vae_t *v);
+/* once per workspace, before the first step (zeroes the padding of every plane image, writes the bias-gradient rows) */
+int mq_vae_ws_init(const mq_vae_t *v, void *ws, int64_t ws_bytes, void *stream);
+/* grad[n_params] = grad1 with grad2 added onto the encoder slice; logprob[batch], dkl[batch] the two values */
+int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x, const float *unit, float *grad, float *logprob,
+                float *dkl, void *ws, int64_t ws_bytes, void *stream);
+/* the whole iteration: mq_vae_grad, then mq_momentum_step(theta, mom, grad, ...) */
+int mq_vae_step(const mq_vae_t *v, float *theta, float *mom, const float *x, const float *unit, float *grad, float *logprob,
+                float *dkl, float decay, float clip, float lr, void *ws, int64_t ws_bytes, void *stream);
+
 /* categorical log-prob (mannequin/distrib.py:24-32): logp[r] = log softmax(logits[r])[sample[r]] and / or
  * d_logits[r] = g[r] * (onehot(sample[r]) - softmax(logits[r])); g is only read when d_logits != NULL */
 int mq_discrete_logprob(const float *logits, const int32_t *sample, const float *g, int64_t rows, int64_t n,

@@ -40,6 +40,12 @@ TC_MODE_BITS = 0x83
 TC_MODES = {"exact": 3, "bf16x3": 3, "fp16x2": 2 | TC_FP16, "bf16x2": 2, "bf16": 1}
 
 
+class MqVae(ctypes.Structure):
+    """mq_vae_t: the net of mnist/vae.py for the fused step (csrc/mq_vae.cu)."""
+    _fields_ = [("batch", c_int64), ("d_img", c_int64), ("hidden", c_int64), ("latent", c_int64), ("n_hidden", c_int32),
+                ("tc", c_int32), ("clip_lo", c_float), ("clip_hi", c_float)]
+
+
 class MqEnv(ctypes.Structure):
     """mq_env_t: the synthetic on-device environment of the rollout kernels."""
     _fields_ = [("d", c_int32), ("a", c_int32), ("horizon", c_int32), ("dt", c_float), ("damp", c_float),
@@ -158,6 +164,11 @@ SIGNATURES = {
     "mq_discrete_logprob": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
     "mq_momentum_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, P]),
     "mq_onehot": (c_int, [P, c_int64, c_int64, P, P]),
+    "mq_vae_n_params": (c_int64, [P]),
+    "mq_vae_ws_bytes": (c_int64, [P]),
+    "mq_vae_ws_init": (c_int, [P, P, c_int64, P]),
+    "mq_vae_grad": (c_int, [P, P, P, P, P, P, P, P, c_int64, P]),
+    "mq_vae_step": (c_int, [P, P, P, P, P, P, P, P, c_float, c_float, c_float, P, c_int64, P]),
     "mq_gauss_sample": (c_int, [P, P, c_int64, P, c_int64, c_int64, P, P, P]),
     "mq_dkl_forward": (c_int, [P, P, c_int64, c_int64, P, P]),
     "mq_dkl_backward": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),

@@ -23,6 +23,35 @@ struct GemmArgs {
                              // one more output row: W and b are adjacent in the flat parameter vector).
 };
 
+// Optional second outputs of the tcgen05 GEMM (mq_gemm_tma.cu): the epilogue's values written ALSO as operand planes,
+// in the kernel's own operand format, so that the next product of a fused plan (csrc/mq_vae.cu) reads them with TMA
+// instead of a pack launch over an fp32 copy.  The destination buffers are zero outside what is written here.
+struct GmEmit {
+    void *out_k; int64_t k_rows_pad, k_kpad;     // planes of C as a K-major operand:  [plane][k_rows_pad][k_kpad], element (m, n)
+    void *out_t; int64_t t_rows_pad, t_kpad;     // planes of C^T (operand of dW = x^T g): [plane][t_rows_pad][t_kpad], element (n, m)
+    int64_t ldc;                                 // row stride of g.c (0 = g.n); g.c may be NULL when only planes are wanted
+};
+
+// One operand-packing job of mq_gemm_tma_pack_multi: fp32 source -> planes, written at an offset of a larger plane image
+// (two sources side by side make the [W_mean | W_logstd] operands of the VAE heads).
+struct GmPackJob {
+    const float *base; int64_t rs, cs;           // src(r, k) = base[row(r) * rs + col(k) * cs]
+    const int32_t *idx; int idx_on_k;            // optional gather on the rows (0) or on k (1)
+    int64_t rows, k;                             // extents of the source
+    int64_t ones_row;                            // > 0: rows ones_row <= r < rows read as 1.0 (bias-gradient row of dW)
+    int64_t rows_cover, k_cover;                 // extents WRITTEN (zero outside the source); k_cover % 8 == 0
+    int64_t rows_pad, k_pad;                     // geometry of a destination plane
+    int64_t row_off, k_off;                      // offsets inside the destination plane (k_off % 8 == 0)
+    void *out;
+    unsigned block0, blocks;                     // filled in by the launcher
+};
+#define GM_MAX_PACK_JOBS 20
+
+int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes);
+int mq_gemm_tma_pack_multi(GmPackJob *jobs, int n_jobs, int mode, void *stream);
+int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64_t b_rows_pad, int64_t k_pad,
+                       const GemmArgs &g, const GmEmit &em, int mode, int64_t splits, void *stream);
+
 __device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int64_t m, int64_t n) {
     if (g.epi == EPI_BIAS_ACT) return mq_act_apply(acc + g.bias[n], g.act, g.leak);
     if (g.epi == EPI_ACT_GRAD) return mq_act_grad(g.y[m * g.n + n], acc, g.act, g.leak);

@@ -67,30 +67,31 @@ __device__ __forceinline__ void gm_split_pair(float a, float b, uint32_t *w) {
 #define GM_KBLOCK 2                    // stages per TMEM accumulation block (K = 128)
 
 // ---- operand packing -------------------------------------------------------------------------------------------
-// out[pl][r][k] (bf16, r < rows_pad, k < k_pad; zero outside the operand) = plane pl of src(r, k), where
-// src(r, k) = base[row(r) * rs + col(k) * cs] with an optional gather on the rows (idx_on_k = 0) or on k (idx_on_k = 1).
-// One thread converts 8 consecutive k of one row; lanes run along the unit-stride axis of the source.
+// A job (GmPackJob, mq_gemm.cuh) writes out[pl][row_off + r][k_off + k] (bf16 / fp16; r < rows_cover, k < k_cover; zero
+// outside the source) = plane pl of src(r, k), where src(r, k) = base[row(r) * rs + col(k) * cs] with an optional gather on
+// the rows (idx_on_k = 0) or on k (idx_on_k = 1).  A whole operand is one job with cover = (rows_pad, k_pad) and no offsets.
+//
+// Plain form: one thread converts 8 consecutive k of one row; lanes run along the unit-stride axis of the source.
 template <int P, int F>
-__global__ void __launch_bounds__(MQ_NT)
-pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k,
-                   int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad, int rows_fast, int64_t ones_row,
-                   __nv_bfloat16 *__restrict__ out) {
-    const int64_t kc_n = k_pad / 8;
-    const int64_t item = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
-    if (item >= rows_pad * kc_n) return;
+__device__ __forceinline__ void gm_pack_plain(const GmPackJob &jb, int rows_fast, int64_t item) {
+    const int64_t kc_n = jb.k_cover / 8;
+    if (item >= jb.rows_cover * kc_n) return;
     int64_t r, kc;
-    if (rows_fast) { kc = item / rows_pad; r = item - kc * rows_pad; }
+    if (rows_fast) { kc = item / jb.rows_cover; r = item - kc * jb.rows_cover; }
     else { r = item / kc_n; kc = item - r * kc_n; }
+    const float *__restrict__ base = jb.base;
+    const int32_t *__restrict__ idx = jb.idx;
+    const int64_t rs = jb.rs, cs = jb.cs, k = jb.k;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-    if (ones_row > 0 && r >= ones_row && r < rows) {         // rows that read as 1.0 (the bias-gradient row of dW = x^T g)
+    if (jb.ones_row > 0 && r >= jb.ones_row && r < jb.rows) {   // rows that read as 1.0 (the bias-gradient row of dW = x^T g)
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (kc * 8 + j < k) ? 1.0f : 0.0f;
-    } else if (r < rows) {
-        const int64_t sr = (idx && !idx_on_k) ? (int64_t)idx[r] : r;
+    } else if (r < jb.rows) {
+        const int64_t sr = (idx && !jb.idx_on_k) ? (int64_t)idx[r] : r;
         const int64_t k0 = kc * 8;
-        if (cs == 1 && !(idx && idx_on_k) && k0 + 8 <= k && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(rs * 4)) & 15) == 0) {
+        if (cs == 1 && !(idx && jb.idx_on_k) && k0 + 8 <= k && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(rs * 4)) & 15) == 0) {
             const float4 lo = __ldg(reinterpret_cast<const float4 *>(base + sr * rs + k0));
             const float4 hi = __ldg(reinterpret_cast<const float4 *>(base + sr * rs + k0) + 1);
             v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
@@ -98,7 +99,7 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (k0 + j < k) {
-                    const int64_t sk = (idx && idx_on_k) ? (int64_t)idx[k0 + j] : k0 + j;
+                    const int64_t sk = (idx && jb.idx_on_k) ? (int64_t)idx[k0 + j] : k0 + j;
                     v[j] = __ldg(base + sr * rs + sk * cs);
                 }
         }
@@ -106,32 +107,34 @@ pack_planes_kernel(const float *__restrict__ base, int64_t rs, int64_t cs, const
     uint32_t w[4][P];
 #pragma unroll
     for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(v[2 * j], v[2 * j + 1], w[j]);
+    __nv_bfloat16 *out = (__nv_bfloat16 *)jb.out;
 #pragma unroll
     for (int pl = 0; pl < P; ++pl)
-        *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + kc * 8) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+        *reinterpret_cast<uint4 *>(out + ((int64_t)pl * jb.rows_pad + jb.row_off + r) * jb.k_pad + jb.k_off + kc * 8) =
+            make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
 }
 
-// The same for operands whose ROWS are the unit-stride axis of the source (A = x^T of dW = x^T g: src(r, k) = x[k][r]),
-// through a shared-memory tile: reads run along r (coalesced), writes along k (128 contiguous bytes per row and plane
-// instead of 16-byte pieces a whole packed row apart).  Tile = 32 rows x 64 k per CTA of 256 threads.
+// Transposing form for operands whose ROWS are the unit-stride axis of the source (A = x^T of dW = x^T g: src(r, k) = x[k][r];
+// B = W of y = x W), through a shared-memory tile: reads run along r (coalesced), writes along k (128 contiguous bytes per
+// row and plane instead of 16-byte pieces a whole packed row apart).  Tile = 32 rows x 64 k per CTA of 256 threads; the
+// source is addressed as base[row(r) + col(k) * cs].
 template <int P, int F>
-__global__ void __launch_bounds__(MQ_NT)
-pack_planes_t_kernel(const float *__restrict__ base, int64_t cs, const int32_t *__restrict__ idx, int idx_on_k, int64_t rows,
-                     int64_t k, int64_t rows_pad, int64_t k_pad, int64_t ones_row, __nv_bfloat16 *__restrict__ out) {
-    __shared__ float tile[64][33];
-    const int64_t r0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 64;
+__device__ __forceinline__ void gm_pack_transposed(const GmPackJob &jb, int64_t bx, int64_t by, float (*tile)[33]) {
+    const float *__restrict__ base = jb.base;
+    const int32_t *__restrict__ idx = jb.idx;
+    const int64_t r0 = bx * 32, k0 = by * 64;
     const int tr = threadIdx.x & 31, tk = threadIdx.x >> 5;
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
         const int kk = pass * 8 + tk;
         const int64_t r = r0 + tr, kg = k0 + kk;
         float v = 0.0f;
-        if (r < rows && kg < k) {
-            if (ones_row > 0 && r >= ones_row) v = 1.0f;
+        if (r < jb.rows && kg < jb.k) {
+            if (jb.ones_row > 0 && r >= jb.ones_row) v = 1.0f;
             else {
-                const int64_t sr = (idx && !idx_on_k) ? (int64_t)idx[r] : r;
-                const int64_t sk = (idx && idx_on_k) ? (int64_t)idx[kg] : kg;
-                v = __ldg(base + sr + sk * cs);
+                const int64_t sr = (idx && !jb.idx_on_k) ? (int64_t)idx[r] : r;
+                const int64_t sk = (idx && jb.idx_on_k) ? (int64_t)idx[kg] : kg;
+                v = __ldg(base + sr + sk * jb.cs);
             }
         }
         tile[kk][tr] = v;
@@ -142,11 +145,38 @@ pack_planes_t_kernel(const float *__restrict__ base, int64_t cs, const int32_t *
 #pragma unroll
     for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(tile[kc * 8 + 2 * j][m], tile[kc * 8 + 2 * j + 1][m], w[j]);
     const int64_t r = r0 + m;
-    if (r < rows_pad && k0 + kc * 8 < k_pad) {
+    __nv_bfloat16 *out = (__nv_bfloat16 *)jb.out;
+    if (r < jb.rows_cover && k0 + kc * 8 < jb.k_cover) {
 #pragma unroll
         for (int pl = 0; pl < P; ++pl)
-            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * rows_pad + r) * k_pad + k0 + kc * 8) =
+            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * jb.rows_pad + jb.row_off + r) * jb.k_pad + jb.k_off + k0 + kc * 8) =
                 make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+    }
+}
+
+static inline bool gm_job_transposed(const GmPackJob &jb) { return jb.rs == 1 && jb.cs != 1; }
+static inline unsigned gm_job_blocks(const GmPackJob &jb) {
+    if (gm_job_transposed(jb)) return (unsigned)(mq_ceil_div(jb.rows_cover, 32) * mq_ceil_div(jb.k_cover, 64));
+    return (unsigned)mq_ceil_div(jb.rows_cover * (jb.k_cover / 8), MQ_NT);
+}
+
+// Up to GM_MAX_PACK_JOBS jobs in ONE launch (the weights of a whole net and its input batch, csrc/mq_vae.cu): a block
+// finds its job by the block ranges the launcher filled in.
+struct GmPackJobs { int n; GmPackJob job[GM_MAX_PACK_JOBS]; };
+
+template <int P, int F>
+__global__ void __launch_bounds__(MQ_NT)
+pack_jobs_kernel(const __grid_constant__ GmPackJobs jobs) {
+    __shared__ float tile[64][33];
+    int j = 0;
+    while (j + 1 < jobs.n && blockIdx.x >= jobs.job[j + 1].block0) ++j;
+    const GmPackJob &jb = jobs.job[j];
+    const int64_t local = (int64_t)blockIdx.x - jb.block0;
+    if (jb.rs == 1 && jb.cs != 1) {
+        const int64_t nbx = (jb.rows_cover + 31) / 32;
+        gm_pack_transposed<P, F>(jb, local % nbx, local / nbx, tile);
+    } else {
+        gm_pack_plain<P, F>(jb, 0, local * MQ_NT + threadIdx.x);
     }
 }
 
@@ -177,7 +207,7 @@ struct GmCfg {
 
 template <int P, int F, bool SPLIT>
 __global__ void __launch_bounds__(GM_NT, 1)
-gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g,
+gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g, GmEmit em,
                 int a_rows_pad, int b_rows_pad) {
     using Cfg = GmCfg<P>;
     extern __shared__ unsigned char smem_raw[];
@@ -297,16 +327,68 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 64; ++j) stage[lane * 65 + j] = acc[j];
         __syncwarp();
+        const bool emit = !SPLIT && (em.out_k != nullptr || em.out_t != nullptr);
+        const int64_t ldc = em.ldc > 0 ? em.ldc : g.n;
         for (int r = 0; r < 32; ++r) {
             const int64_t gm = m0 + quarter * 32 + r;
-            if (gm >= g.m) break;
+            if (gm >= g.m && !emit) break;
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
                 const int64_t gn = n0 + half * 64 + hc * 32 + lane;
-                if (gn >= g.n) continue;
-                const float v = stage[r * 65 + hc * 32 + lane];
-                if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
-                else g.c[gm * g.n + gn] = gemm_epilogue(g, v, gm, gn);
+                float v = 0.0f;
+                if (gm < g.m && gn < g.n) {
+                    v = stage[r * 65 + hc * 32 + lane];
+                    if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
+                    else {
+                        v = gemm_epilogue(g, v, gm, gn);
+                        if (g.c) g.c[gm * ldc + gn] = v;
+                    }
+                }
+                if (emit) stage[r * 65 + hc * 32 + lane] = v;      // the epilogue's value, zero outside C
+            }
+        }
+        if (emit) {
+            // the same values as operand planes of the NEXT product (GmEmit, mq_gemm.cuh)
+            __syncwarp();
+            if (em.out_k) {            // C as a K-major operand: a lane converts 8 consecutive columns of one row
+                __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_k;
+                const int r4 = lane >> 3, ch = lane & 7;
+                const int64_t gn0 = n0 + half * 64 + ch * 8;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + r4;
+                    const int64_t gm = m0 + quarter * 32 + r;
+                    if (gm < g.m && gn0 < g.n) {
+                        uint32_t w[4][P];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(stage[r * 65 + ch * 8 + 2 * j], stage[r * 65 + ch * 8 + 2 * j + 1], w[j]);
+#pragma unroll
+                        for (int pl = 0; pl < P; ++pl)
+                            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.k_rows_pad + gm) * em.k_kpad + gn0) =
+                                make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                    }
+                }
+            }
+            if (em.out_t) {            // C^T: a lane owns a column and converts its 32 rows, 8 at a time
+                __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_t;
+                const int64_t gm0 = m0 + quarter * 32;
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    const int64_t gn = n0 + half * 64 + hc * 32 + lane;
+                    if (gn >= g.n) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (gm0 + q * 8 >= em.t_kpad) continue;
+                        uint32_t w[4][P];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            gm_split_pair<P, F>(stage[(q * 8 + 2 * j) * 65 + hc * 32 + lane], stage[(q * 8 + 2 * j + 1) * 65 + hc * 32 + lane], w[j]);
+#pragma unroll
+                        for (int pl = 0; pl < P; ++pl)
+                            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.t_rows_pad + gn) * em.t_kpad + gm0 + q * 8) =
+                                make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                    }
+                }
             }
         }
     }
@@ -357,53 +439,66 @@ int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes) {
     return mq_round_up(gm_pack_bytes(planes, m, k), 1024) + mq_round_up(gm_pack_bytes(planes, n, k), 1024) + 1024;
 }
 
-template <int P, int F>
-static int gm_pack(const float *base, int64_t rs, int64_t cs, const int32_t *idx, int idx_on_k, int64_t rows, int64_t k,
-                   int64_t ones_row, void *out, void *stream) {
-    const int64_t rows_pad = mq_round_up(rows, 128), k_pad = mq_round_up(k, GM_BK);
-    if (rs == 1 && cs != 1) {          // rows are the unit-stride axis: transpose through shared memory
-        dim3 grid((unsigned)(rows_pad / 32), (unsigned)(k_pad / 64));
-        auto kt = pack_planes_t_kernel<P, F>;
-        MQ_LAUNCH(kt, grid, MQ_NT, 0, stream, base, cs, idx, idx_on_k, rows, k, rows_pad, k_pad, ones_row,
-                  (__nv_bfloat16 *)out);
-        return MQ_OK;
+static int gm_mode_ok(int mode, int *planes, int *fmt) {
+    *planes = mode & MQ_TC_PLANES_MASK; *fmt = (mode & MQ_TC_FP16) ? 1 : 0;      // mode = planes | MQ_TC_FP16
+    if (*planes < 1 || *planes > 3) return 0;
+    if (*fmt && *planes != 2) return 0;
+    return 1;
+}
+
+// All jobs in one launch.  Fills in the block ranges; jobs with nothing to write are dropped.
+int mq_gemm_tma_pack_multi(GmPackJob *jobs, int n_jobs, int mode, void *stream) {
+    int planes, fmt;
+    if (!gm_mode_ok(mode, &planes, &fmt)) return MQ_ERR_UNSUPPORTED;
+    MQ_REQUIRE(n_jobs >= 0 && n_jobs <= GM_MAX_PACK_JOBS, MQ_ERR_INVALID, "mq_gemm_tma_pack_multi: %d jobs (max %d)", n_jobs, GM_MAX_PACK_JOBS);
+    GmPackJobs js;
+    memset(&js, 0, sizeof(js));
+    unsigned total = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        GmPackJob jb = jobs[i];
+        MQ_REQUIRE(jb.k_cover % 8 == 0 && jb.k_off % 8 == 0 && jb.k_pad % GM_BK == 0 && jb.rows_pad % 128 == 0 &&
+                   jb.row_off + jb.rows_cover <= jb.rows_pad && jb.k_off + jb.k_cover <= jb.k_pad, MQ_ERR_SHAPE,
+                   "mq_gemm_tma_pack_multi: job %d geometry", i);
+        jb.block0 = total;
+        jb.blocks = gm_job_blocks(jb);
+        if (jb.blocks == 0) continue;
+        total += jb.blocks;
+        js.job[js.n++] = jb;
     }
-    const int64_t items = rows_pad * (k_pad / 8);
-    auto kp = pack_planes_kernel<P, F>;
-    MQ_LAUNCH(kp, (unsigned)mq_ceil_div(items, MQ_NT), MQ_NT, 0, stream, base, rs, cs, idx, idx_on_k, rows, k,
-              rows_pad, k_pad, 0, ones_row, (__nv_bfloat16 *)out);
+    if (total == 0) return MQ_OK;
+    if (planes == 3) { auto kp = pack_jobs_kernel<3, 0>; MQ_LAUNCH(kp, total, MQ_NT, 0, stream, js); }
+    else if (planes == 2 && fmt) { auto kp = pack_jobs_kernel<2, 1>; MQ_LAUNCH(kp, total, MQ_NT, 0, stream, js); }
+    else if (planes == 2) { auto kp = pack_jobs_kernel<2, 0>; MQ_LAUNCH(kp, total, MQ_NT, 0, stream, js); }
+    else { auto kp = pack_jobs_kernel<1, 0>; MQ_LAUNCH(kp, total, MQ_NT, 0, stream, js); }
     return MQ_OK;
 }
 
-// Launches pack + GEMM.  g.c points at the split-K partial buffer when splits > 1 (g.k_per_split a multiple of 64).
-// `pack` = workspace of mq_gemm_tma_pack_bytes() bytes.  MQ_ERR_UNSUPPORTED when tensor maps are not available.
-int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, void *stream) {
-    const int planes = mode & MQ_TC_PLANES_MASK, fmt = (mode & MQ_TC_FP16) ? 1 : 0;      // mode = planes | MQ_TC_FP16
-    if (fmt && planes != 2) return MQ_ERR_UNSUPPORTED;
+// a whole operand as one job: rows x k of the source into planes of [rows_pad][k_pad]
+static GmPackJob gm_whole_job(const float *base, int64_t rs, int64_t cs, const int32_t *idx, int idx_on_k, int64_t rows,
+                              int64_t k, int64_t ones_row, void *out) {
+    GmPackJob jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.base = base; jb.rs = rs; jb.cs = cs; jb.idx = idx; jb.idx_on_k = idx_on_k; jb.rows = rows; jb.k = k;
+    jb.ones_row = ones_row;
+    jb.rows_pad = jb.rows_cover = mq_round_up(rows, 128);
+    jb.k_pad = jb.k_cover = mq_round_up(k, GM_BK);
+    jb.out = out;
+    return jb;
+}
+
+// The product on operands that are already packed: planes of A at `pa` ([planes][a_rows_pad][k_pad]), of B^T at `pb`
+// ([planes][b_rows_pad][k_pad]).  g.a / g.b are not read; g.c points at the split-K partial buffer when splits > 1
+// (g.k_per_split a multiple of 64; the planes `em` asks for are not written then).
+int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64_t b_rows_pad, int64_t k_pad,
+                       const GemmArgs &g, const GmEmit &em, int mode, int64_t splits, void *stream) {
+    int planes, fmt;
+    if (!gm_mode_ok(mode, &planes, &fmt)) return MQ_ERR_UNSUPPORTED;
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
-    if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
-    const int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128), k_pad = mq_round_up(g.k, GM_BK);
-    unsigned char *pa = (unsigned char *)(((uintptr_t)pack + 1023) & ~(uintptr_t)1023);
-    unsigned char *pb = pa + mq_round_up(gm_pack_bytes(planes, g.m, g.k), 1024);
-    // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
-    int rc;
-    if (planes == 3) {
-        rc = gm_pack<3, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<3, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
-    } else if (planes == 2 && fmt) {
-        rc = gm_pack<2, 1>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<2, 1>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
-    } else if (planes == 2) {
-        rc = gm_pack<2, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<2, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
-    } else {
-        rc = gm_pack<1, 0>(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa, stream);
-        rc = gm_pack<1, 0>(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb, stream);
-    }
-    (void)rc;
+    MQ_REQUIRE(a_rows_pad % 128 == 0 && b_rows_pad % 128 == 0 && k_pad % GM_BK == 0 && a_rows_pad >= g.m && b_rows_pad >= g.n &&
+               k_pad >= g.k && (((uintptr_t)pa | (uintptr_t)pb) & 127) == 0, MQ_ERR_SHAPE, "mq_gemm_tma: packed operand geometry");
     alignas(64) CUtensorMap map_a, map_b;
-    if (!gm_make_map(&map_a, pa, planes * a_rows_pad, k_pad) || !gm_make_map(&map_b, pb, planes * b_rows_pad, k_pad)) {
+    if (!gm_make_map(&map_a, (void *)pa, planes * a_rows_pad, k_pad) || !gm_make_map(&map_b, (void *)pb, planes * b_rows_pad, k_pad)) {
         mq_set_error("mq_gemm_tma: cuTensorMapEncodeTiled failed");
         return MQ_ERR_CUDA;
     }
@@ -413,7 +508,7 @@ int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, 
     do {                                                                                                                   \
         e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
         if (e == cudaSuccess)                                                                                              \
-            gemm_tma_kernel<P_, F_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, (int)a_rows_pad, \
+            gemm_tma_kernel<P_, F_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, em, (int)a_rows_pad, \
                                                                                                 (int)b_rows_pad);          \
     } while (0)
 #define GM_GO_P(SP_)                                              \
@@ -430,7 +525,31 @@ int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, 
     return MQ_OK;
 }
 
+// Launches pack + GEMM.  g.c points at the split-K partial buffer when splits > 1 (g.k_per_split a multiple of 64).
+// `pack` = workspace of mq_gemm_tma_pack_bytes() bytes.  MQ_ERR_UNSUPPORTED when tensor maps are not available.
+int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, void *stream) {
+    int planes, fmt;
+    if (!gm_mode_ok(mode, &planes, &fmt)) return MQ_ERR_UNSUPPORTED;
+    if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
+    if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
+    if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
+    const int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128), k_pad = mq_round_up(g.k, GM_BK);
+    unsigned char *pa = (unsigned char *)(((uintptr_t)pack + 1023) & ~(uintptr_t)1023);
+    unsigned char *pb = pa + mq_round_up(gm_pack_bytes(planes, g.m, g.k), 1024);
+    // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
+    GmPackJob jobs[2];
+    jobs[0] = gm_whole_job(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa);
+    jobs[1] = gm_whole_job(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb);
+    int rc = mq_gemm_tma_pack_multi(jobs, 2, mode, stream);
+    if (rc != MQ_OK) return rc;
+    GmEmit em;
+    memset(&em, 0, sizeof(em));
+    return mq_gemm_tma_packed(pa, a_rows_pad, pb, b_rows_pad, k_pad, g, em, mode, splits, stream);
+}
+
 #else
 int64_t mq_gemm_tma_pack_bytes(int64_t, int64_t, int64_t, int) { return 0; }
 int mq_gemm_tma_launch(const GemmArgs &, int, int64_t, void *, void *) { return MQ_ERR_UNSUPPORTED; }
+int mq_gemm_tma_pack_multi(GmPackJob *, int, int, void *) { return MQ_ERR_UNSUPPORTED; }
+int mq_gemm_tma_packed(const void *, int64_t, const void *, int64_t, int64_t, const GemmArgs &, const GmEmit &, int, int64_t, void *) { return MQ_ERR_UNSUPPORTED; }
 #endif

@@ -394,6 +394,96 @@ def clip_backward(v, g, lo, hi):
 
 
 # --------------------------------------------------------------------------
+# The training step of mnist/vae.py:39-71 (two evaluations of the shared graph)
+# --------------------------------------------------------------------------
+
+def vae_layout(d_img, hidden, latent, n_hidden):
+    """Flat layout of decoder.logprob's parameters (basicnet.py:66-77 order for
+    the graph of vae.py:39-55): encoder hidden (W, b)..., W_mean, b_mean,
+    W_logstd, b_logstd, decoder hidden (W, b)..., W_mean, b_mean, W_logstd,
+    b_logstd.  Returns (encoder spec, decoder spec, offsets, n_params): the
+    specs describe the tanh stacks only, the offsets the four heads."""
+    enc = mlp_spec(d_img, [hidden] * n_hidden, [ACT_TANH] * n_hidden)
+    pos = enc["n_params"]
+    off = {}
+    for name, n_out in (("e_mean", latent), ("e_logstd", latent)):
+        off[name] = (pos, pos + hidden * n_out, n_out)
+        pos += hidden * n_out + n_out
+    off["dec"] = pos
+    dec = mlp_spec(latent, [hidden] * n_hidden, [ACT_TANH] * n_hidden)
+    pos += dec["n_params"]
+    for name, n_out in (("d_mean", d_img), ("d_logstd", d_img)):
+        off[name] = (pos, pos + hidden * n_out, n_out)
+        pos += hidden * n_out + n_out
+    return enc, dec, off, pos
+
+
+def vae_grads(theta, d_img, hidden, latent, n_hidden, x, unit, lo=-6.0, hi=0.0):
+    """vae.py:57-66 with the N(0,1) draw of the latent sample as an input:
+    returns (logprob[B], dkl[B], grad1, grad2) -- grad1 the gradient of
+    sum(logprob) w.r.t. all parameters, grad2 of -sum(dkl) w.r.t. the encoder's,
+    both batch means (basicnet.py:231-236), computed as the reference does: two
+    separate backward passes, the Clip rule (vae.py:26-34) applied in each."""
+    theta = np.asarray(theta, np.float64)
+    enc, dec, off, n_params = vae_layout(d_img, hidden, latent, n_hidden)
+    assert theta.shape == (n_params,)
+    x = np.asarray(x, np.float64).reshape(-1, d_img)
+    batch = x.shape[0]
+    unit = np.asarray(unit, np.float64).reshape(batch, latent)
+
+    def head(name, h):
+        w0, b0, n_out = off[name]
+        return h @ theta[w0:b0].reshape(hidden, n_out) + theta[b0:b0 + n_out]
+
+    def head_grads(name, h, g, grad):
+        w0, b0, n_out = off[name]
+        grad[w0:b0] += (h.T @ g).reshape(-1) / batch
+        grad[b0:b0 + n_out] += g.sum(axis=0) / batch
+        return g @ theta[w0:b0].reshape(hidden, n_out).T
+
+    th_e, th_d = theta[:enc["n_params"]], theta[off["dec"]:off["dec"] + dec["n_params"]]
+    e_outs = mlp_forward(th_e, enc, x)
+    mean_e, raw_e = head("e_mean", e_outs[-1]), head("e_logstd", e_outs[-1])
+    ls_e = clip_forward(raw_e, lo, hi)
+    z, noise = gauss_sample(mean_e, ls_e, unit)                    # distrib.py:48-51
+    d_outs = mlp_forward(th_d, dec, z)
+    mean_d, raw_d = head("d_mean", d_outs[-1]), head("d_logstd", d_outs[-1])
+    ls_d = clip_forward(raw_d, lo, hi)
+    logprob = gauss_logprob(mean_d, ls_d, x)
+    dkl = dkl_uninormal(mean_e, ls_e)
+
+    def encoder_backward(d_mean, d_ls, grad):
+        dh = head_grads("e_mean", e_outs[-1], d_mean, grad)
+        dh = dh + head_grads("e_logstd", e_outs[-1], clip_backward(raw_e, d_ls, lo, hi), grad)
+        grad[:enc["n_params"]] += mlp_backward(th_e, enc, x, e_outs, dh)
+
+    # pass 1: decoder.logprob, upstream +1 (vae.py:60-61)
+    grad1 = np.zeros(n_params)
+    d_mu, d_ls = gauss_logprob_grads(mean_d, ls_d, x, np.ones(batch))
+    dh = head_grads("d_mean", d_outs[-1], d_mu, grad1)
+    dh = dh + head_grads("d_logstd", d_outs[-1], clip_backward(raw_d, d_ls, lo, hi), grad1)
+    g_dec, dz = mlp_backward(th_d, dec, z, d_outs, dh, want_dx=True)
+    grad1[off["dec"]:off["dec"] + dec["n_params"]] += g_dec
+    encoder_backward(dz, dz * noise, grad1)                         # sample: (g, g * noise), distrib.py:51
+    # pass 2: dkl, upstream -1 (vae.py:63-64)
+    grad2 = np.zeros(n_params)
+    d_mean, d_ls = dkl_uninormal_grads(mean_e, ls_e, -np.ones(batch))
+    encoder_backward(d_mean, d_ls, grad2)
+    return logprob, dkl, grad1, grad2[:off["dec"]]
+
+
+def vae_step(theta, momentum, d_img, hidden, latent, n_hidden, x, unit, lr=0.001):
+    """vae.py:57-69: grad1[:len(grad2)] += grad2; momentum = clip(0.9 momentum +
+    0.1 grad1, -1, 1); theta += 0.001 momentum.  Returns (theta, momentum,
+    logprob, dkl, grad)."""
+    logprob, dkl, grad1, grad2 = vae_grads(theta, d_img, hidden, latent, n_hidden, x, unit)
+    grad1 = grad1.copy()
+    grad1[:len(grad2)] += grad2
+    momentum = np.clip(np.asarray(momentum, np.float64) * 0.9 + grad1 * 0.1, -1.0, 1.0)
+    return np.asarray(theta, np.float64) + lr * momentum, momentum, logprob, dkl, grad1
+
+
+# --------------------------------------------------------------------------
 # Trajectory dtype / indexing rules (mannequin/_trajectory.py:9-30,79-86)
 # --------------------------------------------------------------------------
 

@@ -387,6 +387,64 @@ def gen_vae(out):
     out["clip_v"], out["clip_g"], out["clip_y"], out["clip_dx"] = v, cg, np.asarray(y), np.asarray(c_in.last_gradient)
 
 
+def gen_vae_step(out):
+    """The graph of mnist/vae.py:39-55 built from the reference's own classes (small sizes, two hidden layers per side
+    as in the script) and ONE iteration of its loop body, vae.py:60-69, statement by statement: both evaluations, both
+    backward passes, the clipped-momentum update.  The OS-seeded RandomState inside Gauss (distrib.py:46) is replaced by
+    a seeded one while the encoder is constructed, so that the N(0,1) draw of the latent sample is a recorded input."""
+    import importlib.util
+    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", plt)
+    spec = importlib.util.spec_from_file_location("ref_vae", os.path.join(REF, "mnist", "vae.py"))
+    vae = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vae)
+    from mannequin.basicnet import Input, Affine, Tanh
+    from mannequin.distrib import Gauss
+    shape, hidden, latent, batch = (4, 3), 8, 3, 6
+    np.random.seed(142)
+    real_rs = np.random.RandomState
+    encoder = Input(*shape)
+    encoder = Tanh(Affine(encoder, hidden))
+    encoder = Tanh(Affine(encoder, hidden))
+    np.random.RandomState = lambda *a: real_rs(977)
+    try:
+        encoder = Gauss(mean=Affine(encoder, latent, init=0.1), logstd=vae.Clip(Affine(encoder, latent), -6.0, 0.0))
+    finally:
+        np.random.RandomState = real_rs
+    dkl = vae.DKLUninormal(mean=encoder.mean, logstd=encoder.logstd)
+    decoder = encoder.sample
+    decoder = Tanh(Affine(decoder, hidden))
+    decoder = Tanh(Affine(decoder, hidden))
+    decoder = Gauss(mean=Affine(decoder, *shape, init=0.1), logstd=vae.Clip(Affine(decoder, *shape), -6.0, 0.0))
+    rs = real_rs(143)
+    # perturbed parameters: log-deviations on both sides of Clip's range, so that its backward rule is exercised
+    theta = decoder.get_params() + rs.randn(decoder.n_params).astype(np.float32) * 0.6
+    decoder.load_params(theta)
+    theta = decoder.get_params().copy()
+    inps = rs.rand(batch, *shape).astype(np.float32)
+    momentum = (rs.randn(decoder.n_params) * 0.05).astype(np.float32)
+
+    logprob, backprop = decoder.logprob.evaluate(inps, sample=inps)                 # vae.py:60
+    grad1 = backprop(np.ones(batch))
+    dkl_value, backprop = dkl.evaluate(inps)                                          # vae.py:63
+    grad2 = backprop(-np.ones(batch))
+    out["vstep_grad1"], out["vstep_grad2"] = np.array(grad1), np.array(grad2)
+    grad1 = np.array(grad1)
+    grad1[:len(grad2)] += grad2                                                       # vae.py:66
+    mom = momentum * 0.9 + grad1 * 0.1
+    mom = np.clip(mom, -1.0, 1.0)
+    decoder.load_params(decoder.get_params() + 0.001 * mom)                           # vae.py:69
+    out["vstep_dims"] = np.array([shape[0] * shape[1], hidden, latent, 2, batch])
+    out["vstep_theta"], out["vstep_x"], out["vstep_momentum"] = theta, inps, momentum
+    out["vstep_unit"] = real_rs(977).randn(batch, latent)                              # the draw of distrib.py:49
+    out["vstep_logprob"], out["vstep_dkl"] = np.array(logprob), np.array(dkl_value)
+    out["vstep_grad"], out["vstep_momentum_new"] = grad1, mom
+    out["vstep_theta_new"] = decoder.get_params().copy()
+    out["vstep_logstd_e"], out["vstep_logstd_d"] = np.array(encoder.logstd(inps)), np.array(decoder.logstd(inps))
+
+
 def gen_ppo(out, gym):
     """Run benchmarks/ppo.py:run() itself for two chunks and record everything."""
     import mannequin
@@ -779,6 +837,9 @@ def main():
     d = {}
     gen_vae(d)
     groups["vae"] = d
+    d = {}
+    gen_vae_step(d)
+    groups["vae_step"] = d
     d = {}
     gen_es(d, gym)
     groups["es"] = d

@@ -680,6 +680,99 @@ def test_vae_device_step_and_graph_replay():
     assert not np.array_equal(z1, z2) and abs(z1.mean()) < 2.0
 
 
+class _FixedNoise(object):
+    """A device generator that replays one recorded N(0,1) draw (the latent sample of mnist/vae.py)."""
+
+    def __init__(self, unit):
+        from mannequin2_b200 import _device as D
+        self.unit = D.from_host(np.asarray(unit, dtype=np.float32))
+
+    def randn_dev(self, shape):
+        assert tuple(shape) == tuple(self.unit.shape)
+        return self.unit.clone()
+
+
+def test_vae_fused_step_against_reference_run():
+    """The fused plan of csrc/mq_vae.cu (mq_vae_grad / mq_vae_step: one forward and one backward pass, every product on
+    the TMA-fed tcgen05 GEMM) against ONE iteration of mnist/vae.py:57-69 run from the reference's own classes
+    (golden/vae_step.npz): log-probs, DKLs, grad1 + grad2, and the parameters after the clipped-momentum update.  The
+    fixture's sizes are deliberately awkward for the plan: 12 pixels (head columns padded to 16), 3 latents (padded to
+    8), batch 6 (one 128-row tile, one 64-wide K block), two hidden layers per side, log-deviations on both sides of
+    Clip's bound.  Operand formats fp16x2 and exact share the fp32 bar (rtol 2e-5 of the largest entry)."""
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.vae import VAETrainer
+    g = load_golden("vae_step")
+    d_img, hidden, latent, n_hidden, batch = (int(v) for v in g["vstep_dims"])
+    x = D.from_host(g["vstep_x"].reshape(batch, d_img).astype(np.float32))
+    for mode in ("fp16x2", "exact"):
+        np.random.seed(1)
+        tr = VAETrainer(image_shape=(4, 3), hidden=hidden, latent=latent, n_hidden=n_hidden, rng=_FixedNoise(g["vstep_unit"]),
+                        gemm_mode=mode)
+        assert tr.fused_supported() and tr.n_params == len(g["vstep_theta"])
+        tr.decoder.load_params(g["vstep_theta"])
+        grad, lp, kl = tr.grad_fused(x, tr._rng.unit)
+        assert_close(D.to_host(lp), g["vstep_logprob"], rtol=2e-5, atol_scale=2e-6, msg=mode)
+        assert_close(D.to_host(kl), g["vstep_dkl"], rtol=2e-5, atol_scale=2e-6, msg=mode)
+        assert_close(D.to_host(grad), g["vstep_grad"], rtol=2e-5, atol_scale=2e-5, msg=mode)
+        tr.momentum = D.from_host(g["vstep_momentum"].astype(np.float32))
+        tr.step_fused(x)
+        assert np.max(np.abs(D.to_host(tr.momentum) - g["vstep_momentum_new"])) < 5e-5, mode
+        assert np.max(np.abs(np.asarray(tr.decoder.get_params()) - g["vstep_theta_new"])) < 2e-7, mode
+
+
+def test_vae_fused_step_at_baseline_shape():
+    """BASELINE configs[4] (784-400-(20+20)-400-(784+784), batch 4096): the fused plan against the fp64 oracle's
+    two-pass restatement of vae.py:57-66 (O.vae_grads) AND against the node-by-node device graph with the same latent
+    noise; then three iterations of `step_graph` on the fused plan against three of the node-by-node `step_dev`.  The
+    log-deviation heads are shifted so that part of the batch sits on Clip's bounds."""
+    import torch
+    from oracle import mq_oracle as O
+    from mannequin2_b200 import _device as D
+    from mannequin2_b200.vae import VAETrainer
+    rs = np.random.RandomState(5)
+    B, D_IMG, H, L = 4096, 784, 400, 20
+    x_host = rs.rand(B, 28, 28).astype(np.float32)
+    unit = rs.randn(B, L).astype(np.float32)
+    trainers = []
+    for k in range(2):
+        np.random.seed(11)
+        tr = VAETrainer(image_shape=(28, 28), hidden=H, latent=L, n_hidden=1, rng=_FixedNoise(unit))
+        theta = np.asarray(tr.decoder.get_params(), dtype=np.float32).copy()
+        prs = np.random.RandomState(12)
+        theta += (prs.randn(len(theta)) * 0.02).astype(np.float32)
+        tr.decoder.load_params(theta)
+        trainers.append(tr)
+    fused, graph = trainers
+    x = D.from_host(x_host)
+    grad, lp, kl = fused.grad_fused(x.reshape(B, D_IMG), fused._rng.unit)
+    o_lp, o_kl, g1, g2 = O.vae_grads(theta, D_IMG, H, L, 1, x_host.reshape(B, D_IMG), unit)
+    want = g1.copy()
+    want[:len(g2)] += g2
+    assert_close(D.to_host(lp), o_lp, rtol=2e-5, atol_scale=2e-6)
+    assert_close(D.to_host(kl), o_kl, rtol=2e-5, atol_scale=2e-6)
+    assert_close(D.to_host(grad), want, rtol=2e-5, atol_scale=1e-5)
+    # the node-by-node graph (two evaluations, vae.py:60-66) with the same noise
+    from mannequin2_b200.backprop import gemm_mode
+    ones = torch.ones(B, dtype=torch.float32, device=x.device)
+    with gemm_mode("fp16x2"):
+        _, bp = graph.decoder.logprob.evaluate_dev(x, sample=x)
+        n1 = D.to_host(D.as_dev_f32(bp(ones))).astype(np.float64)
+        _, bp = graph.dkl.evaluate_dev(x)
+        n2 = D.to_host(D.as_dev_f32(bp(-ones))).astype(np.float64)
+    n1[:len(n2)] += n2
+    assert_close(D.to_host(grad), n1, rtol=2e-5, atol_scale=1e-5)
+    # three iterations: CUDA-graph replay of the fused plan against the node-by-node step
+    for tr in trainers:
+        tr.decoder.load_params(theta)
+    for _ in range(3):
+        f_stats = [float(v) for v in fused.step_graph(x)]
+        g_stats = [float(v) for v in graph.step_dev(x)]
+        assert abs(f_stats[0] - g_stats[0]) < 1e-4 * (1 + abs(g_stats[0])) and abs(f_stats[1] - g_stats[1]) < 1e-4 * (1 + abs(g_stats[1]))
+    a, b = np.asarray(fused.decoder.get_params(), np.float64), np.asarray(graph.decoder.get_params(), np.float64)
+    assert np.max(np.abs(a - b)) < 1e-6, np.max(np.abs(a - b))
+    assert np.max(np.abs(a - theta)) > 1e-5
+
+
 def test_reinforce_script_loop_and_reward_log():
     """benchmarks/policy.py:29-47 (plain REINFORCE: episode -> Trajectory.discounted -> RunningNormalize -> tanh ->
     logprob backprop -> Adam) written against `mannequin` / `mannequin.gym`, on a small NumPy environment wrapped in

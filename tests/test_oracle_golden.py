@@ -257,6 +257,27 @@ def test_rollout_side_vs_reference():
     assert np.max(np.abs(adv - want.reshape(-1))) < 1e-5
 
 
+def test_vae_step_vs_reference_run():
+    """O.vae_grads / O.vae_step against ONE iteration of mnist/vae.py:57-69 run from the reference's own classes
+    (golden/vae_step.npz, tests/golden/make_golden.py:gen_vae_step): the graph of vae.py:39-55 with two hidden layers
+    per side, log-deviations on both sides of Clip's upper bound, both evaluations, both backward passes and the
+    clipped-momentum update.  The reference computes in float32, the oracle in float64."""
+    g = load_golden("vae_step")
+    d_img, hidden, latent, n_hidden, batch = (int(v) for v in g["vstep_dims"])
+    assert (g["vstep_logstd_d"] == 0.0).any() and (g["vstep_logstd_d"] < 0.0).any() and (g["vstep_logstd_e"] == 0.0).any()
+    lp, dkl, g1, g2 = O.vae_grads(g["vstep_theta"], d_img, hidden, latent, n_hidden, g["vstep_x"], g["vstep_unit"])
+    assert_close(lp, g["vstep_logprob"], rtol=2e-6, atol_scale=2e-6)
+    assert_close(dkl, g["vstep_dkl"], rtol=2e-6, atol_scale=2e-6)
+    assert_close(g1, g["vstep_grad1"], rtol=1e-5, atol_scale=2e-6)
+    assert_close(g2, g["vstep_grad2"], rtol=1e-5, atol_scale=2e-6)
+    th, mom, _, _, grad = O.vae_step(g["vstep_theta"], g["vstep_momentum"], d_img, hidden, latent, n_hidden, g["vstep_x"],
+                                     g["vstep_unit"])
+    assert_close(grad, g["vstep_grad"], rtol=1e-5, atol_scale=2e-6)
+    assert (np.abs(g["vstep_momentum_new"]) == 1.0).any() and (np.abs(g["vstep_momentum_new"]) < 1.0).any()
+    assert np.max(np.abs(mom - g["vstep_momentum_new"])) < 2e-5
+    assert np.max(np.abs(th - g["vstep_theta_new"])) < 2e-7
+
+
 def test_vae_heads_vs_reference_module():
     """DKLUninormal and Clip against mnist/vae.py:13-34 ITSELF (the module imported in the build container with
     matplotlib and autograd replaced by stand-ins, golden/vae.npz): forward values and the flat gradient of a small
