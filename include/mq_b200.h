@@ -112,8 +112,6 @@ typedef struct mq_head {
 const char *mq_last_error(void);
 /* developer aid: device buffer of 8 int64 that mq_fused_train fills with per-phase cycles */
 int mq_debug_set_phase_buffer(void *dev_buf);
-/* developer aid: force the row-tile size of the fused kernels (0 = automatic) */
-int mq_debug_set_tile_rows(int tb);
 /* ---- rollout side: many environments stepped in lock step ------------------------------------
  * NormalizedObservations of mannequin/gym.py:61-84 for the E observations of one time step as ONE batch of
  * RunningNormalize (mannequin/_normalize.py:34-81; E = 1 is the reference's per-step behaviour): out = clip(normalize(raw),
@@ -153,10 +151,6 @@ int mq_actor_env_step(const mq_env_t *env, int64_t n_env, int32_t t, int32_t t_l
 int mq_bootstrap_segments(float *rew, uint8_t *done, const float *v_next, int64_t n_seg, int64_t seg_len, float gam,
                           void *stream);
 
-/* developer aid: 0 makes mq_fused_grad use the tile kernel instead of the row-owner-warp kernel */
-int mq_debug_use_chain_grad(int on);
-/* developer aid: force 8 or 16 warps per CTA in the row-owner-warp gradient kernel (0 = automatic) */
-int mq_debug_set_chain_warps(int nw);
 /* peak microbenchmarks for bench.py's roofline denominators: *flops_out = FLOPs the launch executes;
  * the caller times it with CUDA events.  mq_bench_tensor: back-to-back tcgen05.mma M128 N256 from resident operands,
  * tf32 = 0: kind::f16 (bf16 inputs), 1: kind::tf32. */

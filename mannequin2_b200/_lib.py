@@ -86,9 +86,6 @@ SIGNATURES = {
     "mq_bench_ffma": (c_int, [c_int32, P, POINTER(c_double), P]),
     "mq_bench_tensor": (c_int, [c_int32, c_int32, POINTER(c_double), P]),
     "mq_debug_set_phase_buffer": (c_int, [P]),
-    "mq_debug_set_tile_rows": (c_int, [c_int]),
-    "mq_debug_use_chain_grad": (c_int, [c_int]),
-    "mq_debug_set_chain_warps": (c_int, [c_int]),
     "mq_device_props": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "mq_adam_step": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_double, c_double, c_double,
                              c_double, c_int, P]),

@@ -819,13 +819,6 @@ chain_grad_kernel(ChainPlan p, const float *__restrict__ theta, const float *__r
     chain_for_each_param<NW>(p, [&](int flat, int pad) { dst[flat] = sm.G[pad] * sc; });
 }
 
-static int g_chain_force_nw = 0, g_chain_force_rw = 0;      // developer knobs (0 = automatic)
-extern "C" int mq_debug_set_chain_warps(int nw) {
-    g_chain_force_rw = nw >= 100 ? nw - 100 : 0;           // 116 selects 8 warps x 16 rows
-    g_chain_force_nw = nw >= 100 ? 0 : nw;
-    return MQ_OK;
-}
-
 // Launch helper used by mq_fused_grad.  *grid_out receives the number of CTAs (= partials).
 int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                   int64_t batch, const mq_head_t *head, float scale, float *grad, float *out, float *logp,
@@ -834,9 +827,7 @@ int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const
     const int sms = mq_sm_count();
     // 16 warps / 128-row tiles when the batch feeds every SM with them, else 8 warps / 64 rows
     int nw = (batch >= (int64_t)sms * 128) ? 16 : 8;
-    if (g_chain_force_nw == 8 || g_chain_force_nw == 16) nw = g_chain_force_nw;
     int rw = 8;
-    if (g_chain_force_rw == 16) { rw = 16; nw = 8; }
     if (!chain_plan(net, &p, nw, rw, 0)) {
         if (chain_plan(net, &p, 8, 8, 0)) { nw = 8; rw = 8; }
         else return MQ_ERR_UNSUPPORTED;

@@ -89,17 +89,14 @@ static int64_t plan_build(const mq_net_t *net, int tb, int with_grad, FusedPlan 
     return p->smem_bytes;
 }
 
-static int g_force_tb = 0;            // developer knob (mq_debug_set_tile_rows), 0 = automatic
-extern "C" int mq_debug_set_tile_rows(int tb) { g_force_tb = tb; return MQ_OK; }
 
 static int plan_choose(const mq_net_t *net, int64_t batch, int with_grad, FusedPlan *p, int smem_state = 0,
                        int nt = MQ_NT) {
     const int64_t lim = mq_smem_optin();
     int tb = 128;
     if (batch <= 32) tb = 32; else if (batch <= 64) tb = 64;
-    if (g_force_tb && batch > g_force_tb) tb = g_force_tb;
     // forward only (a few thousand rows per time step of a rollout): smaller tiles until every SM has one
-    else if (!with_grad) while (tb > 32 && batch / tb < mq_sm_count()) tb >>= 1;
+    if (!with_grad) while (tb > 32 && batch / tb < mq_sm_count()) tb >>= 1;
     for (; tb >= 32; tb >>= 1)
         if (plan_build(net, tb, with_grad, p, smem_state, nt) <= lim) return tb;
     return 0;
@@ -873,8 +870,6 @@ int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const 
 int64_t mq_tc3_scratch_bytes();
 int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
                     int64_t n_obs, const float *ret_coef, float *returns, void *stream);
-static int g_use_chain_grad = 1;     // developer knob: 0 forces the tile kernel
-extern "C" int mq_debug_use_chain_grad(int on) { g_use_chain_grad = on; return MQ_OK; }
 
 // ---- host entry points -----------------------------------------------------------------
 static int fused_net_check(const mq_net_t *net, const char *what) {
@@ -1014,7 +1009,7 @@ extern "C" int mq_fused_grad(const mq_net_t *net, const float *theta, const floa
         }
         if (rc != MQ_ERR_UNSUPPORTED) return rc;
     }
-    if (g_use_chain_grad) {
+    {
         int cgrid = 0;
         rc = mq_chain_grad(net, theta, x, row_idx, batch, head, scale, grad, out, logp, ws, ws_bytes, &cgrid,
                            stream);

@@ -29,6 +29,7 @@
 // (x = x0 + 2^-11 x1: fp32 operands to 2^-24, the FFMA bar again, in three plane pairs instead of six -- block 1 of an
 // accumulator set holds exactly the scaled pairs A_0 B_1' + A_1' B_0 and is folded in with one FMA by the owners).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "mq_gemm.cuh"
 #include "mq_tc.cuh"
@@ -199,16 +200,22 @@ template <int P>
 struct GmCfg {
     static constexpr int STAGES = P == 3 ? 2 : (P == 2 ? 3 : 5);
     static constexpr int STAGE_BYTES = 2 * P * GM_TILE_BYTES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;       // + slack for the 1024-byte alignment
+    static constexpr int EPI_BYTES = 8 * 32 * 33 * 4;              // epilogue staging: 32 rows x 32 columns (+ pad) per owner warp
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024;       // + slack for the 1024-byte alignment
     static constexpr bool FOLD = P > 1;
     static constexpr int NB = P > 1 ? 2 : 1;                       // column blocks of an accumulator set
-    static constexpr int TMEM_COLS = P > 1 ? 512 : 128;
+    static constexpr int SET_COLS = P > 1 ? 256 : 128;             // two accumulator sets alternate
+    static constexpr int TMEM_COLS = 2 * SET_COLS;
 };
 
+// PERSISTENT: min(tiles, SMs) CTAs, CTA b takes tiles b, b + gridDim.x, ... (tile = (split z, row tile, column tile),
+// column tiles fastest).  The three roles walk the same tile sequence; stage / accumulator-set indices and barrier
+// parities follow RUNNING chunk and block counters, so the producer and the issuer run into the next tile while the owners
+// still write the previous tile's C (the owners hold it in registers; its accumulator set was released when they read it).
 template <int P, int F, bool SPLIT>
 __global__ void __launch_bounds__(GM_NT, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g, GmEmit em,
-                int a_rows_pad, int b_rows_pad) {
+                int a_rows_pad, int b_rows_pad, int n_splits) {
     using Cfg = GmCfg<P>;
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t s_tmem;
@@ -216,11 +223,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t sbase = (tc_smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
-    const int64_t k_begin = (int64_t)blockIdx.z * g.k_per_split;
-    const int64_t k_end = (k_begin + g.k_per_split < g.k) ? k_begin + g.k_per_split : g.k;
-    const int n_chunks = (int)((k_end - k_begin + GM_BK - 1) / GM_BK);
-    const int n_blocks = Cfg::FOLD ? (n_chunks + GM_KBLOCK - 1) / GM_KBLOCK : (n_chunks > 0 ? 1 : 0);
+    const int tiles_n = (int)((g.n + GM_BN - 1) / GM_BN), tiles_m = (int)((g.m + GM_BM - 1) / GM_BM);
+    const int64_t tiles_mn = (int64_t)tiles_m * tiles_n, n_tiles = tiles_mn * n_splits;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"((uint32_t)Cfg::TMEM_COLS));
@@ -242,20 +246,34 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tc_publish();
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
 
+    // tile t -> (m0, n0, first chunk, chunks)
+#define GM_TILE_DECODE(t_)                                                                                         \
+    const int64_t z_ = (t_) / tiles_mn, rem_ = (t_) - z_ * tiles_mn;                                                \
+    const int m0 = (int)(rem_ / tiles_n) * GM_BM, n0 = (int)(rem_ % tiles_n) * GM_BN;                               \
+    const int64_t k_begin = z_ * g.k_per_split;                                                                     \
+    const int64_t k_end = (k_begin + g.k_per_split < g.k) ? k_begin + g.k_per_split : g.k;                          \
+    const int n_chunks = (int)((k_end - k_begin + GM_BK - 1) / GM_BK);                                              \
+    const int n_blocks = Cfg::FOLD ? (n_chunks + GM_KBLOCK - 1) / GM_KBLOCK : 1
+
     if (warp == 0) {
         // ---- TMA producer ----------------------------------------------------------------------------------------
         if (tc_elect_one()) {
-            for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % Cfg::STAGES;
-                if (c >= Cfg::STAGES) tc_wait(tc_smem_u32(&s_empty[s]), (uint32_t)((c / Cfg::STAGES - 1) & 1));
-                const uint32_t full = tc_smem_u32(&s_full[s]);
-                gm_expect_tx(full, (uint32_t)Cfg::STAGE_BYTES);
-                const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
-                const int kc = (int)(k_begin + (int64_t)c * GM_BK);
+            uint32_t gc = 0;                                   // chunks loaded so far, all tiles
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                GM_TILE_DECODE(t);
+                (void)n_blocks;
+                for (int c = 0; c < n_chunks; ++c, ++gc) {
+                    const uint32_t s = gc % Cfg::STAGES;
+                    if (gc >= (uint32_t)Cfg::STAGES) tc_wait(tc_smem_u32(&s_empty[s]), (gc / Cfg::STAGES - 1) & 1u);
+                    const uint32_t full = tc_smem_u32(&s_full[s]);
+                    gm_expect_tx(full, (uint32_t)Cfg::STAGE_BYTES);
+                    const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
+                    const int kc = (int)(k_begin + (int64_t)c * GM_BK);
 #pragma unroll
-                for (int pl = 0; pl < P; ++pl) {
-                    gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, kc, pl * a_rows_pad + m0, full);
-                    gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, kc, pl * b_rows_pad + n0, full);
+                    for (int pl = 0; pl < P; ++pl) {
+                        gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, kc, pl * a_rows_pad + m0, full);
+                        gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, kc, pl * b_rows_pad + n0, full);
+                    }
                 }
             }
         }
@@ -264,134 +282,168 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ---- MMA issuer --------------------------------------------------------------------------------------------
         const uint32_t hi = gm_desc_hi();
         const uint32_t id2 = tc_idesc_fmt(GM_BM, 2 * GM_BN, 0, 0, F), id1 = tc_idesc_fmt(GM_BM, GM_BN, 0, 0, F);
-        for (int c = 0; c < n_chunks; ++c) {
-            const int s = c % Cfg::STAGES;
-            const int blk = Cfg::FOLD ? c / GM_KBLOCK : 0, set = blk & 1;
-            tc_wait(tc_smem_u32(&s_full[s]), (uint32_t)((c / Cfg::STAGES) & 1));
-            if (Cfg::FOLD && c % GM_KBLOCK == 0 && blk >= 2) tc_wait(tc_smem_u32(&s_accempty[set]), (uint32_t)((blk / 2 - 1) & 1));
-            if (tc_elect_one()) {
-                const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
-                const uint32_t d = tm + set * 256;
-                const uint32_t pl16 = GM_TILE_BYTES >> 4;
+        uint32_t gc = 0, gb = 0;                               // chunks / accumulator blocks issued so far, all tiles
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            GM_TILE_DECODE(t);
+            (void)m0; (void)n0;
+            for (int c = 0; c < n_chunks; ++c, ++gc) {
+                const uint32_t s = gc % Cfg::STAGES;
+                const uint32_t gbl = gb + (Cfg::FOLD ? (uint32_t)(c / GM_KBLOCK) : 0u), set = gbl & 1u;
+                tc_wait(tc_smem_u32(&s_full[s]), (gc / Cfg::STAGES) & 1u);
+                const bool block_start = Cfg::FOLD ? (c % GM_KBLOCK == 0) : (c == 0);
+                if (block_start && gbl >= 2u) tc_wait(tc_smem_u32(&s_accempty[set]), (gbl / 2u - 1u) & 1u);
+                if (tc_elect_one()) {
+                    const uint32_t sa = sbase + s * Cfg::STAGE_BYTES, sb = sa + P * GM_TILE_BYTES;
+                    const uint32_t d = tm + set * Cfg::SET_COLS;
+                    const uint32_t pl16 = GM_TILE_BYTES >> 4;
 #pragma unroll
-                for (int ks = 0; ks < GM_BK / 16; ++ks) {
-                    const uint32_t alo = gm_desc_lo(sa) + 2 * ks, blo = gm_desc_lo(sb) + 2 * ks;     // 32 bytes per K step
-                    const uint32_t first = Cfg::FOLD ? ((c % GM_KBLOCK > 0 || ks > 0) ? 1u : 0u) : ((c > 0 || ks > 0) ? 1u : 0u);
-                    if (P == 1) {
-                        tc_mma(d, alo, hi, blo, hi, id1, first);                              // A_0 x B_0
-                    } else if (P == 2) {
-                        tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
-                        tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
-                    } else {
-                        // block 0 receives ONLY the leading term A_0 B_0 (one truncating add per K step), block 1 all the
-                        // correction terms (<= 2^-8 of it): the accumulator's round-towards-zero bias is 4x smaller than
-                        // with the corrections spread over both blocks, at the same tensor-pipe time (128 + 4 x 64 cycles)
-                        tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
-                        tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
-                        tc_mma(d + GM_BN, alo + pl16, hi, blo + pl16, hi, id1, 1u);           // A_1 x B_1       -> block 1
-                        tc_mma(d + GM_BN, alo, hi, blo + 2 * pl16, hi, id1, 1u);              // A_0 x B_2       -> block 1
-                        tc_mma(d + GM_BN, alo + 2 * pl16, hi, blo, hi, id1, 1u);              // A_2 x B_0       -> block 1
+                    for (int ks = 0; ks < GM_BK / 16; ++ks) {
+                        const uint32_t alo = gm_desc_lo(sa) + 2 * ks, blo = gm_desc_lo(sb) + 2 * ks;     // 32 bytes per K step
+                        const uint32_t first = Cfg::FOLD ? ((c % GM_KBLOCK > 0 || ks > 0) ? 1u : 0u) : ((c > 0 || ks > 0) ? 1u : 0u);
+                        if (P == 1) {
+                            tc_mma(d, alo, hi, blo, hi, id1, first);                              // A_0 x B_0
+                        } else if (P == 2) {
+                            tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
+                            tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
+                        } else {
+                            // block 0 receives ONLY the leading term A_0 B_0 (one truncating add per K step), block 1 all the
+                            // correction terms (<= 2^-8 of it): the accumulator's round-towards-zero bias is 4x smaller than
+                            // with the corrections spread over both blocks, at the same tensor-pipe time (128 + 4 x 64 cycles)
+                            tc_mma(d, alo, hi, blo, hi, id2, first);                              // A_0 x [B_0|B_1] -> blocks 0 | 1
+                            tc_mma(d + GM_BN, alo + pl16, hi, blo, hi, id1, 1u);                  // A_1 x B_0       -> block 1
+                            tc_mma(d + GM_BN, alo + pl16, hi, blo + pl16, hi, id1, 1u);           // A_1 x B_1       -> block 1
+                            tc_mma(d + GM_BN, alo, hi, blo + 2 * pl16, hi, id1, 1u);              // A_0 x B_2       -> block 1
+                            tc_mma(d + GM_BN, alo + 2 * pl16, hi, blo, hi, id1, 1u);              // A_2 x B_0       -> block 1
+                        }
                     }
+                    tc_commit(tc_smem_u32(&s_empty[s]));
+                    if (c == n_chunks - 1 || (Cfg::FOLD && c % GM_KBLOCK == GM_KBLOCK - 1)) tc_commit(tc_smem_u32(&s_accfull[set]));
                 }
-                tc_commit(tc_smem_u32(&s_empty[s]));
-                if (c == n_chunks - 1 || (Cfg::FOLD && c % GM_KBLOCK == GM_KBLOCK - 1)) tc_commit(tc_smem_u32(&s_accfull[set]));
+                __syncwarp();
             }
-            __syncwarp();
+            gb += (uint32_t)n_blocks;
         }
     } else {
         // ---- accumulator owners: row = TMEM lane, 64 columns each ----------------------------------------------------
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const uint32_t tl = tm + ((uint32_t)(quarter * 32) << 16) + half * 64;
-        float acc[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
-        for (int blk = 0; blk < n_blocks; ++blk) {
-            const int set = blk & 1;
-            tc_wait(tc_smem_u32(&s_accfull[set]), (uint32_t)((blk / 2) & 1));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float v[16], w[16];
-                tc_ld16(tl + set * 256 + q * 16, v);
-                if (Cfg::NB == 2) tc_ld16(tl + set * 256 + GM_BN + q * 16, w);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[q * 16 + j] += Cfg::NB == 2 ? (F == 1 ? fmaf(w[j], GM_LOW_UNSCALE, v[j]) : v[j] + w[j]) : v[j];
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) gm_arrive(tc_smem_u32(&s_accempty[set]));
-        }
-        // registers -> C through shared memory (the operand stages are free: every product that read them has completed
-        // and every TMA load has been consumed), so that a warp writes whole 256-byte row segments instead of 32 rows x 4
-        // bytes per instruction -- and reads bias / the saved activations of the act' epilogue the same way
-        float *stage = reinterpret_cast<float *>(smem_raw + (sbase - tc_smem_u32(smem_raw))) + (warp - 2) * (32 * 65);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) stage[lane * 65 + j] = acc[j];
-        __syncwarp();
+        float *stage = reinterpret_cast<float *>(smem_raw + (sbase - tc_smem_u32(smem_raw)) + Cfg::STAGES * Cfg::STAGE_BYTES) + (warp - 2) * (32 * 33);
         const bool emit = !SPLIT && (em.out_k != nullptr || em.out_t != nullptr);
         const int64_t ldc = em.ldc > 0 ? em.ldc : g.n;
-        for (int r = 0; r < 32; ++r) {
-            const int64_t gm = m0 + quarter * 32 + r;
-            if (gm >= g.m && !emit) break;
+        uint32_t gb = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            GM_TILE_DECODE(t);
+            (void)n_chunks;
+            float acc[64];
 #pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+            // the tensor pipe TRUNCATES when it adds into its accumulator, so for P >= 2 a set only ever accumulates one K block
+            // of 128; the owners add each finished block into registers (round to nearest) from the set the pipe is not writing
+            for (int blk = 0; blk < n_blocks; ++blk) {
+                const uint32_t gbl = gb + (uint32_t)blk, set = gbl & 1u;
+                tc_wait(tc_smem_u32(&s_accfull[set]), (gbl / 2u) & 1u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v[16], w[16];
+                    tc_ld16(tl + set * Cfg::SET_COLS + q * 16, v);
+                    if (Cfg::NB == 2) tc_ld16(tl + set * Cfg::SET_COLS + GM_BN + q * 16, w);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[q * 16 + j] += Cfg::NB == 2 ? (F == 1 ? fmaf(w[j], GM_LOW_UNSCALE, v[j]) : v[j] + w[j]) : v[j];
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) gm_arrive(tc_smem_u32(&s_accempty[set]));
+            }
+            gb += (uint32_t)n_blocks;
+            // registers -> C through the warp's staging tile, 32 columns at a time, so that a warp writes whole 128-byte row
+            // segments instead of 32 rows x 4 bytes per instruction -- and reads bias / the saved activations of the act'
+            // epilogue the same way
+            // (a real loop over the two halves, the registers picked by selects: unrolled, the epilogue was 5,000
+            // instructions of straight-line code executed once per tile, and its instruction fetch cost 6 us per launch)
+#pragma unroll 1
             for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = hc ? acc[32 + j] : acc[j];
+                __syncwarp();
                 const int64_t gn = n0 + half * 64 + hc * 32 + lane;
-                float v = 0.0f;
-                if (gm < g.m && gn < g.n) {
-                    v = stage[r * 65 + hc * 32 + lane];
-                    if (SPLIT) g.c[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
-                    else {
-                        v = gemm_epilogue(g, v, gm, gn);
-                        if (g.c) g.c[gm * ldc + gn] = v;
+                const int64_t gm_base = m0 + quarter * 32;
+                const bool col_ok = gn < g.n;
+                // rows in groups of 4: what a group reads from global memory (the saved activations of the act' epilogue) is
+                // fetched BEFORE its rows are processed -- with eight owner warps per SM a load inside the row loop is an
+                // exposed L2 round trip per row
+                const float bias_n = (!SPLIT && g.epi == EPI_BIAS_ACT && col_ok) ? __ldg(g.bias + gn) : 0.0f;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 4) {
+                    const int64_t gmr = gm_base + r0;
+                    if (gmr >= g.m && !emit) break;
+                    float yv[4];
+                    if (!SPLIT && g.epi == EPI_ACT_GRAD) {
+                        const float *yp = g.y + gmr * g.n + gn;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) yv[i] = (col_ok && gmr + i < g.m) ? __ldg(yp + i * g.n) : 0.0f;
+                    }
+                    float *cp = SPLIT ? g.c + (z_ * g.m + gmr) * g.n + gn : (g.c ? g.c + gmr * ldc + gn : nullptr);
+                    const int64_t cstep = SPLIT ? g.n : ldc;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = r0 + i;
+                        float v = 0.0f;
+                        if (gmr + i < g.m && col_ok) {
+                            v = stage[r * 33 + lane];
+                            if (!SPLIT) {
+                                if (g.epi == EPI_BIAS_ACT) v = mq_act_apply(v + bias_n, g.act, g.leak);
+                                else if (g.epi == EPI_ACT_GRAD) v = mq_act_grad(yv[i], v, g.act, g.leak);
+                                else v = g.alpha * v;
+                            }
+                            if (cp) cp[i * cstep] = v;
+                        }
+                        if (emit) stage[r * 33 + lane] = v;          // the epilogue's value, zero outside C
                     }
                 }
-                if (emit) stage[r * 65 + hc * 32 + lane] = v;      // the epilogue's value, zero outside C
-            }
-        }
-        if (emit) {
-            // the same values as operand planes of the NEXT product (GmEmit, mq_gemm.cuh)
-            __syncwarp();
-            if (em.out_k) {            // C as a K-major operand: a lane converts 8 consecutive columns of one row
-                __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_k;
-                const int r4 = lane >> 3, ch = lane & 7;
-                const int64_t gn0 = n0 + half * 64 + ch * 8;
+                if (emit) {
+                    // the same values as operand planes of the NEXT product (GmEmit, mq_gemm.cuh)
+                    __syncwarp();
+                    if (em.out_k) {            // C as a K-major operand: a lane converts 8 consecutive columns of one row
+                        __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_k;
+                        const int r8 = lane >> 2, ch = lane & 3;
+                        const int64_t gn0 = n0 + half * 64 + hc * 32 + ch * 8;
+#pragma unroll 1
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + r8;
+                            const int64_t gm = m0 + quarter * 32 + r;
+                            if (gm < g.m && gn0 < g.n) {
+                                uint32_t w[4][P];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + r4;
-                    const int64_t gm = m0 + quarter * 32 + r;
-                    if (gm < g.m && gn0 < g.n) {
-                        uint32_t w[4][P];
+                                for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(stage[r * 33 + ch * 8 + 2 * j], stage[r * 33 + ch * 8 + 2 * j + 1], w[j]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) gm_split_pair<P, F>(stage[r * 65 + ch * 8 + 2 * j], stage[r * 65 + ch * 8 + 2 * j + 1], w[j]);
+                                for (int pl = 0; pl < P; ++pl)
+                                    *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.k_rows_pad + gm) * em.k_kpad + gn0) =
+                                        make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                            }
+                        }
+                    }
+                    if (em.out_t && gn < g.n) {            // C^T: a lane owns a column and converts its 32 rows, 8 at a time
+                        __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_t;
+                        const int64_t gm0 = m0 + quarter * 32;
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            if (gm0 + q * 8 >= em.t_kpad) continue;
+                            uint32_t w[4][P];
 #pragma unroll
-                        for (int pl = 0; pl < P; ++pl)
-                            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.k_rows_pad + gm) * em.k_kpad + gn0) =
-                                make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                            for (int j = 0; j < 4; ++j)
+                                gm_split_pair<P, F>(stage[(q * 8 + 2 * j) * 33 + lane], stage[(q * 8 + 2 * j + 1) * 33 + lane], w[j]);
+#pragma unroll
+                            for (int pl = 0; pl < P; ++pl)
+                                *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.t_rows_pad + gn) * em.t_kpad + gm0 + q * 8) =
+                                    make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                        }
                     }
                 }
-            }
-            if (em.out_t) {            // C^T: a lane owns a column and converts its 32 rows, 8 at a time
-                __nv_bfloat16 *out = (__nv_bfloat16 *)em.out_t;
-                const int64_t gm0 = m0 + quarter * 32;
-#pragma unroll
-                for (int hc = 0; hc < 2; ++hc) {
-                    const int64_t gn = n0 + half * 64 + hc * 32 + lane;
-                    if (gn >= g.n) continue;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (gm0 + q * 8 >= em.t_kpad) continue;
-                        uint32_t w[4][P];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            gm_split_pair<P, F>(stage[(q * 8 + 2 * j) * 65 + hc * 32 + lane], stage[(q * 8 + 2 * j + 1) * 65 + hc * 32 + lane], w[j]);
-#pragma unroll
-                        for (int pl = 0; pl < P; ++pl)
-                            *reinterpret_cast<uint4 *>(out + ((int64_t)pl * em.t_rows_pad + gn) * em.t_kpad + gm0 + q * 8) =
-                                make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
-                    }
-                }
+                __syncwarp();                  // the next half (or tile) overwrites the staging tile
             }
         }
     }
+#undef GM_TILE_DECODE
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)Cfg::TMEM_COLS));
@@ -502,14 +554,17 @@ int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64
         mq_set_error("mq_gemm_tma: cuTensorMapEncodeTiled failed");
         return MQ_ERR_CUDA;
     }
-    dim3 grid((unsigned)mq_ceil_div(g.n, GM_BN), (unsigned)mq_ceil_div(g.m, GM_BM), (unsigned)splits);
+    const int64_t n_tiles = mq_ceil_div(g.n, GM_BN) * mq_ceil_div(g.m, GM_BM) * (splits > 1 ? splits : 1);
+    // persistent: one CTA per SM at most (developer aid for A/B measurements: MQ_GEMM_ONE_TILE_PER_CTA=1 launches a CTA per tile)
+    static const bool one_tile = getenv("MQ_GEMM_ONE_TILE_PER_CTA") != nullptr;
+    const unsigned grid = (unsigned)((one_tile || n_tiles < mq_sm_count()) ? n_tiles : mq_sm_count());
     cudaError_t e = cudaSuccess;
 #define GM_GO(P_, F_, SP_)                                                                                                 \
     do {                                                                                                                   \
         e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
         if (e == cudaSuccess)                                                                                              \
             gemm_tma_kernel<P_, F_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, em, (int)a_rows_pad, \
-                                                                                                (int)b_rows_pad);          \
+                                                                                                (int)b_rows_pad, (int)(splits > 1 ? splits : 1)); \
     } while (0)
 #define GM_GO_P(SP_)                                              \
     do {                                                          \

@@ -166,16 +166,17 @@ __device__ __forceinline__ float vae_clip_rule(float raw, float g, float lo, flo
 
 // Encoder heads -> latent sample.  ch = h [W_mu | W_ls] (columns 0 .. L-1 and Lp .. Lp+L-1), biases added here.
 //   ls = clip(raw)  (vae.py:26-34), noise = unit * exp(ls), z = mu + noise  (distrib.py:48-51),
-//   dkl = 0.5 (sum(exp(ls) - ls + mu^2) - L)  (vae.py:13-22).  One thread per row (L is a handful of columns).
+//   dkl = 0.5 (sum(exp(ls) - ls + mu^2) - L)  (vae.py:13-22).  One warp per row.
 __global__ void __launch_bounds__(MQ_NT)
 vae_latent_fwd_kernel(const float *__restrict__ ch, const float *__restrict__ b_mu, const float *__restrict__ b_ls,
                       const float *__restrict__ unit, int64_t rows, int L, int Lp, float lo, float hi, float *__restrict__ mu,
                       float *__restrict__ ls, float *__restrict__ ls_raw, float *__restrict__ noise, float *__restrict__ z,
                       float *__restrict__ dkl) {
-    const int64_t r = (int64_t)blockIdx.x * MQ_NT + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * MQ_NT + threadIdx.x) >> 5;      // one warp per row, lanes along the latent axis
     if (r >= rows) return;
     float acc = 0.0f;
-    for (int j = 0; j < L; ++j) {
+    for (int j = lane; j < L; j += 32) {
         const float m = ch[r * 2 * Lp + j] + b_mu[j];
         const float raw = ch[r * 2 * Lp + Lp + j] + b_ls[j];
         const float l = fminf(fmaxf(raw, lo), hi);
@@ -184,7 +185,9 @@ vae_latent_fwd_kernel(const float *__restrict__ ch, const float *__restrict__ b_
         mu[r * L + j] = m; ls[r * L + j] = l; ls_raw[r * L + j] = raw; noise[r * L + j] = nz; z[r * L + j] = m + nz;
         acc += e - l + m * m;
     }
-    dkl[r] = 0.5f * (acc - (float)L);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dkl[r] = 0.5f * (acc - (float)L);
 }
 
 // Upstream gradient of the encoder heads: the logprob pass (+1) arrives through the sample (distrib.py:51: (g, g * noise)),
@@ -219,6 +222,7 @@ vae_head_kernel(float *__restrict__ cd, const float *__restrict__ b_m, const flo
     if (r >= rows) return;
     float *row = cd + r * 2 * Dp;
     float acc = 0.0f;
+#pragma unroll 4
     for (int j = lane; j < D; j += 32) {
         const float m = row[j] + b_m[j];
         const float raw = row[Dp + j] + b_s[j];
@@ -247,7 +251,8 @@ vae_dw_finish_kernel(const float *__restrict__ partial, int splits, int64_t m, i
         else if (dst1 && c >= off1 && c < off1 + nd1) dst = dst1 + r * nd1 + (c - off1);
         else continue;
         float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + e];
+#pragma unroll 8
+        for (int z = 0; z < splits; ++z) s += __ldg(partial + (int64_t)z * total + e);      // split order: bit-reproducible
         *dst = alpha * s;
     }
 }
@@ -386,7 +391,7 @@ extern "C" int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x
         const VaeGemm p = {w.ek[n - 1], d.Bp, w.wf_eh, rp(2 * Lp), B, 2 * Lp, H};
         VAE_TRY(vae_product(d, p, w.ch, 2 * Lp, EPI_SCALE, nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, stream));
     }
-    MQ_LAUNCH(vae_latent_fwd_kernel, (unsigned)mq_ceil_div(B, MQ_NT), MQ_NT, 0, stream, (const float *)w.ch, theta + o.b_mu, theta + o.b_ls, unit, B,
+    MQ_LAUNCH(vae_latent_fwd_kernel, (unsigned)mq_ceil_div(B * 32, MQ_NT), MQ_NT, 0, stream, (const float *)w.ch, theta + o.b_mu, theta + o.b_ls, unit, B,
               (int)L, (int)Lp, lo, hi, w.mu, w.ls, w.ls_raw, w.noise, w.z, dkl);
     {
         GmPackJob jobs[2];
