@@ -853,9 +853,28 @@ class VAEWorkload(object):
     def step_gpu(self, i):
         self.tr.step_graph(self.dev[i % len(self.dev)])
 
-    def step_e2e(self, i):
+    def _upload(self, i):
+        """Batch i from pinned host memory into one of two device buffers, on the copy stream."""
         t = self.torch
-        x = self.pinned[i % len(self.pinned)].to(self.D.device(), non_blocking=True)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = t.cuda.Stream()
+            self._bufs = [t.empty(self.B, 28, 28, device=self.D.device()) for _ in range(2)]
+        buf, ev = self._bufs[i % 2], t.cuda.Event()
+        with t.cuda.stream(self._copy_stream):
+            buf.copy_(self.pinned[i % len(self.pinned)], non_blocking=True)
+            ev.record()
+        return i, buf, ev
+
+    def step_e2e(self, i):
+        # every step's batch is copied from pinned host memory (12.8 MB); the copy of batch i + 1 is issued on a copy stream
+        # before batch i's kernels, as a training loop with a prefetching loader does (the PPO arm does the same)
+        t = self.torch
+        pend = getattr(self, "_pending", None)
+        if pend is None or pend[0] != i:
+            pend = self._upload(i)
+        _, x, ev = pend
+        self._pending = self._upload(i + 1)
+        t.cuda.current_stream().wait_event(ev)
         lp, kl = self.tr.step_graph(x)
         self.out_pinned[0:1].copy_(lp.reshape(1), non_blocking=True)
         self.out_pinned[1:2].copy_(kl.reshape(1), non_blocking=True)
