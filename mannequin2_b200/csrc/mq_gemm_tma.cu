@@ -174,8 +174,10 @@ pack_jobs_kernel(const __grid_constant__ GmPackJobs jobs) {
     const GmPackJob &jb = jobs.job[j];
     const int64_t local = (int64_t)blockIdx.x - jb.block0;
     if (jb.rs == 1 && jb.cs != 1) {
-        const int64_t nbx = (jb.rows_cover + 31) / 32;
-        gm_pack_transposed<P, F>(jb, local % nbx, local / nbx, tile);
+        // k blocks fastest: blocks that run together write neighbouring 128-byte pieces of the same packed rows (with the row
+        // blocks fastest every piece landed in another DRAM page: 4096^2 floats packed at 2.4 TB/s)
+        const int64_t nby = (jb.k_cover + 63) / 64;
+        gm_pack_transposed<P, F>(jb, local / nby, local % nby, tile);
     } else {
         gm_pack_plain<P, F>(jb, 0, local * MQ_NT + threadIdx.x);
     }
