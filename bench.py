@@ -881,9 +881,9 @@ class VAEWorkload(object):
         t.cuda.current_stream().synchronize()
 
     def launches_per_step(self):
-        # fused plan (csrc/mq_vae.cu, one hidden layer per side): 5 packs, 9 products, 4 split-K dW products + their 4
-        # finishes, latent forward / backward, head, momentum step = 24 kernels of this library + the Philox draw
-        return 25
+        # fused plan (csrc/mq_vae.cu, one hidden layer per side): 3 packs, 7 products + 4 split-K dW products and their 4
+        # finishes, latent forward / backward, head, momentum step = 22 kernels of this library + the Philox draw
+        return 23
 
     def dominant_kernel(self, peaks):
         """pack + gemm_tma_kernel on the widest layer (4096 x 784 x 400, y = x W), timed alone."""

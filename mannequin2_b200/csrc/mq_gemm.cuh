@@ -58,3 +58,30 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int
     return g.alpha * acc;
 }
 
+#if !defined(MQ_EMU) && defined(__CUDACC__)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+// ---- the operand planes of the tcgen05 GEMM, shared with the kernels that write planes themselves (csrc/mq_vae.cu) ----------
+#define GM_LOW_SCALE 2048.0f
+#define GM_LOW_UNSCALE 4.8828125e-4f
+
+// P words of packed 16-bit pairs from two values: bf16 planes (F = 0) or fp16 with the scaled low plane (F = 1, P = 2)
+template <int P, int F>
+__device__ __forceinline__ void gm_split_pair(float a, float b, uint32_t *w) {
+    if (F == 1) {
+        const __half2 h0 = __floats2half2_rn(a, b);
+        const float2 f0 = __half22float2(h0);
+        const __half2 h1 = __floats2half2_rn((a - f0.x) * GM_LOW_SCALE, (b - f0.y) * GM_LOW_SCALE);
+        w[0] = *reinterpret_cast<const uint32_t *>(&h0);
+        w[1] = *reinterpret_cast<const uint32_t *>(&h1);
+        return;
+    }
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[pl] = *reinterpret_cast<const uint32_t *>(&h);
+        a -= __uint_as_float(w[pl] << 16);
+        b -= __uint_as_float(w[pl] & 0xFFFF0000u);
+    }
+}
+#endif

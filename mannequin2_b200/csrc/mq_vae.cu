@@ -12,12 +12,12 @@
 //             product and the dW product read), [mean | logstd] heads as ONE product           n_hidden + 1
 //   latent:   Clip, reparameterised sample (vae.py:50 / distrib.py:48-51), DKL (vae.py:13-24)       1 (+ 1 pack of z)
 //   decoder:  hidden layers, [mean | logstd] heads as one 400 x 1568 product                   n_hidden + 1
-//   head:     Gaussian log-prob of the batch (distrib.py:61-68), Clip rule, dZ in place            1 (+ 1 pack)
+//   head:     Gaussian log-prob of the batch (distrib.py:61-68), Clip rule, dZ written as operand planes       1
 //   backward: per layer dW = a^T dZ (+ bias row; split along the batch, fixed-order finish: 2 launches) and
 //             dA = dZ W^T with tanh' in the epilogue, which again emits operand planes               3 per layer
 //   latent backward, encoder backward, clipped-momentum step (vae.py:66-69)
 //
-// = 30 launches for one hidden layer per side, all products on the TMA-fed tcgen05 GEMM (mq_gemm_tma.cu) in the operand
+// = 24 launches for one hidden layer per side, all products on the TMA-fed tcgen05 GEMM (mq_gemm_tma.cu) in the operand
 // format `tc` names (default fp16x2: fp32 products).  Bit-reproducible: fixed split-K order, no atomics.
 //
 // Parameter layout (the flat vector of decoder.logprob, DFS post-order of mannequin/basicnet.py:66-77):
@@ -149,6 +149,23 @@ static int vae_dims(const mq_vae_t *v, VaeDims *d, const char *what) {
     return MQ_OK;
 }
 
+// ---- side stream for the weight-gradient products -----------------------------------------------------------------------
+// Nothing but the final momentum step reads a weight gradient, while the input-gradient products form the critical path of the
+// backward pass and several of them are small (32-64 CTAs).  The dW products (+ their finishes) therefore run on a side stream,
+// forked after the kernel that produces their operand and joined before the step ends: event record / wait pairs, which a CUDA
+// graph capture of the calling stream turns into fork / join edges.  Stream and events are created once by mq_vae_ws_init
+// (outside any capture); without them the plan runs serially on the caller's stream.
+struct VaeAsync { cudaStream_t side; cudaEvent_t ev[2 * VAE_MAX_HIDDEN + 4]; bool ok; };
+static VaeAsync g_async = {};
+
+static void vae_async_init() {
+    if (g_async.ok) return;
+    if (cudaStreamCreateWithFlags(&g_async.side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
+    for (auto &e : g_async.ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    g_async.ok = true;
+}
+
 // ---- kernels ---------------------------------------------------------------------------------------------------------
 
 // the row of ones (plane 0 only) under the transposed activations written by the GEMM epilogue: bias gradients as one
@@ -208,34 +225,87 @@ vae_latent_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ mu
     dzh[r * 2 * Lp + Lp + j] = g1 + g2;
 }
 
-// Decoder heads -> log-prob of the batch and dZ, in place.  cd = h [W_m | W_s] (columns 0 .. D-1 and Dp .. Dp+D-1).
+// Decoder heads -> log-prob of the batch and dZ as OPERAND PLANES.  cd = h [W_m | W_s] (columns 0 .. D-1 and Dp .. Dp+D-1).
 //   logprob = -D/2 ln 2 pi - sum(ls + 0.5 ((x - mean) / exp(ls))^2)  (distrib.py:61-68) with ls = clip(raw);
 //   d/dmean = (x - mean) exp(-2 ls), d/dls = ((x - mean) exp(-ls))^2 - 1, then the Clip rule, times the upstream
 //   gradient `up` = 1 / batch: parameter gradients are batch MEANS (basicnet.py:231-236), and dividing here instead of
 //   after the dW products keeps dZ -- up to exp(12) (x - mean)^2 at the lower clip -- inside the fp16 range of the
-//   fp16x2 operand format for any realistic batch.  One warp per row.
+//   fp16x2 operand format for any realistic batch.
+// dZ (batch x 2 Dp, the largest tensor of the step) is never stored as fp32: a block owns 16 batch rows and walks the pixels
+// in blocks of 128; 16 threads take a row and each writes its 8 + 8 values straight into the K-major planes the dA product
+// reads, and, through a shared-memory tile, thread-per-pixel into the planes of dZ^T the dW product reads (the block's 16
+// batch rows are one 32-byte sector of a row of dZ^T).
+#define VAE_HEAD_ROWS 16
+#define VAE_HEAD_COLS 128
+template <int P, int F>
 __global__ void __launch_bounds__(MQ_NT)
-vae_head_kernel(float *__restrict__ cd, const float *__restrict__ b_m, const float *__restrict__ b_s, const float *__restrict__ x,
-                int64_t rows, int D, int Dp, float lo, float hi, float up, float *__restrict__ logprob) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x * MQ_NT + threadIdx.x) >> 5;
-    if (r >= rows) return;
-    float *row = cd + r * 2 * Dp;
+vae_head_emit_kernel(const float *__restrict__ cd, const float *__restrict__ b_m, const float *__restrict__ b_s,
+                     const float *__restrict__ x, int64_t rows, int D, int Dp, float lo, float hi, float up, float *__restrict__ logprob,
+                     __nv_bfloat16 *__restrict__ out_k, int64_t k_rows_pad, int64_t k_kpad, __nv_bfloat16 *__restrict__ out_t, int64_t t_rows_pad,
+                     int64_t t_kpad) {
+    __shared__ float tile[2][VAE_HEAD_ROWS][VAE_HEAD_COLS + 1];           // [mean | logstd][batch row][pixel]
+    const int row = threadIdx.x >> 4, grp = threadIdx.x & 15;             // phase 1: 16 threads per batch row, 8 pixels each
+    const int64_t b0 = (int64_t)blockIdx.x * VAE_HEAD_ROWS, b = b0 + row;
+    const bool row_ok = b < rows;
     float acc = 0.0f;
-#pragma unroll 4
-    for (int j = lane; j < D; j += 32) {
-        const float m = row[j] + b_m[j];
-        const float raw = row[Dp + j] + b_s[j];
-        const float l = fminf(fmaxf(raw, lo), hi);
-        const float inv = expf(-l);
-        const float zz = (x[r * D + j] - m) * inv;
-        acc += l + 0.5f * zz * zz;
-        row[j] = up * (zz * inv);
-        row[Dp + j] = up * vae_clip_rule(raw, zz * zz - 1.0f, lo, hi);
-    }
+    for (int j0 = 0; j0 < D; j0 += VAE_HEAD_COLS) {
+        const int j = j0 + grp * 8;
+        float dm[8], dl[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) logprob[r] = -(float)D * VAE_HALF_LOG_2PI - acc;
+        for (int i = 0; i < 8; ++i) { dm[i] = 0.0f; dl[i] = 0.0f; }
+        if (row_ok && j < D) {
+            const float *cm = cd + b * 2 * Dp + j, *cl = cm + Dp, *xr = x + b * D + j;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (j + i < D) {
+                    const float m = cm[i] + b_m[j + i];
+                    const float raw = cl[i] + b_s[j + i];
+                    const float l = fminf(fmaxf(raw, lo), hi);
+                    const float inv = expf(-l);
+                    const float zz = (xr[i] - m) * inv;
+                    acc += l + 0.5f * zz * zz;
+                    dm[i] = up * (zz * inv);
+                    dl[i] = up * vae_clip_rule(raw, zz * zz - 1.0f, lo, hi);
+                }
+            }
+            uint32_t wm[4][P], wl[4][P];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { gm_split_pair<P, F>(dm[2 * i], dm[2 * i + 1], wm[i]); gm_split_pair<P, F>(dl[2 * i], dl[2 * i + 1], wl[i]); }
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+                __nv_bfloat16 *o = out_k + ((int64_t)pl * k_rows_pad + b) * k_kpad + j;
+                *reinterpret_cast<uint4 *>(o) = make_uint4(wm[0][pl], wm[1][pl], wm[2][pl], wm[3][pl]);
+                *reinterpret_cast<uint4 *>(o + Dp) = make_uint4(wl[0][pl], wl[1][pl], wl[2][pl], wl[3][pl]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { tile[0][row][grp * 8 + i] = dm[i]; tile[1][row][grp * 8 + i] = dl[i]; }
+        __syncthreads();
+        // phase 2: a thread per (head, pixel): the 16 batch rows of the block are one 32-byte sector of a row of dZ^T (with 8
+        // rows per block every store was half a sector and the kernel took as long as the fp32 round trip it replaces)
+        {
+            const int tcol = threadIdx.x & (VAE_HEAD_COLS - 1), h = threadIdx.x >> 7;
+            if (j0 + tcol < D) {
+                const int64_t c = (int64_t)h * Dp + j0 + tcol;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (b0 + q * 8 >= t_kpad) continue;
+                    uint32_t w[4][P];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gm_split_pair<P, F>(tile[h][q * 8 + 2 * i][tcol], tile[h][q * 8 + 2 * i + 1][tcol], w[i]);
+#pragma unroll
+                    for (int pl = 0; pl < P; ++pl)
+                        *reinterpret_cast<uint4 *>(out_t + ((int64_t)pl * t_rows_pad + c) * t_kpad + b0 + q * 8) = make_uint4(w[0][pl], w[1][pl], w[2][pl], w[3][pl]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    if (grp == 0 && row_ok) logprob[b] = -(float)D * VAE_HALF_LOG_2PI - acc;
 }
 
 // dW (+ bias row) = alpha * sum over the K splits, in split order; columns [0, nd0) go to dst0 (row stride nd0), columns
@@ -325,6 +395,7 @@ extern "C" int mq_vae_ws_init(const mq_vae_t *v, void *ws, int64_t ws_bytes, voi
     MQ_REQUIRE(ws && ws_bytes >= vae_ws(d, nullptr).bytes + 2048, MQ_ERR_INVALID, "mq_vae_ws_init: workspace smaller than mq_vae_ws_bytes()");
     // every plane image is zero outside what the packs and the GEMM epilogues write (padding rows and columns)
     if (cudaMemsetAsync(ws, 0, (size_t)ws_bytes, (cudaStream_t)stream) != cudaSuccess) return mq_check_launch("mq_vae_ws_init");
+    vae_async_init();
     const VaeWs w = vae_ws(d, ws);
     const unsigned short one = (d.mode & MQ_TC_FP16) ? (unsigned short)0x3C00 : (unsigned short)0x3F80;      // 1.0 as fp16 / bf16
     for (int i = 0; i < d.n; ++i) {
@@ -349,6 +420,16 @@ extern "C" int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x
     const int64_t B = d.B, D = d.D, H = d.H, L = d.L, Lp = d.Lp, Dp = d.Dp;
     const int n = (int)d.n;
     const float lo = v->clip_lo, hi = v->clip_hi, inv_b = 1.0f / (float)B;
+
+    // the side stream, ordered after everything issued to `stream` so far (or `stream` itself: serial plan)
+    int n_forks = 0;
+    auto side_after_main = [&]() -> void * {
+        if (!g_async.ok) return stream;
+        cudaEventRecord(g_async.ev[n_forks], (cudaStream_t)stream);
+        cudaStreamWaitEvent(g_async.side, g_async.ev[n_forks], 0);
+        ++n_forks;
+        return (void *)g_async.side;
+    };
 
     // ---- 1. weights in both operand layouts + the batch: one launch ---------------------------------------------------
     // forward operand of W [in, out]: rows = out, K = in  (B^T(n, k) = W[k, n]: rows are the unit-stride axis)
@@ -410,26 +491,31 @@ extern "C" int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x
         const VaeGemm p = {w.dk[n - 1], d.Bp, w.wf_dh, rp(2 * Dp), B, 2 * Dp, H};
         VAE_TRY(vae_product(d, p, w.cd, 2 * Dp, EPI_SCALE, nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, stream));
     }
-    MQ_LAUNCH(vae_head_kernel, (unsigned)mq_ceil_div(B * 32, MQ_NT), MQ_NT, 0, stream, w.cd, theta + o.b_m, theta + o.b_s, x, B, (int)D, (int)Dp, lo, hi,
-              inv_b, logprob);
     {
-        GmPackJob jobs[2];
-        jobs[0] = vae_job(w.cd, 2 * Dp, 1, B, 2 * Dp, 0, w.gdk, d.Bp, kp(2 * Dp), 0, 0, true);
-        jobs[1] = vae_job(w.cd, 1, 2 * Dp, 2 * Dp, B, 0, w.gdt, rp(2 * Dp), d.Bk, 0, 0, true);
-        VAE_TRY(mq_gemm_tma_pack_multi(jobs, 2, d.mode, stream));
+        const unsigned nb = (unsigned)mq_ceil_div(B, VAE_HEAD_ROWS);
+        __nv_bfloat16 *gk = (__nv_bfloat16 *)w.gdk, *gt = (__nv_bfloat16 *)w.gdt;
+#define VAE_HEAD_GO(P_, F_)                                                                                                            \
+        do { auto kh = vae_head_emit_kernel<P_, F_>;                                                                                     \
+             MQ_LAUNCH(kh, nb, MQ_NT, 0, stream, (const float *)w.cd, theta + o.b_m, theta + o.b_s, x, B, (int)D, (int)Dp, lo, hi, inv_b, \
+                       logprob, gk, d.Bp, kp(2 * Dp), gt, rp(2 * Dp), d.Bk); } while (0)
+        if (d.planes == 3) VAE_HEAD_GO(3, 0);
+        else if (d.planes == 2 && (d.mode & MQ_TC_FP16)) VAE_HEAD_GO(2, 1);
+        else if (d.planes == 2) VAE_HEAD_GO(2, 0);
+        else VAE_HEAD_GO(1, 0);
+#undef VAE_HEAD_GO
     }
 
     // ---- 4. decoder backward -----------------------------------------------------------------------------------------------
     {
         const VaeGemm pw = {w.dt[n - 1], rp(H + 1), w.gdt, rp(2 * Dp), H + 1, 2 * Dp, B};
-        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.w_m, D, grad + o.w_s, Dp, D, stream));
+        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.w_m, D, grad + o.w_s, Dp, D, side_after_main()));
         const VaeGemm px = {w.gdk, d.Bp, w.wb_dh, rp(H), B, H, 2 * Dp};
         VAE_TRY(vae_product(d, px, nullptr, 0, EPI_ACT_GRAD, nullptr, w.da[n - 1], w.gk_d[n - 1], d.Bp, kp(H), w.gt_d[n - 1], rp(H), d.Bk, stream));
     }
     for (int i = n - 1; i >= 0; --i) {
         const int64_t in = i == 0 ? L : H;
         const VaeGemm pw = {i == 0 ? w.zt : w.dt[i - 1], rp(in + 1), w.gt_d[i], rp(H), in + 1, H, B};
-        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.wd[i], H, nullptr, 0, 0, stream));
+        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.wd[i], H, nullptr, 0, 0, side_after_main()));
         const VaeGemm px = {w.gk_d[i], d.Bp, w.wb_d[i], rp(in), B, in, H};
         if (i > 0)
             VAE_TRY(vae_product(d, px, nullptr, 0, EPI_ACT_GRAD, nullptr, w.da[i - 1], w.gk_d[i - 1], d.Bp, kp(H), w.gt_d[i - 1], rp(H), d.Bk, stream));
@@ -448,7 +534,7 @@ extern "C" int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x
     }
     {
         const VaeGemm pw = {w.et[n - 1], rp(H + 1), w.ght, rp(2 * Lp), H + 1, 2 * Lp, B};
-        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.w_mu, L, grad + o.w_ls, Lp, L, stream));
+        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.w_mu, L, grad + o.w_ls, Lp, L, side_after_main()));
         const VaeGemm px = {w.ghk, d.Bp, w.wb_eh, rp(H), B, H, 2 * Lp};
         VAE_TRY(vae_product(d, px, nullptr, 0, EPI_ACT_GRAD, nullptr, w.ea[n - 1], n > 1 ? w.gk_e[n - 1] : nullptr, d.Bp, kp(H), w.gt_e[n - 1], rp(H), d.Bk,
                             stream));
@@ -456,12 +542,16 @@ extern "C" int mq_vae_grad(const mq_vae_t *v, const float *theta, const float *x
     for (int i = n - 1; i >= 0; --i) {
         const int64_t in = i == 0 ? D : H;
         const VaeGemm pw = {i == 0 ? w.xt : w.et[i - 1], rp(in + 1), w.gt_e[i], rp(H), in + 1, H, B};
-        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.we[i], H, nullptr, 0, 0, stream));
+        VAE_TRY(vae_dw(d, pw, w.partials, 1.0f, grad + o.we[i], H, nullptr, 0, 0, side_after_main()));
         if (i > 0) {
             const VaeGemm px = {w.gk_e[i], d.Bp, w.wb_e[i], rp(H), B, H, H};
             VAE_TRY(vae_product(d, px, nullptr, 0, EPI_ACT_GRAD, nullptr, w.ea[i - 1], i > 1 ? w.gk_e[i - 1] : nullptr, d.Bp, kp(H), w.gt_e[i - 1], rp(H), d.Bk,
                                 stream));
         }
+    }
+    if (n_forks > 0) {                   // join: the caller's stream continues after the last weight gradient
+        cudaEventRecord(g_async.ev[n_forks], g_async.side);
+        cudaStreamWaitEvent((cudaStream_t)stream, g_async.ev[n_forks], 0);
     }
     MQ_CHECK_LAUNCH("mq_vae_grad");
     return MQ_OK;
