@@ -907,7 +907,8 @@ class VAEWorkload(object):
                     achieved=tf, peak=peaks["bf16"], unit="TFLOP/s", frac=tf / peaks["bf16"], traffic=None,
                     peak_source=peaks["source"], ms_per_launch=ms, issued_bf16_tflops=3 * tf, issued_frac=3 * tf / peaks["bf16"],
                     note="fp32-exact product = 3 pairs of scaled fp16 planes issued as wide tcgen05 instructions from TMA-loaded, "
-                         "128-byte-swizzled planes; the time is pack (2 launches) + GEMM of a 2.6 GFLOP product (DESIGN.md 3.5)")
+                         "128-byte-swizzled planes; the time is pack (1 launch) + GEMM of a 2.6 GFLOP product through mq_gemm_ex; inside the fused "
+                         "plan the operands arrive packed (DESIGN.md 3.5, 3.8)")
 
 
 class ClosedLoopWorkload(PPOLargeWorkload):

@@ -224,6 +224,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     tc_publish();
     const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem, 0);
+    // programmatic dependent launch: everything above (TMEM allocation, barrier init, tensor-map prefetch) may run while the
+    // previous kernel of the stream finishes; nothing that kernel wrote is touched before this wait, and the next kernel may
+    // be scheduled as soon as SMs free up
+    mq_pdl_wait();
+    mq_pdl_trigger();
 
     // tile t -> (m0, n0, first chunk, chunks)
 #define GM_TILE_DECODE(t_)                                                                                         \
@@ -542,8 +547,8 @@ int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64
     do {                                                                                                                   \
         e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
         if (e == cudaSuccess)                                                                                              \
-            gemm_tma_kernel<P_, F_, SP_><<<grid, GM_NT, GmCfg<P_>::SMEM, (cudaStream_t)stream>>>(map_a, map_b, g, em, (int)a_rows_pad, \
-                                                                                                (int)b_rows_pad, (int)(splits > 1 ? splits : 1)); \
+            e = mq_launch_pdl(gemm_tma_kernel<P_, F_, SP_>, dim3(grid), dim3(GM_NT), (size_t)GmCfg<P_>::SMEM, stream, map_a, map_b, g, em, \
+                              (int)a_rows_pad, (int)b_rows_pad, (int)(splits > 1 ? splits : 1));                                \
     } while (0)
 #define GM_GO_P(SP_)                                              \
     do {                                                          \
