@@ -233,6 +233,14 @@ int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, const float
                             const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx,
                             void *ws, int64_t ws_bytes, void *stream, void *side_stream, void *const *events);
 
+/* mq_mlp_forward_ws / mq_mlp_backward_overlap with per-call MQ_TC_* flags for the layers that run on the tcgen05 GEMM
+ * (tc = 0: three bf16 planes, any operand range; 2 | MQ_TC_FP16: fp16x2, the same fp32 bar for |operand| < 65504). */
+int mq_mlp_forward_tc(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx, int64_t batch,
+                      float *acts, int32_t tc, void *ws, int64_t ws_bytes, void *stream);
+int mq_mlp_backward_tc(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                       const float *acts, float *dy, int64_t batch, float scale, float *grad, float *dx, int32_t tc,
+                       void *ws, int64_t ws_bytes, void *stream, void *side_stream, void *const *events);
+
 /* mnist/mlp.py:24-43 at the reference's batch size as ONE persistent launch for a block of optimiser steps
  * (csrc/mq_mlp_fused.cu): 128 CTAs = 16 clusters of 8; the first layer stays split over the CTAs' shared memory with its
  * Adam moments, the 8 K-slice partials of a column slice meet through distributed shared memory, the middle of the net is

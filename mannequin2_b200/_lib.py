@@ -106,6 +106,8 @@ SIGNATURES = {
     "mq_mlp_ws_bytes": (c_int64, [NETP, c_int64]),
     "mq_mlp_forward": (c_int, [NETP, P, P, P, c_int64, P, P]),
     "mq_mlp_forward_ws": (c_int, [NETP, P, P, P, c_int64, P, P, c_int64, P]),
+    "mq_mlp_forward_tc": (c_int, [NETP, P, P, P, c_int64, P, c_int32, P, c_int64, P]),
+    "mq_mlp_backward_tc": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, c_int32, P, c_int64, P, P, P]),
     "mq_mlp_backward": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, P, c_int64, P]),
     "mq_mlp_backward_overlap": (c_int, [NETP, P, P, P, P, P, c_int64, c_float, P, P, P, c_int64, P, P, P]),
     "mq_mlp_train_block_ws_bytes": (c_int64, [NETP, c_int64]),

@@ -163,6 +163,206 @@ extern "C" int64_t mq_gemm_ws_bytes(int64_t m, int64_t n, int64_t k) {
     return (ffma > tc ? ffma : tc) + 256;
 }
 
+// ---- skinny products of a narrow output layer at large batch -------------------------------------------------------
+// The 128 -> 10 layer of mnist/mlp.py at batch 65,536 is three products with one dimension <= 16: through the 64 x 64
+// tiles of gemm_kernel they did 6x the arithmetic of the layer and ran at a tenth of the HBM rate the operands allow
+// (49 + 67 + 46 us against ~6 us of traffic each).  One small kernel per shape, all bound by reading or writing the
+// batch x width activations once:
+//   SKINNY_N   C[m, n <= 16]  = epi(A[m, k] B[k, n])     warp per row, lanes along k, B in shared memory
+//   SKINNY_K   C[m, n]        = epi(A[m, k <= 16] B[k, n])     warp per row, lanes along n, B in shared memory
+//   SKINNY_DW  C[m <= 512, n <= 16] = alpha A[m, k] B[k, n] with k = the batch and A stored k-major (dW = x^T g):
+//              a block per slab of k, a thread per row m with its n sums in registers, fixed-order finish over the slabs
+#define SKINNY_MAX 16
+#define SKINNY_SMEM_FLOATS 4096
+#define SKINNY_ROWS 128                  // rows of A per block (skinny N): a thread per row, A staged 32 columns at a time
+
+// C[m, n <= 16] = epi(A[m, k] B[k, n]).  A block stages 128 rows x 32 columns of A in shared memory with coalesced loads
+// (every thread has 16 independent loads in flight), then thread r walks its row against B (shared memory, broadcast reads).
+__global__ void __launch_bounds__(SKINNY_ROWS)
+gemm_skinny_n_kernel(GemmArgs g) {
+    __shared__ float bs[SKINNY_SMEM_FLOATS];                 // B[k][n]
+    __shared__ float as[SKINNY_ROWS][33];
+    const int n = (int)g.n, k = (int)g.k;
+    for (int e = threadIdx.x; e < k * n; e += SKINNY_ROWS) bs[e] = g.b[(int64_t)(e / n) * g.b_rs + (int64_t)(e % n) * g.b_cs];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int64_t r0 = (int64_t)blockIdx.x * SKINNY_ROWS; r0 < g.m; r0 += (int64_t)gridDim.x * SKINNY_ROWS) {
+        float acc[SKINNY_MAX];
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j) acc[j] = 0.0f;
+        for (int kb = 0; kb < k; kb += 32) {
+            __syncthreads();
+            // warp w loads rows w, w + 4, ...: 32 consecutive columns of a row per instruction
+            float v[SKINNY_ROWS / 4];
+#pragma unroll
+            for (int i = 0; i < SKINNY_ROWS / 4; ++i) {
+                const int64_t r = r0 + wrp + 4 * i;
+                v[i] = (r < g.m && kb + lane < k) ? __ldg(g.a + (g.idx ? (int64_t)g.idx[r] : r) * g.a_rs + (int64_t)(kb + lane) * g.a_cs) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < SKINNY_ROWS / 4; ++i) as[wrp + 4 * i][lane] = v[i];
+            __syncthreads();
+            const int kn = k - kb < 32 ? k - kb : 32;
+            for (int kk = 0; kk < kn; ++kk) {
+                const float a = as[threadIdx.x][kk];
+                const float *brow = bs + (kb + kk) * n;
+#pragma unroll
+                for (int j = 0; j < SKINNY_MAX; ++j) if (j < n) acc[j] = fmaf(a, brow[j], acc[j]);
+            }
+        }
+        const int64_t r = r0 + threadIdx.x;
+        if (r < g.m) {
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j) if (j < n) g.c[r * g.n + j] = gemm_epilogue(g, acc[j], r, j);
+        }
+    }
+}
+
+// C[m, n] = epi(A[m, k <= 16] B[k, n]): elementwise over C, four consecutive columns per thread (n % 4 == 0): every load is
+// independent of every other, the k values of a row are shared by the threads of the row through L1.
+__global__ void __launch_bounds__(MQ_NT)
+gemm_skinny_k_kernel(GemmArgs g) {
+    __shared__ __align__(16) float bs[SKINNY_SMEM_FLOATS];   // B[k][n]
+    const int n = (int)g.n, k = (int)g.k, nq = n >> 2;
+    for (int e = threadIdx.x; e < k * n; e += MQ_NT) bs[e] = g.b[(int64_t)(e / n) * g.b_rs + (int64_t)(e % n) * g.b_cs];
+    __syncthreads();
+    const int64_t total = g.m * nq;
+    for (int64_t e = (int64_t)blockIdx.x * MQ_NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * MQ_NT) {
+        const int64_t r = e / nq;
+        const int c0 = (int)(e - r * nq) * 4;
+        const float *arow = g.a + (g.idx ? (int64_t)g.idx[r] : r) * g.a_rs;
+        float a[SKINNY_MAX];
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j) a[j] = j < k ? __ldg(arow + (int64_t)j * g.a_cs) : 0.0f;
+        float4 y4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (g.epi == EPI_ACT_GRAD) y4 = *reinterpret_cast<const float4 *>(g.y + r * g.n + c0);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j) {
+            if (j < k) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(bs + j * n + c0);
+                acc[0] = fmaf(a[j], b4.x, acc[0]); acc[1] = fmaf(a[j], b4.y, acc[1]);
+                acc[2] = fmaf(a[j], b4.z, acc[2]); acc[3] = fmaf(a[j], b4.w, acc[3]);
+            }
+        }
+        float4 o;
+        if (g.epi == EPI_ACT_GRAD) {
+            o.x = mq_act_grad(y4.x, acc[0], g.act, g.leak); o.y = mq_act_grad(y4.y, acc[1], g.act, g.leak);
+            o.z = mq_act_grad(y4.z, acc[2], g.act, g.leak); o.w = mq_act_grad(y4.w, acc[3], g.act, g.leak);
+        } else if (g.epi == EPI_BIAS_ACT) {
+            o.x = mq_act_apply(acc[0] + g.bias[c0], g.act, g.leak); o.y = mq_act_apply(acc[1] + g.bias[c0 + 1], g.act, g.leak);
+            o.z = mq_act_apply(acc[2] + g.bias[c0 + 2], g.act, g.leak); o.w = mq_act_apply(acc[3] + g.bias[c0 + 3], g.act, g.leak);
+        } else {
+            o = make_float4(g.alpha * acc[0], g.alpha * acc[1], g.alpha * acc[2], g.alpha * acc[3]);
+        }
+        *reinterpret_cast<float4 *>(g.c + r * g.n + c0) = o;
+    }
+}
+
+// partial[slab][m][n]; A(m, kk) = a[m + col(kk) * a_cs] (rows of A are the unit-stride axis), B(kk, j) = b[kk * b_rs + j].
+// Thread = row m; the loop over the slab is unrolled by 8 with the loads of a step issued before its arithmetic.
+__global__ void __launch_bounds__(MQ_NT)
+gemm_skinny_dw_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ partial) {
+    __shared__ float bs[8 * SKINNY_MAX];
+    const int n = (int)g.n;
+    const int64_t k0 = (int64_t)blockIdx.x * k_per_slab;
+    const int64_t k1 = k0 + k_per_slab < g.k ? k0 + k_per_slab : g.k;
+    float acc[2][SKINNY_MAX];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j) acc[p][j] = 0.0f;
+    for (int64_t kb = k0; kb < k1; kb += 8) {
+        __syncthreads();
+        if (threadIdx.x < 8 * n) {
+            const int kk = threadIdx.x / n, j = threadIdx.x - kk * n;
+            bs[kk * SKINNY_MAX + j] = kb + kk < k1 ? __ldg(g.b + (kb + kk) * g.b_rs + j) : 0.0f;
+        }
+        float a[2][8];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int64_t m = threadIdx.x + p * MQ_NT;
+            const bool ones = g.a_ones_row > 0 && m >= g.a_ones_row;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = 0.0f;
+                if (m < g.m && kb + i < k1) {
+                    const int64_t sk = (g.idx && g.idx_on_k) ? (int64_t)g.idx[kb + i] : kb + i;
+                    v = ones ? 1.0f : __ldg(g.a + m + sk * g.a_cs);
+                }
+                a[p][i] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j)
+                if (j < n) {
+                    const float bv = bs[i * SKINNY_MAX + j];
+                    acc[0][j] = fmaf(a[0][i], bv, acc[0][j]);
+                    acc[1][j] = fmaf(a[1][i], bv, acc[1][j]);
+                }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int64_t m = threadIdx.x + p * MQ_NT;
+        if (m < g.m) {
+            float *dst = partial + ((int64_t)blockIdx.x * g.m + m) * n;
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j) if (j < n) dst[j] = acc[p][j];
+        }
+    }
+}
+
+// c[e] = alpha * sum over the slabs of partial[slab][e], a warp per element: lanes take slabs lane, lane + 32, ... (all loads
+// independent), then a fixed butterfly -- bit-reproducible
+__global__ void __launch_bounds__(MQ_NT)
+gemm_skinny_finish_kernel(const float *__restrict__ partial, int slabs, int64_t total, float alpha, float *__restrict__ c) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = ((int64_t)blockIdx.x * MQ_NT + threadIdx.x) >> 5;
+    if (e >= total) return;
+    float s = 0.0f;
+    for (int z = lane; z < slabs; z += 32) s += __ldg(partial + (int64_t)z * total + e);
+    s = mq_warp_sum(s);
+    if (lane == 0) c[e] = alpha * s;
+}
+
+// 1 = handled.  Shapes outside the kernels' limits fall through to the general kernels.
+static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stream) {
+#ifdef MQ_EMU
+    (void)g; (void)ws; (void)ws_bytes; (void)stream;
+    return 0;
+#else
+    const int sms = mq_sm_count();
+    if (g.m >= 2048 && g.n <= SKINNY_MAX && g.k >= 32 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) && g.a_ones_row == 0) {
+        int64_t nb = mq_ceil_div(g.m, SKINNY_ROWS);
+        if (nb > (int64_t)sms * 8) nb = (int64_t)sms * 8;
+        MQ_LAUNCH(gemm_skinny_n_kernel, (unsigned)nb, SKINNY_ROWS, 0, stream, g);
+        return 1;
+    }
+    if (g.m >= 2048 && g.k <= SKINNY_MAX && g.n >= 32 && (g.n & 3) == 0 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) &&
+        g.a_ones_row == 0 && (((uintptr_t)g.c | (uintptr_t)g.y) & 15) == 0) {
+        int64_t nb = mq_ceil_div(g.m * (g.n >> 2), MQ_NT);
+        if (nb > (int64_t)sms * 16) nb = (int64_t)sms * 16;
+        MQ_LAUNCH(gemm_skinny_k_kernel, (unsigned)nb, MQ_NT, 0, stream, g);
+        return 1;
+    }
+    if (ws && g.k >= 4096 && g.n <= SKINNY_MAX && g.m <= 2 * MQ_NT && g.a_rs == 1 && g.b_cs == 1 && g.epi == EPI_SCALE && !(g.idx && !g.idx_on_k)) {
+        int64_t slabs = (int64_t)sms * 8;
+        if (slabs > g.k / 32) slabs = g.k / 32;
+        while (slabs > 1 && slabs * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) --slabs;
+        const int64_t per = mq_round_up(mq_ceil_div(g.k, slabs), 8);
+        slabs = mq_ceil_div(g.k, per);
+        if (slabs * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) return 0;
+        MQ_LAUNCH(gemm_skinny_dw_kernel, (unsigned)slabs, MQ_NT, 0, stream, g, per, (float *)ws);
+        const int64_t total = g.m * g.n;
+        MQ_LAUNCH(gemm_skinny_finish_kernel, (unsigned)mq_ceil_div(total * 32, MQ_NT), MQ_NT, 0, stream, (const float *)ws, (int)slabs, total, g.alpha, g.c);
+        return 1;
+    }
+    return 0;
+#endif
+}
+
 // Decide kernel, tile size and split-K; `ws` may be NULL (then no split and no tensor-core path).
 static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, int32_t tc, void *stream, const char *what) {
     if (g.m <= 0 || g.n <= 0) return MQ_OK;
@@ -188,6 +388,10 @@ static int gemm_run(GemmArgs g, void *ws, int64_t ws_bytes, int32_t tc, void *st
         if (rc != MQ_ERR_UNSUPPORTED) return rc;
     }
     MQ_REQUIRE(!(tc & MQ_TC_FORCE), MQ_ERR_INVALID, "%s: MQ_TC_FORCE needs a workspace of mq_gemm_ws_bytes()", what);
+    if (gemm_skinny(g, ws, ws_bytes, stream)) {
+        MQ_CHECK_LAUNCH(what);
+        return MQ_OK;
+    }
     const bool big = mq_ceil_div(g.m, 64) * mq_ceil_div(g.n, 64) >= sms / 2;
     const int bm = big ? 64 : 32;
     const int64_t tiles = mq_ceil_div(g.m, bm) * mq_ceil_div(g.n, bm);
@@ -301,6 +505,13 @@ extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const flo
 // 784 -> 128 layer of mnist/mlp.py at batch 128: 16 tiles) are split along K, deterministically.
 extern "C" int mq_mlp_forward_ws(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                                  int64_t batch, float *acts, void *ws, int64_t ws_bytes, void *stream) {
+    return mq_mlp_forward_tc(net, theta, x, row_idx, batch, acts, 0, ws, ws_bytes, stream);
+}
+
+// The same with per-call MQ_TC_* flags for the layers that run on the tcgen05 GEMM (0 = three bf16 planes, any range;
+// 2 | MQ_TC_FP16 = fp16x2: the same fp32 bar in half the tensor work and 2/3 of the packed bytes, for |operand| < 65504).
+extern "C" int mq_mlp_forward_tc(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
+                                 int64_t batch, float *acts, int32_t tc, void *ws, int64_t ws_bytes, void *stream) {
     int rc = net_check(net, "mq_mlp_forward");
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_mlp_forward: negative batch");
@@ -317,7 +528,7 @@ extern "C" int mq_mlp_forward_ws(const mq_net_t *net, const float *theta, const 
         g.c = out; g.m = batch; g.n = net->out[l]; g.k = net->in[l];
         g.alpha = 1.0f; g.epi = EPI_BIAS_ACT; g.act = net->act[l]; g.leak = net->leak[l];
         g.bias = theta + net->b_off[l];
-        rc = gemm_run(g, ws, ws ? ws_bytes : 0, 0, stream, "mq_mlp_forward");
+        rc = gemm_run(g, ws, ws ? ws_bytes : 0, tc, stream, "mq_mlp_forward");
         if (rc != MQ_OK) return rc;
         inp = out;
         out += (int64_t)net->out[l] * batch;
@@ -340,6 +551,14 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
                                        const int32_t *row_idx, const float *acts, float *dy, int64_t batch,
                                        float scale, float *grad, float *dx, void *ws, int64_t ws_bytes,
                                        void *stream, void *side_stream, void *const *events) {
+    return mq_mlp_backward_tc(net, theta, x, row_idx, acts, dy, batch, scale, grad, dx, 0, ws, ws_bytes, stream, side_stream, events);
+}
+
+// The same with per-call MQ_TC_* flags (see mq_mlp_forward_tc).
+extern "C" int mq_mlp_backward_tc(const mq_net_t *net, const float *theta, const float *x,
+                                  const int32_t *row_idx, const float *acts, float *dy, int64_t batch,
+                                  float scale, float *grad, float *dx, int32_t tc, void *ws, int64_t ws_bytes,
+                                  void *stream, void *side_stream, void *const *events) {
     int rc = net_check(net, "mq_mlp_backward");
     if (rc != MQ_OK) return rc;
     MQ_REQUIRE(batch >= 1, MQ_ERR_SHAPE, "mq_mlp_backward: empty batch");
@@ -392,7 +611,7 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
         // into b's slot behind W
         const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l];
         if (fuse_bias) { g.m = net->in[l] + 1; g.a_ones_row = net->in[l]; }
-        rc = gemm_run(g, split_ws, split_bytes, 0, w_stream, "mq_mlp_backward(dW)");
+        rc = gemm_run(g, split_ws, split_bytes, tc, w_stream, "mq_mlp_backward(dW)");
         if (rc != MQ_OK) return rc;
         if (!fuse_bias) {
             rc = mq_col_sum(g_cur, nullptr, batch, net->out[l], scale, grad + net->b_off[l], w_stream);
@@ -412,7 +631,7 @@ extern "C" int mq_mlp_backward_overlap(const mq_net_t *net, const float *theta, 
             } else {
                 g.epi = EPI_SCALE;
             }
-            rc = gemm_run(g, main_ws, per, 0, stream, "mq_mlp_backward(dX)");
+            rc = gemm_run(g, main_ws, per, tc, stream, "mq_mlp_backward(dX)");
             if (rc != MQ_OK) return rc;
             g_cur = dst;
         }

@@ -26,7 +26,11 @@ from .ppo import init_mlp
 class MLPTrainer(object):
     def __init__(self, n_in=784, widths=(128, 128, 10), acts=(ACT_LRELU, ACT_LRELU, ACT_NONE), *,
                  leak=0.1, batch=128, horizon=10, lr=1e-3, l2=0.01, params=None, state_dtype="float32",
-                 graph_steps=32, fused=True):
+                 graph_steps=32, fused=True, gemm_mode="fp16x2"):
+        # gemm_mode: operand format of the layers that run on the tcgen05 GEMM (large batches).  "fp16x2" meets the same fp32
+        # bar as "exact" (three bf16 planes) in half the tensor work and 2/3 of the packed bytes; its range precondition
+        # (|operand| < 65504) holds for images, LReLU activations of a normed-column net and their batch-mean gradients.
+        self.tc = _lib.TC_MODES[gemm_mode]
         self.net = _lib.make_net(n_in, list(widths), list(acts), leak=leak)
         if params is None:
             params = init_mlp(n_in, list(widths), 0.1)                # mlp.py:24-27 (init=0.1 head)
@@ -65,13 +69,13 @@ class MLPTrainer(object):
         idx_ptr = idx_ptr if idx_ptr is not None else D.ptr(self.idx) + s * B * 4
         coef_ptr = coef_ptr if coef_ptr is not None else D.ptr(self.coefs) + s * 32
         value, m, v, _ = self.opt.state()
-        D.call("mq_mlp_forward_ws", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, B, D.ptr(self.acts), D.ptr(self.ws), self.wsb,
+        D.call("mq_mlp_forward_tc", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, B, D.ptr(self.acts), self.tc, D.ptr(self.ws), self.wsb,
                D.stream())
         logits = self.acts[self.acts.numel() - B * self.n_out:]
         D.call("mq_softmax_ce_grad", D.ptr(logits), D.ptr(y), idx_ptr, B, self.n_out, self.l2,
                D.ptr(self.dy), D.stream())
-        D.call("mq_mlp_backward_overlap", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
-               D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, D.ptr(self.ws), self.wsb, D.stream(),
+        D.call("mq_mlp_backward_tc", nb, D.ptr(self.theta), D.ptr(x), idx_ptr, D.ptr(self.acts),
+               D.ptr(self.dy), B, 1.0 / B, D.ptr(self.grad), None, self.tc, D.ptr(self.ws), self.wsb, D.stream(),
                None if os.environ.get("MQ_MLP_NO_OVERLAP") else self._side.cuda_stream, self._event_ptrs)
         D.call("mq_adam_step_dev", D.ptr(value), D.ptr(m), D.ptr(v), D.ptr(self.theta), D.ptr(self.grad),
                self.net.n_params, self.opt._code, MQ_F32, coef_ptr, 0, D.stream())

@@ -1204,7 +1204,10 @@ def case_gemm_tc(B):
     close(c1, c2, what="gemm tc vs ffma")
     # layered MLP (mnist/mlp.py and mnist/vae.py encoder shapes) at a batch where every layer is a real contraction:
     # bias + activation epilogue, act' epilogue, gathered rows, split-K weight gradients
-    for n_in, widths, acts, batch, n_src in ((784, [128, 128, 10], [2, 2, 0], 2048, 3000), (784, [400, 40], [1, 0], 4096, 4096)):
+    # (the third configuration: per-call fp16x2 operands through mq_mlp_forward_tc / mq_mlp_backward_tc, and a batch at which
+    # the narrow output layer takes the three skinny-product kernels of mq_gemm.cu)
+    for n_in, widths, acts, batch, n_src, tc in ((784, [128, 128, 10], [2, 2, 0], 2048, 3000, None), (784, [400, 40], [1, 0], 4096, 4096, None),
+                                                 (784, [128, 128, 10], [2, 2, 0], 8192, 3000, L.TC_MODES["fp16x2"])):
         spec, theta, x = mlp_case(rs, n_in, widths, acts, n_src)
         idx = rs.randint(n_src, size=batch).astype(np.int32)
         net = net_of(spec)
@@ -1212,7 +1215,10 @@ def case_gemm_tc(B):
         acts_buf = B.zeros(lib.mq_mlp_acts_floats(net, batch), np.float32)
         wsb = lib.mq_mlp_ws_bytes(net, batch)
         ws = B.zeros(wsb, np.uint8)
-        ok(B, lib.mq_mlp_forward_ws(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), batch, B.ptr(acts_buf), B.ptr(ws), wsb, B.stream))
+        if tc is None:
+            ok(B, lib.mq_mlp_forward_ws(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), batch, B.ptr(acts_buf), B.ptr(ws), wsb, B.stream))
+        else:
+            ok(B, lib.mq_mlp_forward_tc(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), batch, B.ptr(acts_buf), tc, B.ptr(ws), wsb, B.stream))
         outs = O.mlp_forward(theta, spec, x[idx])
         got, pos = B.down(acts_buf), 0
         for o in outs:
@@ -1221,8 +1227,12 @@ def case_gemm_tc(B):
         dy = rs.randn(batch, widths[-1]).astype(np.float32)
         want, wdx = O.mlp_backward(theta, spec, x[idx], outs, dy, want_dx=True)
         grad, dx, hdy = B.zeros(spec["n_params"], np.float32), B.zeros((batch, n_in), np.float32), B.up(dy.copy())
-        ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), batch,
-                                  1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
+        if tc is None:
+            ok(B, lib.mq_mlp_backward(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), batch,
+                                      1.0 / batch, B.ptr(grad), B.ptr(dx), B.ptr(ws), wsb, B.stream))
+        else:
+            ok(B, lib.mq_mlp_backward_tc(net, B.ptr(ht), B.ptr(hx), B.ptr(hi), B.ptr(acts_buf), B.ptr(hdy), batch,
+                                         1.0 / batch, B.ptr(grad), B.ptr(dx), tc, B.ptr(ws), wsb, B.stream, None, None))
         close(B.down(grad), want, what="layered tc grad %s" % (widths,))
         close(B.down(dx), wdx, what="layered tc dx %s" % (widths,))
 
