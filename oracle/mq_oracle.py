@@ -16,6 +16,8 @@ Parity status (see DESIGN.md section "Oracle"):
     The forward expressions are pinned by running the reference code with a
     complex-step stand-in for ``autograd`` (make_golden.py); the closed-form
     derivatives are additionally checked by finite differences;
+  * ``vae_grads`` / ``vae_step`` against one iteration of mnist/vae.py:57-69 run
+    from the reference's own classes (golden/vae_step.npz);
   * ``dkl_uninormal`` / ``clip_*`` against mnist/vae.py imported as a module,
     ``es_apply_returns`` against benchmarks/mutation.py:run() itself,
     ``normalized_observations_step`` against mannequin/gym.py's wrapper, the
