@@ -17,6 +17,8 @@ returns a device-backed flat float32 vector (DeviceVector) holding batch-MEAN
 parameter gradients (basicnet.py:242-249).
 """
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -28,21 +30,30 @@ from ._utils import endswith
 
 # ---------------------------------------------------------------- parameter arena
 class _Arena(object):
+    """Device memory for `Params`, handed out in order so that the parameters of a net built in one go are ONE slice (the
+    flat vector of get_params / load_params).  Only the chunk being filled is held strongly; a full chunk lives as long as
+    a `Params` created in it does (each keeps its chunk alive), so nets that are dropped give their memory back."""
     CHUNK = 1 << 22                      # floats per chunk (16 MB)
 
     def __init__(self):
-        self.chunks = []                 # [tensor, used]
+        self.chunks = []                 # [tensor (the last chunk) or weakref to it (full chunks), floats used]
 
     def alloc(self, n):
         if not self.chunks or self.chunks[-1][1] + n > self.chunks[-1][0].numel():
+            if self.chunks:
+                self.chunks[-1][0] = weakref.ref(self.chunks[-1][0])
             self.chunks.append([D.zeros(max(self.CHUNK, n)), 0])
         c = self.chunks[-1]
         cid, off = len(self.chunks) - 1, c[1]
         c[1] += n
-        return cid, off, c[0][off:off + n]
+        return cid, off, c[0][off:off + n], c[0]
 
     def view(self, cid, off, n):
-        return self.chunks[cid][0][off:off + n]
+        t = self.chunks[cid][0]
+        if isinstance(t, weakref.ref):
+            t = t()
+            assert t is not None, "parameter chunk already released"
+        return t[off:off + n]
 
 
 _arenas = {}
@@ -224,7 +235,7 @@ class Params(Layer):
         shape = tuple(max(1, int(s)) for s in shape)
         assert len(shape) >= 1
         value = np.array(init(*shape), dtype=np.float32).reshape(shape)
-        self._cid, self._off, flat = _arena().alloc(value.size)
+        self._cid, self._off, flat, self._chunk = _arena().alloc(value.size)     # (_chunk: keeps the arena chunk alive)
         flat.copy_(D.from_host(value.reshape(-1)))
         self._flatdev = flat
 

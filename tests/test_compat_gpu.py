@@ -773,6 +773,28 @@ def test_vae_fused_step_at_baseline_shape():
     assert np.max(np.abs(a - theta)) > 1e-5
 
 
+def test_parameter_arena_releases_dropped_nets():
+    """Params live in 16 MB arena chunks so that a net's parameters are one flat slice; a full chunk must go away with the
+    last Params created in it (nets built and dropped in a loop must not accumulate device memory)."""
+    import gc
+    import weakref
+    from mannequin2_b200 import basicnet as bn
+    arena = bn._arena()
+    big = (arena.CHUNK * 3) // 4
+    held = bn.Params(big)                               # forces every later allocation of this size into a new chunk
+    before = len(arena.chunks)
+    for _ in range(3):
+        p = bn.Params(big)
+        assert float(p.dev.sum()) == 0.0
+        del p
+    gc.collect()
+    full = [c[0] for c in arena.chunks[before - 1:-1]]
+    assert len(full) >= 2 and all(isinstance(r, weakref.ref) for r in full)
+    dead = sum(1 for r in full if r() is None)
+    assert dead >= len(full) - 1                        # every dropped chunk is gone; the one `held` lives in may remain
+    assert float(held.dev.sum()) == 0.0 and held.get_params().shape == (big,)
+
+
 def test_reinforce_script_loop_and_reward_log():
     """benchmarks/policy.py:29-47 (plain REINFORCE: episode -> Trajectory.discounted -> RunningNormalize -> tanh ->
     logprob backprop -> Adam) written against `mannequin` / `mannequin.gym`, on a small NumPy environment wrapped in
