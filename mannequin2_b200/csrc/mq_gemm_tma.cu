@@ -28,7 +28,9 @@
 // bar), 2 planes = 16-bit operands, 1 plane = bf16; 2 planes with MQ_TC_FP16 = fp16 planes with the low one scaled by 2^11
 // (x = x0 + 2^-11 x1: fp32 operands to 2^-24, the FFMA bar again, in three plane pairs instead of six -- block 1 of an
 // accumulator set holds exactly the scaled pairs A_0 B_1' + A_1' B_0 and is folded in with one FMA by the owners).
+#ifndef MQ_EMU
 #include <cuda.h>
+#endif
 #include <stdlib.h>
 
 #include "mq_gemm.cuh"
