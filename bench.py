@@ -356,9 +356,9 @@ class PPOLargeWorkload(object):
         self._next = nxt
 
     def launches_per_step(self):
-        # forwards, GAE (memset + scan), normaliser (4), 2 x pack, 2 x image build, then per optimiser step the gradient
-        # kernel + the reduce / exchange / Adam / image kernel
-        return 13 + 2 * self.steps_per_net * 2
+        # 2 forwards (record-fed: + pack + image build each), GAE (memset + scan), normaliser (4), 2 x pack, 2 x image build,
+        # then per optimiser step the gradient kernel + the reduce / exchange / Adam / image kernel
+        return 17 + 2 * self.steps_per_net * 2
 
     def grad_kernel_time(self, net_obj, head, idx_ptr, mb, reps=12):
         """One gradient launch (record-fed tcgen05 kernel -> per-CTA partials), timed alone with CUDA events on its

@@ -266,6 +266,11 @@ int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x, co
 /* The same with per-call MQ_TC_* flags (mq_fused_forward = flags 0). */
 int mq_fused_forward_tc(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                         int64_t batch, float *out, const float *sample, float *logp, int32_t tc, void *stream);
+/* The same from packed records (mq_pack_records) on the record-fed tensor-core kernel, forward only: out[batch, n_out] and /
+ * or logp[batch] (the sample is the record's target); tc_image = operand image of the current parameters
+ * (mq_tc_image_build) in the format `tc` names.  MQ_ERR_UNSUPPORTED when the net does not fit that kernel. */
+int mq_fused_forward_rec(const mq_net_t *net, const float *theta, const float *records, int32_t rec_w, const void *tc_image,
+                         const int32_t *row_idx, int64_t batch, float *out, float *logp, int32_t tc, void *stream);
 /* forward + head + backward in one launch; grad[n_params] = scale * sum_batch */
 int mq_fused_grad(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                   int64_t batch, const mq_head_t *head, float scale, float *grad, float *out,

@@ -116,6 +116,7 @@ SIGNATURES = {
     "mq_fused_ws_bytes": (c_int64, [NETP, c_int64]),
     "mq_fused_forward": (c_int, [NETP, P, P, P, c_int64, P, P, P, P]),
     "mq_fused_forward_tc": (c_int, [NETP, P, P, P, c_int64, P, P, P, c_int32, P]),
+    "mq_fused_forward_rec": (c_int, [NETP, P, P, c_int32, P, P, c_int64, P, P, c_int32, P]),
     "mq_record_width": (c_int32, [NETP]),
     "mq_pack_records": (c_int, [NETP, P, P, P, P, c_int64, P, P]),
     "mq_tc_image_bytes": (c_int64, [NETP, c_int32]),

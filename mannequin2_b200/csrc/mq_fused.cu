@@ -867,6 +867,8 @@ int mq_chain_grad(const mq_net_t *net, const float *theta, const float *x, const
 int mq_tc_launch(const mq_net_t *net, const float *theta, const float *x, const int32_t *row_idx,
                  int64_t batch, const mq_head_t *head, int with_grad, float *out, float *logp,
                  void *ws, int64_t ws_bytes, int *grid_out, void *stream);
+int mq_tc3_launch(const mq_net_t *net, const int32_t *row_idx, int64_t batch, const mq_head_t *head, const float *theta,
+                  int with_grad, float *out, float *logp, void *ws, int64_t ws_bytes, int *grid_out, void *stream);      // mq_tc3.cu
 int64_t mq_tc3_scratch_bytes();
 int mq_tc_es_launch(const mq_net_t *net, const float *theta, const float *noise, int64_t n_members, const float *obs,
                     int64_t n_obs, const float *ret_coef, float *returns, void *stream);
@@ -980,6 +982,26 @@ extern "C" int mq_fused_forward_tc(const mq_net_t *net, const float *theta, cons
               batch, out, sample, logp);
     MQ_CHECK_LAUNCH("mq_fused_forward");
     return MQ_OK;
+}
+
+// Forward pass from PACKED RECORDS (mq_pack_records: x | target | w0 | w1 per row) on the record-fed tensor-core kernel
+// (csrc/mq_tc3.cu, forward only): the two passes over the whole rollout of a PPO update -- value predictions, gae.py:43-45,
+// and the old log-probabilities, ppo.py:27 -- in the operand format `tc` names, two tiles per SM in flight.  The sample of
+// the log-probability is the record's target.  tc_image: operand image of the CURRENT parameters (mq_tc_image_build).
+// MQ_ERR_UNSUPPORTED when the net does not fit that kernel (callers then use mq_fused_forward on the separate arrays).
+extern "C" int mq_fused_forward_rec(const mq_net_t *net, const float *theta, const float *records, int32_t rec_w,
+                                    const void *tc_image, const int32_t *row_idx, int64_t batch, float *out, float *logp,
+                                    int32_t tc, void *stream) {
+    int rc = fused_net_check(net, "mq_fused_forward_rec");
+    if (rc != MQ_OK) return rc;
+    MQ_REQUIRE(batch >= 0, MQ_ERR_SHAPE, "mq_fused_forward_rec: negative batch");
+    if (batch == 0) return MQ_OK;
+    MQ_REQUIRE(records && tc_image && rec_w > 0 && (out || logp), MQ_ERR_INVALID, "mq_fused_forward_rec: null pointer");
+    mq_head_t fh;
+    memset(&fh, 0, sizeof(fh));
+    fh.kind = !logp ? MQ_HEAD_DY : (net->logstd_off >= 0 ? MQ_HEAD_GAUSS_LOGP : MQ_HEAD_DISCRETE_LOGP);
+    fh.records = records; fh.rec_w = rec_w; fh.tc_image = tc_image; fh.tc = tc;
+    return mq_tc3_launch(net, row_idx, batch, &fh, theta, 0, out, logp, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int mq_fused_forward(const mq_net_t *net, const float *theta, const float *x,

@@ -68,11 +68,27 @@ class _Net(object):
         if self.image is None:
             self.records = None
             return
-        if self.records is None or self.records.numel() != rows * self.rec_w:
-            self.records = torch.empty(rows * self.rec_w, dtype=torch.float32, device=D.device())
+        if getattr(self, "_rec_buf", None) is None or self._rec_buf.numel() < rows * self.rec_w:
+            self._rec_buf = torch.empty(rows * self.rec_w, dtype=torch.float32, device=D.device())
+        self.records = self._rec_buf[:rows * self.rec_w]
         D.call("mq_pack_records", ctypes.byref(self.net), D.ptr(x), D.ptr(tgt) if tgt is not None else None,
                D.ptr(w0) if w0 is not None else None, D.ptr(w1) if w1 is not None else None, rows, D.ptr(self.records),
                D.stream())
+
+    def forward_records(self, x, sample, rows, out, logp):
+        """Forward pass over `rows` rows on the record-fed tensor-core kernel (forward only): packs x | sample, refreshes the
+        operand image from the current parameters.  False when the net does not fit that kernel (caller: array-fed forward)."""
+        if self.image is None or rows < 8192:
+            return False
+        self.pack(x, sample, None, None, rows)
+        D.call("mq_tc_image_build", ctypes.byref(self.net), D.ptr(self.theta), self.planes, D.ptr(self.image), D.stream())
+        try:
+            D.call("mq_fused_forward_rec", ctypes.byref(self.net), D.ptr(self.theta), D.ptr(self.records), self.rec_w,
+                   D.ptr(self.image), None, rows, D.ptr(out) if out is not None else None,
+                   D.ptr(logp) if logp is not None else None, self.planes, D.stream())
+        except NotImplementedError:
+            return False
+        return True
 
     def train(self, x, head, idx_table, n_steps, mb, lr, eps=1e-8, col0=0, idx_stride=None):
         """n_steps optimiser steps on the mb rows idx_table[s, col0 : col0 + mb] (i32[n_steps, idx_stride]): the whole
@@ -234,6 +250,8 @@ class PPOUpdater(object):
         """Forward pass over n_rows rows; split=True: this rank computes its slice and the slices are all-gathered
         (every rank ends up with the full vector, bit-identical everywhere)."""
         if not split or mqdist.world() == 1:
+            if net.forward_records(obs, sample, n_rows, out, logp):
+                return
             D.call("mq_fused_forward", ctypes.byref(net.net), D.ptr(net.theta), D.ptr(obs), None, n_rows,
                    D.ptr(out) if out is not None else None, D.ptr(sample) if sample is not None else None,
                    D.ptr(logp) if logp is not None else None, D.stream())
@@ -246,9 +264,12 @@ class PPOUpdater(object):
         part = self._buf("fwd_part", chunk)
         full = self._buf("fwd_full", chunk * w)
         if cnt > 0:
-            smp = (D.ptr(sample) + 4 * lo * self.n_act) if sample is not None else None
-            D.call("mq_fused_forward", ctypes.byref(net.net), D.ptr(net.theta), D.ptr(obs) + 4 * lo * self.n_obs, None, cnt,
-                   D.ptr(part) if out is not None else None, smp, D.ptr(part) if logp is not None else None, D.stream())
+            obs_r = obs.reshape(-1)[lo * self.n_obs:(lo + cnt) * self.n_obs]
+            smp_r = sample.reshape(-1)[lo * self.n_act:(lo + cnt) * self.n_act] if sample is not None else None
+            if not net.forward_records(obs_r, smp_r, cnt, part if out is not None else None, part if logp is not None else None):
+                D.call("mq_fused_forward", ctypes.byref(net.net), D.ptr(net.theta), D.ptr(obs_r), None, cnt,
+                       D.ptr(part) if out is not None else None, D.ptr(smp_r) if smp_r is not None else None,
+                       D.ptr(part) if logp is not None else None, D.stream())
         mqdist.allgather_into(full, part)
         dst[:n_rows].copy_(full[:n_rows])
 

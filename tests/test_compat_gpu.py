@@ -773,6 +773,58 @@ def test_vae_fused_step_at_baseline_shape():
     assert np.max(np.abs(a - theta)) > 1e-5
 
 
+def test_forward_from_packed_records_matches_oracle():
+    """mq_fused_forward_rec: the forward-only form of the record-fed tensor-core kernel (value predictions, gae.py:43-45, and
+    old log-probabilities, ppo.py:27, over a whole rollout) against the fp64 oracle and against the array-fed
+    mq_fused_forward, in the fp16x2 and the three-plane operand formats; 70,001 rows (ragged last tile, several tiles per SM)
+    and 9,000 rows (single wave), with and without a row gather."""
+    import ctypes
+    import torch
+    from oracle import mq_oracle as O
+    from mannequin2_b200 import _device as D, _lib as L
+    lib = L.lib()
+    rs = np.random.RandomState(31)
+    n_obs, n_act = 11, 3
+    for kind in ("policy", "value"):
+        if kind == "policy":
+            spec = O.policy_spec(n_obs, n_act)
+            net = L.make_net(n_obs, [64, 64, n_act], [1, 1, 0], logstd=True)
+        else:
+            spec = O.mlp_spec(n_obs, [64, 64, 1], [1, 1, 0])
+            net = L.make_net(n_obs, [64, 64, 1], [1, 1, 0])
+        theta = (rs.randn(spec["n_params"]) * 0.3).astype(np.float32)
+        nb = ctypes.byref(net)
+        rec_w = int(lib.mq_record_width(nb))
+        for rows, gather in ((70001, False), (9000, True)):
+            obs = rs.randn(rows, n_obs).astype(np.float32)
+            act = rs.randn(rows, n_act).astype(np.float32)
+            idx = rs.randint(rows, size=rows).astype(np.int32) if gather else None
+            sel = idx if gather else slice(None)
+            if kind == "policy":
+                want = O.policy_logprob(theta, spec, obs[sel], act[sel])[0]
+            else:
+                want = O.mlp_forward(theta, spec, obs[sel])[-1].reshape(-1)
+            d_theta, d_obs, d_act = D.from_host(theta), D.from_host(obs), D.from_host(act)
+            d_idx = D.from_host(idx) if gather else None
+            rec = torch.empty(rows * rec_w, dtype=torch.float32, device=D.device())
+            D.call("mq_pack_records", nb, D.ptr(d_obs), D.ptr(d_act) if kind == "policy" else None, None, None, rows, D.ptr(rec),
+                   D.stream())
+            for mode in ("fp16x2", "exact"):
+                tc = L.TC_MODES[mode]
+                img = torch.zeros(int(lib.mq_tc_image_bytes(nb, tc)), dtype=torch.uint8, device=D.device())
+                assert img.numel() > 0
+                D.call("mq_tc_image_build", nb, D.ptr(d_theta), tc, D.ptr(img), D.stream())
+                got = torch.full((rows,), float("nan"), dtype=torch.float32, device=D.device())
+                D.call("mq_fused_forward_rec", nb, D.ptr(d_theta), D.ptr(rec), rec_w, D.ptr(img), D.ptr(d_idx),
+                       rows, D.ptr(got) if kind == "value" else None, D.ptr(got) if kind == "policy" else None, tc, D.stream())
+                assert_close(D.to_host(got), want, rtol=1e-5, atol_scale=2e-6, msg="%s %s rows=%d" % (kind, mode, rows))
+            if not gather:
+                ref = torch.empty(rows, dtype=torch.float32, device=D.device())
+                D.call("mq_fused_forward", nb, D.ptr(d_theta), D.ptr(d_obs), None, rows, D.ptr(ref) if kind == "value" else None,
+                       D.ptr(d_act) if kind == "policy" else None, D.ptr(ref) if kind == "policy" else None, D.stream())
+                assert_close(D.to_host(got), D.to_host(ref), rtol=1e-5, atol_scale=2e-6, msg="%s vs array-fed forward" % kind)
+
+
 def test_parameter_arena_releases_dropped_nets():
     """Params live in 16 MB arena chunks so that a net's parameters are one flat slice; a full chunk must go away with the
     last Params created in it (nets built and dropped in a loop must not accumulate device memory)."""
