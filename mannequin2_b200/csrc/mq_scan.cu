@@ -461,6 +461,208 @@ gae_lookback_kernel(GaeStage el, int64_t n, ScanTile<float> *__restrict__ tiles)
     *reinterpret_cast<float4 *>(el.ret + r0 + 4) = make_float4(rt[4], rt[5], rt[6], rt[7]);
 }
 
+
+// GAE, hybrid register / shared-memory form (the default for 16-byte aligned arrays with n % 16 == 0).
+// The register kernel above is bound by how many rows an SM keeps in flight: every CTA exposes the latency of its loads
+// and of one look-back round trip through L2, and the register file holds only ~16 k rows per SM (ncu: barrier stalls
+// dominate, 64 % of the HBM peak).  Here a CTA owns GH_SUB consecutive sub-chunks of 1024 rows (4 rows = one 128-bit load
+// per thread, fully coalesced): sub-chunk 0 is loaded into registers, sub-chunks 1.. are fetched by bulk copies (TMA engine,
+// one issuing thread, completion counted on an mbarrier) into shared memory at kernel start, so an SM has 32 k rows in
+// flight and there is ONE global look-back per 4096 rows.  The CTA first reduces every sub-chunk to its map (the staged
+// ones are read twice from shared memory), publishes the composed map, looks back, then writes the outputs of the
+// register sub-chunk and walks the staged ones with the value carried on chip.  (Persistent ring-buffered variants with
+// bulk stores were measured 1.4-2x SLOWER: one chain of look-back + ticket latencies per CTA cannot be hidden by 2-4
+// resident CTAs; tools/gae_variants.cu keeps the variants and their timings are in profiles/r2_gae_variants.txt.)
+#define GH_ITEMS 4
+#define GH_SUB 4                                   // sub-chunks per CTA: 1 in registers + 3 staged
+#define GH_CH (MQ_NT * GH_ITEMS)                   // rows per sub-chunk
+#define GH_ROWS (GH_CH * GH_SUB)                   // rows per CTA
+#define GH_STAGE (GH_CH * 4 + (GH_CH + 4) * 4 + GH_CH)   // rewards | values (+ the value after the newest row) | done flags
+#define GH_SMEM (GH_STAGE * (GH_SUB - 1))
+
+__device__ __forceinline__ unsigned gh_s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gh_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gh_s32(dst)), "l"(src), "r"(bytes), "r"(gh_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void gh_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(gh_s32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// the 4 rows of this thread in a staged sub-chunk: maps newest row first, like the register path
+struct GhRows { float rw[GH_ITEMS], vl[GH_ITEMS + 1]; unsigned dn; };
+__device__ __forceinline__ void gh_rows(const unsigned char *st, int i0, GhRows &r) {
+    const float4 a = *reinterpret_cast<const float4 *>(st + (size_t)i0 * 4);
+    const float4 b = *reinterpret_cast<const float4 *>(st + GH_CH * 4 + (size_t)i0 * 4);
+    const unsigned d = *reinterpret_cast<const unsigned *>(st + GH_CH * 4 + (GH_CH + 4) * 4 + i0);
+    r.rw[0] = a.x; r.rw[1] = a.y; r.rw[2] = a.z; r.rw[3] = a.w;
+    r.vl[0] = b.x; r.vl[1] = b.y; r.vl[2] = b.z; r.vl[3] = b.w;
+    r.vl[4] = *reinterpret_cast<const float *>(st + GH_CH * 4 + (size_t)(i0 + 4) * 4);
+    r.dn = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.dn |= ((d >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+}
+__device__ __forceinline__ Lin<float> gh_warp_scan(Lin<float> v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Lin<float> p = lin_shfl_up(v, o);
+        if (lane >= o) v = lin_then(p, v);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(MQ_NT, 8)
+gae_hybrid_kernel(GaeStage el, int64_t n, ScanTile<float> *__restrict__ tiles) {
+    extern __shared__ __align__(128) unsigned char gh_smem[];
+    __shared__ uint64_t full[GH_SUB - 1];
+    __shared__ Lin<float> warp_tot[GH_SUB][MQ_NT / 32];
+    __shared__ float s_yin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = blockIdx.x;                                  // (block index = chunk: see scan_lookback_kernel)
+    const int64_t hi = n - 1 - c * GH_ROWS;                        // newest row of the CTA
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < GH_SUB - 1; ++j)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gh_s32(&full[j])), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+#pragma unroll
+        for (int j = 0; j < GH_SUB - 1; ++j) {
+            unsigned char *st = gh_smem + (size_t)j * GH_STAGE;
+            // stage slot i <-> row lo_full + i; rows before the start of the data are left out (their threads stay idle)
+            const int64_t hj = hi - (int64_t)(j + 1) * GH_CH, lo_full = hj - (GH_CH - 1);
+            const int64_t lo = lo_full > 0 ? lo_full : 0;
+            const int cnt = (int)(hj - lo + 1), off = (int)(lo - lo_full);
+            if (cnt > 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(gh_s32(&full[j])), "r"((unsigned)(cnt * 9 + 16)) : "memory");
+                gh_bulk_load(st + off * 4, el.rew + lo, (unsigned)(cnt * 4), &full[j]);
+                gh_bulk_load(st + GH_CH * 4 + off * 4, el.val + lo, (unsigned)(cnt * 4 + 16), &full[j]);   // + val[hj + 1 ..]
+                gh_bulk_load(st + GH_CH * 4 + (GH_CH + 4) * 4 + off, el.done + lo, (unsigned)cnt, &full[j]);
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gh_s32(&full[j])) : "memory");
+            }
+        }
+    }
+    // ---- sub-chunk 0: registers --------------------------------------------------------------------
+    const int64_t r0 = hi - (int64_t)threadIdx.x * GH_ITEMS - (GH_ITEMS - 1);
+    const bool live = r0 >= 0;
+    float vl[GH_ITEMS + 1], eb[GH_ITEMS];
+    unsigned dn = 0;
+    {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        unsigned d = 0;
+        vl[4] = 0.0f;
+        if (live) {
+            a = *reinterpret_cast<const float4 *>(el.rew + r0);
+            b = *reinterpret_cast<const float4 *>(el.val + r0);
+            d = *reinterpret_cast<const unsigned *>(el.done + r0);
+            vl[4] = el.val[r0 + GH_ITEMS];
+        }
+        eb[0] = a.x; eb[1] = a.y; eb[2] = a.z; eb[3] = a.w;        // rewards for now
+        vl[0] = b.x; vl[1] = b.y; vl[2] = b.z; vl[3] = b.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dn |= ((d >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+    }
+    __syncthreads();                                               // barriers initialised before anyone waits on them
+    Lin<float> incl[GH_SUB];
+    {
+        Lin<float> local; local.a = 1.0f; local.b = 0.0f;
+#pragma unroll
+        for (int k = GH_ITEMS - 1; k >= 0; --k) {
+            Lin<float> e;
+            if (dn & (1u << k)) { e.a = 0.0f; e.b = eb[k] - vl[k]; }
+            else { e.a = el.gl; e.b = eb[k] + el.g * vl[k + 1] - vl[k]; }
+            eb[k] = e.b;
+            if (live) local = lin_then(local, e);
+        }
+        incl[0] = gh_warp_scan(local);
+    }
+    // ---- staged sub-chunks: maps only ---------------------------------------------------------------
+    const int i0 = GH_CH - ((int)threadIdx.x + 1) * GH_ITEMS;      // this thread's rows in a stage
+#pragma unroll
+    for (int j = 0; j < GH_SUB - 1; ++j) {
+        const int64_t lo_full = hi - (int64_t)(j + 2) * GH_CH + 1;
+        Lin<float> lj; lj.a = 1.0f; lj.b = 0.0f;
+        gh_wait(&full[j], 0u);
+        if (lo_full + i0 >= 0) {
+            GhRows r;
+            gh_rows(gh_smem + (size_t)j * GH_STAGE, i0, r);
+#pragma unroll
+            for (int k = GH_ITEMS - 1; k >= 0; --k) {
+                Lin<float> e;
+                if (r.dn & (1u << k)) { e.a = 0.0f; e.b = r.rw[k] - r.vl[k]; }
+                else { e.a = el.gl; e.b = r.rw[k] + el.g * r.vl[k + 1] - r.vl[k]; }
+                lj = lin_then(lj, e);
+            }
+        }
+        incl[1 + j] = gh_warp_scan(lj);
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < GH_SUB; ++j) warp_tot[j][warp] = incl[j];
+    }
+    __syncthreads();
+    Lin<float> excl[GH_SUB], tot[GH_SUB];
+    Lin<float> all; all.a = 1.0f; all.b = 0.0f;
+#pragma unroll
+    for (int j = 0; j < GH_SUB; ++j) {
+        Lin<float> wp; wp.a = 1.0f; wp.b = 0.0f;
+        Lin<float> t = wp;
+#pragma unroll
+        for (int w = 0; w < MQ_NT / 32; ++w) {
+            if (w == warp) wp = t;
+            t = lin_then(t, warp_tot[j][w]);
+        }
+        const Lin<float> prev = lin_shfl_up(incl[j], 1);
+        excl[j] = (lane == 0) ? wp : lin_then(wp, prev);
+        tot[j] = t;
+        all = lin_then(all, t);
+    }
+    if (threadIdx.x < 32) {
+        const float y0 = scan_publish_and_lookback<float>(tiles, c, all);
+        if (threadIdx.x == 0) s_yin = y0;
+    }
+    __syncthreads();
+    float yin = s_yin;
+    if (live) {
+        float y = excl[0].b + excl[0].a * yin;
+        float av[GH_ITEMS], rt[GH_ITEMS];
+#pragma unroll
+        for (int k = GH_ITEMS - 1; k >= 0; --k) {
+            y = eb[k] + ((dn & (1u << k)) ? 0.0f : el.gl) * y;
+            av[k] = y;
+            rt[k] = y + vl[k];
+        }
+        *reinterpret_cast<float4 *>(el.adv + r0) = make_float4(av[0], av[1], av[2], av[3]);
+        *reinterpret_cast<float4 *>(el.ret + r0) = make_float4(rt[0], rt[1], rt[2], rt[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < GH_SUB - 1; ++j) {
+        yin = tot[j].b + tot[j].a * yin;                           // value entering staged sub-chunk j
+        const int64_t q0 = hi - (int64_t)(j + 2) * GH_CH + 1 + i0;
+        if (q0 >= 0) {
+            GhRows r;
+            gh_rows(gh_smem + (size_t)j * GH_STAGE, i0, r);
+            float y = excl[1 + j].b + excl[1 + j].a * yin;
+            float av[GH_ITEMS], rt[GH_ITEMS];
+#pragma unroll
+            for (int k = GH_ITEMS - 1; k >= 0; --k) {
+                const bool dk = (r.dn & (1u << k)) != 0u;
+                const float b = dk ? r.rw[k] - r.vl[k] : r.rw[k] + el.g * r.vl[k + 1] - r.vl[k];
+                y = b + (dk ? 0.0f : el.gl) * y;
+                av[k] = y;
+                rt[k] = y + r.vl[k];
+            }
+            *reinterpret_cast<float4 *>(el.adv + q0) = make_float4(av[0], av[1], av[2], av[3]);
+            *reinterpret_cast<float4 *>(el.ret + q0) = make_float4(rt[0], rt[1], rt[2], rt[3]);
+        }
+    }
+}
+
 #else
 struct GaeStage { const float *rew, *val; const uint8_t *done; float *adv, *ret; float g, gl; int vec; };
 struct DiscStage { const double *in; double *out; double keep, step; };
@@ -474,6 +676,12 @@ extern "C" int64_t mq_scan_ws_bytes(int64_t n) {
 #ifndef MQ_EMU
 static bool scan_try_register_kernel(const GaeStage &st, int64_t n, ScanTile<float> *tiles, int64_t nb, void *stream) {
     if (!st.vec || (n & 7) != 0) return false;
+    if ((n & 15) == 0) {                                   // bulk copies: 16-byte granules of the done flags as well
+        if (cudaFuncSetAttribute(gae_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GH_SMEM) != cudaSuccess)
+            return false;
+        MQ_LAUNCH(gae_hybrid_kernel, (unsigned)mq_ceil_div(n, (int64_t)GH_ROWS), MQ_NT, GH_SMEM, stream, st, n, tiles);
+        return true;
+    }
     MQ_LAUNCH(gae_lookback_kernel, (unsigned)nb, MQ_NT, 0, stream, st, n, tiles);
     return true;
 }

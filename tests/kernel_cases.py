@@ -198,8 +198,9 @@ def case_gather(B):
     assert lib.mq_gather_rows(B.ptr(hs), B.ptr(hi), 0, 44, 40, B.ptr(dst), B.stream) == 0     # empty index
 
 
-def case_scan(B, sizes=(1, 2, 700, 2048, 2049, 5000, 70001)):
-    """benchmarks/gae.py:43-64,69 and mannequin/_utils.py:9-20."""
+def case_scan(B, sizes=(1, 2, 700, 2048, 2049, 3088, 4096, 4112, 5000, 70000, 70001)):
+    """benchmarks/gae.py:43-64,69 and mannequin/_utils.py:9-20.  Sizes with n % 16 == 0 above 2048 take the hybrid register /
+    shared-memory kernel (one CTA, whole CTAs, a ragged last CTA), n % 8 == 0 the register kernel, the rest the staged one."""
     lib = B.lib
     rs = np.random.RandomState(3)
     for n in sizes:
@@ -237,6 +238,19 @@ def case_scan(B, sizes=(1, 2, 700, 2048, 2049, 5000, 70001)):
         ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 0.99, 0.95, B.ptr(adv), B.ptr(ret), B.ptr(ws),
                          wsb, B.stream))
         close(B.down(adv), O.gae_advantages(r, v, d)[0], what="gae edge")
+    # no episode end at all over 41 CTAs of the hybrid kernel: every look-back walks a full 32-descriptor window of open
+    # maps; and a single end in the middle
+    n = 4096 * 40 + 16
+    r, v = rs.randn(n).astype(np.float32), rs.randn(n + 1).astype(np.float32)
+    for d in (np.zeros(n, np.uint8), (np.arange(n) == n // 2).astype(np.uint8)):
+        wsb = lib.mq_scan_ws_bytes(n)
+        hr, hv, hd, ws = B.up(r), B.up(v), B.up(d), B.zeros(wsb, np.uint8)
+        adv, ret = B.zeros(n, np.float32), B.zeros(n, np.float32)
+        ok(B, lib.mq_gae(B.ptr(hr), B.ptr(hv), B.ptr(hd), n, 0.99, 0.95, B.ptr(adv), B.ptr(ret), B.ptr(ws),
+                         wsb, B.stream))
+        wa, wr = O.gae_advantages(r, v, d)
+        close(B.down(adv), wa, what="gae open look-back")
+        close(B.down(ret), wr, what="gae open look-back (returns)")
     # reference output of benchmarks/gae.py:gae() (tests/golden/gae.npz), first chunk
     g = golden("gae")
     spec = O.mlp_spec(11, [64, 64, 1], [O.ACT_TANH, O.ACT_TANH, O.ACT_NONE])
