@@ -281,14 +281,22 @@ norm_apply1_f32_kernel(const float *__restrict__ x, int64_t n, const double *__r
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
     float4 *o4 = reinterpret_cast<float4 *>(out);
     const int64_t nq = n >> 2;
-    for (int64_t q = tid; q < nq; q += nth) {
-        const float4 u = x4[q];
+    auto apply4 = [&](const float4 u) {
         float4 r;
         r.x = (float)(((double)u.x - m) * inv); r.y = (float)(((double)u.y - m) * inv);
         r.z = (float)(((double)u.z - m) * inv); r.w = (float)(((double)u.w - m) * inv);
         if (fuse_tanh) { r.x = tanhf(r.x); r.y = tanhf(r.y); r.z = tanhf(r.z); r.w = tanhf(r.w); }
-        o4[q] = r;
+        return r;
+    };
+    int64_t q = tid;
+    for (; q + 3 * nth < nq; q += 4 * nth) {           // four independent loads in flight per thread (one input stream)
+        const float4 u0 = x4[q], u1 = x4[q + nth], u2 = x4[q + 2 * nth], u3 = x4[q + 3 * nth];
+        o4[q] = apply4(u0);
+        o4[q + nth] = apply4(u1);
+        o4[q + 2 * nth] = apply4(u2);
+        o4[q + 3 * nth] = apply4(u3);
     }
+    for (; q < nq; q += nth) o4[q] = apply4(x4[q]);
     for (int64_t i = (nq << 2) + tid; i < n; i += nth) {
         const float z = (float)(((double)x[i] - m) * inv);
         out[i] = fuse_tanh ? tanhf(z) : z;
