@@ -39,6 +39,8 @@ struct GmPackJob {
     const int32_t *idx; int idx_on_k;            // optional gather on the rows (0) or on k (1)
     int64_t rows, k;                             // extents of the source
     int64_t ones_row;                            // > 0: rows ones_row <= r < rows read as 1.0 (bias-gradient row of dW)
+    int64_t ones_col;                            // > 0: columns ones_col <= k < k-extent read as 1.0, the source has ones_col columns
+                                                 // (the same row of ones when x^T is fed as an MN-major operand: plain form only)
     int64_t rows_cover, k_cover;                 // extents WRITTEN (zero outside the source); k_cover % 8 == 0
     int64_t rows_pad, k_pad;                     // geometry of a destination plane
     int64_t row_off, k_off;                      // offsets inside the destination plane (k_off % 8 == 0)
@@ -51,6 +53,11 @@ int64_t mq_gemm_tma_pack_bytes(int64_t m, int64_t n, int64_t k, int planes);
 int mq_gemm_tma_pack_multi(GmPackJob *jobs, int n_jobs, int mode, void *stream);
 int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64_t b_rows_pad, int64_t k_pad,
                        const GemmArgs &g, const GmEmit &em, int mode, int64_t splits, void *stream);
+// the same with either operand MN-major (a_mn / b_mn != 0): planes [plane][k rows pad][m or n pad] -- the operand's M (N) axis
+// is the unit-stride axis of its image; *_rows_pad is then the K-row count of a plane and *_mn_pad its row length in elements
+int mq_gemm_tma_packed_mn(const void *pa, int64_t a_rows_pad, int a_mn, int64_t a_mn_pad, const void *pb, int64_t b_rows_pad,
+                          int b_mn, int64_t b_mn_pad, int64_t k_pad, const GemmArgs &g, const GmEmit &em, int mode,
+                          int64_t splits, void *stream);
 
 __device__ __forceinline__ float gemm_epilogue(const GemmArgs &g, float acc, int64_t m, int64_t n) {
     if (g.epi == EPI_BIAS_ACT) return mq_act_apply(acc + g.bias[n], g.act, g.leak);

@@ -61,7 +61,8 @@ __device__ __forceinline__ void gm_pack_plain(const GmPackJob &jb, int rows_fast
     else { r = item / kc_n; kc = item - r * kc_n; }
     const float *__restrict__ base = jb.base;
     const int32_t *__restrict__ idx = jb.idx;
-    const int64_t rs = jb.rs, cs = jb.cs, k = jb.k;
+    const int64_t rs = jb.rs, cs = jb.cs;
+    const int64_t k = jb.ones_col > 0 ? jb.ones_col : jb.k;     // columns the source really has
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0f;
@@ -82,6 +83,11 @@ __device__ __forceinline__ void gm_pack_plain(const GmPackJob &jb, int rows_fast
                     const int64_t sk = (idx && jb.idx_on_k) ? (int64_t)idx[k0 + j] : k0 + j;
                     v[j] = __ldg(base + sr * rs + sk * cs);
                 }
+        }
+        if (jb.ones_col > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (kc * 8 + j >= jb.ones_col && kc * 8 + j < jb.k) v[j] = 1.0f;
         }
     }
     uint32_t w[4][P];
@@ -175,6 +181,11 @@ __device__ __forceinline__ void gm_arrive(uint32_t mbar) {
 }
 // K-major operand tile with 128-byte swizzle: 8-row groups 1024 bytes apart; layout type 2 (SWIZZLE_128B) in bits 61-63
 __device__ __forceinline__ uint32_t gm_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+// MN-major operand tile with 128-byte swizzle (the operand's M / N axis is the unit-stride axis: x^T of dW = x^T g read from
+// the planes of x): a tile is two blocks of [64 k rows][64 m = 128 bytes] (8 KB each, one TMA box each); leading byte offset
+// = distance between the 64-element blocks along M / N (8192), stride byte offset = distance between groups of 8 k rows
+// (1024); a K step of 16 is two such groups (2048 bytes).
+__device__ __forceinline__ uint32_t gm_desc_lo_mn(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((8192u >> 4) << 16); }
 __device__ __forceinline__ uint32_t gm_desc_hi() { return ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
 
 template <int P>
@@ -196,7 +207,7 @@ struct GmCfg {
 template <int P, int F, bool SPLIT>
 __global__ void __launch_bounds__(GM_NT, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g, GmEmit em,
-                int a_rows_pad, int b_rows_pad, int n_splits) {
+                int a_rows_pad, int b_rows_pad, int n_splits, int a_mn, int b_mn) {
     using Cfg = GmCfg<P>;
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t s_tmem;
@@ -257,8 +268,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int kc = (int)(k_begin + (int64_t)c * GM_BK);
 #pragma unroll
                     for (int pl = 0; pl < P; ++pl) {
-                        gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, kc, pl * a_rows_pad + m0, full);
-                        gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, kc, pl * b_rows_pad + n0, full);
+                        if (!a_mn) gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, kc, pl * a_rows_pad + m0, full);
+                        else {
+                            gm_tma_load(sa + pl * GM_TILE_BYTES, &map_a, m0, pl * a_rows_pad + kc, full);
+                            gm_tma_load(sa + pl * GM_TILE_BYTES + 8192, &map_a, m0 + 64, pl * a_rows_pad + kc, full);
+                        }
+                        if (!b_mn) gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, kc, pl * b_rows_pad + n0, full);
+                        else {
+                            gm_tma_load(sb + pl * GM_TILE_BYTES, &map_b, n0, pl * b_rows_pad + kc, full);
+                            gm_tma_load(sb + pl * GM_TILE_BYTES + 8192, &map_b, n0 + 64, pl * b_rows_pad + kc, full);
+                        }
                     }
                 }
             }
@@ -267,7 +286,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp == 1) {
         // ---- MMA issuer --------------------------------------------------------------------------------------------
         const uint32_t hi = gm_desc_hi();
-        const uint32_t id2 = tc_idesc_fmt(GM_BM, 2 * GM_BN, 0, 0, F), id1 = tc_idesc_fmt(GM_BM, GM_BN, 0, 0, F);
+        const uint32_t id2 = tc_idesc_fmt(GM_BM, 2 * GM_BN, a_mn, b_mn, F), id1 = tc_idesc_fmt(GM_BM, GM_BN, a_mn, b_mn, F);
+        const uint32_t a_k16 = a_mn ? (2048u >> 4) : 2u, b_k16 = b_mn ? (2048u >> 4) : 2u;     // descriptor advance per K step of 16
         uint32_t gc = 0, gb = 0;                               // chunks / accumulator blocks issued so far, all tiles
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             GM_TILE_DECODE(t);
@@ -284,7 +304,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t pl16 = GM_TILE_BYTES >> 4;
 #pragma unroll
                     for (int ks = 0; ks < GM_BK / 16; ++ks) {
-                        const uint32_t alo = gm_desc_lo(sa) + 2 * ks, blo = gm_desc_lo(sb) + 2 * ks;     // 32 bytes per K step
+                        const uint32_t alo = (a_mn ? gm_desc_lo_mn(sa) : gm_desc_lo(sa)) + a_k16 * ks;
+                        const uint32_t blo = (b_mn ? gm_desc_lo_mn(sb) : gm_desc_lo(sb)) + b_k16 * ks;
                         const uint32_t first = Cfg::FOLD ? ((c % GM_KBLOCK > 0 || ks > 0) ? 1u : 0u) : ((c > 0 || ks > 0) ? 1u : 0u);
                         if (P == 1) {
                             tc_mma(d, alo, hi, blo, hi, id1, first);                              // A_0 x B_0
@@ -468,8 +489,23 @@ static int gm_make_map(CUtensorMap *map, void *base, int64_t rows_total, int64_t
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// MN-major image: [P * k_rows_pad][mn_pad] bf16, box 64 (m or n: one 128-byte swizzle row) x 64 (k rows)
+static int gm_make_map_mn(CUtensorMap *map, void *base, int64_t k_rows_total, int64_t mn_pad) {
+    gm_encode_fn enc = gm_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[2] = {(cuuint64_t)mn_pad, (cuuint64_t)k_rows_total};
+    const cuuint64_t strides[1] = {(cuuint64_t)mn_pad * 2};
+    const cuuint32_t box[2] = {64, GM_BK};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// bytes of one packed operand: the larger of its K-major image [rows_pad 128][k_pad 64] and its MN-major image
+// [k rows pad 128][rows pad 128] (the launcher picks the form by the source's unit-stride axis)
 static int64_t gm_pack_bytes(int planes, int64_t rows, int64_t k) {
-    return (int64_t)planes * mq_round_up(rows, 128) * mq_round_up(k, GM_BK) * 2;
+    const int64_t kmaj = mq_round_up(rows, 128) * mq_round_up(k, GM_BK), mnmaj = mq_round_up(k, 128) * mq_round_up(rows, 128);
+    return (int64_t)planes * (kmaj > mnmaj ? kmaj : mnmaj) * 2;
 }
 
 // workspace the packed-operand GEMM needs for an m x n x k product with `planes` planes (without split-K partials)
@@ -529,14 +565,27 @@ static GmPackJob gm_whole_job(const float *base, int64_t rs, int64_t cs, const i
 // (g.k_per_split a multiple of 64; the planes `em` asks for are not written then).
 int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64_t b_rows_pad, int64_t k_pad,
                        const GemmArgs &g, const GmEmit &em, int mode, int64_t splits, void *stream) {
+    return mq_gemm_tma_packed_mn(pa, a_rows_pad, 0, 0, pb, b_rows_pad, 0, 0, k_pad, g, em, mode, splits, stream);
+}
+
+int mq_gemm_tma_packed_mn(const void *pa, int64_t a_rows_pad, int a_mn, int64_t a_mn_pad, const void *pb, int64_t b_rows_pad,
+                          int b_mn, int64_t b_mn_pad, int64_t k_pad, const GemmArgs &g, const GmEmit &em, int mode,
+                          int64_t splits, void *stream) {
     int planes, fmt;
     if (!gm_mode_ok(mode, &planes, &fmt)) return MQ_ERR_UNSUPPORTED;
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
-    MQ_REQUIRE(a_rows_pad % 128 == 0 && b_rows_pad % 128 == 0 && k_pad % GM_BK == 0 && a_rows_pad >= g.m && b_rows_pad >= g.n &&
-               k_pad >= g.k && (((uintptr_t)pa | (uintptr_t)pb) & 127) == 0, MQ_ERR_SHAPE, "mq_gemm_tma: packed operand geometry");
+    a_mn = a_mn ? 1 : 0; b_mn = b_mn ? 1 : 0;
+    MQ_REQUIRE(a_rows_pad % 128 == 0 && b_rows_pad % 128 == 0 && k_pad % GM_BK == 0 && (((uintptr_t)pa | (uintptr_t)pb) & 127) == 0,
+               MQ_ERR_SHAPE, "mq_gemm_tma: packed operand geometry");
+    MQ_REQUIRE(a_mn ? (a_rows_pad >= g.k && a_mn_pad % 128 == 0 && a_mn_pad >= g.m) : (a_rows_pad >= g.m && k_pad >= g.k),
+               MQ_ERR_SHAPE, "mq_gemm_tma: packed operand geometry (A)");
+    MQ_REQUIRE(b_mn ? (b_rows_pad >= g.k && b_mn_pad % 128 == 0 && b_mn_pad >= g.n) : (b_rows_pad >= g.n && k_pad >= g.k),
+               MQ_ERR_SHAPE, "mq_gemm_tma: packed operand geometry (B)");
     alignas(64) CUtensorMap map_a, map_b;
-    if (!gm_make_map(&map_a, (void *)pa, planes * a_rows_pad, k_pad) || !gm_make_map(&map_b, (void *)pb, planes * b_rows_pad, k_pad)) {
+    const int ok_a = a_mn ? gm_make_map_mn(&map_a, (void *)pa, planes * a_rows_pad, a_mn_pad) : gm_make_map(&map_a, (void *)pa, planes * a_rows_pad, k_pad);
+    const int ok_b = b_mn ? gm_make_map_mn(&map_b, (void *)pb, planes * b_rows_pad, b_mn_pad) : gm_make_map(&map_b, (void *)pb, planes * b_rows_pad, k_pad);
+    if (!ok_a || !ok_b) {
         mq_set_error("mq_gemm_tma: cuTensorMapEncodeTiled failed");
         return MQ_ERR_CUDA;
     }
@@ -550,7 +599,7 @@ int mq_gemm_tma_packed(const void *pa, int64_t a_rows_pad, const void *pb, int64
         e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
         if (e == cudaSuccess)                                                                                              \
             e = mq_launch_pdl(gemm_tma_kernel<P_, F_, SP_>, dim3(grid), dim3(GM_NT), (size_t)GmCfg<P_>::SMEM, stream, map_a, map_b, g, em, \
-                              (int)a_rows_pad, (int)b_rows_pad, (int)(splits > 1 ? splits : 1));                                \
+                              (int)a_rows_pad, (int)b_rows_pad, (int)(splits > 1 ? splits : 1), a_mn, b_mn);                    \
     } while (0)
 #define GM_GO_P(SP_)                                              \
     do {                                                          \
@@ -574,18 +623,33 @@ int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, 
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return MQ_ERR_UNSUPPORTED;
     if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
-    const int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128), k_pad = mq_round_up(g.k, GM_BK);
+    int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128);
+    const int64_t k_pad = mq_round_up(g.k, GM_BK);
     unsigned char *pa = (unsigned char *)(((uintptr_t)pack + 1023) & ~(uintptr_t)1023);
     unsigned char *pb = pa + mq_round_up(gm_pack_bytes(planes, g.m, g.k), 1024);
     // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
+    // An operand whose M (N) axis is the unit-stride axis of its source (x^T and g of dW = x^T g, W of y = x W) is packed
+    // in the SOURCE orientation -- the plain, fully coalesced form: planes [k][m] -- and fed to the tensor pipe MN-major,
+    // instead of being transposed through shared memory (the 65,536 x 784 minibatch of the MLP: 213 us at 1.9 TB/s).
+    const int a_mn = g.a_rs == 1 && g.a_cs != 1, b_mn = g.b_cs == 1 && g.b_rs != 1;
+    int64_t a_mn_pad = 0, b_mn_pad = 0;
     GmPackJob jobs[2];
-    jobs[0] = gm_whole_job(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa);
-    jobs[1] = gm_whole_job(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb);
+    if (a_mn) {
+        jobs[0] = gm_whole_job(g.a, g.a_cs, 1, g.idx, g.idx ? !g.idx_on_k : 0, g.k, g.m, 0, pa);     // rows = k, columns = m
+        if (g.a_ones_row > 0) jobs[0].ones_col = g.a_ones_row;
+        a_mn_pad = jobs[0].k_pad = jobs[0].k_cover = mq_round_up(g.m, 128);
+        a_rows_pad = jobs[0].rows_pad;
+    } else jobs[0] = gm_whole_job(g.a, g.a_rs, g.a_cs, g.idx, g.idx_on_k, g.m, g.k, g.a_ones_row, pa);
+    if (b_mn) {
+        jobs[1] = gm_whole_job(g.b, g.b_rs, 1, nullptr, 0, g.k, g.n, 0, pb);
+        b_mn_pad = jobs[1].k_pad = jobs[1].k_cover = mq_round_up(g.n, 128);
+        b_rows_pad = jobs[1].rows_pad;
+    } else jobs[1] = gm_whole_job(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pb);
     int rc = mq_gemm_tma_pack_multi(jobs, 2, mode, stream);
     if (rc != MQ_OK) return rc;
     GmEmit em;
     memset(&em, 0, sizeof(em));
-    return mq_gemm_tma_packed(pa, a_rows_pad, pb, b_rows_pad, k_pad, g, em, mode, splits, stream);
+    return mq_gemm_tma_packed_mn(pa, a_rows_pad, a_mn, a_mn_pad, pb, b_rows_pad, b_mn, b_mn_pad, k_pad, g, em, mode, splits, stream);
 }
 
 #else
@@ -593,4 +657,5 @@ int64_t mq_gemm_tma_pack_bytes(int64_t, int64_t, int64_t, int) { return 0; }
 int mq_gemm_tma_launch(const GemmArgs &, int, int64_t, void *, void *) { return MQ_ERR_UNSUPPORTED; }
 int mq_gemm_tma_pack_multi(GmPackJob *, int, int, void *) { return MQ_ERR_UNSUPPORTED; }
 int mq_gemm_tma_packed(const void *, int64_t, const void *, int64_t, int64_t, const GemmArgs &, const GmEmit &, int, int64_t, void *) { return MQ_ERR_UNSUPPORTED; }
+int mq_gemm_tma_packed_mn(const void *, int64_t, int, int64_t, const void *, int64_t, int, int64_t, int64_t, const GemmArgs &, const GmEmit &, int, int64_t, void *) { return MQ_ERR_UNSUPPORTED; }
 #endif
