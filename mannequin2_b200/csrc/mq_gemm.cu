@@ -327,6 +327,157 @@ gemm_skinny_finish_kernel(const float *__restrict__ partial, int slabs, int64_t 
     if (lane == 0) c[e] = alpha * s;
 }
 
+#ifndef MQ_EMU
+// ---- streaming forms of the three skinny products (dense fp32 operands, the shapes of a narrow output layer) -------------
+// Each reads / writes the batch x width activations ONCE at HBM rate; the general kernels above remain for strided or
+// gathered operands and other widths.
+
+// SKINNY_N, A rows dense (a_cs = 1, 16-byte aligned rows), k <= 128, k % 4 == 0: a WARP per row, lane l holds columns
+// 4l .. 4l+3 of the row (one 128-bit load: the row is one coalesced 512-byte read) and rows 4l .. 4l+3 of B in registers;
+// the 32 partial sums of each of the (<= 16) outputs are added by a transposing butterfly (halving the live outputs at
+// every level: 16 shuffles per row instead of 5 per output).  Four rows per warp in flight.  Fixed order: bit-reproducible.
+__global__ void __launch_bounds__(128, 4)
+gemm_skinny_n_warp_kernel(GemmArgs g) {
+    const int n = (int)g.n, k = (int)g.k;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * 128) >> 5;
+    float b[4][SKINNY_MAX];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j)
+            b[i][j] = (4 * lane + i < k && j < n) ? __ldg(g.b + (int64_t)(4 * lane + i) * g.b_rs + (int64_t)j * g.b_cs) : 0.0f;
+    const bool has = 4 * lane < k;
+    const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    for (int64_t r0 = warp * 4; r0 < g.m; r0 += nwarps * 4) {
+        float4 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t r = r0 + q;
+            a[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (has && r < g.m) a[q] = __ldg(reinterpret_cast<const float4 *>(g.a + (g.idx ? (int64_t)g.idx[r] : r) * g.a_rs) + lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float p[SKINNY_MAX];
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j)
+                p[j] = fmaf(a[q].w, b[3][j], fmaf(a[q].z, b[2][j], fmaf(a[q].y, b[1][j], a[q].x * b[0][j])));
+            float p8[8], p4[4], p2[2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool up = (lane & 16) != 0;
+                const float got = __shfl_xor_sync(0xffffffffu, up ? p[i] : p[i + 8], 16);
+                p8[i] = (up ? p[i + 8] : p[i]) + got;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool up = (lane & 8) != 0;
+                const float got = __shfl_xor_sync(0xffffffffu, up ? p8[i] : p8[i + 4], 8);
+                p4[i] = (up ? p8[i + 4] : p8[i]) + got;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool up = (lane & 4) != 0;
+                const float got = __shfl_xor_sync(0xffffffffu, up ? p4[i] : p4[i + 2], 4);
+                p2[i] = (up ? p4[i + 2] : p4[i]) + got;
+            }
+            const bool up = (lane & 2) != 0;
+            float v = (up ? p2[1] : p2[0]) + __shfl_xor_sync(0xffffffffu, up ? p2[0] : p2[1], 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            const int64_t r = r0 + q;
+            if (r < g.m && (lane & 1) == 0 && slot < n) g.c[r * g.n + slot] = gemm_epilogue(g, v, r, slot);
+        }
+    }
+}
+
+// SKINNY_DW, both operands dense (A = x^T with x [k][md] contiguous, B [k][n] contiguous; md <= 128, md % 4 == 0, k % 4 == 0):
+// a block per slab of k; tiles of 64 batch rows of x and of B arrive in shared memory by bulk copies (TMA engine, two stages,
+// one issuing thread, completion counted on an mbarrier), thread (m, half) adds the rows of its parity into n sums in
+// registers (x conflict-free along m, B broadcast), halves combined in a fixed order; the bias-gradient row (a_ones_row)
+// is the column sum of B, kept by the m = 0 threads.
+#define SKDW_TILE 64
+#define SKDW_STAGE (SKDW_TILE * 128 * 4 + SKDW_TILE * SKINNY_MAX * 4)
+__global__ void __launch_bounds__(MQ_NT)
+gemm_skinny_dw_tma_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char sk_smem[];
+    __shared__ __align__(8) uint64_t full[2];
+    const int n = (int)g.n, md = (int)(g.a_ones_row > 0 ? g.a_ones_row : g.m);
+    const int64_t k0 = (int64_t)blockIdx.x * k_per_slab;
+    const int64_t k1 = k0 + k_per_slab < g.k ? k0 + k_per_slab : g.k;
+    const int ntiles = (int)((k1 - k0 + SKDW_TILE - 1) / SKDW_TILE);
+    const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
+    auto bar = [&](int s) { return (unsigned)__cvta_generic_to_shared(&full[s]); };
+    auto issue = [&](int t) {
+        const int s = t & 1;
+        const int64_t kb = k0 + (int64_t)t * SKDW_TILE;
+        const unsigned rows = (unsigned)(k1 - kb < SKDW_TILE ? k1 - kb : SKDW_TILE);
+        const unsigned ba = rows * (unsigned)md * 4u, bb = rows * (unsigned)n * 4u;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)s * SKDW_STAGE);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar(s)), "r"(ba + bb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(g.a + kb * md), "r"(ba), "r"(bar(s)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + SKDW_TILE * 128 * 4), "l"(g.b + kb * n), "r"(bb), "r"(bar(s)) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(0)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(1)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    __syncthreads();
+    float acc[SKINNY_MAX], ones[SKINNY_MAX];
+#pragma unroll
+    for (int j = 0; j < SKINNY_MAX; ++j) { acc[j] = 0.0f; ones[j] = 0.0f; }
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        unsigned ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar(s)), "r"((unsigned)((t >> 1) & 1)) : "memory");
+        } while (!ok);
+        const int64_t kb = k0 + (int64_t)t * SKDW_TILE;
+        const int rows = (int)(k1 - kb < SKDW_TILE ? k1 - kb : SKDW_TILE);
+        const float *xa = reinterpret_cast<const float *>(sk_smem + (size_t)s * SKDW_STAGE);
+        const float *gb = xa + SKDW_TILE * 128;
+#pragma unroll 4
+        for (int r = half; r < rows; r += 2) {
+            const float a = m < md ? xa[r * md + m] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j)
+                if (j < n) {
+                    const float gv = gb[r * n + j];
+                    acc[j] = fmaf(a, gv, acc[j]);
+                    if (m == 0) ones[j] += gv;
+                }
+        }
+        __syncthreads();                                   // every read of stage s is done
+        if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
+    }
+    // halves in a fixed order through the (now idle) first stage
+    float *red = reinterpret_cast<float *>(sk_smem);
+    if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j) {
+            red[m * SKINNY_MAX + j] = acc[j];
+            if (m == 0) red[128 * SKINNY_MAX + j] = ones[j];
+        }
+    }
+    __syncthreads();
+    if (half == 0) {
+        float *dst = partial + (int64_t)blockIdx.x * g.m * n;
+#pragma unroll
+        for (int j = 0; j < SKINNY_MAX; ++j)
+            if (j < n) {
+                if (m < md) dst[(int64_t)m * n + j] = acc[j] + red[m * SKINNY_MAX + j];
+                if (m == 0 && g.a_ones_row > 0) dst[g.a_ones_row * n + j] = ones[j] + red[128 * SKINNY_MAX + j];
+            }
+    }
+}
+#endif
+
 // 1 = handled.  Shapes outside the kernels' limits fall through to the general kernels.
 static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stream) {
 #ifdef MQ_EMU
@@ -335,6 +486,12 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
 #else
     const int sms = mq_sm_count();
     if (g.m >= 2048 && g.n <= SKINNY_MAX && g.k >= 32 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) && g.a_ones_row == 0) {
+        if (g.a_cs == 1 && g.k <= 128 && (g.k & 3) == 0 && (g.a_rs & 3) == 0 && ((uintptr_t)g.a & 15) == 0) {
+            int64_t nbw = mq_ceil_div(g.m, 16);               // 4 warps x 4 rows per block and pass
+            if (nbw > (int64_t)sms * 16) nbw = (int64_t)sms * 16;
+            MQ_LAUNCH(gemm_skinny_n_warp_kernel, (unsigned)nbw, 128, 0, stream, g);
+            return 1;
+        }
         int64_t nb = mq_ceil_div(g.m, SKINNY_ROWS);
         if (nb > (int64_t)sms * 8) nb = (int64_t)sms * 8;
         MQ_LAUNCH(gemm_skinny_n_kernel, (unsigned)nb, SKINNY_ROWS, 0, stream, g);
@@ -348,6 +505,21 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
         return 1;
     }
     if (ws && g.k >= 4096 && g.n <= SKINNY_MAX && g.m <= 2 * MQ_NT && g.a_rs == 1 && g.b_cs == 1 && g.epi == EPI_SCALE && !(g.idx && !g.idx_on_k)) {
+        const int64_t md = g.a_ones_row > 0 ? g.a_ones_row : g.m;
+        if (!g.idx && md <= 128 && (md & 3) == 0 && (g.k & 3) == 0 && g.a_cs == md && g.b_rs == g.n && (g.a_ones_row == 0 || g.m == md + 1) &&
+            (((uintptr_t)g.a | (uintptr_t)g.b) & 15) == 0) {
+            int64_t sl = (int64_t)sms * 3;                     // three blocks per SM (2 x 36 KB of stages each), all resident
+            if (sl > g.k / 64) sl = g.k / 64;
+            const int64_t per4 = mq_round_up(mq_ceil_div(g.k, sl), 8);
+            sl = mq_ceil_div(g.k, per4);
+            if (sl * g.m * g.n * (int64_t)sizeof(float) <= ws_bytes &&
+                cudaFuncSetAttribute(gemm_skinny_dw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SKDW_STAGE) == cudaSuccess) {
+                MQ_LAUNCH(gemm_skinny_dw_tma_kernel, (unsigned)sl, MQ_NT, 2 * SKDW_STAGE, stream, g, per4, (float *)ws);
+                const int64_t tot = g.m * g.n;
+                MQ_LAUNCH(gemm_skinny_finish_kernel, (unsigned)mq_ceil_div(tot * 32, MQ_NT), MQ_NT, 0, stream, (const float *)ws, (int)sl, tot, g.alpha, g.c);
+                return 1;
+            }
+        }
         int64_t slabs = (int64_t)sms * 8;
         if (slabs > g.k / 32) slabs = g.k / 32;
         while (slabs > 1 && slabs * g.m * g.n * (int64_t)sizeof(float) > ws_bytes) --slabs;
