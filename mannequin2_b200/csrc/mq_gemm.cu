@@ -391,6 +391,136 @@ gemm_skinny_n_warp_kernel(GemmArgs g) {
     }
 }
 
+// SKINNY_N, thread-per-row form (the default; the warp-per-row kernel above measured 293 warp instructions per row -- all 16
+// output slots computed and reduced, 128 registers -- and stays for n > 12... it is the fallback when shared memory cannot be
+// raised): a block of 128 threads owns 128 rows; THREAD r fetches ITS row (k * 4 <= 512 bytes, gathered rows included) with one
+// bulk copy (TMA engine) into a padded shared-memory row (pitch 132 floats: 128-bit reads of consecutive rows fall in different
+// bank groups), all 128 copies complete on one mbarrier; B sits in shared memory padded to NP columns and is read as
+// broadcast 128-bit words.  ~53 warp instructions per row instead of 293; no block barrier in the row loop (a thread re-arms
+// only its own row).
+#define SKN_PITCH 132
+template <int NP>
+__global__ void __launch_bounds__(128)
+gemm_skinny_n_rows_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) float skn_smem[];
+    __shared__ __align__(8) uint64_t bar_mem;
+    float *as = skn_smem, *bs = skn_smem + 128 * SKN_PITCH;     // A tile [128][132], B [k][NP]
+    const int n = (int)g.n, k = (int)g.k;
+    for (int e = threadIdx.x; e < k * NP; e += 128) {
+        const int kk = e / NP, j = e - kk * NP;
+        bs[e] = j < n ? __ldg(g.b + (int64_t)kk * g.b_rs + (int64_t)j * g.b_cs) : 0.0f;
+    }
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_mem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(128u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    float *my = as + threadIdx.x * SKN_PITCH;
+    const unsigned my_s = (unsigned)__cvta_generic_to_shared(my);
+    unsigned phase = 0;
+    for (int64_t r0 = (int64_t)blockIdx.x * 128; r0 < g.m; r0 += (int64_t)gridDim.x * 128) {
+        const int64_t r = r0 + threadIdx.x;
+        if (r < g.m) {
+            const float *src = g.a + (g.idx ? (int64_t)g.idx[r] : r) * g.a_rs;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // my reads of the row's previous contents are done
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)k * 4u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(my_s), "l"(src), "r"((unsigned)k * 4u), "r"(bar) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+        unsigned ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        } while (!ok);
+        phase ^= 1u;
+        if (r >= g.m) continue;
+        float acc[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) acc[j] = 0.0f;
+        for (int q = 0; q < k; q += 4) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(my + q);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j4 = 0; j4 < NP; j4 += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bs + (q + i) * NP + j4);
+                    acc[j4] = fmaf(av[i], b4.x, acc[j4]); acc[j4 + 1] = fmaf(av[i], b4.y, acc[j4 + 1]);
+                    acc[j4 + 2] = fmaf(av[i], b4.z, acc[j4 + 2]); acc[j4 + 3] = fmaf(av[i], b4.w, acc[j4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) if (j < n) g.c[r * g.n + j] = gemm_epilogue(g, acc[j], r, j);
+    }
+}
+
+// SKINNY_K, n <= 128 (one column quad per lane): a WARP per row, lane l owns columns 4l .. 4l+3 with ITS quad of every row of B
+// in registers (no shared memory, no staging barrier); the row's k values are one coalesced load (lane j loads A[r][j]) handed
+// round by shuffles; four rows per warp in flight.  The item-per-thread kernel below measured 490 warp instructions per row
+// (a 64-bit division per item, 16 predicated k steps with their shared-memory loads): instruction-issue bound at 44 us for
+// 70 MB of traffic.
+__global__ void __launch_bounds__(MQ_NT, 2)
+gemm_skinny_k_warp_kernel(GemmArgs g) {
+    const int n = (int)g.n, k = (int)g.k, nq = n >> 2;
+    const int lane = threadIdx.x & 31;
+    const bool col = lane < nq;
+    float4 b[SKINNY_MAX];
+#pragma unroll
+    for (int j = 0; j < SKINNY_MAX; ++j) {
+        b[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (col && j < k) {
+            const float *bp = g.b + (int64_t)j * g.b_rs + (int64_t)(4 * lane) * g.b_cs;
+            b[j] = make_float4(__ldg(bp), __ldg(bp + g.b_cs), __ldg(bp + 2 * g.b_cs), __ldg(bp + 3 * g.b_cs));
+        }
+    }
+    float4 bias4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (col && g.epi == EPI_BIAS_ACT) bias4 = make_float4(g.bias[4 * lane], g.bias[4 * lane + 1], g.bias[4 * lane + 2], g.bias[4 * lane + 3]);
+    const int64_t warp = ((int64_t)blockIdx.x * MQ_NT + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * MQ_NT) >> 5;
+    for (int64_t r0 = warp * 4; r0 < g.m; r0 += nwarps * 4) {
+        float av[4];
+        float4 y4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + u;
+            av[u] = 0.0f;
+            y4[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (r < g.m) {
+                if (lane < k) av[u] = __ldg(g.a + (g.idx ? (int64_t)g.idx[r] : r) * g.a_rs + (int64_t)lane * g.a_cs);
+                if (col && g.epi == EPI_ACT_GRAD) y4[u] = __ldg(reinterpret_cast<const float4 *>(g.y + r * g.n) + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + u;
+            if (r >= g.m) break;                               // warp-uniform
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int j = 0; j < SKINNY_MAX; ++j) {
+                if (j < k) {                                   // warp-uniform
+                    const float a = __shfl_sync(0xffffffffu, av[u], j);
+                    acc.x = fmaf(a, b[j].x, acc.x); acc.y = fmaf(a, b[j].y, acc.y);
+                    acc.z = fmaf(a, b[j].z, acc.z); acc.w = fmaf(a, b[j].w, acc.w);
+                }
+            }
+            float4 o;
+            if (g.epi == EPI_ACT_GRAD) {
+                o.x = mq_act_grad(y4[u].x, acc.x, g.act, g.leak); o.y = mq_act_grad(y4[u].y, acc.y, g.act, g.leak);
+                o.z = mq_act_grad(y4[u].z, acc.z, g.act, g.leak); o.w = mq_act_grad(y4[u].w, acc.w, g.act, g.leak);
+            } else if (g.epi == EPI_BIAS_ACT) {
+                o.x = mq_act_apply(acc.x + bias4.x, g.act, g.leak); o.y = mq_act_apply(acc.y + bias4.y, g.act, g.leak);
+                o.z = mq_act_apply(acc.z + bias4.z, g.act, g.leak); o.w = mq_act_apply(acc.w + bias4.w, g.act, g.leak);
+            } else {
+                o = make_float4(g.alpha * acc.x, g.alpha * acc.y, g.alpha * acc.z, g.alpha * acc.w);
+            }
+            if (col) *(reinterpret_cast<float4 *>(g.c + r * g.n) + lane) = o;
+        }
+    }
+}
+
 // SKINNY_DW, both operands dense (A = x^T with x [k][md] contiguous, B [k][n] contiguous; md <= 128, md % 4 == 0, k % 4 == 0):
 // a block per slab of k; tiles of 64 batch rows of x and of B arrive in shared memory by bulk copies (TMA engine, two stages,
 // one issuing thread, completion counted on an mbarrier), thread (m, half) adds the rows of its parity into n sums in
@@ -487,6 +617,16 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
     const int sms = mq_sm_count();
     if (g.m >= 2048 && g.n <= SKINNY_MAX && g.k >= 32 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) && g.a_ones_row == 0) {
         if (g.a_cs == 1 && g.k <= 128 && (g.k & 3) == 0 && (g.a_rs & 3) == 0 && ((uintptr_t)g.a & 15) == 0) {
+            const int np = g.n <= 12 ? 12 : 16;
+            const int smem = (128 * SKN_PITCH + (int)g.k * np) * (int)sizeof(float);
+            auto kr = np == 12 ? gemm_skinny_n_rows_kernel<12> : gemm_skinny_n_rows_kernel<16>;
+            if (cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+                int64_t nbr = mq_ceil_div(g.m, 128);
+                if (nbr > (int64_t)sms * 3) nbr = (int64_t)sms * 3;          // three blocks (3 x 72 KB) per SM
+                MQ_LAUNCH(kr, (unsigned)nbr, 128, smem, stream, g);
+                return 1;
+            }
+            cudaGetLastError();
             int64_t nbw = mq_ceil_div(g.m, 16);               // 4 warps x 4 rows per block and pass
             if (nbw > (int64_t)sms * 16) nbw = (int64_t)sms * 16;
             MQ_LAUNCH(gemm_skinny_n_warp_kernel, (unsigned)nbw, 128, 0, stream, g);
@@ -499,6 +639,12 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
     }
     if (g.m >= 2048 && g.k <= SKINNY_MAX && g.n >= 32 && (g.n & 3) == 0 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) &&
         g.a_ones_row == 0 && (((uintptr_t)g.c | (uintptr_t)g.y) & 15) == 0) {
+        if (g.n <= 128) {
+            int64_t nbw = mq_ceil_div(g.m, 32);               // 8 warps x 4 rows per block and pass
+            if (nbw > (int64_t)sms * 2) nbw = (int64_t)sms * 2;
+            MQ_LAUNCH(gemm_skinny_k_warp_kernel, (unsigned)nbw, MQ_NT, 0, stream, g);
+            return 1;
+        }
         int64_t nb = mq_ceil_div(g.m * (g.n >> 2), MQ_NT);
         if (nb > (int64_t)sms * 16) nb = (int64_t)sms * 16;
         MQ_LAUNCH(gemm_skinny_k_kernel, (unsigned)nb, MQ_NT, 0, stream, g);
