@@ -1000,9 +1000,11 @@ def kernel_sweep(peaks):
     from mannequin2_b200 import _device as D, _lib as L
     lib, dev, out = L.lib(), D.device(), {}
 
-    def timeit(fn, reps=5, inner=1):
-        """Median device time of fn; inner > 1 enqueues that many calls per event pair (for sequences of SHORT launches,
-        where the host would otherwise leave bubbles between them) and returns the time per call."""
+    def timeit(fn, reps=5, inner=4):
+        """Median device time of fn per call, `inner` calls enqueued back to back per event pair: the kernels here take
+        0.1-0.4 ms, and a single launch between two events also measures the event records and the launch gap (3-8 us:
+        tanh forward read 0.099 ms alone against 0.0925 ms per launch in a train of them).  Arrays of 256 MB - 1 GB: every
+        launch streams from HBM, nothing survives in the 126 MB L2 from the previous one."""
         ts = []
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1050,7 +1052,7 @@ def kernel_sweep(peaks):
     with torch.cuda.graph(graph):                         # host does not leave bubbles between them
         for _i in range(4):
             nrm()
-    ms = timeit(graph.replay) / 4
+    ms = timeit(graph.replay, inner=1) / 4
     del graph
     # 8 B read (one statistics pass + the apply pass) + 4 B write per element
     out["normalize_update_apply_64Mi"] = dict(bytes_per_elem=12, ms=ms, gbs=12.0 * n / ms / 1e6,
@@ -1079,7 +1081,7 @@ def kernel_sweep(peaks):
     for tc, key in ((3, "affine_4096x784x400_fwd_dx_dw_tcgen05_exact"), (0x82, "affine_4096x784x400_fwd_dx_dw_tcgen05_fp16x2"),
                     (2, "affine_4096x784x400_fwd_dx_dw_tcgen05_bf16x2"),
                     (1, "affine_4096x784x400_fwd_dx_dw_tcgen05_bf16"), (L.TC_OFF, "affine_4096x784x400_fwd_dx_dw_ffma")):
-        ms = timeit(lambda: three(tc), reps=8)
+        ms = timeit(lambda: three(tc), reps=8, inner=1)
         out[key] = dict(flop=flops, ms=ms, fp32_tflops=flops / ms / 1e9,
                         frac_of_bf16_peak=flops / ms / 1e9 / peaks["bf16"],
                         issued_bf16_tflops=(pairs[tc] * flops / ms / 1e9) if tc in pairs else None,
@@ -1091,12 +1093,12 @@ def kernel_sweep(peaks):
     gws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
     for tc, name in ((3, "exact"), (0x82, "fp16x2"), (2, "bf16x2"), (1, "bf16")):
         ms = timeit(lambda: D.call("mq_gemm_ex", D.ptr(x), kin, 1, D.ptr(w), nout, 1, D.ptr(y), bsz, nout, kin, 1.0, tc, D.ptr(gws),
-                                   wsb, D.stream()), reps=8)
+                                   wsb, D.stream()), reps=8, inner=1)
         fl = 2.0 * bsz * kin * nout
         out["gemm_4096x784x400_%s" % name] = dict(ms=ms, fp32_tflops=fl / ms / 1e9, frac_of_bf16_peak=fl / ms / 1e9 / peaks["bf16"],
                                                   issued_bf16_tflops=pairs[tc] * fl / ms / 1e9)
         ms = timeit(lambda: D.call("mq_gemm_ex", D.ptr(xa), big, 1, D.ptr(xb), big, 1, D.ptr(xc), big, big, big, 1.0, tc, D.ptr(gws2),
-                                   wsb2, D.stream()), reps=5)
+                                   wsb2, D.stream()), reps=5, inner=1)
         fl = 2.0 * big ** 3
         out["gemm_4096cubed_%s" % name] = dict(ms=ms, fp32_tflops=fl / ms / 1e9, frac_of_bf16_peak=fl / ms / 1e9 / peaks["bf16"],
                                                issued_bf16_tflops=pairs[tc] * fl / ms / 1e9,
