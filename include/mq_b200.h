@@ -104,6 +104,10 @@ typedef struct mq_head {
 #define MQ_TC_FORCE       0x10  /* use the tensor-core kernel whenever the net fits (default: batch >= 8192) */
 #define MQ_TC_OFF         0x20  /* never use it (FFMA kernels)                                                */
 #define MQ_TC_NOPIPE      0x40  /* developer aid (A/B measurements): no K-chunk pipelining between layers          */
+#define MQ_TC_KEEP_X      0x100 /* mq_mlp_forward_tc / mq_mlp_backward_tc: the forward pass leaves the operand planes of the
+                                 * gathered input batch in the workspace and the backward pass of the SAME step (same ws, x,
+                                 * row_idx, batch and mode, no other call on ws in between) reads them for dW_0 instead of
+                                 * packing x^T again.  Ignored when layer 0 does not run on the tensor-core GEMM.           */
 /* When row_idx != NULL, x and every head array are indexed by row_idx[i] (they
  * are whole-rollout arrays, mannequin/_trajectory.py:79-86 fused into the load);
  * otherwise by the minibatch position i. */

@@ -36,6 +36,7 @@ class MqHead(ctypes.Structure):
 
 TC_FORCE, TC_OFF = 0x10, 0x20          # MQ_TC_* flags; the low two bits select the bf16 planes (0 = 3 = exact)
 TC_FP16 = 0x80                         # MQ_TC_FP16: with two planes, fp16 planes with the low one scaled by 2^11
+TC_KEEP_X = 0x100                      # MQ_TC_KEEP_X: layered MLP forward leaves the planes of x for dW_0 of the same step
 TC_MODE_BITS = 0x83
 TC_MODES = {"exact": 3, "bf16x3": 3, "fp16x2": 2 | TC_FP16, "bf16x2": 2, "bf16": 1}
 

@@ -809,9 +809,33 @@ static int64_t mlp_gemm_ws(const mq_net_t *net, int64_t batch) {
 }
 
 // [gradient buffers: nbuf x batch x max width floats][workspace of the dW products][workspace of the forward / dX products]
-extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
+static int64_t mlp_scratch_bytes(const mq_net_t *net, int64_t batch) {
     const int64_t nbuf = net->n_layers > 2 ? net->n_layers : 2;     // one gradient buffer per layer (overlapped backward)
     return mq_round_up(nbuf * batch * net_max_width(net) * (int64_t)sizeof(float), 1024) + 2 * mlp_gemm_ws(net, batch) + 256;
+}
+// MQ_TC_KEEP_X: the operand planes of the gathered input batch (+ a column of ones), packed by the forward pass and read
+// again by dW_0 = x^T g of the backward pass: [3 planes at most][batch padded to 128][(in + 1) padded to 128] 16-bit words
+static int64_t mlp_xplanes_rows(int64_t batch) { return mq_round_up(batch, 128); }
+static int64_t mlp_xplanes_pitch(const mq_net_t *net) { return mq_round_up((int64_t)net->in[0] + 1, 128); }
+static int64_t mlp_xplanes_bytes(const mq_net_t *net, int64_t batch) {
+    return mq_round_up(3 * mlp_xplanes_rows(batch) * mlp_xplanes_pitch(net) * 2, 1024) + 1024;
+}
+static void *mlp_xplanes_ptr(const mq_net_t *net, int64_t batch, void *ws) {
+    return (void *)(((uintptr_t)ws + (uintptr_t)mlp_scratch_bytes(net, batch) + 1023) & ~(uintptr_t)1023);
+}
+// the forward product of layer 0 takes the tensor-core path (and, with MQ_TC_KEEP_X, leaves the planes of x behind)
+static bool mlp_keeps_x(const mq_net_t *net, int64_t batch, int32_t tc, void *ws) {
+    if (!ws || !(tc & MQ_TC_KEEP_X)) return false;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.m = batch; g.n = net->out[0]; g.k = net->in[0];
+    return gemm_tc_wanted(g, tc);
+}
+
+// [gradient buffers: nbuf x batch x max width floats][workspace of the dW products][workspace of the forward / dX products]
+// [planes of the input batch, MQ_TC_KEEP_X]
+extern "C" int64_t mq_mlp_ws_bytes(const mq_net_t *net, int64_t batch) {
+    return mlp_scratch_bytes(net, batch) + mlp_xplanes_bytes(net, batch);
 }
 
 extern "C" int mq_mlp_forward(const mq_net_t *net, const float *theta, const float *x,
@@ -846,6 +870,22 @@ extern "C" int mq_mlp_forward_tc(const mq_net_t *net, const float *theta, const 
         g.c = out; g.m = batch; g.n = net->out[l]; g.k = net->in[l];
         g.alpha = 1.0f; g.epi = EPI_BIAS_ACT; g.act = net->act[l]; g.leak = net->leak[l];
         g.bias = theta + net->b_off[l];
+#ifndef MQ_EMU
+        if (l == 0 && ws && ws_bytes >= mq_mlp_ws_bytes(net, batch) && mlp_keeps_x(net, batch, tc, ws)) {
+            // pack the gathered batch ONCE per step: this product reads the planes K-major, dW_0 of the backward pass MN-major
+            const int planes = (tc & MQ_TC_PLANES_MASK) ? (tc & MQ_TC_PLANES_MASK) : 3;
+            GmPackJob jb;
+            memset(&jb, 0, sizeof(jb));
+            jb.base = x; jb.rs = net->in[0]; jb.cs = 1; jb.idx = row_idx; jb.idx_on_k = 0;
+            jb.rows = batch; jb.k = (int64_t)net->in[0] + 1; jb.ones_col = net->in[0];
+            jb.rows_pad = jb.rows_cover = mlp_xplanes_rows(batch);
+            jb.k_pad = jb.k_cover = mlp_xplanes_pitch(net);
+            jb.out = mlp_xplanes_ptr(net, batch, ws);
+            rc = mq_gemm_tma_pack_multi(&jb, 1, planes | (tc & MQ_TC_FP16), stream);
+            if (rc == MQ_OK) { g.a_planes = jb.out; g.a_planes_rows_pad = jb.rows_pad; g.a_planes_pitch = jb.k_pad; g.a_planes_mn = 0; }
+            else if (rc != MQ_ERR_UNSUPPORTED) return rc;
+        }
+#endif
         rc = gemm_run(g, ws, ws ? ws_bytes : 0, tc, stream, "mq_mlp_forward");
         if (rc != MQ_OK) return rc;
         inp = out;
@@ -929,6 +969,10 @@ extern "C" int mq_mlp_backward_tc(const mq_net_t *net, const float *theta, const
         // into b's slot behind W
         const bool fuse_bias = net->b_off[l] == net->w_off[l] + net->in[l] * net->out[l];
         if (fuse_bias) { g.m = net->in[l] + 1; g.a_ones_row = net->in[l]; }
+        if (l == 0 && mlp_keeps_x(net, batch, tc, ws)) {     // the forward pass of this step left the planes of x (+ ones) behind
+            g.a_planes = mlp_xplanes_ptr(net, batch, ws); g.a_planes_rows_pad = mlp_xplanes_rows(batch);
+            g.a_planes_pitch = mlp_xplanes_pitch(net); g.a_planes_mn = 1;
+        }
         rc = gemm_run(g, split_ws, split_bytes, tc, w_stream, "mq_mlp_backward(dW)");
         if (rc != MQ_OK) return rc;
         if (!fuse_bias) {

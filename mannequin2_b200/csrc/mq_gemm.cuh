@@ -21,6 +21,12 @@ struct GemmArgs {
     const float *y;          // EPI_ACT_GRAD, [M,N] row-major
     int64_t a_ones_row;      // > 0: rows m >= a_ones_row of A read as 1.0 (dW = x^T g with the bias gradient 1^T g as
                              // one more output row: W and b are adjacent in the flat parameter vector).
+    // Operand planes of A that already exist (tensor-core path only; every other path reads `a`): the image
+    // [plane][a_planes_rows_pad][a_planes_pitch] of the SOURCE matrix of A in the mode of this call, read K-major
+    // (a_planes_mn = 0: rows = m, columns = k) or MN-major (a_planes_mn = 1: rows = k, columns = m).  The layered MLP packs its
+    // gathered minibatch once per step (with a column of ones behind the last feature) and feeds it to the forward product
+    // K-major and to dW = x^T g MN-major.
+    const void *a_planes; int64_t a_planes_rows_pad, a_planes_pitch; int a_planes_mn;
 };
 
 // Optional second outputs of the tcgen05 GEMM (mq_gemm_tma.cu): the epilogue's values written ALSO as operand planes,

@@ -624,9 +624,36 @@ int mq_gemm_tma_launch(const GemmArgs &g, int mode, int64_t splits, void *pack, 
     if (g.m >= (1LL << 31) - 256 || g.n >= (1LL << 31) - 256 || g.k >= (1LL << 31) - 256) return MQ_ERR_UNSUPPORTED;
     if (!gm_encoder()) return MQ_ERR_UNSUPPORTED;
     int64_t a_rows_pad = mq_round_up(g.m, 128), b_rows_pad = mq_round_up(g.n, 128);
-    const int64_t k_pad = mq_round_up(g.k, GM_BK);
+    int64_t k_pad = mq_round_up(g.k, GM_BK);
     unsigned char *pa = (unsigned char *)(((uintptr_t)pack + 1023) & ~(uintptr_t)1023);
     unsigned char *pb = pa + mq_round_up(gm_pack_bytes(planes, g.m, g.k), 1024);
+    if (g.a_planes) {
+        // A is already packed (GemmArgs::a_planes): only B is packed here, at the start of the workspace (with the row length
+        // of A's image when both are K-major: one tensor-map geometry per product)
+        const bool mn = g.a_planes_mn != 0;
+        MQ_REQUIRE(((uintptr_t)g.a_planes & 127) == 0 && g.a_planes_rows_pad % 128 == 0 && g.a_planes_pitch % 128 == 0 &&
+                   (mn ? (g.a_planes_rows_pad >= g.k && g.a_planes_pitch >= g.m) : (g.a_planes_rows_pad >= g.m && g.a_planes_pitch >= k_pad)),
+                   MQ_ERR_SHAPE, "mq_gemm_tma: geometry of the pre-packed operand");
+        const int b_mn0 = g.b_cs == 1 && g.b_rs != 1;
+        if (!mn) k_pad = g.a_planes_pitch;
+        GmPackJob jb;
+        int64_t b_mn_pad0 = 0;
+        if (b_mn0) {
+            jb = gm_whole_job(g.b, g.b_rs, 1, nullptr, 0, g.k, g.n, 0, pa);
+            b_mn_pad0 = jb.k_pad = jb.k_cover = mq_round_up(g.n, 128);
+            b_rows_pad = jb.rows_pad;
+        } else {
+            jb = gm_whole_job(g.b, g.b_cs, g.b_rs, nullptr, 0, g.n, g.k, 0, pa);
+            jb.k_pad = k_pad;                                  // (columns beyond k_cover are never read: chunks end at k_cover)
+            if ((int64_t)planes * jb.rows_pad * jb.k_pad * 2 > mq_gemm_tma_pack_bytes(g.m, g.n, g.k, planes) - 1024) return MQ_ERR_UNSUPPORTED;
+        }
+        int rc0 = mq_gemm_tma_pack_multi(&jb, 1, mode, stream);
+        if (rc0 != MQ_OK) return rc0;
+        GmEmit em0;
+        memset(&em0, 0, sizeof(em0));
+        return mq_gemm_tma_packed_mn(g.a_planes, g.a_planes_rows_pad, mn ? 1 : 0, mn ? g.a_planes_pitch : 0, pa, b_rows_pad, b_mn0, b_mn_pad0,
+                                     k_pad, g, em0, mode, splits, stream);
+    }
     // A(m, k) = a[row(m) * a_rs + k * a_cs]; B as rows n with K contiguous: B^T(n, k) = b[k * b_rs + n * b_cs]
     // An operand whose M (N) axis is the unit-stride axis of its source (x^T and g of dW = x^T g, W of y = x W) is packed
     // in the SOURCE orientation -- the plain, fully coalesced form: planes [k][m] -- and fed to the tensor pipe MN-major,

@@ -30,7 +30,8 @@ class MLPTrainer(object):
         # gemm_mode: operand format of the layers that run on the tcgen05 GEMM (large batches).  "fp16x2" meets the same fp32
         # bar as "exact" (three bf16 planes) in half the tensor work and 2/3 of the packed bytes; its range precondition
         # (|operand| < 65504) holds for images, LReLU activations of a normed-column net and their batch-mean gradients.
-        self.tc = _lib.TC_MODES[gemm_mode]
+        # (+ MQ_TC_KEEP_X: a step's forward and backward pass share `ws`, so the gathered minibatch is packed once per step)
+        self.tc = _lib.TC_MODES[gemm_mode] | _lib.TC_KEEP_X
         self.net = _lib.make_net(n_in, list(widths), list(acts), leak=leak)
         if params is None:
             params = init_mlp(n_in, list(widths), 0.1)                # mlp.py:24-27 (init=0.1 head)

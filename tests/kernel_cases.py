@@ -1221,7 +1221,12 @@ def case_gemm_tc(B):
     # (the third configuration: per-call fp16x2 operands through mq_mlp_forward_tc / mq_mlp_backward_tc, and a batch at which
     # the narrow output layer takes the three skinny-product kernels of mq_gemm.cu)
     for n_in, widths, acts, batch, n_src, tc in ((784, [128, 128, 10], [2, 2, 0], 2048, 3000, None), (784, [400, 40], [1, 0], 4096, 4096, None),
-                                                 (784, [128, 128, 10], [2, 2, 0], 8192, 3000, L.TC_MODES["fp16x2"])):
+                                                 (784, [128, 128, 10], [2, 2, 0], 8192, 3000, L.TC_MODES["fp16x2"]),
+                                                 # MQ_TC_KEEP_X: the forward pass's planes of x feed dW_0 (MN-major), ragged batch
+                                                 (784, [128, 128, 10], [2, 2, 0], 8200, 3000, L.TC_MODES["fp16x2"] | L.TC_KEEP_X),
+                                                 # (Tanh: a draw with a hidden pre-activation within rounding of LReLU's kink makes
+                                                 #  either slope a correct fp32 result and the comparison meaningless)
+                                                 (784, [128, 10], [1, 0], 8192, 3000, L.TC_MODES["exact"] | L.TC_KEEP_X)):
         spec, theta, x = mlp_case(rs, n_in, widths, acts, n_src)
         idx = rs.randint(n_src, size=batch).astype(np.int32)
         net = net_of(spec)
