@@ -463,14 +463,15 @@ gemm_skinny_n_rows_kernel(GemmArgs g) {
 // round by shuffles; four rows per warp in flight.  The item-per-thread kernel below measured 490 warp instructions per row
 // (a 64-bit division per item, 16 predicated k steps with their shared-memory loads): instruction-issue bound at 44 us for
 // 70 MB of traffic.
+template <int KP, int U>                                      // k <= KP rows of B in registers, U rows of A per warp in flight
 __global__ void __launch_bounds__(MQ_NT, 2)
 gemm_skinny_k_warp_kernel(GemmArgs g) {
     const int n = (int)g.n, k = (int)g.k, nq = n >> 2;
     const int lane = threadIdx.x & 31;
     const bool col = lane < nq;
-    float4 b[SKINNY_MAX];
+    float4 b[KP];
 #pragma unroll
-    for (int j = 0; j < SKINNY_MAX; ++j) {
+    for (int j = 0; j < KP; ++j) {
         b[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (col && j < k) {
             const float *bp = g.b + (int64_t)j * g.b_rs + (int64_t)(4 * lane) * g.b_cs;
@@ -480,11 +481,11 @@ gemm_skinny_k_warp_kernel(GemmArgs g) {
     float4 bias4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (col && g.epi == EPI_BIAS_ACT) bias4 = make_float4(g.bias[4 * lane], g.bias[4 * lane + 1], g.bias[4 * lane + 2], g.bias[4 * lane + 3]);
     const int64_t warp = ((int64_t)blockIdx.x * MQ_NT + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * MQ_NT) >> 5;
-    for (int64_t r0 = warp * 4; r0 < g.m; r0 += nwarps * 4) {
-        float av[4];
-        float4 y4[4];
+    for (int64_t r0 = warp * U; r0 < g.m; r0 += nwarps * U) {
+        float av[U];
+        float4 y4[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t r = r0 + u;
             av[u] = 0.0f;
             y4[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -494,12 +495,12 @@ gemm_skinny_k_warp_kernel(GemmArgs g) {
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t r = r0 + u;
             if (r >= g.m) break;                               // warp-uniform
             float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-            for (int j = 0; j < SKINNY_MAX; ++j) {
+            for (int j = 0; j < KP; ++j) {
                 if (j < k) {                                   // warp-uniform
                     const float a = __shfl_sync(0xffffffffu, av[u], j);
                     acc.x = fmaf(a, b[j].x, acc.x); acc.y = fmaf(a, b[j].y, acc.y);
@@ -528,7 +529,8 @@ gemm_skinny_k_warp_kernel(GemmArgs g) {
 // is the column sum of B, kept by the m = 0 threads.
 #define SKDW_TILE 64
 #define SKDW_STAGE (SKDW_TILE * 128 * 4 + SKDW_TILE * SKINNY_MAX * 4)
-__global__ void __launch_bounds__(MQ_NT)
+template <int NP>                                             // n <= NP sums per thread (columns n .. NP-1 read neighbouring words of
+__global__ void __launch_bounds__(MQ_NT)                      // the stage and are never stored: no predicate in the inner loop)
 gemm_skinny_dw_tma_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char sk_smem[];
     __shared__ __align__(8) uint64_t full[2];
@@ -558,9 +560,9 @@ gemm_skinny_dw_tma_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ pa
         if (ntiles > 1) issue(1);
     }
     __syncthreads();
-    float acc[SKINNY_MAX], ones[SKINNY_MAX];
+    float acc[NP], ones = 0.0f;                              // ones: column threadIdx.x of B summed over the slab (threads < n)
 #pragma unroll
-    for (int j = 0; j < SKINNY_MAX; ++j) { acc[j] = 0.0f; ones[j] = 0.0f; }
+    for (int j = 0; j < NP; ++j) acc[j] = 0.0f;
     for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         unsigned ok;
@@ -572,17 +574,17 @@ gemm_skinny_dw_tma_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ pa
         const int rows = (int)(k1 - kb < SKDW_TILE ? k1 - kb : SKDW_TILE);
         const float *xa = reinterpret_cast<const float *>(sk_smem + (size_t)s * SKDW_STAGE);
         const float *gb = xa + SKDW_TILE * 128;
+        if (m < md) {
 #pragma unroll 4
-        for (int r = half; r < rows; r += 2) {
-            const float a = m < md ? xa[r * md + m] : 0.0f;
+            for (int r = half; r < rows; r += 2) {
+                const float a = xa[r * md + m];
+                const float *gr = gb + r * n;
 #pragma unroll
-            for (int j = 0; j < SKINNY_MAX; ++j)
-                if (j < n) {
-                    const float gv = gb[r * n + j];
-                    acc[j] = fmaf(a, gv, acc[j]);
-                    if (m == 0) ones[j] += gv;
-                }
+                for (int j = 0; j < NP; ++j) acc[j] = fmaf(a, gr[j], acc[j]);
+            }
         }
+        if ((int)threadIdx.x < n)
+            for (int r = 0; r < rows; ++r) ones += gb[r * n + threadIdx.x];
         __syncthreads();                                   // every read of stage s is done
         if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
     }
@@ -590,20 +592,15 @@ gemm_skinny_dw_tma_kernel(GemmArgs g, int64_t k_per_slab, float *__restrict__ pa
     float *red = reinterpret_cast<float *>(sk_smem);
     if (half == 1) {
 #pragma unroll
-        for (int j = 0; j < SKINNY_MAX; ++j) {
-            red[m * SKINNY_MAX + j] = acc[j];
-            if (m == 0) red[128 * SKINNY_MAX + j] = ones[j];
-        }
+        for (int j = 0; j < NP; ++j) red[m * SKINNY_MAX + j] = acc[j];
     }
     __syncthreads();
     if (half == 0) {
         float *dst = partial + (int64_t)blockIdx.x * g.m * n;
 #pragma unroll
-        for (int j = 0; j < SKINNY_MAX; ++j)
-            if (j < n) {
-                if (m < md) dst[(int64_t)m * n + j] = acc[j] + red[m * SKINNY_MAX + j];
-                if (m == 0 && g.a_ones_row > 0) dst[g.a_ones_row * n + j] = ones[j] + red[128 * SKINNY_MAX + j];
-            }
+        for (int j = 0; j < NP; ++j)
+            if (j < n && m < md) dst[(int64_t)m * n + j] = acc[j] + red[m * SKINNY_MAX + j];
+        if ((int)threadIdx.x < n && g.a_ones_row > 0) dst[g.a_ones_row * n + threadIdx.x] = ones;
     }
 }
 #endif
@@ -640,9 +637,10 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
     if (g.m >= 2048 && g.k <= SKINNY_MAX && g.n >= 32 && (g.n & 3) == 0 && g.k * g.n <= SKINNY_SMEM_FLOATS && !(g.idx && g.idx_on_k) &&
         g.a_ones_row == 0 && (((uintptr_t)g.c | (uintptr_t)g.y) & 15) == 0) {
         if (g.n <= 128) {
-            int64_t nbw = mq_ceil_div(g.m, 32);               // 8 warps x 4 rows per block and pass
+            int64_t nbw = mq_ceil_div(g.m, 64);               // 8 warps x 8 (4) rows per block and pass
             if (nbw > (int64_t)sms * 2) nbw = (int64_t)sms * 2;
-            MQ_LAUNCH(gemm_skinny_k_warp_kernel, (unsigned)nbw, MQ_NT, 0, stream, g);
+            if (g.k <= 10) { auto kk = gemm_skinny_k_warp_kernel<10, 8>; MQ_LAUNCH(kk, (unsigned)nbw, MQ_NT, 0, stream, g); }
+            else { auto kk = gemm_skinny_k_warp_kernel<SKINNY_MAX, 4>; MQ_LAUNCH(kk, (unsigned)nbw, MQ_NT, 0, stream, g); }
             return 1;
         }
         int64_t nb = mq_ceil_div(g.m * (g.n >> 2), MQ_NT);
@@ -658,9 +656,10 @@ static int gemm_skinny(const GemmArgs &g, void *ws, int64_t ws_bytes, void *stre
             if (sl > g.k / 64) sl = g.k / 64;
             const int64_t per4 = mq_round_up(mq_ceil_div(g.k, sl), 8);
             sl = mq_ceil_div(g.k, per4);
+            auto kd = g.n <= 10 ? gemm_skinny_dw_tma_kernel<10> : gemm_skinny_dw_tma_kernel<SKINNY_MAX>;
             if (sl * g.m * g.n * (int64_t)sizeof(float) <= ws_bytes &&
-                cudaFuncSetAttribute(gemm_skinny_dw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SKDW_STAGE) == cudaSuccess) {
-                MQ_LAUNCH(gemm_skinny_dw_tma_kernel, (unsigned)sl, MQ_NT, 2 * SKDW_STAGE, stream, g, per4, (float *)ws);
+                cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SKDW_STAGE) == cudaSuccess) {
+                MQ_LAUNCH(kd, (unsigned)sl, MQ_NT, 2 * SKDW_STAGE, stream, g, per4, (float *)ws);
                 const int64_t tot = g.m * g.n;
                 MQ_LAUNCH(gemm_skinny_finish_kernel, (unsigned)mq_ceil_div(tot * 32, MQ_NT), MQ_NT, 0, stream, (const float *)ws, (int)sl, tot, g.alpha, g.c);
                 return 1;
