@@ -47,7 +47,7 @@ if __name__ == "__main__":
     small = {"case_scan": dict(sizes=(1, 2, 700, 2048, 2049, 5000)),
              "case_ppo_reference_replay": dict(n_steps=20)}
     # tensor-core (tcgen05) and peer-memory cases have no host emulation: they are checked on a B200 only
-    gpu_only = {"case_gemm_tc", "case_tc_paths", "case_reduce_step"}
+    gpu_only = {"case_gemm_tc", "case_tc_paths", "case_tc_modes", "case_reduce_step"}
     small["case_discrete"] = dict(batches=(64, 300))
     small["case_entropy"] = dict(batches=(64, 300))
     for fn in K.ALL_CASES:
