@@ -27,6 +27,27 @@ def test_header_and_binding_agree(lib):
         assert hasattr(lib, name), name
 
 
+def test_flag_constants_match_header():
+    """The MQ_TC_* flags the host layer passes are the header's (a drifted bit would silently select another operand format)."""
+    header = open(os.path.join(ROOT, "include", "mq_b200.h")).read()
+    flags = {k: int(v, 0) for k, v in re.findall(r"#define\s+(MQ_TC_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)", header)}
+    assert flags["MQ_TC_FORCE"] == _lib.TC_FORCE and flags["MQ_TC_OFF"] == _lib.TC_OFF
+    assert flags["MQ_TC_FP16"] == _lib.TC_FP16 and flags["MQ_TC_KEEP_X"] == _lib.TC_KEEP_X
+    assert _lib.TC_MODE_BITS == flags["MQ_TC_PLANES_MASK"] | flags["MQ_TC_FP16"]
+    assert _lib.TC_MODES["fp16x2"] == 2 | flags["MQ_TC_FP16"] and _lib.TC_MODES["exact"] == 3
+    bits = [flags[k] for k in ("MQ_TC_FORCE", "MQ_TC_OFF", "MQ_TC_NOPIPE", "MQ_TC_FP16", "MQ_TC_KEEP_X")]
+    assert len(set(bits)) == len(bits) and all(b & flags["MQ_TC_PLANES_MASK"] == 0 and b & (b - 1) == 0 for b in bits)
+
+
+def test_layered_mlp_workspace_holds_the_input_planes(lib):
+    """mq_mlp_ws_bytes includes the region MQ_TC_KEEP_X keeps the operand planes of the input batch in
+    (3 planes x batch padded to 128 x (784 + 1 ones column) padded to 128 16-bit words)."""
+    net = _lib.make_net(784, [128, 128, 10], [2, 2, 0])
+    for batch in (128, 8200, 65536):
+        rows = (batch + 127) // 128 * 128
+        assert lib.mq_mlp_ws_bytes(ctypes.byref(net), batch) >= 3 * rows * 896 * 2
+
+
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MqNet) == 4 * 5 + 4 * 8 * 6
     assert ctypes.sizeof(_lib.MqHead) == 16 + 4 * 8 + 8 + 4 + 4 + 8
