@@ -204,7 +204,12 @@ struct GmCfg {
 // column tiles fastest).  The three roles walk the same tile sequence; stage / accumulator-set indices and barrier
 // parities follow RUNNING chunk and block counters, so the producer and the issuer run into the next tile while the owners
 // still write the previous tile's C (the owners hold it in registers; its accumulator set was released when they read it).
-template <int P, int F, bool SPLIT>
+// YPRE: the act' epilogue fetches its saved activations in groups of 8 rows, one group AHEAD (up to 16 rows of a warp in
+// flight) instead of 4 rows at the top of their own iteration.  Chosen by the launcher for SHORT contractions (K <= 256), where
+// a tile is all epilogue and eight exposed round trips per half made the 65,536 x 128 x 128 dX product of the MLP take 70 us
+// against 37 us with the bias epilogue; as the only form it cost every other product registers and code (the fused VAE step
+// 0.304 -> 0.311 ms), hence a separate instantiation.
+template <int P, int F, bool SPLIT, bool YPRE = false>
 __global__ void __launch_bounds__(GM_NT, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g, GmEmit em,
                 int a_rows_pad, int b_rows_pad, int n_splits, int a_mn, int b_mn) {
@@ -379,20 +384,38 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // fetched BEFORE its rows are processed -- with eight owner warps per SM a load inside the row loop is an
                 // exposed L2 round trip per row
                 const float bias_n = (!SPLIT && g.epi == EPI_BIAS_ACT && col_ok) ? __ldg(g.bias + gn) : 0.0f;
+                constexpr int RG = YPRE ? 8 : 4;
+                const bool want_y = !SPLIT && g.epi == EPI_ACT_GRAD;
+                float yn[RG];
+#pragma unroll
+                for (int i = 0; i < RG; ++i) yn[i] = 0.0f;
+                if (YPRE && want_y) {
+                    const float *yp = g.y + gm_base * g.n + gn;
+#pragma unroll
+                    for (int i = 0; i < RG; ++i) yn[i] = (col_ok && gm_base + i < g.m) ? __ldg(yp + i * g.n) : 0.0f;
+                }
 #pragma unroll 1
-                for (int r0 = 0; r0 < 32; r0 += 4) {
+                for (int r0 = 0; r0 < 32; r0 += RG) {
                     const int64_t gmr = gm_base + r0;
                     if (gmr >= g.m && !emit) break;
-                    float yv[4];
-                    if (!SPLIT && g.epi == EPI_ACT_GRAD) {
+                    float yv[RG];
+                    if (YPRE) {
+#pragma unroll
+                        for (int i = 0; i < RG; ++i) yv[i] = yn[i];
+                        if (want_y && r0 + RG < 32) {
+                            const float *yp = g.y + (gmr + RG) * g.n + gn;
+#pragma unroll
+                            for (int i = 0; i < RG; ++i) yn[i] = (col_ok && gmr + RG + i < g.m) ? __ldg(yp + i * g.n) : 0.0f;
+                        }
+                    } else if (want_y) {
                         const float *yp = g.y + gmr * g.n + gn;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) yv[i] = (col_ok && gmr + i < g.m) ? __ldg(yp + i * g.n) : 0.0f;
+                        for (int i = 0; i < RG; ++i) yv[i] = (col_ok && gmr + i < g.m) ? __ldg(yp + i * g.n) : 0.0f;
                     }
                     float *cp = SPLIT ? g.c + (z_ * g.m + gmr) * g.n + gn : (g.c ? g.c + gmr * ldc + gn : nullptr);
                     const int64_t cstep = SPLIT ? g.n : ldc;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < RG; ++i) {
                         const int r = r0 + i;
                         float v = 0.0f;
                         if (gmr + i < g.m && col_ok) {
@@ -594,11 +617,13 @@ int mq_gemm_tma_packed_mn(const void *pa, int64_t a_rows_pad, int a_mn, int64_t 
     static const bool one_tile = getenv("MQ_GEMM_ONE_TILE_PER_CTA") != nullptr;
     const unsigned grid = (unsigned)((one_tile || n_tiles < mq_sm_count()) ? n_tiles : mq_sm_count());
     cudaError_t e = cudaSuccess;
+    const bool ypre = splits <= 1 && g.epi == EPI_ACT_GRAD && g.k <= 256;      // short contraction with the act' epilogue
 #define GM_GO(P_, F_, SP_)                                                                                                 \
     do {                                                                                                                   \
-        e = cudaFuncSetAttribute(gemm_tma_kernel<P_, F_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM); \
+        auto kfn_ = (!SP_ && ypre) ? gemm_tma_kernel<P_, F_, false, true> : gemm_tma_kernel<P_, F_, SP_, false>;             \
+        e = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, GmCfg<P_>::SMEM);                      \
         if (e == cudaSuccess)                                                                                              \
-            e = mq_launch_pdl(gemm_tma_kernel<P_, F_, SP_>, dim3(grid), dim3(GM_NT), (size_t)GmCfg<P_>::SMEM, stream, map_a, map_b, g, em, \
+            e = mq_launch_pdl(kfn_, dim3(grid), dim3(GM_NT), (size_t)GmCfg<P_>::SMEM, stream, map_a, map_b, g, em, \
                               (int)a_rows_pad, (int)b_rows_pad, (int)(splits > 1 ? splits : 1), a_mn, b_mn);                    \
     } while (0)
 #define GM_GO_P(SP_)                                              \
